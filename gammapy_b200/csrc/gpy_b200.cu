@@ -1,0 +1,1163 @@
+// gpy_b200.cu -- host runtime + C ABI of libgpy_b200.so (see include/gpy_b200.h).
+//
+// The runtime plays the role of gammapy's MapEvaluator bookkeeping (datasets/evaluator.py:128-243,
+// 282-286, 465-481): per source it decides when the exposure cutout has to be re-centred, when the
+// spatial model has to be re-integrated and re-convolved with the PSF (cached otherwise), and packs
+// one launch of the fused fold + Cash kernel for all datasets and all parameter vectors of a call.
+// All integer geometry (Cutout2D slices, oversampling factors) is computed here in IEEE doubles with
+// the reference's operation order, because a different rounding shifts a cutout by one pixel.
+//
+// Reference citations are relative to /root/reference/gammapy.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/gpy_b200.h"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t err__ = (expr);                                                            \
+    if (err__ != cudaSuccess)                                                              \
+      return fail(GPY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), \
+                  __FILE__, __LINE__);                                                     \
+  } while (0)
+
+#define GPY_TRY(expr)          \
+  do {                         \
+    int rc__ = (expr);         \
+    if (rc__ != GPY_OK) return rc__; \
+  } while (0)
+
+constexpr double kDegH = 0.017453292519943295;
+constexpr double kCutoutMargin = 0.1;  // deg, datasets/evaluator.py:17
+constexpr int kMaxOversampling = 200;  // modeling/models/spatial.py:54
+constexpr int kSlotsPerSource = 6;     // cached (spatial params, cutout) -> PSF-convolved cube
+
+// ---------------------------------------------------------------------------------------------
+// host geometry: the integer rules of astropy Cutout2D / overlap_slices and gammapy WcsGeom.cutout
+// ---------------------------------------------------------------------------------------------
+struct GeomH {
+  int nx, ny;
+  double binsz, crval_lon, crpix_x, crpix_y;
+};
+
+struct Rect {
+  int x0 = 0, y0 = 0, cx = 0, cy = 0;
+  bool operator==(const Rect& o) const { return x0 == o.x0 && y0 == o.y0 && cx == o.cx && cy == o.cy; }
+};
+
+enum CutStatus { CUT_OK = 0, CUT_NO_OVERLAP = 1, CUT_VALUE_ERROR = 2 };
+
+double py_mod(double a, double b) {  // Python float %
+  double m = std::fmod(a, b);
+  if (m != 0.0 && ((b < 0) != (m < 0))) m += b;
+  return m;
+}
+
+void world_to_pix(const GeomH& g, double lon, double lat, double& px, double& py) {
+  // wcs_world2pix(lon, lat, 0): pix = img / cdelt + crpix - 1 (wcslib linx2p simple path)
+  double dlon = py_mod(lon - g.crval_lon + 180.0, 360.0) - 180.0;
+  px = dlon / (-g.binsz) + g.crpix_x - 1.0;
+  py = lat / g.binsz + g.crpix_y - 1.0;
+}
+
+double round_up_to_odd(double f) {  // utils/array.py:110
+  return std::floor(std::ceil(f) / 2.0) * 2.0 + 1.0;
+}
+
+// WcsGeom.cutout (maps/wcs/geom.py:886-930) -> parent slices, mode "trim"
+CutStatus cutout_rect(const GeomH& g, double lon, double lat, double width_deg, bool odd_npix, Rect& out) {
+  double width_npix = width_deg / g.binsz;
+  // np.clip(x, min_npix=1, None); NaN propagates
+  if (width_npix < 1.0) width_npix = 1.0;
+  if (odd_npix) width_npix = round_up_to_odd(width_npix);
+  double rounded = std::nearbyint(width_npix);  // np.round: half to even
+  if (!std::isfinite(rounded)) return CUT_VALUE_ERROR;  // int(nan) raises ValueError
+  long shape = (long)rounded;
+  double px, py;
+  world_to_pix(g, lon, lat, px, py);
+  if (!std::isfinite(px) || !std::isfinite(py)) return CUT_VALUE_ERROR;
+  const double pos[2] = {py, px};
+  const int large[2] = {g.ny, g.nx};
+  long emin[2], emax[2];
+  for (int a = 0; a < 2; ++a) {
+    emin[a] = (long)std::ceil(pos[a] - (double)shape / 2.0);
+    emax[a] = (long)std::ceil(pos[a] + (double)shape / 2.0);
+  }
+  for (int a = 0; a < 2; ++a)
+    if (emax[a] <= 0) return CUT_NO_OVERLAP;
+  for (int a = 0; a < 2; ++a)
+    if (emin[a] >= large[a]) return CUT_NO_OVERLAP;
+  long y0 = std::max(0L, emin[0]), y1 = std::min((long)large[0], emax[0]);
+  long x0 = std::max(0L, emin[1]), x1 = std::min((long)large[1], emax[1]);
+  out.x0 = (int)x0;
+  out.y0 = (int)y0;
+  out.cx = (int)(x1 - x0);
+  out.cy = (int)(y1 - y0);
+  if (out.cx <= 0 || out.cy <= 0) return CUT_NO_OVERLAP;
+  return CUT_OK;
+}
+
+GeomH sub_geom(const GeomH& g, const Rect& r) {  // Cutout2D.wcs: crpix -= origin
+  GeomH s = g;
+  s.nx = r.cx;
+  s.ny = r.cy;
+  s.crpix_x = g.crpix_x - r.x0;
+  s.crpix_y = g.crpix_y - r.y0;
+  return s;
+}
+
+double angular_separation_h(double lon1, double lat1, double lon2, double lat2) {
+  double sdlon = std::sin(lon2 - lon1), cdlon = std::cos(lon2 - lon1);
+  double slat1 = std::sin(lat1), slat2 = std::sin(lat2);
+  double clat1 = std::cos(lat1), clat2 = std::cos(lat2);
+  double num1 = clat2 * sdlon;
+  double num2 = clat1 * slat2 - slat1 * clat2 * cdlon;
+  double den = slat1 * slat2 + clat1 * clat2 * cdlon;
+  return std::atan2(std::hypot(num1, num2), den);
+}
+
+int n_spatial_params(int type) { return type == GPY_SPATIAL_POINT ? 2 : type == GPY_SPATIAL_GAUSS ? 5 : 6; }
+int n_spectral_params(int type) { return type == GPY_SPECTRAL_PL ? 3 : type == GPY_SPECTRAL_LP ? 4 : 5; }
+
+double evaluation_radius(int type, const double* sp) {  // spatial.py:573-579, 672-678, 941-947
+  if (type == GPY_SPATIAL_POINT) return 0.0;
+  if (type == GPY_SPATIAL_GAUSS) return 5 * sp[2];
+  return 1.1 * sp[2] * (1 + sp[5]);
+}
+
+double evaluation_bin_size_min(int type, const double* sp) {  // spatial.py:568-571, 667-670, 933-939
+  if (type == GPY_SPATIAL_POINT) return 0.0;
+  if (type == GPY_SPATIAL_GAUSS) return sp[2] / 3.0;
+  return sp[2] * (1 - sp[5]) / 10.0;
+}
+
+// DiskSpatialModel._evaluate_norm_factor (spatial.py:951-969).  The reference integrates with
+// scipy.integrate.quad; the integrand is smooth and pi-periodic, so a composite Gauss-Legendre rule
+// converges to double precision (checked against quad in tests/test_spatial_gpu.py).
+double disk_norm_factor(double r0, double e) {
+  double semi_minor = r0 * std::sqrt(1 - e * e);
+  double A = 1 / (std::sin(r0) * std::sin(r0));
+  double B = 1 / (std::sin(semi_minor) * std::sin(semi_minor));
+  double C = A - B;
+  auto fcn = [&](double x) {
+    double cs2 = std::cos(x) * std::cos(x);
+    return 1 - std::sqrt(1 - 1 / (B + C * cs2));
+  };
+  double integral;
+  if (e == 0) {
+    integral = M_PI * fcn(0.0);
+  } else {
+    // 8-point Gauss-Legendre on 64 panels
+    static const double xg[4] = {0.1834346424956498, 0.5255324099163290, 0.7966664774136267, 0.9602898564975363};
+    static const double wg[4] = {0.3626837833783620, 0.3137066458778873, 0.2223810344533745, 0.1012285362903763};
+    const int panels = 64;
+    double hpan = M_PI / panels, s = 0.0;
+    for (int p = 0; p < panels; ++p) {
+      double c = (p + 0.5) * hpan, hw = 0.5 * hpan;
+      for (int k = 0; k < 4; ++k) s += wg[k] * (fcn(c - hw * xg[k]) + fcn(c + hw * xg[k]));
+    }
+    integral = s * 0.5 * hpan;
+  }
+  return 1.0 / (2 * integral);
+}
+
+// ---------------------------------------------------------------------------------------------
+// runtime objects
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return GPY_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max(bytes, (size_t)256);
+    CUDA_TRY(cudaMalloc(&p, want));
+    cap = want;
+    return GPY_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Slot {  // one cached integrate_geom (+ PSF convolution) result
+  DevBuf w, conv;
+  Rect rect;
+  int x0a = 0, pitch = 0, planes = 0, f = 0;
+  std::vector<double> key;  // spatial parameter values
+  bool valid = false;
+  uint64_t stamp = 0;
+};
+
+struct Source {
+  gpy_source_desc desc;
+  bool initialised = false;  // MapEvaluator.exposure is not None
+  bool contributes = true;
+  Rect rect;                 // exposure cutout
+  double cached_lon = 0.0, cached_lat = 0.0;  // evaluator.py:93 _cached_position (radians)
+  std::vector<double> cached_spatial;         // _cached_parameter_values_spatial
+  bool has_cached_spatial = false;
+  Slot slots[kSlotsPerSource];
+  int last_f = 0;
+  int n_spatial_evals = 0;
+};
+
+}  // namespace
+
+struct gpy_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t launches = 0;
+  uint64_t stamp = 0;
+  void* pinned = nullptr;
+  size_t pinned_cap = 0;
+  cudaEvent_t h2d_done = nullptr;
+  bool h2d_pending = false;
+  DevBuf staging, flux, partials, stat, tiles, scratch_a, scratch_b, scratch_c;
+  std::vector<gpy_dataset*> tiles_for;  // dataset list the tile table was built for
+  std::vector<uint64_t> tiles_ver;
+  double* stat_pinned = nullptr;
+  size_t stat_pinned_cap = 0;
+  size_t fold_smem_set = 0, conv_smem_set = 0;
+  double log_trunc = 0.0;
+  int max_smem_optin = 0;
+};
+
+struct gpy_dataset {
+  gpy_context* ctx = nullptr;
+  GeomH geom;
+  int nT = 0, nR = 0, nRp = 0, n_groups = 1, n_nodes = 0, psf_k = 0;
+  uint64_t version = 0;
+  const float *exposure = nullptr, *background = nullptr, *counts = nullptr;
+  const uint8_t* mask = nullptr;
+  std::vector<uint8_t> mask_image;  // empty = all true
+  DevBuf d_edges, d_nodes, d_ecenter, d_edisp, d_band, d_omega, d_kflip, d_planes;
+  std::vector<gpy::ConvPlane> planes;
+  int max_h = 0, max_kw = 4;
+  bool has_psf = false, has_diag = false;
+  std::vector<Source> sources;
+  gpy_background_desc bkg{0, -1, -1, -1};
+};
+
+namespace {
+
+int ensure_pinned(gpy_context* c, size_t bytes) {
+  if (bytes <= c->pinned_cap) return GPY_OK;
+  if (c->pinned) cudaFreeHost(c->pinned);
+  c->pinned = nullptr;
+  c->pinned_cap = 0;
+  size_t want = std::max(bytes * 2, (size_t)1 << 16);
+  CUDA_TRY(cudaMallocHost(&c->pinned, want));
+  c->pinned_cap = want;
+  return GPY_OK;
+}
+
+int ensure_stat_pinned(gpy_context* c, size_t n) {
+  if (n <= c->stat_pinned_cap) return GPY_OK;
+  if (c->stat_pinned) cudaFreeHost(c->stat_pinned);
+  c->stat_pinned = nullptr;
+  c->stat_pinned_cap = 0;
+  size_t want = std::max(n * 2, (size_t)1024);
+  CUDA_TRY(cudaMallocHost((void**)&c->stat_pinned, want * sizeof(double)));
+  c->stat_pinned_cap = want;
+  return GPY_OK;
+}
+
+struct Packer {  // lays out the per-call descriptor block, uploaded with one cudaMemcpyAsync
+  std::vector<uint8_t> bytes;
+  size_t add(const void* src, size_t n, size_t align = 16) {
+    size_t off = (bytes.size() + align - 1) / align * align;
+    bytes.resize(off + n);
+    if (n) std::memcpy(bytes.data() + off, src, n);
+    return off;
+  }
+};
+
+int upload_to(DevBuf& buf, const void* src, size_t bytes, cudaStream_t s) {
+  GPY_TRY(buf.reserve(bytes));
+  if (bytes) CUDA_TRY(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, s));
+  return GPY_OK;
+}
+
+gpy::WcsDev wcs_of(const GeomH& g) { return gpy::WcsDev{g.crval_lon, g.binsz, g.crpix_x, g.crpix_y}; }
+
+// ---- K1 + K2 into a slot ---------------------------------------------------------------------
+// SpatialModel.integrate_geom on the evaluator geometry `rect` of dataset geometry `pg`, then
+// WcsNDMap.convolve.  `omega` is the parent solid-angle image (device).
+int compute_spatial(gpy_context* c, const GeomH& pg, const double* omega, const Rect& rect, int type,
+                    const double* sp, float* w_out, int pitch, int xpad, int* f_out) {
+  GeomH eg = sub_geom(pg, rect);
+  gpy::SpatialJob j;
+  std::memset(&j, 0, sizeof(j));
+  j.type = type;
+  j.ecx = rect.cx;
+  j.ecy = rect.cy;
+  j.pitch = pitch;
+  j.xpad = xpad;
+  j.ex0 = rect.x0;
+  j.ey0 = rect.y0;
+  j.parent_nx = pg.nx;
+  j.wcs_e = wcs_of(eg);
+  j.solid_angle = omega;
+  j.out = w_out;
+  j.lon0 = sp[0] * kDegH;
+  j.lat0 = sp[1] * kDegH;
+  int f = 1;
+  if (type == GPY_SPATIAL_POINT) {
+    world_to_pix(eg, sp[0], sp[1], j.px0, j.py0);
+  } else {
+    const double pix_scale = pg.binsz;
+    const double radius = evaluation_radius(type, sp);
+    bool have_f = false;
+    Rect inner;
+    // try: wcs_geom.cutout(position, 2 * max(r_eval, pix_scale)) (spatial.py:255-264)
+    double width = 2 * (radius > pix_scale || std::isnan(radius) ? radius : pix_scale);  // np.maximum
+    CutStatus cs = cutout_rect(eg, sp[0], sp[1], width, false, inner);
+    if (cs != CUT_OK) {
+      f = 1;
+      have_f = true;
+    }
+    if (!have_f) {
+      double res = evaluation_bin_size_min(type, sp);
+      if (res > 0) {
+        double ratio = std::ceil(pix_scale / res);
+        f = ratio > (double)kMaxOversampling ? kMaxOversampling : (int)ratio;
+        if (f > kMaxOversampling) f = kMaxOversampling;
+      } else {
+        f = kMaxOversampling;
+      }
+    }
+    double e = sp[3];
+    double phi = py_mod(sp[4] * kDegH - 0.0, M_PI - 0.0) + 0.0;  // wrap_at(phi, 0, 180 deg)
+    j.ecc = e;
+    j.phi = phi;
+    j.major = sp[2] * kDegH;
+    if (type == GPY_SPATIAL_GAUSS) {
+      double sigma = sp[2] * kDegH;
+      if (e == 0) {
+        j.a = 1.0 - std::cos(sigma);
+        j.norm = 1 / (4 * M_PI * j.a * (1.0 - std::exp(-1.0 / j.a)));
+      } else {
+        double minor = sigma * std::sqrt(1 - e * e);
+        j.norm = 1 / (2 * M_PI * sigma * minor);
+      }
+    } else {
+      j.edge_width = sp[5];
+      j.norm = disk_norm_factor(sp[2] * kDegH, e);
+    }
+    if (f > 1) {
+      j.ix0 = inner.x0;
+      j.iy0 = inner.y0;
+      j.icx = inner.cx;
+      j.icy = inner.cy;
+      GeomH cg = sub_geom(eg, inner);
+      // WcsGeom.upsample + get_resampled_wcs: crpix' = (crpix - 0.5) * f + 0.5, cdelt' = cdelt / f
+      j.wcs_up.crval_lon = cg.crval_lon;
+      j.wcs_up.binsz = cg.binsz / f;
+      j.wcs_up.crpix_x = (cg.crpix_x - 0.5) * f + 0.5;
+      j.wcs_up.crpix_y = (cg.crpix_y - 0.5) * f + 0.5;
+    }
+  }
+  j.f = f;
+  if (f_out) *f_out = f;
+  dim3 grid((pitch + 127) / 128, rect.cy);
+  gpy::spatial_fill_kernel<<<grid, 128, 0, c->stream>>>(j);
+  c->launches++;
+  if (type != GPY_SPATIAL_POINT && f > 1) {
+    long long warps = (long long)j.icx * j.icy;
+    int blocks = (int)((warps * 32 + 255) / 256);
+    gpy::spatial_oversample_kernel<<<blocks, 256, 0, c->stream>>>(j);
+    c->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return GPY_OK;
+}
+
+size_t conv_smem_bytes(int h, int kw) {
+  return ((size_t)(gpy::kConvTY + 2 * h) * (gpy::kConvTX + kw) + (size_t)(2 * h + 1) * kw) * sizeof(float);
+}
+
+int launch_conv(gpy_context* c, const float* image, int cy, int cx, int pitch, int xpad, const float* kflip,
+                const gpy::ConvPlane* planes_dev, int n_planes, int max_h, int max_kw, float* out) {
+  size_t smem = conv_smem_bytes(max_h, max_kw);
+  if (smem > (size_t)c->max_smem_optin)
+    return fail(GPY_ERR_UNSUPPORTED, "PSF kernel too large for the shared-memory stencil (half width %d)", max_h);
+  if (smem > c->conv_smem_set) {
+    CUDA_TRY(cudaFuncSetAttribute(gpy::psf_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    c->conv_smem_set = smem;
+  }
+  dim3 grid((pitch + gpy::kConvTX - 1) / gpy::kConvTX, (cy + gpy::kConvTY - 1) / gpy::kConvTY, n_planes);
+  gpy::psf_conv_kernel<<<grid, gpy::kConvThreads, smem, c->stream>>>(image, cy, cx, pitch, xpad, kflip, planes_dev,
+                                                                     out, (size_t)cy * pitch);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return GPY_OK;
+}
+
+// Flip, crop to the non-zero support and pad each kernel plane (maps/wcs/ndmap.py:961: float32 planes).
+void prepare_planes(const float* kernel, int n_planes, int K, std::vector<float>& kflip,
+                    std::vector<gpy::ConvPlane>& planes, int& max_h, int& max_kw) {
+  const int hK = (K - 1) / 2;
+  kflip.clear();
+  planes.resize(n_planes);
+  max_h = 0;
+  max_kw = 4;
+  for (int t = 0; t < n_planes; ++t) {
+    const float* kp = kernel + (size_t)t * K * K;
+    int h = 0;
+    for (int i = 0; i < K; ++i)
+      for (int jx = 0; jx < K; ++jx)
+        if (kp[(size_t)i * K + jx] != 0.0f) h = std::max(h, std::max(std::abs(i - hK), std::abs(jx - hK)));
+    int kw = (2 * h + 1 + 3) / 4 * 4;
+    gpy::ConvPlane pl{h, kw, (int)kflip.size(), 0};
+    kflip.resize(kflip.size() + (size_t)(2 * h + 1) * kw, 0.0f);
+    for (int i = 0; i <= 2 * h; ++i)
+      for (int jx = 0; jx <= 2 * h; ++jx)
+        kflip[pl.koff + (size_t)i * kw + jx] = kp[(size_t)(hK + h - i) * K + (hK + h - jx)];
+    planes[t] = pl;
+    max_h = std::max(max_h, h);
+    max_kw = std::max(max_kw, kw);
+  }
+}
+
+// MapEvaluator.update geometry (evaluator.py:174-243) for spatial parameters `sp`.
+int evaluator_update(const gpy_dataset* ds, const Source& src, const double* sp, Rect& rect, bool& contributes) {
+  const int type = src.desc.spatial_type;
+  const double psf_width = ds->has_psf ? ds->geom.binsz * ds->psf_k : 0.0;  // np.max(kernel geom width)
+  const double radius = evaluation_radius(type, sp);
+  const double cutout_width = psf_width + 2 * (radius + kCutoutMargin);  // evaluator.py:169-172
+  // SkyModel.contributes(mask, margin=psf_width) (cube.py:246-286)
+  Rect mrect;
+  CutStatus cs = cutout_rect(ds->geom, sp[0], sp[1], 2 * radius + kCutoutMargin + psf_width, false, mrect);
+  contributes = false;
+  if (cs == CUT_OK) {
+    if (ds->mask_image.empty()) {
+      contributes = true;
+    } else {
+      for (int y = mrect.y0; y < mrect.y0 + mrect.cy && !contributes; ++y) {
+        const uint8_t* row = ds->mask_image.data() + (size_t)y * ds->geom.nx;
+        for (int x = mrect.x0; x < mrect.x0 + mrect.cx; ++x)
+          if (row[x]) {
+            contributes = true;
+            break;
+          }
+      }
+    }
+  }
+  if (!contributes) return GPY_OK;
+  cs = cutout_rect(ds->geom, sp[0], sp[1], cutout_width, true, rect);
+  if (cs == CUT_VALUE_ERROR)
+    return fail(GPY_ERR_INVALID, "non-finite source position / size in MapEvaluator.update (Cutout2D raises ValueError)");
+  if (cs == CUT_NO_OVERLAP)
+    return fail(GPY_ERR_INVALID, "source cutout does not overlap the dataset geometry (NoOverlapError)");
+  return GPY_OK;
+}
+
+// Find or build the slot holding integrate_geom (x) PSF for (sp, rect).
+int get_slot(gpy_dataset* ds, Source& src, const double* sp, const Rect& rect, Slot** out) {
+  gpy_context* c = ds->ctx;
+  const int nsp = n_spatial_params(src.desc.spatial_type);
+  Slot* victim = &src.slots[0];
+  for (auto& s : src.slots) {
+    if (s.valid && s.rect == rect && (int)s.key.size() == nsp &&
+        std::memcmp(s.key.data(), sp, nsp * sizeof(double)) == 0) {
+      s.stamp = ++c->stamp;
+      *out = &s;
+      return GPY_OK;
+    }
+    if (!s.valid) {
+      if (victim->valid) victim = &s;
+    } else if (victim->valid && s.stamp < victim->stamp) {
+      victim = &s;
+    }
+  }
+  Slot& s = *victim;
+  s.valid = false;
+  s.rect = rect;
+  s.x0a = rect.x0 & ~3;
+  s.pitch = (rect.x0 + rect.cx - s.x0a + 3) / 4 * 4;
+  const bool conv = ds->has_psf && src.desc.apply_psf;
+  s.planes = conv ? ds->nT : 1;
+  const size_t img = (size_t)rect.cy * s.pitch;
+  GPY_TRY(s.w.reserve(img * sizeof(float)));
+  GPY_TRY(compute_spatial(c, ds->geom, (const double*)ds->d_omega.p, rect, src.desc.spatial_type, sp,
+                          (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f));
+  if (conv) {
+    GPY_TRY(s.conv.reserve(img * ds->nT * sizeof(float)));
+    GPY_TRY(launch_conv(c, (const float*)s.w.p, rect.cy, rect.cx, s.pitch, rect.x0 - s.x0a,
+                        (const float*)ds->d_kflip.p, (const gpy::ConvPlane*)ds->d_planes.p, ds->nT, ds->max_h,
+                        ds->max_kw, (float*)s.conv.p));
+  }
+  s.key.assign(sp, sp + nsp);
+  s.valid = true;
+  s.stamp = ++c->stamp;
+  src.last_f = s.f;
+  src.n_spatial_evals++;
+  *out = &s;
+  return GPY_OK;
+}
+
+struct EvalRequest {
+  gpy_dataset* const* datasets;
+  int n_datasets;
+  const double* params;
+  int n_vec, n_par;
+  const uint8_t* source_enable;  // single-dataset npred only
+  int include_background;
+  double* npred_out;  // device
+};
+
+int check_par(int idx, int n_par, const char* what) {
+  if (idx < 0 || idx >= n_par) return fail(GPY_ERR_INVALID, "parameter index %d of %s outside [0, %d)", idx, what, n_par);
+  return GPY_OK;
+}
+
+// Build descriptors, refresh spatial caches, launch K0 + fused fold/Cash + reduction.
+// Leaves stat[b * D + d] in c->stat (device).
+int evaluate(gpy_context* c, const EvalRequest& rq) {
+  const int D = rq.n_datasets, B = rq.n_vec;
+  if (D <= 0 || B <= 0) return fail(GPY_ERR_INVALID, "need at least one dataset and one parameter vector");
+  if (c->h2d_pending) {
+    CUDA_TRY(cudaEventSynchronize(c->h2d_done));
+    c->h2d_pending = false;
+  }
+  std::vector<gpy::DatasetDev> dsd(D);
+  std::vector<gpy::EvalDev> evals((size_t)D * B);
+  std::vector<gpy::InstDev> insts;
+  std::vector<gpy::FluxJob> jobs;
+  std::vector<size_t> job_flux_off;
+  size_t flux_len = 0;
+  int n_tiles = 0, max_inst = 1;
+  size_t max_fold_smem = 0;
+  const bool sequential = (B == 1);
+
+  for (int d = 0; d < D; ++d) {
+    gpy_dataset* ds = rq.datasets[d];
+    if (!ds || ds->ctx != c) return fail(GPY_ERR_INVALID, "dataset %d does not belong to this context", d);
+    gpy::DatasetDev& dd = dsd[d];
+    dd.nx = ds->geom.nx;
+    dd.ny = ds->geom.ny;
+    dd.nT = ds->nT;
+    dd.nR = ds->nR;
+    dd.nRp = ds->nRp;
+    dd.n_groups = ds->n_groups;
+    dd.P = (long long)ds->geom.nx * ds->geom.ny;
+    dd.tile_begin = n_tiles;
+    dd.n_tiles = (int)((dd.P + gpy::kFoldTPX - 1) / gpy::kFoldTPX);
+    n_tiles += dd.n_tiles;
+    dd.exposure = ds->exposure;
+    dd.background = ds->background;
+    dd.counts = rq.npred_out ? nullptr : ds->counts;
+    dd.mask = ds->mask;
+    dd.edisp = (const double*)ds->d_edisp.p;
+    dd.band = (const int*)ds->d_band.p;
+    dd.ecenter = (const double*)ds->d_ecenter.p;
+    if (!rq.npred_out && !ds->counts) return fail(GPY_ERR_INVALID, "dataset %d has no counts: stat undefined", d);
+
+    for (int b = 0; b < B; ++b) {
+      const double* pv = rq.params + (size_t)b * rq.n_par;
+      gpy::EvalDev& ev = evals[(size_t)d * B + b];
+      ev.inst_begin = (int)insts.size();
+      ev.bkg_enabled = 0;
+      ev.bkg_norm = 1.0;
+      ev.bkg_tilt = 0.0;
+      ev.bkg_ref = 1.0;
+      if (ds->bkg.enabled) {
+        GPY_TRY(check_par(ds->bkg.par_norm, rq.n_par, "background norm"));
+        GPY_TRY(check_par(ds->bkg.par_tilt, rq.n_par, "background tilt"));
+        GPY_TRY(check_par(ds->bkg.par_reference, rq.n_par, "background reference"));
+        ev.bkg_enabled = 1;
+        ev.bkg_norm = pv[ds->bkg.par_norm];
+        ev.bkg_tilt = pv[ds->bkg.par_tilt];
+        ev.bkg_ref = pv[ds->bkg.par_reference];
+      }
+      for (size_t si = 0; si < ds->sources.size(); ++si) {
+        Source& src = ds->sources[si];
+        const int nsp = n_spatial_params(src.desc.spatial_type);
+        const int nsc = n_spectral_params(src.desc.spectral_type);
+        double sp[6] = {0, 0, 0, 0, 0, 0}, sc[5] = {0, 0, 0, 0, 0};
+        for (int k = 0; k < nsp; ++k) {
+          GPY_TRY(check_par(src.desc.spatial_par[k], rq.n_par, "a spatial parameter"));
+          sp[k] = pv[src.desc.spatial_par[k]];
+        }
+        for (int k = 0; k < nsc; ++k) {
+          GPY_TRY(check_par(src.desc.spectral_par[k], rq.n_par, "a spectral parameter"));
+          sc[k] = pv[src.desc.spectral_par[k]];
+        }
+        // ---- MapEvaluator.needs_update (evaluator.py:128-144) on the persistent or a scratch state
+        bool initialised = src.initialised, contributes = src.contributes;
+        Rect rect = src.rect;
+        double clon = src.cached_lon, clat = src.cached_lat;
+        bool needs_update;
+        if (!contributes) {
+          needs_update = false;
+        } else if (!initialised) {
+          needs_update = true;
+        } else {
+          bool changed = !src.has_cached_spatial ||
+                         std::memcmp(src.cached_spatial.data(), sp, nsp * sizeof(double)) != 0;
+          if (!changed) {
+            needs_update = false;
+          } else {  // irf_position_changed (evaluator.py:465-481)
+            double lon = sp[0] * kDegH, lat = sp[1] * kDegH;
+            double sep = angular_separation_h(lon, lat, clon, clat);
+            bool moved = sep > (evaluation_radius(src.desc.spatial_type, sp) + kCutoutMargin) * kDegH;
+            if (moved) {
+              clon = lon;
+              clat = lat;
+            }
+            needs_update = moved;
+          }
+        }
+        if (needs_update) {
+          GPY_TRY(evaluator_update(ds, src, sp, rect, contributes));
+          initialised = true;
+        }
+        if (sequential) {
+          src.initialised = initialised;
+          src.contributes = contributes;
+          src.rect = rect;
+          src.cached_lon = clon;
+          src.cached_lat = clat;
+          if (contributes) {  // parameters_spatial_changed(reset=True) inside compute_flux_spatial
+            src.cached_spatial.assign(sp, sp + nsp);
+            src.has_cached_spatial = true;
+          }
+        }
+        if (!contributes) continue;
+        if (rq.source_enable && !rq.source_enable[si]) continue;
+        // _compute_npred: amplitude == 0 -> zeros (evaluator.py:385-389)
+        const int amp_idx = src.desc.spectral_type == GPY_SPECTRAL_LP ? 0 : 1;
+        if (sc[amp_idx] == 0.0) continue;
+        Slot* slot = nullptr;
+        GPY_TRY(get_slot(ds, src, sp, rect, &slot));
+        gpy::InstDev in;
+        std::memset(&in, 0, sizeof(in));
+        in.x0 = rect.x0;
+        in.y0 = rect.y0;
+        in.cx = rect.cx;
+        in.cy = rect.cy;
+        in.x0a = slot->x0a;
+        in.pitch = slot->pitch;
+        in.planes = slot->planes;
+        in.group = (src.desc.apply_edisp || !ds->has_diag) ? 0 : 1;
+        in.flux_off = (int)flux_len;
+        in.conv = (const float*)(slot->planes == 1 ? slot->w.p : slot->conv.p);
+        insts.push_back(in);
+        gpy::FluxJob job;
+        std::memset(&job, 0, sizeof(job));
+        job.type = src.desc.spectral_type;
+        job.n_bins = ds->nT;
+        job.n_nodes = ds->n_nodes;
+        for (int k = 0; k < 5; ++k) job.p[k] = sc[k];
+        job.edges = (const double*)ds->d_edges.p;
+        job.nodes = (const double*)ds->d_nodes.p;
+        jobs.push_back(job);
+        job_flux_off.push_back(flux_len);
+        flux_len += ds->nT;
+      }
+      ev.inst_count = (int)insts.size() - ev.inst_begin;
+      max_inst = std::max(max_inst, ev.inst_count);
+    }
+    size_t smem = ((size_t)ds->n_groups * ds->nT * gpy::kFoldTPX + (size_t)ds->n_groups * ds->nT * ds->nRp + ds->nRp + 8) *
+                  sizeof(double);
+    max_fold_smem = std::max(max_fold_smem, smem);
+  }
+  max_fold_smem += (size_t)max_inst * sizeof(int);
+  if (max_fold_smem > (size_t)c->max_smem_optin)
+    return fail(GPY_ERR_UNSUPPORTED, "energy axes too large for the fused fold kernel (%zu bytes of shared memory)",
+                max_fold_smem);
+
+  // tile -> dataset table, cached per dataset list
+  bool same = (int)c->tiles_for.size() == D;
+  for (int d = 0; same && d < D; ++d)
+    same = c->tiles_for[d] == rq.datasets[d] && c->tiles_ver[d] == rq.datasets[d]->version;
+  if (!same) {
+    std::vector<int> tile_ds((size_t)n_tiles);
+    for (int d = 0; d < D; ++d) std::fill_n(tile_ds.begin() + dsd[d].tile_begin, dsd[d].n_tiles, d);
+    GPY_TRY(upload_to(c->tiles, tile_ds.data(), tile_ds.size() * sizeof(int), c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));  // tile_ds is a stack vector
+    c->tiles_for.assign(rq.datasets, rq.datasets + D);
+    c->tiles_ver.resize(D);
+    for (int d = 0; d < D; ++d) c->tiles_ver[d] = rq.datasets[d]->version;
+  }
+
+  GPY_TRY(c->flux.reserve(std::max(flux_len, (size_t)1) * sizeof(double)));
+  GPY_TRY(c->partials.reserve((size_t)B * n_tiles * sizeof(double)));
+  GPY_TRY(c->stat.reserve((size_t)B * D * sizeof(double)));
+  for (size_t i = 0; i < jobs.size(); ++i) jobs[i].out = (double*)c->flux.p + job_flux_off[i];
+
+  Packer pk;
+  size_t off_ds = pk.add(dsd.data(), dsd.size() * sizeof(gpy::DatasetDev));
+  size_t off_ev = pk.add(evals.data(), evals.size() * sizeof(gpy::EvalDev));
+  size_t off_in = pk.add(insts.data(), insts.size() * sizeof(gpy::InstDev));
+  size_t off_jb = pk.add(jobs.data(), jobs.size() * sizeof(gpy::FluxJob));
+  GPY_TRY(ensure_pinned(c, pk.bytes.size()));
+  std::memcpy(c->pinned, pk.bytes.data(), pk.bytes.size());
+  GPY_TRY(c->staging.reserve(pk.bytes.size()));
+  CUDA_TRY(cudaMemcpyAsync(c->staging.p, c->pinned, pk.bytes.size(), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaEventRecord(c->h2d_done, c->stream));
+  c->h2d_pending = true;
+  uint8_t* base = (uint8_t*)c->staging.p;
+
+  if (!jobs.empty()) {
+    gpy::spectral_flux_kernel<<<(unsigned)jobs.size(), 64, 0, c->stream>>>((const gpy::FluxJob*)(base + off_jb));
+    c->launches++;
+  }
+  gpy::FoldParams fp;
+  std::memset(&fp, 0, sizeof(fp));
+  fp.ds = (const gpy::DatasetDev*)(base + off_ds);
+  fp.tile_ds = (const int*)c->tiles.p;
+  fp.evals = (const gpy::EvalDev*)(base + off_ev);
+  fp.insts = (const gpy::InstDev*)(base + off_in);
+  fp.flux = (const double*)c->flux.p;
+  fp.partials = (double*)c->partials.p;
+  fp.npred_out = rq.npred_out;
+  fp.B = B;
+  fp.n_tiles = n_tiles;
+  fp.n_datasets = D;
+  fp.include_background = rq.include_background;
+  fp.max_inst = max_inst;
+  fp.log_trunc = c->log_trunc;
+  if (max_fold_smem > c->fold_smem_set) {
+    CUDA_TRY(cudaFuncSetAttribute(gpy::fold_cash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)max_fold_smem));
+    c->fold_smem_set = max_fold_smem;
+  }
+  gpy::fold_cash_kernel<<<(unsigned)((size_t)B * n_tiles), gpy::kFoldThreads, max_fold_smem, c->stream>>>(fp);
+  c->launches++;
+  gpy::reduce_stat_kernel<<<dim3(B, D), 256, 0, c->stream>>>((const double*)c->partials.p, fp.ds, n_tiles, D,
+                                                              (double*)c->stat.p);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return GPY_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* gpy_last_error(void) { return g_last_error.c_str(); }
+int gpy_abi_version(void) { return GPY_ABI_VERSION; }
+
+int gpy_init(int device, void* stream, gpy_context_t** out) {
+  if (!out) return fail(GPY_ERR_INVALID, "ctx output pointer is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0)
+    return fail(GPY_ERR_CUDA, "no CUDA device available (%s): libgpy_b200 has no CPU fallback",
+                err != cudaSuccess ? cudaGetErrorString(err) : "device count 0");
+  if (device < 0 || device >= count) return fail(GPY_ERR_INVALID, "device %d outside [0, %d)", device, count);
+  CUDA_TRY(cudaSetDevice(device));
+  gpy_context* c = new gpy_context();
+  c->device = device;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete c;
+      return fail(GPY_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    }
+    c->own_stream = true;
+  }
+  cudaEventCreateWithFlags(&c->h2d_done, cudaEventDisableTiming);
+  cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  c->log_trunc = std::log((double)(float)1e-25);  // Cython: log(<float>TRUNCATION_VALUE), .pyx:35
+  *out = c;
+  return GPY_OK;
+}
+
+int gpy_finalize(gpy_context_t* c) {
+  if (!c) return GPY_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (DevBuf* b : {&c->staging, &c->flux, &c->partials, &c->stat, &c->tiles, &c->scratch_a, &c->scratch_b, &c->scratch_c})
+    b->release();
+  if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->stat_pinned) cudaFreeHost(c->stat_pinned);
+  if (c->h2d_done) cudaEventDestroy(c->h2d_done);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return GPY_OK;
+}
+
+int64_t gpy_launch_count(const gpy_context_t* c) { return c ? c->launches : 0; }
+
+int gpy_dataset_create(gpy_context_t* c, const gpy_dataset_desc* desc, gpy_dataset_t** out) {
+  if (!c || !desc || !out) return fail(GPY_ERR_INVALID, "NULL argument to gpy_dataset_create");
+  *out = nullptr;
+  const gpy_geom_desc& g = desc->geom;
+  if (g.nx <= 0 || g.ny <= 0 || g.n_true <= 0 || g.n_reco <= 0 || !(g.binsz > 0))
+    return fail(GPY_ERR_INVALID, "invalid geometry (nx=%d ny=%d n_true=%d n_reco=%d binsz=%g)", g.nx, g.ny, g.n_true,
+                g.n_reco, g.binsz);
+  if (!desc->exposure || !desc->edisp || !desc->energy_true_edges || !desc->energy_reco_center)
+    return fail(GPY_ERR_INVALID, "exposure, edisp and the energy axes are required");
+  if (((uintptr_t)desc->exposure & 15) != 0)
+    return fail(GPY_ERR_INVALID, "exposure must be 16-byte aligned");
+  if (desc->psf_kernel && (desc->psf_k <= 0 || desc->psf_k % 2 == 0))
+    return fail(GPY_ERR_INVALID, "psf_k must be odd and positive, got %d", desc->psf_k);
+  if (desc->n_nodes < 2 || !desc->nodes) return fail(GPY_ERR_INVALID, "integrate_spectrum nodes missing (n_nodes >= 2)");
+  CUDA_TRY(cudaSetDevice(c->device));
+  gpy_dataset* ds = new gpy_dataset();
+  ds->ctx = c;
+  ds->geom = GeomH{g.nx, g.ny, g.binsz, g.crval_lon, g.crpix_x, g.crpix_y};
+  ds->nT = g.n_true;
+  ds->nR = g.n_reco;
+  ds->nRp = (g.n_reco + 7) / 8 * 8;
+  ds->n_nodes = desc->n_nodes;
+  ds->exposure = desc->exposure;
+  ds->background = desc->background;
+  ds->counts = desc->counts;
+  ds->mask = desc->mask;
+  ds->version = ++c->stamp;
+  const size_t P = (size_t)g.nx * g.ny;
+  if (desc->mask_image) ds->mask_image.assign(desc->mask_image, desc->mask_image + P);
+  ds->has_diag = desc->edisp_diagonal != nullptr;
+  ds->n_groups = ds->has_diag ? 2 : 1;
+  auto cleanup = [&](int rc) {
+    gpy_dataset_destroy(ds);
+    return rc;
+  };
+  cudaStream_t s = c->stream;
+  int rc;
+  if ((rc = upload_to(ds->d_edges, desc->energy_true_edges, (ds->nT + 1) * sizeof(double), s))) return cleanup(rc);
+  if ((rc = upload_to(ds->d_ecenter, desc->energy_reco_center, ds->nR * sizeof(double), s))) return cleanup(rc);
+  if ((rc = upload_to(ds->d_nodes, desc->nodes, (size_t)ds->nT * ds->n_nodes * sizeof(double), s))) return cleanup(rc);
+  // edisp groups, reco axis zero padded to a multiple of 8, and the non-zero band per reco chunk
+  const int nchunks = ds->nRp / 8;
+  std::vector<double> ed((size_t)ds->n_groups * ds->nT * ds->nRp, 0.0);
+  std::vector<int> band((size_t)ds->n_groups * nchunks * 2, 0);
+  for (int gi = 0; gi < ds->n_groups; ++gi) {
+    const double* src = gi == 0 ? desc->edisp : desc->edisp_diagonal;
+    for (int t = 0; t < ds->nT; ++t)
+      for (int r = 0; r < ds->nR; ++r) ed[((size_t)gi * ds->nT + t) * ds->nRp + r] = src[(size_t)t * ds->nR + r];
+    for (int ch = 0; ch < nchunks; ++ch) {
+      int lo = ds->nT, hi = 0;
+      for (int t = 0; t < ds->nT; ++t)
+        for (int r = 8 * ch; r < std::min(8 * ch + 8, ds->nR); ++r) {
+          double v = src[(size_t)t * ds->nR + r];
+          if (v != 0.0) {  // NaN counts as non-zero
+            lo = std::min(lo, t);
+            hi = std::max(hi, t + 1);
+          }
+        }
+      if (lo > hi) lo = hi = 0;
+      band[((size_t)gi * nchunks + ch) * 2] = lo;
+      band[((size_t)gi * nchunks + ch) * 2 + 1] = hi;
+    }
+  }
+  if ((rc = upload_to(ds->d_edisp, ed.data(), ed.size() * sizeof(double), s))) return cleanup(rc);
+  if ((rc = upload_to(ds->d_band, band.data(), band.size() * sizeof(int), s))) return cleanup(rc);
+  std::vector<float> kflip;
+  if (desc->psf_kernel) {
+    ds->has_psf = true;
+    ds->psf_k = desc->psf_k;
+    prepare_planes(desc->psf_kernel, ds->nT, desc->psf_k, kflip, ds->planes, ds->max_h, ds->max_kw);
+    if ((rc = upload_to(ds->d_kflip, kflip.data(), kflip.size() * sizeof(float), s))) return cleanup(rc);
+    if ((rc = upload_to(ds->d_planes, ds->planes.data(), ds->planes.size() * sizeof(gpy::ConvPlane), s)))
+      return cleanup(rc);
+  }
+  if ((rc = ds->d_omega.reserve(P * sizeof(double)))) return cleanup(rc);
+  gpy::solid_angle_kernel<<<dim3((g.nx + 127) / 128, g.ny), 128, 0, s>>>(wcs_of(ds->geom), g.nx, g.ny,
+                                                                          (double*)ds->d_omega.p);
+  c->launches++;
+  cudaError_t e = cudaStreamSynchronize(s);  // host staging vectors go out of scope
+  if (e != cudaSuccess) return cleanup(fail(GPY_ERR_CUDA, "dataset upload failed: %s", cudaGetErrorString(e)));
+  *out = ds;
+  return GPY_OK;
+}
+
+int gpy_dataset_destroy(gpy_dataset_t* ds) {
+  if (!ds) return GPY_OK;
+  cudaSetDevice(ds->ctx->device);
+  cudaStreamSynchronize(ds->ctx->stream);
+  for (DevBuf* b : {&ds->d_edges, &ds->d_nodes, &ds->d_ecenter, &ds->d_edisp, &ds->d_band, &ds->d_omega, &ds->d_kflip,
+                    &ds->d_planes})
+    b->release();
+  for (auto& src : ds->sources)
+    for (auto& sl : src.slots) {
+      sl.w.release();
+      sl.conv.release();
+    }
+  ds->ctx->tiles_for.clear();
+  delete ds;
+  return GPY_OK;
+}
+
+int gpy_dataset_set_counts(gpy_dataset_t* ds, const float* counts_device) {
+  if (!ds) return fail(GPY_ERR_INVALID, "NULL dataset");
+  ds->counts = counts_device;
+  return GPY_OK;
+}
+
+int gpy_dataset_set_models(gpy_dataset_t* ds, const gpy_source_desc* sources, int32_t n_sources,
+                           const gpy_background_desc* background) {
+  if (!ds) return fail(GPY_ERR_INVALID, "NULL dataset");
+  if (n_sources < 0 || (n_sources > 0 && !sources)) return fail(GPY_ERR_INVALID, "bad source list");
+  for (int i = 0; i < n_sources; ++i) {
+    if (sources[i].spatial_type < 0 || sources[i].spatial_type > 2)
+      return fail(GPY_ERR_UNSUPPORTED, "source %d: unsupported spatial model type %d", i, sources[i].spatial_type);
+    if (sources[i].spectral_type < 0 || sources[i].spectral_type > 2)
+      return fail(GPY_ERR_UNSUPPORTED, "source %d: unsupported spectral model type %d", i, sources[i].spectral_type);
+  }
+  cudaSetDevice(ds->ctx->device);
+  cudaStreamSynchronize(ds->ctx->stream);
+  for (auto& src : ds->sources)
+    for (auto& sl : src.slots) {
+      sl.w.release();
+      sl.conv.release();
+    }
+  ds->sources.clear();
+  ds->sources.resize(n_sources);
+  for (int i = 0; i < n_sources; ++i) ds->sources[i].desc = sources[i];
+  if (background)
+    ds->bkg = *background;
+  else
+    ds->bkg = gpy_background_desc{0, -1, -1, -1};
+  return GPY_OK;
+}
+
+int gpy_dataset_source_state(const gpy_dataset_t* ds, int32_t source, gpy_source_state* out) {
+  if (!ds || !out) return fail(GPY_ERR_INVALID, "NULL argument");
+  if (source < 0 || source >= (int)ds->sources.size()) return fail(GPY_ERR_INVALID, "source index out of range");
+  const Source& s = ds->sources[source];
+  out->initialised = s.initialised;
+  out->contributes = s.contributes;
+  out->x0 = s.rect.x0;
+  out->y0 = s.rect.y0;
+  out->cx = s.rect.cx;
+  out->cy = s.rect.cy;
+  out->oversampling = s.last_f;
+  out->n_spatial_evals = s.n_spatial_evals;
+  return GPY_OK;
+}
+
+int gpy_stat_sum_device(gpy_context_t* c, gpy_dataset_t* const* datasets, int32_t n_datasets, const double* params,
+                        int32_t n_vec, int32_t n_par, double* stat_device) {
+  if (!c || !datasets || !params || !stat_device) return fail(GPY_ERR_INVALID, "NULL argument to gpy_stat_sum_device");
+  CUDA_TRY(cudaSetDevice(c->device));
+  EvalRequest rq{datasets, n_datasets, params, n_vec, n_par, nullptr, 1, nullptr};
+  GPY_TRY(evaluate(c, rq));
+  CUDA_TRY(cudaMemcpyAsync(stat_device, c->stat.p, (size_t)n_vec * n_datasets * sizeof(double),
+                           cudaMemcpyDeviceToDevice, c->stream));
+  return GPY_OK;
+}
+
+int gpy_stat_sum(gpy_context_t* c, gpy_dataset_t* const* datasets, int32_t n_datasets, const double* params,
+                 int32_t n_vec, int32_t n_par, double* stat, double* stat_per_dataset) {
+  if (!c || !datasets || !params || !stat) return fail(GPY_ERR_INVALID, "NULL argument to gpy_stat_sum");
+  CUDA_TRY(cudaSetDevice(c->device));
+  EvalRequest rq{datasets, n_datasets, params, n_vec, n_par, nullptr, 1, nullptr};
+  GPY_TRY(evaluate(c, rq));
+  const size_t n = (size_t)n_vec * n_datasets;
+  GPY_TRY(ensure_stat_pinned(c, n));
+  CUDA_TRY(cudaMemcpyAsync(c->stat_pinned, c->stat.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->h2d_pending = false;
+  for (int b = 0; b < n_vec; ++b) {
+    double s = 0.0;  // Datasets.stat_sum: python loop `stat_sum += dataset.stat_sum_likelihood()` in dataset order
+    for (int d = 0; d < n_datasets; ++d) s += c->stat_pinned[(size_t)b * n_datasets + d];
+    stat[b] = s;
+  }
+  if (stat_per_dataset) std::memcpy(stat_per_dataset, c->stat_pinned, n * sizeof(double));
+  return GPY_OK;
+}
+
+int gpy_npred(gpy_context_t* c, gpy_dataset_t* ds, const double* params, int32_t n_par, const uint8_t* source_enable,
+              int32_t include_background, double* npred_device) {
+  if (!c || !ds || !params || !npred_device) return fail(GPY_ERR_INVALID, "NULL argument to gpy_npred");
+  CUDA_TRY(cudaSetDevice(c->device));
+  gpy_dataset_t* list[1] = {ds};
+  EvalRequest rq{list, 1, params, 1, n_par, source_enable, include_background, npred_device};
+  GPY_TRY(evaluate(c, rq));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->h2d_pending = false;
+  return GPY_OK;
+}
+
+static int cash_common(gpy_context_t* c, const double* counts, const double* npred, const double* weight, int64_t n,
+                       double* out) {
+  if (!c || !out || (n > 0 && (!counts || !npred))) return fail(GPY_ERR_INVALID, "NULL argument to gpy_cash_sum");
+  if (n < 0) return fail(GPY_ERR_INVALID, "negative length");
+  if (n == 0) {
+    *out = 0.0;
+    return GPY_OK;
+  }
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)n * sizeof(double);
+  GPY_TRY(c->scratch_a.reserve(bytes));
+  GPY_TRY(c->scratch_b.reserve(bytes));
+  if (weight) GPY_TRY(c->scratch_c.reserve(bytes));
+  CUDA_TRY(cudaMemcpyAsync(c->scratch_a.p, counts, bytes, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->scratch_b.p, npred, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (weight) CUDA_TRY(cudaMemcpyAsync(c->scratch_c.p, weight, bytes, cudaMemcpyHostToDevice, c->stream));
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  GPY_TRY(c->partials.reserve((size_t)blocks * sizeof(double)));
+  GPY_TRY(c->stat.reserve(sizeof(double)));
+  gpy::cash_sum_kernel<<<blocks, 256, 0, c->stream>>>((const double*)c->scratch_a.p, (const double*)c->scratch_b.p,
+                                                       weight ? (const double*)c->scratch_c.p : nullptr, n, c->log_trunc,
+                                                       (double*)c->partials.p);
+  gpy::final_sum_kernel<<<1, 256, 0, c->stream>>>((const double*)c->partials.p, blocks, 2.0, (double*)c->stat.p);
+  c->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, c->stat.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return GPY_OK;
+}
+
+int gpy_cash_sum(gpy_context_t* c, const double* counts, const double* npred, int64_t n, double* out) {
+  return cash_common(c, counts, npred, nullptr, n, out);
+}
+
+int gpy_weighted_cash_sum(gpy_context_t* c, const double* counts, const double* npred, const double* weight, int64_t n,
+                          double* out) {
+  if (!weight && n > 0) return fail(GPY_ERR_INVALID, "NULL weight");
+  return cash_common(c, counts, npred, weight, n, out);
+}
+
+int gpy_solid_angle(gpy_context_t* c, const gpy_geom_desc* g, double* out) {
+  if (!c || !g || !out) return fail(GPY_ERR_INVALID, "NULL argument to gpy_solid_angle");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t P = (size_t)g->nx * g->ny;
+  GPY_TRY(c->scratch_a.reserve(P * sizeof(double)));
+  GeomH gh{g->nx, g->ny, g->binsz, g->crval_lon, g->crpix_x, g->crpix_y};
+  gpy::solid_angle_kernel<<<dim3((g->nx + 127) / 128, g->ny), 128, 0, c->stream>>>(wcs_of(gh), g->nx, g->ny,
+                                                                                    (double*)c->scratch_a.p);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, c->scratch_a.p, P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return GPY_OK;
+}
+
+int gpy_integrate_geom(gpy_context_t* c, const gpy_geom_desc* g, int32_t spatial_type, const double* sp, float* out,
+                       int32_t* oversampling) {
+  if (!c || !g || !sp || !out) return fail(GPY_ERR_INVALID, "NULL argument to gpy_integrate_geom");
+  if (spatial_type < 0 || spatial_type > 2) return fail(GPY_ERR_UNSUPPORTED, "unsupported spatial model type %d", spatial_type);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t P = (size_t)g->nx * g->ny;
+  GeomH gh{g->nx, g->ny, g->binsz, g->crval_lon, g->crpix_x, g->crpix_y};
+  GPY_TRY(c->scratch_a.reserve(P * sizeof(double)));
+  const int pitch = (g->nx + 3) / 4 * 4;
+  GPY_TRY(c->scratch_b.reserve((size_t)pitch * g->ny * sizeof(float)));
+  gpy::solid_angle_kernel<<<dim3((g->nx + 127) / 128, g->ny), 128, 0, c->stream>>>(wcs_of(gh), g->nx, g->ny,
+                                                                                    (double*)c->scratch_a.p);
+  c->launches++;
+  Rect full;
+  full.x0 = 0;
+  full.y0 = 0;
+  full.cx = g->nx;
+  full.cy = g->ny;
+  int f = 0;
+  GPY_TRY(compute_spatial(c, gh, (const double*)c->scratch_a.p, full, spatial_type, sp, (float*)c->scratch_b.p, pitch, 0,
+                          &f));
+  if (oversampling) *oversampling = f;
+  CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)g->nx * sizeof(float), c->scratch_b.p, (size_t)pitch * sizeof(float),
+                             (size_t)g->nx * sizeof(float), g->ny, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return GPY_OK;
+}
+
+int gpy_psf_convolve(gpy_context_t* c, const float* image, int32_t ny, int32_t nx, const float* kernel,
+                     int32_t n_planes, int32_t k, float* out) {
+  if (!c || !image || !kernel || !out) return fail(GPY_ERR_INVALID, "NULL argument to gpy_psf_convolve");
+  if (ny <= 0 || nx <= 0 || n_planes <= 0 || k <= 0 || k % 2 == 0)
+    return fail(GPY_ERR_INVALID, "bad shape for gpy_psf_convolve (kernel side must be odd)");
+  CUDA_TRY(cudaSetDevice(c->device));
+  std::vector<float> kflip;
+  std::vector<gpy::ConvPlane> planes;
+  int max_h, max_kw;
+  prepare_planes(kernel, n_planes, k, kflip, planes, max_h, max_kw);
+  const int pitch = (nx + 3) / 4 * 4;
+  DevBuf d_img, d_k, d_pl, d_out;
+  int rc = GPY_OK;
+  auto done = [&](int r) {
+    d_img.release();
+    d_k.release();
+    d_pl.release();
+    d_out.release();
+    return r;
+  };
+  if ((rc = d_img.reserve((size_t)pitch * ny * sizeof(float)))) return done(rc);
+  if ((rc = d_out.reserve((size_t)pitch * ny * n_planes * sizeof(float)))) return done(rc);
+  cudaError_t e = cudaMemsetAsync(d_img.p, 0, (size_t)pitch * ny * sizeof(float), c->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(d_img.p, (size_t)pitch * sizeof(float), image, (size_t)nx * sizeof(float),
+                          (size_t)nx * sizeof(float), ny, cudaMemcpyHostToDevice, c->stream);
+  if (e != cudaSuccess) return done(fail(GPY_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(e)));
+  if ((rc = upload_to(d_k, kflip.data(), kflip.size() * sizeof(float), c->stream))) return done(rc);
+  if ((rc = upload_to(d_pl, planes.data(), planes.size() * sizeof(gpy::ConvPlane), c->stream))) return done(rc);
+  if ((rc = launch_conv(c, (const float*)d_img.p, ny, nx, pitch, 0, (const float*)d_k.p,
+                        (const gpy::ConvPlane*)d_pl.p, n_planes, max_h, max_kw, (float*)d_out.p)))
+    return done(rc);
+  e = cudaMemcpy2DAsync(out, (size_t)nx * sizeof(float), d_out.p, (size_t)pitch * sizeof(float),
+                        (size_t)nx * sizeof(float), (size_t)ny * n_planes, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) return done(fail(GPY_ERR_CUDA, "convolution failed: %s", cudaGetErrorString(e)));
+  return done(GPY_OK);
+}
+
+int gpy_spectral_integral(gpy_context_t* c, int32_t spectral_type, const double* sp, const double* edges,
+                          int32_t n_bins, const double* nodes, int32_t n_nodes, double* out) {
+  if (!c || !sp || !edges || !out) return fail(GPY_ERR_INVALID, "NULL argument to gpy_spectral_integral");
+  if (spectral_type < 0 || spectral_type > 2) return fail(GPY_ERR_UNSUPPORTED, "unsupported spectral model type %d", spectral_type);
+  if (spectral_type != GPY_SPECTRAL_PL && (!nodes || n_nodes < 2)) return fail(GPY_ERR_INVALID, "nodes required");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t nn = nodes ? (size_t)n_bins * n_nodes : 0;
+  GPY_TRY(c->scratch_a.reserve((n_bins + 1 + nn + n_bins) * sizeof(double) + sizeof(gpy::FluxJob) + 64));
+  double* d_edges = (double*)c->scratch_a.p;
+  double* d_nodes = d_edges + n_bins + 1;
+  double* d_out = d_nodes + nn;
+  gpy::FluxJob* d_job = (gpy::FluxJob*)(((uintptr_t)(d_out + n_bins) + 15) & ~(uintptr_t)15);
+  gpy::FluxJob job;
+  std::memset(&job, 0, sizeof(job));
+  job.type = spectral_type;
+  job.n_bins = n_bins;
+  job.n_nodes = n_nodes;
+  for (int k = 0; k < n_spectral_params(spectral_type); ++k) job.p[k] = sp[k];
+  job.edges = d_edges;
+  job.nodes = d_nodes;
+  job.out = d_out;
+  CUDA_TRY(cudaMemcpyAsync(d_edges, edges, (n_bins + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (nn) CUDA_TRY(cudaMemcpyAsync(d_nodes, nodes, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_job, &job, sizeof(job), cudaMemcpyHostToDevice, c->stream));
+  gpy::spectral_flux_kernel<<<1, 64, 0, c->stream>>>(d_job);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, d_out, n_bins * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return GPY_OK;
+}
+
+}  // extern "C"

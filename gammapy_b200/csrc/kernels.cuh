@@ -1,0 +1,668 @@
+// kernels.cuh -- sm_100a device code of libgpy_b200: the forward-fold likelihood hot path.
+//
+// Kernels (numbers follow BASELINE.json north_star / DESIGN.md):
+//   K0  spectral_flux_kernel   energy-bin integrals of the spectral models           (a9 in SURVEY.md §8)
+//   K1  spatial_fill_kernel / spatial_oversample_kernel / solid_angle_kernel         (a10, a10p, a10g, a10d)
+//   K2  psf_conv_kernel        per-energy direct stencil, smem tiled, fp32            (a11)
+//   K3+K4 fold_cash_kernel     exposure x flux -> edisp contraction -> + background -> masked Cash,
+//                              fp64 accumulate, batch of parameter vectors per launch  (a2-a6, a12-a14)
+//   reduce_stat_kernel         deterministic second stage of the stat reduction
+//   cash_sum_kernel            stand-alone (weighted) Cash for the compiled-stat registry (a3, a3')
+//
+// Reference citations are relative to /root/reference/gammapy.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace gpy {
+
+constexpr double kDeg = 0.017453292519943295;  // astropy deg -> rad factor (pi / 180)
+constexpr double kTrunc = 1e-25;               // stats/fit_statistics_cython.pyx:12-13
+constexpr double kEdge95 = 2.326174307353347;  // modeling/models/spatial.py:974
+
+// ----------------------------------------------------------------------------------------------
+// WCS: CAR about the equator.  lon = crval + cdelt_x (i + 1 - crpix_x), lat = cdelt_y (j + 1 - crpix_y)
+// (maps/wcs/geom.py:401-413; wcslib linp2x simple path).  No FMA contraction: keep numpy's rounding.
+// ----------------------------------------------------------------------------------------------
+struct WcsDev {
+  double crval_lon, binsz, crpix_x, crpix_y;
+};
+
+__device__ __forceinline__ void pix_to_world_deg(const WcsDev& w, double px, double py, double& lon,
+                                                 double& lat) {
+  lon = __dadd_rn(w.crval_lon, __dmul_rn(-w.binsz, __dadd_rn(__dadd_rn(px, 1.0), -w.crpix_x)));
+  lat = __dmul_rn(w.binsz, __dadd_rn(__dadd_rn(py, 1.0), -w.crpix_y));
+}
+
+// astropy.coordinates.angular_separation (Vincenty), radians.
+__device__ __forceinline__ double angular_separation(double lon1, double lat1, double lon2, double lat2) {
+  double sdlon, cdlon, slat1, clat1, slat2, clat2;
+  sincos(lon2 - lon1, &sdlon, &cdlon);
+  sincos(lat1, &slat1, &clat1);
+  sincos(lat2, &slat2, &clat2);
+  double num1 = clat2 * sdlon;
+  double num2 = clat1 * slat2 - slat1 * clat2 * cdlon;
+  double den = slat1 * slat2 + clat1 * clat2 * cdlon;
+  return atan2(hypot(num1, num2), den);
+}
+
+// astropy.coordinates.position_angle, radians.
+__device__ __forceinline__ double position_angle(double lon1, double lat1, double lon2, double lat2) {
+  double sdl, cdl, s1, c1, s2, c2;
+  sincos(lon2 - lon1, &sdl, &cdl);
+  sincos(lat1, &s1, &c1);
+  sincos(lat2, &s2, &c2);
+  double x = s2 * c1 - c2 * s1 * cdl;
+  double y = sdl * c2;
+  return atan2(y, x);
+}
+
+// ----------------------------------------------------------------------------------------------
+// WcsGeom.solid_angle (maps/wcs/geom.py:816-854): planar-triangle area from the four pixel corners.
+// ----------------------------------------------------------------------------------------------
+__global__ void solid_angle_kernel(WcsDev w, int nx, int ny, double* __restrict__ out) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (x >= nx || y >= ny) return;
+  // corner grid coord[yy][xx], yy in {y, y+1} (edge y-0.5, y+0.5), xx likewise.
+  double lon[2][2], lat[2][2];
+#pragma unroll
+  for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+    for (int ix = 0; ix < 2; ++ix) {
+      double lo, la;
+      pix_to_world_deg(w, (double)x - 0.5 + ix, (double)y - 0.5 + iy, lo, la);
+      lon[iy][ix] = lo * kDeg;
+      lat[iy][ix] = la * kDeg;
+    }
+  // names as in the reference: first index is the y edge, second the x edge
+  // low_left = [:-1,:-1] -> (0,0); low_right = [1:,:-1] -> (1,0); up_left = [:-1,1:] -> (0,1); up_right -> (1,1)
+  double ll_lon = lon[0][0], ll_lat = lat[0][0];
+  double lr_lon = lon[1][0], lr_lat = lat[1][0];
+  double ul_lon = lon[0][1], ul_lat = lat[0][1];
+  double ur_lon = lon[1][1], ur_lat = lat[1][1];
+  double low = angular_separation(ll_lon, ll_lat, lr_lon, lr_lat);
+  double left = angular_separation(ll_lon, ll_lat, ul_lon, ul_lat);
+  double up = angular_separation(ul_lon, ul_lat, ur_lon, ur_lat);
+  double right = angular_separation(lr_lon, lr_lat, ur_lon, ur_lat);
+  double angle_low_right =
+      position_angle(lr_lon, lr_lat, ur_lon, ur_lat) - position_angle(lr_lon, lr_lat, ll_lon, ll_lat);
+  double angle_up_left =
+      position_angle(ul_lon, ul_lat, ur_lon, ur_lat) - position_angle(ll_lon, ll_lat, ul_lon, ul_lat);
+  double area_low_right = 0.5 * low * right * sin(angle_low_right);
+  double area_up_left = 0.5 * up * left * sin(angle_up_left);
+  out[(size_t)y * nx + x] = fabs(area_low_right + area_up_left);
+}
+
+// ----------------------------------------------------------------------------------------------
+// K1: SpatialModel.integrate_geom (modeling/models/spatial.py:222-309, 609-631)
+// ----------------------------------------------------------------------------------------------
+struct SpatialJob {
+  int type;            // gpy_spatial_type
+  int f;               // oversampling factor
+  int ecx, ecy;        // evaluator (exposure cutout) image size
+  int pitch, xpad;     // output row pitch (floats) and left padding: out[y * pitch + xpad + x]
+  int ix0, iy0, icx, icy;  // inner cutout (2 max(r_eval, pix)) in evaluator pixel coords, f > 1 only
+  int ex0, ey0;        // evaluator origin in parent pixels (solid angle lookup)
+  int parent_nx;
+  int pad_;
+  WcsDev wcs_e;        // evaluator geometry
+  WcsDev wcs_up;       // upsampled inner cutout geometry (f > 1)
+  double lon0, lat0;   // source position, rad
+  double a, norm;      // gauss e == 0: a = 1 - cos(sigma); norm of gauss / disk
+  double major, ecc, phi;  // rad; phi wrapped to [0, pi)
+  double edge_width;
+  double px0, py0;     // point source: position in evaluator pixel coordinates
+  const double* solid_angle;  // parent [ny, nx] sr
+  float* out;          // [ecy, pitch]
+};
+
+__device__ __forceinline__ double sigma_eff_dev(const SpatialJob& j, double lon, double lat) {
+  // compute_sigma_eff (spatial.py:57-67)
+  double phi_0 = position_angle(j.lon0, j.lat0, lon, lat);
+  double d_phi = j.phi - phi_0;
+  double minor = j.major * sqrt(1.0 - j.ecc * j.ecc);
+  double sd, cd;
+  sincos(d_phi, &sd, &cd);
+  double a2 = (j.major * sd) * (j.major * sd);
+  double b2 = (minor * cd) * (minor * cd);
+  return j.major * minor / sqrt(a2 + b2);
+}
+
+__device__ __forceinline__ double eval_spatial(const SpatialJob& j, double lon_deg, double lat_deg) {
+  double lon = lon_deg * kDeg, lat = lat_deg * kDeg;
+  double sep = angular_separation(lon, lat, j.lon0, j.lat0);
+  if (j.type == 1) {  // GaussianSpatialModel.evaluate (spatial.py:684-701)
+    double a = j.a;
+    if (j.ecc != 0.0) a = 1.0 - cos(sigma_eff_dev(j, lon, lat));
+    double exponent = -0.5 * ((1.0 - cos(sep)) / a);
+    return j.norm * exp(exponent);
+  }
+  // DiskSpatialModel.evaluate (spatial.py:977-993)
+  double sigma_eff = j.major;
+  if (j.ecc != 0.0) sigma_eff = sigma_eff_dev(j, lon, lat);
+  double value = (sep - sigma_eff) / (sigma_eff * j.edge_width);
+  return j.norm * (0.5 * (1.0 - erf(value * kEdge95)));
+}
+
+// One thread per output element (padded pitch): zero padding, point weights, f == 1 evaluation.
+__global__ void spatial_fill_kernel(SpatialJob j) {
+  int xp = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (xp >= j.pitch || y >= j.ecy) return;
+  int x = xp - j.xpad;
+  float v = 0.f;
+  if (x >= 0 && x < j.ecx) {
+    if (j.type == 0) {
+      // PointSpatialModel._grid_weights (spatial.py:589-598): no solid angle
+      double dx = fabs((double)x - j.px0);
+      dx = dx < 1.0 ? 1.0 - dx : 0.0;
+      double dy = fabs((double)y - j.py0);
+      dy = dy < 1.0 ? 1.0 - dy : 0.0;
+      v = (float)(dx * dy);
+    } else if (j.f == 1) {
+      double lon, lat;
+      pix_to_world_deg(j.wcs_e, (double)x, (double)y, lon, lat);
+      double g = eval_spatial(j, lon, lat);
+      double omega = j.solid_angle[(size_t)(j.ey0 + y) * j.parent_nx + (j.ex0 + x)];
+      v = (float)(g * omega);  // float64 result, cast at the convolution input (ndmap.py:984)
+    }
+  }
+  j.out[(size_t)y * j.pitch + xp] = v;
+}
+
+// f > 1: one warp per inner-cutout pixel, lanes stride the f*f sub-pixels; the block sum is rounded
+// to float32 by the stack into the float32 map (spatial.py:295-296, ndmap.py:1170), then * solid angle.
+__global__ void spatial_oversample_kernel(SpatialJob j) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= j.icx * j.icy) return;
+  int ix = warp % j.icx, iy = warp / j.icx;
+  int f = j.f, ff = f * f;
+  double sum = 0.0;
+  for (int k = lane; k < ff; k += 32) {
+    int sx = k % f, sy = k / f;
+    double lon, lat;
+    pix_to_world_deg(j.wcs_up, (double)(ix * f + sx), (double)(iy * f + sy), lon, lat);
+    double g = eval_spatial(j, lon, lat);
+    // numpy: evaluate(...) / f**2 is a true division per element
+    g = __ddiv_rn(g, (double)ff);
+    if (!isnan(g)) sum += g;  // block_reduce(func=np.nansum)
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) {
+    int x = j.ix0 + ix, y = j.iy0 + iy;
+    float s32 = (float)sum;
+    if (!isfinite(s32)) s32 = 0.f;  // stack(nan_to_num=True)
+    double omega = j.solid_angle[(size_t)(j.ey0 + y) * j.parent_nx + (j.ex0 + x)];
+    j.out[(size_t)y * j.pitch + j.xpad + x] = (float)((double)s32 * omega);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K2: WcsNDMap.convolve(PSFKernel), mode "same" (maps/wcs/ndmap.py:920-1010) as a direct stencil.
+//   image  [cy][pitch] float32, zero outside [xpad, xpad + cx)
+//   planes: per energy the kernel flipped, cropped to its non-zero half width h and padded to kw
+//   out    [plane][cy][pitch] float32 (zero in the padding columns)
+// Tile 64 x 32 outputs per 256-thread block; each thread 8 outputs (two float4 groups 32 apart, so
+// the LDS.128 of a quarter warp are contiguous); fp32 FMA along a kernel row, fp64 across rows.
+// ----------------------------------------------------------------------------------------------
+struct ConvPlane {
+  int h;     // tight half width of the plane's support
+  int kw;    // padded row width of the flipped kernel (multiple of 4, >= 2h + 1)
+  int koff;  // offset (floats) of the plane in the flipped-kernel buffer
+  int pad_;
+};
+
+constexpr int kConvTX = 64, kConvTY = 32, kConvThreads = 256;
+
+__global__ void __launch_bounds__(kConvThreads)
+psf_conv_kernel(const float* __restrict__ image, int cy, int cx, int pitch, int xpad,
+                const float* __restrict__ kflip, const ConvPlane* __restrict__ planes,
+                float* __restrict__ out, size_t plane_stride) {
+  extern __shared__ __align__(16) float conv_smem[];
+  const ConvPlane pl = planes[blockIdx.z];
+  const int h = pl.h, kw = pl.kw, nrow = 2 * h + 1;
+  const int spitch = kConvTX + kw;        // multiple of 4
+  const int srows = kConvTY + 2 * h;
+  float* in_s = conv_smem;                // [srows][spitch]
+  float* k_s = conv_smem + (size_t)srows * spitch;  // [nrow][kw]
+  const int tx0 = blockIdx.x * kConvTX, ty0 = blockIdx.y * kConvTY;
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < nrow * kw; i += kConvThreads) k_s[i] = kflip[pl.koff + i];
+  for (int i = tid; i < srows * spitch; i += kConvThreads) {
+    int ry = i / spitch, c = i - ry * spitch;
+    int y = ty0 - h + ry, xp = tx0 - h + c;
+    float v = 0.f;
+    if (y >= 0 && y < cy && xp >= 0 && xp < pitch) v = image[(size_t)y * pitch + xp];
+    in_s[i] = v;
+  }
+  __syncthreads();
+
+  const int tx = tid & 7, ly = tid >> 3;
+  const int xa = 4 * tx, xb = 32 + 4 * tx;
+  double acc_a[4] = {0, 0, 0, 0}, acc_b[4] = {0, 0, 0, 0};
+  for (int i = 0; i < nrow; ++i) {
+    const float* r = in_s + (size_t)(ly + i) * spitch;
+    const float* kr = k_s + (size_t)i * kw;
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 wa0 = *reinterpret_cast<const float4*>(r + xa);
+    float4 wb0 = *reinterpret_cast<const float4*>(r + xb);
+    for (int j0 = 0; j0 < kw; j0 += 4) {
+      float4 wa1 = *reinterpret_cast<const float4*>(r + xa + j0 + 4);
+      float4 wb1 = *reinterpret_cast<const float4*>(r + xb + j0 + 4);
+      float4 kk = *reinterpret_cast<const float4*>(kr + j0);
+      float wina[8] = {wa0.x, wa0.y, wa0.z, wa0.w, wa1.x, wa1.y, wa1.z, wa1.w};
+      float winb[8] = {wb0.x, wb0.y, wb0.z, wb0.w, wb1.x, wb1.y, wb1.z, wb1.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a[k] = fmaf(kk.x, wina[k], a[k]);
+        a[k] = fmaf(kk.y, wina[k + 1], a[k]);
+        a[k] = fmaf(kk.z, wina[k + 2], a[k]);
+        a[k] = fmaf(kk.w, wina[k + 3], a[k]);
+        b[k] = fmaf(kk.x, winb[k], b[k]);
+        b[k] = fmaf(kk.y, winb[k + 1], b[k]);
+        b[k] = fmaf(kk.z, winb[k + 2], b[k]);
+        b[k] = fmaf(kk.w, winb[k + 3], b[k]);
+      }
+      wa0 = wa1;
+      wb0 = wb1;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      acc_a[k] += (double)a[k];
+      acc_b[k] += (double)b[k];
+    }
+  }
+  const int y = ty0 + ly;
+  if (y < cy) {
+    float* o = out + blockIdx.z * plane_stride + (size_t)y * pitch;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int xpa = tx0 + xa + k, xpb = tx0 + xb + k;
+      if (xpa < pitch) o[xpa] = (xpa >= xpad && xpa < xpad + cx) ? (float)acc_a[k] : 0.f;
+      if (xpb < pitch) o[xpb] = (xpb >= xpad && xpb < xpad + cx) ? (float)acc_b[k] : 0.f;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K0: SpectralModel.integral over the true-energy bins (modeling/models/spectral.py:353-371)
+// ----------------------------------------------------------------------------------------------
+struct FluxJob {
+  int type;      // gpy_spectral_type
+  int n_bins;
+  int n_nodes;
+  int pad_;
+  double p[5];          // parameter values in the reference class order
+  const double* edges;  // [n_bins + 1]
+  const double* nodes;  // [n_bins, n_nodes]
+  double* out;          // [n_bins]
+};
+
+__device__ __forceinline__ bool isclose0(double val) { return fabs(val) <= 1e-8; }  // np.isclose(val, 0)
+
+// PowerLawSpectralModel.evaluate_integral (spectral.py:1039-1067)
+__device__ __forceinline__ double pl_integral(double emin, double emax, double index, double amplitude,
+                                              double reference) {
+  double val = -1.0 * index + 1.0;
+  if (isclose0(val)) return amplitude * reference * log(emax / emin);
+  double prefactor = amplitude * reference / val;
+  double upper = pow(emax / reference, val);
+  double lower = pow(emin / reference, val);
+  return prefactor * (upper - lower);
+}
+
+__device__ __forceinline__ double spectral_eval(int type, const double* p, double e) {
+  if (type == 0) return p[1] * pow(e / p[2], -p[0]);  // PowerLaw.evaluate (spectral.py:1034-1037)
+  if (type == 1) {  // LogParabola.evaluate (spectral.py:1903-1908): amplitude, reference, alpha, beta
+    double xx = e / p[1];
+    double exponent = -p[2] - p[3] * log(xx);
+    return p[0] * pow(xx, exponent);
+  }
+  // ExpCutoffPowerLaw.evaluate (spectral.py:1561-1567): index, amplitude, reference, lambda_, alpha
+  double pwl = p[1] * pow(e / p[2], -p[0]);
+  double cutoff = exp(-pow(e * p[3], p[4]));
+  return pwl * cutoff;
+}
+
+__device__ __forceinline__ double log_scale(double v) {
+  // LogScale._scale: np.clip(values, tiny, inf) then log (utils/interpolation.py:207-210); NaN stays NaN
+  const double tiny = 2.2250738585072014e-308;
+  if (v < tiny) v = tiny;
+  return log(v);
+}
+
+__global__ void spectral_flux_kernel(const FluxJob* __restrict__ jobs) {
+  const FluxJob job = jobs[blockIdx.x];
+  for (int t = threadIdx.x; t < job.n_bins; t += blockDim.x) {
+    double emin = job.edges[t], emax = job.edges[t + 1];
+    double result;
+    if (job.type == 0) {
+      result = pl_integral(emin, emax, job.p[0], job.p[1], job.p[2]);
+    } else {
+      // integrate_spectrum + trapz_loglog (spectral.py:103-164, utils/integrate.py:8-49)
+      const double* nd = job.nodes + (size_t)t * job.n_nodes;
+      double e0 = nd[0], y0 = spectral_eval(job.type, job.p, e0);
+      result = 0.0;
+      for (int k = 1; k < job.n_nodes; ++k) {
+        double e1 = nd[k], y1 = spectral_eval(job.type, job.p, e1);
+        double index = -log_scale(y0 / y1) / log_scale(e0 / e1);
+        if (isnan(index)) index = INFINITY;
+        result += pl_integral(e0, e1, index, y0, e0);
+        e0 = e1;
+        y0 = y1;
+      }
+    }
+    job.out[t] = result;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K3 + K4 fused: apply_exposure -> apply_edisp -> stack -> + background -> clip -> masked Cash
+//   (datasets/evaluator.py:346-377, datasets/utils.py:66-84, maps/wcs/ndmap.py:1138-1181,
+//    datasets/map.py:775-822, stats/fit_statistics.py:281-293, fit_statistics_cython.pyx:55-85)
+// ----------------------------------------------------------------------------------------------
+struct DatasetDev {
+  int nx, ny, nT, nR;
+  int nRp;        // nR rounded up to a multiple of 8
+  int n_groups;   // edisp matrices: 0 = dataset edisp, 1 = diagonal response
+  int tile_begin, n_tiles;
+  long long P;    // ny * nx
+  const float* exposure;    // [nT, P]
+  const float* background;  // [nR, P] or null
+  const float* counts;      // [nR, P] or null
+  const uint8_t* mask;      // [nR, P] or null
+  const double* edisp;      // [n_groups, nT, nRp] zero padded
+  const int* band;          // [n_groups, nRp / 8, 2] first / last+1 true bin with non-zero pdf per reco chunk
+  const double* ecenter;    // [nR]
+};
+
+struct InstDev {  // one source in one parameter vector
+  int x0, y0, cx, cy;  // evaluator cutout in parent pixels
+  int x0a, pitch;      // slot column origin (x0 rounded down to a multiple of 4) and row pitch
+  int planes;          // nT, or 1 when the PSF is not applied (broadcast over energy)
+  int group;           // edisp group
+  int flux_off;        // offset of F[nT] in the flux buffer
+  int pad_;
+  const float* conv;   // [planes, cy, pitch]
+};
+
+struct EvalDev {  // one (dataset, parameter vector)
+  int inst_begin, inst_count;
+  int bkg_enabled, pad_;
+  double bkg_norm, bkg_tilt, bkg_ref;
+};
+
+struct FoldParams {
+  const DatasetDev* ds;
+  const int* tile_ds;       // dataset index of every tile
+  const EvalDev* evals;     // [n_datasets * B], index d * B + b
+  const InstDev* insts;
+  const double* flux;
+  double* partials;         // [B, n_tiles]
+  double* npred_out;        // [nR, P] or null (single dataset, B == 1)
+  int B, n_tiles, n_datasets;
+  int include_background;   // add background model and clip at 0 (MapDataset.npred) or signal only
+  int max_inst;             // capacity of the per-block overlap list
+  int pad_;
+  double log_trunc;         // log((double)(float)1e-25): Cython narrows the constant to C float
+};
+
+constexpr int kFoldTPX = 128;      // pixels per tile
+constexpr int kFoldThreads = 128;
+
+__device__ __forceinline__ double block_sum_128(double v, double* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < kFoldThreads / 32; ++w) r += scratch[w];
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(kFoldThreads) fold_cash_kernel(const FoldParams P) {
+  extern __shared__ __align__(16) double fold_smem[];
+  const int b = blockIdx.x % P.B;
+  const int tile = blockIdx.x / P.B;
+  const int d = P.tile_ds[tile];
+  const DatasetDev D = P.ds[d];
+  const EvalDev ev = P.evals[(size_t)d * P.B + b];
+  const int nT = D.nT, nR = D.nR, nRp = D.nRp, G = D.n_groups;
+  const long long p0 = (long long)(tile - D.tile_begin) * kFoldTPX;
+  const int npx = (int)min((long long)kFoldTPX, D.P - p0);
+  const int tid = threadIdx.x;
+
+  double* vs = fold_smem;                                   // [G][nT][TPX]
+  double* pdf_s = vs + (size_t)G * nT * kFoldTPX;           // [G][nT][nRp]
+  double* bkgfac = pdf_s + (size_t)G * nT * nRp;            // [nRp]
+  double* scratch = bkgfac + nRp;                           // [8]
+  int* list = reinterpret_cast<int*>(scratch + 8);          // [max_inst]
+  __shared__ int n_list;
+
+  for (int i = tid; i < G * nT * nRp; i += kFoldThreads) pdf_s[i] = D.edisp[i];
+  if (tid < nRp) {
+    double fac = 1.0;
+    if (ev.bkg_enabled && tid < nR)  // PowerLawNormSpectralModel.evaluate (spectral.py:1159-1162)
+      fac = ev.bkg_norm * pow(D.ecenter[tid] / ev.bkg_ref, -ev.bkg_tilt);
+    bkgfac[tid] = fac;
+  }
+  // rows covered by this tile -> instances whose cutout can overlap it
+  const int y_first = (int)(p0 / D.nx), y_last = (int)((p0 + npx - 1) / D.nx);
+  if (tid == 0) {
+    int n = 0;
+    for (int i = 0; i < ev.inst_count; ++i) {
+      const InstDev& in = P.insts[ev.inst_begin + i];
+      if (in.y0 <= y_last && in.y0 + in.cy > y_first) list[n++] = ev.inst_begin + i;
+    }
+    n_list = n;
+  }
+  __syncthreads();
+  const int nl = n_list;
+
+  // ---- phase 1: v[g][t][p] = 1e4 * exposure[t,p] * sum_s F_s[t] * conv_s[t,p]  (fp64) ----
+  const bool vec4 = (D.nx % 4) == 0;
+  if (vec4) {
+    const int q = tid & 31, slot = tid >> 5;  // 32 pixel quads x 4 energy slots
+    const long long pq = p0 + 4 * q;
+    const bool live = 4 * q < npx;            // npx is a multiple of 4 when nx % 4 == 0
+    const int y = live ? (int)(pq / D.nx) : 0, x = live ? (int)(pq - (long long)y * D.nx) : 0;
+    for (int g = 0; g < G; ++g) {
+      for (int t = slot; t < nT; t += 4) {
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        if (live) {
+          for (int l = 0; l < nl; ++l) {
+            const InstDev in = P.insts[list[l]];
+            if (in.group != g) continue;
+            int ly = y - in.y0, lx = x - in.x0a;
+            if (ly < 0 || ly >= in.cy || lx < 0 || lx + 3 >= in.pitch) continue;
+            int tt = in.planes == 1 ? 0 : t;
+            const float4 c = __ldg(reinterpret_cast<const float4*>(
+                in.conv + ((size_t)tt * in.cy + ly) * in.pitch + lx));
+            const double F = P.flux[in.flux_off + t];
+            double a0 = F * (double)c.x, a1 = F * (double)c.y, a2 = F * (double)c.z, a3 = F * (double)c.w;
+            // WcsNDMap.stack(nan_to_num=True): non-finite source values do not enter the sum
+            s0 += isfinite(a0) ? a0 : 0.0;
+            s1 += isfinite(a1) ? a1 : 0.0;
+            s2 += isfinite(a2) ? a2 : 0.0;
+            s3 += isfinite(a3) ? a3 : 0.0;
+          }
+          const float4 e = __ldg(reinterpret_cast<const float4*>(D.exposure + (size_t)t * D.P + pq));
+          s0 = (s0 * (double)e.x) * 1e4;
+          s1 = (s1 * (double)e.y) * 1e4;
+          s2 = (s2 * (double)e.z) * 1e4;
+          s3 = (s3 * (double)e.w) * 1e4;
+        }
+        double* dst = vs + ((size_t)g * nT + t) * kFoldTPX + 4 * q;
+        *reinterpret_cast<double2*>(dst) = make_double2(s0, s1);
+        *reinterpret_cast<double2*>(dst + 2) = make_double2(s2, s3);
+      }
+    }
+  } else {
+    const long long p = p0 + tid;
+    const bool live = tid < npx;
+    const int y = live ? (int)(p / D.nx) : 0, x = live ? (int)(p - (long long)y * D.nx) : 0;
+    for (int g = 0; g < G; ++g) {
+      for (int t = 0; t < nT; ++t) {
+        double s = 0.0;
+        if (live) {
+          for (int l = 0; l < nl; ++l) {
+            const InstDev in = P.insts[list[l]];
+            if (in.group != g) continue;
+            int ly = y - in.y0, lx = x - in.x0;
+            if (ly < 0 || ly >= in.cy || lx < 0 || lx >= in.cx) continue;
+            int tt = in.planes == 1 ? 0 : t;
+            float c = __ldg(in.conv + ((size_t)tt * in.cy + ly) * in.pitch + (x - in.x0a));
+            double a = P.flux[in.flux_off + t] * (double)c;
+            s += isfinite(a) ? a : 0.0;
+          }
+          s = (s * (double)__ldg(D.exposure + (size_t)t * D.P + p)) * 1e4;
+        }
+        vs[((size_t)g * nT + t) * kFoldTPX + tid] = s;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: edisp contraction on reco chunks of 8, two pixels per thread; Cash epilogue ----
+  const int pp = tid & 63, cpar = tid >> 6;
+  const int nchunks = nRp >> 3;
+  double stat = 0.0;
+  for (int c = cpar; c < nchunks; c += 2) {
+    double acc0[8], acc1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.0;
+    for (int g = 0; g < G; ++g) {
+      const int tlo = D.band[(g * nchunks + c) * 2], thi = D.band[(g * nchunks + c) * 2 + 1];
+      const double* vrow = vs + (size_t)g * nT * kFoldTPX + 2 * pp;
+      const double* prow = pdf_s + (size_t)g * nT * nRp + 8 * c;
+      for (int t = tlo; t < thi; ++t) {
+        const double2 v = *reinterpret_cast<const double2*>(vrow + (size_t)t * kFoldTPX);
+        const double2 m0 = *reinterpret_cast<const double2*>(prow + (size_t)t * nRp);
+        const double2 m1 = *reinterpret_cast<const double2*>(prow + (size_t)t * nRp + 2);
+        const double2 m2 = *reinterpret_cast<const double2*>(prow + (size_t)t * nRp + 4);
+        const double2 m3 = *reinterpret_cast<const double2*>(prow + (size_t)t * nRp + 6);
+        const double m[8] = {m0.x, m0.y, m1.x, m1.y, m2.x, m2.y, m3.x, m3.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc0[j] = fma(v.x, m[j], acc0[j]);
+          acc1[j] = fma(v.y, m[j], acc1[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = 8 * c + j;
+      if (r >= nR) break;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int lp = 2 * pp + k;
+        if (lp >= npx) continue;
+        const size_t idx = (size_t)r * D.P + p0 + lp;
+        double mu = k == 0 ? acc0[j] : acc1[j];
+        if (P.include_background) {
+          if (D.background) mu += (double)__ldg(D.background + idx) * bkgfac[r];
+          if (mu < 0.0) mu = 0.0;  // npred_total.data[npred_total.data < 0.0] = 0 (map.py:787)
+        }
+        if (P.npred_out) P.npred_out[idx] = mu;
+        if (D.counts) {
+          const bool m = D.mask ? (__ldg(D.mask + idx) != 0) : true;
+          if (m) {
+            const double n = (double)__ldg(D.counts + idx);
+            double npr, lognpr = 0.0;
+            if (mu > kTrunc) {
+              npr = mu;
+              if (n > 0.0) lognpr = log(mu);
+            } else {
+              npr = kTrunc;
+              lognpr = P.log_trunc;
+            }
+            stat += npr;
+            if (n > 0.0) stat -= n * lognpr;
+          }
+        }
+      }
+    }
+  }
+  double total = block_sum_128(stat, scratch);
+  if (tid == 0) P.partials[(size_t)b * P.n_tiles + tile] = total;
+}
+
+// Second stage: stat[b, d] = 2 * sum of the tile partials of dataset d, fixed summation order.
+__global__ void __launch_bounds__(256)
+reduce_stat_kernel(const double* __restrict__ partials, const DatasetDev* __restrict__ ds, int n_tiles,
+                   int n_datasets, double* __restrict__ stat) {
+  __shared__ double sm[256];
+  const int b = blockIdx.x, d = blockIdx.y;
+  const int begin = ds[d].tile_begin, n = ds[d].n_tiles;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += partials[(size_t)b * n_tiles + begin + i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) stat[(size_t)b * n_datasets + d] = 2.0 * sm[0];
+}
+
+// ----------------------------------------------------------------------------------------------
+// Stand-alone Cash sums (stats/fit_statistics_cython.pyx:17-85) over already-masked 1-D fp64 arrays.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cash_sum_kernel(const double* __restrict__ counts, const double* __restrict__ npred,
+                const double* __restrict__ weight, long long n, double log_trunc,
+                double* __restrict__ partials) {
+  __shared__ double sm[256];
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    double npr = npred[i], c = counts[i], lognpr = 0.0;
+    if (npr > kTrunc) {
+      if (c > 0.0) lognpr = log(npr);
+    } else {
+      npr = kTrunc;
+      lognpr = log_trunc;
+    }
+    if (weight) {
+      double w = weight[i];
+      if (w > 0.0) {
+        s += w * npr;
+        if (c > 0.0) s -= w * c * lognpr;
+      }
+    } else {
+      s += npr;
+      if (c > 0.0) s -= c * lognpr;
+    }
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = sm[0];
+}
+
+__global__ void __launch_bounds__(256)
+final_sum_kernel(const double* __restrict__ partials, int n, double scale, double* __restrict__ out) {
+  __shared__ double sm[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += partials[i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = scale * sm[0];
+}
+
+}  // namespace gpy

@@ -1,0 +1,178 @@
+/*
+ * gpy_b200.h -- C ABI of libgpy_b200.so: gammapy's forward-fold likelihood hot path on B200 (sm_100a).
+ *
+ * One shared library, plain pointers and sizes, no torch / numpy / astropy types.  Every entry point
+ * names the reference interface (path relative to /root/reference/gammapy) it stands in for.  The
+ * reference is pure Python (+ one Cython file), so the binding a maintainer would add is a ctypes
+ * stub -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - units: angles deg, energies TeV, exposure m2 s, flux cm-2 s-1 TeV-1 (npred = flux*exposure*1e4,
+ *     datasets/evaluator.py:346-352).
+ *   - cubes are C-order (energy, lat(y), lon(x)), x fastest, as numpy / gammapy Map.data.
+ *   - "DEVICE" pointers are CUDA device memory owned by the caller (e.g. torch tensors) and must
+ *     outlive the dataset handle; "HOST" pointers are read during the call only.
+ *   - image WCS: CAR projection about the equator (crval latitude 0), square pixels
+ *     (maps/wcs/geom.py:294-417: crpix = (n+1)/2, cdelt = (-binsz, +binsz)).
+ *   - every function returns 0 on success, a negative gpy_status otherwise; gpy_last_error() gives
+ *     the message of the last failure on the calling thread.  There is no CPU fallback: without a
+ *     CUDA device gpy_init fails with GPY_ERR_CUDA.
+ *   - calls on one context are not thread-safe (the reference's caller is the single-threaded Minuit
+ *     callback, modeling/iminuit.py:23-31).
+ */
+#ifndef GPY_B200_H
+#define GPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPY_ABI_VERSION 1
+
+typedef enum {
+  GPY_OK = 0,
+  GPY_ERR_INVALID = -1,     /* bad argument / unsupported configuration (Python side raises ValueError) */
+  GPY_ERR_CUDA = -2,        /* CUDA runtime failure, no device, launch error */
+  GPY_ERR_UNSUPPORTED = -3  /* valid in the reference but outside this path's scope */
+} gpy_status;
+
+/* modeling/models/spatial.py: PointSpatialModel :558, GaussianSpatialModel :639, DiskSpatialModel :898 */
+typedef enum { GPY_SPATIAL_POINT = 0, GPY_SPATIAL_GAUSS = 1, GPY_SPATIAL_DISK = 2 } gpy_spatial_type;
+/* modeling/models/spectral.py: PowerLaw :1002, LogParabola :1865, ExpCutoffPowerLaw :1520 */
+typedef enum { GPY_SPECTRAL_PL = 0, GPY_SPECTRAL_LP = 1, GPY_SPECTRAL_ECPL = 2 } gpy_spectral_type;
+
+typedef struct gpy_context gpy_context_t;
+typedef struct gpy_dataset gpy_dataset_t;
+
+/* WcsGeom of the counts cube (maps/wcs/geom.py:294-417) reduced to what the path reads. */
+typedef struct {
+  int32_t nx, ny;           /* image size in pixels (lon, lat) */
+  int32_t n_true, n_reco;   /* energy_true / energy bins */
+  double binsz;             /* deg */
+  double crval_lon;         /* deg; crval latitude must be 0 */
+  double crpix_x, crpix_y;  /* FITS 1-based reference pixel */
+} gpy_geom_desc;
+
+/* The MapDataset attributes the path consumes (datasets/map.py:410; §8 a4-a6, a17 of SURVEY.md). */
+typedef struct {
+  gpy_geom_desc geom;
+  const double* energy_true_edges;   /* HOST [n_true+1] */
+  const double* energy_reco_center;  /* HOST [n_reco]; MapAxis.center of the reco axis (FoVBackgroundModel.evaluate_geom) */
+  const float* exposure;             /* DEVICE [n_true, ny, nx] */
+  const float* background;           /* DEVICE [n_reco, ny, nx] or NULL */
+  const float* counts;               /* DEVICE [n_reco, ny, nx] or NULL (required for stat) */
+  const uint8_t* mask;               /* DEVICE [n_reco, ny, nx] or NULL: mask_safe*mask_fit (datasets/core.py:73-81) */
+  const uint8_t* mask_image;         /* HOST [ny, nx] or NULL (= all true): MapDataset.mask_image (datasets/map.py:1040-1048) */
+  const float* psf_kernel;           /* HOST [n_true, psf_k, psf_k] float32, PSFKernel.data planes normalised (irf/psf/kernel.py:70-80), or NULL */
+  int32_t psf_k;                     /* odd kernel side */
+  const double* edisp;               /* HOST [n_true, n_reco] EDispKernel.pdf_matrix (irf/edisp/kernel.py:71-77) */
+  const double* edisp_diagonal;      /* HOST [n_true, n_reco] diagonal response (evaluator.py:245-250) or NULL */
+  const double* nodes;               /* HOST [n_true, n_nodes] geomspace nodes of integrate_spectrum (spectral.py:132-134) */
+  int32_t n_nodes;                   /* int(max(100*log10(e_hi/e_lo), 2)) evaluated by the caller with numpy */
+} gpy_dataset_desc;
+
+/* One SkyModel: where its parameters sit in the parameter vector handed to gpy_stat_sum / gpy_npred.
+ * Parameter order follows the reference classes:
+ *   point: lon_0, lat_0            gauss: lon_0, lat_0, sigma, e, phi     disk: lon_0, lat_0, r_0, e, phi, edge_width
+ *   pl: index, amplitude, reference      lp: amplitude, reference, alpha, beta
+ *   ecpl: index, amplitude, reference, lambda_, alpha
+ */
+typedef struct {
+  int32_t spatial_type;     /* gpy_spatial_type */
+  int32_t spectral_type;    /* gpy_spectral_type */
+  int32_t spatial_par[6];   /* column of each spatial parameter in params[b, :] (unused entries -1) */
+  int32_t spectral_par[5];  /* column of each spectral parameter */
+  int32_t apply_psf;        /* SkyModel.apply_irf["psf"]   (modeling/models/cube.py) */
+  int32_t apply_edisp;      /* SkyModel.apply_irf["edisp"] : 0 -> diagonal response (evaluator.py:371-377) */
+} gpy_source_desc;
+
+/* FoVBackgroundModel with PowerLawNormSpectralModel (modeling/models/cube.py:622-756, spectral.py:1134-1162). */
+typedef struct {
+  int32_t enabled;          /* 0: npred_background = background (datasets/map.py:812-813) */
+  int32_t par_norm, par_tilt, par_reference;
+} gpy_background_desc;
+
+/* Evaluator state of one source (MapEvaluator: datasets/evaluator.py:174-243), for inspection / tests. */
+typedef struct {
+  int32_t initialised;      /* update() has run */
+  int32_t contributes;      /* SkyModel.contributes(mask, margin=psf_width) */
+  int32_t x0, y0, cx, cy;   /* exposure cutout in parent pixels (parent slices of _cutout_view) */
+  int32_t oversampling;     /* factor used by the last integrate_geom */
+  int32_t n_spatial_evals;  /* how often spatial + PSF were recomputed (cache behaviour, evaluator.py:282-286) */
+} gpy_source_state;
+
+const char* gpy_last_error(void);
+int gpy_abi_version(void);
+
+/* Create a context on CUDA device `device`; `stream` is a cudaStream_t (NULL: the library makes its own). */
+int gpy_init(int device, void* stream, gpy_context_t** ctx);
+int gpy_finalize(gpy_context_t* ctx);
+/* Number of this library's kernel launches since gpy_init (bench.py "gpu_launches"). */
+int64_t gpy_launch_count(const gpy_context_t* ctx);
+
+/* MapDataset.__init__ side: register the resident cubes, upload the static IRF kernels. */
+int gpy_dataset_create(gpy_context_t* ctx, const gpy_dataset_desc* desc, gpy_dataset_t** ds);
+int gpy_dataset_destroy(gpy_dataset_t* ds);
+/* Replace the counts cube pointer (MapDataset.fake overwrites counts, datasets/map.py:1538-1554). */
+int gpy_dataset_set_counts(gpy_dataset_t* ds, const float* counts_device);
+/* MapDataset.models setter (datasets/map.py:674-694): one evaluator per SkyModel, caches reset. */
+int gpy_dataset_set_models(gpy_dataset_t* ds, const gpy_source_desc* sources, int32_t n_sources,
+                           const gpy_background_desc* background);
+int gpy_dataset_source_state(const gpy_dataset_t* ds, int32_t source, gpy_source_state* out);
+
+/* Datasets.stat_sum (datasets/core.py:264-277) for a batch of parameter vectors.
+ *   params  HOST [n_vec, n_par] parameter VALUES (not factors); shared by all datasets.
+ *   stat    HOST [n_vec]        sum over datasets (summed in dataset order, as the Python loop does)
+ *   stat_per_dataset HOST [n_vec, n_datasets] or NULL
+ * n_vec == 1 advances the evaluators' cache state exactly like one reference evaluation
+ * (MapEvaluator.needs_update / update / parameters_spatial_changed).  n_vec > 1 evaluates each
+ * vector from the current state without mutating it (profile scans, finite-difference gradients).
+ */
+int gpy_stat_sum(gpy_context_t* ctx, gpy_dataset_t* const* datasets, int32_t n_datasets,
+                 const double* params, int32_t n_vec, int32_t n_par, double* stat,
+                 double* stat_per_dataset);
+
+/* Same evaluation, leaving the per-(vector, dataset) stats on the device:
+ *   stat_device DEVICE [n_vec, n_datasets] float64.  No host synchronisation: the caller owns the
+ *   stream order (e.g. an NCCL all-reduce of the buffer on the same stream). */
+int gpy_stat_sum_device(gpy_context_t* ctx, gpy_dataset_t* const* datasets, int32_t n_datasets,
+                        const double* params, int32_t n_vec, int32_t n_par, double* stat_device);
+
+/* MapDataset.npred (datasets/map.py:775-788) / npred_signal (:824-880) for one parameter vector.
+ *   source_enable HOST [n_sources] or NULL (all): npred_signal(model_names=...)
+ *   include_background: add npred_background (:790-813) and clip negatives to 0 (:787)
+ *   npred_device DEVICE [n_reco, ny, nx] float64
+ */
+int gpy_npred(gpy_context_t* ctx, gpy_dataset_t* ds, const double* params, int32_t n_par,
+              const uint8_t* source_enable, int32_t include_background, double* npred_device);
+
+/* Compiled-stat registry entries (utils/compilation.py:35-87; stats/fit_statistics_cython.pyx:17-85):
+ * HOST float64 arrays in, HOST scalar out.  cash_sum_compiled / weighted_cash_sum_compiled. */
+int gpy_cash_sum(gpy_context_t* ctx, const double* counts, const double* npred, int64_t n, double* out);
+int gpy_weighted_cash_sum(gpy_context_t* ctx, const double* counts, const double* npred,
+                          const double* weight, int64_t n, double* out);
+
+/* Single-stage entry points (the parity tests exercise each kernel through these).
+ * SpatialModel.integrate_geom on an image geometry (modeling/models/spatial.py:222-309, 609-631):
+ *   spatial_params HOST in the class order above; out HOST [ny, nx] float32 (the value the PSF
+ *   convolution consumes, maps/wcs/ndmap.py:984); oversampling: factor used. */
+int gpy_integrate_geom(gpy_context_t* ctx, const gpy_geom_desc* geom, int32_t spatial_type,
+                       const double* spatial_params, float* out, int32_t* oversampling);
+/* WcsNDMap.convolve(PSFKernel) of one image with n_planes kernels, mode "same" (maps/wcs/ndmap.py:920-1010):
+ *   image HOST [ny, nx] float32, kernel HOST [n_planes, k, k] float32, out HOST [n_planes, ny, nx] float32. */
+int gpy_psf_convolve(gpy_context_t* ctx, const float* image, int32_t ny, int32_t nx, const float* kernel,
+                     int32_t n_planes, int32_t k, float* out);
+/* SpectralModel.integral over bins (modeling/models/spectral.py:353-371, 103-164, 1039-1067):
+ *   edges HOST [n_bins+1], nodes HOST [n_bins, n_nodes], out HOST [n_bins]. */
+int gpy_spectral_integral(gpy_context_t* ctx, int32_t spectral_type, const double* spectral_params,
+                          const double* edges, int32_t n_bins, const double* nodes, int32_t n_nodes,
+                          double* out);
+/* WcsGeom.solid_angle (maps/wcs/geom.py:803-854): out HOST [ny, nx] float64 sr. */
+int gpy_solid_angle(gpy_context_t* ctx, const gpy_geom_desc* geom, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPY_B200_H */

@@ -1,0 +1,247 @@
+"""Oracle: WCS image geometry (CAR about the equator), spherical trig, cutouts.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Restates, float-for-float where the arithmetic is under /root/reference and
+from the published formulas where it lives in astropy/wcslib
+(astropy >=6.1.5,<8.0 per the reference's pyproject.toml:23-35):
+
+* ``WcsGeom.create``            maps/wcs/geom.py:294-417   (crpix=(n+1)/2, cdelt=(-binsz,+binsz))
+* ``WcsGeom.upsample``          maps/wcs/geom.py:766-779   (+ get_resampled_wcs: crpix'=(crpix-0.5)*f+0.5)
+* ``WcsGeom.solid_angle``       maps/wcs/geom.py:803-854   (planar-triangle formula on pixel corners)
+* ``WcsGeom.cutout``            maps/wcs/geom.py:886-930   (astropy Cutout2D / overlap_slices rule)
+* ``WcsGeom.cutout_slices``     maps/wcs/geom.py:168-193
+* ``WcsGeom.to_odd_npix``       maps/wcs/geom.py:1106-1138
+* ``round_up_to_odd``           utils/array.py:110
+* astropy ``angular_separation`` (Vincenty) and ``position_angle``.
+
+CAR with ``crval = (lon0, 0)`` is the plain linear map
+``lon = lon0 + cdelt_x (i + 1 - crpix_x)``, ``lat = cdelt_y (j + 1 - crpix_y)``
+(wcslib: native pole at delta_p = 90 deg reduces the spherical rotation to a
+longitude offset).  Off-equator CAR is an oblique projection and is refused.
+"""
+import numpy as np
+
+DEG = np.pi / 180.0  # astropy deg->rad factor 0.017453292519943295
+
+
+class NoOverlapError(ValueError):
+    """astropy.nddata.utils.NoOverlapError stand-in."""
+
+
+def angular_separation(lon1, lat1, lon2, lat2):
+    """Vincenty great-circle separation, all angles in radians (astropy.coordinates.angular_separation)."""
+    sdlon = np.sin(lon2 - lon1)
+    cdlon = np.cos(lon2 - lon1)
+    slat1 = np.sin(lat1)
+    slat2 = np.sin(lat2)
+    clat1 = np.cos(lat1)
+    clat2 = np.cos(lat2)
+    num1 = clat2 * sdlon
+    num2 = clat1 * slat2 - slat1 * clat2 * cdlon
+    denominator = slat1 * slat2 + clat1 * clat2 * cdlon
+    return np.arctan2(np.hypot(num1, num2), denominator)
+
+
+def position_angle(lon1, lat1, lon2, lat2):
+    """Position angle (radians, East of North) from point 1 to point 2 (astropy.coordinates.position_angle)."""
+    deltalon = lon2 - lon1
+    colat = np.cos(lat2)
+    x = np.sin(lat2) * np.cos(lat1) - colat * np.sin(lat1) * np.cos(deltalon)
+    y = np.sin(deltalon) * colat
+    return np.arctan2(y, x)
+
+
+def round_up_to_odd(f):
+    """utils/array.py:110."""
+    return (np.ceil(f) // 2 * 2 + 1).astype(int)
+
+
+def overlap_slices(large_shape, small_shape, position, mode="trim"):
+    """astropy.nddata.utils.overlap_slices for modes 'trim' and 'partial' (2-D, (y, x) order)."""
+    if any(not np.isfinite(p) for p in position):
+        raise ValueError("Input position contains invalid values (NaNs or infs).")
+    edges_min = [int(np.ceil(pos - (s / 2.0))) for pos, s in zip(position, small_shape)]
+    edges_max = [int(np.ceil(pos + (s / 2.0))) for pos, s in zip(position, small_shape)]
+    for e_max in edges_max:
+        if e_max <= 0:
+            raise NoOverlapError("Arrays do not overlap.")
+    for e_min, large in zip(edges_min, large_shape):
+        if e_min >= large:
+            raise NoOverlapError("Arrays do not overlap.")
+    slices_large = tuple(
+        slice(max(0, e_min), min(large, e_max))
+        for e_min, e_max, large in zip(edges_min, edges_max, large_shape)
+    )
+    if mode == "trim":
+        slices_small = tuple(slice(0, s.stop - s.start) for s in slices_large)
+    else:
+        slices_small = tuple(
+            slice(max(0, -e_min), min(large - e_min, e_max - e_min))
+            for e_min, e_max, large in zip(edges_min, edges_max, large_shape)
+        )
+    return slices_large, slices_small
+
+
+class ImageGeom:
+    """2-D CAR WCS image geometry; (nx, ny) pixels of ``binsz`` deg, 0-based pixel coords."""
+
+    def __init__(self, nx, ny, binsz, crval_lon, crpix_x, crpix_y, crval_lat=0.0):
+        if crval_lat != 0.0:
+            raise NotImplementedError("oracle: CAR restated only for crval latitude 0 (oblique otherwise)")
+        self.nx = int(nx)
+        self.ny = int(ny)
+        self.binsz = float(binsz)
+        self.crval_lon = float(crval_lon)
+        self.crval_lat = 0.0
+        self.crpix_x = float(crpix_x)
+        self.crpix_y = float(crpix_y)
+
+    # -- construction ---------------------------------------------------------------------
+    @classmethod
+    def create(cls, skydir=(0.0, 0.0), binsz=0.5, width=None, npix=None):
+        """maps/wcs/geom.py:294-417 (square pixels only)."""
+        if npix is None:
+            if not isinstance(width, (tuple, list)):
+                width = (width, width)
+            npix = (
+                int(np.rint(float(width[0]) / binsz)),
+                int(np.rint(float(width[1]) / binsz)),
+            )
+        elif not isinstance(npix, (tuple, list)):
+            npix = (int(npix), int(npix))
+        nx, ny = int(npix[0]), int(npix[1])
+        return cls(nx, ny, binsz, skydir[0], (nx + 1) / 2.0, (ny + 1) / 2.0, skydir[1])
+
+    def copy(self, **kw):
+        d = dict(nx=self.nx, ny=self.ny, binsz=self.binsz, crval_lon=self.crval_lon,
+                 crpix_x=self.crpix_x, crpix_y=self.crpix_y)
+        d.update(kw)
+        return ImageGeom(**d)
+
+    @property
+    def data_shape(self):
+        return (self.ny, self.nx)
+
+    @property
+    def width(self):
+        """maps/wcs/geom.py:223-227: cdelt * npix (lon, lat) in deg."""
+        return (self.binsz * self.nx, self.binsz * self.ny)
+
+    @property
+    def pixel_scale(self):
+        """np.max(pixel_scales) – proj_plane_pixel_scales = |cdelt| for a diagonal PC matrix."""
+        return self.binsz
+
+    @property
+    def center_pix(self):
+        return ((self.nx - 1) / 2.0, (self.ny - 1) / 2.0)
+
+    @property
+    def center_skydir(self):
+        lon, lat = self.pix_to_world(*self.center_pix)
+        return float(lon), float(lat)
+
+    # -- transforms ------------------------------------------------------------------------
+    def pix_to_world(self, px, py):
+        """wcs_pix2world(px, py, 0) in deg."""
+        px = np.asarray(px, dtype=float)
+        py = np.asarray(py, dtype=float)
+        lon = self.crval_lon + (-self.binsz) * (px + 1.0 - self.crpix_x)
+        lat = self.binsz * (py + 1.0 - self.crpix_y)
+        lon, lat = np.broadcast_arrays(lon, lat)
+        return lon, lat
+
+    def world_to_pix(self, lon, lat):
+        """wcs_world2pix(lon, lat, 0); longitude difference wrapped into [-180, 180)."""
+        dlon = (np.asarray(lon, dtype=float) - self.crval_lon + 180.0) % 360.0 - 180.0
+        px = dlon / (-self.binsz) + self.crpix_x - 1.0
+        py = np.asarray(lat, dtype=float) / self.binsz + self.crpix_y - 1.0
+        return px, py
+
+    def get_coord(self, mode="center"):
+        """Pixel-centre (or edge) lon/lat grids in deg, shape (ny[+1], nx[+1])."""
+        if mode == "edges":
+            x = np.arange(-0.5, self.nx, dtype=float)
+            y = np.arange(-0.5, self.ny, dtype=float)
+        else:
+            x = np.arange(self.nx, dtype=float)
+            y = np.arange(self.ny, dtype=float)
+        return self.pix_to_world(x[np.newaxis, :], y[:, np.newaxis])
+
+    # -- derived geometries ------------------------------------------------------------------
+    def upsample(self, factor):
+        """maps/wcs/geom.py:766-771 + maps/wcs/geom.py get_resampled_wcs (crpix'=(crpix-0.5)*f+0.5, cdelt/=f)."""
+        return ImageGeom(
+            self.nx * factor, self.ny * factor, self.binsz / factor, self.crval_lon,
+            (self.crpix_x - 0.5) * factor + 0.5, (self.crpix_y - 0.5) * factor + 0.5,
+        )
+
+    def to_odd_npix(self, max_radius=None):
+        """maps/wcs/geom.py:1106-1138."""
+        if max_radius is None:
+            width = max(self.width)
+        else:
+            width = 2 * max_radius
+        width_npix = width / self.binsz
+        npix = int(round_up_to_odd(np.float64(width_npix)))
+        return ImageGeom.create(skydir=self.center_skydir, binsz=self.binsz, npix=npix)
+
+    def cutout_info(self, position, width, mode="trim", odd_npix=False, min_npix=1):
+        """maps/wcs/geom.py:886-930 -> (cutout geom, parent (y, x) slices).
+
+        ``position`` = (lon, lat) deg; ``width`` = float or (lon_width, lat_width) deg.
+        """
+        if not isinstance(width, (tuple, list, np.ndarray)):
+            width = (width, width)
+        width = np.array([float(width[0]), float(width[1])])
+        width_npix = np.clip(width / self.binsz, min_npix, None)
+        if odd_npix:
+            width_npix = round_up_to_odd(width_npix)
+        # Cutout2D: size in (ny, nx) order, shape = int(np.round(size))
+        shape = (int(np.round(width_npix[1])), int(np.round(width_npix[0])))
+        px, py = self.world_to_pix(position[0], position[1])
+        slices_large, _ = overlap_slices(self.data_shape, shape, (float(py), float(px)), mode=mode)
+        ys, xs = slices_large
+        geom = ImageGeom(
+            xs.stop - xs.start, ys.stop - ys.start, self.binsz, self.crval_lon,
+            self.crpix_x - xs.start, self.crpix_y - ys.start,
+        )
+        return geom, (ys, xs)
+
+    def cutout(self, position, width, **kw):
+        return self.cutout_info(position, width, **kw)[0]
+
+    def cutout_slices(self, parent, mode="partial"):
+        """maps/wcs/geom.py:168-193: slices of this (cutout) geom inside ``parent``."""
+        px, py = parent.world_to_pix(*self.center_skydir)
+        large, small = overlap_slices(parent.data_shape, self.data_shape, (float(py), float(px)), mode=mode)
+        return {"parent-slices": large, "cutout-slices": small}
+
+    # -- solid angle ---------------------------------------------------------------------------
+    def solid_angle(self):
+        """maps/wcs/geom.py:816-854, sr, shape (ny, nx)."""
+        lon, lat = self.get_coord(mode="edges")
+        lon = lon * DEG
+        lat = lat * DEG
+
+        def pt(sy, sx):
+            return lon[sy, sx], lat[sy, sx]
+
+        lo, hi = slice(None, -1), slice(1, None)
+        low_left = pt(lo, lo)
+        low_right = pt(hi, lo)
+        up_left = pt(lo, hi)
+        up_right = pt(hi, hi)
+
+        low = angular_separation(*low_left, *low_right)
+        left = angular_separation(*low_left, *up_left)
+        up = angular_separation(*up_left, *up_right)
+        right = angular_separation(*low_right, *up_right)
+
+        angle_low_right = position_angle(*low_right, *up_right) - position_angle(*low_right, *low_left)
+        angle_up_left = position_angle(*up_left, *up_right) - position_angle(*low_left, *up_left)
+
+        area_low_right = 0.5 * low * right * np.sin(angle_low_right)
+        area_up_left = 0.5 * up * left * np.sin(angle_up_left)
+        return np.abs(area_low_right + area_up_left)
