@@ -1,0 +1,391 @@
+"""``MapDataset`` / ``Datasets`` with the reference's API, evaluated on the GPU.
+
+Reference: datasets/map.py (MapDataset :410, create :947-1024, npred :775-880, fake :1538-1554),
+datasets/core.py (Dataset.mask :73-81, stat_sum_likelihood :88-90, Datasets.stat_sum :264-277).
+Maps are numpy on the host (user-facing, mutable); the first likelihood evaluation mirrors them into HBM.
+After an in-place edit of map data call ``reset_data_cache()`` (re-assigning an attribute is detected).
+"""
+import itertools
+
+import numpy as np
+
+from .irf import RAD_AXIS_DEFAULT, EDispKernelMap, PSFKernel, PSFMap
+from .maps import Map, MapAxis
+from .modeling.models import FoVBackgroundModel, Models, SkyModel
+from .modeling.parameter import Parameters
+from .utils import get_random_state
+
+__all__ = ["MapDataset", "Datasets"]
+
+_ds_counter = itertools.count()
+PSF_CONTAINMENT = 0.999  # datasets/evaluator.py:16
+PSF_MAX_RADIUS = None    # datasets/evaluator.py:15
+
+
+class MapDataset:
+    """Binned 3D dataset with Cash statistic (datasets/map.py:410)."""
+
+    tag = "MapDataset"
+    stat_type = "cash"
+
+    def __init__(self, models=None, counts=None, exposure=None, background=None, psf=None, edisp=None,
+                 mask_safe=None, mask_fit=None, gti=None, meta_table=None, name=None, meta=None, stat_type="cash"):
+        if stat_type != "cash":
+            raise NotImplementedError("only stat_type='cash' is on the accelerated path")
+        self._name = name if name is not None else f"dataset-{next(_ds_counter):04d}"
+        self._device = None
+        self._engine = None
+        self._models_version = 0
+        self._source_names = []
+        self._psf_kernel_cache = None
+        self._counts = counts
+        self._exposure = exposure
+        self._background = background
+        self._psf = psf
+        self._edisp = edisp
+        self._mask_safe = mask_safe
+        self._mask_fit = mask_fit
+        self.gti = gti
+        self.meta_table = meta_table
+        self.meta = meta
+        self._models = None
+        self.models = models
+
+    # -- map attributes: setters invalidate the device mirror ------------------------------------------------
+    def _invalidate(self, counts_only=False):
+        if self._device is not None and counts_only and self._counts is not None:
+            self._device.refresh_counts()
+            return
+        if self._device is not None:
+            self._device.close()
+        self._device = None
+        self._engine = None
+        self._psf_kernel_cache = None
+
+    name = property(lambda self: self._name)
+    counts = property(lambda self: self._counts)
+    exposure = property(lambda self: self._exposure)
+    background = property(lambda self: self._background)
+    psf = property(lambda self: self._psf)
+    edisp = property(lambda self: self._edisp)
+    mask_safe = property(lambda self: self._mask_safe)
+    mask_fit = property(lambda self: self._mask_fit)
+
+    @counts.setter
+    def counts(self, value):
+        had = self._counts is not None
+        self._counts = value
+        self._invalidate(counts_only=had and value is not None)
+
+    @exposure.setter
+    def exposure(self, value):
+        self._exposure = value
+        self._invalidate()
+
+    @background.setter
+    def background(self, value):
+        self._background = value
+        self._invalidate()
+
+    @psf.setter
+    def psf(self, value):
+        self._psf = value
+        self._invalidate()
+
+    @edisp.setter
+    def edisp(self, value):
+        self._edisp = value
+        self._invalidate()
+
+    @mask_safe.setter
+    def mask_safe(self, value):
+        self._mask_safe = value
+        self._invalidate()
+
+    @mask_fit.setter
+    def mask_fit(self, value):
+        self._mask_fit = value
+        self._invalidate()
+
+    def reset_data_cache(self):
+        """Drop the HBM mirror (and evaluator caches): call after editing map data in place."""
+        self._invalidate()
+
+    def _data_fingerprint(self):
+        maps = (self._counts, self._exposure, self._background, self._mask_safe, self._mask_fit)
+        return tuple((id(m), id(m.data), m.data.__array_interface__["data"][0]) if m is not None else None for m in maps)
+
+    @property
+    def _geom(self):
+        """Main analysis geometry (datasets/map.py:701-716)."""
+        for m in (self._counts, self._background, self._mask_safe, self._mask_fit):
+            if m is not None:
+                return m.geom
+        raise ValueError("Either 'counts', 'background', 'mask_fit' or 'mask_safe' must be defined.")
+
+    @property
+    def geoms(self):
+        out = {"geom": self._geom}
+        if self._exposure is not None:
+            out["geom_exposure"] = self._exposure.geom
+        return out
+
+    @property
+    def data_shape(self):
+        return self._geom.data_shape
+
+    @property
+    def mask(self):
+        """Combined fit and safe mask (datasets/core.py:73-81)."""
+        if self.mask_safe is not None and self.mask_fit is not None:
+            return self.mask_safe * self.mask_fit
+        if self.mask_fit is not None:
+            return self.mask_fit
+        return self.mask_safe
+
+    @property
+    def mask_image(self):
+        """datasets/map.py:1040-1048."""
+        mask = self.mask
+        if mask is None:
+            m = Map.from_geom(self._geom.to_image(), dtype=bool)
+            m.data |= True
+            return m
+        return mask.reduce_over_axes(func=np.logical_or)
+
+    # -- models ------------------------------------------------------------------------------------------------
+    @property
+    def models(self):
+        return self._models
+
+    @models.setter
+    def models(self, models):
+        """datasets/map.py:674-694: new evaluators, i.e. every cache is dropped."""
+        if models is not None:
+            models = Models(models).select(datasets_names=self.name)
+            for m in models:
+                if not isinstance(m, (SkyModel, FoVBackgroundModel)):
+                    raise NotImplementedError(f"{type(m).__name__} is outside the accelerated path")
+        self._models = models
+        self._models_version += 1
+        self._engine = None
+
+    @property
+    def background_model(self):
+        if self._models is None:
+            return None
+        for m in self._models:
+            if isinstance(m, FoVBackgroundModel):
+                return m
+        return None
+
+    @property
+    def parameters(self):
+        return self._models.parameters if self._models is not None else Parameters([])
+
+    # -- IRF reduction (static inputs of the path) ---------------------------------------------------------------
+    def _psf_kernel_for_evaluators(self):
+        """``PSFMap.get_psf_kernel(geom, containment=0.999)`` (evaluator.py:221-226) for a position-independent PSF."""
+        if self._psf is None:
+            return None
+        if isinstance(self._psf, PSFKernel):
+            return self._psf
+        if self._psf_kernel_cache is None:
+            self._psf_kernel_cache = self._psf.get_psf_kernel(
+                geom=self._exposure.geom, containment=PSF_CONTAINMENT, max_radius=PSF_MAX_RADIUS)
+        return self._psf_kernel_cache
+
+    # -- device side ----------------------------------------------------------------------------------------------
+    def _device_dataset(self, ctx):
+        from .engine import DeviceDataset
+
+        if self._exposure is None:
+            raise ValueError("MapDataset needs an exposure map to evaluate models")
+        if self._device is not None and self._device._uploaded != self._data_fingerprint():
+            self._invalidate()
+        if self._device is None:
+            self._device = DeviceDataset(self, ctx)
+        return self._device
+
+    def _get_engine(self):
+        from .engine import LikelihoodEngine
+
+        stale = self._engine is None or self._engine._signature != LikelihoodEngine.signature([self])
+        if not stale and self._device._uploaded != self._data_fingerprint():
+            stale = True
+        if stale:
+            self._engine = LikelihoodEngine([self])
+        return self._engine
+
+    # -- predictions ------------------------------------------------------------------------------------------------
+    def _npred_map(self, data):
+        return Map.from_geom(self._geom, data=data, dtype=float)
+
+    def npred(self):
+        """Total predicted counts (datasets/map.py:775-788)."""
+        return self._npred_map(self._get_engine().npred(0, include_background=True))
+
+    def npred_signal(self, model_names=None, stack=True):
+        """Predicted signal counts (datasets/map.py:824-880)."""
+        eng = self._get_engine()
+        names = self._source_names
+        if model_names is not None:
+            if isinstance(model_names, str):
+                model_names = [model_names]
+            for n in model_names:
+                if n not in names:
+                    raise KeyError(n)
+        if stack:
+            enable = None if model_names is None else [n in model_names for n in names]
+            return self._npred_map(eng.npred(0, source_enable=enable, include_background=False))
+        selected = names if model_names is None else model_names
+        cubes = []
+        for n in selected:
+            enable = [m == n for m in names]
+            cubes.append(eng.npred(0, source_enable=enable, include_background=False))
+        label_axis = MapAxis(np.arange(len(selected) + 1) - 0.5, name="models")
+        label_axis.labels = list(selected)
+        geom = self._geom.to_cube([label_axis])
+        return Map.from_geom(geom, data=np.array(cubes), dtype=float)
+
+    def npred_background(self):
+        """Predicted background counts (datasets/map.py:790-813) = npred with every source switched off."""
+        if self._background is None:
+            return None
+        eng = self._get_engine()
+        data = eng.npred(0, source_enable=[False] * len(self._source_names), include_background=True)
+        return self._npred_map(data)
+
+    def stat_sum_likelihood(self):
+        """Cash sum given the current parameters (datasets/core.py:88-90, fit_statistics.py:281-293)."""
+        if self._counts is None:
+            raise ValueError("MapDataset has no counts")
+        return self._get_engine().stat_sum()
+
+    stat_sum = stat_sum_likelihood
+
+    def stat_array(self):
+        """Per-bin Cash (stats/fit_statistics.py:29-79, 295-298) from the GPU npred cube."""
+        n_on = np.asarray(self._counts.data, dtype=float)
+        mu_on = self.npred().data
+        mu_on = np.where(mu_on <= 1e-25, 1e-25, mu_on)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return 2 * (mu_on - n_on * np.log(mu_on))
+
+    def fake(self, random_state="random-seed"):
+        """Poisson counts from npred with the legacy RandomState (datasets/map.py:1538-1554)."""
+        random_state = get_random_state(random_state)
+        npred = self.npred()
+        data = np.nan_to_num(npred.data, copy=True, nan=0.0, posinf=0.0, neginf=0.0)
+        npred.data = random_state.poisson(data).astype("float")
+        self.counts = npred
+
+    def evaluator_state(self, model_name):
+        """Cutout / cache state of one model's evaluator (MapEvaluator, datasets/evaluator.py:174-243)."""
+        eng = self._get_engine()
+        return eng.source_state(0, self._source_names.index(model_name))
+
+    # -- construction --------------------------------------------------------------------------------------------------
+    @classmethod
+    def create(cls, geom, energy_axis_true=None, migra_axis=None, rad_axis=None, binsz_irf=0.2,
+               reference_time="2000-01-01", name=None, meta_table=None, reco_psf=False, **kwargs):
+        """Zero-filled dataset (datasets/map.py:947-1024): float32 counts / background / exposure, boolean
+        mask_safe (all False, as the reference), Gaussian-free default IRFs: PSF none, edisp diagonal."""
+        if migra_axis is not None or reco_psf:
+            raise NotImplementedError("EDispMap (migra) and RecoPSFMap are outside the accelerated path")
+        energy_axis = geom.axes["energy"]
+        if energy_axis_true is None:
+            energy_axis_true = energy_axis.copy(name="energy_true")
+        if energy_axis_true.name != "energy_true":
+            raise ValueError("energy_axis_true must be named 'energy_true'")
+        geom_image = geom.to_image()
+        geom_true = geom_image.to_cube([energy_axis_true])
+        kwargs.setdefault("counts", Map.from_geom(geom, unit=""))
+        kwargs.setdefault("background", Map.from_geom(geom, unit=""))
+        kwargs.setdefault("exposure", Map.from_geom(geom_true, unit="m2 s"))
+        kwargs.setdefault("mask_safe", Map.from_geom(geom, unit="", dtype=bool))
+        kwargs.setdefault("edisp", EDispKernelMap.from_diagonal_response(energy_axis, energy_axis_true))
+        kwargs.setdefault("psf", None)
+        del rad_axis, binsz_irf, reference_time
+        return cls(name=name, meta_table=meta_table, **kwargs)
+
+    def __repr__(self):
+        return f"MapDataset(name={self.name!r}, geom={self._geom!r}, models={None if self._models is None else self._models.names})"
+
+
+class Datasets(list):
+    """Container of datasets with a joint likelihood (datasets/core.py:140)."""
+
+    def __init__(self, datasets=None):
+        if datasets is None:
+            datasets = []
+        elif isinstance(datasets, MapDataset):
+            datasets = [datasets]
+        super().__init__(datasets)
+        names = [d.name for d in self]
+        if len(set(names)) != len(names):
+            raise ValueError("Dataset names must be unique")
+        self._engine = None
+
+    @property
+    def names(self):
+        return [d.name for d in self]
+
+    @property
+    def models(self):
+        """Unique models of all datasets (datasets/core.py:179-199)."""
+        seen, out = set(), []
+        for d in self:
+            for m in (d.models or []):
+                if id(m) not in seen:
+                    seen.add(id(m))
+                    out.append(m)
+        return Models(out)
+
+    @models.setter
+    def models(self, models):
+        for d in self:
+            d.models = models
+
+    @property
+    def parameters(self):
+        return self.models.parameters.unique_parameters
+
+    def _get_engine(self):
+        from .engine import LikelihoodEngine
+
+        stale = self._engine is None or self._engine._signature != LikelihoodEngine.signature(self)
+        if not stale:
+            stale = any(d._device is None or d._device._uploaded != d._data_fingerprint() for d in self)
+        if stale:
+            self._engine = LikelihoodEngine(self)
+        return self._engine
+
+    def stat_sum(self):
+        """Joint fit statistic (datasets/core.py:264-277); no priors on this path."""
+        return self._get_engine().stat_sum()
+
+    def stat_sum_likelihood(self):
+        return self.stat_sum()
+
+    def stat_sum_batch(self, values, per_dataset=False):
+        """Joint statistic for a batch of full parameter vectors [B, n_par] in ONE launch
+        (what ``Fit.stat_profile`` / ``stat_surface`` loop over, modeling/fit.py:351-519)."""
+        return self._get_engine().stat_sum(values, per_dataset=per_dataset)
+
+    def parameter_vector(self):
+        eng = self._get_engine()
+        return eng.values(), eng.parameters
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            for d in self:
+                if d.name == key:
+                    return d
+            raise KeyError(key)
+        if isinstance(key, slice):
+            return Datasets(list.__getitem__(self, key))
+        return list.__getitem__(self, key)
+
+    def __repr__(self):
+        return f"Datasets({self.names})"

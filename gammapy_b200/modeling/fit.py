@@ -1,0 +1,357 @@
+"""``Fit`` front end driving the batched GPU likelihood (modeling/fit.py:147-519 in the reference).
+
+iminuit is not a dependency.  The optimiser is a variable-metric (BFGS) minimiser in the reference's
+*factor* space (modeling/iminuit.py:23-51: ``MinuitLikelihood.fcn(*factors)``, errordef 1, tol 0.1 ->
+EDM goal 2e-4) whose gradient (central differences) and line search are evaluated as ONE batched launch
+each through ``Datasets.stat_sum_batch``; ``covariance`` is a batched finite-difference Hesse.
+``stat_profile`` / ``stat_surface`` (fit.py:351-519) hand all scan points to a single launch.
+"""
+import itertools
+import logging
+
+import numpy as np
+
+log = logging.getLogger(__name__)
+
+__all__ = ["Fit", "FitResult", "OptimizeResult", "CovarianceResult"]
+
+
+class _Likelihood:
+    """modeling/likelihood.py + iminuit.py:23-31: factors in, joint stat out (single or batched)."""
+
+    def __init__(self, datasets):
+        from ..datasets import Datasets, MapDataset
+
+        if isinstance(datasets, MapDataset):
+            datasets = Datasets([datasets])
+        elif not isinstance(datasets, Datasets):
+            datasets = Datasets(list(datasets))
+        self.datasets = datasets
+        self.engine = datasets._get_engine()
+        self.free = [p for p in self.engine.parameters if not p.frozen]
+        self.cols = np.array([self.engine.parameters.index(p) for p in self.free], dtype=int)
+        self.n_calls = 0
+        self.n_launches = 0
+
+    @property
+    def factors(self):
+        return np.array([p.factor for p in self.free], dtype=float)
+
+    def values_from_factors(self, factors):
+        """[B, n_free] factors -> [B, n_par] values via Parameter.inverse_transform (parameter.py:564-574)."""
+        factors = np.atleast_2d(np.asarray(factors, dtype=float))
+        vals = np.tile(self.engine.values(), (factors.shape[0], 1))
+        for j, p in enumerate(self.free):
+            vals[:, self.cols[j]] = p.inverse_transform(factors[:, j])
+        return vals
+
+    def set_factors(self, factors):
+        for p, f in zip(self.free, factors):
+            p.factor = f
+
+    def fcn(self, factors):
+        self.set_factors(factors)
+        self.n_calls += 1
+        self.n_launches += 1
+        return self.engine.stat_sum()
+
+    def fcn_batch(self, factors, chunk=512):
+        vals = self.values_from_factors(factors)
+        out = np.empty(vals.shape[0], dtype=float)
+        for i in range(0, vals.shape[0], chunk):
+            out[i:i + chunk] = np.atleast_1d(self.engine.stat_sum(vals[i:i + chunk]))
+            self.n_launches += 1
+        self.n_calls += vals.shape[0]
+        return out
+
+
+class OptimizeResult:
+    def __init__(self, parameters, total_stat, nfev, success, message, trace=None, backend="bfgs-b200", method="bfgs"):
+        self.parameters = parameters
+        self.total_stat = total_stat
+        self.nfev = nfev
+        self.success = success
+        self.message = message
+        self.trace = trace
+        self.backend = backend
+        self.method = method
+
+    def __repr__(self):
+        return (f"OptimizeResult(backend={self.backend!r}, success={self.success}, message={self.message!r}, "
+                f"nfev={self.nfev}, total_stat={self.total_stat:.4f})")
+
+
+class CovarianceResult:
+    def __init__(self, matrix, success, message, backend="hesse-b200"):
+        self.matrix = matrix
+        self.success = success
+        self.message = message
+        self.backend = backend
+
+
+class FitResult:
+    def __init__(self, optimize_result=None, covariance_result=None):
+        self.optimize_result = optimize_result
+        self.covariance_result = covariance_result
+
+    @property
+    def parameters(self):
+        return self.optimize_result.parameters
+
+    @property
+    def total_stat(self):
+        return self.optimize_result.total_stat
+
+    @property
+    def success(self):
+        ok = self.optimize_result.success
+        if self.covariance_result is not None:
+            ok = ok and self.covariance_result.success
+        return ok
+
+    @property
+    def nfev(self):
+        return self.optimize_result.nfev
+
+    def __repr__(self):
+        return f"FitResult({self.optimize_result!r})"
+
+
+def _bounds(like):
+    lo = np.array([p.factor_min if not np.isnan(p.min) else -np.inf for p in like.free])
+    hi = np.array([p.factor_max if not np.isnan(p.max) else np.inf for p in like.free])
+    return lo, hi
+
+
+def _steps(like):
+    """Initial finite-difference steps in factor space: the parameter error if known, else 1 % (Minuit's default)."""
+    steps = []
+    for p in like.free:
+        if p.error > 0:
+            s = abs(p.error / p.scale)
+        else:
+            s = 0.01 * max(abs(p.factor), 1e-3) if p.factor != 0 else 0.01
+        steps.append(s)
+    return np.array(steps)
+
+
+def _gradient(like, x, f0, h, lo, hi):
+    """Central differences with all 2 n points in one launch; also returns the diagonal second derivatives."""
+    n = len(x)
+    pts = np.tile(x, (2 * n, 1))
+    hp = np.minimum(h, hi - x)
+    hm = np.minimum(h, x - lo)
+    hp = np.where(hp <= 0, 0.0, hp)
+    hm = np.where(hm <= 0, 0.0, hm)
+    for i in range(n):
+        pts[2 * i, i] += hp[i]
+        pts[2 * i + 1, i] -= hm[i]
+    f = like.fcn_batch(pts)
+    fp, fm = f[0::2], f[1::2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        g = (fp - fm) / (hp + hm)
+        g2 = 2 * (hm * fp + hp * fm - (hp + hm) * f0) / (hp * hm * (hp + hm))
+    one_sided = (hp == 0) | (hm == 0)
+    g = np.where(np.isfinite(g), g, 0.0)
+    g2 = np.where(one_sided | ~np.isfinite(g2), np.nan, g2)
+    return g, g2
+
+
+def _minimize(like, tol=0.1, max_iter=200, store_trace=False):
+    """BFGS with batched gradient + batched line search; stops on Minuit's EDM criterion."""
+    x = like.factors.copy()
+    n = len(x)
+    lo, hi = _bounds(like)
+    x = np.clip(x, lo, hi)
+    edm_goal = 0.002 * tol * 1.0
+    trace = []
+    f = like.fcn(x)
+    if n == 0:
+        return x, f, True, "no free parameters", trace
+    h = _steps(like)
+    g, g2 = _gradient(like, x, f, h, lo, hi)
+    # initial inverse Hessian from the diagonal curvature (what Migrad seeds from)
+    diag = np.where(np.isfinite(g2) & (g2 > 0), 1.0 / np.where(g2 > 0, g2, 1.0), h * h)
+    H = np.diag(diag)
+    alphas = np.array([1.0, 0.5, 0.25, 0.1, 0.03, 0.01, 1e-3, 1.5, 2.0, 4.0])
+    message, success = "maximum number of iterations reached", False
+    for it in range(max_iter):
+        edm = 0.5 * float(g @ H @ g)
+        if store_trace:
+            trace.append((it, f, x.copy()))
+        if edm < edm_goal and it > 0:
+            success, message = True, f"Optimization terminated successfully (EDM = {edm:.3g})."
+            break
+        p = -H @ g
+        if not np.all(np.isfinite(p)) or g @ p >= 0:
+            H = np.diag(diag)
+            p = -H @ g
+        cand = np.clip(x[np.newaxis, :] + alphas[:, np.newaxis] * p[np.newaxis, :], lo, hi)
+        fc = like.fcn_batch(cand)
+        fc = np.where(np.isfinite(fc), fc, np.inf)
+        best = int(np.argmin(fc))
+        if not fc[best] < f:
+            # shrink further before giving up
+            small = np.array([3e-4, 1e-4, 1e-5, 1e-6])
+            cand = np.clip(x[np.newaxis, :] + small[:, np.newaxis] * p[np.newaxis, :], lo, hi)
+            fc = np.where(np.isfinite(fc2 := like.fcn_batch(cand)), fc2, np.inf)
+            best = int(np.argmin(fc))
+            if not fc[best] < f:
+                if edm < 10 * edm_goal:
+                    success, message = True, f"Optimization terminated: no further decrease (EDM = {edm:.3g})."
+                else:
+                    message = f"line search failed (EDM = {edm:.3g})"
+                break
+        x_new, f_new = cand[best], float(fc[best])
+        # refresh steps from the current metric (like Minuit: step ~ 0.1 sigma..)
+        h = np.maximum(0.1 * np.sqrt(np.abs(np.diag(H))), 1e-8 * np.maximum(np.abs(x_new), 1.0))
+        g_new, g2 = _gradient(like, x_new, f_new, h, lo, hi)
+        s, y = x_new - x, g_new - g
+        sy = float(s @ y)
+        if sy > 1e-12 * np.linalg.norm(s) * np.linalg.norm(y):
+            rho = 1.0 / sy
+            I = np.eye(n)
+            H = (I - rho * np.outer(s, y)) @ H @ (I - rho * np.outer(y, s)) + rho * np.outer(s, s)
+        x, f, g = x_new, f_new, g_new
+    like.set_factors(x)
+    return x, f, success, message, trace
+
+
+def _hesse(like, x, f0):
+    """Symmetric finite-difference Hessian in factor space; 1 + 2n + 2n(n-1) points, batched."""
+    n = len(x)
+    lo, hi = _bounds(like)
+    h = _steps(like)
+    # refine steps so that the stat changes by ~errordef along each axis
+    g, g2 = _gradient(like, x, f0, h, lo, hi)
+    good = np.isfinite(g2) & (g2 > 0)
+    h = np.where(good, np.sqrt(2.0 * 0.1 / np.where(good, g2, 1.0)), h)
+    h = np.minimum(h, np.minimum(hi - x, x - lo) * 0.5 + (~np.isfinite(hi - x + x - lo)) * 0)
+    h = np.where(h > 0, h, _steps(like))
+    pts = []
+    for i in range(n):
+        for s in (+1, -1):
+            p = x.copy()
+            p[i] += s * h[i]
+            pts.append(p)
+    pairs = list(itertools.combinations(range(n), 2))
+    for i, j in pairs:
+        for si, sj in ((1, 1), (1, -1), (-1, 1), (-1, -1)):
+            p = x.copy()
+            p[i] += si * h[i]
+            p[j] += sj * h[j]
+            pts.append(p)
+    f = like.fcn_batch(np.array(pts)) if pts else np.zeros(0)
+    like.set_factors(x)
+    hess = np.zeros((n, n))
+    for i in range(n):
+        hess[i, i] = (f[2 * i] - 2 * f0 + f[2 * i + 1]) / (h[i] * h[i])
+    base = 2 * n
+    for k, (i, j) in enumerate(pairs):
+        fpp, fpm, fmp, fmm = f[base + 4 * k: base + 4 * k + 4]
+        hess[i, j] = hess[j, i] = (fpp - fpm - fmp + fmm) / (4 * h[i] * h[j])
+    return hess
+
+
+class Fit:
+    """Fit class (modeling/fit.py:81).  ``backend`` is informational: the optimiser is the built-in batched BFGS."""
+
+    def __init__(self, backend="minuit", optimize_opts=None, covariance_opts=None, confidence_opts=None,
+                 store_trace=False):
+        self.backend = backend
+        self.optimize_opts = dict(optimize_opts or {})
+        self.covariance_opts = dict(covariance_opts or {})
+        self.confidence_opts = dict(confidence_opts or {})
+        self.store_trace = store_trace
+        self._last_like = None
+
+    def run(self, datasets):
+        """Optimize then estimate the covariance (fit.py:147-181)."""
+        opt = self.optimize(datasets)
+        cov = self.covariance(datasets, optimize_result=opt)
+        return FitResult(optimize_result=opt, covariance_result=cov)
+
+    def optimize(self, datasets):
+        """fit.py:183-244: autoscale the parameters, minimise the joint stat over the free factors."""
+        like = _Likelihood(datasets)
+        self._last_like = like
+        params = like.datasets.parameters
+        params.check_limits()
+        if len(like.free) == 0:
+            raise ValueError("No free parameters for fitting")
+        for p in like.engine.parameters:
+            p.autoscale()
+        tol = self.optimize_opts.get("tol", 0.1)
+        max_iter = self.optimize_opts.get("max_iter", 200)
+        x, f, success, message, trace = _minimize(like, tol=tol, max_iter=max_iter, store_trace=self.store_trace)
+        params.check_limits()
+        return OptimizeResult(parameters=params, total_stat=f, nfev=like.n_calls, success=success, message=message,
+                              trace=trace if self.store_trace else None)
+
+    def covariance(self, datasets, optimize_result=None):
+        """fit.py:246-300: Hesse in factor space, rescaled to values; errors written to the parameters."""
+        like = _Likelihood(datasets)
+        x = like.factors
+        f0 = like.fcn(x)
+        hess = _hesse(like, x, f0)
+        scale = np.array([p.scale for p in like.free])
+        success, message = True, "Hesse terminated successfully."
+        try:
+            cov_f = 2.0 * np.linalg.inv(hess)  # errordef = 1 on 2 log L: cov = 2 H^-1
+            if not np.all(np.diag(cov_f) > 0):
+                raise np.linalg.LinAlgError("non-positive variance")
+        except np.linalg.LinAlgError as exc:
+            success, message = False, f"Hesse failed: {exc}"
+            cov_f = np.full_like(hess, np.nan)
+        cov = cov_f * np.outer(scale, scale)
+        if success:
+            for p, var in zip(like.free, np.diag(cov)):
+                p.error = float(np.sqrt(var))
+        self._last_like = like
+        return CovarianceResult(matrix=cov, success=success, message=message)
+
+    def stat_profile(self, datasets, parameter, reoptimize=False):
+        """fit.py:351-422: the joint stat on ``parameter.scan_values``, all points in one launch."""
+        like = _Likelihood(datasets)
+        parameter = like.datasets.parameters[parameter] if isinstance(parameter, str) else parameter
+        values = np.asarray(parameter.scan_values, dtype=float)
+        if reoptimize:
+            stats, results = [], []
+            saved = [(p, p.value, p.frozen) for p in like.engine.parameters]
+            try:
+                parameter.frozen = True
+                for v in values:
+                    parameter.value = v
+                    res = self.optimize(like.datasets)
+                    stats.append(res.total_stat)
+                    results.append(res)
+            finally:
+                for p, v, fr in saved:
+                    p.value, p.frozen = v, fr
+            return {f"{parameter.name}_scan": values, "stat_scan": np.array(stats), "fit_results": results}
+        base = like.engine.values()
+        col = like.engine.parameters.index(parameter)
+        grid = np.tile(base, (len(values), 1))
+        grid[:, col] = values
+        stats = np.atleast_1d(like.engine.stat_sum(grid))
+        return {f"{parameter.name}_scan": values, "stat_scan": stats, "fit_results": []}
+
+    def stat_surface(self, datasets, x, y, reoptimize=False):
+        """fit.py:424-519: joint stat on the (x, y) grid, one launch (chunks of 512 vectors)."""
+        if reoptimize:
+            raise NotImplementedError("stat_surface(reoptimize=True) is not implemented")
+        like = _Likelihood(datasets)
+        pars = like.datasets.parameters
+        x = pars[x] if isinstance(x, str) else x
+        y = pars[y] if isinstance(y, str) else y
+        xv, yv = np.asarray(x.scan_values, float), np.asarray(y.scan_values, float)
+        base = like.engine.values()
+        cx, cy = like.engine.parameters.index(x), like.engine.parameters.index(y)
+        grid = np.tile(base, (len(xv) * len(yv), 1))
+        for k, (a, b) in enumerate(itertools.product(xv, yv)):
+            grid[k, cx], grid[k, cy] = a, b
+        stats = np.empty(len(grid))
+        for i in range(0, len(grid), 512):
+            stats[i:i + 512] = np.atleast_1d(like.engine.stat_sum(grid[i:i + 512]))
+        return {f"{x.name}_scan": xv, f"{y.name}_scan": yv, "stat_scan": stats.reshape(len(xv), len(yv)),
+                "fit_results": []}

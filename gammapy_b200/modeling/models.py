@@ -1,0 +1,450 @@
+"""Sky models of the hot path: 3 spectral x 3 spatial models, ``SkyModel``, ``FoVBackgroundModel``.
+
+Reference: modeling/models/core.py (ModelBase), spectral.py (PowerLaw :1002-1067, PowerLawNorm :1134-1162,
+ExpCutoffPowerLaw :1520-1567, LogParabola :1865-1908), spatial.py (Point :558-631, Gaussian :639-701,
+Disk :898-993), cube.py (SkyModel :33, FoVBackgroundModel :622-756).
+
+Model objects only carry parameters; bin integrals (``SpectralModel.integral``) and pixel integrals
+(``SpatialModel.integrate_geom``) run on the GPU through the C ABI.  ``evaluate`` is the plain
+differential form, kept for user code that samples a model at a few energies / positions.
+"""
+import copy
+import ctypes as C
+import itertools
+
+import numpy as np
+
+from ..utils import DEG, SkyCoord, angular_separation, position_angle
+from .parameter import Parameter, Parameters
+
+__all__ = [
+    "Model", "SpectralModel", "SpatialModel", "PowerLawSpectralModel", "PowerLawNormSpectralModel",
+    "LogParabolaSpectralModel", "ExpCutoffPowerLawSpectralModel", "PointSpatialModel", "GaussianSpatialModel",
+    "DiskSpatialModel", "SkyModel", "FoVBackgroundModel", "Models", "DatasetModels",
+]
+
+_name_counter = itertools.count()
+
+
+def make_name(name=None):
+    if name is None:
+        return f"model-{next(_name_counter):04d}"
+    return str(name)
+
+
+class ModelBase:
+    """Parameter bookkeeping of modeling/models/core.py:ModelBase."""
+
+    _type = None
+    tag = ["ModelBase"]
+
+    def __init__(self, **kwargs):
+        self.default_parameters = Parameters(
+            [v for k, v in itertools.chain(*[vars(c).items() for c in reversed(type(self).__mro__)])
+             if isinstance(v, Parameter)])
+        names = []
+        for par in self.default_parameters:
+            if par.name in names:
+                continue
+            names.append(par.name)
+            value = kwargs.pop(par.name, None)
+            new = par.copy()
+            if isinstance(value, Parameter):
+                new = value
+            elif value is not None:
+                new.quantity = value
+            self.__dict__[par.name] = new
+        self._par_names = names
+        if kwargs:
+            raise TypeError(f"{type(self).__name__}: unexpected arguments {sorted(kwargs)}")
+
+    @property
+    def type(self):
+        return self._type
+
+    @property
+    def parameters(self):
+        return Parameters([self.__dict__[n] for n in self._par_names])
+
+    def copy(self, **kwargs):
+        return copy.deepcopy(self)
+
+    def freeze(self):
+        self.parameters.freeze_all()
+
+    def unfreeze(self):
+        for p, d in zip(self.parameters, [self.default_parameters[n] for n in self._par_names]):
+            p.frozen = d.frozen
+
+    def __repr__(self):
+        pars = ", ".join(f"{p.name}={p.value!r}" for p in self.parameters)
+        return f"{type(self).__name__}({pars})"
+
+
+Model = ModelBase
+
+
+# ------------------------------------------------------------------------------------------------
+# spectral
+# ------------------------------------------------------------------------------------------------
+class SpectralModel(ModelBase):
+    _type = "spectral"
+    _gpy_type = None
+
+    def __call__(self, energy):
+        return self.evaluate(np.asarray(energy, dtype=float), *[p.value for p in self.parameters])
+
+    def integral(self, energy_min, energy_max, **kwargs):
+        """``SpectralModel.integral`` (spectral.py:353-371) per bin, computed by the CUDA kernel K0."""
+        from .._lib import Context, check
+
+        emin = np.atleast_1d(np.asarray(energy_min, dtype=float))
+        emax = np.atleast_1d(np.asarray(energy_max, dtype=float))
+        emin, emax = np.broadcast_arrays(emin, emax)
+        out = np.empty(emin.shape, dtype=float)
+        if self._gpy_type is None:
+            raise NotImplementedError(f"{type(self).__name__}.integral is outside the accelerated path")
+        ctx = Context.get()
+        pars = np.array([p.value for p in self.parameters], dtype=float)
+        for i, (lo, hi) in enumerate(zip(emin.ravel(), emax.ravel())):
+            edges = np.array([lo, hi], dtype=float)
+            nodes = integration_nodes(edges)
+            res = np.empty(1)
+            check(ctx.lib.gpy_spectral_integral(
+                ctx.handle, self._gpy_type, pars.ctypes.data_as(C.c_void_p), edges.ctypes.data_as(C.c_void_p), 1,
+                nodes.ctypes.data_as(C.c_void_p), nodes.shape[1], res.ctypes.data_as(C.c_void_p)))
+            out.ravel()[i] = res[0]
+        return out if np.ndim(energy_min) or np.ndim(energy_max) else float(out[0])
+
+
+def integration_nodes(edges, ndecade=100):
+    """geomspace nodes of ``integrate_spectrum`` (spectral.py:132-134): the node count sits on a float
+    knife-edge, so it is evaluated here with the reference's numpy expression and passed to the kernel."""
+    edges = np.asarray(edges, dtype=float)
+    energy_min, energy_max = edges[:-1], edges[1:]
+    num = np.maximum(np.max(ndecade * np.log10(energy_max / energy_min)), 2)
+    return np.ascontiguousarray(np.geomspace(energy_min, energy_max, num=int(num), axis=-1))
+
+
+class PowerLawSpectralModel(SpectralModel):
+    tag = ["PowerLawSpectralModel", "pl"]
+    _gpy_type = 0
+    index = Parameter("index", 2.0)
+    amplitude = Parameter("amplitude", "1e-12 cm-2 s-1 TeV-1", scale_method="scale10", interp="log")
+    reference = Parameter("reference", "1 TeV", frozen=True)
+
+    @staticmethod
+    def evaluate(energy, index, amplitude, reference):
+        return amplitude * np.power((energy / reference), -index)
+
+
+class PowerLawNormSpectralModel(SpectralModel):
+    tag = ["PowerLawNormSpectralModel", "pl-norm"]
+    tilt = Parameter("tilt", 0, frozen=True)
+    norm = Parameter("norm", 1, unit="", interp="log")
+    reference = Parameter("reference", "1 TeV", frozen=True)
+
+    @staticmethod
+    def evaluate(energy, tilt, norm, reference):
+        return norm * np.power((energy / reference), -tilt)
+
+
+class ExpCutoffPowerLawSpectralModel(SpectralModel):
+    tag = ["ExpCutoffPowerLawSpectralModel", "ecpl"]
+    _gpy_type = 2
+    index = Parameter("index", 1.5)
+    amplitude = Parameter("amplitude", "1e-12 cm-2 s-1 TeV-1", scale_method="scale10", interp="log")
+    reference = Parameter("reference", "1 TeV", frozen=True)
+    lambda_ = Parameter("lambda_", "0.1 TeV-1")
+    alpha = Parameter("alpha", "1.0", frozen=True)
+
+    @staticmethod
+    def evaluate(energy, index, amplitude, reference, lambda_, alpha):
+        pwl = amplitude * (energy / reference) ** (-index)
+        cutoff = np.exp(-np.power(energy * lambda_, alpha))
+        return pwl * cutoff
+
+
+class LogParabolaSpectralModel(SpectralModel):
+    tag = ["LogParabolaSpectralModel", "lp"]
+    _gpy_type = 1
+    amplitude = Parameter("amplitude", "1e-12 cm-2 s-1 TeV-1", scale_method="scale10", interp="log")
+    reference = Parameter("reference", "10 TeV", frozen=True)
+    alpha = Parameter("alpha", 2)
+    beta = Parameter("beta", 1)
+
+    @staticmethod
+    def evaluate(energy, amplitude, reference, alpha, beta):
+        xx = energy / reference
+        exponent = -alpha - beta * np.log(xx)
+        return amplitude * np.power(xx, exponent)
+
+
+# ------------------------------------------------------------------------------------------------
+# spatial
+# ------------------------------------------------------------------------------------------------
+class SpatialModel(ModelBase):
+    _type = "spatial"
+    _gpy_type = None
+
+    def __init__(self, **kwargs):
+        self.frame = kwargs.pop("frame", "icrs")
+        super().__init__(**kwargs)
+
+    @property
+    def position(self):
+        return SkyCoord(self.lon_0.value, self.lat_0.value, frame=self.frame)
+
+    @property
+    def position_lonlat(self):
+        return self.lon_0.value * DEG, self.lat_0.value * DEG
+
+    @property
+    def is_energy_dependent(self):
+        return False
+
+    def __call__(self, lon, lat):
+        return self.evaluate(np.asarray(lon, float), np.asarray(lat, float), *[p.value for p in self.parameters])
+
+    def integrate_geom(self, geom, oversampling_factor=None):
+        """``SpatialModel.integrate_geom`` (spatial.py:222-309) on an image geometry, CUDA kernel K1.
+
+        Returns the float32 image the PSF convolution consumes (ndmap.py:984)."""
+        from .._lib import Context, GeomDesc, check
+        from ..maps import Map
+
+        if oversampling_factor is not None:
+            raise NotImplementedError("integrate_geom: the oversampling factor is chosen as the reference does")
+        if geom.frame != self.frame:
+            raise NotImplementedError("model frame and geometry frame differ: frame transforms are out of scope")
+        g = geom.to_image()
+        desc = GeomDesc(g.npix[0], g.npix[1], 1, 1, g.binsz, g.crval[0], g.crpix[0], g.crpix[1])
+        pars = np.array([p.value for p in self.parameters], dtype=float)
+        out = np.empty(g.data_shape, dtype=np.float32)
+        f = C.c_int32(0)
+        ctx = Context.get()
+        check(ctx.lib.gpy_integrate_geom(ctx.handle, C.byref(desc), self._gpy_type, pars.ctypes.data_as(C.c_void_p),
+                                         out.ctypes.data_as(C.c_void_p), C.byref(f)))
+        m = Map.from_geom(g, data=out, unit="" if self._gpy_type == 0 else "")
+        m.meta["oversampling_factor"] = int(f.value)
+        return m
+
+
+class PointSpatialModel(SpatialModel):
+    tag = ["PointSpatialModel", "point"]
+    _gpy_type = 0
+    lon_0 = Parameter("lon_0", "0 deg")
+    lat_0 = Parameter("lat_0", "0 deg", min=-90, max=90)
+
+    @property
+    def evaluation_bin_size_min(self):
+        return 0.0
+
+    @property
+    def evaluation_radius(self):
+        return 0.0
+
+
+class GaussianSpatialModel(SpatialModel):
+    tag = ["GaussianSpatialModel", "gauss"]
+    _gpy_type = 1
+    lon_0 = Parameter("lon_0", "0 deg")
+    lat_0 = Parameter("lat_0", "0 deg", min=-90, max=90)
+    sigma = Parameter("sigma", "1 deg", min=0)
+    e = Parameter("e", 0, min=0, max=1, frozen=True)
+    phi = Parameter("phi", "0 deg", frozen=True, min=-180, max=180)
+
+    @property
+    def evaluation_bin_size_min(self):
+        return self.sigma.value / 3.0
+
+    @property
+    def evaluation_radius(self):
+        return 5 * self.sigma.value
+
+    @staticmethod
+    def evaluate(lon, lat, lon_0, lat_0, sigma, e, phi):
+        """sr-1 (spatial.py:684-701); angles in deg."""
+        lon, lat, lon_0, lat_0, sigma, phi = (v * DEG for v in (lon, lat, lon_0, lat_0, sigma, phi))
+        sep = angular_separation(lon, lat, lon_0, lat_0)
+        phi = phi % np.pi
+        if e == 0:
+            a = 1.0 - np.cos(sigma)
+            norm = 1 / (4 * np.pi * a * (1.0 - np.exp(-1.0 / a)))
+        else:
+            minor_axis, sigma_eff = _sigma_eff(lon_0, lat_0, lon, lat, phi, sigma, e)
+            a = 1.0 - np.cos(sigma_eff)
+            norm = 1 / (2 * np.pi * sigma * minor_axis)
+        return norm * np.exp(-0.5 * ((1 - np.cos(sep)) / a))
+
+
+def _sigma_eff(lon_0, lat_0, lon, lat, phi, major_axis, e):
+    phi_0 = position_angle(lon_0, lat_0, lon, lat)
+    d_phi = phi - phi_0
+    minor_axis = major_axis * np.sqrt(1 - e**2)
+    a2 = (major_axis * np.sin(d_phi)) ** 2
+    b2 = (minor_axis * np.cos(d_phi)) ** 2
+    return minor_axis, major_axis * minor_axis / np.sqrt(a2 + b2)
+
+
+class DiskSpatialModel(SpatialModel):
+    tag = ["DiskSpatialModel", "disk"]
+    _gpy_type = 2
+    lon_0 = Parameter("lon_0", "0 deg")
+    lat_0 = Parameter("lat_0", "0 deg", min=-90, max=90)
+    r_0 = Parameter("r_0", "1 deg", min=0)
+    e = Parameter("e", 0, min=0, max=1, frozen=True)
+    phi = Parameter("phi", "0 deg", frozen=True, min=-180, max=180)
+    edge_width = Parameter("edge_width", value=0.01, min=0, max=1, frozen=True)
+
+    @property
+    def evaluation_bin_size_min(self):
+        return self.r_0.value * (1 - self.edge_width.value) / 10.0
+
+    @property
+    def evaluation_radius(self):
+        return 1.1 * self.r_0.value * (1 + self.edge_width.value)
+
+
+# ------------------------------------------------------------------------------------------------
+# cube
+# ------------------------------------------------------------------------------------------------
+class SkyModel:
+    """Spatial x spectral source model (modeling/models/cube.py:33)."""
+
+    tag = ["SkyModel", "sky-model"]
+    _apply_irf_default = {"exposure": True, "psf": True, "edisp": True}
+
+    def __init__(self, spectral_model, spatial_model=None, temporal_model=None, name=None, apply_irf=None,
+                 datasets_names=None):
+        if temporal_model is not None:
+            raise NotImplementedError("temporal models are outside the accelerated path")
+        if spatial_model is None:
+            raise NotImplementedError("SkyModel without a spatial model is outside the accelerated path")
+        self.spatial_model = spatial_model
+        self.spectral_model = spectral_model
+        self.temporal_model = None
+        self._name = make_name(name)
+        self.apply_irf = dict(self._apply_irf_default if apply_irf is None else apply_irf)
+        self.datasets_names = [datasets_names] if isinstance(datasets_names, str) else datasets_names
+
+    @property
+    def name(self):
+        return self._name
+
+    @property
+    def parameters(self):
+        return Parameters.from_stack([self.spatial_model.parameters, self.spectral_model.parameters])
+
+    @property
+    def position(self):
+        return self.spatial_model.position
+
+    @property
+    def evaluation_radius(self):
+        return self.spatial_model.evaluation_radius
+
+    @property
+    def frame(self):
+        return self.spatial_model.frame
+
+    def copy(self, name=None, **kwargs):
+        new = copy.deepcopy(self)
+        new._name = make_name(name)
+        return new
+
+    def freeze(self, model_type=None):
+        if model_type in (None, "spatial"):
+            self.spatial_model.freeze()
+        if model_type in (None, "spectral"):
+            self.spectral_model.freeze()
+
+    def __repr__(self):
+        return f"SkyModel(name={self.name!r}, spatial_model={self.spatial_model!r}, spectral_model={self.spectral_model!r})"
+
+
+class FoVBackgroundModel:
+    """Field-of-view background: norm * (E / E0)^-tilt on the background map (cube.py:622-756)."""
+
+    tag = ["FoVBackgroundModel", "fov-bkg"]
+
+    def __init__(self, dataset_name, spectral_model=None, spatial_model=None, name=None):
+        if spatial_model is not None:
+            raise NotImplementedError("FoVBackgroundModel spatial models are outside the accelerated path")
+        if spectral_model is None:
+            spectral_model = PowerLawNormSpectralModel()
+        if not isinstance(spectral_model, PowerLawNormSpectralModel):
+            raise NotImplementedError("FoVBackgroundModel: only PowerLawNormSpectralModel is accelerated")
+        self.spectral_model = spectral_model
+        self.spatial_model = None
+        self.datasets_names = [dataset_name] if isinstance(dataset_name, str) else list(dataset_name)
+        self._name = make_name(name if name is not None else f"{self.datasets_names[0]}-bkg")
+
+    @property
+    def name(self):
+        return self._name
+
+    @property
+    def parameters(self):
+        return self.spectral_model.parameters
+
+    def copy(self, name=None, **kwargs):
+        new = copy.deepcopy(self)
+        new._name = make_name(name)
+        return new
+
+    def __repr__(self):
+        return f"FoVBackgroundModel(name={self.name!r}, datasets_names={self.datasets_names}, spectral_model={self.spectral_model!r})"
+
+
+class Models(list):
+    """List of models with a joint ``Parameters`` view (modeling/models/core.py DatasetModels)."""
+
+    def __init__(self, models=None):
+        if models is None:
+            models = []
+        elif isinstance(models, (SkyModel, FoVBackgroundModel)):
+            models = [models]
+        super().__init__(models)
+        names = [m.name for m in self]
+        if len(set(names)) != len(names):
+            raise ValueError("Model names must be unique")
+        self._penalties = None
+
+    @property
+    def parameters(self):
+        return Parameters.from_stack([m.parameters for m in self])
+
+    @property
+    def names(self):
+        return [m.name for m in self]
+
+    def select(self, datasets_names=None, name_substring=None, tag=None):
+        out = []
+        for m in self:
+            if datasets_names is not None and m.datasets_names is not None:
+                wanted = [datasets_names] if isinstance(datasets_names, str) else datasets_names
+                if not any(n in m.datasets_names for n in wanted):
+                    continue
+            if name_substring is not None and name_substring not in m.name:
+                continue
+            if tag is not None and not any(t in m.tag for t in ([tag] if isinstance(tag, str) else tag)):
+                continue
+            out.append(m)
+        return Models(out)
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            for m in self:
+                if m.name == key:
+                    return m
+            raise KeyError(f"No model named {key!r}; available: {self.names}")
+        if isinstance(key, slice):
+            return Models(list.__getitem__(self, key))
+        return list.__getitem__(self, key)
+
+    def copy(self):
+        return Models([m.copy(name=m.name) for m in self])
+
+
+DatasetModels = Models

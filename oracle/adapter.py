@@ -1,0 +1,66 @@
+"""Oracle adapter (TEST INFRASTRUCTURE ONLY): turn the product's host-side objects (numpy maps, model
+parameter values) into the plain arrays / dicts the oracle restatement consumes.  Only reads attributes;
+the oracle recomputes every geometry / model quantity itself."""
+import numpy as np
+
+from .evaluator import Dataset, DatasetEvaluator
+from .wcs import ImageGeom
+
+_SPATIAL = {"PointSpatialModel": "point", "GaussianSpatialModel": "gauss", "DiskSpatialModel": "disk"}
+_SPECTRAL = {"PowerLawSpectralModel": "pl", "LogParabolaSpectralModel": "lp", "ExpCutoffPowerLawSpectralModel": "ecpl",
+             "PowerLawNormSpectralModel": "pl-norm"}
+
+
+def geom_to_oracle(geom):
+    return ImageGeom(geom.npix[0], geom.npix[1], geom.binsz, geom.crval[0], geom.crpix[0], geom.crpix[1], geom.crval[1])
+
+
+def model_to_oracle(model):
+    if type(model).__name__ == "FoVBackgroundModel":
+        spec = {"type": "pl-norm", **{p.name: p.value for p in model.spectral_model.parameters}}
+        return {"type": "fov-bkg", "name": model.name, "spectral": spec}
+    spatial = {"type": _SPATIAL[type(model.spatial_model).__name__],
+               **{p.name: p.value for p in model.spatial_model.parameters}}
+    spectral = {"type": _SPECTRAL[type(model.spectral_model).__name__],
+                **{p.name: p.value for p in model.spectral_model.parameters}}
+    return {"name": model.name, "spatial": spatial, "spectral": spectral, "apply_irf": dict(model.apply_irf)}
+
+
+def dataset_to_oracle(ds):
+    """gammapy_b200.MapDataset -> oracle.evaluator.Dataset (the IRF kernels are the identical static arrays)."""
+    geom = ds._geom
+    e_true = ds.exposure.geom.axes["energy_true"]
+    e_reco = geom.axes["energy"]
+    psf = ds._psf_kernel_for_evaluators()
+    if ds.edisp is not None:
+        edisp = np.asarray(ds.edisp.get_edisp_kernel(energy_axis=e_reco).pdf_matrix, dtype=float)
+    else:
+        from gammapy_b200.irf import EDispKernel
+
+        edisp = EDispKernel.from_diagonal_response(e_true, e_reco).pdf_matrix
+    return Dataset(
+        geom=geom_to_oracle(geom), energy_edges=e_reco.edges, energy_true_edges=e_true.edges,
+        energy_center=e_reco.center, exposure=np.asarray(ds.exposure.data),
+        background=None if ds.background is None else np.asarray(ds.background.data),
+        counts=None if ds.counts is None else np.asarray(ds.counts.data),
+        mask_safe=None if ds.mask_safe is None else np.asarray(ds.mask_safe.data),
+        mask_fit=None if ds.mask_fit is None else np.asarray(ds.mask_fit.data),
+        psf_kernel=None if psf is None else np.asarray(psf.data, dtype=float), edisp=edisp, name=ds.name,
+    )
+
+
+def evaluator_for(ds, conv="fft32"):
+    """DatasetEvaluator with the dataset's current models / parameter values."""
+    return DatasetEvaluator(dataset_to_oracle(ds), [model_to_oracle(m) for m in (ds.models or [])], conv=conv)
+
+
+def refresh_models(de, ds):
+    """Copy the current parameter values into an existing oracle evaluator (keeps its cache state)."""
+    for m in (ds.models or []):
+        new = model_to_oracle(m)
+        if new.get("type") == "fov-bkg":
+            de.bkg_model["spectral"].update(new["spectral"])
+        else:
+            ev = de.evaluators[new["name"]]
+            ev.model["spatial"].update(new["spatial"])
+            ev.model["spectral"].update(new["spectral"])

@@ -27,7 +27,7 @@ def pl_evaluate(energy, index, amplitude, reference):
 
 def pl_evaluate_integral(energy_min, energy_max, index, amplitude, reference):
     """spectral.py:1039-1067 (arrays broadcast; ``index`` may be an array, as trapz_loglog passes it)."""
-    val = -1 * index + 1
+    val = np.asarray(-1 * index + 1, dtype=float)  # Quantity arithmetic in the reference: numpy semantics
     with np.errstate(all="ignore"):
         prefactor = amplitude * reference / val
         upper = np.power((energy_max / reference), val)

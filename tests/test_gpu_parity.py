@@ -1,0 +1,396 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): per-bin npred within 1e-5 relative, total stat within 1e-3
+absolute.  Against the reference's float32-FFT convolution the per-bin comparison carries the absolute
+floor ``4 * eps_f32 * max(signal slice)`` (the FFT's own error is ~2e-7 x peak); against
+the exact (float64) variant of the oracle no floor is needed.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+pytestmark = pytest.mark.gpu
+
+EPS32 = np.finfo(np.float32).eps
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# kernel 4: Cash sums (compiled-stat registry boundary)
+# ---------------------------------------------------------------------------------------------------------
+def test_cash_sum_registry_vs_reference(ctx):
+    from gammapy_b200.stats import get_fit_statistics_compiled
+    from oracle import cash
+
+    reg = get_fit_statistics_compiled()
+    assert reg["TRUNCATION_VALUE"] == 1e-25
+    rng = np.random.RandomState(1)
+    mu = rng.gamma(2.0, 2.0, 1_000_003)
+    mu[::1000] = 0.0
+    mu[5::1000] = -1.0
+    mu[7::1000] = 1e-26
+    n = rng.poisson(np.clip(mu, 0, None)).astype(float)
+    w = rng.uniform(-0.2, 1.0, mu.size)
+    ref = cash.reference_module()
+    want = ref.cash_sum_cython(n, mu) if ref is not None else cash.cash_sum(n, mu)
+    got = reg["cash_sum_compiled"](n, mu)
+    assert abs(got - want) < 1e-6  # 1e6 bins, |stat| ~ 5e6: fp64 summation order only
+    want_w = ref.weighted_cash_sum_cython(n, mu, w) if ref is not None else cash.weighted_cash_sum(n, mu, w)
+    assert abs(reg["weighted_cash_sum_compiled"](n, mu, w) - want_w) < 1e-6
+
+
+def test_cash_sum_edge_cases(ctx):
+    from gammapy_b200.stats import cash_sum_cuda, weighted_cash_sum_cuda
+    from oracle import cash
+
+    assert cash_sum_cuda(np.zeros(0), np.zeros(0)) == 0.0
+    n = np.array([0.0, 3.0, 0.0, 2.0, 1.0])
+    mu = np.array([0.0, 0.0, -5.0, np.nan, 1e-30])
+    assert_allclose(cash_sum_cuda(n, mu), cash.cash_sum(n, mu), rtol=1e-14)
+    assert_allclose(weighted_cash_sum_cuda(n, mu, np.array([1.0, 0.0, 2.0, -1.0, 0.5])),
+                    cash.weighted_cash_sum(n, mu, np.array([1.0, 0.0, 2.0, -1.0, 0.5])), rtol=1e-14)
+    # golden per-bin values of the reference's test fixture
+    from tests.test_oracle_kat import CASH_REF, MU_SIG, N_ON
+
+    assert_allclose(cash_sum_cuda(np.array(N_ON, float), np.array(MU_SIG)), np.sum(CASH_REF), rtol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# kernel 1: geometry + spatial models
+# ---------------------------------------------------------------------------------------------------------
+def _geom_desc(geom):
+    from gammapy_b200 import _lib
+
+    return _lib.GeomDesc(geom.nx, geom.ny, 1, 1, geom.binsz, geom.crval_lon, geom.crpix_x, geom.crpix_y)
+
+
+def test_solid_angle(ctx):
+    from gammapy_b200 import _lib
+    from oracle import wcs
+
+    geom = wcs.ImageGeom.create(skydir=(0.0, 0.0), binsz=0.02, width=(6, 3))
+    out = np.empty(geom.data_shape)
+    _lib.check(ctx.lib.gpy_solid_angle(ctx.handle, C.byref(_geom_desc(geom)), _ptr(out)))
+    assert_allclose(out, geom.solid_angle(), rtol=1e-9)
+
+
+SPATIAL_CASES = [
+    ("point", dict(lon_0=0.013, lat_0=-0.271), 0, [0.013, -0.271]),
+    ("point-center", dict(lon_0=0.0, lat_0=0.0), 0, [0.0, 0.0]),
+    ("gauss-f1", dict(lon_0=0.2, lat_0=0.1, sigma=0.3, e=0.0, phi=0.0), 1, [0.2, 0.1, 0.3, 0.0, 0.0]),
+    ("gauss-f2", dict(lon_0=-0.31, lat_0=0.17, sigma=0.05, e=0.0, phi=0.0), 1, [-0.31, 0.17, 0.05, 0.0, 0.0]),
+    ("gauss-f7", dict(lon_0=0.4, lat_0=-0.4, sigma=0.01, e=0.0, phi=0.0), 1, [0.4, -0.4, 0.01, 0.0, 0.0]),
+    ("gauss-tiny-f200", dict(lon_0=0.1, lat_0=0.1, sigma=1e-4, e=0.0, phi=0.0), 1, [0.1, 0.1, 1e-4, 0.0, 0.0]),
+    ("gauss-elongated", dict(lon_0=0.1, lat_0=-0.2, sigma=0.2, e=0.7, phi=30.0), 1, [0.1, -0.2, 0.2, 0.7, 30.0]),
+    ("gauss-edge", dict(lon_0=0.95, lat_0=0.0, sigma=0.05, e=0.0, phi=0.0), 1, [0.95, 0.0, 0.05, 0.0, 0.0]),
+    ("gauss-outside", dict(lon_0=5.0, lat_0=0.0, sigma=0.05, e=0.0, phi=0.0), 1, [5.0, 0.0, 0.05, 0.0, 0.0]),
+    ("disk", dict(lon_0=0.1, lat_0=0.2, r_0=0.3, e=0.0, phi=0.0, edge_width=0.01), 2, [0.1, 0.2, 0.3, 0.0, 0.0, 0.01]),
+    ("disk-elongated", dict(lon_0=-0.2, lat_0=0.1, r_0=0.4, e=0.6, phi=110.0, edge_width=0.05), 2,
+     [-0.2, 0.1, 0.4, 0.6, 110.0, 0.05]),
+]
+
+
+@pytest.mark.parametrize("name,pars,gtype,vec", SPATIAL_CASES, ids=[c[0] for c in SPATIAL_CASES])
+def test_integrate_geom(ctx, name, pars, gtype, vec):
+    from gammapy_b200 import _lib
+    from oracle import spatial, wcs
+
+    geom = wcs.ImageGeom.create(skydir=(0.0, 0.0), binsz=0.02, width=(2.0, 1.6))
+    model = {"type": ["point", "gauss", "disk"][gtype], **pars}
+    want = spatial.integrate_geom(model, geom).astype(np.float32)  # cast at the convolution input
+    out = np.empty(geom.data_shape, dtype=np.float32)
+    f = C.c_int32(0)
+    v = np.array(vec, dtype=float)
+    _lib.check(ctx.lib.gpy_integrate_geom(ctx.handle, C.byref(_geom_desc(geom)), gtype, _ptr(v), _ptr(out), C.byref(f)))
+    scale = max(float(np.abs(want).max()), 1e-300)
+    assert_allclose(out, want, rtol=2e-6, atol=2 * EPS32 * scale)
+    if name == "gauss-tiny-f200":
+        assert f.value == 200  # test_large_oversampling: capped at MAX_OVERSAMPLING
+        assert_allclose(out.sum(), 1, rtol=1e-3)
+    if name == "gauss-f2":
+        assert f.value == 2
+    if name == "gauss-outside":
+        assert f.value == 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# kernel 0: spectral integrals
+# ---------------------------------------------------------------------------------------------------------
+SPECTRAL_CASES = [
+    ("pl", 0, [2.3, 4.0, 1.0], {"type": "pl", "index": 2.3, "amplitude": 4.0, "reference": 1.0}),
+    ("pl-index1", 0, [1.0, 2.0, 1.0], {"type": "pl", "index": 1.0, "amplitude": 2.0, "reference": 1.0}),
+    ("lp", 1, [4.0, 1.0, 2.3, 0.5], {"type": "lp", "amplitude": 4.0, "reference": 1.0, "alpha": 2.3, "beta": 0.5}),
+    ("ecpl", 2, [1.6, 4.0, 1.0, 0.1, 1.0], {"type": "ecpl", "index": 1.6, "amplitude": 4.0, "reference": 1.0,
+                                             "lambda_": 0.1, "alpha": 1.0}),
+    ("ecpl-hard-cutoff", 2, [2.0, 1e-12, 1.0, 5.0, 1.0], {"type": "ecpl", "index": 2.0, "amplitude": 1e-12,
+                                                        "reference": 1.0, "lambda_": 5.0, "alpha": 1.0}),
+]
+
+
+@pytest.mark.parametrize("name,gtype,vec,model", SPECTRAL_CASES, ids=[c[0] for c in SPECTRAL_CASES])
+def test_spectral_integral(ctx, name, gtype, vec, model):
+    from gammapy_b200 import _lib
+    from oracle import spectral
+
+    edges = np.geomspace(0.03, 300.0, 61)
+    nodes = np.ascontiguousarray(spectral.integrate_nodes(edges[:-1], edges[1:]))
+    want = spectral.integral(model, edges[:-1], edges[1:])
+    out = np.empty(60)
+    v = np.array(vec, dtype=float)
+    _lib.check(ctx.lib.gpy_spectral_integral(ctx.handle, gtype, _ptr(v), _ptr(edges), 60, _ptr(nodes), nodes.shape[1],
+                                             _ptr(out)))
+    assert_allclose(out, want, rtol=1e-11, atol=1e-300)
+
+
+def test_spectral_goldens_on_gpu(ctx):
+    """modeling/models/tests/test_spectral.py TEST_MODELS integral_1_10TeV through the public model API."""
+    from gammapy_b200 import ExpCutoffPowerLawSpectralModel, LogParabolaSpectralModel, PowerLawSpectralModel
+
+    assert_allclose(PowerLawSpectralModel(index=2.3, amplitude=4, reference=1).integral(1.0, 10.0),
+                    2.9227116204223784, rtol=1e-7)
+    assert_allclose(ExpCutoffPowerLawSpectralModel(index=1.6, amplitude=4, reference=1, lambda_=0.1).integral(1.0, 10.0),
+                    3.765838739678921, rtol=1e-5)
+    assert_allclose(LogParabolaSpectralModel(alpha=2.3, amplitude=4, reference=1, beta=0.5).integral(1.0, 10.0),
+                    2.255689748270628, rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# kernel 2: PSF convolution
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,K", [((97, 113), 67), ((40, 31), 9), ((5, 7), 21), ((200, 227), 101)])
+def test_psf_convolve(ctx, shape, K):
+    from gammapy_b200 import _lib
+    from oracle import evaluator
+
+    rng = np.random.RandomState(3)
+    img = rng.gamma(0.5, 1.0, shape).astype(np.float32)
+    img[rng.uniform(size=shape) < 0.5] = 0
+    yy, xx = np.mgrid[:K, :K] - (K - 1) / 2
+    planes = []
+    for s in (0.8, 2.0, K / 7.0):
+        k = np.exp(-0.5 * (xx**2 + yy**2) / s**2) * (1 + 0.1 * xx / K)  # slightly asymmetric: catches a missing flip
+        k[np.hypot(xx, yy) > 3.7 * s] = 0
+        planes.append(k / k.sum())
+    kern = np.array(planes)
+    want = evaluator.convolve_exact64(img, kern)
+    out = np.empty((3,) + shape, dtype=np.float32)
+    k32 = np.ascontiguousarray(kern, dtype=np.float32)
+    _lib.check(ctx.lib.gpy_psf_convolve(ctx.handle, _ptr(img), shape[0], shape[1], _ptr(k32), 3, K, _ptr(out)))
+    assert_allclose(out, want, rtol=2e-6, atol=1e-7 * float(want.max()))
+    ref32 = evaluator.convolve_fft32(img, kern)
+    assert_allclose(out, ref32, rtol=1e-5, atol=4 * EPS32 * float(want.max()))
+
+
+def test_convolve_vs_smooth_api(ctx):
+    """maps/wcs/tests/test_ndmap.py:622-635 shape: Map.convolve with a normalised Gaussian kernel conserves the sum."""
+    from gammapy_b200 import Map, PSFKernel, WcsGeom
+
+    geom = WcsGeom.create(binsz=0.05, width=(5, 5))
+    m = Map.from_geom(geom)
+    m.data[50, 50] = 1.0
+    kernel = PSFKernel.from_gauss(geom, sigma=0.1, max_radius=1.0)
+    out = m.convolve(kernel)
+    assert out.data.shape == m.data.shape
+    assert_allclose(out.data.sum(), 1.0, rtol=1e-5)
+    assert out.data[50, 50] == out.data.max()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# full path: npred + Cash
+# ---------------------------------------------------------------------------------------------------------
+def _check_npred(got, de_fft, de_exact):
+    want_exact = de_exact.npred()
+    want_fft = de_fft.npred()
+    bkg = de_exact.npred_background()
+    sig = want_exact - (bkg if bkg is not None else 0.0)
+    # exact arithmetic oracle: pure relative tolerance on total npred
+    assert_allclose(got, want_exact, rtol=1e-5, atol=1e-12 * float(want_exact.max()))
+    # the reference's float32 FFT: relative 1e-5 plus its own noise floor per energy slice
+    floor = 4 * EPS32 * sig.reshape(sig.shape[0], -1).max(axis=1)[:, None, None]
+    assert np.all(np.abs(got - want_fft) <= 1e-5 * np.abs(want_fft) + floor)
+
+
+@pytest.mark.parametrize("width,mask_radius", [((2.0, 2.0), 0.9), ((4.0, 4.0), 1.8), ((1.5, 1.0), None)])
+def test_c1_npred_and_stat(ctx, width, mask_radius):
+    from gammapy_b200 import configs
+    from oracle import adapter
+
+    ds = configs.make_c1(width=width, mask_radius=mask_radius)
+    de_fft = adapter.evaluator_for(ds, conv="fft32")
+    de_exact = adapter.evaluator_for(ds, conv="exact64")
+    got = ds.npred().data
+    assert got.dtype == np.float64 and got.shape == ds.data_shape
+    _check_npred(got, de_fft, de_exact)
+    # cutout of the evaluator = parent slices of _cutout_view
+    st = ds.evaluator_state("model-simu")
+    ys, xs = de_fft.evaluators["model-simu"].slices
+    assert (st["x0"], st["y0"], st["cx"], st["cy"]) == (xs.start, ys.start, xs.stop - xs.start, ys.stop - ys.start)
+    # counts drawn with the reference's legacy RandomState from the oracle npred, shared by both sides
+    counts = de_fft.fake(0)
+    de_exact.ds.counts = counts
+    from gammapy_b200 import Map
+
+    ds.counts = Map.from_geom(ds._geom, data=counts, dtype=float)
+    stat = ds.stat_sum_likelihood()
+    assert abs(stat - de_exact.stat_sum()) < 1e-3
+    assert abs(stat - de_fft.stat_sum()) < 1e-3
+    assert abs(stat - de_fft.stat_sum(use_reference=False)) < 1e-3
+
+
+def test_npred_psf_after_edisp_total_gpu(ctx):
+    """datasets/tests/test_map.py:1418-1445 on the GPU path: sum(npred) = 129553.858658."""
+    from gammapy_b200 import (FoVBackgroundModel, MapAxis, MapDataset, PointSpatialModel, PowerLawSpectralModel,
+                              PSFMap, SkyModel, WcsGeom)
+
+    energy_axis = MapAxis.from_energy_bounds("1 TeV", "10 TeV", nbin=3)
+    energy_axis_true = MapAxis.from_energy_bounds("0.8 TeV", "15 TeV", nbin=6, name="energy_true")
+    geom = WcsGeom.create(width=4, binsz=0.02, axes=[energy_axis])
+    dataset = MapDataset.create(geom=geom, energy_axis_true=energy_axis_true)
+    dataset.background.data += 1
+    dataset.exposure.data += 1e12
+    dataset.mask_safe.data += True
+    dataset.psf = PSFMap.from_gauss(energy_axis_true=energy_axis_true, sigma=0.2)
+    model = SkyModel(spectral_model=PowerLawSpectralModel(), spatial_model=PointSpatialModel(), name="test-model")
+    dataset.models = [FoVBackgroundModel(dataset_name=dataset.name), model]
+    npred = dataset.npred()
+    assert_allclose(npred.data.sum(), 129553.858658)
+
+
+def test_c2_five_sources_and_batch_scan(ctx):
+    from gammapy_b200 import Datasets, Map, configs
+    from oracle import adapter
+
+    ds = configs.make_c2()
+    de_fft = adapter.evaluator_for(ds, conv="fft32")
+    de_exact = adapter.evaluator_for(ds, conv="exact64")
+    got = ds.npred().data
+    _check_npred(got, de_fft, de_exact)
+    # per-model signal (npred_signal(model_names=...)) against the oracle's per-evaluator cubes
+    _, parts = de_exact.npred_signal(per_model=True)
+    for name in ("src-0", "src-2", "src-3"):
+        sig = ds.npred_signal(model_names=[name]).data
+        assert_allclose(sig, parts[name], rtol=1e-5, atol=1e-7 * float(parts[name].max()))
+    counts = de_fft.fake(1)
+    de_exact.ds.counts = counts
+    ds.counts = Map.from_geom(ds._geom, data=counts, dtype=float)
+    datasets = Datasets([ds])
+    base = datasets.stat_sum()
+    assert abs(base - de_exact.stat_sum()) < 1e-3
+    # 256-point profile of the index of source 0, all in one launch == one by one == oracle
+    par = ds.models["src-0"].spectral_model.index
+    values, plist = datasets.parameter_vector()
+    col = [i for i, p in enumerate(plist) if p is par][0]
+    scan = np.linspace(1.8, 2.8, 256)
+    grid = np.tile(values, (256, 1))
+    grid[:, col] = scan
+    batch = datasets.stat_sum_batch(grid)
+    assert batch.shape == (256,)
+    for k in (0, 100, 255):
+        par.value = scan[k]
+        one = datasets.stat_sum()
+        assert abs(one - batch[k]) < 1e-6
+        adapter.refresh_models(de_exact, ds)
+        assert abs(batch[k] - de_exact.stat_sum()) < 1e-3
+    par.value = 2.3
+    # batch with a moving spatial parameter: every vector gets its own re-convolved cube
+    lon = ds.models["src-1"].spatial_model.lon_0
+    col = [i for i, p in enumerate(plist) if p is lon][0]
+    grid = np.tile(values, (3, 1))
+    grid[:, col] += [0.0, 0.013, -0.02]
+    batch = datasets.stat_sum_batch(grid)
+    assert abs(batch[0] - base) < 1e-6
+    for k in (1, 2):
+        lon.value = grid[k, col]
+        adapter.refresh_models(de_exact, ds)
+        assert abs(batch[k] - de_exact.stat_sum()) < 1e-3
+    lon.value = values[col]
+
+
+def test_evaluator_cache_semantics(ctx):
+    """datasets/tests/test_evaluator.py:242-279 spirit: spatial flux is re-evaluated only when spatial
+    parameters change; the cutout is re-centred only after a drift > r_eval + 0.1 deg."""
+    from gammapy_b200 import configs
+    from oracle import adapter
+
+    ds = configs.make_c1(width=(4.0, 4.0), mask_radius=1.8)
+    de = adapter.evaluator_for(ds, conv="exact64")
+    model = ds.models["model-simu"]
+    ds.npred()
+    de.npred()
+    s0 = ds.evaluator_state("model-simu")
+    assert s0["n_spatial_evals"] == 1 and s0["oversampling"] == 1
+    model.spectral_model.index.value = 2.5
+    model.spectral_model.amplitude.value = 2e-11
+    ds.npred()
+    assert ds.evaluator_state("model-simu")["n_spatial_evals"] == 1
+    model.spatial_model.lon_0.value = 0.3  # small drift: same cutout, new convolution
+    adapter.refresh_models(de, ds)
+    got, want = ds.npred().data, de.npred()
+    s1 = ds.evaluator_state("model-simu")
+    assert s1["n_spatial_evals"] == 2
+    assert (s1["x0"], s1["y0"], s1["cx"], s1["cy"]) == (s0["x0"], s0["y0"], s0["cx"], s0["cy"])
+    assert_allclose(got, want, rtol=1e-5)
+    model.spatial_model.sigma.value = 0.05  # r_eval shrinks to 0.25 deg: the 0.3 deg offset from (0, 0) now exceeds
+    model.spatial_model.lon_0.value = 0.5   # r_eval + 0.1 -> update() re-centres the cutout
+    adapter.refresh_models(de, ds)
+    got, want = ds.npred().data, de.npred()
+    s2 = ds.evaluator_state("model-simu")
+    ys, xs = de.evaluators["model-simu"].slices
+    assert (s2["x0"], s2["y0"], s2["cx"], s2["cy"]) == (xs.start, ys.start, xs.stop - xs.start, ys.stop - ys.start)
+    assert (s2["cx"], s2["cy"]) != (s0["cx"], s0["cy"])
+    assert s2["oversampling"] == 2
+    assert_allclose(got, want, rtol=1e-5, atol=1e-12 * want.max())
+    model.spectral_model.amplitude.value = 0.0  # evaluator.py:385-389
+    assert_allclose(ds.npred_signal().data.sum(), 0)
+
+
+def test_source_outside_mask_does_not_contribute(ctx):
+    from gammapy_b200 import configs
+
+    ds = configs.make_c1(width=(4.0, 4.0), mask_radius=0.5)
+    ds.models["model-simu"].spatial_model.lon_0.value = -1.9
+    ds.models["model-simu"].spatial_model.lat_0.value = -1.9
+    ds.models["model-simu"].spatial_model.sigma.value = 0.02
+    sig = ds.npred_signal().data
+    assert sig.sum() == 0
+    assert ds.evaluator_state("model-simu")["contributes"] == 0
+
+
+def test_joint_datasets_sum(ctx):
+    from gammapy_b200 import Map, configs
+    from oracle import adapter
+
+    datasets = configs.make_c4(n_obs=3, width=(2.0, 2.0), mask_radius=0.9)
+    des = []
+    for i, ds in enumerate(datasets):
+        de = adapter.evaluator_for(ds, conv="exact64")
+        counts = de.fake(100 + i)
+        ds.counts = Map.from_geom(ds._geom, data=counts, dtype=float)
+        des.append(de)
+    total, per = datasets._get_engine().stat_sum(per_dataset=True)
+    want = [de.stat_sum() for de in des]
+    assert_allclose(per, want, atol=1e-3, rtol=0)
+    assert abs(total - sum(want)) < 1e-3
+    assert abs(datasets.stat_sum() - total) < 1e-9
+
+
+def test_errors_are_loud(ctx):
+    from gammapy_b200 import GaussianSpatialModel, MapAxis, PowerLawSpectralModel, SkyModel, WcsGeom, configs
+
+    with pytest.raises(NotImplementedError):
+        WcsGeom.create(skydir=(0, 10), binsz=0.1, width=2)  # oblique CAR
+    ds = configs.make_dataset(width=(1.0, 1.0), mask_radius=None)
+    bad = SkyModel(spatial_model=GaussianSpatialModel(frame="icrs"), spectral_model=PowerLawSpectralModel(), name="x")
+    ds.models = [bad]
+    with pytest.raises(NotImplementedError):
+        ds.npred()
+    ds.models = []
+    ds.counts = None
+    with pytest.raises(ValueError):
+        ds.stat_sum_likelihood()
+    assert MapAxis.from_energy_bounds(1, 10, 3).nbin == 3
