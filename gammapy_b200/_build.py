@@ -29,7 +29,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + SOURCES + ["-o", LIB]
+    extra = os.environ.get("GPY_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + SOURCES + ["-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(" ".join(cmd))

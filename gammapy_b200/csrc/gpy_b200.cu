@@ -554,7 +554,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   std::vector<size_t> job_flux_off;
   size_t flux_len = 0;
   int n_tiles = 0, max_inst = 1;
-  size_t max_fold_smem = 0;
+  int max_nT = 0, max_nRp = 0, max_G = 0;
   const bool sequential = (B == 1);
 
   for (int d = 0; d < D; ++d) {
@@ -685,13 +685,20 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       ev.inst_count = (int)insts.size() - ev.inst_begin;
       max_inst = std::max(max_inst, ev.inst_count);
     }
-    size_t smem = ((size_t)ds->n_groups * ds->nT * gpy::kFoldTPX + (size_t)ds->n_groups * ds->nT * ds->nRp + ds->nRp + 8) *
-                  sizeof(double);
-    max_fold_smem = std::max(max_fold_smem, smem);
+    max_nT = std::max(max_nT, ds->nT);
+    max_nRp = std::max(max_nRp, ds->nRp);
+    max_G = std::max(max_G, ds->n_groups);
   }
-  max_fold_smem += (size_t)max_inst * sizeof(int);
+  // sized for the largest dataset of the call (nT * nRp of one dataset bounds every other's)
+  size_t max_fold_smem = 0;
+  for (int d = 0; d < D; ++d)
+    max_fold_smem = std::max(max_fold_smem, gpy::fold_smem_bytes(rq.datasets[d]->n_groups, rq.datasets[d]->nT,
+                                                                 rq.datasets[d]->nRp, max_inst));
+  (void)max_nT;
+  (void)max_nRp;
+  (void)max_G;
   if (max_fold_smem > (size_t)c->max_smem_optin)
-    return fail(GPY_ERR_UNSUPPORTED, "energy axes too large for the fused fold kernel (%zu bytes of shared memory)",
+    return fail(GPY_ERR_UNSUPPORTED, "energy axes / source list too large for the fused fold kernel (%zu bytes of shared memory)",
                 max_fold_smem);
 
   // tile -> dataset table, cached per dataset list
@@ -748,6 +755,8 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   if (max_fold_smem > c->fold_smem_set) {
     CUDA_TRY(cudaFuncSetAttribute(gpy::fold_cash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)max_fold_smem));
+    CUDA_TRY(cudaFuncSetAttribute(gpy::fold_cash_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
     c->fold_smem_set = max_fold_smem;
   }
   gpy::fold_cash_kernel<<<(unsigned)((size_t)B * n_tiles), gpy::kFoldThreads, max_fold_smem, c->stream>>>(fp);

@@ -413,9 +413,20 @@ struct FoldParams {
 };
 
 constexpr int kFoldTPX = 128;      // pixels per tile
-constexpr int kFoldThreads = 128;
+constexpr int kFoldThreads = 256;
+constexpr int kFoldTCH = 16;       // true-energy bins staged in shared memory per pass
+#ifndef GPY_FOLD_MINBLOCKS
+#define GPY_FOLD_MINBLOCKS 3
+#endif
 
-__device__ __forceinline__ double block_sum_128(double v, double* scratch) {
+// Shared memory of one block: v chunk [G][TCH][TPX] f64, pdf [G][nT][nRp] f64, bkgfac [nRp], scratch [8],
+// overlap list [max_inst] InstDev.
+__host__ __device__ inline size_t fold_smem_bytes(int G, int nT, int nRp, int max_inst) {
+  return ((size_t)G * kFoldTCH * kFoldTPX + (size_t)G * nT * nRp + nRp + 8) * sizeof(double) +
+         (size_t)max_inst * sizeof(InstDev);
+}
+
+__device__ __forceinline__ double block_sum_256(double v, double* scratch) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -429,7 +440,14 @@ __device__ __forceinline__ double block_sum_128(double v, double* scratch) {
   return r;
 }
 
-__global__ void __launch_bounds__(kFoldThreads) fold_cash_kernel(const FoldParams P) {
+// One block = one tile of 128 consecutive pixels x one parameter vector.
+//   phase 1 (per pass of 16 true-energy bins): thread (pixel quad q, energy slot) computes
+//       v[g][t][p] = 1e4 * exposure[t,p] * sum_s F_s[t] * conv_s[t,p]          (fp64, float4 loads)
+//     for the sources whose cutout overlaps the tile, into shared memory;
+//   phase 2: thread (pixel pair, reco chunk of 8) accumulates acc[r] += pdf[t][r] * v[t][p] over the
+//     non-zero band of the edisp matrix; accumulators stay in registers across the passes;
+//   epilogue: + background * norm (E/E0)^-tilt, clip, masked Cash term, block reduction.
+__global__ void __launch_bounds__(kFoldThreads, GPY_FOLD_MINBLOCKS) fold_cash_kernel(const FoldParams P) {
   extern __shared__ __align__(16) double fold_smem[];
   const int b = blockIdx.x % P.B;
   const int tile = blockIdx.x / P.B;
@@ -441,11 +459,11 @@ __global__ void __launch_bounds__(kFoldThreads) fold_cash_kernel(const FoldParam
   const int npx = (int)min((long long)kFoldTPX, D.P - p0);
   const int tid = threadIdx.x;
 
-  double* vs = fold_smem;                                   // [G][nT][TPX]
-  double* pdf_s = vs + (size_t)G * nT * kFoldTPX;           // [G][nT][nRp]
-  double* bkgfac = pdf_s + (size_t)G * nT * nRp;            // [nRp]
-  double* scratch = bkgfac + nRp;                           // [8]
-  int* list = reinterpret_cast<int*>(scratch + 8);          // [max_inst]
+  double* vs = fold_smem;                                      // [G][TCH][TPX]
+  double* pdf_s = vs + (size_t)G * kFoldTCH * kFoldTPX;        // [G][nT][nRp]
+  double* bkgfac = pdf_s + (size_t)G * nT * nRp;               // [nRp]
+  double* scratch = bkgfac + nRp;                              // [8]
+  InstDev* slist = reinterpret_cast<InstDev*>(scratch + 8);    // [max_inst]
   __shared__ int n_list;
 
   for (int i = tid; i < G * nT * nRp; i += kFoldThreads) pdf_s[i] = D.edisp[i];
@@ -455,144 +473,171 @@ __global__ void __launch_bounds__(kFoldThreads) fold_cash_kernel(const FoldParam
       fac = ev.bkg_norm * pow(D.ecenter[tid] / ev.bkg_ref, -ev.bkg_tilt);
     bkgfac[tid] = fac;
   }
-  // rows covered by this tile -> instances whose cutout can overlap it
+  // sources whose cutout overlaps the rows (and, for a single-row tile, the columns) of this tile
   const int y_first = (int)(p0 / D.nx), y_last = (int)((p0 + npx - 1) / D.nx);
-  if (tid == 0) {
+  const int x_first = (int)(p0 - (long long)y_first * D.nx);
+  const int x_last = (int)(p0 + npx - 1 - (long long)y_last * D.nx);
+  if (tid < 32) {
     int n = 0;
-    for (int i = 0; i < ev.inst_count; ++i) {
-      const InstDev& in = P.insts[ev.inst_begin + i];
-      if (in.y0 <= y_last && in.y0 + in.cy > y_first) list[n++] = ev.inst_begin + i;
+    for (int base = 0; base < ev.inst_count; base += 32) {
+      const int i = base + tid;
+      bool ov = false;
+      InstDev in;
+      if (i < ev.inst_count) {
+        in = P.insts[ev.inst_begin + i];
+        ov = in.y0 <= y_last && in.y0 + in.cy > y_first;
+        if (ov && y_first == y_last) ov = in.x0 <= x_last && in.x0 + in.cx > x_first;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ov);
+      if (ov) slist[n + __popc(m & ((1u << tid) - 1u))] = in;
+      n += __popc(m);
     }
-    n_list = n;
+    if (tid == 0) n_list = n;
   }
   __syncthreads();
   const int nl = n_list;
 
-  // ---- phase 1: v[g][t][p] = 1e4 * exposure[t,p] * sum_s F_s[t] * conv_s[t,p]  (fp64) ----
-  const bool vec4 = (D.nx % 4) == 0;
-  if (vec4) {
-    const int q = tid & 31, slot = tid >> 5;  // 32 pixel quads x 4 energy slots
-    const long long pq = p0 + 4 * q;
-    const bool live = 4 * q < npx;            // npx is a multiple of 4 when nx % 4 == 0
-    const int y = live ? (int)(pq / D.nx) : 0, x = live ? (int)(pq - (long long)y * D.nx) : 0;
-    for (int g = 0; g < G; ++g) {
-      for (int t = slot; t < nT; t += 4) {
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        if (live) {
-          for (int l = 0; l < nl; ++l) {
-            const InstDev in = P.insts[list[l]];
-            if (in.group != g) continue;
-            int ly = y - in.y0, lx = x - in.x0a;
-            if (ly < 0 || ly >= in.cy || lx < 0 || lx + 3 >= in.pitch) continue;
-            int tt = in.planes == 1 ? 0 : t;
-            const float4 c = __ldg(reinterpret_cast<const float4*>(
-                in.conv + ((size_t)tt * in.cy + ly) * in.pitch + lx));
-            const double F = P.flux[in.flux_off + t];
-            double a0 = F * (double)c.x, a1 = F * (double)c.y, a2 = F * (double)c.z, a3 = F * (double)c.w;
-            // WcsNDMap.stack(nan_to_num=True): non-finite source values do not enter the sum
-            s0 += isfinite(a0) ? a0 : 0.0;
-            s1 += isfinite(a1) ? a1 : 0.0;
-            s2 += isfinite(a2) ? a2 : 0.0;
-            s3 += isfinite(a3) ? a3 : 0.0;
-          }
-          const float4 e = __ldg(reinterpret_cast<const float4*>(D.exposure + (size_t)t * D.P + pq));
-          s0 = (s0 * (double)e.x) * 1e4;
-          s1 = (s1 * (double)e.y) * 1e4;
-          s2 = (s2 * (double)e.z) * 1e4;
-          s3 = (s3 * (double)e.w) * 1e4;
-        }
-        double* dst = vs + ((size_t)g * nT + t) * kFoldTPX + 4 * q;
-        *reinterpret_cast<double2*>(dst) = make_double2(s0, s1);
-        *reinterpret_cast<double2*>(dst + 2) = make_double2(s2, s3);
-      }
-    }
-  } else {
-    const long long p = p0 + tid;
-    const bool live = tid < npx;
-    const int y = live ? (int)(p / D.nx) : 0, x = live ? (int)(p - (long long)y * D.nx) : 0;
-    for (int g = 0; g < G; ++g) {
-      for (int t = 0; t < nT; ++t) {
-        double s = 0.0;
-        if (live) {
-          for (int l = 0; l < nl; ++l) {
-            const InstDev in = P.insts[list[l]];
-            if (in.group != g) continue;
-            int ly = y - in.y0, lx = x - in.x0;
-            if (ly < 0 || ly >= in.cy || lx < 0 || lx >= in.cx) continue;
-            int tt = in.planes == 1 ? 0 : t;
-            float c = __ldg(in.conv + ((size_t)tt * in.cy + ly) * in.pitch + (x - in.x0a));
-            double a = P.flux[in.flux_off + t] * (double)c;
-            s += isfinite(a) ? a : 0.0;
-          }
-          s = (s * (double)__ldg(D.exposure + (size_t)t * D.P + p)) * 1e4;
-        }
-        vs[((size_t)g * nT + t) * kFoldTPX + tid] = s;
-      }
-    }
+  // phase-1 coordinates: 32 pixel quads x 8 energy slots
+  const int q = tid & 31, slot = tid >> 5;
+  const long long pq = p0 + 4 * q;
+  const bool vec4 = (D.nx % 4) == 0;      // quads are row-aligned and 16-byte aligned
+  int qy[4], qx[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long p = pq + k;
+    const bool live = 4 * q + k < npx;
+    qy[k] = live ? (int)(p / D.nx) : -1;
+    qx[k] = live ? (int)(p - (long long)qy[k] * D.nx) : 0;
   }
-  __syncthreads();
-
-  // ---- phase 2: edisp contraction on reco chunks of 8, two pixels per thread; Cash epilogue ----
-  const int pp = tid & 63, cpar = tid >> 6;
+  // phase-2 coordinates: 64 pixel pairs x 4 reco-chunk slots
+  const int pp = tid & 63, cslot = tid >> 6;
   const int nchunks = nRp >> 3;
+
   double stat = 0.0;
-  for (int c = cpar; c < nchunks; c += 2) {
+  for (int cbase = 0; cbase < nchunks; cbase += 4) {  // one pass for nR <= 32
+    const int c = cbase + cslot;
     double acc0[8], acc1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.0;
-    for (int g = 0; g < G; ++g) {
-      const int tlo = D.band[(g * nchunks + c) * 2], thi = D.band[(g * nchunks + c) * 2 + 1];
-      const double* vrow = vs + (size_t)g * nT * kFoldTPX + 2 * pp;
-      const double* prow = pdf_s + (size_t)g * nT * nRp + 8 * c;
-      for (int t = tlo; t < thi; ++t) {
-        const double2 v = *reinterpret_cast<const double2*>(vrow + (size_t)t * kFoldTPX);
-        const double2 m0 = *reinterpret_cast<const double2*>(prow + (size_t)t * nRp);
-        const double2 m1 = *reinterpret_cast<const double2*>(prow + (size_t)t * nRp + 2);
-        const double2 m2 = *reinterpret_cast<const double2*>(prow + (size_t)t * nRp + 4);
-        const double2 m3 = *reinterpret_cast<const double2*>(prow + (size_t)t * nRp + 6);
-        const double m[8] = {m0.x, m0.y, m1.x, m1.y, m2.x, m2.y, m3.x, m3.y};
+
+    for (int t0 = 0; t0 < nT; t0 += kFoldTCH) {
+      // ---- phase 1 ----
+      for (int g = 0; g < G; ++g) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc0[j] = fma(v.x, m[j], acc0[j]);
-          acc1[j] = fma(v.y, m[j], acc1[j]);
+        for (int tt = 0; tt < kFoldTCH / 8; ++tt) {
+          const int tl = slot + 8 * tt, t = t0 + tl;
+          double s[4] = {0.0, 0.0, 0.0, 0.0};
+          if (t < nT && qy[0] >= 0) {
+            for (int l = 0; l < nl; ++l) {
+              const InstDev& in = slist[l];
+              if (in.group != g) continue;
+              const int tp = in.planes == 1 ? 0 : t;
+              const double F = P.flux[in.flux_off + t];
+              const float* plane = in.conv + (size_t)tp * in.cy * in.pitch;
+              const int ly = qy[0] - in.y0, lx = qx[0] - in.x0a;
+              if (vec4) {
+                if (ly < 0 || ly >= in.cy || lx < 0 || lx >= in.pitch) continue;
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(plane + (size_t)ly * in.pitch + lx));
+                const double a0 = F * (double)cv.x, a1 = F * (double)cv.y, a2 = F * (double)cv.z,
+                             a3 = F * (double)cv.w;
+                // WcsNDMap.stack(nan_to_num=True): non-finite source values do not enter the sum
+                s[0] += isfinite(a0) ? a0 : 0.0;
+                s[1] += isfinite(a1) ? a1 : 0.0;
+                s[2] += isfinite(a2) ? a2 : 0.0;
+                s[3] += isfinite(a3) ? a3 : 0.0;
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (qy[k] < 0) continue;
+                  const int lyk = qy[k] - in.y0, lxk = qx[k] - in.x0;
+                  if (lyk < 0 || lyk >= in.cy || lxk < 0 || lxk >= in.cx) continue;
+                  const double a = F * (double)__ldg(plane + (size_t)lyk * in.pitch + (qx[k] - in.x0a));
+                  s[k] += isfinite(a) ? a : 0.0;
+                }
+              }
+            }
+            const float* erow = D.exposure + (size_t)t * D.P + pq;
+            if (vec4) {
+              const float4 e = __ldg(reinterpret_cast<const float4*>(erow));
+              s[0] = (s[0] * (double)e.x) * 1e4;
+              s[1] = (s[1] * (double)e.y) * 1e4;
+              s[2] = (s[2] * (double)e.z) * 1e4;
+              s[3] = (s[3] * (double)e.w) * 1e4;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (qy[k] >= 0) s[k] = (s[k] * (double)__ldg(erow + k)) * 1e4;
+            }
+          }
+          double* dst = vs + ((size_t)g * kFoldTCH + tl) * kFoldTPX + 4 * q;
+          *reinterpret_cast<double2*>(dst) = make_double2(s[0], s[1]);
+          *reinterpret_cast<double2*>(dst + 2) = make_double2(s[2], s[3]);
         }
       }
-    }
+      __syncthreads();
+      // ---- phase 2 ----
+      if (c < nchunks) {
+        for (int g = 0; g < G; ++g) {
+          const int blo = D.band[(g * nchunks + c) * 2], bhi = D.band[(g * nchunks + c) * 2 + 1];
+          const int tlo = max(blo, t0), thi = min(bhi, t0 + kFoldTCH);
+          const double* vrow = vs + (size_t)g * kFoldTCH * kFoldTPX + 2 * pp;
+          const double* prow = pdf_s + (size_t)g * nT * nRp + 8 * c;
+          for (int t = tlo; t < thi; ++t) {
+            const double2 v = *reinterpret_cast<const double2*>(vrow + (size_t)(t - t0) * kFoldTPX);
+            const double2 m0 = *reinterpret_cast<const double2*>(prow + (size_t)t * nRp);
+            const double2 m1 = *reinterpret_cast<const double2*>(prow + (size_t)t * nRp + 2);
+            const double2 m2 = *reinterpret_cast<const double2*>(prow + (size_t)t * nRp + 4);
+            const double2 m3 = *reinterpret_cast<const double2*>(prow + (size_t)t * nRp + 6);
+            const double m[8] = {m0.x, m0.y, m1.x, m1.y, m2.x, m2.y, m3.x, m3.y};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int r = 8 * c + j;
-      if (r >= nR) break;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int lp = 2 * pp + k;
-        if (lp >= npx) continue;
-        const size_t idx = (size_t)r * D.P + p0 + lp;
-        double mu = k == 0 ? acc0[j] : acc1[j];
-        if (P.include_background) {
-          if (D.background) mu += (double)__ldg(D.background + idx) * bkgfac[r];
-          if (mu < 0.0) mu = 0.0;  // npred_total.data[npred_total.data < 0.0] = 0 (map.py:787)
-        }
-        if (P.npred_out) P.npred_out[idx] = mu;
-        if (D.counts) {
-          const bool m = D.mask ? (__ldg(D.mask + idx) != 0) : true;
-          if (m) {
-            const double n = (double)__ldg(D.counts + idx);
-            double npr, lognpr = 0.0;
-            if (mu > kTrunc) {
-              npr = mu;
-              if (n > 0.0) lognpr = log(mu);
-            } else {
-              npr = kTrunc;
-              lognpr = P.log_trunc;
+            for (int j = 0; j < 8; ++j) {
+              acc0[j] = fma(v.x, m[j], acc0[j]);
+              acc1[j] = fma(v.y, m[j], acc1[j]);
             }
-            stat += npr;
-            if (n > 0.0) stat -= n * lognpr;
+          }
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- epilogue for reco chunk c: background, clip, Cash ----
+    if (c < nchunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = 8 * c + j;
+        if (r >= nR) break;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int lp = 2 * pp + k;
+          if (lp >= npx) continue;
+          const size_t idx = (size_t)r * D.P + p0 + lp;
+          double mu = k == 0 ? acc0[j] : acc1[j];
+          if (P.include_background) {
+            if (D.background) mu += (double)__ldg(D.background + idx) * bkgfac[r];
+            if (mu < 0.0) mu = 0.0;  // npred_total.data[npred_total.data < 0.0] = 0 (map.py:787)
+          }
+          if (P.npred_out) P.npred_out[idx] = mu;
+          if (D.counts) {
+            const bool m = D.mask ? (__ldg(D.mask + idx) != 0) : true;
+            if (m) {
+              const double n = (double)__ldg(D.counts + idx);
+              double npr, lognpr = 0.0;
+              if (mu > kTrunc) {
+                npr = mu;
+                if (n > 0.0) lognpr = log(mu);
+              } else {
+                npr = kTrunc;
+                lognpr = P.log_trunc;
+              }
+              stat += npr;
+              if (n > 0.0) stat -= n * lognpr;
+            }
           }
         }
       }
     }
   }
-  double total = block_sum_128(stat, scratch);
+  double total = block_sum_256(stat, scratch);
   if (tid == 0) P.partials[(size_t)b * P.n_tiles + tile] = total;
 }
 
