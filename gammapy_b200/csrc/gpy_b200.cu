@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -244,7 +245,10 @@ struct gpy_context {
   std::vector<uint64_t> tiles_ver;
   double* stat_pinned = nullptr;
   size_t stat_pinned_cap = 0;
-  size_t fold_smem_set = 0, conv_smem_set = 0;
+  size_t fold_smem_set = 0, conv_smem_set = 0, tma_smem_set[2] = {0, 0};
+  int tma_blocks_per_sm[2] = {0, 0};
+  int num_sms = 0;
+  bool force_generic = false;
   double log_trunc = 0.0;
   int max_smem_optin = 0;
 };
@@ -261,6 +265,7 @@ struct gpy_dataset {
   std::vector<gpy::ConvPlane> planes;
   int max_h = 0, max_kw = 4;
   bool has_psf = false, has_diag = false;
+  int groups_used = 1;  // 2 when some source opts out of the edisp (diagonal response)
   std::vector<Source> sources;
   gpy_background_desc bkg{0, -1, -1, -1};
 };
@@ -554,7 +559,8 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   std::vector<size_t> job_flux_off;
   size_t flux_len = 0;
   int n_tiles = 0, max_inst = 1;
-  int max_nT = 0, max_nRp = 0, max_G = 0;
+  int max_nT = 0, max_nR = 0, max_nRp = 0, max_G = 0;
+  bool tma_ok = true;
   const bool sequential = (B == 1);
 
   for (int d = 0; d < D; ++d) {
@@ -566,7 +572,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     dd.nT = ds->nT;
     dd.nR = ds->nR;
     dd.nRp = ds->nRp;
-    dd.n_groups = ds->n_groups;
+    dd.n_groups = ds->groups_used;
     dd.P = (long long)ds->geom.nx * ds->geom.ny;
     dd.tile_begin = n_tiles;
     dd.n_tiles = (int)((dd.P + gpy::kFoldTPX - 1) / gpy::kFoldTPX);
@@ -668,6 +674,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         in.planes = slot->planes;
         in.group = (src.desc.apply_edisp || !ds->has_diag) ? 0 : 1;
         in.flux_off = (int)flux_len;
+        in.plane_stride = slot->planes == 1 ? 0 : rect.cy * slot->pitch;
         in.conv = (const float*)(slot->planes == 1 ? slot->w.p : slot->conv.p);
         insts.push_back(in);
         gpy::FluxJob job;
@@ -686,20 +693,27 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       max_inst = std::max(max_inst, ev.inst_count);
     }
     max_nT = std::max(max_nT, ds->nT);
+    max_nR = std::max(max_nR, ds->nR);
     max_nRp = std::max(max_nRp, ds->nRp);
-    max_G = std::max(max_G, ds->n_groups);
+    max_G = std::max(max_G, ds->groups_used);
+    const size_t P64 = (size_t)ds->geom.nx * ds->geom.ny;
+    auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+    if (ds->geom.nx % 4 != 0 || P64 % 16 != 0 || !al16(ds->exposure) || !al16(ds->background) || !al16(ds->counts) ||
+        !al16(ds->mask) || P64 * (size_t)std::max(ds->nT, ds->nR) > (size_t)INT32_MAX)
+      tma_ok = false;
   }
-  // sized for the largest dataset of the call (nT * nRp of one dataset bounds every other's)
+  const gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G, max_inst);
+  if (lay.total > (size_t)c->max_smem_optin || c->force_generic) tma_ok = false;
   size_t max_fold_smem = 0;
-  for (int d = 0; d < D; ++d)
-    max_fold_smem = std::max(max_fold_smem, gpy::fold_smem_bytes(rq.datasets[d]->n_groups, rq.datasets[d]->nT,
-                                                                 rq.datasets[d]->nRp, max_inst));
-  (void)max_nT;
-  (void)max_nRp;
-  (void)max_G;
-  if (max_fold_smem > (size_t)c->max_smem_optin)
-    return fail(GPY_ERR_UNSUPPORTED, "energy axes / source list too large for the fused fold kernel (%zu bytes of shared memory)",
-                max_fold_smem);
+  if (!tma_ok) {
+    for (int d = 0; d < D; ++d)
+      max_fold_smem = std::max(max_fold_smem, gpy::fold_smem_bytes(rq.datasets[d]->groups_used, rq.datasets[d]->nT,
+                                                                   rq.datasets[d]->nRp, max_inst));
+    if (max_fold_smem > (size_t)c->max_smem_optin)
+      return fail(GPY_ERR_UNSUPPORTED,
+                  "energy axes / source list too large for the fused fold kernel (%zu bytes of shared memory)",
+                  max_fold_smem);
+  }
 
   // tile -> dataset table, cached per dataset list
   bool same = (int)c->tiles_for.size() == D;
@@ -752,14 +766,36 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   fp.include_background = rq.include_background;
   fp.max_inst = max_inst;
   fp.log_trunc = c->log_trunc;
-  if (max_fold_smem > c->fold_smem_set) {
-    CUDA_TRY(cudaFuncSetAttribute(gpy::fold_cash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)max_fold_smem));
-    CUDA_TRY(cudaFuncSetAttribute(gpy::fold_cash_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  cudaSharedmemCarveoutMaxShared));
-    c->fold_smem_set = max_fold_smem;
+  fp.smem_nT = max_nT;
+  fp.smem_nR = max_nR;
+  fp.smem_nRp = max_nRp;
+  fp.smem_G = max_G;
+  const size_t n_items = (size_t)B * n_tiles;
+  if (tma_ok) {
+    const int variant = rq.npred_out ? 1 : 0;
+    auto kern = variant ? gpy::fold_cash_tma_kernel<true> : gpy::fold_cash_tma_kernel<false>;
+    if (lay.total > c->tma_smem_set[variant]) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
+      c->tma_smem_set[variant] = lay.total;
+      c->tma_blocks_per_sm[variant] = 0;
+    }
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, gpy::kFoldThreads, lay.total));
+    per_sm = std::max(per_sm, 1);
+    const unsigned grid = (unsigned)std::min(n_items, (size_t)per_sm * c->num_sms);
+    kern<<<grid, gpy::kFoldThreads, lay.total, c->stream>>>(fp);
+  } else {
+    if (max_fold_smem > c->fold_smem_set) {
+      CUDA_TRY(cudaFuncSetAttribute(gpy::fold_cash_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)max_fold_smem));
+      CUDA_TRY(cudaFuncSetAttribute(gpy::fold_cash_generic_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
+      c->fold_smem_set = max_fold_smem;
+    }
+    gpy::fold_cash_generic_kernel<<<(unsigned)n_items, gpy::kFoldThreads, max_fold_smem, c->stream>>>(fp);
   }
-  gpy::fold_cash_kernel<<<(unsigned)((size_t)B * n_tiles), gpy::kFoldThreads, max_fold_smem, c->stream>>>(fp);
   c->launches++;
   gpy::reduce_stat_kernel<<<dim3(B, D), 256, 0, c->stream>>>((const double*)c->partials.p, fp.ds, n_tiles, D,
                                                               (double*)c->stat.p);
@@ -802,6 +838,8 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
   }
   cudaEventCreateWithFlags(&c->h2d_done, cudaEventDisableTiming);
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+  c->force_generic = std::getenv("GPY_FORCE_GENERIC_FOLD") != nullptr;
   c->log_trunc = std::log((double)(float)1e-25);  // Cython: log(<float>TRUNCATION_VALUE), .pyx:35
   *out = c;
   return GPY_OK;
@@ -949,7 +987,11 @@ int gpy_dataset_set_models(gpy_dataset_t* ds, const gpy_source_desc* sources, in
     }
   ds->sources.clear();
   ds->sources.resize(n_sources);
-  for (int i = 0; i < n_sources; ++i) ds->sources[i].desc = sources[i];
+  ds->groups_used = 1;
+  for (int i = 0; i < n_sources; ++i) {
+    ds->sources[i].desc = sources[i];
+    if (!sources[i].apply_edisp && ds->has_diag) ds->groups_used = 2;
+  }
   if (background)
     ds->bkg = *background;
   else

@@ -4,7 +4,8 @@
 //   K0  spectral_flux_kernel   energy-bin integrals of the spectral models           (a9 in SURVEY.md §8)
 //   K1  spatial_fill_kernel / spatial_oversample_kernel / solid_angle_kernel         (a10, a10p, a10g, a10d)
 //   K2  psf_conv_kernel        per-energy direct stencil, smem tiled, fp32            (a11)
-//   K3+K4 fold_cash_kernel     exposure x flux -> edisp contraction -> + background -> masked Cash,
+//   K3+K4 fold_cash_tma_kernel (bulk-copy staged, persistent) / fold_cash_generic_kernel (any shape)
+//                              exposure x flux -> edisp contraction -> + background -> masked Cash,
 //                              fp64 accumulate, batch of parameter vectors per launch  (a2-a6, a12-a14)
 //   reduce_stat_kernel         deterministic second stage of the stat reduction
 //   cash_sum_kernel            stand-alone (weighted) Cash for the compiled-stat registry (a3, a3')
@@ -387,7 +388,7 @@ struct InstDev {  // one source in one parameter vector
   int planes;          // nT, or 1 when the PSF is not applied (broadcast over energy)
   int group;           // edisp group
   int flux_off;        // offset of F[nT] in the flux buffer
-  int pad_;
+  int plane_stride;    // cy * pitch, or 0 when planes == 1 (same image for every energy)
   const float* conv;   // [planes, cy, pitch]
 };
 
@@ -408,6 +409,7 @@ struct FoldParams {
   int B, n_tiles, n_datasets;
   int include_background;   // add background model and clip at 0 (MapDataset.npred) or signal only
   int max_inst;             // capacity of the per-block overlap list
+  int smem_nT, smem_nR, smem_nRp, smem_G;  // largest axes of the launch: fixed shared-memory layout (bulk-copy kernel)
   int pad_;
   double log_trunc;         // log((double)(float)1e-25): Cython narrows the constant to C float
 };
@@ -447,7 +449,7 @@ __device__ __forceinline__ double block_sum_256(double v, double* scratch) {
 //   phase 2: thread (pixel pair, reco chunk of 8) accumulates acc[r] += pdf[t][r] * v[t][p] over the
 //     non-zero band of the edisp matrix; accumulators stay in registers across the passes;
 //   epilogue: + background * norm (E/E0)^-tilt, clip, masked Cash term, block reduction.
-__global__ void __launch_bounds__(kFoldThreads, GPY_FOLD_MINBLOCKS) fold_cash_kernel(const FoldParams P) {
+__global__ void __launch_bounds__(kFoldThreads, GPY_FOLD_MINBLOCKS) fold_cash_generic_kernel(const FoldParams P) {
   extern __shared__ __align__(16) double fold_smem[];
   const int b = blockIdx.x % P.B;
   const int tile = blockIdx.x / P.B;
@@ -639,6 +641,334 @@ __global__ void __launch_bounds__(kFoldThreads, GPY_FOLD_MINBLOCKS) fold_cash_ke
   }
   double total = block_sum_256(stat, scratch);
   if (tid == 0) P.partials[(size_t)b * P.n_tiles + tile] = total;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Bulk-copy (TMA engine) staged, persistent variant of the fused fold + Cash kernel.
+//
+// Each CTA loops over work items (tile of 128 pixels, parameter vector).  The exposure tile [nT][128],
+// and the background / counts / mask tiles [nR][128] of the NEXT item are fetched by 1-D
+// cp.async.bulk copies (one 512-byte row segment each, completion on an mbarrier) while the current
+// item is being computed, so phase 1, phase 2 and the Cash epilogue read shared memory only; the
+// per-source PSF-convolved cubes (irregular cutouts) are read with 128-bit __ldg loads.
+// Requirements (checked on the host, otherwise the generic kernel runs): nx % 4 == 0, P % 16 == 0,
+// 16-byte aligned cubes.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct FoldSmem {  // byte offsets of the fixed shared-memory layout
+  size_t es, bs, cs, ms, vs, pdf, bkgfac, scratch, slist, bars, total;
+};
+__host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int G, int max_inst) {
+  FoldSmem L;
+  size_t o = 0;
+  L.es = o;      o += (size_t)nT * kFoldTPX * 4;
+  L.bs = o;      o += (size_t)nR * kFoldTPX * 4;
+  L.cs = o;      o += (size_t)nR * kFoldTPX * 4;
+  L.ms = o;      o += ((size_t)nR * kFoldTPX + 15) / 16 * 16;
+  L.vs = o;      o += (size_t)G * kFoldTCH * kFoldTPX * 8;
+  L.pdf = o;     o += (size_t)G * nT * nRp * 8;
+  L.bkgfac = o;  o += (size_t)nRp * 8;
+  L.scratch = o; o += 8 * 8;
+  L.slist = o;   o += (size_t)max_inst * sizeof(InstDev);
+  L.bars = (o + 7) / 8 * 8;
+  L.total = L.bars + 2 * 8;
+  return L;
+}
+
+constexpr int kFoldLMax = 4;  // overlapping sources whose per-thread offsets live in registers
+
+template <bool WRITE_NPRED>
+__global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const FoldParams P) {
+  extern __shared__ __align__(128) unsigned char fold_raw[];
+  const FoldSmem L = fold_tma_layout(P.smem_nT, P.smem_nR, P.smem_nRp, P.smem_G, P.max_inst);
+  float* es = reinterpret_cast<float*>(fold_raw + L.es);
+  float* bs = reinterpret_cast<float*>(fold_raw + L.bs);
+  float* cs = reinterpret_cast<float*>(fold_raw + L.cs);
+  unsigned char* ms = fold_raw + L.ms;
+  double* vs = reinterpret_cast<double*>(fold_raw + L.vs);
+  double* pdf_s = reinterpret_cast<double*>(fold_raw + L.pdf);
+  double* bkgfac = reinterpret_cast<double*>(fold_raw + L.bkgfac);
+  double* scratch = reinterpret_cast<double*>(fold_raw + L.scratch);
+  InstDev* slist = reinterpret_cast<InstDev*>(fold_raw + L.slist);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + L.bars);  // [0] exposure, [1] epilogue inputs
+  __shared__ int n_list;
+
+  const int tid = threadIdx.x;
+  const int n_items = P.B * P.n_tiles;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // producers (warp 0): bulk copies of one item's tiles
+  auto issue_expo = [&](int item) {
+    const int tile = item / P.B;
+    const DatasetDev& D = P.ds[P.tile_ds[tile]];
+    const int p0 = (tile - D.tile_begin) * kFoldTPX;
+    const int npx = min(kFoldTPX, (int)D.P - p0);
+    const uint32_t row = (uint32_t)npx * 4u;
+    if (tid == 0) mbar_arrive_expect_tx(&bars[0], row * (uint32_t)D.nT);
+    __syncwarp();
+    for (int t = tid; t < D.nT; t += 32)
+      bulk_g2s(es + t * kFoldTPX, D.exposure + (size_t)t * D.P + p0, row, &bars[0]);
+  };
+  auto issue_epi = [&](int item) {
+    const int tile = item / P.B;
+    const DatasetDev& D = P.ds[P.tile_ds[tile]];
+    const int p0 = (tile - D.tile_begin) * kFoldTPX;
+    const int npx = min(kFoldTPX, (int)D.P - p0);
+    const uint32_t row = (uint32_t)npx * 4u;
+    uint32_t total = 0;
+    if (D.background && P.include_background) total += row * (uint32_t)D.nR;
+    if (D.counts) total += row * (uint32_t)D.nR;
+    if (D.counts && D.mask) total += (uint32_t)npx * (uint32_t)D.nR;
+    if (tid == 0) mbar_arrive_expect_tx(&bars[1], total);
+    __syncwarp();
+    for (int r = tid; r < D.nR; r += 32) {
+      const size_t off = (size_t)r * D.P + p0;
+      if (D.background && P.include_background) bulk_g2s(bs + r * kFoldTPX, D.background + off, row, &bars[1]);
+      if (D.counts) bulk_g2s(cs + r * kFoldTPX, D.counts + off, row, &bars[1]);
+      if (D.counts && D.mask) bulk_g2s(ms + r * kFoldTPX, D.mask + off, (uint32_t)npx, &bars[1]);
+    }
+  };
+
+  int item = blockIdx.x;
+  if (item < n_items && tid < 32) {
+    issue_expo(item);
+    issue_epi(item);
+  }
+  uint32_t parity = 0;
+  int cur_ds = -1;
+
+  const int q = tid & 31, slot = tid >> 5;   // phase 1: 32 pixel quads x 8 energy slots
+  const int pp = tid & 63, cslot = tid >> 6;  // phase 2: 64 pixel pairs x 4 reco-chunk slots
+
+  for (; item < n_items; item += gridDim.x, parity ^= 1u) {
+    const int b = item % P.B;
+    const int tile = item / P.B;
+    const int d = P.tile_ds[tile];
+    const DatasetDev D = P.ds[d];
+    const EvalDev ev = P.evals[(size_t)d * P.B + b];
+    const int nT = D.nT, nR = D.nR, nRp = D.nRp, G = D.n_groups;
+    const int p0 = (tile - D.tile_begin) * kFoldTPX;
+    const int npx = min(kFoldTPX, (int)D.P - p0);
+    const int next = item + gridDim.x;
+
+    if (d != cur_ds) {  // edisp matrices of this dataset (block-uniform branch)
+      for (int i = tid; i < G * nT * nRp; i += kFoldThreads) pdf_s[i] = D.edisp[i];
+      cur_ds = d;
+    }
+    if (tid < nRp) {
+      double fac = 1.0;
+      if (ev.bkg_enabled && tid < nR)  // PowerLawNormSpectralModel.evaluate (spectral.py:1159-1162)
+        fac = ev.bkg_norm * pow(D.ecenter[tid] / ev.bkg_ref, -ev.bkg_tilt);
+      bkgfac[tid] = fac;
+    }
+    const int y_first = p0 / D.nx, y_last = (p0 + npx - 1) / D.nx;
+    const int x_first = p0 - y_first * D.nx, x_last = p0 + npx - 1 - y_last * D.nx;
+    if (tid < 32) {
+      int n = 0;
+      for (int base = 0; base < ev.inst_count; base += 32) {
+        const int i = base + tid;
+        bool ov = false;
+        InstDev in;
+        if (i < ev.inst_count) {
+          in = P.insts[ev.inst_begin + i];
+          ov = in.y0 <= y_last && in.y0 + in.cy > y_first;
+          if (ov && y_first == y_last) ov = in.x0 <= x_last && in.x0 + in.cx > x_first;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ov);
+        if (ov) slist[n + __popc(m & ((1u << tid) - 1u))] = in;
+        n += __popc(m);
+      }
+      if (tid == 0) n_list = n;
+    }
+    __syncthreads();
+    const int nl = n_list;
+
+    // this thread's pixel quad and its offset inside every overlapping cutout (-1: outside)
+    const int pq = p0 + 4 * q;
+    const bool qlive = 4 * q < npx;
+    const int qy = pq / D.nx, qx = pq - qy * D.nx;
+    int off[kFoldLMax];
+#pragma unroll
+    for (int l = 0; l < kFoldLMax; ++l) {
+      off[l] = -1;
+      if (l < nl && qlive) {
+        const InstDev& in = slist[l];
+        const int ly = qy - in.y0, lx = qx - in.x0a;
+        if (ly >= 0 && ly < in.cy && lx >= 0 && lx < in.pitch) off[l] = ly * in.pitch + lx;
+      }
+    }
+
+    const int nchunks = nRp >> 3;
+    double stat = 0.0;
+    for (int cbase = 0; cbase < nchunks; cbase += 4) {  // one pass for nR <= 32
+      const int c = cbase + cslot;
+      double acc0[8], acc1[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.0;
+
+      for (int t0 = 0; t0 < nT; t0 += kFoldTCH) {
+        if (cbase == 0 && t0 == 0) mbar_wait(&bars[0], parity);  // exposure tile has landed
+        // ---- phase 1: v[g][t][p] = 1e4 * exposure[t,p] * sum_s F_s[t] * conv_s[t,p] ----
+        for (int g = 0; g < G; ++g) {
+#pragma unroll
+          for (int tt = 0; tt < kFoldTCH / 8; ++tt) {
+            const int tl = slot + 8 * tt, t = t0 + tl;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            if (t < nT && qlive) {
+#pragma unroll
+              for (int l = 0; l < kFoldLMax; ++l) {
+                if (off[l] < 0) continue;
+                const InstDev& in = slist[l];
+                if (in.group != g) continue;
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(in.conv + (size_t)t * in.plane_stride + off[l]));
+                const double F = P.flux[in.flux_off + t];
+                const double a0 = F * (double)cv.x, a1 = F * (double)cv.y, a2 = F * (double)cv.z, a3 = F * (double)cv.w;
+                // WcsNDMap.stack(nan_to_num=True): non-finite source values do not enter the sum
+                s0 += isfinite(a0) ? a0 : 0.0;
+                s1 += isfinite(a1) ? a1 : 0.0;
+                s2 += isfinite(a2) ? a2 : 0.0;
+                s3 += isfinite(a3) ? a3 : 0.0;
+              }
+              for (int l = kFoldLMax; l < nl; ++l) {  // rare: more than kFoldLMax sources on one tile
+                const InstDev& in = slist[l];
+                if (in.group != g) continue;
+                const int ly = qy - in.y0, lx = qx - in.x0a;
+                if (ly < 0 || ly >= in.cy || lx < 0 || lx >= in.pitch) continue;
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(in.conv + (size_t)t * in.plane_stride +
+                                                                        ly * in.pitch + lx));
+                const double F = P.flux[in.flux_off + t];
+                const double a0 = F * (double)cv.x, a1 = F * (double)cv.y, a2 = F * (double)cv.z, a3 = F * (double)cv.w;
+                s0 += isfinite(a0) ? a0 : 0.0;
+                s1 += isfinite(a1) ? a1 : 0.0;
+                s2 += isfinite(a2) ? a2 : 0.0;
+                s3 += isfinite(a3) ? a3 : 0.0;
+              }
+              const float4 e = *reinterpret_cast<const float4*>(es + t * kFoldTPX + 4 * q);
+              s0 = (s0 * (double)e.x) * 1e4;
+              s1 = (s1 * (double)e.y) * 1e4;
+              s2 = (s2 * (double)e.z) * 1e4;
+              s3 = (s3 * (double)e.w) * 1e4;
+            }
+            double* dst = vs + ((size_t)g * kFoldTCH + tl) * kFoldTPX + 4 * q;
+            *reinterpret_cast<double2*>(dst) = make_double2(s0, s1);
+            *reinterpret_cast<double2*>(dst + 2) = make_double2(s2, s3);
+          }
+        }
+        __syncthreads();
+        // exposure tile fully consumed: start fetching the next item's while phase 2 / the epilogue run
+        if (tid < 32 && cbase + 4 >= nchunks && t0 + kFoldTCH >= nT && next < n_items) issue_expo(next);
+        // ---- phase 2: acc[r] += pdf[t][r] * v[t][p] over the non-zero band ----
+        if (c < nchunks) {
+          for (int g = 0; g < G; ++g) {
+            const int blo = D.band[(g * nchunks + c) * 2], bhi = D.band[(g * nchunks + c) * 2 + 1];
+            const int tlo = max(blo, t0), thi = min(bhi, t0 + kFoldTCH);
+            const double* vrow = vs + (size_t)g * kFoldTCH * kFoldTPX + 2 * pp;
+            const double* prow = pdf_s + (size_t)g * nT * nRp + 8 * c;
+            for (int t = tlo; t < thi; ++t) {
+              const double2 v = *reinterpret_cast<const double2*>(vrow + (t - t0) * kFoldTPX);
+              const double2 m0 = *reinterpret_cast<const double2*>(prow + t * nRp);
+              const double2 m1 = *reinterpret_cast<const double2*>(prow + t * nRp + 2);
+              const double2 m2 = *reinterpret_cast<const double2*>(prow + t * nRp + 4);
+              const double2 m3 = *reinterpret_cast<const double2*>(prow + t * nRp + 6);
+              const double m[8] = {m0.x, m0.y, m1.x, m1.y, m2.x, m2.y, m3.x, m3.y};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                acc0[j] = fma(v.x, m[j], acc0[j]);
+                acc1[j] = fma(v.y, m[j], acc1[j]);
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+
+      // ---- epilogue for reco chunk c: background, clip, Cash (inputs staged in shared memory) ----
+      if (cbase == 0) mbar_wait(&bars[1], parity);
+      if (c < nchunks && 2 * pp < npx) {
+        const bool has_bkg = D.background && P.include_background;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = 8 * c + j;
+          if (r >= nR) break;
+          double mu0 = acc0[j], mu1 = acc1[j];
+          if (P.include_background) {
+            if (has_bkg) {
+              const float2 bg = *reinterpret_cast<const float2*>(bs + r * kFoldTPX + 2 * pp);
+              mu0 += (double)bg.x * bkgfac[r];
+              mu1 += (double)bg.y * bkgfac[r];
+            }
+            if (mu0 < 0.0) mu0 = 0.0;  // npred_total.data[npred_total.data < 0.0] = 0 (map.py:787)
+            if (mu1 < 0.0) mu1 = 0.0;
+          }
+          if (WRITE_NPRED) {
+            double* o = P.npred_out + (size_t)r * D.P + p0 + 2 * pp;
+            *reinterpret_cast<double2*>(o) = make_double2(mu0, mu1);
+          }
+          if (D.counts) {
+            const float2 cn = *reinterpret_cast<const float2*>(cs + r * kFoldTPX + 2 * pp);
+            unsigned short mk = 0x0101;
+            if (D.mask) mk = *reinterpret_cast<const unsigned short*>(ms + r * kFoldTPX + 2 * pp);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const double mu = k == 0 ? mu0 : mu1;
+              const double n = (double)(k == 0 ? cn.x : cn.y);
+              const bool m = ((mk >> (8 * k)) & 0xff) != 0;
+              if (m) {
+                double npr, lognpr = 0.0;
+                if (mu > kTrunc) {
+                  npr = mu;
+                  if (n > 0.0) lognpr = log(mu);
+                } else {
+                  npr = kTrunc;
+                  lognpr = P.log_trunc;
+                }
+                stat += npr;
+                if (n > 0.0) stat -= n * lognpr;
+              }
+            }
+          }
+        }
+      }
+    }
+    const double total = block_sum_256(stat, scratch);  // contains a block barrier after every epilogue read
+    if (tid == 0) P.partials[(size_t)b * P.n_tiles + tile] = total;
+    if (tid < 32 && next < n_items) issue_epi(next);
+    __syncthreads();  // scratch / list reuse in the next item
+  }
 }
 
 // Second stage: stat[b, d] = 2 * sum of the tile partials of dataset d, fixed summation order.
