@@ -685,8 +685,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 struct FoldSmem {  // byte offsets of the fixed shared-memory layout
-  size_t es, bs, cs, ms, vs, pdf, bkgfac, scratch, slist, bars, total;
+  size_t es, bs, cs, ms, pdf, flux, bkgfac, scratch, slist, bars, total;
 };
+constexpr int kFoldLMax = 4;  // overlapping sources whose per-thread offsets live in registers
 __host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int G, int max_inst) {
   FoldSmem L;
   size_t o = 0;
@@ -694,8 +695,8 @@ __host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int
   L.bs = o;      o += (size_t)nR * kFoldTPX * 4;
   L.cs = o;      o += (size_t)nR * kFoldTPX * 4;
   L.ms = o;      o += ((size_t)nR * kFoldTPX + 15) / 16 * 16;
-  L.vs = o;      o += (size_t)G * kFoldTCH * kFoldTPX * 8;
   L.pdf = o;     o += (size_t)G * nT * nRp * 8;
+  L.flux = o;    o += (size_t)kFoldLMax * nT * 8;
   L.bkgfac = o;  o += (size_t)nRp * 8;
   L.scratch = o; o += 8 * 8;
   L.slist = o;   o += (size_t)max_inst * sizeof(InstDev);
@@ -704,8 +705,10 @@ __host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int
   return L;
 }
 
-constexpr int kFoldLMax = 4;  // overlapping sources whose per-thread offsets live in registers
-
+// Thread (pixel pair, reco chunk c of 8 bins) walks the non-zero true-energy band of its chunk:
+//   v[k]    = 1e4 * exposure[t,p_k] * sum_s F_s[t] * conv_s[t,p_k]      (fp64; exposure from shared memory)
+//   acc[r] += pdf[t][r] * v[k]                                          (16 FMAs per true bin)
+// with no block barrier inside the band loop: warps run free and hide each other's load latency.
 template <bool WRITE_NPRED>
 __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const FoldParams P) {
   extern __shared__ __align__(128) unsigned char fold_raw[];
@@ -714,8 +717,8 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   float* bs = reinterpret_cast<float*>(fold_raw + L.bs);
   float* cs = reinterpret_cast<float*>(fold_raw + L.cs);
   unsigned char* ms = fold_raw + L.ms;
-  double* vs = reinterpret_cast<double*>(fold_raw + L.vs);
   double* pdf_s = reinterpret_cast<double*>(fold_raw + L.pdf);
+  double* flux_s = reinterpret_cast<double*>(fold_raw + L.flux);  // [kFoldLMax][nT]
   double* bkgfac = reinterpret_cast<double*>(fold_raw + L.bkgfac);
   double* scratch = reinterpret_cast<double*>(fold_raw + L.scratch);
   InstDev* slist = reinterpret_cast<InstDev*>(fold_raw + L.slist);
@@ -731,7 +734,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   }
   __syncthreads();
 
-  // producers (warp 0): bulk copies of one item's tiles
+  // producers (warp 0): bulk copies of one item's tiles, 512-byte row segments
   auto issue_expo = [&](int item) {
     const int tile = item / P.B;
     const DatasetDev& D = P.ds[P.tile_ds[tile]];
@@ -749,15 +752,16 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const int p0 = (tile - D.tile_begin) * kFoldTPX;
     const int npx = min(kFoldTPX, (int)D.P - p0);
     const uint32_t row = (uint32_t)npx * 4u;
+    const bool has_bkg = D.background && P.include_background;
     uint32_t total = 0;
-    if (D.background && P.include_background) total += row * (uint32_t)D.nR;
+    if (has_bkg) total += row * (uint32_t)D.nR;
     if (D.counts) total += row * (uint32_t)D.nR;
     if (D.counts && D.mask) total += (uint32_t)npx * (uint32_t)D.nR;
     if (tid == 0) mbar_arrive_expect_tx(&bars[1], total);
     __syncwarp();
     for (int r = tid; r < D.nR; r += 32) {
       const size_t off = (size_t)r * D.P + p0;
-      if (D.background && P.include_background) bulk_g2s(bs + r * kFoldTPX, D.background + off, row, &bars[1]);
+      if (has_bkg) bulk_g2s(bs + r * kFoldTPX, D.background + off, row, &bars[1]);
       if (D.counts) bulk_g2s(cs + r * kFoldTPX, D.counts + off, row, &bars[1]);
       if (D.counts && D.mask) bulk_g2s(ms + r * kFoldTPX, D.mask + off, (uint32_t)npx, &bars[1]);
     }
@@ -770,9 +774,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   }
   uint32_t parity = 0;
   int cur_ds = -1;
-
-  const int q = tid & 31, slot = tid >> 5;   // phase 1: 32 pixel quads x 8 energy slots
-  const int pp = tid & 63, cslot = tid >> 6;  // phase 2: 64 pixel pairs x 4 reco-chunk slots
+  const int pp = tid & 63, cslot = tid >> 6;  // 64 pixel pairs x 4 reco-chunk slots
 
   for (; item < n_items; item += gridDim.x, parity ^= 1u) {
     const int b = item % P.B;
@@ -816,109 +818,102 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     }
     __syncthreads();
     const int nl = n_list;
+    // spectral fluxes of the first kFoldLMax overlapping sources -> shared memory
+    for (int i = tid; i < min(nl, kFoldLMax) * nT; i += kFoldThreads) {
+      const int l = i / nT, t = i - l * nT;
+      flux_s[l * nT + t] = P.flux[slist[l].flux_off + t];
+    }
 
-    // this thread's pixel quad and its offset inside every overlapping cutout (-1: outside)
-    const int pq = p0 + 4 * q;
-    const bool qlive = 4 * q < npx;
-    const int qy = pq / D.nx, qx = pq - qy * D.nx;
-    int off[kFoldLMax];
+    // this thread's pixel pair and its offset inside every overlapping cutout (-1: outside)
+    const int ppx = p0 + 2 * pp;
+    const bool live = 2 * pp < npx;
+    const int qy = ppx / D.nx, qx = ppx - qy * D.nx;  // nx % 4 == 0: the pair lies in one row
+    int off[kFoldLMax], grp[kFoldLMax], pstr[kFoldLMax];
+    const float* cptr[kFoldLMax];
 #pragma unroll
     for (int l = 0; l < kFoldLMax; ++l) {
       off[l] = -1;
-      if (l < nl && qlive) {
+      grp[l] = 0;
+      pstr[l] = 0;
+      cptr[l] = nullptr;
+      if (l < nl && live) {
         const InstDev& in = slist[l];
         const int ly = qy - in.y0, lx = qx - in.x0a;
-        if (ly >= 0 && ly < in.cy && lx >= 0 && lx < in.pitch) off[l] = ly * in.pitch + lx;
+        if (ly >= 0 && ly < in.cy && lx >= 0 && lx < in.pitch) {
+          off[l] = ly * in.pitch + lx;
+          grp[l] = in.group;
+          pstr[l] = in.plane_stride;
+          cptr[l] = in.conv + off[l];
+        }
       }
     }
+    __syncthreads();  // flux_s visible
 
     const int nchunks = nRp >> 3;
     double stat = 0.0;
+    bool waited_e = false;
     for (int cbase = 0; cbase < nchunks; cbase += 4) {  // one pass for nR <= 32
       const int c = cbase + cslot;
       double acc0[8], acc1[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.0;
-
-      for (int t0 = 0; t0 < nT; t0 += kFoldTCH) {
-        if (cbase == 0 && t0 == 0) mbar_wait(&bars[0], parity);  // exposure tile has landed
-        // ---- phase 1: v[g][t][p] = 1e4 * exposure[t,p] * sum_s F_s[t] * conv_s[t,p] ----
+      if (!waited_e) {
+        mbar_wait(&bars[0], parity);  // exposure tile has landed
+        waited_e = true;
+      }
+      if (c < nchunks && live) {
         for (int g = 0; g < G; ++g) {
+          const int blo = D.band[(g * nchunks + c) * 2], bhi = D.band[(g * nchunks + c) * 2 + 1];
+          const double* prow = pdf_s + (size_t)g * nT * nRp + 8 * c;
+#pragma unroll 2
+          for (int t = blo; t < bhi; ++t) {
+            double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-          for (int tt = 0; tt < kFoldTCH / 8; ++tt) {
-            const int tl = slot + 8 * tt, t = t0 + tl;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            if (t < nT && qlive) {
-#pragma unroll
-              for (int l = 0; l < kFoldLMax; ++l) {
-                if (off[l] < 0) continue;
-                const InstDev& in = slist[l];
-                if (in.group != g) continue;
-                const float4 cv = __ldg(reinterpret_cast<const float4*>(in.conv + (size_t)t * in.plane_stride + off[l]));
-                const double F = P.flux[in.flux_off + t];
-                const double a0 = F * (double)cv.x, a1 = F * (double)cv.y, a2 = F * (double)cv.z, a3 = F * (double)cv.w;
-                // WcsNDMap.stack(nan_to_num=True): non-finite source values do not enter the sum
-                s0 += isfinite(a0) ? a0 : 0.0;
-                s1 += isfinite(a1) ? a1 : 0.0;
-                s2 += isfinite(a2) ? a2 : 0.0;
-                s3 += isfinite(a3) ? a3 : 0.0;
-              }
-              for (int l = kFoldLMax; l < nl; ++l) {  // rare: more than kFoldLMax sources on one tile
-                const InstDev& in = slist[l];
-                if (in.group != g) continue;
-                const int ly = qy - in.y0, lx = qx - in.x0a;
-                if (ly < 0 || ly >= in.cy || lx < 0 || lx >= in.pitch) continue;
-                const float4 cv = __ldg(reinterpret_cast<const float4*>(in.conv + (size_t)t * in.plane_stride +
-                                                                        ly * in.pitch + lx));
-                const double F = P.flux[in.flux_off + t];
-                const double a0 = F * (double)cv.x, a1 = F * (double)cv.y, a2 = F * (double)cv.z, a3 = F * (double)cv.w;
-                s0 += isfinite(a0) ? a0 : 0.0;
-                s1 += isfinite(a1) ? a1 : 0.0;
-                s2 += isfinite(a2) ? a2 : 0.0;
-                s3 += isfinite(a3) ? a3 : 0.0;
-              }
-              const float4 e = *reinterpret_cast<const float4*>(es + t * kFoldTPX + 4 * q);
-              s0 = (s0 * (double)e.x) * 1e4;
-              s1 = (s1 * (double)e.y) * 1e4;
-              s2 = (s2 * (double)e.z) * 1e4;
-              s3 = (s3 * (double)e.w) * 1e4;
+            for (int l = 0; l < kFoldLMax; ++l) {
+              if (off[l] < 0 || grp[l] != g) continue;
+              const float2 cv = __ldg(reinterpret_cast<const float2*>(cptr[l] + (size_t)t * pstr[l]));
+              const double F = flux_s[l * nT + t];
+              s0 = fma(F, (double)cv.x, s0);
+              s1 = fma(F, (double)cv.y, s1);
             }
-            double* dst = vs + ((size_t)g * kFoldTCH + tl) * kFoldTPX + 4 * q;
-            *reinterpret_cast<double2*>(dst) = make_double2(s0, s1);
-            *reinterpret_cast<double2*>(dst + 2) = make_double2(s2, s3);
-          }
-        }
-        __syncthreads();
-        // exposure tile fully consumed: start fetching the next item's while phase 2 / the epilogue run
-        if (tid < 32 && cbase + 4 >= nchunks && t0 + kFoldTCH >= nT && next < n_items) issue_expo(next);
-        // ---- phase 2: acc[r] += pdf[t][r] * v[t][p] over the non-zero band ----
-        if (c < nchunks) {
-          for (int g = 0; g < G; ++g) {
-            const int blo = D.band[(g * nchunks + c) * 2], bhi = D.band[(g * nchunks + c) * 2 + 1];
-            const int tlo = max(blo, t0), thi = min(bhi, t0 + kFoldTCH);
-            const double* vrow = vs + (size_t)g * kFoldTCH * kFoldTPX + 2 * pp;
-            const double* prow = pdf_s + (size_t)g * nT * nRp + 8 * c;
-            for (int t = tlo; t < thi; ++t) {
-              const double2 v = *reinterpret_cast<const double2*>(vrow + (t - t0) * kFoldTPX);
-              const double2 m0 = *reinterpret_cast<const double2*>(prow + t * nRp);
-              const double2 m1 = *reinterpret_cast<const double2*>(prow + t * nRp + 2);
-              const double2 m2 = *reinterpret_cast<const double2*>(prow + t * nRp + 4);
-              const double2 m3 = *reinterpret_cast<const double2*>(prow + t * nRp + 6);
-              const double m[8] = {m0.x, m0.y, m1.x, m1.y, m2.x, m2.y, m3.x, m3.y};
+            for (int l = kFoldLMax; l < nl; ++l) {  // rare: more than kFoldLMax sources on one tile
+              const InstDev& in = slist[l];
+              if (in.group != g) continue;
+              const int ly = qy - in.y0, lx = qx - in.x0a;
+              if (ly < 0 || ly >= in.cy || lx < 0 || lx >= in.pitch) continue;
+              const float2 cv = __ldg(reinterpret_cast<const float2*>(in.conv + (size_t)t * in.plane_stride +
+                                                                      ly * in.pitch + lx));
+              const double F = P.flux[in.flux_off + t];
+              s0 = fma(F, (double)cv.x, s0);
+              s1 = fma(F, (double)cv.y, s1);
+            }
+            const float2 e = *reinterpret_cast<const float2*>(es + t * kFoldTPX + 2 * pp);
+            double v0 = (s0 * (double)e.x) * 1e4, v1 = (s1 * (double)e.y) * 1e4;
+            // WcsNDMap.stack(nan_to_num=True): a non-finite source term does not enter the sum
+            if (!isfinite(v0)) v0 = 0.0;
+            if (!isfinite(v1)) v1 = 0.0;
+            const double2 m0 = *reinterpret_cast<const double2*>(prow + t * nRp);
+            const double2 m1 = *reinterpret_cast<const double2*>(prow + t * nRp + 2);
+            const double2 m2 = *reinterpret_cast<const double2*>(prow + t * nRp + 4);
+            const double2 m3 = *reinterpret_cast<const double2*>(prow + t * nRp + 6);
+            const double m[8] = {m0.x, m0.y, m1.x, m1.y, m2.x, m2.y, m3.x, m3.y};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                acc0[j] = fma(v.x, m[j], acc0[j]);
-                acc1[j] = fma(v.y, m[j], acc1[j]);
-              }
+            for (int j = 0; j < 8; ++j) {
+              acc0[j] = fma(v0, m[j], acc0[j]);
+              acc1[j] = fma(v1, m[j], acc1[j]);
             }
           }
         }
-        __syncthreads();
+      }
+      const bool last = cbase + 4 >= nchunks;
+      if (last) {
+        __syncthreads();  // every warp is done with the exposure tile: fetch the next item's behind the epilogue
+        if (tid < 32 && next < n_items) issue_expo(next);
       }
 
       // ---- epilogue for reco chunk c: background, clip, Cash (inputs staged in shared memory) ----
       if (cbase == 0) mbar_wait(&bars[1], parity);
-      if (c < nchunks && 2 * pp < npx) {
+      if (c < nchunks && live) {
         const bool has_bkg = D.background && P.include_background;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -967,7 +962,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const double total = block_sum_256(stat, scratch);  // contains a block barrier after every epilogue read
     if (tid == 0) P.partials[(size_t)b * P.n_tiles + tile] = total;
     if (tid < 32 && next < n_items) issue_epi(next);
-    __syncthreads();  // scratch / list reuse in the next item
+    __syncthreads();  // scratch / list / flux reuse in the next item
   }
 }
 
