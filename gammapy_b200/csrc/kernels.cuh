@@ -404,7 +404,9 @@ struct FoldParams {
   const EvalDev* evals;     // [n_datasets * B], index d * B + b
   const InstDev* insts;
   const double* flux;
-  double* partials;         // [B, n_tiles]
+  double* partials;         // [B, n_tiles] (generic) or [B, n_tiles, 8] (warp partials of the bulk-copy kernel)
+  const int* lists;         // [B * n_tiles][kBinCap + 1] per-item overlap lists (bin_sources_kernel)
+  const double* bkgfac;     // [n_datasets * B][smem_nRp] background factors (bin_sources_kernel)
   double* npred_out;        // [nR, P] or null (single dataset, B == 1)
   int B, n_tiles, n_datasets;
   int include_background;   // add background model and clip at 0 (MapDataset.npred) or signal only
@@ -684,236 +686,288 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-struct FoldSmem {  // byte offsets of the fixed shared-memory layout
-  size_t es, bs, cs, ms, pdf, flux, bkgfac, scratch, slist, bars, total;
+// ---- tile binning + background factors (one warp per work item), launched before the fold ----------
+constexpr int kBinCap = 63;  // overlapping sources recorded per (tile, vector); the host falls back beyond
+struct BinParams {
+  const DatasetDev* ds;
+  const int* tile_ds;
+  const EvalDev* evals;
+  const InstDev* insts;
+  int* lists;        // [n_items][kBinCap + 1]: count, then instance indices in ascending order
+  double* bkgfac;    // [n_datasets * B][max_nRp]
+  int B, n_tiles, n_datasets, max_nRp;
 };
-constexpr int kFoldLMax = 4;  // overlapping sources whose per-thread offsets live in registers
-__host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int G, int max_inst) {
+
+__global__ void __launch_bounds__(256) bin_sources_kernel(const BinParams P) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const long long n_items = (long long)P.B * P.n_tiles;
+  // background factors norm * (E_c / E_0)^-tilt (PowerLawNormSpectralModel.evaluate, spectral.py:1159-1162)
+  if (gw < (long long)P.n_datasets * P.B) {
+    const int d = (int)(gw / P.B);
+    const DatasetDev& D = P.ds[d];
+    const EvalDev& ev = P.evals[gw];
+    for (int r = lane; r < P.max_nRp; r += 32) {
+      double fac = 1.0;
+      if (ev.bkg_enabled && r < D.nR) fac = ev.bkg_norm * pow(D.ecenter[r] / ev.bkg_ref, -ev.bkg_tilt);
+      P.bkgfac[gw * P.max_nRp + r] = fac;
+    }
+  }
+  if (gw >= n_items) return;
+  const int b = (int)(gw % P.B);
+  const int tile = (int)(gw / P.B);
+  const int d = P.tile_ds[tile];
+  const DatasetDev& D = P.ds[d];
+  const EvalDev& ev = P.evals[(size_t)d * P.B + b];
+  const int p0 = (tile - D.tile_begin) * kFoldTPX;
+  const int npx = min(kFoldTPX, (int)D.P - p0);
+  const int y_first = p0 / D.nx, y_last = (p0 + npx - 1) / D.nx;
+  const int x_first = p0 - y_first * D.nx, x_last = p0 + npx - 1 - y_last * D.nx;
+  int* out = P.lists + gw * (kBinCap + 1);
+  int n = 0;
+  for (int base = 0; base < ev.inst_count; base += 32) {
+    const int i = base + lane;
+    bool ov = false;
+    if (i < ev.inst_count) {
+      const InstDev& in = P.insts[ev.inst_begin + i];
+      ov = in.y0 <= y_last && in.y0 + in.cy > y_first;
+      if (ov && y_first == y_last) ov = in.x0 <= x_last && in.x0 + in.cx > x_first;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ov);
+    const int pos = n + __popc(m & ((1u << lane) - 1u));
+    if (ov && pos < kBinCap) out[1 + pos] = ev.inst_begin + i;
+    n += __popc(m);
+  }
+  if (lane == 0) out[0] = min(n, kBinCap);
+}
+
+struct FoldSmem {  // byte offsets of the fixed shared-memory layout
+  size_t es, bs, cs, ms, vs, pdf, bars, total;
+};
+constexpr int kFoldLMax = 4;        // overlapping sources whose per-lane pointers live in registers
+constexpr int kFoldWarps = 8;       // compute warps, each owns 16 pixels of the tile
+constexpr int kFoldTmaThreads = (kFoldWarps + 1) * 32;  // + one producer warp
+__host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int G) {
   FoldSmem L;
   size_t o = 0;
-  L.es = o;      o += (size_t)nT * kFoldTPX * 4;
-  L.bs = o;      o += (size_t)nR * kFoldTPX * 4;
-  L.cs = o;      o += (size_t)nR * kFoldTPX * 4;
-  L.ms = o;      o += ((size_t)nR * kFoldTPX + 15) / 16 * 16;
-  L.pdf = o;     o += (size_t)G * nT * nRp * 8;
-  L.flux = o;    o += (size_t)kFoldLMax * nT * 8;
-  L.bkgfac = o;  o += (size_t)nRp * 8;
-  L.scratch = o; o += 8 * 8;
-  L.slist = o;   o += (size_t)max_inst * sizeof(InstDev);
+  L.es = o;   o += (size_t)nT * kFoldTPX * 4;
+  L.bs = o;   o += (size_t)nR * kFoldTPX * 4;
+  L.cs = o;   o += (size_t)nR * kFoldTPX * 4;
+  L.ms = o;   o += ((size_t)nR * kFoldTPX + 15) / 16 * 16;
+  L.vs = o;   o += (size_t)G * kFoldTCH * kFoldTPX * 8;
+  L.pdf = o;  o += (size_t)G * nT * nRp * 8;
   L.bars = (o + 7) / 8 * 8;
-  L.total = L.bars + 2 * 8;
+  L.total = L.bars + 4 * 8;
   return L;
 }
 
-// Thread (pixel pair, reco chunk c of 8 bins) walks the non-zero true-energy band of its chunk:
-//   v[k]    = 1e4 * exposure[t,p_k] * sum_s F_s[t] * conv_s[t,p_k]      (fp64; exposure from shared memory)
-//   acc[r] += pdf[t][r] * v[k]                                          (16 FMAs per true bin)
-// with no block barrier inside the band loop: warps run free and hide each other's load latency.
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised, persistent fold + Cash kernel.
+//   producer warp : per work item, 1-D bulk copies (TMA engine) of the exposure tile [nT][128] and of the
+//                   background / counts / mask tiles [nR][128] into shared memory; full / empty mbarriers.
+//   compute warp w: owns pixels [16 w, 16 w + 16) of the tile for BOTH phases, so the phases need only
+//                   __syncwarp: phase 1 lanes = 4 pixel quads x 8 true-energy slots, phase 2 lanes = 8 pixel
+//                   pairs x 4 reco chunks.  The Cash partial of a warp goes to partials[b][8 tile + w].
 template <bool WRITE_NPRED>
-__global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const FoldParams P) {
+__global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const FoldParams P) {
   extern __shared__ __align__(128) unsigned char fold_raw[];
-  const FoldSmem L = fold_tma_layout(P.smem_nT, P.smem_nR, P.smem_nRp, P.smem_G, P.max_inst);
+  const FoldSmem L = fold_tma_layout(P.smem_nT, P.smem_nR, P.smem_nRp, P.smem_G);
   float* es = reinterpret_cast<float*>(fold_raw + L.es);
   float* bs = reinterpret_cast<float*>(fold_raw + L.bs);
   float* cs = reinterpret_cast<float*>(fold_raw + L.cs);
   unsigned char* ms = fold_raw + L.ms;
+  double* vs = reinterpret_cast<double*>(fold_raw + L.vs);
   double* pdf_s = reinterpret_cast<double*>(fold_raw + L.pdf);
-  double* flux_s = reinterpret_cast<double*>(fold_raw + L.flux);  // [kFoldLMax][nT]
-  double* bkgfac = reinterpret_cast<double*>(fold_raw + L.bkgfac);
-  double* scratch = reinterpret_cast<double*>(fold_raw + L.scratch);
-  InstDev* slist = reinterpret_cast<InstDev*>(fold_raw + L.slist);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + L.bars);  // [0] exposure, [1] epilogue inputs
-  __shared__ int n_list;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + L.bars);
+  uint64_t* full_e = &bars[0];   // exposure tile landed
+  uint64_t* full_x = &bars[1];   // epilogue inputs landed
+  uint64_t* empty_e = &bars[2];  // all compute warps are done with the exposure tile
+  uint64_t* empty_x = &bars[3];  // all compute warps are done with the epilogue inputs
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_items = P.B * P.n_tiles;
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    mbar_init(full_e, 1);
+    mbar_init(full_x, 1);
+    mbar_init(empty_e, kFoldWarps);
+    mbar_init(empty_x, kFoldWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // edisp matrices: single-dataset launches keep them in shared memory for the whole kernel
+  const bool pdf_shared = P.n_datasets == 1;
+  if (pdf_shared) {
+    const DatasetDev& D0 = P.ds[0];
+    for (int i = tid; i < D0.n_groups * D0.nT * D0.nRp; i += kFoldTmaThreads) pdf_s[i] = D0.edisp[i];
   }
   __syncthreads();
 
-  // producers (warp 0): bulk copies of one item's tiles, 512-byte row segments
-  auto issue_expo = [&](int item) {
-    const int tile = item / P.B;
-    const DatasetDev& D = P.ds[P.tile_ds[tile]];
-    const int p0 = (tile - D.tile_begin) * kFoldTPX;
-    const int npx = min(kFoldTPX, (int)D.P - p0);
-    const uint32_t row = (uint32_t)npx * 4u;
-    if (tid == 0) mbar_arrive_expect_tx(&bars[0], row * (uint32_t)D.nT);
-    __syncwarp();
-    for (int t = tid; t < D.nT; t += 32)
-      bulk_g2s(es + t * kFoldTPX, D.exposure + (size_t)t * D.P + p0, row, &bars[0]);
-  };
-  auto issue_epi = [&](int item) {
-    const int tile = item / P.B;
-    const DatasetDev& D = P.ds[P.tile_ds[tile]];
-    const int p0 = (tile - D.tile_begin) * kFoldTPX;
-    const int npx = min(kFoldTPX, (int)D.P - p0);
-    const uint32_t row = (uint32_t)npx * 4u;
-    const bool has_bkg = D.background && P.include_background;
-    uint32_t total = 0;
-    if (has_bkg) total += row * (uint32_t)D.nR;
-    if (D.counts) total += row * (uint32_t)D.nR;
-    if (D.counts && D.mask) total += (uint32_t)npx * (uint32_t)D.nR;
-    if (tid == 0) mbar_arrive_expect_tx(&bars[1], total);
-    __syncwarp();
-    for (int r = tid; r < D.nR; r += 32) {
-      const size_t off = (size_t)r * D.P + p0;
-      if (has_bkg) bulk_g2s(bs + r * kFoldTPX, D.background + off, row, &bars[1]);
-      if (D.counts) bulk_g2s(cs + r * kFoldTPX, D.counts + off, row, &bars[1]);
-      if (D.counts && D.mask) bulk_g2s(ms + r * kFoldTPX, D.mask + off, (uint32_t)npx, &bars[1]);
+  if (warp == kFoldWarps) {
+    // ================= producer warp =================
+    uint32_t parity = 0;
+    bool first = true;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int tile = item / P.B;
+      const DatasetDev& D = P.ds[P.tile_ds[tile]];
+      const int p0 = (tile - D.tile_begin) * kFoldTPX;
+      const int npx = min(kFoldTPX, (int)D.P - p0);
+      const uint32_t row = (uint32_t)npx * 4u;
+      const bool has_bkg = D.background && P.include_background;
+      if (!first) mbar_wait(empty_e, parity ^ 1u);  // previous item's exposure tile fully consumed
+      if (lane == 0) mbar_arrive_expect_tx(full_e, row * (uint32_t)D.nT);
+      __syncwarp();
+      for (int t = lane; t < D.nT; t += 32)
+        bulk_g2s(es + t * kFoldTPX, D.exposure + (size_t)t * D.P + p0, row, full_e);
+      if (!first) mbar_wait(empty_x, parity ^ 1u);
+      uint32_t total = 0;
+      if (has_bkg) total += row * (uint32_t)D.nR;
+      if (D.counts) total += row * (uint32_t)D.nR;
+      if (D.counts && D.mask) total += (uint32_t)npx * (uint32_t)D.nR;
+      if (lane == 0) mbar_arrive_expect_tx(full_x, total);
+      __syncwarp();
+      for (int r = lane; r < D.nR; r += 32) {
+        const size_t off = (size_t)r * D.P + p0;
+        if (has_bkg) bulk_g2s(bs + r * kFoldTPX, D.background + off, row, full_x);
+        if (D.counts) bulk_g2s(cs + r * kFoldTPX, D.counts + off, row, full_x);
+        if (D.counts && D.mask) bulk_g2s(ms + r * kFoldTPX, D.mask + off, (uint32_t)npx, full_x);
+      }
+      first = false;
+      parity ^= 1u;
     }
-  };
-
-  int item = blockIdx.x;
-  if (item < n_items && tid < 32) {
-    issue_expo(item);
-    issue_epi(item);
+    return;
   }
-  uint32_t parity = 0;
-  int cur_ds = -1;
-  const int pp = tid & 63, cslot = tid >> 6;  // 64 pixel pairs x 4 reco-chunk slots
 
-  for (; item < n_items; item += gridDim.x, parity ^= 1u) {
+  // ================= compute warps =================
+  const int px0 = 16 * warp;                      // first pixel of this warp inside the tile
+  const int q = lane & 3, tslot = lane >> 2;      // phase 1: 4 pixel quads x 8 true-energy slots
+  const int pr = lane & 7, cslot = lane >> 3;     // phase 2: 8 pixel pairs x 4 reco chunks
+  double* vw = vs + px0;                          // this warp's columns of v[g][t][128]
+  uint32_t parity = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, parity ^= 1u) {
     const int b = item % P.B;
     const int tile = item / P.B;
     const int d = P.tile_ds[tile];
-    const DatasetDev D = P.ds[d];
-    const EvalDev ev = P.evals[(size_t)d * P.B + b];
-    const int nT = D.nT, nR = D.nR, nRp = D.nRp, G = D.n_groups;
+    const DatasetDev& D = P.ds[d];
+    const int nT = D.nT, nR = D.nR, nRp = D.nRp, G = D.n_groups, nx = D.nx;
     const int p0 = (tile - D.tile_begin) * kFoldTPX;
     const int npx = min(kFoldTPX, (int)D.P - p0);
-    const int next = item + gridDim.x;
+    const double* pdf = pdf_shared ? pdf_s : D.edisp;
+    const double* bkgfac = P.bkgfac + ((size_t)d * P.B + b) * P.smem_nRp;
+    const int* list = P.lists + (size_t)item * (kBinCap + 1);
+    const int nl = __ldg(list);
 
-    if (d != cur_ds) {  // edisp matrices of this dataset (block-uniform branch)
-      for (int i = tid; i < G * nT * nRp; i += kFoldThreads) pdf_s[i] = D.edisp[i];
-      cur_ds = d;
-    }
-    if (tid < nRp) {
-      double fac = 1.0;
-      if (ev.bkg_enabled && tid < nR)  // PowerLawNormSpectralModel.evaluate (spectral.py:1159-1162)
-        fac = ev.bkg_norm * pow(D.ecenter[tid] / ev.bkg_ref, -ev.bkg_tilt);
-      bkgfac[tid] = fac;
-    }
-    const int y_first = p0 / D.nx, y_last = (p0 + npx - 1) / D.nx;
-    const int x_first = p0 - y_first * D.nx, x_last = p0 + npx - 1 - y_last * D.nx;
-    if (tid < 32) {
-      int n = 0;
-      for (int base = 0; base < ev.inst_count; base += 32) {
-        const int i = base + tid;
-        bool ov = false;
-        InstDev in;
-        if (i < ev.inst_count) {
-          in = P.insts[ev.inst_begin + i];
-          ov = in.y0 <= y_last && in.y0 + in.cy > y_first;
-          if (ov && y_first == y_last) ov = in.x0 <= x_last && in.x0 + in.cx > x_first;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, ov);
-        if (ov) slist[n + __popc(m & ((1u << tid) - 1u))] = in;
-        n += __popc(m);
-      }
-      if (tid == 0) n_list = n;
-    }
-    __syncthreads();
-    const int nl = n_list;
-    // spectral fluxes of the first kFoldLMax overlapping sources -> shared memory
-    for (int i = tid; i < min(nl, kFoldLMax) * nT; i += kFoldThreads) {
-      const int l = i / nT, t = i - l * nT;
-      flux_s[l * nT + t] = P.flux[slist[l].flux_off + t];
-    }
-
-    // this thread's pixel pair and its offset inside every overlapping cutout (-1: outside)
-    const int ppx = p0 + 2 * pp;
-    const bool live = 2 * pp < npx;
-    const int qy = ppx / D.nx, qx = ppx - qy * D.nx;  // nx % 4 == 0: the pair lies in one row
-    int off[kFoldLMax], grp[kFoldLMax], pstr[kFoldLMax];
+    // phase-1 quad of this lane and its pointer into every overlapping cutout (nullptr: outside)
+    const int lq = px0 + 4 * q;                   // local pixel of the quad
+    const bool qlive = lq < npx;
+    const int pq = p0 + lq;
+    const int qy = pq / nx, qx = pq - qy * nx;    // nx % 4 == 0: the quad lies in one row
     const float* cptr[kFoldLMax];
+    int pstr[kFoldLMax], foff[kFoldLMax], grp[kFoldLMax];
 #pragma unroll
     for (int l = 0; l < kFoldLMax; ++l) {
-      off[l] = -1;
-      grp[l] = 0;
-      pstr[l] = 0;
       cptr[l] = nullptr;
-      if (l < nl && live) {
-        const InstDev& in = slist[l];
+      pstr[l] = 0;
+      foff[l] = 0;
+      grp[l] = -1;
+      if (l < nl) {
+        const InstDev& in = P.insts[__ldg(list + 1 + l)];
         const int ly = qy - in.y0, lx = qx - in.x0a;
-        if (ly >= 0 && ly < in.cy && lx >= 0 && lx < in.pitch) {
-          off[l] = ly * in.pitch + lx;
-          grp[l] = in.group;
-          pstr[l] = in.plane_stride;
-          cptr[l] = in.conv + off[l];
-        }
+        grp[l] = in.group;
+        foff[l] = in.flux_off;
+        pstr[l] = in.plane_stride;
+        if (qlive && ly >= 0 && ly < in.cy && lx >= 0 && lx < in.pitch) cptr[l] = in.conv + ly * in.pitch + lx;
       }
     }
-    __syncthreads();  // flux_s visible
 
     const int nchunks = nRp >> 3;
     double stat = 0.0;
-    bool waited_e = false;
+    mbar_wait(full_e, parity);
     for (int cbase = 0; cbase < nchunks; cbase += 4) {  // one pass for nR <= 32
       const int c = cbase + cslot;
       double acc0[8], acc1[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.0;
-      if (!waited_e) {
-        mbar_wait(&bars[0], parity);  // exposure tile has landed
-        waited_e = true;
-      }
-      if (c < nchunks && live) {
+      for (int t0 = 0; t0 < nT; t0 += kFoldTCH) {
+        // ---- phase 1: v[g][t][p] = 1e4 * exposure[t,p] * sum_s F_s[t] * conv_s[t,p] ----
         for (int g = 0; g < G; ++g) {
-          const int blo = D.band[(g * nchunks + c) * 2], bhi = D.band[(g * nchunks + c) * 2 + 1];
-          const double* prow = pdf_s + (size_t)g * nT * nRp + 8 * c;
-#pragma unroll 2
-          for (int t = blo; t < bhi; ++t) {
-            double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-            for (int l = 0; l < kFoldLMax; ++l) {
-              if (off[l] < 0 || grp[l] != g) continue;
-              const float2 cv = __ldg(reinterpret_cast<const float2*>(cptr[l] + (size_t)t * pstr[l]));
-              const double F = flux_s[l * nT + t];
-              s0 = fma(F, (double)cv.x, s0);
-              s1 = fma(F, (double)cv.y, s1);
-            }
-            for (int l = kFoldLMax; l < nl; ++l) {  // rare: more than kFoldLMax sources on one tile
-              const InstDev& in = slist[l];
-              if (in.group != g) continue;
-              const int ly = qy - in.y0, lx = qx - in.x0a;
-              if (ly < 0 || ly >= in.cy || lx < 0 || lx >= in.pitch) continue;
-              const float2 cv = __ldg(reinterpret_cast<const float2*>(in.conv + (size_t)t * in.plane_stride +
-                                                                      ly * in.pitch + lx));
-              const double F = P.flux[in.flux_off + t];
-              s0 = fma(F, (double)cv.x, s0);
-              s1 = fma(F, (double)cv.y, s1);
-            }
-            const float2 e = *reinterpret_cast<const float2*>(es + t * kFoldTPX + 2 * pp);
-            double v0 = (s0 * (double)e.x) * 1e4, v1 = (s1 * (double)e.y) * 1e4;
-            // WcsNDMap.stack(nan_to_num=True): a non-finite source term does not enter the sum
-            if (!isfinite(v0)) v0 = 0.0;
-            if (!isfinite(v1)) v1 = 0.0;
-            const double2 m0 = *reinterpret_cast<const double2*>(prow + t * nRp);
-            const double2 m1 = *reinterpret_cast<const double2*>(prow + t * nRp + 2);
-            const double2 m2 = *reinterpret_cast<const double2*>(prow + t * nRp + 4);
-            const double2 m3 = *reinterpret_cast<const double2*>(prow + t * nRp + 6);
-            const double m[8] = {m0.x, m0.y, m1.x, m1.y, m2.x, m2.y, m3.x, m3.y};
+          for (int tt = 0; tt < kFoldTCH / 8; ++tt) {
+            const int tl = tslot + 8 * tt, t = t0 + tl;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            if (t < nT && qlive) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              acc0[j] = fma(v0, m[j], acc0[j]);
-              acc1[j] = fma(v1, m[j], acc1[j]);
+              for (int l = 0; l < kFoldLMax; ++l) {
+                if (cptr[l] == nullptr || grp[l] != g) continue;
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(cptr[l] + (size_t)t * pstr[l]));
+                const double F = __ldg(P.flux + foff[l] + t);
+                s0 = fma(F, (double)cv.x, s0);
+                s1 = fma(F, (double)cv.y, s1);
+                s2 = fma(F, (double)cv.z, s2);
+                s3 = fma(F, (double)cv.w, s3);
+              }
+              for (int l = kFoldLMax; l < nl; ++l) {  // rare: more than kFoldLMax sources on one tile
+                const InstDev& in = P.insts[__ldg(list + 1 + l)];
+                if (in.group != g) continue;
+                const int ly = qy - in.y0, lx = qx - in.x0a;
+                if (ly < 0 || ly >= in.cy || lx < 0 || lx >= in.pitch) continue;
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(in.conv + (size_t)t * in.plane_stride +
+                                                                        ly * in.pitch + lx));
+                const double F = __ldg(P.flux + in.flux_off + t);
+                s0 = fma(F, (double)cv.x, s0);
+                s1 = fma(F, (double)cv.y, s1);
+                s2 = fma(F, (double)cv.z, s2);
+                s3 = fma(F, (double)cv.w, s3);
+              }
+              const float4 e = *reinterpret_cast<const float4*>(es + t * kFoldTPX + lq);
+              s0 = (s0 * (double)e.x) * 1e4;
+              s1 = (s1 * (double)e.y) * 1e4;
+              s2 = (s2 * (double)e.z) * 1e4;
+              s3 = (s3 * (double)e.w) * 1e4;
+              // WcsNDMap.stack(nan_to_num=True): a non-finite source term does not enter the sum
+              if (!isfinite(s0)) s0 = 0.0;
+              if (!isfinite(s1)) s1 = 0.0;
+              if (!isfinite(s2)) s2 = 0.0;
+              if (!isfinite(s3)) s3 = 0.0;
+            }
+            double* dst = vw + ((size_t)g * kFoldTCH + tl) * kFoldTPX + 4 * q;
+            *reinterpret_cast<double2*>(dst) = make_double2(s0, s1);
+            *reinterpret_cast<double2*>(dst + 2) = make_double2(s2, s3);
+          }
+        }
+        __syncwarp();
+        // ---- phase 2: acc[r] += pdf[t][r] * v[t][p] over the non-zero band ----
+        if (c < nchunks) {
+          for (int g = 0; g < G; ++g) {
+            const int blo = __ldg(D.band + (g * nchunks + c) * 2), bhi = __ldg(D.band + (g * nchunks + c) * 2 + 1);
+            const int tlo = max(blo, t0), thi = min(bhi, t0 + kFoldTCH);
+            const double* vrow = vw + (size_t)g * kFoldTCH * kFoldTPX + 2 * pr;
+            const double* prow = pdf + (size_t)g * nT * nRp + 8 * c;
+            for (int t = tlo; t < thi; ++t) {
+              const double2 v = *reinterpret_cast<const double2*>(vrow + (t - t0) * kFoldTPX);
+              const double2 m0 = *reinterpret_cast<const double2*>(prow + t * nRp);
+              const double2 m1 = *reinterpret_cast<const double2*>(prow + t * nRp + 2);
+              const double2 m2 = *reinterpret_cast<const double2*>(prow + t * nRp + 4);
+              const double2 m3 = *reinterpret_cast<const double2*>(prow + t * nRp + 6);
+              const double m[8] = {m0.x, m0.y, m1.x, m1.y, m2.x, m2.y, m3.x, m3.y};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                acc0[j] = fma(v.x, m[j], acc0[j]);
+                acc1[j] = fma(v.y, m[j], acc1[j]);
+              }
             }
           }
         }
+        __syncwarp();
       }
       const bool last = cbase + 4 >= nchunks;
-      if (last) {
-        __syncthreads();  // every warp is done with the exposure tile: fetch the next item's behind the epilogue
-        if (tid < 32 && next < n_items) issue_expo(next);
-      }
+      if (last && lane == 0) mbar_arrive(empty_e);  // this warp no longer reads the exposure tile
 
       // ---- epilogue for reco chunk c: background, clip, Cash (inputs staged in shared memory) ----
-      if (cbase == 0) mbar_wait(&bars[1], parity);
-      if (c < nchunks && live) {
+      if (cbase == 0) mbar_wait(full_x, parity);
+      const int lp = px0 + 2 * pr;
+      if (c < nchunks && lp < npx) {
         const bool has_bkg = D.background && P.include_background;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -922,27 +976,27 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
           double mu0 = acc0[j], mu1 = acc1[j];
           if (P.include_background) {
             if (has_bkg) {
-              const float2 bg = *reinterpret_cast<const float2*>(bs + r * kFoldTPX + 2 * pp);
-              mu0 += (double)bg.x * bkgfac[r];
-              mu1 += (double)bg.y * bkgfac[r];
+              const float2 bg = *reinterpret_cast<const float2*>(bs + r * kFoldTPX + lp);
+              const double fac = __ldg(bkgfac + r);
+              mu0 += (double)bg.x * fac;
+              mu1 += (double)bg.y * fac;
             }
             if (mu0 < 0.0) mu0 = 0.0;  // npred_total.data[npred_total.data < 0.0] = 0 (map.py:787)
             if (mu1 < 0.0) mu1 = 0.0;
           }
           if (WRITE_NPRED) {
-            double* o = P.npred_out + (size_t)r * D.P + p0 + 2 * pp;
+            double* o = P.npred_out + (size_t)r * D.P + p0 + lp;
             *reinterpret_cast<double2*>(o) = make_double2(mu0, mu1);
           }
           if (D.counts) {
-            const float2 cn = *reinterpret_cast<const float2*>(cs + r * kFoldTPX + 2 * pp);
+            const float2 cn = *reinterpret_cast<const float2*>(cs + r * kFoldTPX + lp);
             unsigned short mk = 0x0101;
-            if (D.mask) mk = *reinterpret_cast<const unsigned short*>(ms + r * kFoldTPX + 2 * pp);
+            if (D.mask) mk = *reinterpret_cast<const unsigned short*>(ms + r * kFoldTPX + lp);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               const double mu = k == 0 ? mu0 : mu1;
               const double n = (double)(k == 0 ? cn.x : cn.y);
-              const bool m = ((mk >> (8 * k)) & 0xff) != 0;
-              if (m) {
+              if (((mk >> (8 * k)) & 0xff) != 0) {
                 double npr, lognpr = 0.0;
                 if (mu > kTrunc) {
                   npr = mu;
@@ -959,20 +1013,22 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         }
       }
     }
-    const double total = block_sum_256(stat, scratch);  // contains a block barrier after every epilogue read
-    if (tid == 0) P.partials[(size_t)b * P.n_tiles + tile] = total;
-    if (tid < 32 && next < n_items) issue_epi(next);
-    __syncthreads();  // scratch / list / flux reuse in the next item
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_x);  // this warp no longer reads the epilogue tiles
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) stat += __shfl_xor_sync(0xffffffffu, stat, o);
+    if (lane == 0) P.partials[((size_t)b * P.n_tiles + tile) * kFoldWarps + warp] = stat;
   }
 }
 
 // Second stage: stat[b, d] = 2 * sum of the tile partials of dataset d, fixed summation order.
 __global__ void __launch_bounds__(256)
 reduce_stat_kernel(const double* __restrict__ partials, const DatasetDev* __restrict__ ds, int n_tiles,
-                   int n_datasets, double* __restrict__ stat) {
+                   int n_datasets, int per_tile, double* __restrict__ stat) {
   __shared__ double sm[256];
   const int b = blockIdx.x, d = blockIdx.y;
-  const int begin = ds[d].tile_begin, n = ds[d].n_tiles;
+  const int begin = ds[d].tile_begin * per_tile, n = ds[d].n_tiles * per_tile;
+  n_tiles *= per_tile;
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) s += partials[(size_t)b * n_tiles + begin + i];
   sm[threadIdx.x] = s;
