@@ -744,8 +744,8 @@ __global__ void __launch_bounds__(256) bin_sources_kernel(const BinParams P) {
 struct FoldSmem {  // byte offsets of the fixed shared-memory layout
   size_t es, bs, cs, ms, vs, pdf, bars, total;
 };
-constexpr int kFoldLMax = 4;        // overlapping sources whose per-lane pointers live in registers
-constexpr int kFoldWarps = 8;       // compute warps, each owns 16 pixels of the tile
+constexpr int kFoldLMax = 4;        // overlapping sources whose per-thread pointers live in registers
+constexpr int kFoldWarps = 8;       // compute warps
 constexpr int kFoldTmaThreads = (kFoldWarps + 1) * 32;  // + one producer warp
 __host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int G) {
   FoldSmem L;
@@ -754,7 +754,7 @@ __host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int
   L.bs = o;   o += (size_t)nR * kFoldTPX * 4;
   L.cs = o;   o += (size_t)nR * kFoldTPX * 4;
   L.ms = o;   o += ((size_t)nR * kFoldTPX + 15) / 16 * 16;
-  L.vs = o;   o += (size_t)G * kFoldTCH * kFoldTPX * 8;
+  L.vs = o;   o += (size_t)2 * G * kFoldTCH * kFoldTPX * 8;  // double buffered
   L.pdf = o;  o += (size_t)G * nT * nRp * 8;
   L.bars = (o + 7) / 8 * 8;
   L.total = L.bars + 4 * 8;
@@ -764,13 +764,30 @@ __host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void compute_barrier() {  // the 8 compute warps only (named barrier 1)
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
 
 // Warp-specialised, persistent fold + Cash kernel.
 //   producer warp : per work item, 1-D bulk copies (TMA engine) of the exposure tile [nT][128] and of the
 //                   background / counts / mask tiles [nR][128] into shared memory; full / empty mbarriers.
-//   compute warp w: owns pixels [16 w, 16 w + 16) of the tile for BOTH phases, so the phases need only
-//                   __syncwarp: phase 1 lanes = 4 pixel quads x 8 true-energy slots, phase 2 lanes = 8 pixel
-//                   pairs x 4 reco chunks.  The Cash partial of a warp goes to partials[b][8 tile + w].
+//   compute warps : phase 1 (thread = pixel quad x true-energy slot) writes v[t][p] for 16 true bins into one
+//                   half of a double-buffered shared array; phase 2 (thread = pixel pair x reco chunk, chunk
+//                   uniform per warp so the band loop and the Cash log do not diverge) accumulates in registers.
+//                   One named barrier per pass; the Cash partial of every warp goes to partials[b][8 tile + w].
 template <bool WRITE_NPRED>
 __global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const FoldParams P) {
   extern __shared__ __align__(128) unsigned char fold_raw[];
@@ -815,12 +832,14 @@ __global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const
       const int npx = min(kFoldTPX, (int)D.P - p0);
       const uint32_t row = (uint32_t)npx * 4u;
       const bool has_bkg = D.background && P.include_background;
-      if (!first) mbar_wait(empty_e, parity ^ 1u);  // previous item's exposure tile fully consumed
+      if (!first)  // previous item's exposure tile fully consumed
+        while (!mbar_try_wait(empty_e, parity ^ 1u)) __nanosleep(200);
       if (lane == 0) mbar_arrive_expect_tx(full_e, row * (uint32_t)D.nT);
       __syncwarp();
       for (int t = lane; t < D.nT; t += 32)
         bulk_g2s(es + t * kFoldTPX, D.exposure + (size_t)t * D.P + p0, row, full_e);
-      if (!first) mbar_wait(empty_x, parity ^ 1u);
+      if (!first)
+        while (!mbar_try_wait(empty_x, parity ^ 1u)) __nanosleep(200);
       uint32_t total = 0;
       if (has_bkg) total += row * (uint32_t)D.nR;
       if (D.counts) total += row * (uint32_t)D.nR;
@@ -840,10 +859,8 @@ __global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const
   }
 
   // ================= compute warps =================
-  const int px0 = 16 * warp;                      // first pixel of this warp inside the tile
-  const int q = lane & 3, tslot = lane >> 2;      // phase 1: 4 pixel quads x 8 true-energy slots
-  const int pr = lane & 7, cslot = lane >> 3;     // phase 2: 8 pixel pairs x 4 reco chunks
-  double* vw = vs + px0;                          // this warp's columns of v[g][t][128]
+  const int q = tid & 31, slot = tid >> 5;    // phase 1: 32 pixel quads x 8 true-energy slots
+  const int pp = tid & 63, cslot = tid >> 6;  // phase 2: 64 pixel pairs x 4 reco chunks (warp-uniform chunk)
   uint32_t parity = 0;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x, parity ^= 1u) {
     const int b = item % P.B;
@@ -858,10 +875,9 @@ __global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const
     const int* list = P.lists + (size_t)item * (kBinCap + 1);
     const int nl = __ldg(list);
 
-    // phase-1 quad of this lane and its pointer into every overlapping cutout (nullptr: outside)
-    const int lq = px0 + 4 * q;                   // local pixel of the quad
-    const bool qlive = lq < npx;
-    const int pq = p0 + lq;
+    // phase-1 quad of this thread and its pointer into every overlapping cutout (nullptr: outside)
+    const bool qlive = 4 * q < npx;
+    const int pq = p0 + 4 * q;
     const int qy = pq / nx, qx = pq - qy * nx;    // nx % 4 == 0: the quad lies in one row
     const float* cptr[kFoldLMax];
     int pstr[kFoldLMax], foff[kFoldLMax], grp[kFoldLMax];
@@ -882,19 +898,23 @@ __global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const
     }
 
     const int nchunks = nRp >> 3;
+    const int vstride = G * kFoldTCH * kFoldTPX;  // one half of the double buffer
     double stat = 0.0;
-    mbar_wait(full_e, parity);
-    for (int cbase = 0; cbase < nchunks; cbase += 4) {  // one pass for nR <= 32
+    int pass = 0;                                 // global pass counter of this item (buffer parity)
+    while (!mbar_try_wait(full_e, parity)) {}
+    for (int cbase = 0; cbase < nchunks; cbase += 4) {  // one sweep for nR <= 32
       const int c = cbase + cslot;
+      const bool last_sweep = cbase + 4 >= nchunks;
       double acc0[8], acc1[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.0;
-      for (int t0 = 0; t0 < nT; t0 += kFoldTCH) {
+      for (int t0 = 0; t0 < nT; t0 += kFoldTCH, ++pass) {
+        double* vbuf = vs + (pass & 1) * vstride;
         // ---- phase 1: v[g][t][p] = 1e4 * exposure[t,p] * sum_s F_s[t] * conv_s[t,p] ----
         for (int g = 0; g < G; ++g) {
 #pragma unroll
           for (int tt = 0; tt < kFoldTCH / 8; ++tt) {
-            const int tl = tslot + 8 * tt, t = t0 + tl;
+            const int tl = slot + 8 * tt, t = t0 + tl;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             if (t < nT && qlive) {
 #pragma unroll
@@ -920,7 +940,7 @@ __global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const
                 s2 = fma(F, (double)cv.z, s2);
                 s3 = fma(F, (double)cv.w, s3);
               }
-              const float4 e = *reinterpret_cast<const float4*>(es + t * kFoldTPX + lq);
+              const float4 e = *reinterpret_cast<const float4*>(es + t * kFoldTPX + 4 * q);
               s0 = (s0 * (double)e.x) * 1e4;
               s1 = (s1 * (double)e.y) * 1e4;
               s2 = (s2 * (double)e.z) * 1e4;
@@ -931,18 +951,22 @@ __global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const
               if (!isfinite(s2)) s2 = 0.0;
               if (!isfinite(s3)) s3 = 0.0;
             }
-            double* dst = vw + ((size_t)g * kFoldTCH + tl) * kFoldTPX + 4 * q;
+            double* dst = vbuf + ((size_t)g * kFoldTCH + tl) * kFoldTPX + 4 * q;
             *reinterpret_cast<double2*>(dst) = make_double2(s0, s1);
             *reinterpret_cast<double2*>(dst + 2) = make_double2(s2, s3);
           }
         }
-        __syncwarp();
+        if (last_sweep && t0 + kFoldTCH >= nT) {  // this warp no longer reads the exposure tile
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_e);
+        }
+        compute_barrier();  // v of this pass visible; the other half of the buffer is free again
         // ---- phase 2: acc[r] += pdf[t][r] * v[t][p] over the non-zero band ----
         if (c < nchunks) {
           for (int g = 0; g < G; ++g) {
             const int blo = __ldg(D.band + (g * nchunks + c) * 2), bhi = __ldg(D.band + (g * nchunks + c) * 2 + 1);
             const int tlo = max(blo, t0), thi = min(bhi, t0 + kFoldTCH);
-            const double* vrow = vw + (size_t)g * kFoldTCH * kFoldTPX + 2 * pr;
+            const double* vrow = vbuf + (size_t)g * kFoldTCH * kFoldTPX + 2 * pp;
             const double* prow = pdf + (size_t)g * nT * nRp + 8 * c;
             for (int t = tlo; t < thi; ++t) {
               const double2 v = *reinterpret_cast<const double2*>(vrow + (t - t0) * kFoldTPX);
@@ -959,14 +983,12 @@ __global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const
             }
           }
         }
-        __syncwarp();
       }
-      const bool last = cbase + 4 >= nchunks;
-      if (last && lane == 0) mbar_arrive(empty_e);  // this warp no longer reads the exposure tile
 
       // ---- epilogue for reco chunk c: background, clip, Cash (inputs staged in shared memory) ----
-      if (cbase == 0) mbar_wait(full_x, parity);
-      const int lp = px0 + 2 * pr;
+      if (cbase == 0)
+        while (!mbar_try_wait(full_x, parity)) {}
+      const int lp = 2 * pp;
       if (c < nchunks && lp < npx) {
         const bool has_bkg = D.background && P.include_background;
 #pragma unroll
@@ -1018,6 +1040,9 @@ __global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) stat += __shfl_xor_sync(0xffffffffu, stat, o);
     if (lane == 0) P.partials[((size_t)b * P.n_tiles + tile) * kFoldWarps + warp] = stat;
+    // the next item's first phase 1 writes buffer (pass & 1) of ITS numbering = 0, which some warp may still be
+    // reading as the last pass of this item when the pass count is odd: realign with one barrier
+    compute_barrier();
   }
 }
 
