@@ -240,7 +240,7 @@ struct gpy_context {
   size_t pinned_cap = 0;
   cudaEvent_t h2d_done = nullptr;
   bool h2d_pending = false;
-  DevBuf staging, flux, partials, stat, tiles, lists, bkgfac, scratch_a, scratch_b, scratch_c;
+  DevBuf staging, flux, partials, stat, tiles, scratch_a, scratch_b, scratch_c;
   std::vector<gpy_dataset*> tiles_for;  // dataset list the tile table was built for
   std::vector<uint64_t> tiles_ver;
   double* stat_pinned = nullptr;
@@ -249,7 +249,6 @@ struct gpy_context {
   int tma_blocks_per_sm[2] = {0, 0};
   int num_sms = 0;
   bool force_generic = false;
-  int fold_mode = 0;  // GPY_FOLD_KERNEL: 0 auto (bulk-copy staged when eligible), 2 generic
   double log_trunc = 0.0;
   int max_smem_optin = 0;
 };
@@ -703,8 +702,8 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         !al16(ds->mask) || P64 * (size_t)std::max(ds->nT, ds->nR) > (size_t)INT32_MAX)
       tma_ok = false;
   }
-  const gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G);
-  if (lay.total > (size_t)c->max_smem_optin || c->fold_mode == 2 || max_inst > gpy::kBinCap) tma_ok = false;
+  const gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G, max_inst);
+  if (lay.total > (size_t)c->max_smem_optin || c->force_generic) tma_ok = false;
   size_t max_fold_smem = 0;
   if (!tma_ok) {
     for (int d = 0; d < D; ++d)
@@ -731,7 +730,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   }
 
   GPY_TRY(c->flux.reserve(std::max(flux_len, (size_t)1) * sizeof(double)));
-  GPY_TRY(c->partials.reserve((size_t)B * n_tiles * 2 * sizeof(double)));
+  GPY_TRY(c->partials.reserve((size_t)B * n_tiles * sizeof(double)));
   GPY_TRY(c->stat.reserve((size_t)B * D * sizeof(double)));
   for (size_t i = 0; i < jobs.size(); ++i) jobs[i].out = (double*)c->flux.p + job_flux_off[i];
 
@@ -772,43 +771,21 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   fp.smem_nRp = max_nRp;
   fp.smem_G = max_G;
   const size_t n_items = (size_t)B * n_tiles;
-  int per_tile = 1;
-  const int variant = rq.npred_out ? 1 : 0;
   if (tma_ok) {
-    // tile binning + background factors, then the warp-specialised bulk-copy kernel
-    GPY_TRY(c->lists.reserve(n_items * (gpy::kBinCap + 1) * sizeof(int)));
-    GPY_TRY(c->bkgfac.reserve((size_t)D * B * max_nRp * sizeof(double)));
-    GPY_TRY(c->partials.reserve(n_items * gpy::kFoldWarps * sizeof(double)));
-    gpy::BinParams bp;
-    bp.ds = fp.ds;
-    bp.tile_ds = fp.tile_ds;
-    bp.evals = fp.evals;
-    bp.insts = fp.insts;
-    bp.lists = (int*)c->lists.p;
-    bp.bkgfac = (double*)c->bkgfac.p;
-    bp.B = B;
-    bp.n_tiles = n_tiles;
-    bp.n_datasets = D;
-    bp.max_nRp = max_nRp;
-    const size_t bin_warps = std::max(n_items, (size_t)D * B);
-    gpy::bin_sources_kernel<<<(unsigned)((bin_warps + 7) / 8), 256, 0, c->stream>>>(bp);
-    c->launches++;
-    fp.lists = (const int*)c->lists.p;
-    fp.bkgfac = (const double*)c->bkgfac.p;
-    fp.partials = (double*)c->partials.p;
+    const int variant = rq.npred_out ? 1 : 0;
     auto kern = variant ? gpy::fold_cash_tma_kernel<true> : gpy::fold_cash_tma_kernel<false>;
     if (lay.total > c->tma_smem_set[variant]) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
       c->tma_smem_set[variant] = lay.total;
+      c->tma_blocks_per_sm[variant] = 0;
     }
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, gpy::kFoldTmaThreads, lay.total));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, gpy::kFoldThreads, lay.total));
     per_sm = std::max(per_sm, 1);
     const unsigned grid = (unsigned)std::min(n_items, (size_t)per_sm * c->num_sms);
-    kern<<<grid, gpy::kFoldTmaThreads, lay.total, c->stream>>>(fp);
-    per_tile = gpy::kFoldWarps;
+    kern<<<grid, gpy::kFoldThreads, lay.total, c->stream>>>(fp);
   } else {
     if (max_fold_smem > c->fold_smem_set) {
       CUDA_TRY(cudaFuncSetAttribute(gpy::fold_cash_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -821,7 +798,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   }
   c->launches++;
   gpy::reduce_stat_kernel<<<dim3(B, D), 256, 0, c->stream>>>((const double*)c->partials.p, fp.ds, n_tiles, D,
-                                                              per_tile, (double*)c->stat.p);
+                                                              (double*)c->stat.p);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return GPY_OK;
@@ -863,8 +840,6 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
   c->force_generic = std::getenv("GPY_FORCE_GENERIC_FOLD") != nullptr;
-  if (const char* m = std::getenv("GPY_FOLD_KERNEL")) c->fold_mode = std::atoi(m);
-  if (c->force_generic) c->fold_mode = 2;
   c->log_trunc = std::log((double)(float)1e-25);  // Cython: log(<float>TRUNCATION_VALUE), .pyx:35
   *out = c;
   return GPY_OK;
@@ -874,8 +849,7 @@ int gpy_finalize(gpy_context_t* c) {
   if (!c) return GPY_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->staging, &c->flux, &c->partials, &c->stat, &c->tiles, &c->lists, &c->bkgfac, &c->scratch_a,
-                    &c->scratch_b, &c->scratch_c})
+  for (DevBuf* b : {&c->staging, &c->flux, &c->partials, &c->stat, &c->tiles, &c->scratch_a, &c->scratch_b, &c->scratch_c})
     b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->stat_pinned) cudaFreeHost(c->stat_pinned);

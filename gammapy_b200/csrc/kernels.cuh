@@ -404,9 +404,7 @@ struct FoldParams {
   const EvalDev* evals;     // [n_datasets * B], index d * B + b
   const InstDev* insts;
   const double* flux;
-  double* partials;         // [B, n_tiles] (generic) or [B, n_tiles, 8] (warp partials of the bulk-copy kernel)
-  const int* lists;         // [B * n_tiles][kBinCap + 1] per-item overlap lists (bin_sources_kernel)
-  const double* bkgfac;     // [n_datasets * B][smem_nRp] background factors (bin_sources_kernel)
+  double* partials;         // [B, n_tiles]
   double* npred_out;        // [nR, P] or null (single dataset, B == 1)
   int B, n_tiles, n_datasets;
   int include_background;   // add background model and clip at 0 (MapDataset.npred) or signal only
@@ -686,230 +684,164 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-// ---- tile binning + background factors (one warp per work item), launched before the fold ----------
-constexpr int kBinCap = 63;  // overlapping sources recorded per (tile, vector); the host falls back beyond
-struct BinParams {
-  const DatasetDev* ds;
-  const int* tile_ds;
-  const EvalDev* evals;
-  const InstDev* insts;
-  int* lists;        // [n_items][kBinCap + 1]: count, then instance indices in ascending order
-  double* bkgfac;    // [n_datasets * B][max_nRp]
-  int B, n_tiles, n_datasets, max_nRp;
-};
-
-__global__ void __launch_bounds__(256) bin_sources_kernel(const BinParams P) {
-  const int lane = threadIdx.x & 31;
-  const long long gw = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
-  const long long n_items = (long long)P.B * P.n_tiles;
-  // background factors norm * (E_c / E_0)^-tilt (PowerLawNormSpectralModel.evaluate, spectral.py:1159-1162)
-  if (gw < (long long)P.n_datasets * P.B) {
-    const int d = (int)(gw / P.B);
-    const DatasetDev& D = P.ds[d];
-    const EvalDev& ev = P.evals[gw];
-    for (int r = lane; r < P.max_nRp; r += 32) {
-      double fac = 1.0;
-      if (ev.bkg_enabled && r < D.nR) fac = ev.bkg_norm * pow(D.ecenter[r] / ev.bkg_ref, -ev.bkg_tilt);
-      P.bkgfac[gw * P.max_nRp + r] = fac;
-    }
-  }
-  if (gw >= n_items) return;
-  const int b = (int)(gw % P.B);
-  const int tile = (int)(gw / P.B);
-  const int d = P.tile_ds[tile];
-  const DatasetDev& D = P.ds[d];
-  const EvalDev& ev = P.evals[(size_t)d * P.B + b];
-  const int p0 = (tile - D.tile_begin) * kFoldTPX;
-  const int npx = min(kFoldTPX, (int)D.P - p0);
-  const int y_first = p0 / D.nx, y_last = (p0 + npx - 1) / D.nx;
-  const int x_first = p0 - y_first * D.nx, x_last = p0 + npx - 1 - y_last * D.nx;
-  int* out = P.lists + gw * (kBinCap + 1);
-  int n = 0;
-  for (int base = 0; base < ev.inst_count; base += 32) {
-    const int i = base + lane;
-    bool ov = false;
-    if (i < ev.inst_count) {
-      const InstDev& in = P.insts[ev.inst_begin + i];
-      ov = in.y0 <= y_last && in.y0 + in.cy > y_first;
-      if (ov && y_first == y_last) ov = in.x0 <= x_last && in.x0 + in.cx > x_first;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, ov);
-    const int pos = n + __popc(m & ((1u << lane) - 1u));
-    if (ov && pos < kBinCap) out[1 + pos] = ev.inst_begin + i;
-    n += __popc(m);
-  }
-  if (lane == 0) out[0] = min(n, kBinCap);
-}
-
 struct FoldSmem {  // byte offsets of the fixed shared-memory layout
-  size_t es, bs, cs, ms, vs, pdf, bars, total;
+  size_t es, bs, cs, ms, vs, pdf, bkgfac, scratch, slist, bars, total;
 };
-constexpr int kFoldLMax = 4;        // overlapping sources whose per-thread pointers live in registers
-constexpr int kFoldWarps = 8;       // compute warps
-constexpr int kFoldTmaThreads = (kFoldWarps + 1) * 32;  // + one producer warp
-__host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int G) {
+__host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int G, int max_inst) {
   FoldSmem L;
   size_t o = 0;
-  L.es = o;   o += (size_t)nT * kFoldTPX * 4;
-  L.bs = o;   o += (size_t)nR * kFoldTPX * 4;
-  L.cs = o;   o += (size_t)nR * kFoldTPX * 4;
-  L.ms = o;   o += ((size_t)nR * kFoldTPX + 15) / 16 * 16;
-  L.vs = o;   o += (size_t)2 * G * kFoldTCH * kFoldTPX * 8;  // double buffered
-  L.pdf = o;  o += (size_t)G * nT * nRp * 8;
+  L.es = o;      o += (size_t)nT * kFoldTPX * 4;
+  L.bs = o;      o += (size_t)nR * kFoldTPX * 4;
+  L.cs = o;      o += (size_t)nR * kFoldTPX * 4;
+  L.ms = o;      o += ((size_t)nR * kFoldTPX + 15) / 16 * 16;
+  L.vs = o;      o += (size_t)G * kFoldTCH * kFoldTPX * 8;
+  L.pdf = o;     o += (size_t)G * nT * nRp * 8;
+  L.bkgfac = o;  o += (size_t)nRp * 8;
+  L.scratch = o; o += 8 * 8;
+  L.slist = o;   o += (size_t)max_inst * sizeof(InstDev);
   L.bars = (o + 7) / 8 * 8;
-  L.total = L.bars + 4 * 8;
+  L.total = L.bars + 2 * 8;
   return L;
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void compute_barrier() {  // the 8 compute warps only (named barrier 1)
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-}
+constexpr int kFoldLMax = 4;  // overlapping sources whose per-thread offsets live in registers
 
-// Warp-specialised, persistent fold + Cash kernel.
-//   producer warp : per work item, 1-D bulk copies (TMA engine) of the exposure tile [nT][128] and of the
-//                   background / counts / mask tiles [nR][128] into shared memory; full / empty mbarriers.
-//   compute warps : phase 1 (thread = pixel quad x true-energy slot) writes v[t][p] for 16 true bins into one
-//                   half of a double-buffered shared array; phase 2 (thread = pixel pair x reco chunk, chunk
-//                   uniform per warp so the band loop and the Cash log do not diverge) accumulates in registers.
-//                   One named barrier per pass; the Cash partial of every warp goes to partials[b][8 tile + w].
 template <bool WRITE_NPRED>
-__global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const FoldParams P) {
+__global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const FoldParams P) {
   extern __shared__ __align__(128) unsigned char fold_raw[];
-  const FoldSmem L = fold_tma_layout(P.smem_nT, P.smem_nR, P.smem_nRp, P.smem_G);
+  const FoldSmem L = fold_tma_layout(P.smem_nT, P.smem_nR, P.smem_nRp, P.smem_G, P.max_inst);
   float* es = reinterpret_cast<float*>(fold_raw + L.es);
   float* bs = reinterpret_cast<float*>(fold_raw + L.bs);
   float* cs = reinterpret_cast<float*>(fold_raw + L.cs);
   unsigned char* ms = fold_raw + L.ms;
   double* vs = reinterpret_cast<double*>(fold_raw + L.vs);
   double* pdf_s = reinterpret_cast<double*>(fold_raw + L.pdf);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + L.bars);
-  uint64_t* full_e = &bars[0];   // exposure tile landed
-  uint64_t* full_x = &bars[1];   // epilogue inputs landed
-  uint64_t* empty_e = &bars[2];  // all compute warps are done with the exposure tile
-  uint64_t* empty_x = &bars[3];  // all compute warps are done with the epilogue inputs
+  double* bkgfac = reinterpret_cast<double*>(fold_raw + L.bkgfac);
+  double* scratch = reinterpret_cast<double*>(fold_raw + L.scratch);
+  InstDev* slist = reinterpret_cast<InstDev*>(fold_raw + L.slist);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + L.bars);  // [0] exposure, [1] epilogue inputs
+  __shared__ int n_list;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int n_items = P.B * P.n_tiles;
   if (tid == 0) {
-    mbar_init(full_e, 1);
-    mbar_init(full_x, 1);
-    mbar_init(empty_e, kFoldWarps);
-    mbar_init(empty_x, kFoldWarps);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  // edisp matrices: single-dataset launches keep them in shared memory for the whole kernel
-  const bool pdf_shared = P.n_datasets == 1;
-  if (pdf_shared) {
-    const DatasetDev& D0 = P.ds[0];
-    for (int i = tid; i < D0.n_groups * D0.nT * D0.nRp; i += kFoldTmaThreads) pdf_s[i] = D0.edisp[i];
   }
   __syncthreads();
 
-  if (warp == kFoldWarps) {
-    // ================= producer warp =================
-    uint32_t parity = 0;
-    bool first = true;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int tile = item / P.B;
-      const DatasetDev& D = P.ds[P.tile_ds[tile]];
-      const int p0 = (tile - D.tile_begin) * kFoldTPX;
-      const int npx = min(kFoldTPX, (int)D.P - p0);
-      const uint32_t row = (uint32_t)npx * 4u;
-      const bool has_bkg = D.background && P.include_background;
-      if (!first)  // previous item's exposure tile fully consumed
-        while (!mbar_try_wait(empty_e, parity ^ 1u)) __nanosleep(200);
-      if (lane == 0) mbar_arrive_expect_tx(full_e, row * (uint32_t)D.nT);
-      __syncwarp();
-      for (int t = lane; t < D.nT; t += 32)
-        bulk_g2s(es + t * kFoldTPX, D.exposure + (size_t)t * D.P + p0, row, full_e);
-      if (!first)
-        while (!mbar_try_wait(empty_x, parity ^ 1u)) __nanosleep(200);
-      uint32_t total = 0;
-      if (has_bkg) total += row * (uint32_t)D.nR;
-      if (D.counts) total += row * (uint32_t)D.nR;
-      if (D.counts && D.mask) total += (uint32_t)npx * (uint32_t)D.nR;
-      if (lane == 0) mbar_arrive_expect_tx(full_x, total);
-      __syncwarp();
-      for (int r = lane; r < D.nR; r += 32) {
-        const size_t off = (size_t)r * D.P + p0;
-        if (has_bkg) bulk_g2s(bs + r * kFoldTPX, D.background + off, row, full_x);
-        if (D.counts) bulk_g2s(cs + r * kFoldTPX, D.counts + off, row, full_x);
-        if (D.counts && D.mask) bulk_g2s(ms + r * kFoldTPX, D.mask + off, (uint32_t)npx, full_x);
-      }
-      first = false;
-      parity ^= 1u;
+  // producers (warp 0): bulk copies of one item's tiles
+  auto issue_expo = [&](int item) {
+    const int tile = item / P.B;
+    const DatasetDev& D = P.ds[P.tile_ds[tile]];
+    const int p0 = (tile - D.tile_begin) * kFoldTPX;
+    const int npx = min(kFoldTPX, (int)D.P - p0);
+    const uint32_t row = (uint32_t)npx * 4u;
+    if (tid == 0) mbar_arrive_expect_tx(&bars[0], row * (uint32_t)D.nT);
+    __syncwarp();
+    for (int t = tid; t < D.nT; t += 32)
+      bulk_g2s(es + t * kFoldTPX, D.exposure + (size_t)t * D.P + p0, row, &bars[0]);
+  };
+  auto issue_epi = [&](int item) {
+    const int tile = item / P.B;
+    const DatasetDev& D = P.ds[P.tile_ds[tile]];
+    const int p0 = (tile - D.tile_begin) * kFoldTPX;
+    const int npx = min(kFoldTPX, (int)D.P - p0);
+    const uint32_t row = (uint32_t)npx * 4u;
+    uint32_t total = 0;
+    if (D.background && P.include_background) total += row * (uint32_t)D.nR;
+    if (D.counts) total += row * (uint32_t)D.nR;
+    if (D.counts && D.mask) total += (uint32_t)npx * (uint32_t)D.nR;
+    if (tid == 0) mbar_arrive_expect_tx(&bars[1], total);
+    __syncwarp();
+    for (int r = tid; r < D.nR; r += 32) {
+      const size_t off = (size_t)r * D.P + p0;
+      if (D.background && P.include_background) bulk_g2s(bs + r * kFoldTPX, D.background + off, row, &bars[1]);
+      if (D.counts) bulk_g2s(cs + r * kFoldTPX, D.counts + off, row, &bars[1]);
+      if (D.counts && D.mask) bulk_g2s(ms + r * kFoldTPX, D.mask + off, (uint32_t)npx, &bars[1]);
     }
-    return;
-  }
+  };
 
-  // ================= compute warps =================
-  const int q = tid & 31, slot = tid >> 5;    // phase 1: 32 pixel quads x 8 true-energy slots
-  const int pp = tid & 63, cslot = tid >> 6;  // phase 2: 64 pixel pairs x 4 reco chunks (warp-uniform chunk)
+  int item = blockIdx.x;
+  if (item < n_items && tid < 32) {
+    issue_expo(item);
+    issue_epi(item);
+  }
   uint32_t parity = 0;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x, parity ^= 1u) {
+  int cur_ds = -1;
+
+  const int q = tid & 31, slot = tid >> 5;   // phase 1: 32 pixel quads x 8 energy slots
+  const int pp = tid & 63, cslot = tid >> 6;  // phase 2: 64 pixel pairs x 4 reco-chunk slots
+
+  for (; item < n_items; item += gridDim.x, parity ^= 1u) {
     const int b = item % P.B;
     const int tile = item / P.B;
     const int d = P.tile_ds[tile];
-    const DatasetDev& D = P.ds[d];
-    const int nT = D.nT, nR = D.nR, nRp = D.nRp, G = D.n_groups, nx = D.nx;
+    const DatasetDev D = P.ds[d];
+    const EvalDev ev = P.evals[(size_t)d * P.B + b];
+    const int nT = D.nT, nR = D.nR, nRp = D.nRp, G = D.n_groups;
     const int p0 = (tile - D.tile_begin) * kFoldTPX;
     const int npx = min(kFoldTPX, (int)D.P - p0);
-    const double* pdf = pdf_shared ? pdf_s : D.edisp;
-    const double* bkgfac = P.bkgfac + ((size_t)d * P.B + b) * P.smem_nRp;
-    const int* list = P.lists + (size_t)item * (kBinCap + 1);
-    const int nl = __ldg(list);
+    const int next = item + gridDim.x;
 
-    // phase-1 quad of this thread and its pointer into every overlapping cutout (nullptr: outside)
-    const bool qlive = 4 * q < npx;
+    if (d != cur_ds) {  // edisp matrices of this dataset (block-uniform branch)
+      for (int i = tid; i < G * nT * nRp; i += kFoldThreads) pdf_s[i] = D.edisp[i];
+      cur_ds = d;
+    }
+    if (tid < nRp) {
+      double fac = 1.0;
+      if (ev.bkg_enabled && tid < nR)  // PowerLawNormSpectralModel.evaluate (spectral.py:1159-1162)
+        fac = ev.bkg_norm * pow(D.ecenter[tid] / ev.bkg_ref, -ev.bkg_tilt);
+      bkgfac[tid] = fac;
+    }
+    const int y_first = p0 / D.nx, y_last = (p0 + npx - 1) / D.nx;
+    const int x_first = p0 - y_first * D.nx, x_last = p0 + npx - 1 - y_last * D.nx;
+    if (tid < 32) {
+      int n = 0;
+      for (int base = 0; base < ev.inst_count; base += 32) {
+        const int i = base + tid;
+        bool ov = false;
+        InstDev in;
+        if (i < ev.inst_count) {
+          in = P.insts[ev.inst_begin + i];
+          ov = in.y0 <= y_last && in.y0 + in.cy > y_first;
+          if (ov && y_first == y_last) ov = in.x0 <= x_last && in.x0 + in.cx > x_first;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ov);
+        if (ov) slist[n + __popc(m & ((1u << tid) - 1u))] = in;
+        n += __popc(m);
+      }
+      if (tid == 0) n_list = n;
+    }
+    __syncthreads();
+    const int nl = n_list;
+
+    // this thread's pixel quad and its offset inside every overlapping cutout (-1: outside)
     const int pq = p0 + 4 * q;
-    const int qy = pq / nx, qx = pq - qy * nx;    // nx % 4 == 0: the quad lies in one row
-    const float* cptr[kFoldLMax];
-    int pstr[kFoldLMax], foff[kFoldLMax], grp[kFoldLMax];
+    const bool qlive = 4 * q < npx;
+    const int qy = pq / D.nx, qx = pq - qy * D.nx;
+    int off[kFoldLMax];
 #pragma unroll
     for (int l = 0; l < kFoldLMax; ++l) {
-      cptr[l] = nullptr;
-      pstr[l] = 0;
-      foff[l] = 0;
-      grp[l] = -1;
-      if (l < nl) {
-        const InstDev& in = P.insts[__ldg(list + 1 + l)];
+      off[l] = -1;
+      if (l < nl && qlive) {
+        const InstDev& in = slist[l];
         const int ly = qy - in.y0, lx = qx - in.x0a;
-        grp[l] = in.group;
-        foff[l] = in.flux_off;
-        pstr[l] = in.plane_stride;
-        if (qlive && ly >= 0 && ly < in.cy && lx >= 0 && lx < in.pitch) cptr[l] = in.conv + ly * in.pitch + lx;
+        if (ly >= 0 && ly < in.cy && lx >= 0 && lx < in.pitch) off[l] = ly * in.pitch + lx;
       }
     }
 
     const int nchunks = nRp >> 3;
-    const int vstride = G * kFoldTCH * kFoldTPX;  // one half of the double buffer
     double stat = 0.0;
-    int pass = 0;                                 // global pass counter of this item (buffer parity)
-    while (!mbar_try_wait(full_e, parity)) {}
-    for (int cbase = 0; cbase < nchunks; cbase += 4) {  // one sweep for nR <= 32
+    for (int cbase = 0; cbase < nchunks; cbase += 4) {  // one pass for nR <= 32
       const int c = cbase + cslot;
-      const bool last_sweep = cbase + 4 >= nchunks;
       double acc0[8], acc1[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.0;
-      for (int t0 = 0; t0 < nT; t0 += kFoldTCH, ++pass) {
-        double* vbuf = vs + (pass & 1) * vstride;
+
+      for (int t0 = 0; t0 < nT; t0 += kFoldTCH) {
+        if (cbase == 0 && t0 == 0) mbar_wait(&bars[0], parity);  // exposure tile has landed
         // ---- phase 1: v[g][t][p] = 1e4 * exposure[t,p] * sum_s F_s[t] * conv_s[t,p] ----
         for (int g = 0; g < G; ++g) {
 #pragma unroll
@@ -919,55 +851,53 @@ __global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const
             if (t < nT && qlive) {
 #pragma unroll
               for (int l = 0; l < kFoldLMax; ++l) {
-                if (cptr[l] == nullptr || grp[l] != g) continue;
-                const float4 cv = __ldg(reinterpret_cast<const float4*>(cptr[l] + (size_t)t * pstr[l]));
-                const double F = __ldg(P.flux + foff[l] + t);
-                s0 = fma(F, (double)cv.x, s0);
-                s1 = fma(F, (double)cv.y, s1);
-                s2 = fma(F, (double)cv.z, s2);
-                s3 = fma(F, (double)cv.w, s3);
+                if (off[l] < 0) continue;
+                const InstDev& in = slist[l];
+                if (in.group != g) continue;
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(in.conv + (size_t)t * in.plane_stride + off[l]));
+                const double F = P.flux[in.flux_off + t];
+                const double a0 = F * (double)cv.x, a1 = F * (double)cv.y, a2 = F * (double)cv.z, a3 = F * (double)cv.w;
+                // WcsNDMap.stack(nan_to_num=True): non-finite source values do not enter the sum
+                s0 += isfinite(a0) ? a0 : 0.0;
+                s1 += isfinite(a1) ? a1 : 0.0;
+                s2 += isfinite(a2) ? a2 : 0.0;
+                s3 += isfinite(a3) ? a3 : 0.0;
               }
               for (int l = kFoldLMax; l < nl; ++l) {  // rare: more than kFoldLMax sources on one tile
-                const InstDev& in = P.insts[__ldg(list + 1 + l)];
+                const InstDev& in = slist[l];
                 if (in.group != g) continue;
                 const int ly = qy - in.y0, lx = qx - in.x0a;
                 if (ly < 0 || ly >= in.cy || lx < 0 || lx >= in.pitch) continue;
                 const float4 cv = __ldg(reinterpret_cast<const float4*>(in.conv + (size_t)t * in.plane_stride +
                                                                         ly * in.pitch + lx));
-                const double F = __ldg(P.flux + in.flux_off + t);
-                s0 = fma(F, (double)cv.x, s0);
-                s1 = fma(F, (double)cv.y, s1);
-                s2 = fma(F, (double)cv.z, s2);
-                s3 = fma(F, (double)cv.w, s3);
+                const double F = P.flux[in.flux_off + t];
+                const double a0 = F * (double)cv.x, a1 = F * (double)cv.y, a2 = F * (double)cv.z, a3 = F * (double)cv.w;
+                s0 += isfinite(a0) ? a0 : 0.0;
+                s1 += isfinite(a1) ? a1 : 0.0;
+                s2 += isfinite(a2) ? a2 : 0.0;
+                s3 += isfinite(a3) ? a3 : 0.0;
               }
               const float4 e = *reinterpret_cast<const float4*>(es + t * kFoldTPX + 4 * q);
               s0 = (s0 * (double)e.x) * 1e4;
               s1 = (s1 * (double)e.y) * 1e4;
               s2 = (s2 * (double)e.z) * 1e4;
               s3 = (s3 * (double)e.w) * 1e4;
-              // WcsNDMap.stack(nan_to_num=True): a non-finite source term does not enter the sum
-              if (!isfinite(s0)) s0 = 0.0;
-              if (!isfinite(s1)) s1 = 0.0;
-              if (!isfinite(s2)) s2 = 0.0;
-              if (!isfinite(s3)) s3 = 0.0;
             }
-            double* dst = vbuf + ((size_t)g * kFoldTCH + tl) * kFoldTPX + 4 * q;
+            double* dst = vs + ((size_t)g * kFoldTCH + tl) * kFoldTPX + 4 * q;
             *reinterpret_cast<double2*>(dst) = make_double2(s0, s1);
             *reinterpret_cast<double2*>(dst + 2) = make_double2(s2, s3);
           }
         }
-        if (last_sweep && t0 + kFoldTCH >= nT) {  // this warp no longer reads the exposure tile
-          __syncwarp();
-          if (lane == 0) mbar_arrive(empty_e);
-        }
-        compute_barrier();  // v of this pass visible; the other half of the buffer is free again
+        __syncthreads();
+        // exposure tile fully consumed: start fetching the next item's while phase 2 / the epilogue run
+        if (tid < 32 && cbase + 4 >= nchunks && t0 + kFoldTCH >= nT && next < n_items) issue_expo(next);
         // ---- phase 2: acc[r] += pdf[t][r] * v[t][p] over the non-zero band ----
         if (c < nchunks) {
           for (int g = 0; g < G; ++g) {
-            const int blo = __ldg(D.band + (g * nchunks + c) * 2), bhi = __ldg(D.band + (g * nchunks + c) * 2 + 1);
+            const int blo = D.band[(g * nchunks + c) * 2], bhi = D.band[(g * nchunks + c) * 2 + 1];
             const int tlo = max(blo, t0), thi = min(bhi, t0 + kFoldTCH);
-            const double* vrow = vbuf + (size_t)g * kFoldTCH * kFoldTPX + 2 * pp;
-            const double* prow = pdf + (size_t)g * nT * nRp + 8 * c;
+            const double* vrow = vs + (size_t)g * kFoldTCH * kFoldTPX + 2 * pp;
+            const double* prow = pdf_s + (size_t)g * nT * nRp + 8 * c;
             for (int t = tlo; t < thi; ++t) {
               const double2 v = *reinterpret_cast<const double2*>(vrow + (t - t0) * kFoldTPX);
               const double2 m0 = *reinterpret_cast<const double2*>(prow + t * nRp);
@@ -983,13 +913,12 @@ __global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const
             }
           }
         }
+        __syncthreads();
       }
 
       // ---- epilogue for reco chunk c: background, clip, Cash (inputs staged in shared memory) ----
-      if (cbase == 0)
-        while (!mbar_try_wait(full_x, parity)) {}
-      const int lp = 2 * pp;
-      if (c < nchunks && lp < npx) {
+      if (cbase == 0) mbar_wait(&bars[1], parity);
+      if (c < nchunks && 2 * pp < npx) {
         const bool has_bkg = D.background && P.include_background;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -998,27 +927,27 @@ __global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const
           double mu0 = acc0[j], mu1 = acc1[j];
           if (P.include_background) {
             if (has_bkg) {
-              const float2 bg = *reinterpret_cast<const float2*>(bs + r * kFoldTPX + lp);
-              const double fac = __ldg(bkgfac + r);
-              mu0 += (double)bg.x * fac;
-              mu1 += (double)bg.y * fac;
+              const float2 bg = *reinterpret_cast<const float2*>(bs + r * kFoldTPX + 2 * pp);
+              mu0 += (double)bg.x * bkgfac[r];
+              mu1 += (double)bg.y * bkgfac[r];
             }
             if (mu0 < 0.0) mu0 = 0.0;  // npred_total.data[npred_total.data < 0.0] = 0 (map.py:787)
             if (mu1 < 0.0) mu1 = 0.0;
           }
           if (WRITE_NPRED) {
-            double* o = P.npred_out + (size_t)r * D.P + p0 + lp;
+            double* o = P.npred_out + (size_t)r * D.P + p0 + 2 * pp;
             *reinterpret_cast<double2*>(o) = make_double2(mu0, mu1);
           }
           if (D.counts) {
-            const float2 cn = *reinterpret_cast<const float2*>(cs + r * kFoldTPX + lp);
+            const float2 cn = *reinterpret_cast<const float2*>(cs + r * kFoldTPX + 2 * pp);
             unsigned short mk = 0x0101;
-            if (D.mask) mk = *reinterpret_cast<const unsigned short*>(ms + r * kFoldTPX + lp);
+            if (D.mask) mk = *reinterpret_cast<const unsigned short*>(ms + r * kFoldTPX + 2 * pp);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               const double mu = k == 0 ? mu0 : mu1;
               const double n = (double)(k == 0 ? cn.x : cn.y);
-              if (((mk >> (8 * k)) & 0xff) != 0) {
+              const bool m = ((mk >> (8 * k)) & 0xff) != 0;
+              if (m) {
                 double npr, lognpr = 0.0;
                 if (mu > kTrunc) {
                   npr = mu;
@@ -1035,25 +964,20 @@ __global__ void __launch_bounds__(kFoldTmaThreads, 2) fold_cash_tma_kernel(const
         }
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty_x);  // this warp no longer reads the epilogue tiles
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) stat += __shfl_xor_sync(0xffffffffu, stat, o);
-    if (lane == 0) P.partials[((size_t)b * P.n_tiles + tile) * kFoldWarps + warp] = stat;
-    // the next item's first phase 1 writes buffer (pass & 1) of ITS numbering = 0, which some warp may still be
-    // reading as the last pass of this item when the pass count is odd: realign with one barrier
-    compute_barrier();
+    const double total = block_sum_256(stat, scratch);  // contains a block barrier after every epilogue read
+    if (tid == 0) P.partials[(size_t)b * P.n_tiles + tile] = total;
+    if (tid < 32 && next < n_items) issue_epi(next);
+    __syncthreads();  // scratch / list reuse in the next item
   }
 }
 
 // Second stage: stat[b, d] = 2 * sum of the tile partials of dataset d, fixed summation order.
 __global__ void __launch_bounds__(256)
 reduce_stat_kernel(const double* __restrict__ partials, const DatasetDev* __restrict__ ds, int n_tiles,
-                   int n_datasets, int per_tile, double* __restrict__ stat) {
+                   int n_datasets, double* __restrict__ stat) {
   __shared__ double sm[256];
   const int b = blockIdx.x, d = blockIdx.y;
-  const int begin = ds[d].tile_begin * per_tile, n = ds[d].n_tiles * per_tile;
-  n_tiles *= per_tile;
+  const int begin = ds[d].tile_begin, n = ds[d].n_tiles;
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) s += partials[(size_t)b * n_tiles + begin + i];
   sm[threadIdx.x] = s;
