@@ -1,0 +1,127 @@
+"""Host-side mirror of the gammapy API: axes, geometry, parameters, models, static IRF builders (CPU only)."""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+from gammapy_b200 import (DiskSpatialModel, EDispKernelMap, FoVBackgroundModel, GaussianSpatialModel, Map, MapAxis,
+                          MapDataset, Models, Parameter, PointSpatialModel, PowerLawSpectralModel, PSFMap, SkyModel,
+                          WcsGeom, configs)
+from oracle import adapter, wcs
+
+
+def test_map_axis_energy():
+    ax = MapAxis.from_energy_bounds("0.1 TeV", "10 TeV", nbin=10)
+    assert ax.nbin == 10 and ax.name == "energy"
+    assert_allclose(ax.edges, np.geomspace(0.1, 10, 11), rtol=1e-14)
+    assert_allclose(ax.center, np.sqrt(ax.edges[:-1] * ax.edges[1:]), rtol=1e-14)
+    ax2 = MapAxis.from_energy_bounds(100, 1e4, nbin=2, unit="GeV", name="energy_true")
+    assert_allclose(ax2.edges, [0.1, 1.0, 10.0], rtol=1e-14)
+    assert ax.copy(name="energy_true").name == "energy_true" and ax.name == "energy"
+    rad = MapAxis.from_bounds(0, 0.66, nbin=66, name="rad", unit="deg")
+    assert_allclose(rad.center[0], 0.005)
+    assert rad.upsample(20).nbin == 1320
+
+
+def test_wcs_geom_matches_oracle_geometry():
+    geom = WcsGeom.create(skydir=(0, 0), binsz=0.02, width=(4, 3), frame="galactic")
+    og = adapter.geom_to_oracle(geom)
+    assert geom.data_shape == (150, 200) == og.data_shape
+    assert_allclose(geom.solid_angle(), og.solid_angle(), rtol=1e-14)
+    lon, lat = og.get_coord()
+    c = geom.get_coord()
+    assert_allclose(c["lon"], lon)
+    assert_allclose(c["lat"], lat)
+    ys, xs = geom.cutout_slices_for((0.2, 0.1), 4.52, odd_npix=True)
+    _, (oys, oxs) = og.cutout_info((0.2, 0.1), 4.52, odd_npix=True)
+    assert (ys, xs) == (oys, oxs)
+    assert geom.to_odd_npix(max_radius=0.66).npix == (67, 67)
+    with pytest.raises(NotImplementedError):
+        WcsGeom.create(skydir=(10, 5), binsz=0.1, width=1)
+    with pytest.raises(NotImplementedError):
+        WcsGeom.create(binsz=0.1, width=1, proj="TAN")
+
+
+def test_parameter_factor_scale_contract():
+    """modeling/parameter.py:524-574: scale10 autoscale, factor <-> value."""
+    par = Parameter("amplitude", "3e-12 cm-2 s-1 TeV-1")
+    assert par.unit == "cm-2 s-1 TeV-1" and par.value == 3e-12
+    par.autoscale()
+    assert_allclose(par.scale, 1e-12)
+    assert_allclose(par.factor, 3.0)
+    par.factor = 4.5
+    assert_allclose(par.value, 4.5e-12)
+    lim = Parameter("index", 2.0, min=1, max=5)
+    assert_allclose([lim.factor_min, lim.factor_max], [1, 5])
+    scan = Parameter("norm", 1.0, error=0.1)
+    assert_allclose(scan.scan_values, np.linspace(0.8, 1.2, 11))
+    with pytest.raises(TypeError):
+        Parameter("x", 1.0, frozen="yes")
+
+
+def test_models_parameters_and_selection():
+    spatial = GaussianSpatialModel(lon_0="0.2 deg", lat_0="0.1 deg", sigma="0.3 deg", frame="galactic")
+    spectral = PowerLawSpectralModel(index=3, amplitude="1e-11 cm-2 s-1 TeV-1", reference="1 TeV")
+    model = SkyModel(spatial_model=spatial, spectral_model=spectral, name="src")
+    assert model.parameters.names == ["lon_0", "lat_0", "sigma", "e", "phi", "index", "amplitude", "reference"]
+    assert [p.name for p in model.parameters.free_parameters] == ["lon_0", "lat_0", "sigma", "index", "amplitude"]
+    assert_allclose(model.evaluation_radius, 1.5)
+    disk = DiskSpatialModel(r_0=2.0)
+    assert_allclose([disk.evaluation_radius, disk.evaluation_bin_size_min], [2.222, 0.198])
+    assert PointSpatialModel().evaluation_radius == 0
+    bkg = FoVBackgroundModel(dataset_name="a")
+    models = Models([model, bkg])
+    assert models.select(datasets_names="a").names == ["src", "a-bkg"]
+    assert models.select(datasets_names="b").names == ["src"]
+    with pytest.raises(TypeError):
+        model.spectral_model.index = 2.0  # parameters are assigned through .value, as in the reference
+    # independent copies per instance
+    other = PowerLawSpectralModel()
+    other.index.value = 1.0
+    assert spectral.index.value == 3
+
+
+def test_static_irf_builders():
+    e_true = MapAxis.from_energy_bounds(0.03, 30, 20, name="energy_true")
+    e_reco = MapAxis.from_energy_bounds(0.1, 10, 10)
+    geom = WcsGeom.create(skydir=(0, 0), binsz=0.02, width=4, frame="galactic", axes=[e_true])
+    sigma = np.geomspace(0.12, 0.04, 20)
+    kernel = PSFMap.from_gauss(e_true, sigma=sigma).get_psf_kernel(geom, containment=0.999)
+    data = kernel.data
+    assert data.shape[0] == 20 and data.shape[1] == data.shape[2] and data.shape[1] % 2 == 1
+    assert_allclose(data.sum(axis=(1, 2)), 1.0, rtol=1e-12)
+    assert np.all(data >= 0)
+    h = data.shape[1] // 2
+    assert np.all(data[:, h, h] == data.max(axis=(1, 2)))  # peaked at the centre pixel
+    # narrower PSF at high energy -> smaller support
+    support = [(np.abs(np.nonzero(p)[0] - h)).max() for p in data]
+    assert support[0] > support[-1]
+    # containment radius of a Gaussian: r = sigma sqrt(-2 ln(1 - f)), grid resolution 0.0005 deg
+    psf = PSFMap.from_gauss(e_true, sigma=0.05)
+    assert_allclose(psf.containment_radius(0.68), 0.05 * np.sqrt(-2 * np.log(0.32)), atol=6e-4)
+    edisp = EDispKernelMap.from_gauss(e_reco, e_true, sigma=0.15, bias=0).get_edisp_kernel().pdf_matrix
+    assert edisp.shape == (20, 10)
+    assert np.all(edisp.sum(axis=1) <= 1 + 1e-12) and edisp.sum(axis=1).max() > 0.99
+    diag = EDispKernelMap.from_diagonal_response(e_reco, e_true).get_edisp_kernel().pdf_matrix
+    assert_allclose(diag.sum(axis=1)[(e_true.edges[:-1] >= 0.1) & (e_true.edges[1:] <= 10)], 1.0)
+
+
+def test_map_dataset_create_and_masks():
+    ds = configs.make_c1(width=(1.0, 1.0), mask_radius=0.4)
+    assert ds.counts.data.dtype == np.float32 and ds.exposure.data.dtype == np.float32
+    assert ds.mask.data.dtype == bool
+    assert ds.mask_image.data.shape == (50, 50)
+    assert ds.mask_image.data.sum() == (ds.mask_fit.data[0]).sum()
+    assert ds.models.names == ["model-simu", "c1-bkg"]
+    empty = MapDataset.create(ds._geom)
+    assert not empty.mask_safe.data.any()  # as the reference: all-False safe mask until the user sets it
+    m = Map.from_geom(ds._geom)
+    assert m.data.dtype == np.float32  # maps/core.py:269 default dtype
+    assert (m + 1.5).data.dtype == np.float64 or (m + 1.5).data.dtype == np.float32
+
+
+def test_oracle_adapter_roundtrip():
+    ds = configs.make_c2(width=(2.0, 2.0), mask_radius=0.9)
+    de = adapter.evaluator_for(ds)
+    assert len(de.evaluators) == 5 and de.bkg_model is not None
+    assert de.ds.exposure.shape == (20, 100, 100) and de.ds.edisp.shape == (20, 10)
+    assert_allclose(de.ds.energy_center, ds._geom.axes["energy"].center)

@@ -228,3 +228,22 @@ def test_oracle_noise_floor_small():
     a = adapter.evaluator_for(ds, conv="fft32").npred()
     b = adapter.evaluator_for(ds, conv="exact64").npred()
     assert np.max(np.abs(a - b) / b) < 5e-6
+
+
+def test_golden_fixture_file():
+    """tests/golden/reference_kats.json (transcribed reference constants) against the oracle."""
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_kats.json")
+    gold = json.load(open(path))
+    c = gold["cash"]
+    assert_allclose(cash.cash(c["n_on"], c["mu_sig"]), c["cash"])
+    s = gold["spectral"]
+    pl = dict(s["powerlaw"], type="pl")
+    assert_allclose(spectral.integral(pl, 1.0, 10.0), pl["integral_1_10TeV"], rtol=1e-7)
+    ecpl = dict(s["ecpl"], type="ecpl")
+    assert_allclose(spectral.integral(ecpl, [1.0], [10.0]), ecpl["integral_1_10TeV"], rtol=1e-5)
+    lp = dict(s["logpar"], type="lp")
+    assert_allclose(spectral.integral(lp, [1.0], [10.0]), lp["integral_1_10TeV"], rtol=1e-5)
+    assert_allclose(spatial.disk_evaluate(1.0, 46.0, 1.0, 45.0, 2.0), gold["spatial"]["disk_value"], rtol=1e-7)
