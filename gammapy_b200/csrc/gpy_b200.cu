@@ -52,7 +52,8 @@ int fail(int code, const char* fmt, ...) {
 constexpr double kDegH = 0.017453292519943295;
 constexpr double kCutoutMargin = 0.1;  // deg, datasets/evaluator.py:17
 constexpr int kMaxOversampling = 200;  // modeling/models/spatial.py:54
-constexpr int kSlotsPerSource = 6;     // cached (spatial params, cutout) -> PSF-convolved cube
+constexpr int kSlotsPerSource = 6;     // cached (spatial params, cutout) -> PSF-convolved cube, kept between calls
+constexpr int kSlotsHardCap = 96;      // beyond this the per-call extras are trimmed at the next call
 
 // ---------------------------------------------------------------------------------------------
 // host geometry: the integer rules of astropy Cutout2D / overlap_slices and gammapy WcsGeom.cutout
@@ -213,6 +214,7 @@ struct Slot {  // one cached integrate_geom (+ PSF convolution) result
   std::vector<double> key;  // spatial parameter values
   bool valid = false;
   uint64_t stamp = 0;
+  uint64_t call_id = 0;  // evaluate() call that last handed this slot to a kernel: never evicted within that call
 };
 
 struct Source {
@@ -223,7 +225,7 @@ struct Source {
   double cached_lon = 0.0, cached_lat = 0.0;  // evaluator.py:93 _cached_position (radians)
   std::vector<double> cached_spatial;         // _cached_parameter_values_spatial
   bool has_cached_spatial = false;
-  Slot slots[kSlotsPerSource];
+  std::vector<Slot> slots = std::vector<Slot>(kSlotsPerSource);
   int last_f = 0;
   int n_spatial_evals = 0;
 };
@@ -484,23 +486,27 @@ int evaluator_update(const gpy_dataset* ds, const Source& src, const double* sp,
   return GPY_OK;
 }
 
-// Find or build the slot holding integrate_geom (x) PSF for (sp, rect).
-int get_slot(gpy_dataset* ds, Source& src, const double* sp, const Rect& rect, Slot** out) {
+// Find or build the slot holding integrate_geom (x) PSF for (sp, rect).  Slots handed out during the current
+// evaluate() call are pinned (their buffers are referenced by kernels not yet run); when every slot is pinned
+// the list grows, so a batch may hold any number of distinct spatial parameter tuples.
+int get_slot(gpy_dataset* ds, Source& src, const double* sp, const Rect& rect, uint64_t call_id, Slot** out) {
   gpy_context* c = ds->ctx;
   const int nsp = n_spatial_params(src.desc.spatial_type);
-  Slot* victim = &src.slots[0];
+  Slot* victim = nullptr;
   for (auto& s : src.slots) {
     if (s.valid && s.rect == rect && (int)s.key.size() == nsp &&
         std::memcmp(s.key.data(), sp, nsp * sizeof(double)) == 0) {
       s.stamp = ++c->stamp;
+      s.call_id = call_id;
       *out = &s;
       return GPY_OK;
     }
-    if (!s.valid) {
-      if (victim->valid) victim = &s;
-    } else if (victim->valid && s.stamp < victim->stamp) {
-      victim = &s;
-    }
+    if (s.valid && s.call_id == call_id) continue;  // pinned
+    if (!victim || (!s.valid && victim->valid) || (s.valid == victim->valid && s.stamp < victim->stamp)) victim = &s;
+  }
+  if (!victim) {
+    src.slots.emplace_back();
+    victim = &src.slots.back();
   }
   Slot& s = *victim;
   s.valid = false;
@@ -522,6 +528,7 @@ int get_slot(gpy_dataset* ds, Source& src, const double* sp, const Rect& rect, S
   s.key.assign(sp, sp + nsp);
   s.valid = true;
   s.stamp = ++c->stamp;
+  s.call_id = call_id;
   src.last_f = s.f;
   src.n_spatial_evals++;
   *out = &s;
@@ -562,10 +569,21 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   int max_nT = 0, max_nR = 0, max_nRp = 0, max_G = 0;
   bool tma_ok = true;
   const bool sequential = (B == 1);
+  const uint64_t call_id = ++c->stamp;
 
   for (int d = 0; d < D; ++d) {
     gpy_dataset* ds = rq.datasets[d];
     if (!ds || ds->ctx != c) return fail(GPY_ERR_INVALID, "dataset %d does not belong to this context", d);
+    for (auto& src : ds->sources)
+      if (src.slots.size() > (size_t)kSlotsHardCap) {  // extras of an earlier large batch: drop the oldest
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        std::sort(src.slots.begin(), src.slots.end(), [](const Slot& a, const Slot& b) { return a.stamp > b.stamp; });
+        for (size_t i = kSlotsPerSource; i < src.slots.size(); ++i) {
+          src.slots[i].w.release();
+          src.slots[i].conv.release();
+        }
+        src.slots.resize(kSlotsPerSource);
+      }
     gpy::DatasetDev& dd = dsd[d];
     dd.nx = ds->geom.nx;
     dd.ny = ds->geom.ny;
@@ -662,7 +680,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         const int amp_idx = src.desc.spectral_type == GPY_SPECTRAL_LP ? 0 : 1;
         if (sc[amp_idx] == 0.0) continue;
         Slot* slot = nullptr;
-        GPY_TRY(get_slot(ds, src, sp, rect, &slot));
+        GPY_TRY(get_slot(ds, src, sp, rect, call_id, &slot));
         gpy::InstDev in;
         std::memset(&in, 0, sizeof(in));
         in.x0 = rect.x0;

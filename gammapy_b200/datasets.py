@@ -282,6 +282,9 @@ class MapDataset:
 
     def evaluator_state(self, model_name):
         """Cutout / cache state of one model's evaluator (MapEvaluator, datasets/evaluator.py:174-243)."""
+        owner = getattr(self._device, "models_owner", None) if self._device is not None else None
+        if owner is not None and owner._signature == owner.signature(owner.datasets):
+            return owner.source_state(owner.datasets.index(self), self._source_names.index(model_name))
         eng = self._get_engine()
         return eng.source_state(0, self._source_names.index(model_name))
 

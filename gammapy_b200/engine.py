@@ -38,6 +38,7 @@ class DeviceDataset:
         self.ctx = ctx
         self.dataset = dataset
         self.handle = None
+        self.models_owner = None
         self.torch = torch
         self._keep = {}
         self._uploaded = {}
@@ -194,6 +195,14 @@ class LikelihoodEngine:
         arr = (_lib.SourceDesc * max(len(srcs), 1))(*srcs)
         _lib.check(self.ctx.lib.gpy_dataset_set_models(dev.handle, arr, len(srcs), C.byref(bkg)))
         ds._source_names = names
+        dev.models_owner = self
+
+    def _claim(self):
+        """The C handle of a dataset holds ONE model table: (re)install this engine's parameter columns when
+        another engine (e.g. ``MapDataset.npred`` vs ``Datasets.stat_sum``) configured it last."""
+        for ds in self.datasets:
+            if ds._device.models_owner is not self:
+                self._set_models(ds, ds._device)
 
     # -- evaluation ----------------------------------------------------------------------------------
     def values(self):
@@ -213,6 +222,7 @@ class LikelihoodEngine:
         if v2.shape[1] != self.n_par:
             raise ValueError(f"expected {self.n_par} parameter values per vector, got {v2.shape[1]}")
         B, D = v2.shape[0], len(self.datasets)
+        self._claim()
         stat = np.empty(B, dtype=float)
         per = np.empty((B, D), dtype=float) if per_dataset else None
         _lib.check(self.ctx.lib.gpy_stat_sum(self.ctx.handle, self._handles, D, _ptr(v2), B, self.n_par, _ptr(stat),
@@ -224,6 +234,7 @@ class LikelihoodEngine:
     def stat_sum_device(self, values, out):
         """Asynchronous variant: per-(vector, dataset) stats into the CUDA tensor ``out`` [B, D] float64."""
         v2 = np.ascontiguousarray(values, dtype=float).reshape(-1, self.n_par)
+        self._claim()
         _lib.check(self.ctx.lib.gpy_stat_sum_device(self.ctx.handle, self._handles, len(self.datasets), _ptr(v2),
                                                     v2.shape[0], self.n_par, C.c_void_p(out.data_ptr())))
 
@@ -235,6 +246,7 @@ class LikelihoodEngine:
             values = self.values()
         values = np.ascontiguousarray(values, dtype=float)
         ds = self.datasets[index]
+        self._claim()
         out = torch.empty(ds.data_shape, dtype=torch.float64, device=self.ctx.torch_device)
         en = None
         if source_enable is not None:
@@ -246,5 +258,6 @@ class LikelihoodEngine:
 
     def source_state(self, index, source):
         st = _lib.SourceState()
+        self._claim()
         _lib.check(self.ctx.lib.gpy_dataset_source_state(self.datasets[index]._device.handle, source, C.byref(st)))
         return {f: getattr(st, f) for f, _ in st._fields_}

@@ -24,7 +24,7 @@ class _Likelihood:
 
         if isinstance(datasets, MapDataset):
             datasets = Datasets([datasets])
-        elif not isinstance(datasets, Datasets):
+        elif not isinstance(datasets, Datasets) and not hasattr(datasets, "_get_engine"):
             datasets = Datasets(list(datasets))
         self.datasets = datasets
         self.engine = datasets._get_engine()

@@ -1,0 +1,133 @@
+"""Fit-level parity: the same optimiser (gammapy_b200.modeling.Fit, batched BFGS + Hesse in factor space) drives
+the GPU likelihood and the oracle; fitted parameters must agree within 0.01 sigma (BASELINE.json north_star).
+The reference's own fit numbers (test_map_fit) need $GAMMAPY_DATA + iminuit: parity unpinned, see DESIGN.md."""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+pytestmark = pytest.mark.gpu
+
+
+class OracleEngine:
+    """The LikelihoodEngine interface (values / parameters / stat_sum) served by the CPU oracle."""
+
+    def __init__(self, ds, de, parameters):
+        self.ds, self.de, self.parameters = ds, de, parameters
+        self.n_evals = 0
+
+    def values(self):
+        return np.array([p.value for p in self.parameters], dtype=float)
+
+    def stat_sum(self, values=None):
+        from oracle import adapter
+
+        if values is None:
+            values = self.values()
+        values = np.asarray(values, dtype=float)
+        single = values.ndim == 1
+        saved = self.values()
+        out = []
+        for vec in np.atleast_2d(values):
+            for p, v in zip(self.parameters, vec):
+                p._value = float(v)
+            adapter.refresh_models(self.de, self.ds)
+            out.append(self.de.stat_sum())
+            self.n_evals += 1
+        for p, v in zip(self.parameters, saved):
+            p._value = float(v)
+        adapter.refresh_models(self.de, self.ds)
+        return out[0] if single else np.array(out)
+
+
+class OracleDatasets:
+    def __init__(self, ds, de):
+        self.ds = ds
+        self._engine = OracleEngine(ds, de, list(ds.models.parameters.unique_parameters))
+
+    def _get_engine(self):
+        return self._engine
+
+    @property
+    def parameters(self):
+        return self.ds.models.parameters.unique_parameters
+
+
+def _perturb(ds):
+    m = ds.models["model-simu"]
+    m.spatial_model.lon_0.value = 0.23
+    m.spatial_model.lat_0.value = 0.08
+    m.spatial_model.sigma.value = 0.27
+    m.spectral_model.index.value = 2.8
+    m.spectral_model.amplitude.value = 1.3e-11
+    ds.background_model.spectral_model.norm.value = 1.05
+
+
+def _free_values(ds):
+    return {f"{p.name}": (p.value, p.error) for p in ds.models.parameters.unique_parameters if not p.frozen}
+
+
+@pytest.mark.parametrize("conv,stat_tol", [("exact64", 1e-3), ("fft32", 1e-2)])
+def test_fit_gpu_vs_oracle_same_optimiser(ctx, conv, stat_tol):
+    """``exact64``: the strict criteria.  ``fft32`` (the reference's float32 FFT): every re-convolution carries
+    ~1e-7 x peak of FFT rounding noise, i.e. a few 1e-3 on a stat of -7.9e6, so the stat bound is 1e-2 there;
+    the fitted parameters still agree within 0.01 sigma."""
+    from gammapy_b200 import Datasets, Fit, Map, configs
+    from oracle import adapter
+
+    ds = configs.make_c1(width=(2.0, 2.0), mask_radius=0.9)
+    de = adapter.evaluator_for(ds, conv=conv)
+    counts = adapter.evaluator_for(ds, conv="fft32").fake(0)
+    de.ds.counts = counts
+    ds.counts = Map.from_geom(ds._geom, data=counts, dtype=float)
+    truth = {k: v[0] for k, v in _free_values(ds).items()}
+
+    _perturb(ds)
+    fit = Fit(optimize_opts={"tol": 1e-3})
+    res_gpu = fit.run(Datasets([ds]))
+    assert res_gpu.success, res_gpu.optimize_result.message
+    gpu = _free_values(ds)
+    stat_gpu = res_gpu.total_stat
+
+    _perturb(ds)
+    res_cpu = Fit(optimize_opts={"tol": 1e-3}).run(OracleDatasets(ds, de))
+    assert res_cpu.success, res_cpu.optimize_result.message
+    cpu = _free_values(ds)
+
+    print(conv, stat_gpu, res_cpu.total_stat, gpu, cpu)
+    assert abs(stat_gpu - res_cpu.total_stat) < stat_tol
+    for name in gpu:
+        val_g, err_g = gpu[name]
+        val_c, err_c = cpu[name]
+        assert err_g > 0
+        assert abs(val_g - val_c) < 0.01 * err_g, (name, val_g, val_c, err_g)
+        assert_allclose(err_g, err_c, rtol=2e-2)
+        # and the fit recovers the simulated truth within errors
+        assert abs(val_g - truth[name]) < 5 * err_g, (name, val_g, truth[name], err_g)
+
+
+def test_stat_profile_and_surface_batched(ctx):
+    from gammapy_b200 import Datasets, Fit, Map, configs
+    from oracle import adapter
+
+    ds = configs.make_c1(width=(2.0, 2.0), mask_radius=0.9)
+    de = adapter.evaluator_for(ds, conv="exact64")
+    ds.counts = Map.from_geom(ds._geom, data=de.fake(0), dtype=float)
+    datasets = Datasets([ds])
+    index = ds.models["model-simu"].spectral_model.index
+    index.scan_values = np.linspace(2.5, 3.5, 9)
+    prof = Fit().stat_profile(datasets, index)
+    assert prof["stat_scan"].shape == (9,)
+    for k in (0, 4, 8):
+        index.value = index.scan_values[k]
+        assert abs(datasets.stat_sum() - prof["stat_scan"][k]) < 1e-6
+        adapter.refresh_models(de, ds)
+        assert abs(de.stat_sum() - prof["stat_scan"][k]) < 1e-3
+    index.value = 3.0
+    assert np.argmin(prof["stat_scan"]) in (3, 4, 5)
+    sigma = ds.models["model-simu"].spatial_model.sigma
+    sigma.scan_values = np.array([0.25, 0.3, 0.35])
+    index.scan_values = np.array([2.8, 3.0, 3.2])
+    surf = Fit().stat_surface(datasets, sigma, index)
+    assert surf["stat_scan"].shape == (3, 3)
+    sigma.value, index.value = 0.35, 2.8
+    assert abs(datasets.stat_sum() - surf["stat_scan"][2, 0]) < 1e-6

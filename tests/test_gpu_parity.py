@@ -394,3 +394,47 @@ def test_errors_are_loud(ctx):
     with pytest.raises(ValueError):
         ds.stat_sum_likelihood()
     assert MapAxis.from_energy_bounds(1, 10, 3).nbin == 3
+
+
+def test_batch_with_many_spatial_tuples(ctx):
+    """A finite-difference gradient batch holds more distinct spatial parameter tuples than the per-source
+    cache keeps between calls: every vector must still see its own PSF-convolved cube."""
+    from gammapy_b200 import Datasets, Map, configs
+    from oracle import adapter
+
+    ds = configs.make_c1(width=(2.0, 2.0), mask_radius=0.9)
+    de = adapter.evaluator_for(ds, conv="exact64")
+    ds.counts = Map.from_geom(ds._geom, data=de.fake(3), dtype=float)
+    datasets = Datasets([ds])
+    values, plist = datasets.parameter_vector()
+    m = ds.models["model-simu"].spatial_model
+    cols = {p.name: i for i, p in enumerate(plist)}
+    grid = np.tile(values, (13, 1))
+    grid[1:5, cols["lon_0"]] += [0.01, -0.01, 0.02, -0.02]
+    grid[5:9, cols["lat_0"]] += [0.01, -0.01, 0.02, -0.02]
+    grid[9:13, cols["sigma"]] += [0.01, -0.01, 0.02, -0.02]
+    batch = datasets.stat_sum_batch(grid)
+    again = datasets.stat_sum_batch(grid)
+    assert_allclose(batch, again, rtol=0, atol=1e-9)  # deterministic, cache hit or not
+    for k in range(13):
+        m.lon_0.value, m.lat_0.value, m.sigma.value = grid[k, cols["lon_0"]], grid[k, cols["lat_0"]], grid[k, cols["sigma"]]
+        adapter.refresh_models(de, ds)
+        assert abs(batch[k] - de.stat_sum()) < 1e-3, k
+        assert abs(batch[k] - datasets.stat_sum()) < 1e-6, k
+
+
+def test_two_engines_share_one_dataset(ctx):
+    """MapDataset-level calls (npred) and Datasets-level calls (stat_sum) alternate on one device handle."""
+    from gammapy_b200 import Datasets, Map, configs
+    from oracle import adapter
+
+    a = configs.make_c1(name="a", width=(1.6, 1.6), mask_radius=0.7)
+    b = configs.make_c2(name="b", width=(2.0, 2.0), mask_radius=0.9)
+    for ds, seed in ((a, 1), (b, 2)):
+        ds.counts = Map.from_geom(ds._geom, data=adapter.evaluator_for(ds, conv="exact64").fake(seed), dtype=float)
+    joint = Datasets([a, b])
+    want = a.stat_sum_likelihood() + b.stat_sum_likelihood()
+    assert abs(joint.stat_sum() - want) < 1e-6
+    npred_b = b.npred().data  # re-installs b's own parameter columns on the shared handle
+    assert abs(joint.stat_sum() - want) < 1e-6
+    assert_allclose(b.npred().data, npred_b)
