@@ -190,18 +190,28 @@ double disk_norm_factor(double r0, double e) {
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
-  int reserve(size_t bytes) {
+  cudaStream_t pool_stream = nullptr;  // non-null: stream-ordered allocation (cudaMallocAsync pool, no device sync)
+  int reserve(size_t bytes, cudaStream_t stream = nullptr) {
     if (bytes <= cap) return GPY_OK;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
+    release();
     size_t want = std::max(bytes, (size_t)256);
-    CUDA_TRY(cudaMalloc(&p, want));
+    if (stream) {
+      CUDA_TRY(cudaMallocAsync(&p, want, stream));
+      pool_stream = stream;
+    } else {
+      CUDA_TRY(cudaMalloc(&p, want));
+      pool_stream = nullptr;
+    }
     cap = want;
     return GPY_OK;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (pool_stream)
+        cudaFreeAsync(p, pool_stream);
+      else
+        cudaFree(p);
+    }
     p = nullptr;
     cap = 0;
   }
@@ -516,11 +526,11 @@ int get_slot(gpy_dataset* ds, Source& src, const double* sp, const Rect& rect, u
   const bool conv = ds->has_psf && src.desc.apply_psf;
   s.planes = conv ? ds->nT : 1;
   const size_t img = (size_t)rect.cy * s.pitch;
-  GPY_TRY(s.w.reserve(img * sizeof(float)));
+  GPY_TRY(s.w.reserve(img * sizeof(float), c->stream));
   GPY_TRY(compute_spatial(c, ds->geom, (const double*)ds->d_omega.p, rect, src.desc.spatial_type, sp,
                           (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f));
   if (conv) {
-    GPY_TRY(s.conv.reserve(img * ds->nT * sizeof(float)));
+    GPY_TRY(s.conv.reserve(img * ds->nT * sizeof(float), c->stream));
     GPY_TRY(launch_conv(c, (const float*)s.w.p, rect.cy, rect.cx, s.pitch, rect.x0 - s.x0a,
                         (const float*)ds->d_kflip.p, (const gpy::ConvPlane*)ds->d_planes.p, ds->nT, ds->max_h,
                         ds->max_kw, (float*)s.conv.p));
@@ -858,6 +868,13 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
   c->force_generic = std::getenv("GPY_FORCE_GENERIC_FOLD") != nullptr;
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;  // slot buffers come and go with the batch size: keep them in the pool
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   c->log_trunc = std::log((double)(float)1e-25);  // Cython: log(<float>TRUNCATION_VALUE), .pyx:35
   *out = c;
   return GPY_OK;

@@ -840,7 +840,13 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.0;
 
-      for (int t0 = 0; t0 < nT; t0 += kFoldTCH) {
+      if (nl == 0) {
+        // no source reaches this tile: npred = background only.  Keep the exposure pipeline in step.
+        if (cbase == 0) mbar_wait(&bars[0], parity);
+        __syncthreads();
+        if (tid < 32 && cbase + 4 >= nchunks && next < n_items) issue_expo(next);
+      }
+      for (int t0 = 0; t0 < (nl > 0 ? nT : 0); t0 += kFoldTCH) {
         if (cbase == 0 && t0 == 0) mbar_wait(&bars[0], parity);  // exposure tile has landed
         // ---- phase 1: v[g][t][p] = 1e4 * exposure[t,p] * sum_s F_s[t] * conv_s[t,p] ----
         for (int g = 0; g < G; ++g) {
