@@ -261,6 +261,7 @@ struct gpy_context {
   int tma_blocks_per_sm[2] = {0, 0};
   int num_sms = 0;
   bool force_generic = false;
+  int fold_mode = 0;  // GPY_FOLD_KERNEL: 0 auto (bulk-copy staged kernel when eligible), 2 generic
   double log_trunc = 0.0;
   int max_smem_optin = 0;
 };
@@ -758,7 +759,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   }
 
   GPY_TRY(c->flux.reserve(std::max(flux_len, (size_t)1) * sizeof(double)));
-  GPY_TRY(c->partials.reserve((size_t)B * n_tiles * sizeof(double)));
+  GPY_TRY(c->partials.reserve((size_t)B * n_tiles * (gpy::kFoldThreads / 32) * sizeof(double)));
   GPY_TRY(c->stat.reserve((size_t)B * D * sizeof(double)));
   for (size_t i = 0; i < jobs.size(); ++i) jobs[i].out = (double*)c->flux.p + job_flux_off[i];
 
@@ -799,21 +800,22 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   fp.smem_nRp = max_nRp;
   fp.smem_G = max_G;
   const size_t n_items = (size_t)B * n_tiles;
+  int per_tile = 1;
+  const int variant = rq.npred_out ? 1 : 0;
   if (tma_ok) {
-    const int variant = rq.npred_out ? 1 : 0;
     auto kern = variant ? gpy::fold_cash_tma_kernel<true> : gpy::fold_cash_tma_kernel<false>;
     if (lay.total > c->tma_smem_set[variant]) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
       c->tma_smem_set[variant] = lay.total;
-      c->tma_blocks_per_sm[variant] = 0;
     }
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, gpy::kFoldThreads, lay.total));
     per_sm = std::max(per_sm, 1);
     const unsigned grid = (unsigned)std::min(n_items, (size_t)per_sm * c->num_sms);
     kern<<<grid, gpy::kFoldThreads, lay.total, c->stream>>>(fp);
+    per_tile = gpy::kFoldThreads / 32;
   } else {
     if (max_fold_smem > c->fold_smem_set) {
       CUDA_TRY(cudaFuncSetAttribute(gpy::fold_cash_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -826,7 +828,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   }
   c->launches++;
   gpy::reduce_stat_kernel<<<dim3(B, D), 256, 0, c->stream>>>((const double*)c->partials.p, fp.ds, n_tiles, D,
-                                                              (double*)c->stat.p);
+                                                              per_tile, (double*)c->stat.p);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return GPY_OK;
@@ -868,6 +870,8 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
   c->force_generic = std::getenv("GPY_FORCE_GENERIC_FOLD") != nullptr;
+  if (const char* m = std::getenv("GPY_FOLD_KERNEL")) c->fold_mode = std::atoi(m);
+  if (c->fold_mode == 2) c->force_generic = true;
   {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {

@@ -13,6 +13,7 @@
 // Reference citations are relative to /root/reference/gammapy.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdio>
 #include <math.h>
 #include <stdint.h>
 
@@ -684,6 +685,31 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+
 struct FoldSmem {  // byte offsets of the fixed shared-memory layout
   size_t es, bs, cs, ms, vs, pdf, bkgfac, scratch, slist, bars, total;
 };
@@ -717,13 +743,14 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   double* vs = reinterpret_cast<double*>(fold_raw + L.vs);
   double* pdf_s = reinterpret_cast<double*>(fold_raw + L.pdf);
   double* bkgfac = reinterpret_cast<double*>(fold_raw + L.bkgfac);
-  double* scratch = reinterpret_cast<double*>(fold_raw + L.scratch);
   InstDev* slist = reinterpret_cast<InstDev*>(fold_raw + L.slist);
   uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + L.bars);  // [0] exposure, [1] epilogue inputs
   __shared__ int n_list;
 
   const int tid = threadIdx.x;
   const int n_items = P.B * P.n_tiles;
+  // L2 policy: the per-source PSF-convolved cubes are re-read by every evaluation (keep), the dataset cubes stream
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -731,19 +758,28 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   }
   __syncthreads();
 
-  // producers (warp 0): bulk copies of one item's tiles
+  // producers: thread 0 arms the mbarrier with the byte count BEFORE a CTA barrier, then every warp issues its
+  // share of the 1-D bulk copies (one 512-byte row segment per lane), so the ~70-cycle issue cost of a copy is
+  // spread over the 8 warps instead of sitting on warp 0's critical path.
+  auto arm_expo = [&](int item) {
+    const int tile = item / P.B;
+    const DatasetDev& D = P.ds[P.tile_ds[tile]];
+    const int p0 = (tile - D.tile_begin) * kFoldTPX;
+    const int npx = min(kFoldTPX, (int)D.P - p0);
+    mbar_arrive_expect_tx(&bars[0], (uint32_t)npx * 4u * (uint32_t)D.nT);
+  };
   auto issue_expo = [&](int item) {
     const int tile = item / P.B;
     const DatasetDev& D = P.ds[P.tile_ds[tile]];
     const int p0 = (tile - D.tile_begin) * kFoldTPX;
     const int npx = min(kFoldTPX, (int)D.P - p0);
     const uint32_t row = (uint32_t)npx * 4u;
-    if (tid == 0) mbar_arrive_expect_tx(&bars[0], row * (uint32_t)D.nT);
-    __syncwarp();
-    for (int t = tid; t < D.nT; t += 32)
-      bulk_g2s(es + t * kFoldTPX, D.exposure + (size_t)t * D.P + p0, row, &bars[0]);
+    const int t = (tid & 31) * (kFoldThreads / 32) + (tid >> 5);  // row handled by this lane
+    if (t < D.nT) bulk_g2s_hint(es + t * kFoldTPX, D.exposure + (size_t)t * D.P + p0, row, &bars[0], pol_stream);
+    for (int t2 = t + kFoldThreads; t2 < D.nT; t2 += kFoldThreads)
+      bulk_g2s_hint(es + t2 * kFoldTPX, D.exposure + (size_t)t2 * D.P + p0, row, &bars[0], pol_stream);
   };
-  auto issue_epi = [&](int item) {
+  auto arm_epi = [&](int item) {
     const int tile = item / P.B;
     const DatasetDev& D = P.ds[P.tile_ds[tile]];
     const int p0 = (tile - D.tile_begin) * kFoldTPX;
@@ -753,23 +789,44 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     if (D.background && P.include_background) total += row * (uint32_t)D.nR;
     if (D.counts) total += row * (uint32_t)D.nR;
     if (D.counts && D.mask) total += (uint32_t)npx * (uint32_t)D.nR;
-    if (tid == 0) mbar_arrive_expect_tx(&bars[1], total);
-    __syncwarp();
-    for (int r = tid; r < D.nR; r += 32) {
+    mbar_arrive_expect_tx(&bars[1], total);
+  };
+  auto issue_epi = [&](int item) {
+    const int tile = item / P.B;
+    const DatasetDev& D = P.ds[P.tile_ds[tile]];
+    const int p0 = (tile - D.tile_begin) * kFoldTPX;
+    const int npx = min(kFoldTPX, (int)D.P - p0);
+    const uint32_t row = (uint32_t)npx * 4u;
+    const bool has_bkg = D.background && P.include_background;
+    // copy index i = 3 r + which, spread over (lane, warp) like the exposure rows
+    for (int i = (tid & 31) * (kFoldThreads / 32) + (tid >> 5); i < 3 * D.nR; i += kFoldThreads) {
+      const int r = i / 3, which = i - 3 * r;
       const size_t off = (size_t)r * D.P + p0;
-      if (D.background && P.include_background) bulk_g2s(bs + r * kFoldTPX, D.background + off, row, &bars[1]);
-      if (D.counts) bulk_g2s(cs + r * kFoldTPX, D.counts + off, row, &bars[1]);
-      if (D.counts && D.mask) bulk_g2s(ms + r * kFoldTPX, D.mask + off, (uint32_t)npx, &bars[1]);
+      if (which == 0 && has_bkg) bulk_g2s_hint(bs + r * kFoldTPX, D.background + off, row, &bars[1], pol_stream);
+      if (which == 1 && D.counts) bulk_g2s_hint(cs + r * kFoldTPX, D.counts + off, row, &bars[1], pol_stream);
+      if (which == 2 && D.counts && D.mask) bulk_g2s_hint(ms + r * kFoldTPX, D.mask + off, (uint32_t)npx, &bars[1], pol_stream);
     }
   };
 
   int item = blockIdx.x;
-  if (item < n_items && tid < 32) {
+  if (item < n_items) {
+    if (tid == 0) {
+      arm_expo(item);
+      arm_epi(item);
+    }
+    __syncthreads();
     issue_expo(item);
     issue_epi(item);
   }
   uint32_t parity = 0;
   int cur_ds = -1;
+#ifdef GPY_FOLD_TIMING
+  long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+#define GPY_TICK(i) do { if (tid == 0) { long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } } while (0)
+#else
+#define GPY_TICK(i) do { } while (0)
+#endif
 
   const int q = tid & 31, slot = tid >> 5;   // phase 1: 32 pixel quads x 8 energy slots
   const int pp = tid & 63, cslot = tid >> 6;  // phase 2: 64 pixel pairs x 4 reco-chunk slots
@@ -814,7 +871,9 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
       }
       if (tid == 0) n_list = n;
     }
+    GPY_TICK(0);
     __syncthreads();
+    GPY_TICK(1);
     const int nl = n_list;
 
     // this thread's pixel quad and its offset inside every overlapping cutout (-1: outside)
@@ -828,7 +887,9 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
       if (l < nl && qlive) {
         const InstDev& in = slist[l];
         const int ly = qy - in.y0, lx = qx - in.x0a;
+#ifndef GPY_EXP_NO_CONV
         if (ly >= 0 && ly < in.cy && lx >= 0 && lx < in.pitch) off[l] = ly * in.pitch + lx;
+#endif
       }
     }
 
@@ -843,11 +904,14 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
       if (nl == 0) {
         // no source reaches this tile: npred = background only.  Keep the exposure pipeline in step.
         if (cbase == 0) mbar_wait(&bars[0], parity);
+        if (tid == 0 && cbase + 4 >= nchunks && next < n_items) arm_expo(next);
         __syncthreads();
-        if (tid < 32 && cbase + 4 >= nchunks && next < n_items) issue_expo(next);
+        if (cbase + 4 >= nchunks && next < n_items) issue_expo(next);
       }
       for (int t0 = 0; t0 < (nl > 0 ? nT : 0); t0 += kFoldTCH) {
+        GPY_TICK(2);
         if (cbase == 0 && t0 == 0) mbar_wait(&bars[0], parity);  // exposure tile has landed
+        GPY_TICK(3);
         // ---- phase 1: v[g][t][p] = 1e4 * exposure[t,p] * sum_s F_s[t] * conv_s[t,p] ----
         for (int g = 0; g < G; ++g) {
 #pragma unroll
@@ -860,7 +924,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
                 if (off[l] < 0) continue;
                 const InstDev& in = slist[l];
                 if (in.group != g) continue;
-                const float4 cv = __ldg(reinterpret_cast<const float4*>(in.conv + (size_t)t * in.plane_stride + off[l]));
+                const float4 cv = ldg_f4_hint(in.conv + (size_t)t * in.plane_stride + off[l], pol_keep);
                 const double F = P.flux[in.flux_off + t];
                 const double a0 = F * (double)cv.x, a1 = F * (double)cv.y, a2 = F * (double)cv.z, a3 = F * (double)cv.w;
                 // WcsNDMap.stack(nan_to_num=True): non-finite source values do not enter the sum
@@ -894,9 +958,14 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
             *reinterpret_cast<double2*>(dst + 2) = make_double2(s2, s3);
           }
         }
+        GPY_TICK(4);
+        const bool fetch_next = cbase + 4 >= nchunks && t0 + kFoldTCH >= nT && next < n_items;
+        if (tid == 0 && fetch_next) arm_expo(next);
         __syncthreads();
+        GPY_TICK(5);
         // exposure tile fully consumed: start fetching the next item's while phase 2 / the epilogue run
-        if (tid < 32 && cbase + 4 >= nchunks && t0 + kFoldTCH >= nT && next < n_items) issue_expo(next);
+        if (fetch_next) issue_expo(next);
+        GPY_TICK(6);
         // ---- phase 2: acc[r] += pdf[t][r] * v[t][p] over the non-zero band ----
         if (c < nchunks) {
           for (int g = 0; g < G; ++g) {
@@ -919,11 +988,15 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
             }
           }
         }
+        GPY_TICK(7);
         __syncthreads();
+        GPY_TICK(5);
       }
 
       // ---- epilogue for reco chunk c: background, clip, Cash (inputs staged in shared memory) ----
+      GPY_TICK(2);
       if (cbase == 0) mbar_wait(&bars[1], parity);
+      GPY_TICK(8);
       if (c < nchunks && 2 * pp < npx) {
         const bool has_bkg = D.background && P.include_background;
 #pragma unroll
@@ -957,7 +1030,11 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
                 double npr, lognpr = 0.0;
                 if (mu > kTrunc) {
                   npr = mu;
+#ifdef GPY_EXP_NO_LOG
+                  if (n > 0.0) lognpr = mu;
+#else
                   if (n > 0.0) lognpr = log(mu);
+#endif
                 } else {
                   npr = kTrunc;
                   lognpr = P.log_trunc;
@@ -970,20 +1047,31 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         }
       }
     }
-    const double total = block_sum_256(stat, scratch);  // contains a block barrier after every epilogue read
-    if (tid == 0) P.partials[(size_t)b * P.n_tiles + tile] = total;
-    if (tid < 32 && next < n_items) issue_epi(next);
-    __syncthreads();  // scratch / list reuse in the next item
+    GPY_TICK(9);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) stat += __shfl_xor_sync(0xffffffffu, stat, o);
+    if ((tid & 31) == 0) P.partials[((size_t)b * P.n_tiles + tile) * (kFoldThreads / 32) + (tid >> 5)] = stat;
+    if (tid == 0 && next < n_items) arm_epi(next);
+    __syncthreads();  // every warp is past its epilogue reads; list / bkgfac reuse in the next item
+    GPY_TICK(10);
+    if (next < n_items) issue_epi(next);
+    GPY_TICK(11);
   }
+#ifdef GPY_FOLD_TIMING
+  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 100))
+    printf("[fold timing] block %d: list %lld | sync-after-list %lld | misc %lld | expo wait %lld | phase1 %lld | phase syncs %lld | issue expo %lld | phase2 %lld | epi wait %lld | epilogue %lld | end barrier %lld | issue epi %lld\n",
+           blockIdx.x, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7], tacc[8], tacc[9], tacc[10], tacc[11]);
+#endif
 }
 
 // Second stage: stat[b, d] = 2 * sum of the tile partials of dataset d, fixed summation order.
 __global__ void __launch_bounds__(256)
 reduce_stat_kernel(const double* __restrict__ partials, const DatasetDev* __restrict__ ds, int n_tiles,
-                   int n_datasets, double* __restrict__ stat) {
+                   int n_datasets, int per_tile, double* __restrict__ stat) {
   __shared__ double sm[256];
   const int b = blockIdx.x, d = blockIdx.y;
-  const int begin = ds[d].tile_begin, n = ds[d].n_tiles;
+  const int begin = ds[d].tile_begin * per_tile, n = ds[d].n_tiles * per_tile;
+  n_tiles *= per_tile;
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) s += partials[(size_t)b * n_tiles + begin + i];
   sm[threadIdx.x] = s;
