@@ -252,7 +252,7 @@ struct gpy_context {
   size_t pinned_cap = 0;
   cudaEvent_t h2d_done = nullptr;
   bool h2d_pending = false;
-  DevBuf staging, flux, partials, stat, tiles, scratch_a, scratch_b, scratch_c;
+  DevBuf zeros, staging, flux, partials, stat, tiles, scratch_a, scratch_b, scratch_c;
   std::vector<gpy_dataset*> tiles_for;  // dataset list the tile table was built for
   std::vector<uint64_t> tiles_ver;
   double* stat_pinned = nullptr;
@@ -274,7 +274,8 @@ struct gpy_dataset {
   const float *exposure = nullptr, *background = nullptr, *counts = nullptr;
   const uint8_t* mask = nullptr;
   std::vector<uint8_t> mask_image;  // empty = all true
-  DevBuf d_edges, d_nodes, d_ecenter, d_edisp, d_band, d_omega, d_kflip, d_planes;
+  DevBuf d_edges, d_nodes, d_ecenter, d_edisp, d_band, d_pdfc, d_omega, d_kflip, d_planes;
+  int pdfc_rows[2] = {0, 0};  // band-compressed rows when 1 / 2 edisp groups are in use
   std::vector<gpy::ConvPlane> planes;
   int max_h = 0, max_kw = 4;
   bool has_psf = false, has_diag = false;
@@ -577,7 +578,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   std::vector<size_t> job_flux_off;
   size_t flux_len = 0;
   int n_tiles = 0, max_inst = 1;
-  int max_nT = 0, max_nR = 0, max_nRp = 0, max_G = 0;
+  int max_nT = 0, max_nR = 0, max_nRp = 0, max_G = 0, max_pdfc_rows = 1;
   bool tma_ok = true;
   const bool sequential = (B == 1);
   const uint64_t call_id = ++c->stamp;
@@ -612,6 +613,9 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     dd.mask = ds->mask;
     dd.edisp = (const double*)ds->d_edisp.p;
     dd.band = (const int*)ds->d_band.p;
+    dd.pdfc = (const double*)ds->d_pdfc.p;
+    dd.pdfc_rows = ds->pdfc_rows[ds->groups_used - 1];
+    max_pdfc_rows = std::max(max_pdfc_rows, dd.pdfc_rows);
     dd.ecenter = (const double*)ds->d_ecenter.p;
     if (!rq.npred_out && !ds->counts) return fail(GPY_ERR_INVALID, "dataset %d has no counts: stat undefined", d);
 
@@ -711,6 +715,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         job.type = src.desc.spectral_type;
         job.n_bins = ds->nT;
         job.n_nodes = ds->n_nodes;
+        job.sanitize = 1;
         for (int k = 0; k < 5; ++k) job.p[k] = sc[k];
         job.edges = (const double*)ds->d_edges.p;
         job.nodes = (const double*)ds->d_nodes.p;
@@ -731,7 +736,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         !al16(ds->mask) || P64 * (size_t)std::max(ds->nT, ds->nR) > (size_t)INT32_MAX)
       tma_ok = false;
   }
-  const gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G, max_inst);
+  const gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G, max_pdfc_rows, max_inst);
   if (lay.total > (size_t)c->max_smem_optin || c->force_generic) tma_ok = false;
   size_t max_fold_smem = 0;
   if (!tma_ok) {
@@ -799,6 +804,12 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   fp.smem_nR = max_nR;
   fp.smem_nRp = max_nRp;
   fp.smem_G = max_G;
+  fp.smem_pdfc_rows = max_pdfc_rows;
+  if (!c->zeros.p) {
+    GPY_TRY(c->zeros.reserve(256));
+    CUDA_TRY(cudaMemsetAsync(c->zeros.p, 0, 256, c->stream));
+  }
+  fp.zeros = (const float*)c->zeros.p;
   const size_t n_items = (size_t)B * n_tiles;
   int per_tile = 1;
   const int variant = rq.npred_out ? 1 : 0;
@@ -888,7 +899,7 @@ int gpy_finalize(gpy_context_t* c) {
   if (!c) return GPY_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->staging, &c->flux, &c->partials, &c->stat, &c->tiles, &c->scratch_a, &c->scratch_b, &c->scratch_c})
+  for (DevBuf* b : {&c->zeros, &c->staging, &c->flux, &c->partials, &c->stat, &c->tiles, &c->scratch_a, &c->scratch_b, &c->scratch_c})
     b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->stat_pinned) cudaFreeHost(c->stat_pinned);
@@ -943,7 +954,8 @@ int gpy_dataset_create(gpy_context_t* c, const gpy_dataset_desc* desc, gpy_datas
   // edisp groups, reco axis zero padded to a multiple of 8, and the non-zero band per reco chunk
   const int nchunks = ds->nRp / 8;
   std::vector<double> ed((size_t)ds->n_groups * ds->nT * ds->nRp, 0.0);
-  std::vector<int> band((size_t)ds->n_groups * nchunks * 2, 0);
+  std::vector<int> band((size_t)ds->n_groups * nchunks * 4, 0);
+  std::vector<double> pdfc;
   for (int gi = 0; gi < ds->n_groups; ++gi) {
     const double* src = gi == 0 ? desc->edisp : desc->edisp_diagonal;
     for (int t = 0; t < ds->nT; ++t)
@@ -959,10 +971,20 @@ int gpy_dataset_create(gpy_context_t* c, const gpy_dataset_desc* desc, gpy_datas
           }
         }
       if (lo > hi) lo = hi = 0;
-      band[((size_t)gi * nchunks + ch) * 2] = lo;
-      band[((size_t)gi * nchunks + ch) * 2 + 1] = hi;
+      int* b4 = &band[((size_t)gi * nchunks + ch) * 4];
+      b4[0] = lo;
+      b4[1] = hi;
+      b4[2] = (int)(pdfc.size() / 8);  // first row of this chunk in the band-compressed matrix
+      for (int t = lo; t < hi; ++t)
+        for (int j = 0; j < 8; ++j) {
+          const int r = 8 * ch + j;
+          pdfc.push_back(r < ds->nR ? src[(size_t)t * ds->nR + r] : 0.0);
+        }
     }
+    ds->pdfc_rows[gi] = (int)(pdfc.size() / 8);
   }
+  if (pdfc.empty()) pdfc.resize(8, 0.0);
+  if ((rc = upload_to(ds->d_pdfc, pdfc.data(), pdfc.size() * sizeof(double), s))) return cleanup(rc);
   if ((rc = upload_to(ds->d_edisp, ed.data(), ed.size() * sizeof(double), s))) return cleanup(rc);
   if ((rc = upload_to(ds->d_band, band.data(), band.size() * sizeof(int), s))) return cleanup(rc);
   std::vector<float> kflip;
@@ -988,7 +1010,7 @@ int gpy_dataset_destroy(gpy_dataset_t* ds) {
   if (!ds) return GPY_OK;
   cudaSetDevice(ds->ctx->device);
   cudaStreamSynchronize(ds->ctx->stream);
-  for (DevBuf* b : {&ds->d_edges, &ds->d_nodes, &ds->d_ecenter, &ds->d_edisp, &ds->d_band, &ds->d_omega, &ds->d_kflip,
+  for (DevBuf* b : {&ds->d_edges, &ds->d_nodes, &ds->d_ecenter, &ds->d_edisp, &ds->d_band, &ds->d_pdfc, &ds->d_omega, &ds->d_kflip,
                     &ds->d_planes})
     b->release();
   for (auto& src : ds->sources)

@@ -298,7 +298,7 @@ struct FluxJob {
   int type;      // gpy_spectral_type
   int n_bins;
   int n_nodes;
-  int pad_;
+  int sanitize;         // 1: zero the vector when any bin is non-finite (likelihood path), 0: raw integrals
   double p[5];          // parameter values in the reference class order
   const double* edges;  // [n_bins + 1]
   const double* nodes;  // [n_bins, n_nodes]
@@ -340,6 +340,9 @@ __device__ __forceinline__ double log_scale(double v) {
 
 __global__ void spectral_flux_kernel(const FluxJob* __restrict__ jobs) {
   const FluxJob job = jobs[blockIdx.x];
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
   for (int t = threadIdx.x; t < job.n_bins; t += blockDim.x) {
     double emin = job.edges[t], emax = job.edges[t + 1];
     double result;
@@ -359,8 +362,15 @@ __global__ void spectral_flux_kernel(const FluxJob* __restrict__ jobs) {
         y0 = y1;
       }
     }
+    if (!isfinite(result)) bad = 1;
     job.out[t] = result;
   }
+  if (!job.sanitize) return;
+  // A non-finite flux in ANY true-energy bin makes the source's whole npred non-finite after the edisp
+  // matmul (0 * NaN = NaN), and WcsNDMap.stack(nan_to_num=True) then drops the source: zero flux here.
+  __syncthreads();
+  if (bad)
+    for (int t = threadIdx.x; t < job.n_bins; t += blockDim.x) job.out[t] = 0.0;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -379,7 +389,11 @@ struct DatasetDev {
   const float* counts;      // [nR, P] or null
   const uint8_t* mask;      // [nR, P] or null
   const double* edisp;      // [n_groups, nT, nRp] zero padded
-  const int* band;          // [n_groups, nRp / 8, 2] first / last+1 true bin with non-zero pdf per reco chunk
+  const int* band;          // [n_groups, nRp / 8, 4]: first / last+1 true bin with non-zero pdf per reco chunk, row offset
+                            // of the chunk in the band-compressed matrix, pad
+  const double* pdfc;       // band-compressed edisp: for every (group, chunk) the rows [lo, hi) x 8 reco bins, contiguous
+  int pdfc_rows;            // total rows (of 8 doubles) in pdfc
+  int pad2_;
   const double* ecenter;    // [nR]
 };
 
@@ -411,6 +425,8 @@ struct FoldParams {
   int include_background;   // add background model and clip at 0 (MapDataset.npred) or signal only
   int max_inst;             // capacity of the per-block overlap list
   int smem_nT, smem_nR, smem_nRp, smem_G;  // largest axes of the launch: fixed shared-memory layout (bulk-copy kernel)
+  int smem_pdfc_rows, pad3_;
+  const float* zeros;       // >= 16 bytes of zeros: load target of (thread, source) pairs outside the cutout
   int pad_;
   double log_trunc;         // log((double)(float)1e-25): Cython narrows the constant to C float
 };
@@ -581,7 +597,7 @@ __global__ void __launch_bounds__(kFoldThreads, GPY_FOLD_MINBLOCKS) fold_cash_ge
       // ---- phase 2 ----
       if (c < nchunks) {
         for (int g = 0; g < G; ++g) {
-          const int blo = D.band[(g * nchunks + c) * 2], bhi = D.band[(g * nchunks + c) * 2 + 1];
+          const int blo = D.band[(g * nchunks + c) * 4], bhi = D.band[(g * nchunks + c) * 4 + 1];
           const int tlo = max(blo, t0), thi = min(bhi, t0 + kFoldTCH);
           const double* vrow = vs + (size_t)g * kFoldTCH * kFoldTPX + 2 * pp;
           const double* prow = pdf_s + (size_t)g * nT * nRp + 8 * c;
@@ -697,7 +713,7 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
 }
 __device__ __forceinline__ float4 ldg_f4_hint(const float* p, uint64_t pol) {
   float4 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+  asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p), "l"(pol));
   return v;
@@ -710,20 +726,21 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
       : "memory");
 }
 
+constexpr int kTmaTCH = 32;  // true-energy bins per pass of the bulk-copy kernel (2 passes at nT = 60)
 struct FoldSmem {  // byte offsets of the fixed shared-memory layout
-  size_t es, bs, cs, ms, vs, pdf, bkgfac, scratch, slist, bars, total;
+  size_t es, bs, cs, ms, vs, pdf, flux, bkgfac, slist, bars, total;
 };
-__host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int G, int max_inst) {
+__host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int G, int pdfc_rows, int max_inst) {
   FoldSmem L;
   size_t o = 0;
   L.es = o;      o += (size_t)nT * kFoldTPX * 4;
   L.bs = o;      o += (size_t)nR * kFoldTPX * 4;
   L.cs = o;      o += (size_t)nR * kFoldTPX * 4;
   L.ms = o;      o += ((size_t)nR * kFoldTPX + 15) / 16 * 16;
-  L.vs = o;      o += (size_t)G * kFoldTCH * kFoldTPX * 8;
-  L.pdf = o;     o += (size_t)G * nT * nRp * 8;
+  L.vs = o;      o += (size_t)G * kTmaTCH * kFoldTPX * 8;
+  L.pdf = o;     o += (size_t)pdfc_rows * 64;
+  L.flux = o;    o += (size_t)4 * nT * 8;  // spectral fluxes of the kFoldLMax sources held in registers
   L.bkgfac = o;  o += (size_t)nRp * 8;
-  L.scratch = o; o += 8 * 8;
   L.slist = o;   o += (size_t)max_inst * sizeof(InstDev);
   L.bars = (o + 7) / 8 * 8;
   L.total = L.bars + 2 * 8;
@@ -735,13 +752,14 @@ constexpr int kFoldLMax = 4;  // overlapping sources whose per-thread offsets li
 template <bool WRITE_NPRED>
 __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const FoldParams P) {
   extern __shared__ __align__(128) unsigned char fold_raw[];
-  const FoldSmem L = fold_tma_layout(P.smem_nT, P.smem_nR, P.smem_nRp, P.smem_G, P.max_inst);
+  const FoldSmem L = fold_tma_layout(P.smem_nT, P.smem_nR, P.smem_nRp, P.smem_G, P.smem_pdfc_rows, P.max_inst);
   float* es = reinterpret_cast<float*>(fold_raw + L.es);
   float* bs = reinterpret_cast<float*>(fold_raw + L.bs);
   float* cs = reinterpret_cast<float*>(fold_raw + L.cs);
   unsigned char* ms = fold_raw + L.ms;
   double* vs = reinterpret_cast<double*>(fold_raw + L.vs);
   double* pdf_s = reinterpret_cast<double*>(fold_raw + L.pdf);
+  double* flux_s = reinterpret_cast<double*>(fold_raw + L.flux);  // [kFoldLMax][nT], zero rows beyond nl
   double* bkgfac = reinterpret_cast<double*>(fold_raw + L.bkgfac);
   InstDev* slist = reinterpret_cast<InstDev*>(fold_raw + L.slist);
   uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + L.bars);  // [0] exposure, [1] epilogue inputs
@@ -843,7 +861,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const int next = item + gridDim.x;
 
     if (d != cur_ds) {  // edisp matrices of this dataset (block-uniform branch)
-      for (int i = tid; i < G * nT * nRp; i += kFoldThreads) pdf_s[i] = D.edisp[i];
+      for (int i = tid; i < D.pdfc_rows * 8; i += kFoldThreads) pdf_s[i] = D.pdfc[i];
       cur_ds = d;
     }
     if (tid < nRp) {
@@ -876,22 +894,34 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     GPY_TICK(1);
     const int nl = n_list;
 
-    // this thread's pixel quad and its offset inside every overlapping cutout (-1: outside)
+    // spectral fluxes of the first kFoldLMax overlapping sources -> shared memory (zero rows beyond nl)
+    for (int i = tid; i < kFoldLMax * nT; i += kFoldThreads) {
+      const int l = i / nT, t = i - l * nT;
+      flux_s[i] = l < nl ? P.flux[slist[l].flux_off + t] : 0.0;
+    }
+    // this thread's pixel quad and, per overlapping source, a pointer into its cutout; outside the cutout the
+    // pointer targets a zero word with stride 0, so phase 1 is branch free and its loads can all be in flight
     const int pq = p0 + 4 * q;
     const bool qlive = 4 * q < npx;
     const int qy = pq / D.nx, qx = pq - qy * D.nx;
-    int off[kFoldLMax];
+    const float* cptr[kFoldLMax];
+    int pstr[kFoldLMax], grp[kFoldLMax];
 #pragma unroll
     for (int l = 0; l < kFoldLMax; ++l) {
-      off[l] = -1;
+      cptr[l] = P.zeros;
+      pstr[l] = 0;
+      grp[l] = 0;
       if (l < nl && qlive) {
         const InstDev& in = slist[l];
         const int ly = qy - in.y0, lx = qx - in.x0a;
-#ifndef GPY_EXP_NO_CONV
-        if (ly >= 0 && ly < in.cy && lx >= 0 && lx < in.pitch) off[l] = ly * in.pitch + lx;
-#endif
+        grp[l] = in.group;
+        if (ly >= 0 && ly < in.cy && lx >= 0 && lx < in.pitch) {
+          cptr[l] = in.conv + ly * in.pitch + lx;
+          pstr[l] = in.plane_stride;
+        }
       }
     }
+    __syncthreads();  // flux_s visible
 
     const int nchunks = nRp >> 3;
     double stat = 0.0;
@@ -908,30 +938,25 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         __syncthreads();
         if (cbase + 4 >= nchunks && next < n_items) issue_expo(next);
       }
-      for (int t0 = 0; t0 < (nl > 0 ? nT : 0); t0 += kFoldTCH) {
+      for (int t0 = 0; t0 < (nl > 0 ? nT : 0); t0 += kTmaTCH) {
         GPY_TICK(2);
         if (cbase == 0 && t0 == 0) mbar_wait(&bars[0], parity);  // exposure tile has landed
         GPY_TICK(3);
         // ---- phase 1: v[g][t][p] = 1e4 * exposure[t,p] * sum_s F_s[t] * conv_s[t,p] ----
         for (int g = 0; g < G; ++g) {
 #pragma unroll
-          for (int tt = 0; tt < kFoldTCH / 8; ++tt) {
+          for (int tt = 0; tt < kTmaTCH / 8; ++tt) {
             const int tl = slot + 8 * tt, t = t0 + tl;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             if (t < nT && qlive) {
 #pragma unroll
               for (int l = 0; l < kFoldLMax; ++l) {
-                if (off[l] < 0) continue;
-                const InstDev& in = slist[l];
-                if (in.group != g) continue;
-                const float4 cv = ldg_f4_hint(in.conv + (size_t)t * in.plane_stride + off[l], pol_keep);
-                const double F = P.flux[in.flux_off + t];
-                const double a0 = F * (double)cv.x, a1 = F * (double)cv.y, a2 = F * (double)cv.z, a3 = F * (double)cv.w;
-                // WcsNDMap.stack(nan_to_num=True): non-finite source values do not enter the sum
-                s0 += isfinite(a0) ? a0 : 0.0;
-                s1 += isfinite(a1) ? a1 : 0.0;
-                s2 += isfinite(a2) ? a2 : 0.0;
-                s3 += isfinite(a3) ? a3 : 0.0;
+                const float4 cv = ldg_f4_hint(cptr[l] + (size_t)t * pstr[l], pol_keep);
+                const double F = grp[l] == g ? flux_s[l * nT + t] : 0.0;
+                s0 = fma(F, (double)cv.x, s0);
+                s1 = fma(F, (double)cv.y, s1);
+                s2 = fma(F, (double)cv.z, s2);
+                s3 = fma(F, (double)cv.w, s3);
               }
               for (int l = kFoldLMax; l < nl; ++l) {  // rare: more than kFoldLMax sources on one tile
                 const InstDev& in = slist[l];
@@ -941,11 +966,10 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
                 const float4 cv = __ldg(reinterpret_cast<const float4*>(in.conv + (size_t)t * in.plane_stride +
                                                                         ly * in.pitch + lx));
                 const double F = P.flux[in.flux_off + t];
-                const double a0 = F * (double)cv.x, a1 = F * (double)cv.y, a2 = F * (double)cv.z, a3 = F * (double)cv.w;
-                s0 += isfinite(a0) ? a0 : 0.0;
-                s1 += isfinite(a1) ? a1 : 0.0;
-                s2 += isfinite(a2) ? a2 : 0.0;
-                s3 += isfinite(a3) ? a3 : 0.0;
+                s0 = fma(F, (double)cv.x, s0);
+                s1 = fma(F, (double)cv.y, s1);
+                s2 = fma(F, (double)cv.z, s2);
+                s3 = fma(F, (double)cv.w, s3);
               }
               const float4 e = *reinterpret_cast<const float4*>(es + t * kFoldTPX + 4 * q);
               s0 = (s0 * (double)e.x) * 1e4;
@@ -953,13 +977,13 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
               s2 = (s2 * (double)e.z) * 1e4;
               s3 = (s3 * (double)e.w) * 1e4;
             }
-            double* dst = vs + ((size_t)g * kFoldTCH + tl) * kFoldTPX + 4 * q;
+            double* dst = vs + ((size_t)g * kTmaTCH + tl) * kFoldTPX + 4 * q;
             *reinterpret_cast<double2*>(dst) = make_double2(s0, s1);
             *reinterpret_cast<double2*>(dst + 2) = make_double2(s2, s3);
           }
         }
         GPY_TICK(4);
-        const bool fetch_next = cbase + 4 >= nchunks && t0 + kFoldTCH >= nT && next < n_items;
+        const bool fetch_next = cbase + 4 >= nchunks && t0 + kTmaTCH >= nT && next < n_items;
         if (tid == 0 && fetch_next) arm_expo(next);
         __syncthreads();
         GPY_TICK(5);
@@ -969,16 +993,17 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         // ---- phase 2: acc[r] += pdf[t][r] * v[t][p] over the non-zero band ----
         if (c < nchunks) {
           for (int g = 0; g < G; ++g) {
-            const int blo = D.band[(g * nchunks + c) * 2], bhi = D.band[(g * nchunks + c) * 2 + 1];
-            const int tlo = max(blo, t0), thi = min(bhi, t0 + kFoldTCH);
-            const double* vrow = vs + (size_t)g * kFoldTCH * kFoldTPX + 2 * pp;
-            const double* prow = pdf_s + (size_t)g * nT * nRp + 8 * c;
+            const int4 bnd = *reinterpret_cast<const int4*>(D.band + (g * nchunks + c) * 4);
+            const int blo = bnd.x, bhi = bnd.y;
+            const int tlo = max(blo, t0), thi = min(bhi, t0 + kTmaTCH);
+            const double* vrow = vs + (size_t)g * kTmaTCH * kFoldTPX + 2 * pp;
+            const double* prow = pdf_s + (bnd.z - blo) * 8;  // band-compressed rows of this chunk
             for (int t = tlo; t < thi; ++t) {
               const double2 v = *reinterpret_cast<const double2*>(vrow + (t - t0) * kFoldTPX);
-              const double2 m0 = *reinterpret_cast<const double2*>(prow + t * nRp);
-              const double2 m1 = *reinterpret_cast<const double2*>(prow + t * nRp + 2);
-              const double2 m2 = *reinterpret_cast<const double2*>(prow + t * nRp + 4);
-              const double2 m3 = *reinterpret_cast<const double2*>(prow + t * nRp + 6);
+              const double2 m0 = *reinterpret_cast<const double2*>(prow + t * 8);
+              const double2 m1 = *reinterpret_cast<const double2*>(prow + t * 8 + 2);
+              const double2 m2 = *reinterpret_cast<const double2*>(prow + t * 8 + 4);
+              const double2 m3 = *reinterpret_cast<const double2*>(prow + t * 8 + 6);
               const double m[8] = {m0.x, m0.y, m1.x, m1.y, m2.x, m2.y, m3.x, m3.y};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
