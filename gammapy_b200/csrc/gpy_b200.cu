@@ -252,7 +252,7 @@ struct gpy_context {
   size_t pinned_cap = 0;
   cudaEvent_t h2d_done = nullptr;
   bool h2d_pending = false;
-  DevBuf zeros, staging, flux, partials, stat, tiles, scratch_a, scratch_b, scratch_c;
+  DevBuf zeros, desc, staging, flux, partials, stat, tiles, scratch_a, scratch_b, scratch_c;
   std::vector<gpy_dataset*> tiles_for;  // dataset list the tile table was built for
   std::vector<uint64_t> tiles_ver;
   double* stat_pinned = nullptr;
@@ -736,8 +736,9 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         !al16(ds->mask) || P64 * (size_t)std::max(ds->nT, ds->nR) > (size_t)INT32_MAX)
       tma_ok = false;
   }
-  const gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G, max_pdfc_rows, max_inst);
-  if (lay.total > (size_t)c->max_smem_optin || c->force_generic) tma_ok = false;
+  const gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G, max_pdfc_rows);
+  if (lay.total > (size_t)c->max_smem_optin || c->force_generic || max_inst > gpy::kFoldLMax + gpy::kDescOverflow)
+    tma_ok = false;
   size_t max_fold_smem = 0;
   if (!tma_ok) {
     for (int d = 0; d < D; ++d)
@@ -814,6 +815,22 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   int per_tile = 1;
   const int variant = rq.npred_out ? 1 : 0;
   if (tma_ok) {
+    const gpy::DescLayout dl = gpy::desc_layout(max_nT, max_nRp);
+    GPY_TRY(c->desc.reserve(n_items * (size_t)dl.bytes, c->stream));
+    gpy::PrepParams pp;
+    pp.ds = fp.ds;
+    pp.tile_ds = fp.tile_ds;
+    pp.evals = fp.evals;
+    pp.insts = fp.insts;
+    pp.flux = fp.flux;
+    pp.desc = (unsigned char*)c->desc.p;
+    pp.B = B;
+    pp.n_tiles = n_tiles;
+    pp.max_nT = max_nT;
+    pp.max_nRp = max_nRp;
+    gpy::prep_items_kernel<<<(unsigned)((n_items + 7) / 8), 256, 0, c->stream>>>(pp);
+    c->launches++;
+    fp.desc = (const unsigned char*)c->desc.p;
     auto kern = variant ? gpy::fold_cash_tma_kernel<true> : gpy::fold_cash_tma_kernel<false>;
     if (lay.total > c->tma_smem_set[variant]) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
@@ -899,7 +916,7 @@ int gpy_finalize(gpy_context_t* c) {
   if (!c) return GPY_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->zeros, &c->staging, &c->flux, &c->partials, &c->stat, &c->tiles, &c->scratch_a, &c->scratch_b, &c->scratch_c})
+  for (DevBuf* b : {&c->zeros, &c->desc, &c->staging, &c->flux, &c->partials, &c->stat, &c->tiles, &c->scratch_a, &c->scratch_b, &c->scratch_c})
     b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->stat_pinned) cudaFreeHost(c->stat_pinned);

@@ -426,6 +426,7 @@ struct FoldParams {
   int max_inst;             // capacity of the per-block overlap list
   int smem_nT, smem_nR, smem_nRp, smem_G;  // largest axes of the launch: fixed shared-memory layout (bulk-copy kernel)
   int smem_pdfc_rows, pad3_;
+  const unsigned char* desc;  // [B * n_tiles][desc_layout(smem_nT, smem_nRp).bytes] item descriptors (prep_items_kernel)
   const float* zeros;       // >= 16 bytes of zeros: load target of (thread, source) pairs outside the cutout
   int pad_;
   double log_trunc;         // log((double)(float)1e-25): Cython narrows the constant to C float
@@ -726,44 +727,126 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
       : "memory");
 }
 
-constexpr int kTmaTCH = 32;  // true-energy bins per pass of the bulk-copy kernel (2 passes at nT = 60)
-struct FoldSmem {  // byte offsets of the fixed shared-memory layout
-  size_t es, bs, cs, ms, vs, pdf, flux, bkgfac, slist, bars, total;
+// ---- per-item work descriptors --------------------------------------------------------------------------
+// prep_items_kernel (one warp per (tile, vector) item, after K0) resolves everything an item needs besides the
+// data cubes: the sources whose cutout overlaps the tile (first kFoldLMax as InstDev copies + their spectral
+// fluxes, further ones as indices), and the background factors norm (E/E0)^-tilt.  The fold kernel fetches
+// the descriptor of the NEXT item with one bulk copy while it computes the current one, so its prologue is a
+// single mbarrier wait instead of a serial list build over global memory.
+constexpr int kFoldLMax = 4;       // overlapping sources held in registers by the fold kernel
+constexpr int kDescOverflow = 60;  // further overlapping sources per item (indices; slow path)
+struct DescLayout {
+  int inst, flux, bkg, over, bytes;  // byte offsets inside a descriptor; header = int4 {nl, n_over, 0, 0}
 };
-__host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int G, int pdfc_rows, int max_inst) {
-  FoldSmem L;
-  size_t o = 0;
-  L.es = o;      o += (size_t)nT * kFoldTPX * 4;
-  L.bs = o;      o += (size_t)nR * kFoldTPX * 4;
-  L.cs = o;      o += (size_t)nR * kFoldTPX * 4;
-  L.ms = o;      o += ((size_t)nR * kFoldTPX + 15) / 16 * 16;
-  L.vs = o;      o += (size_t)G * kTmaTCH * kFoldTPX * 8;
-  L.pdf = o;     o += (size_t)pdfc_rows * 64;
-  L.flux = o;    o += (size_t)4 * nT * 8;  // spectral fluxes of the kFoldLMax sources held in registers
-  L.bkgfac = o;  o += (size_t)nRp * 8;
-  L.slist = o;   o += (size_t)max_inst * sizeof(InstDev);
-  L.bars = (o + 7) / 8 * 8;
-  L.total = L.bars + 2 * 8;
+__host__ __device__ inline DescLayout desc_layout(int nT, int nRp) {
+  DescLayout L;
+  L.inst = 16;
+  L.flux = L.inst + kFoldLMax * (int)sizeof(InstDev);
+  L.bkg = L.flux + kFoldLMax * nT * 8;
+  L.over = L.bkg + nRp * 8;
+  L.bytes = (L.over + kDescOverflow * 4 + 15) / 16 * 16;
   return L;
 }
 
-constexpr int kFoldLMax = 4;  // overlapping sources whose per-thread offsets live in registers
+struct PrepParams {
+  const DatasetDev* ds;
+  const int* tile_ds;
+  const EvalDev* evals;
+  const InstDev* insts;
+  const double* flux;
+  unsigned char* desc;  // [B * n_tiles][desc bytes]
+  int B, n_tiles, max_nT, max_nRp;
+};
+
+__global__ void __launch_bounds__(256) prep_items_kernel(const PrepParams P) {
+  const int lane = threadIdx.x & 31;
+  const long long item = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+  if (item >= (long long)P.B * P.n_tiles) return;
+  const DescLayout L = desc_layout(P.max_nT, P.max_nRp);
+  unsigned char* out = P.desc + (size_t)item * L.bytes;
+  const int b = (int)(item % P.B);
+  const int tile = (int)(item / P.B);
+  const int d = P.tile_ds[tile];
+  const DatasetDev& D = P.ds[d];
+  const EvalDev& ev = P.evals[(size_t)d * P.B + b];
+  const int p0 = (tile - D.tile_begin) * kFoldTPX;
+  const int npx = min(kFoldTPX, (int)D.P - p0);
+  const int y_first = p0 / D.nx, y_last = (p0 + npx - 1) / D.nx;
+  const int x_first = p0 - y_first * D.nx, x_last = p0 + npx - 1 - y_last * D.nx;
+  InstDev* oinst = reinterpret_cast<InstDev*>(out + L.inst);
+  double* oflux = reinterpret_cast<double*>(out + L.flux);
+  double* obkg = reinterpret_cast<double*>(out + L.bkg);
+  int* oover = reinterpret_cast<int*>(out + L.over);
+  int n = 0;
+  for (int base = 0; base < ev.inst_count; base += 32) {
+    const int i = base + lane;
+    bool ov = false;
+    InstDev in;
+    if (i < ev.inst_count) {
+      in = P.insts[ev.inst_begin + i];
+      ov = in.y0 <= y_last && in.y0 + in.cy > y_first;
+      if (ov && y_first == y_last) ov = in.x0 <= x_last && in.x0 + in.cx > x_first;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ov);
+    const int pos = n + __popc(m & ((1u << lane) - 1u));
+    if (ov) {
+      if (pos < kFoldLMax)
+        oinst[pos] = in;
+      else if (pos < kFoldLMax + kDescOverflow)
+        oover[pos - kFoldLMax] = ev.inst_begin + i;
+    }
+    n += __popc(m);
+  }
+  __syncwarp();
+  const int nl = min(n, kFoldLMax);
+  if (lane == 0) *reinterpret_cast<int4*>(out) = make_int4(nl, min(max(n - kFoldLMax, 0), kDescOverflow), 0, 0);
+  // fluxes of the register-resident sources, zero rows beyond nl (row stride = max_nT)
+  for (int i = lane; i < kFoldLMax * P.max_nT; i += 32) {
+    const int l = i / P.max_nT, t = i - l * P.max_nT;
+    double v = 0.0;
+    if (l < nl && t < D.nT) v = P.flux[oinst[l].flux_off + t];
+    oflux[i] = v;
+  }
+  // background factors norm * (E_c / E_0)^-tilt (PowerLawNormSpectralModel.evaluate, spectral.py:1159-1162)
+  for (int r = lane; r < P.max_nRp; r += 32) {
+    double fac = 1.0;
+    if (ev.bkg_enabled && r < D.nR) fac = ev.bkg_norm * pow(D.ecenter[r] / ev.bkg_ref, -ev.bkg_tilt);
+    obkg[r] = fac;
+  }
+}
+
+constexpr int kTmaTCH = 32;  // true-energy bins per pass of the bulk-copy kernel (2 passes at nT = 60)
+struct FoldSmem {  // byte offsets of the fixed shared-memory layout
+  size_t es, bs, cs, ms, vs, pdf, desc, bars, total;
+};
+__host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int G, int pdfc_rows) {
+  FoldSmem L;
+  size_t o = 0;
+  L.es = o;    o += (size_t)nT * kFoldTPX * 4;
+  L.bs = o;    o += (size_t)nR * kFoldTPX * 4;
+  L.cs = o;    o += (size_t)nR * kFoldTPX * 4;
+  L.ms = o;    o += ((size_t)nR * kFoldTPX + 15) / 16 * 16;
+  L.vs = o;    o += (size_t)G * kTmaTCH * kFoldTPX * 8;
+  L.pdf = o;   o += (size_t)pdfc_rows * 64;
+  L.desc = o;  o += (size_t)2 * desc_layout(nT, nRp).bytes;  // double buffered item descriptors
+  L.bars = (o + 7) / 8 * 8;
+  L.total = L.bars + 3 * 8;
+  return L;
+}
 
 template <bool WRITE_NPRED>
 __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const FoldParams P) {
   extern __shared__ __align__(128) unsigned char fold_raw[];
-  const FoldSmem L = fold_tma_layout(P.smem_nT, P.smem_nR, P.smem_nRp, P.smem_G, P.smem_pdfc_rows, P.max_inst);
+  const FoldSmem L = fold_tma_layout(P.smem_nT, P.smem_nR, P.smem_nRp, P.smem_G, P.smem_pdfc_rows);
   float* es = reinterpret_cast<float*>(fold_raw + L.es);
   float* bs = reinterpret_cast<float*>(fold_raw + L.bs);
   float* cs = reinterpret_cast<float*>(fold_raw + L.cs);
   unsigned char* ms = fold_raw + L.ms;
   double* vs = reinterpret_cast<double*>(fold_raw + L.vs);
   double* pdf_s = reinterpret_cast<double*>(fold_raw + L.pdf);
-  double* flux_s = reinterpret_cast<double*>(fold_raw + L.flux);  // [kFoldLMax][nT], zero rows beyond nl
-  double* bkgfac = reinterpret_cast<double*>(fold_raw + L.bkgfac);
-  InstDev* slist = reinterpret_cast<InstDev*>(fold_raw + L.slist);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + L.bars);  // [0] exposure, [1] epilogue inputs
-  __shared__ int n_list;
+  unsigned char* desc_s = fold_raw + L.desc;
+  const DescLayout DL = desc_layout(P.smem_nT, P.smem_nRp);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + L.bars);  // [0] exposure, [1] epilogue inputs, [2] descriptor
 
   const int tid = threadIdx.x;
   const int n_items = P.B * P.n_tiles;
@@ -772,6 +855,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -826,11 +910,17 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     }
   };
 
+  auto fetch_desc = [&](int it, uint32_t buf) {  // thread 0: one bulk copy of the item's work descriptor
+    mbar_arrive_expect_tx(&bars[2], (uint32_t)DL.bytes);
+    bulk_g2s(desc_s + buf * DL.bytes, P.desc + (size_t)it * DL.bytes, (uint32_t)DL.bytes, &bars[2]);
+  };
+
   int item = blockIdx.x;
   if (item < n_items) {
     if (tid == 0) {
       arm_expo(item);
       arm_epi(item);
+      fetch_desc(item, 0);
     }
     __syncthreads();
     issue_expo(item);
@@ -854,7 +944,6 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const int tile = item / P.B;
     const int d = P.tile_ds[tile];
     const DatasetDev D = P.ds[d];
-    const EvalDev ev = P.evals[(size_t)d * P.B + b];
     const int nT = D.nT, nR = D.nR, nRp = D.nRp, G = D.n_groups;
     const int p0 = (tile - D.tile_begin) * kFoldTPX;
     const int npx = min(kFoldTPX, (int)D.P - p0);
@@ -864,41 +953,21 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
       for (int i = tid; i < D.pdfc_rows * 8; i += kFoldThreads) pdf_s[i] = D.pdfc[i];
       cur_ds = d;
     }
-    if (tid < nRp) {
-      double fac = 1.0;
-      if (ev.bkg_enabled && tid < nR)  // PowerLawNormSpectralModel.evaluate (spectral.py:1159-1162)
-        fac = ev.bkg_norm * pow(D.ecenter[tid] / ev.bkg_ref, -ev.bkg_tilt);
-      bkgfac[tid] = fac;
-    }
-    const int y_first = p0 / D.nx, y_last = (p0 + npx - 1) / D.nx;
-    const int x_first = p0 - y_first * D.nx, x_last = p0 + npx - 1 - y_last * D.nx;
-    if (tid < 32) {
-      int n = 0;
-      for (int base = 0; base < ev.inst_count; base += 32) {
-        const int i = base + tid;
-        bool ov = false;
-        InstDev in;
-        if (i < ev.inst_count) {
-          in = P.insts[ev.inst_begin + i];
-          ov = in.y0 <= y_last && in.y0 + in.cy > y_first;
-          if (ov && y_first == y_last) ov = in.x0 <= x_last && in.x0 + in.cx > x_first;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, ov);
-        if (ov) slist[n + __popc(m & ((1u << tid) - 1u))] = in;
-        n += __popc(m);
-      }
-      if (tid == 0) n_list = n;
-    }
+    // work descriptor of this item (prefetched); start fetching the next one into the other buffer
+    // The fetch of the NEXT descriptor is issued after the first CTA barrier of this item (below): by then every
+    // thread has observed the completion of this phase.  Issuing it earlier lets the barrier run two phases ahead
+    // of a slow thread, whose parity wait would then never return.
+    mbar_wait(&bars[2], parity);
+    bool desc_fetched = false;
+    const unsigned char* dsc = desc_s + parity * DL.bytes;
+    const int nl = reinterpret_cast<const int*>(dsc)[0], nover = reinterpret_cast<const int*>(dsc)[1];
+    const InstDev* slist = reinterpret_cast<const InstDev*>(dsc + DL.inst);
+    const double* flux_s = reinterpret_cast<const double*>(dsc + DL.flux);  // [kFoldLMax][smem_nT]
+    const double* bkgfac = reinterpret_cast<const double*>(dsc + DL.bkg);
+    const int* over = reinterpret_cast<const int*>(dsc + DL.over);
+    const int fstride = P.smem_nT;
     GPY_TICK(0);
-    __syncthreads();
     GPY_TICK(1);
-    const int nl = n_list;
-
-    // spectral fluxes of the first kFoldLMax overlapping sources -> shared memory (zero rows beyond nl)
-    for (int i = tid; i < kFoldLMax * nT; i += kFoldThreads) {
-      const int l = i / nT, t = i - l * nT;
-      flux_s[i] = l < nl ? P.flux[slist[l].flux_off + t] : 0.0;
-    }
     // this thread's pixel quad and, per overlapping source, a pointer into its cutout; outside the cutout the
     // pointer targets a zero word with stride 0, so phase 1 is branch free and its loads can all be in flight
     const int pq = p0 + 4 * q;
@@ -921,8 +990,6 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         }
       }
     }
-    __syncthreads();  // flux_s visible
-
     const int nchunks = nRp >> 3;
     double stat = 0.0;
     for (int cbase = 0; cbase < nchunks; cbase += 4) {  // one pass for nR <= 32
@@ -936,6 +1003,8 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         if (cbase == 0) mbar_wait(&bars[0], parity);
         if (tid == 0 && cbase + 4 >= nchunks && next < n_items) arm_expo(next);
         __syncthreads();
+        if (!desc_fetched && tid == 0 && next < n_items) fetch_desc(next, parity ^ 1u);
+        desc_fetched = true;
         if (cbase + 4 >= nchunks && next < n_items) issue_expo(next);
       }
       for (int t0 = 0; t0 < (nl > 0 ? nT : 0); t0 += kTmaTCH) {
@@ -952,14 +1021,14 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
 #pragma unroll
               for (int l = 0; l < kFoldLMax; ++l) {
                 const float4 cv = ldg_f4_hint(cptr[l] + (size_t)t * pstr[l], pol_keep);
-                const double F = grp[l] == g ? flux_s[l * nT + t] : 0.0;
+                const double F = grp[l] == g ? flux_s[l * fstride + t] : 0.0;
                 s0 = fma(F, (double)cv.x, s0);
                 s1 = fma(F, (double)cv.y, s1);
                 s2 = fma(F, (double)cv.z, s2);
                 s3 = fma(F, (double)cv.w, s3);
               }
-              for (int l = kFoldLMax; l < nl; ++l) {  // rare: more than kFoldLMax sources on one tile
-                const InstDev& in = slist[l];
+              for (int o = 0; o < nover; ++o) {  // rare: more than kFoldLMax sources on one tile
+                const InstDev& in = P.insts[over[o]];
                 if (in.group != g) continue;
                 const int ly = qy - in.y0, lx = qx - in.x0a;
                 if (ly < 0 || ly >= in.cy || lx < 0 || lx >= in.pitch) continue;
@@ -987,6 +1056,8 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         if (tid == 0 && fetch_next) arm_expo(next);
         __syncthreads();
         GPY_TICK(5);
+        if (!desc_fetched && tid == 0 && next < n_items) fetch_desc(next, parity ^ 1u);
+        desc_fetched = true;
         // exposure tile fully consumed: start fetching the next item's while phase 2 / the epilogue run
         if (fetch_next) issue_expo(next);
         GPY_TICK(6);
