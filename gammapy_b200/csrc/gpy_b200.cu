@@ -843,7 +843,6 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     per_sm = std::max(per_sm, 1);
     const unsigned grid = (unsigned)std::min(n_items, (size_t)per_sm * c->num_sms);
     kern<<<grid, gpy::kFoldThreads, lay.total, c->stream>>>(fp);
-    per_tile = gpy::kFoldThreads / 32;
   } else {
     if (max_fold_smem > c->fold_smem_set) {
       CUDA_TRY(cudaFuncSetAttribute(gpy::fold_cash_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -847,6 +847,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   unsigned char* desc_s = fold_raw + L.desc;
   const DescLayout DL = desc_layout(P.smem_nT, P.smem_nRp);
   uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + L.bars);  // [0] exposure, [1] epilogue inputs, [2] descriptor
+  __shared__ double wsum[kFoldThreads / 32];
 
   const int tid = threadIdx.x;
   const int n_items = P.B * P.n_tiles;
@@ -1146,9 +1147,12 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     GPY_TICK(9);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) stat += __shfl_xor_sync(0xffffffffu, stat, o);
-    if ((tid & 31) == 0) P.partials[((size_t)b * P.n_tiles + tile) * (kFoldThreads / 32) + (tid >> 5)] = stat;
+    if ((tid & 31) == 0) wsum[tid >> 5] = stat;
     if (tid == 0 && next < n_items) arm_epi(next);
     __syncthreads();  // every warp is past its epilogue reads; list / bkgfac reuse in the next item
+    if (tid == 0)     // fixed summation order; no warp can rewrite wsum before passing a barrier with thread 0
+      P.partials[(size_t)b * P.n_tiles + tile] =
+          ((wsum[0] + wsum[1]) + (wsum[2] + wsum[3])) + ((wsum[4] + wsum[5]) + (wsum[6] + wsum[7]));
     GPY_TICK(10);
     if (next < n_items) issue_epi(next);
     GPY_TICK(11);
