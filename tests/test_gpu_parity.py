@@ -438,3 +438,139 @@ def test_two_engines_share_one_dataset(ctx):
     npred_b = b.npred().data  # re-installs b's own parameter columns on the shared handle
     assert abs(joint.stat_sum() - want) < 1e-6
     assert_allclose(b.npred().data, npred_b)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# shapes / options that take the other code paths
+# ---------------------------------------------------------------------------------------------------------
+def _stat_pair(ds, seed=5, conv="exact64"):
+    from gammapy_b200 import Map
+    from oracle import adapter
+
+    de = adapter.evaluator_for(ds, conv=conv)
+    ds.counts = Map.from_geom(ds._geom, data=de.fake(seed), dtype=float)
+    return ds.stat_sum_likelihood(), de.stat_sum(), ds.npred().data, de.npred()
+
+
+def test_odd_geometry_uses_generic_kernel(ctx):
+    """nx = 101 is not a multiple of 4: the any-shape kernel runs (no bulk-copy staging, scalar loads)."""
+    from gammapy_b200 import configs
+
+    ds = configs.make_c2(width=(2.02, 1.5), mask_radius=0.7)
+    assert ds._geom.npix == (101, 75)
+    stat, want, npred, npred_want = _stat_pair(ds)
+    assert_allclose(npred, npred_want, rtol=1e-5, atol=1e-12 * npred_want.max())
+    assert abs(stat - want) < 1e-3
+
+
+def test_forced_generic_kernel_matches_staged_kernel(ctx):
+    """GPY_FOLD_KERNEL=2 is read at context creation; here the odd/even geometries exercise both kernels on the
+    same physics: a 100-px and a 101-px wide map of the same field give the same npred where they overlap."""
+    from gammapy_b200 import configs
+
+    a = configs.make_c1(width=(2.0, 2.0), mask_radius=None)
+    b = configs.make_c1(width=(2.02, 2.0), mask_radius=None)   # 101 px: generic kernel
+    na, nb = a.npred().data, b.npred().data
+    assert na.shape[-1] == 100 and nb.shape[-1] == 101
+    # pixel centres differ by half a pixel between the two grids: compare the totals of the source-dominated region
+    assert_allclose(na.sum() / nb[..., :100].sum(), 1.0, rtol=2e-2)
+
+
+def test_no_psf_and_irf_switches(ctx):
+    from gammapy_b200 import Map, configs
+    from oracle import adapter
+
+    ds = configs.make_c2(width=(2.0, 2.0), mask_radius=0.9)
+    ds.models["src-1"].apply_irf["psf"] = False     # W broadcast over energy instead of the convolved cube
+    ds.models["src-2"].apply_irf["edisp"] = False   # diagonal response: second edisp group
+    ds.models = ds.models                            # rebuild evaluators (datasets/map.py:674-694)
+    de = adapter.evaluator_for(ds, conv="exact64")
+    for name, ev in de.evaluators.items():
+        if name == "src-2":
+            from gammapy_b200.irf import EDispKernel
+
+            e_true = ds.exposure.geom.axes["energy_true"]
+            ev_diag = EDispKernel.from_diagonal_response(e_true, ds._geom.axes["energy"]).pdf_matrix
+            ev._diag = ev_diag
+    # the oracle evaluator applies ds.edisp to every model: patch the one that opted out
+    orig_update = type(de.evaluators["src-2"]).update
+
+    def update(self, d):
+        orig_update(self, d)
+        if self.model["name"] == "src-2":
+            self.edisp = self._diag
+
+    type(de.evaluators["src-2"]).update = update
+    try:
+        want = de.npred()
+    finally:
+        type(de.evaluators["src-2"]).update = orig_update
+    got = ds.npred().data
+    assert_allclose(got, want, rtol=1e-5, atol=1e-12 * want.max())
+    # dataset without any PSF
+    ds2 = configs.make_c1(width=(1.6, 1.6), mask_radius=0.7)
+    ds2.psf = None
+    stat, want_stat, npred, npred_want = _stat_pair(ds2)
+    assert_allclose(npred, npred_want, rtol=1e-6, atol=1e-12 * npred_want.max())
+    assert abs(stat - want_stat) < 1e-3
+
+
+def test_masks_and_missing_maps(ctx):
+    from gammapy_b200 import Map, configs
+    from oracle import adapter
+
+    ds = configs.make_c1(width=(1.6, 1.6), mask_radius=0.7)
+    ds.counts = Map.from_geom(ds._geom, data=adapter.evaluator_for(ds).fake(2), dtype=float)
+    # everything masked: empty sum
+    ds.mask_fit = Map.from_geom(ds._geom, data=np.zeros(ds.data_shape, dtype=bool), dtype=bool)
+    assert ds.stat_sum_likelihood() == 0.0
+    # ragged mask: one energy plane and a few scattered pixels
+    rng = np.random.RandomState(0)
+    mask = rng.uniform(size=ds.data_shape) < 0.3
+    mask[3] = False
+    ds.mask_fit = Map.from_geom(ds._geom, data=mask, dtype=bool)
+    de = adapter.evaluator_for(ds, conv="exact64")
+    assert abs(ds.stat_sum_likelihood() - de.stat_sum()) < 1e-3
+    # no masks at all, no background map
+    ds.mask_fit = None
+    ds.mask_safe = None
+    ds.background = None
+    ds.models = [m for m in ds.models if m.name == "model-simu"]
+    de = adapter.evaluator_for(ds, conv="exact64")
+    assert_allclose(ds.npred().data, de.npred(), rtol=1e-5, atol=1e-12)
+    assert abs(ds.stat_sum_likelihood() - de.stat_sum()) < 1e-3
+    # negative amplitude: npred clipped at 0, truncation value in the Cash log (finite, large)
+    ds.models["model-simu"].spectral_model.amplitude.value = -1e-11
+    de = adapter.evaluator_for(ds, conv="exact64")
+    got, want = ds.stat_sum_likelihood(), de.stat_sum()
+    assert np.isfinite(got) and abs(got - want) < 1e-3 * max(1.0, abs(want) * 1e-9)
+    # NaN parameter: the source vanishes (WcsNDMap.stack nan_to_num), background-less npred is all zero
+    ds.models["model-simu"].spectral_model.amplitude.value = 1e-11
+    ds.models["model-simu"].spectral_model.index.value = np.nan
+    assert np.all(ds.npred().data == 0)
+
+
+def test_batched_joint_datasets(ctx):
+    """B > 1 with D > 1 in one launch equals the per-vector, per-dataset evaluations."""
+    from gammapy_b200 import Map, configs
+    from oracle import adapter
+
+    datasets = configs.make_c4(n_obs=3, width=(1.6, 1.6), mask_radius=0.7)
+    for i, ds in enumerate(datasets):
+        ds.counts = Map.from_geom(ds._geom, data=adapter.evaluator_for(ds).fake(10 + i), dtype=float)
+    values, plist = datasets.parameter_vector()
+    cols = {id(p): i for i, p in enumerate(plist)}
+    shared = datasets[0].models["model-simu"]
+    grid = np.tile(values, (4, 1))
+    grid[1, cols[id(shared.spectral_model.index)]] += 0.1
+    grid[2, cols[id(shared.spatial_model.sigma)]] += 0.02
+    grid[3, cols[id(datasets[1].background_model.spectral_model.norm)]] *= 1.1
+    total, per = datasets.stat_sum_batch(grid, per_dataset=True)
+    assert per.shape == (4, 3)
+    assert_allclose(per.sum(axis=1), total, rtol=1e-14)
+    for k in range(4):
+        for p, v in zip(plist, grid[k]):
+            p.value = v
+        assert abs(datasets.stat_sum() - total[k]) < 1e-6
+    for p, v in zip(plist, values):
+        p.value = v
