@@ -35,6 +35,7 @@ class DatasetDesc(C.Structure):
         ("edisp_diagonal", C.c_void_p),
         ("nodes", C.c_void_p),
         ("n_nodes", C.c_int32),
+        ("weight", C.c_void_p),
     ]
 
 

@@ -273,6 +273,7 @@ struct gpy_dataset {
   uint64_t version = 0;
   const float *exposure = nullptr, *background = nullptr, *counts = nullptr;
   const uint8_t* mask = nullptr;
+  const float* weight = nullptr;
   std::vector<uint8_t> mask_image;  // empty = all true
   DevBuf d_edges, d_nodes, d_ecenter, d_edisp, d_band, d_pdfc, d_omega, d_kflip, d_planes;
   int pdfc_rows[2] = {0, 0};  // band-compressed rows when 1 / 2 edisp groups are in use
@@ -611,6 +612,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     dd.background = ds->background;
     dd.counts = rq.npred_out ? nullptr : ds->counts;
     dd.mask = ds->mask;
+    dd.weight = ds->weight;
     dd.edisp = (const double*)ds->d_edisp.p;
     dd.band = (const int*)ds->d_band.p;
     dd.pdfc = (const double*)ds->d_pdfc.p;
@@ -733,7 +735,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     const size_t P64 = (size_t)ds->geom.nx * ds->geom.ny;
     auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
     if (ds->geom.nx % 4 != 0 || P64 % 16 != 0 || !al16(ds->exposure) || !al16(ds->background) || !al16(ds->counts) ||
-        !al16(ds->mask) || P64 * (size_t)std::max(ds->nT, ds->nR) > (size_t)INT32_MAX)
+        !al16(ds->mask) || ds->weight != nullptr || P64 * (size_t)std::max(ds->nT, ds->nR) > (size_t)INT32_MAX)
       tma_ok = false;
   }
   const gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G, max_pdfc_rows);
@@ -953,6 +955,7 @@ int gpy_dataset_create(gpy_context_t* c, const gpy_dataset_desc* desc, gpy_datas
   ds->background = desc->background;
   ds->counts = desc->counts;
   ds->mask = desc->mask;
+  ds->weight = desc->weight;
   ds->version = ++c->stamp;
   const size_t P = (size_t)g.nx * g.ny;
   if (desc->mask_image) ds->mask_image.assign(desc->mask_image, desc->mask_image + P);

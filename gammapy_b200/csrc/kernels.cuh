@@ -388,6 +388,7 @@ struct DatasetDev {
   const float* background;  // [nR, P] or null
   const float* counts;      // [nR, P] or null
   const uint8_t* mask;      // [nR, P] or null
+  const float* weight;      // [nR, P] or null: float mask of the weighted Cash (generic kernel only)
   const double* edisp;      // [n_groups, nT, nRp] zero padded
   const int* band;          // [n_groups, nRp / 8, 4]: first / last+1 true bin with non-zero pdf per reco chunk, row offset
                             // of the chunk in the band-compressed matrix, pad
@@ -649,8 +650,16 @@ __global__ void __launch_bounds__(kFoldThreads, GPY_FOLD_MINBLOCKS) fold_cash_ge
                 npr = kTrunc;
                 lognpr = P.log_trunc;
               }
-              stat += npr;
-              if (n > 0.0) stat -= n * lognpr;
+              if (D.weight) {  // weighted_cash_sum_cython (fit_statistics_cython.pyx:17-51)
+                const double w = (double)__ldg(D.weight + idx);
+                if (w > 0.0) {
+                  stat += w * npr;
+                  if (n > 0.0) stat -= w * n * lognpr;
+                }
+              } else {
+                stat += npr;
+                if (n > 0.0) stat -= n * lognpr;
+              }
             }
           }
         }

@@ -30,8 +30,9 @@ class MapDataset:
 
     def __init__(self, models=None, counts=None, exposure=None, background=None, psf=None, edisp=None,
                  mask_safe=None, mask_fit=None, gti=None, meta_table=None, name=None, meta=None, stat_type="cash"):
-        if stat_type != "cash":
-            raise NotImplementedError("only stat_type='cash' is on the accelerated path")
+        if stat_type not in ("cash", "cash_weighted"):
+            raise NotImplementedError("only stat_type 'cash' and 'cash_weighted' are on the accelerated path")
+        self.stat_type = stat_type
         self._name = name if name is not None else f"dataset-{next(_ds_counter):04d}"
         self._device = None
         self._engine = None
@@ -265,12 +266,15 @@ class MapDataset:
     stat_sum = stat_sum_likelihood
 
     def stat_array(self):
-        """Per-bin Cash (stats/fit_statistics.py:29-79, 295-298) from the GPU npred cube."""
+        """Per-bin Cash (stats/fit_statistics.py:29-79, 295-298, 323-329) from the GPU npred cube."""
         n_on = np.asarray(self._counts.data, dtype=float)
         mu_on = self.npred().data
         mu_on = np.where(mu_on <= 1e-25, 1e-25, mu_on)
         with np.errstate(divide="ignore", invalid="ignore"):
-            return 2 * (mu_on - n_on * np.log(mu_on))
+            stat = 2 * (mu_on - n_on * np.log(mu_on))
+        if self.stat_type == "cash_weighted" and self.mask is not None:
+            stat = stat * np.asarray(self.mask.data, dtype=float)
+        return stat
 
     def fake(self, random_state="random-seed"):
         """Poisson counts from npred with the legacy RandomState (datasets/map.py:1538-1554)."""

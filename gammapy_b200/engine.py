@@ -79,7 +79,13 @@ class DeviceDataset:
         if mask is not None:
             mdata = np.asarray(mask.data)
             if mdata.dtype != bool:
-                raise NotImplementedError("float (weighted) masks need stat_type='cash_weighted', which is not on the GPU path yet")
+                # WeightedCashFitStatistic (stats/fit_statistics.py:304-321): mask = ~(mask == False), weights = mask[mask]
+                if ds.stat_type != "cash_weighted":
+                    raise ValueError("float masks need stat_type='cash_weighted'")
+                desc.weight = self._to_device("weight", mdata, np.float32).data_ptr()
+                mdata = ~(mdata == False)  # noqa: E712
+            elif ds.stat_type == "cash_weighted":
+                desc.weight = self._to_device("weight", mdata, np.float32).data_ptr()
             desc.mask = self._to_device("mask", mdata, np.uint8).data_ptr()
             host["mask_image"] = np.ascontiguousarray(np.logical_or.reduce(mdata, axis=0), dtype=np.uint8)
             desc.mask_image = _ptr(host["mask_image"])

@@ -71,6 +71,9 @@ typedef struct {
   const double* edisp_diagonal;      /* HOST [n_true, n_reco] diagonal response (evaluator.py:245-250) or NULL */
   const double* nodes;               /* HOST [n_true, n_nodes] geomspace nodes of integrate_spectrum (spectral.py:132-134) */
   int32_t n_nodes;                   /* int(max(100*log10(e_hi/e_lo), 2)) evaluated by the caller with numpy */
+  const float* weight;               /* DEVICE [n_reco, ny, nx] or NULL: float mask of stat_type "cash_weighted"
+                                        (WeightedCashFitStatistic, stats/fit_statistics.py:301-329); bins with
+                                        weight 0 are excluded, `mask` must then be (weight != 0) */
 } gpy_dataset_desc;
 
 /* One SkyModel: where its parameters sit in the parameter vector handed to gpy_stat_sum / gpy_npred.

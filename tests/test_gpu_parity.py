@@ -574,3 +574,32 @@ def test_batched_joint_datasets(ctx):
         assert abs(datasets.stat_sum() - total[k]) < 1e-6
     for p, v in zip(plist, values):
         p.value = v
+
+
+def test_weighted_cash_dataset(ctx):
+    """stat_type='cash_weighted' with a float mask (WeightedCashFitStatistic, fit_statistics.py:301-329)."""
+    from gammapy_b200 import Map, MapDataset, configs
+    from oracle import adapter, cash
+
+    base = configs.make_c1(width=(1.6, 1.6), mask_radius=None)
+    rng = np.random.RandomState(4)
+    weights = rng.uniform(0, 1, size=base.data_shape)
+    weights[rng.uniform(size=base.data_shape) < 0.3] = 0.0
+    ds = MapDataset(models=base.models, counts=None, exposure=base.exposure, background=base.background,
+                    psf=base.psf, edisp=base.edisp, mask_safe=None,
+                    mask_fit=Map.from_geom(base._geom, data=weights, dtype=float), name=base.name,
+                    stat_type="cash_weighted")
+    de = adapter.evaluator_for(base, conv="exact64")
+    counts = de.fake(6)
+    ds.counts = Map.from_geom(ds._geom, data=counts, dtype=float)
+    npred = de.npred()
+    mask = ~(weights == False)  # noqa: E712
+    ref = cash.reference_module()
+    w32 = weights.astype(np.float32).astype(float)  # the device copy of the weights is float32
+    if ref is not None:
+        want = ref.weighted_cash_sum_cython(counts[mask], npred[mask], w32[mask])
+    else:
+        want = cash.weighted_cash_sum(counts[mask], npred[mask], w32[mask])
+    got = ds.stat_sum_likelihood()
+    assert abs(got - want) < 1e-3
+    assert_allclose(ds.stat_array().sum(), got, rtol=1e-6)
