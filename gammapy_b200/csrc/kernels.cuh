@@ -1103,6 +1103,12 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
       GPY_TICK(2);
       if (cbase == 0) mbar_wait(&bars[1], parity);
       GPY_TICK(8);
+      // mu = acc + background model, clipped, parked in the (now free) v buffer as [r - r0][128]; the Cash terms
+      // are then computed in a second pass that deals the bins round-robin over all 256 threads, so the warps
+      // that own the low-energy reco chunks (where every bin has counts and needs a log) do not become the
+      // critical path of the item.
+      const int r0 = 8 * cbase;
+      double* mus = vs;
       if (c < nchunks && 2 * pp < npx) {
         const bool has_bkg = D.background && P.include_background;
 #pragma unroll
@@ -1119,39 +1125,37 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
             if (mu0 < 0.0) mu0 = 0.0;  // npred_total.data[npred_total.data < 0.0] = 0 (map.py:787)
             if (mu1 < 0.0) mu1 = 0.0;
           }
-          if (WRITE_NPRED) {
-            double* o = P.npred_out + (size_t)r * D.P + p0 + 2 * pp;
-            *reinterpret_cast<double2*>(o) = make_double2(mu0, mu1);
-          }
+          *reinterpret_cast<double2*>(mus + (r - r0) * kFoldTPX + 2 * pp) = make_double2(mu0, mu1);
+        }
+      }
+      __syncthreads();
+      {
+        const int nr = min(nR - r0, 32);
+        for (int i = tid; i < nr * kFoldTPX; i += kFoldThreads) {
+          const int rr = i >> 7, lp = i & (kFoldTPX - 1);  // kFoldTPX == 128
+          if (lp >= npx) continue;
+          const int r = r0 + rr;
+          const double mu = mus[i];
+          if (WRITE_NPRED) P.npred_out[(size_t)r * D.P + p0 + lp] = mu;
           if (D.counts) {
-            const float2 cn = *reinterpret_cast<const float2*>(cs + r * kFoldTPX + 2 * pp);
-            unsigned short mk = 0x0101;
-            if (D.mask) mk = *reinterpret_cast<const unsigned short*>(ms + r * kFoldTPX + 2 * pp);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const double mu = k == 0 ? mu0 : mu1;
-              const double n = (double)(k == 0 ? cn.x : cn.y);
-              const bool m = ((mk >> (8 * k)) & 0xff) != 0;
-              if (m) {
-                double npr, lognpr = 0.0;
-                if (mu > kTrunc) {
-                  npr = mu;
-#ifdef GPY_EXP_NO_LOG
-                  if (n > 0.0) lognpr = mu;
-#else
-                  if (n > 0.0) lognpr = log(mu);
-#endif
-                } else {
-                  npr = kTrunc;
-                  lognpr = P.log_trunc;
-                }
-                stat += npr;
-                if (n > 0.0) stat -= n * lognpr;
+            const bool m = D.mask ? ms[r * kFoldTPX + lp] != 0 : true;
+            if (m) {
+              const double n = (double)cs[r * kFoldTPX + lp];
+              double npr, lognpr = 0.0;
+              if (mu > kTrunc) {
+                npr = mu;
+                if (n > 0.0) lognpr = log(mu);
+              } else {
+                npr = kTrunc;
+                lognpr = P.log_trunc;
               }
+              stat += npr;
+              if (n > 0.0) stat -= n * lognpr;
             }
           }
         }
       }
+      if (cbase + 4 < nchunks) __syncthreads();  // the next sweep's phase 1 rewrites the v buffer
     }
     GPY_TICK(9);
 #pragma unroll
