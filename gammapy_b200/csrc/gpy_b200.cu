@@ -18,6 +18,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
+
 #include "../../include/gpy_b200.h"
 #include "kernels.cuh"
 
@@ -277,6 +279,9 @@ struct gpy_dataset {
   std::vector<uint8_t> mask_image;  // empty = all true
   DevBuf d_edges, d_nodes, d_ecenter, d_edisp, d_band, d_pdfc, d_omega, d_kflip, d_planes;
   int pdfc_rows[2] = {0, 0};  // band-compressed rows when 1 / 2 edisp groups are in use
+  DevBuf d_tmaps;             // 4 CUtensorMap: exposure, background, counts, mask (2-D [rows][P] tensors, box [rows][128])
+  std::vector<DevBuf> retired_tmaps;  // earlier map blocks: a rewritten map gets a NEW address (descriptor caches)
+  bool has_tmaps = false;
   std::vector<gpy::ConvPlane> planes;
   int max_h = 0, max_kw = 4;
   bool has_psf = false, has_diag = false;
@@ -466,6 +471,61 @@ void prepare_planes(const float* kernel, int n_planes, int K, std::vector<float>
   }
 }
 
+// 2-D tensor maps for the bulk-tensor (TMA) loads of the fold kernel: tensor [rows][P] (P innermost), box [rows][128].
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+bool encode_map(CUtensorMap* out, const void* base, bool is_u8, size_t P, int rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || !base || rows > 256) return false;
+  const size_t esz = is_u8 ? 1 : 4;
+  cuuint64_t dims[2] = {(cuuint64_t)P, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(P * esz)};
+  cuuint32_t box[2] = {(cuuint32_t)gpy::kFoldTPX, (cuuint32_t)rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(out, is_u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// (Re)build the dataset's tensor maps; leaves has_tmaps false when the shape is not eligible (the kernel then uses
+// 1-D bulk copies) or the driver entry point is missing.
+int build_tmaps(gpy_dataset* ds) {
+  ds->has_tmaps = false;
+  const size_t P = (size_t)ds->geom.nx * ds->geom.ny;
+  if (P % 16 != 0 || ds->geom.nx % 4 != 0 || P < (size_t)gpy::kFoldTPX) return GPY_OK;
+  alignas(64) CUtensorMap maps[4];
+  std::memset(maps, 0, sizeof(maps));
+  if (!encode_map(&maps[0], ds->exposure, false, P, ds->nT)) return GPY_OK;
+  if (ds->background && !encode_map(&maps[1], ds->background, false, P, ds->nR)) return GPY_OK;
+  if (ds->counts && !encode_map(&maps[2], ds->counts, false, P, ds->nR)) return GPY_OK;
+  if (ds->mask && !encode_map(&maps[3], ds->mask, true, P, ds->nR)) return GPY_OK;
+  if (ds->d_tmaps.p) {  // never rewrite a tensor map in place: the GPU may hold the old one in its descriptor cache
+    ds->retired_tmaps.push_back(ds->d_tmaps);
+    ds->d_tmaps = DevBuf();
+  }
+  GPY_TRY(ds->d_tmaps.reserve(sizeof(maps)));
+  CUDA_TRY(cudaMemcpyAsync(ds->d_tmaps.p, maps, sizeof(maps), cudaMemcpyHostToDevice, ds->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ds->ctx->stream));
+  ds->has_tmaps = true;
+  return GPY_OK;
+}
+
 // MapEvaluator.update geometry (evaluator.py:174-243) for spatial parameters `sp`.
 int evaluator_update(const gpy_dataset* ds, const Source& src, const double* sp, Rect& rect, bool& contributes) {
   const int type = src.desc.spatial_type;
@@ -619,6 +679,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     dd.pdfc_rows = ds->pdfc_rows[ds->groups_used - 1];
     max_pdfc_rows = std::max(max_pdfc_rows, dd.pdfc_rows);
     dd.ecenter = (const double*)ds->d_ecenter.p;
+    dd.tmaps = ds->has_tmaps ? ds->d_tmaps.p : nullptr;
     if (!rq.npred_out && !ds->counts) return fail(GPY_ERR_INVALID, "dataset %d has no counts: stat undefined", d);
 
     for (int b = 0; b < B; ++b) {
@@ -1021,6 +1082,7 @@ int gpy_dataset_create(gpy_context_t* c, const gpy_dataset_desc* desc, gpy_datas
   c->launches++;
   cudaError_t e = cudaStreamSynchronize(s);  // host staging vectors go out of scope
   if (e != cudaSuccess) return cleanup(fail(GPY_ERR_CUDA, "dataset upload failed: %s", cudaGetErrorString(e)));
+  if ((rc = build_tmaps(ds))) return cleanup(rc);
   *out = ds;
   return GPY_OK;
 }
@@ -1029,7 +1091,7 @@ int gpy_dataset_destroy(gpy_dataset_t* ds) {
   if (!ds) return GPY_OK;
   cudaSetDevice(ds->ctx->device);
   cudaStreamSynchronize(ds->ctx->stream);
-  for (DevBuf* b : {&ds->d_edges, &ds->d_nodes, &ds->d_ecenter, &ds->d_edisp, &ds->d_band, &ds->d_pdfc, &ds->d_omega, &ds->d_kflip,
+  for (DevBuf* b : {&ds->d_edges, &ds->d_nodes, &ds->d_ecenter, &ds->d_edisp, &ds->d_band, &ds->d_pdfc, &ds->d_tmaps, &ds->d_omega, &ds->d_kflip,
                     &ds->d_planes})
     b->release();
   for (auto& src : ds->sources)
@@ -1037,6 +1099,7 @@ int gpy_dataset_destroy(gpy_dataset_t* ds) {
       sl.w.release();
       sl.conv.release();
     }
+  for (auto& b : ds->retired_tmaps) b.release();
   ds->ctx->tiles_for.clear();
   delete ds;
   return GPY_OK;
@@ -1045,7 +1108,8 @@ int gpy_dataset_destroy(gpy_dataset_t* ds) {
 int gpy_dataset_set_counts(gpy_dataset_t* ds, const float* counts_device) {
   if (!ds) return fail(GPY_ERR_INVALID, "NULL dataset");
   ds->counts = counts_device;
-  return GPY_OK;
+  cudaStreamSynchronize(ds->ctx->stream);
+  return build_tmaps(ds);
 }
 
 int gpy_dataset_set_models(gpy_dataset_t* ds, const gpy_source_desc* sources, int32_t n_sources,

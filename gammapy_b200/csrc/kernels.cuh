@@ -396,6 +396,7 @@ struct DatasetDev {
   int pdfc_rows;            // total rows (of 8 doubles) in pdfc
   int pad2_;
   const double* ecenter;    // [nR]
+  const void* tmaps;        // 4 CUtensorMap (exposure, background, counts, mask; 128 B each) or null: 1-D bulk copies
 };
 
 struct InstDev {  // one source in one parameter vector
@@ -736,6 +737,14 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+
 // ---- per-item work descriptors --------------------------------------------------------------------------
 // prep_items_kernel (one warp per (tile, vector) item, after K0) resolves everything an item needs besides the
 // data cubes: the sources whose cutout overlaps the tile (first kFoldLMax as InstDev copies + their spectral
@@ -878,7 +887,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const DatasetDev& D = P.ds[P.tile_ds[tile]];
     const int p0 = (tile - D.tile_begin) * kFoldTPX;
     const int npx = min(kFoldTPX, (int)D.P - p0);
-    mbar_arrive_expect_tx(&bars[0], (uint32_t)npx * 4u * (uint32_t)D.nT);
+    if (!D.tmaps) mbar_arrive_expect_tx(&bars[0], (uint32_t)npx * 4u * (uint32_t)D.nT);
   };
   auto issue_expo = [&](int item) {
     const int tile = item / P.B;
@@ -886,6 +895,13 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const int p0 = (tile - D.tile_begin) * kFoldTPX;
     const int npx = min(kFoldTPX, (int)D.P - p0);
     const uint32_t row = (uint32_t)npx * 4u;
+    if (D.tmaps) {  // one 2-D tensor copy of the whole [nT][128] box (out-of-range columns are zero filled)
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&bars[0], (uint32_t)kFoldTPX * 4u * (uint32_t)D.nT);
+        tma_load_2d(es, D.tmaps, p0, 0, &bars[0], pol_stream);
+      }
+      return;
+    }
     const int t = (tid & 31) * (kFoldThreads / 32) + (tid >> 5);  // row handled by this lane
     if (t < D.nT) bulk_g2s_hint(es + t * kFoldTPX, D.exposure + (size_t)t * D.P + p0, row, &bars[0], pol_stream);
     for (int t2 = t + kFoldThreads; t2 < D.nT; t2 += kFoldThreads)
@@ -898,6 +914,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const int npx = min(kFoldTPX, (int)D.P - p0);
     const uint32_t row = (uint32_t)npx * 4u;
     uint32_t total = 0;
+    if (D.tmaps) return;  // armed together with the tensor copies, after the barrier
     if (D.background && P.include_background) total += row * (uint32_t)D.nR;
     if (D.counts) total += row * (uint32_t)D.nR;
     if (D.counts && D.mask) total += (uint32_t)npx * (uint32_t)D.nR;
@@ -910,6 +927,20 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const int npx = min(kFoldTPX, (int)D.P - p0);
     const uint32_t row = (uint32_t)npx * 4u;
     const bool has_bkg = D.background && P.include_background;
+    if (D.tmaps) {
+      if (tid == 0) {
+        const unsigned char* tm = reinterpret_cast<const unsigned char*>(D.tmaps);
+        uint32_t total = 0;
+        if (has_bkg) total += (uint32_t)kFoldTPX * 4u * (uint32_t)D.nR;
+        if (D.counts) total += (uint32_t)kFoldTPX * 4u * (uint32_t)D.nR;
+        if (D.counts && D.mask) total += (uint32_t)kFoldTPX * (uint32_t)D.nR;
+        mbar_arrive_expect_tx(&bars[1], total);
+        if (has_bkg) tma_load_2d(bs, tm + 128, p0, 0, &bars[1], pol_stream);
+        if (D.counts) tma_load_2d(cs, tm + 256, p0, 0, &bars[1], pol_stream);
+        if (D.counts && D.mask) tma_load_2d(ms, tm + 384, p0, 0, &bars[1], pol_stream);
+      }
+      return;
+    }
     // copy index i = 3 r + which, spread over (lane, warp) like the exposure rows
     for (int i = (tid & 31) * (kFoldThreads / 32) + (tid >> 5); i < 3 * D.nR; i += kFoldThreads) {
       const int r = i / 3, which = i - 3 * r;
