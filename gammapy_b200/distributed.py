@@ -89,12 +89,14 @@ class ShardedDatasets:
             D = len(eng.datasets)
             if self._buf is None or self._buf.shape != (B, D):
                 self._buf = torch.zeros(B, D, dtype=torch.float64, device=eng.ctx.torch_device)
+                self._host = torch.zeros(B, dtype=torch.float64).pin_memory()
             eng.stat_sum_device(v2, self._buf)
             with torch.cuda.stream(eng.ctx.stream):
-                total = self._buf.sum(dim=1)
-            allreduce_stat(total, eng.ctx.stream)
+                total = self._buf[:, 0] if D == 1 else self._buf.sum(dim=1)
+                allreduce_stat(total, None)  # NCCL enqueues behind the kernels of the current (library) stream
+                self._host.copy_(total, non_blocking=True)
             eng.ctx.stream.synchronize()
-            out = total.cpu().numpy()
+            out = self._host.numpy().copy()
         return float(out[0]) if values.ndim == 1 else out
 
     def stat_sum(self):
