@@ -349,6 +349,10 @@ def run_ours(args):
         line["e2e"]["value"] *= 1  # the public-API loop above evaluates one vector per call
     if rank == 0 and not args.no_extras and not distributed and args.workload.startswith("c3"):
         line["extras"] = extras(engine, datasets, ds, base, cols)
+        try:
+            line["extras"]["fit"] = fit_wall_time(with_cpu=not args.no_cpu_baseline)
+        except Exception as exc:
+            line["extras"]["fit"] = {"error": repr(exc)}
     if rank == 0 and not args.no_cpu_baseline and not distributed:
         try:
             dt, sample, kind = cpu_evals(ds, steps=3, warmup=1)
@@ -400,6 +404,45 @@ def extras(engine, datasets, ds, base, cols):
     sd = torch.zeros(B, 1, dtype=torch.float64, device=ctx.torch_device)
     ms = timed(lambda k: engine.stat_sum_device(grid, sd), 3)
     out["batched_scan"] = {"vectors_per_launch": B, "ms_per_launch": ms, "vectors_per_s": B * 1e3 / ms}
+    return out
+
+
+def fit_wall_time(with_cpu=True):
+    """BASELINE.json metric (iii): wall time of a full Cash fit of the C1 dataset (analysis_3d shape, 6 free
+    parameters: lon_0, lat_0, sigma, index, amplitude, background norm), same optimiser (batched BFGS + Hesse in
+    factor space) on the GPU likelihood and on the CPU oracle."""
+    from gammapy_b200 import Datasets, Fit, Map, configs
+    from oracle import adapter
+
+    def perturb(ds):
+        m = ds.models["model-simu"]
+        m.spatial_model.lon_0.value, m.spatial_model.lat_0.value, m.spatial_model.sigma.value = 0.23, 0.08, 0.27
+        m.spectral_model.index.value, m.spectral_model.amplitude.value = 2.8, 1.3e-11
+        ds.background_model.spectral_model.norm.value = 1.05
+
+    ds = configs.make_c1(name="c1-fit")
+    ds.fake(random_state=0)
+    datasets = Datasets([ds])
+    perturb(ds)
+    datasets.stat_sum()  # device mirror + first (cold) evaluation outside the timed fit, as for the CPU arm
+    t0 = time.perf_counter()
+    res = Fit().run(datasets)
+    gpu_s = time.perf_counter() - t0
+    out = {"workload": "C1: 200x200 px, 10/20 energy bins, Gaussian x PowerLaw + background, 6 free parameters",
+           "gpu_fit_s": gpu_s, "gpu_nfev": int(res.nfev), "gpu_success": bool(res.success),
+           "gpu_total_stat": float(res.total_stat)}
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from tests.test_gpu_fit import OracleDatasets
+
+        de = adapter.evaluator_for(ds, conv="fft32")
+        perturb(ds)
+        od = OracleDatasets(ds, de)
+        od._get_engine().stat_sum()
+        t0 = time.perf_counter()
+        res_c = Fit().run(od)
+        out.update({"cpu_fit_s": time.perf_counter() - t0, "cpu_nfev": int(res_c.nfev), "cpu_success": bool(res_c.success),
+                    "cpu_total_stat": float(res_c.total_stat), "cpu_cores": os.cpu_count()})
     return out
 
 
