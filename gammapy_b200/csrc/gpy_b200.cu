@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -254,7 +255,7 @@ struct gpy_context {
   size_t pinned_cap = 0;
   cudaEvent_t h2d_done = nullptr;
   bool h2d_pending = false;
-  DevBuf zeros, desc, staging, flux, partials, stat, tiles, scratch_a, scratch_b, scratch_c;
+  DevBuf zeros, desc, dedup, staging, flux, partials, stat, tiles, scratch_a, scratch_b, scratch_c;
   std::vector<gpy_dataset*> tiles_for;  // dataset list the tile table was built for
   std::vector<uint64_t> tiles_ver;
   double* stat_pinned = nullptr;
@@ -263,6 +264,7 @@ struct gpy_context {
   int tma_blocks_per_sm[2] = {0, 0};
   int num_sms = 0;
   bool force_generic = false;
+  bool no_dedup = false;  // GPY_NO_DEDUP: evaluate every item of a batch even when identical to vector 0's
   int fold_mode = 0;  // GPY_FOLD_KERNEL: 0 auto (bulk-copy staged kernel when eligible), 2 generic
   double log_trunc = 0.0;
   int max_smem_optin = 0;
@@ -623,6 +625,12 @@ int check_par(int idx, int n_par, const char* what) {
   return GPY_OK;
 }
 
+struct FluxKey {  // (dataset, source) + the bit patterns of the spectral parameters
+  uint64_t source;
+  uint64_t p[5];
+  bool operator<(const FluxKey& o) const { return std::memcmp(this, &o, sizeof(FluxKey)) < 0; }
+};
+
 // Build descriptors, refresh spatial caches, launch K0 + fused fold/Cash + reduction.
 // Leaves stat[b * D + d] in c->stat (device).
 int evaluate(gpy_context* c, const EvalRequest& rq) {
@@ -637,6 +645,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   std::vector<gpy::InstDev> insts;
   std::vector<gpy::FluxJob> jobs;
   std::vector<size_t> job_flux_off;
+  std::map<FluxKey, size_t> flux_seen;
   size_t flux_len = 0;
   int n_tiles = 0, max_inst = 1;
   int max_nT = 0, max_nR = 0, max_nRp = 0, max_G = 0, max_pdfc_rows = 1;
@@ -769,22 +778,34 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         in.pitch = slot->pitch;
         in.planes = slot->planes;
         in.group = (src.desc.apply_edisp || !ds->has_diag) ? 0 : 1;
-        in.flux_off = (int)flux_len;
         in.plane_stride = slot->planes == 1 ? 0 : rect.cy * slot->pitch;
         in.conv = (const float*)(slot->planes == 1 ? slot->w.p : slot->conv.p);
+        // Equal spectral tuples of one source across the vectors of a batch share one flux vector: K0 integrates it
+        // once and the item signatures (prep_items_kernel) can tell that two vectors see the same source.
+        FluxKey key;
+        std::memset(&key, 0, sizeof(key));
+        key.source = ((uint64_t)d << 32) | (uint64_t)si;
+        std::memcpy(key.p, sc, sizeof(key.p));
+        auto hit = B > 1 ? flux_seen.find(key) : flux_seen.end();
+        if (hit != flux_seen.end()) {
+          in.flux_off = (int)hit->second;
+        } else {
+          in.flux_off = (int)flux_len;
+          if (B > 1) flux_seen.emplace(key, flux_len);
+          gpy::FluxJob job;
+          std::memset(&job, 0, sizeof(job));
+          job.type = src.desc.spectral_type;
+          job.n_bins = ds->nT;
+          job.n_nodes = ds->n_nodes;
+          job.sanitize = 1;
+          for (int k = 0; k < 5; ++k) job.p[k] = sc[k];
+          job.edges = (const double*)ds->d_edges.p;
+          job.nodes = (const double*)ds->d_nodes.p;
+          jobs.push_back(job);
+          job_flux_off.push_back(flux_len);
+          flux_len += ds->nT;
+        }
         insts.push_back(in);
-        gpy::FluxJob job;
-        std::memset(&job, 0, sizeof(job));
-        job.type = src.desc.spectral_type;
-        job.n_bins = ds->nT;
-        job.n_nodes = ds->n_nodes;
-        job.sanitize = 1;
-        for (int k = 0; k < 5; ++k) job.p[k] = sc[k];
-        job.edges = (const double*)ds->d_edges.p;
-        job.nodes = (const double*)ds->d_nodes.p;
-        jobs.push_back(job);
-        job_flux_off.push_back(flux_len);
-        flux_len += ds->nT;
       }
       ev.inst_count = (int)insts.size() - ev.inst_begin;
       max_inst = std::max(max_inst, ev.inst_count);
@@ -875,7 +896,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   }
   fp.zeros = (const float*)c->zeros.p;
   const size_t n_items = (size_t)B * n_tiles;
-  int per_tile = 1;
+  const unsigned char* reduce_dup = nullptr;
   const int variant = rq.npred_out ? 1 : 0;
   if (tma_ok) {
     const gpy::DescLayout dl = gpy::desc_layout(max_nT, max_nRp);
@@ -891,7 +912,34 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     pp.n_tiles = n_tiles;
     pp.max_nT = max_nT;
     pp.max_nRp = max_nRp;
-    gpy::prep_items_kernel<<<(unsigned)((n_items + 7) / 8), 256, 0, c->stream>>>(pp);
+    // B > 1: evaluate each distinct (tile, vector) item once (see dedup_*_kernel)
+    const bool dedup = B > 1 && !c->no_dedup;
+    pp.sig = nullptr;
+    pp.work = nullptr;
+    pp.n_work = nullptr;
+    const unsigned item_blocks = (unsigned)((n_items + 7) / 8);
+    if (dedup) {
+      const size_t o_work = n_items * 8, o_cnt = o_work + n_items * 4, o_off = o_cnt + (size_t)n_tiles * 4,
+                   o_n = o_off + (size_t)n_tiles * 4, o_dup = o_n + 16;
+      GPY_TRY(c->dedup.reserve(o_dup + n_items, c->stream));
+      uint8_t* q = (uint8_t*)c->dedup.p;
+      pp.sig = (unsigned long long*)q;
+      int* work = (int*)(q + o_work);
+      int* cnt = (int*)(q + o_cnt);
+      int* off = (int*)(q + o_off);
+      int* n_work = (int*)(q + o_n);
+      unsigned char* dup = q + o_dup;
+      const unsigned tb = (unsigned)((n_tiles + 255) / 256);
+      gpy::item_signature_kernel<<<item_blocks, 256, 0, c->stream>>>(pp);
+      gpy::dedup_count_kernel<<<tb, 256, 0, c->stream>>>(pp.sig, B, n_tiles, cnt);
+      gpy::dedup_scan_kernel<<<1, 1024, 0, c->stream>>>(cnt, n_tiles, off, n_work);
+      gpy::dedup_scatter_kernel<<<tb, 256, 0, c->stream>>>(pp.sig, off, B, n_tiles, work, dup);
+      c->launches += 4;
+      pp.work = fp.work = work;
+      pp.n_work = fp.n_work = n_work;
+      reduce_dup = dup;
+    }
+    gpy::prep_items_kernel<<<item_blocks, 256, 0, c->stream>>>(pp);
     c->launches++;
     fp.desc = (const unsigned char*)c->desc.p;
     auto kern = variant ? gpy::fold_cash_tma_kernel<true> : gpy::fold_cash_tma_kernel<false>;
@@ -918,7 +966,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   }
   c->launches++;
   gpy::reduce_stat_kernel<<<dim3(B, D), 256, 0, c->stream>>>((const double*)c->partials.p, fp.ds, n_tiles, D,
-                                                              per_tile, (double*)c->stat.p);
+                                                              B, reduce_dup, (double*)c->stat.p);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return GPY_OK;
@@ -960,6 +1008,7 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
   c->force_generic = std::getenv("GPY_FORCE_GENERIC_FOLD") != nullptr;
+  c->no_dedup = std::getenv("GPY_NO_DEDUP") != nullptr;
   if (const char* m = std::getenv("GPY_FOLD_KERNEL")) c->fold_mode = std::atoi(m);
   if (c->fold_mode == 2) c->force_generic = true;
   {
@@ -978,7 +1027,7 @@ int gpy_finalize(gpy_context_t* c) {
   if (!c) return GPY_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->zeros, &c->desc, &c->staging, &c->flux, &c->partials, &c->stat, &c->tiles, &c->scratch_a, &c->scratch_b, &c->scratch_c})
+  for (DevBuf* b : {&c->zeros, &c->desc, &c->dedup, &c->staging, &c->flux, &c->partials, &c->stat, &c->tiles, &c->scratch_a, &c->scratch_b, &c->scratch_c})
     b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->stat_pinned) cudaFreeHost(c->stat_pinned);

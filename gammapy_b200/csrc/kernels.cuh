@@ -429,6 +429,8 @@ struct FoldParams {
   int smem_nT, smem_nR, smem_nRp, smem_G;  // largest axes of the launch: fixed shared-memory layout (bulk-copy kernel)
   int smem_pdfc_rows, pad3_;
   const unsigned char* desc;  // [B * n_tiles][desc_layout(smem_nT, smem_nRp).bytes] item descriptors (prep_items_kernel)
+  const int* work;          // [*n_work] item indices to evaluate, or null: all B * n_tiles items (B == 1)
+  const int* n_work;
   const float* zeros;       // >= 16 bytes of zeros: load target of (thread, source) pairs outside the cutout
   int pad_;
   double log_trunc;         // log((double)(float)1e-25): Cython narrows the constant to C float
@@ -745,6 +747,69 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0,
       : "memory");
 }
 
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {  // splitmix64 finaliser
+  x ^= x >> 30;
+  x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27;
+  x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+
+// ---- batched calls: evaluate every distinct item once ----------------------------------------------------------
+// In a profile scan or a finite-difference gradient most (tile, vector) items are identical to the item of vector 0
+// on the same tile (the varied source does not reach the tile).  prep_items_kernel writes a 64-bit signature of
+// everything an item depends on; the three kernels below build, in a deterministic order, the list of items that
+// differ from vector 0, and reduce_stat_kernel reads the partial of (tile, 0) for the others.
+__global__ void __launch_bounds__(256)
+dedup_count_kernel(const unsigned long long* __restrict__ sig, int B, int n_tiles, int* __restrict__ count) {
+  const int tile = blockIdx.x * 256 + threadIdx.x;
+  if (tile >= n_tiles) return;
+  const unsigned long long s0 = sig[(size_t)tile * B];
+  int n = 1;
+  for (int b = 1; b < B; ++b) n += sig[(size_t)tile * B + b] != s0;
+  count[tile] = n;
+}
+
+__global__ void __launch_bounds__(1024) dedup_scan_kernel(const int* __restrict__ count, int n_tiles, int* __restrict__ offset,
+                                                          int* __restrict__ n_work) {
+  __shared__ int sm[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_tiles; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n_tiles ? count[i] : 0;
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+      const int add = threadIdx.x >= o ? sm[threadIdx.x - o] : 0;
+      __syncthreads();
+      sm[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (i < n_tiles) offset[i] = carry + sm[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sm[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_work = carry;
+}
+
+__global__ void __launch_bounds__(256)
+dedup_scatter_kernel(const unsigned long long* __restrict__ sig, const int* __restrict__ offset, int B, int n_tiles,
+                     int* __restrict__ work, unsigned char* __restrict__ dup) {
+  const int tile = blockIdx.x * 256 + threadIdx.x;
+  if (tile >= n_tiles) return;
+  const unsigned long long s0 = sig[(size_t)tile * B];
+  int pos = offset[tile];
+  for (int b = 0; b < B; ++b) {
+    const bool unique = b == 0 || sig[(size_t)tile * B + b] != s0;
+    dup[(size_t)tile * B + b] = unique ? 0 : 1;
+    if (unique) work[pos++] = tile * B + b;
+  }
+}
+
 // ---- per-item work descriptors --------------------------------------------------------------------------
 // prep_items_kernel (one warp per (tile, vector) item, after K0) resolves everything an item needs besides the
 // data cubes: the sources whose cutout overlaps the tile (first kFoldLMax as InstDev copies + their spectral
@@ -773,12 +838,52 @@ struct PrepParams {
   const InstDev* insts;
   const double* flux;
   unsigned char* desc;  // [B * n_tiles][desc bytes]
+  unsigned long long* sig;  // item_signature_kernel: [B * n_tiles] content signature of every item
+  const int* work;          // prep_items_kernel: items to describe ([*n_work]), or null: all of them
+  const int* n_work;
   int B, n_tiles, max_nT, max_nRp;
 };
 
-__global__ void __launch_bounds__(256) prep_items_kernel(const PrepParams P) {
+// One warp per item: 64-bit order-independent signature of everything the item's result depends on besides the
+// dataset's own cubes: for every source overlapping the tile its PSF-convolved cube (pointer; a cube belongs to one
+// spatial tuple and one cutout), flux vector (offset; the host shares equal spectral tuples) and edisp group, and
+// the background parameters.
+__global__ void __launch_bounds__(256) item_signature_kernel(const PrepParams P) {
   const int lane = threadIdx.x & 31;
   const long long item = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+  if (item >= (long long)P.B * P.n_tiles) return;
+  const int b = (int)(item % P.B);
+  const int tile = (int)(item / P.B);
+  const int d = P.tile_ds[tile];
+  const DatasetDev& D = P.ds[d];
+  const EvalDev ev = P.evals[(size_t)d * P.B + b];
+  const long long pix0 = (long long)(tile - D.tile_begin) * kFoldTPX;
+  const int npx = (int)min((long long)kFoldTPX, D.P - pix0);
+  const int y_first = (int)(pix0 / D.nx), y_last = (int)((pix0 + npx - 1) / D.nx);
+  const int x_first = (int)(pix0 % D.nx), x_last = (int)((pix0 + npx - 1) % D.nx);
+  unsigned long long h = 0;
+  for (int i = lane; i < ev.inst_count; i += 32) {
+    const InstDev in = P.insts[ev.inst_begin + i];
+    bool ov = in.y0 <= y_last && in.y0 + in.cy > y_first;
+    if (ov && y_first == y_last) ov = in.x0 <= x_last && in.x0 + in.cx > x_first;
+    if (ov)
+      h += mix64((unsigned long long)in.conv ^ mix64(((unsigned long long)(unsigned)in.flux_off << 8) ^ (unsigned)in.group));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  if (ev.bkg_enabled)
+    h += mix64(__double_as_longlong(ev.bkg_norm)) + mix64(__double_as_longlong(ev.bkg_tilt) ^ 0x9e37ull) +
+         mix64(__double_as_longlong(ev.bkg_ref) ^ 0x79b9ull);
+  if (lane == 0) P.sig[item] = h;
+}
+
+__global__ void __launch_bounds__(256) prep_items_kernel(const PrepParams P) {
+  const int lane = threadIdx.x & 31;
+  long long item = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+  if (P.work) {
+    if (item >= *P.n_work) return;
+    item = P.work[item];
+  }
   if (item >= (long long)P.B * P.n_tiles) return;
   const DescLayout L = desc_layout(P.max_nT, P.max_nRp);
   unsigned char* out = P.desc + (size_t)item * L.bytes;
@@ -956,7 +1061,9 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     bulk_g2s(desc_s + buf * DL.bytes, P.desc + (size_t)it * DL.bytes, (uint32_t)DL.bytes, &bars[2]);
   };
 
-  int item = blockIdx.x;
+  const int n_work = P.work ? *P.n_work : n_items;
+  int w = blockIdx.x;
+  int item = w < n_work ? (P.work ? P.work[w] : w) : n_items;
   if (item < n_items) {
     if (tid == 0) {
       arm_expo(item);
@@ -980,7 +1087,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   const int q = tid & 31, slot = tid >> 5;   // phase 1: 32 pixel quads x 8 energy slots
   const int pp = tid & 63, cslot = tid >> 6;  // phase 2: 64 pixel pairs x 4 reco-chunk slots
 
-  for (; item < n_items; item += gridDim.x, parity ^= 1u) {
+  for (; item < n_items; parity ^= 1u) {
     const int b = item % P.B;
     const int tile = item / P.B;
     const int d = P.tile_ds[tile];
@@ -988,7 +1095,8 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const int nT = D.nT, nR = D.nR, nRp = D.nRp, G = D.n_groups;
     const int p0 = (tile - D.tile_begin) * kFoldTPX;
     const int npx = min(kFoldTPX, (int)D.P - p0);
-    const int next = item + gridDim.x;
+    w += gridDim.x;
+    const int next = w < n_work ? (P.work ? __ldg(P.work + w) : w) : n_items;  // n_items: no further item
 
     if (d != cur_ds) {  // edisp matrices of this dataset (block-uniform branch)
       for (int i = tid; i < D.pdfc_rows * 8; i += kFoldThreads) pdf_s[i] = D.pdfc[i];
@@ -1199,6 +1307,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
           ((wsum[0] + wsum[1]) + (wsum[2] + wsum[3])) + ((wsum[4] + wsum[5]) + (wsum[6] + wsum[7]));
     GPY_TICK(10);
     if (next < n_items) issue_epi(next);
+    item = next;
     GPY_TICK(11);
   }
 #ifdef GPY_FOLD_TIMING
@@ -1211,13 +1320,17 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
 // Second stage: stat[b, d] = 2 * sum of the tile partials of dataset d, fixed summation order.
 __global__ void __launch_bounds__(256)
 reduce_stat_kernel(const double* __restrict__ partials, const DatasetDev* __restrict__ ds, int n_tiles,
-                   int n_datasets, int per_tile, double* __restrict__ stat) {
+                   int n_datasets, int B, const unsigned char* __restrict__ dup, double* __restrict__ stat) {
   __shared__ double sm[256];
   const int b = blockIdx.x, d = blockIdx.y;
-  const int begin = ds[d].tile_begin * per_tile, n = ds[d].n_tiles * per_tile;
-  n_tiles *= per_tile;
+  const int begin = ds[d].tile_begin, n = ds[d].n_tiles;
   double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += 256) s += partials[(size_t)b * n_tiles + begin + i];
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int tile = begin + i;
+    // items identical to vector 0 on this tile were not evaluated: read the partial of (tile, 0)
+    const int bb = (dup && dup[(size_t)tile * B + b]) ? 0 : b;
+    s += partials[(size_t)bb * n_tiles + tile];
+  }
   sm[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {

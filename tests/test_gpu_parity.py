@@ -576,6 +576,44 @@ def test_batched_joint_datasets(ctx):
         p.value = v
 
 
+def test_batch_items_equal_to_vector_zero_are_shared(ctx):
+    """In a scan most (tile, vector) items equal vector 0's and are evaluated once (dedup_*_kernel): the batch must
+    be bit-identical to the per-vector calls, whichever vector carries the change, and when nothing changes."""
+    from gammapy_b200 import Datasets, Map, configs
+    from oracle import adapter
+
+    ds = configs.make_c3(width=(8.0, 5.0), n_sources=6, n_reco=10, n_true=20)
+    ds.counts = Map.from_geom(ds._geom, data=adapter.evaluator_for(ds).fake(21), dtype=float)
+    datasets = Datasets([ds])
+    values, plist = datasets.parameter_vector()
+    names = [m.name for m in ds.models if m.name != ds.background_model.name]
+    a, b = ds.models[names[0]], ds.models[names[3]]
+    cols = {id(p): i for i, p in enumerate(plist)}
+    grid = np.tile(values, (9, 1))
+    grid[1, cols[id(a.spectral_model.amplitude)]] *= 1.3          # one source, spectral only
+    grid[2, cols[id(b.spectral_model.amplitude)]] *= 0.0          # source switched off (amplitude == 0)
+    grid[3, cols[id(b.spatial_model.lon_0)]] += 0.03              # one source, spatial
+    grid[4, cols[id(ds.background_model.spectral_model.norm)]] *= 1.05   # every tile differs
+    grid[5] = grid[1]                                             # same change twice: shares the flux vector
+    grid[6, cols[id(a.spectral_model.amplitude)]] *= 1.3
+    grid[6, cols[id(b.spatial_model.lon_0)]] += 0.03              # two changes at once
+    # 7, 8: identical to vector 0
+    batch = datasets.stat_sum_batch(grid)
+    assert batch[5] == batch[1] and batch[7] == batch[0] and batch[8] == batch[0]
+    assert len(set(batch[[0, 1, 2, 3, 4, 6]])) == 6
+    for k in range(9):
+        for p, v in zip(plist, grid[k]):
+            p.value = v
+        assert datasets.stat_sum() == batch[k], k
+    for p, v in zip(plist, values):
+        p.value = v
+    # vector 0 is the odd one out: nothing may be shared with it
+    grid2 = np.tile(grid[4], (3, 1))
+    grid2[0] = values
+    batch2 = datasets.stat_sum_batch(grid2)
+    assert batch2[0] == batch[0] and batch2[1] == batch[4] and batch2[2] == batch[4]
+
+
 def test_weighted_cash_dataset(ctx):
     """stat_type='cash_weighted' with a float mask (WeightedCashFitStatistic, fit_statistics.py:301-329)."""
     from gammapy_b200 import Map, MapDataset, configs
