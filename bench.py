@@ -404,6 +404,18 @@ def extras(engine, datasets, ds, base, cols):
     sd = torch.zeros(B, 1, dtype=torch.float64, device=ctx.torch_device)
     ms = timed(lambda k: engine.stat_sum_device(grid, sd), 3)
     out["batched_scan"] = {"vectors_per_launch": B, "ms_per_launch": ms, "vectors_per_s": B * 1e3 / ms}
+    # central-difference gradient over every spectral + position parameter (what Minuit computes each iteration):
+    # vector 0 = the base point, then +-h per parameter; items equal to the base point's are evaluated once
+    gcols = list(cols) + [i for i, p in enumerate(engine.parameters) if p.name in ("lon_0", "lat_0")]
+    grid = np.tile(base, (1 + 2 * len(gcols), 1))
+    for j, cidx in enumerate(gcols):
+        h = 1e-3 * max(abs(base[cidx]), 1.0) if engine.parameters[cidx].name not in ("lon_0", "lat_0") else 1e-3
+        grid[1 + 2 * j, cidx] += h
+        grid[2 + 2 * j, cidx] -= h
+    sd = torch.zeros(grid.shape[0], 1, dtype=torch.float64, device=ctx.torch_device)
+    engine.stat_sum_device(grid, sd)  # builds the PSF-convolved cubes of the displaced positions once
+    ms = timed(lambda k: engine.stat_sum_device(grid, sd), 3)
+    out["fd_gradient"] = {"parameters": len(gcols), "vectors_per_launch": int(grid.shape[0]), "ms_per_gradient": ms}
     return out
 
 

@@ -259,6 +259,7 @@ struct gpy_context {
   std::vector<gpy_dataset*> tiles_for;  // dataset list the tile table was built for
   std::vector<uint64_t> tiles_ver;
   double* stat_pinned = nullptr;
+  int* nwork_pinned = nullptr;  // read-back of the batched worklist length
   size_t stat_pinned_cap = 0;
   size_t fold_smem_set = 0, conv_smem_set = 0, tma_smem_set[2] = {0, 0};
   int tma_blocks_per_sm[2] = {0, 0};
@@ -643,6 +644,8 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   std::vector<gpy::DatasetDev> dsd(D);
   std::vector<gpy::EvalDev> evals((size_t)D * B);
   std::vector<gpy::InstDev> insts;
+  std::vector<int> inst_src;  // source index of every entry of insts
+  std::vector<int> diffs;     // batched calls: see EvalDev::diff_begin
   std::vector<gpy::FluxJob> jobs;
   std::vector<size_t> job_flux_off;
   std::map<FluxKey, size_t> flux_seen;
@@ -806,9 +809,36 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
           flux_len += ds->nT;
         }
         insts.push_back(in);
+        inst_src.push_back((int)si);
       }
       ev.inst_count = (int)insts.size() - ev.inst_begin;
       max_inst = std::max(max_inst, ev.inst_count);
+      ev.differs_all = 0;
+      ev.diff_begin = (int)diffs.size();
+      if (b > 0) {  // which sources differ from vector 0's: merge walk over the two lists (both in source order)
+        const gpy::EvalDev& e0 = evals[(size_t)d * B];
+        ev.differs_all = ev.bkg_enabled != e0.bkg_enabled || std::memcmp(&ev.bkg_norm, &e0.bkg_norm, 3 * sizeof(double)) != 0;
+        int i = e0.inst_begin, j = ev.inst_begin;
+        const int ie = i + e0.inst_count, je = j + ev.inst_count;
+        while (!ev.differs_all && (i < ie || j < je)) {
+          const int si = i < ie ? inst_src[i] : INT32_MAX, sj = j < je ? inst_src[j] : INT32_MAX;
+          if (si == sj) {
+            const gpy::InstDev &p = insts[i], &q = insts[j];
+            if (p.conv != q.conv || p.flux_off != q.flux_off || p.group != q.group || p.x0 != q.x0 || p.y0 != q.y0 ||
+                p.cx != q.cx || p.cy != q.cy) {
+              diffs.push_back(i);
+              diffs.push_back(j);
+            }
+            ++i;
+            ++j;
+          } else if (si < sj) {
+            diffs.push_back(i++);
+          } else {
+            diffs.push_back(j++);
+          }
+        }
+      }
+      ev.diff_count = (int)diffs.size() - ev.diff_begin;
     }
     max_nT = std::max(max_nT, ds->nT);
     max_nR = std::max(max_nR, ds->nR);
@@ -858,6 +888,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   size_t off_ev = pk.add(evals.data(), evals.size() * sizeof(gpy::EvalDev));
   size_t off_in = pk.add(insts.data(), insts.size() * sizeof(gpy::InstDev));
   size_t off_jb = pk.add(jobs.data(), jobs.size() * sizeof(gpy::FluxJob));
+  size_t off_df = pk.add(diffs.data(), diffs.size() * sizeof(int));
   GPY_TRY(ensure_pinned(c, pk.bytes.size()));
   std::memcpy(c->pinned, pk.bytes.data(), pk.bytes.size());
   GPY_TRY(c->staging.reserve(pk.bytes.size()));
@@ -900,45 +931,54 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   const int variant = rq.npred_out ? 1 : 0;
   if (tma_ok) {
     const gpy::DescLayout dl = gpy::desc_layout(max_nT, max_nRp);
-    GPY_TRY(c->desc.reserve(n_items * (size_t)dl.bytes, c->stream));
     gpy::PrepParams pp;
     pp.ds = fp.ds;
     pp.tile_ds = fp.tile_ds;
     pp.evals = fp.evals;
     pp.insts = fp.insts;
     pp.flux = fp.flux;
-    pp.desc = (unsigned char*)c->desc.p;
     pp.B = B;
     pp.n_tiles = n_tiles;
     pp.max_nT = max_nT;
     pp.max_nRp = max_nRp;
     // B > 1: evaluate each distinct (tile, vector) item once (see dedup_*_kernel)
     const bool dedup = B > 1 && !c->no_dedup;
-    pp.sig = nullptr;
     pp.work = nullptr;
     pp.n_work = nullptr;
-    const unsigned item_blocks = (unsigned)((n_items + 7) / 8);
+    unsigned item_blocks = (unsigned)((n_items + 7) / 8);
+    size_t n_work_host = n_items;
     if (dedup) {
-      const size_t o_work = n_items * 8, o_cnt = o_work + n_items * 4, o_off = o_cnt + (size_t)n_tiles * 4,
-                   o_n = o_off + (size_t)n_tiles * 4, o_dup = o_n + 16;
+      const size_t o_cnt = n_items * 4, o_off = o_cnt + (size_t)n_tiles * 4, o_n = o_off + (size_t)n_tiles * 4,
+                   o_dup = o_n + 16;
       GPY_TRY(c->dedup.reserve(o_dup + n_items, c->stream));
       uint8_t* q = (uint8_t*)c->dedup.p;
-      pp.sig = (unsigned long long*)q;
-      int* work = (int*)(q + o_work);
+      int* work = (int*)q;
       int* cnt = (int*)(q + o_cnt);
       int* off = (int*)(q + o_off);
       int* n_work = (int*)(q + o_n);
       unsigned char* dup = q + o_dup;
-      const unsigned tb = (unsigned)((n_tiles + 255) / 256);
-      gpy::item_signature_kernel<<<item_blocks, 256, 0, c->stream>>>(pp);
-      gpy::dedup_count_kernel<<<tb, 256, 0, c->stream>>>(pp.sig, B, n_tiles, cnt);
+      const unsigned tb = (unsigned)((n_tiles + 7) / 8);
+      gpy::dedup_flag_kernel<<<tb, 256, 0, c->stream>>>(fp.ds, fp.tile_ds, fp.evals, fp.insts,
+                                                        (const int*)(base + off_df), B, n_tiles, dup, cnt);
       gpy::dedup_scan_kernel<<<1, 1024, 0, c->stream>>>(cnt, n_tiles, off, n_work);
-      gpy::dedup_scatter_kernel<<<tb, 256, 0, c->stream>>>(pp.sig, off, B, n_tiles, work, dup);
-      c->launches += 4;
+      gpy::dedup_scatter_kernel<<<tb, 256, 0, c->stream>>>(dup, off, B, n_tiles, work);
+      c->launches += 3;
       pp.work = fp.work = work;
       pp.n_work = fp.n_work = n_work;
       reduce_dup = dup;
+      // The worklist length sizes the descriptor buffer and the two grids: one 4-byte read-back (the only host
+      // synchronisation inside a batched call; B == 1 calls stay fully asynchronous).
+      if (!c->nwork_pinned) CUDA_TRY(cudaMallocHost((void**)&c->nwork_pinned, 16));
+      CUDA_TRY(cudaMemcpyAsync(c->nwork_pinned, n_work, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      c->h2d_pending = false;
+      n_work_host = (size_t)c->nwork_pinned[0];
+      if (n_work_host < (size_t)n_tiles || n_work_host > n_items)
+        return fail(GPY_ERR_CUDA, "batched worklist length %zu outside [%d, %zu]", n_work_host, n_tiles, n_items);
+      item_blocks = (unsigned)((n_work_host + 7) / 8);
     }
+    GPY_TRY(c->desc.reserve(n_work_host * (size_t)dl.bytes, c->stream));
+    pp.desc = (unsigned char*)c->desc.p;
     gpy::prep_items_kernel<<<item_blocks, 256, 0, c->stream>>>(pp);
     c->launches++;
     fp.desc = (const unsigned char*)c->desc.p;
@@ -952,7 +992,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, gpy::kFoldThreads, lay.total));
     per_sm = std::max(per_sm, 1);
-    const unsigned grid = (unsigned)std::min(n_items, (size_t)per_sm * c->num_sms);
+    const unsigned grid = (unsigned)std::min(n_work_host, (size_t)per_sm * c->num_sms);
     kern<<<grid, gpy::kFoldThreads, lay.total, c->stream>>>(fp);
   } else {
     if (max_fold_smem > c->fold_smem_set) {
@@ -1031,6 +1071,7 @@ int gpy_finalize(gpy_context_t* c) {
     b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->stat_pinned) cudaFreeHost(c->stat_pinned);
+  if (c->nwork_pinned) cudaFreeHost(c->nwork_pinned);
   if (c->h2d_done) cudaEventDestroy(c->h2d_done);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;

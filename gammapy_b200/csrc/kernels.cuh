@@ -411,7 +411,9 @@ struct InstDev {  // one source in one parameter vector
 
 struct EvalDev {  // one (dataset, parameter vector)
   int inst_begin, inst_count;
-  int bkg_enabled, pad_;
+  int bkg_enabled;
+  int differs_all;             // batched calls: every tile differs from vector 0's (background parameters changed)
+  int diff_begin, diff_count;  // batched calls: indices (into insts) of the sources that differ from vector 0's
   double bkg_norm, bkg_tilt, bkg_ref;
 };
 
@@ -428,7 +430,7 @@ struct FoldParams {
   int max_inst;             // capacity of the per-block overlap list
   int smem_nT, smem_nR, smem_nRp, smem_G;  // largest axes of the launch: fixed shared-memory layout (bulk-copy kernel)
   int smem_pdfc_rows, pad3_;
-  const unsigned char* desc;  // [B * n_tiles][desc_layout(smem_nT, smem_nRp).bytes] item descriptors (prep_items_kernel)
+  const unsigned char* desc;  // [work items][desc_layout(smem_nT, smem_nRp).bytes] item descriptors (prep_items_kernel)
   const int* work;          // [*n_work] item indices to evaluate, or null: all B * n_tiles items (B == 1)
   const int* n_work;
   const float* zeros;       // >= 16 bytes of zeros: load target of (thread, source) pairs outside the cutout
@@ -747,28 +749,44 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0,
       : "memory");
 }
 
-__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {  // splitmix64 finaliser
-  x ^= x >> 30;
-  x *= 0xbf58476d1ce4e5b9ull;
-  x ^= x >> 27;
-  x *= 0x94d049bb133111ebull;
-  x ^= x >> 31;
-  return x;
-}
-
 // ---- batched calls: evaluate every distinct item once ----------------------------------------------------------
 // In a profile scan or a finite-difference gradient most (tile, vector) items are identical to the item of vector 0
-// on the same tile (the varied source does not reach the tile).  prep_items_kernel writes a 64-bit signature of
-// everything an item depends on; the three kernels below build, in a deterministic order, the list of items that
-// differ from vector 0, and reduce_stat_kernel reads the partial of (tile, 0) for the others.
+// on the same tile: the varied source does not reach the tile.  The host lists, per vector, the sources that differ
+// from vector 0's (EvalDev::diff_*: another PSF-convolved cube, flux vector or edisp group, or present in one of the
+// two only); an item is a duplicate when none of them overlaps its tile and the background parameters are equal.
+// The kernels below flag the duplicates and build, in a deterministic order, the list of items to evaluate;
+// reduce_stat_kernel reads the partial of (tile, 0) for the duplicates.
 __global__ void __launch_bounds__(256)
-dedup_count_kernel(const unsigned long long* __restrict__ sig, int B, int n_tiles, int* __restrict__ count) {
-  const int tile = blockIdx.x * 256 + threadIdx.x;
+dedup_flag_kernel(const DatasetDev* __restrict__ ds, const int* __restrict__ tile_ds, const EvalDev* __restrict__ evals,
+                  const InstDev* __restrict__ insts, const int* __restrict__ diffs, int B, int n_tiles,
+                  unsigned char* __restrict__ dup, int* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int tile = (int)(((long long)blockIdx.x * 256 + threadIdx.x) >> 5);  // one warp per tile
   if (tile >= n_tiles) return;
-  const unsigned long long s0 = sig[(size_t)tile * B];
-  int n = 1;
-  for (int b = 1; b < B; ++b) n += sig[(size_t)tile * B + b] != s0;
-  count[tile] = n;
+  const int d = tile_ds[tile];
+  const DatasetDev& D = ds[d];
+  const long long pix0 = (long long)(tile - D.tile_begin) * kFoldTPX;
+  const int npx = (int)min((long long)kFoldTPX, D.P - pix0);
+  const int y_first = (int)(pix0 / D.nx), y_last = (int)((pix0 + npx - 1) / D.nx);
+  const int x_first = (int)(pix0 % D.nx), x_last = (int)((pix0 + npx - 1) % D.nx);
+  int n = 0;
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    const int b = b0 + lane;
+    bool unique = false;
+    if (b < B) {
+      const EvalDev& ev = evals[(size_t)d * B + b];
+      unique = b == 0 || ev.differs_all;
+      for (int k = 0; k < ev.diff_count && !unique; ++k) {
+        const InstDev& in = insts[diffs[ev.diff_begin + k]];
+        bool ov = in.y0 <= y_last && in.y0 + in.cy > y_first;
+        if (ov && y_first == y_last) ov = in.x0 <= x_last && in.x0 + in.cx > x_first;
+        unique = ov;
+      }
+      dup[(size_t)tile * B + b] = unique ? 0 : 1;
+    }
+    n += __popc(__ballot_sync(0xffffffffu, unique));
+  }
+  if (lane == 0) count[tile] = n;
 }
 
 __global__ void __launch_bounds__(1024) dedup_scan_kernel(const int* __restrict__ count, int n_tiles, int* __restrict__ offset,
@@ -797,16 +815,18 @@ __global__ void __launch_bounds__(1024) dedup_scan_kernel(const int* __restrict_
 }
 
 __global__ void __launch_bounds__(256)
-dedup_scatter_kernel(const unsigned long long* __restrict__ sig, const int* __restrict__ offset, int B, int n_tiles,
-                     int* __restrict__ work, unsigned char* __restrict__ dup) {
-  const int tile = blockIdx.x * 256 + threadIdx.x;
+dedup_scatter_kernel(const unsigned char* __restrict__ dup, const int* __restrict__ offset, int B, int n_tiles,
+                     int* __restrict__ work) {
+  const int lane = threadIdx.x & 31;
+  const int tile = (int)(((long long)blockIdx.x * 256 + threadIdx.x) >> 5);  // one warp per tile, vectors in order
   if (tile >= n_tiles) return;
-  const unsigned long long s0 = sig[(size_t)tile * B];
   int pos = offset[tile];
-  for (int b = 0; b < B; ++b) {
-    const bool unique = b == 0 || sig[(size_t)tile * B + b] != s0;
-    dup[(size_t)tile * B + b] = unique ? 0 : 1;
-    if (unique) work[pos++] = tile * B + b;
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    const int b = b0 + lane;
+    const bool unique = b < B && dup[(size_t)tile * B + b] == 0;
+    const unsigned m = __ballot_sync(0xffffffffu, unique);
+    if (unique) work[pos + __popc(m & ((1u << lane) - 1u))] = tile * B + b;
+    pos += __popc(m);
   }
 }
 
@@ -837,56 +857,19 @@ struct PrepParams {
   const EvalDev* evals;
   const InstDev* insts;
   const double* flux;
-  unsigned char* desc;  // [B * n_tiles][desc bytes]
-  unsigned long long* sig;  // item_signature_kernel: [B * n_tiles] content signature of every item
+  unsigned char* desc;  // [number of work items][desc bytes]
   const int* work;          // prep_items_kernel: items to describe ([*n_work]), or null: all of them
   const int* n_work;
   int B, n_tiles, max_nT, max_nRp;
 };
 
-// One warp per item: 64-bit order-independent signature of everything the item's result depends on besides the
-// dataset's own cubes: for every source overlapping the tile its PSF-convolved cube (pointer; a cube belongs to one
-// spatial tuple and one cutout), flux vector (offset; the host shares equal spectral tuples) and edisp group, and
-// the background parameters.
-__global__ void __launch_bounds__(256) item_signature_kernel(const PrepParams P) {
-  const int lane = threadIdx.x & 31;
-  const long long item = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
-  if (item >= (long long)P.B * P.n_tiles) return;
-  const int b = (int)(item % P.B);
-  const int tile = (int)(item / P.B);
-  const int d = P.tile_ds[tile];
-  const DatasetDev& D = P.ds[d];
-  const EvalDev ev = P.evals[(size_t)d * P.B + b];
-  const long long pix0 = (long long)(tile - D.tile_begin) * kFoldTPX;
-  const int npx = (int)min((long long)kFoldTPX, D.P - pix0);
-  const int y_first = (int)(pix0 / D.nx), y_last = (int)((pix0 + npx - 1) / D.nx);
-  const int x_first = (int)(pix0 % D.nx), x_last = (int)((pix0 + npx - 1) % D.nx);
-  unsigned long long h = 0;
-  for (int i = lane; i < ev.inst_count; i += 32) {
-    const InstDev in = P.insts[ev.inst_begin + i];
-    bool ov = in.y0 <= y_last && in.y0 + in.cy > y_first;
-    if (ov && y_first == y_last) ov = in.x0 <= x_last && in.x0 + in.cx > x_first;
-    if (ov)
-      h += mix64((unsigned long long)in.conv ^ mix64(((unsigned long long)(unsigned)in.flux_off << 8) ^ (unsigned)in.group));
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
-  if (ev.bkg_enabled)
-    h += mix64(__double_as_longlong(ev.bkg_norm)) + mix64(__double_as_longlong(ev.bkg_tilt) ^ 0x9e37ull) +
-         mix64(__double_as_longlong(ev.bkg_ref) ^ 0x79b9ull);
-  if (lane == 0) P.sig[item] = h;
-}
-
 __global__ void __launch_bounds__(256) prep_items_kernel(const PrepParams P) {
   const int lane = threadIdx.x & 31;
-  long long item = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
-  if (P.work) {
-    if (item >= *P.n_work) return;
-    item = P.work[item];
-  }
-  if (item >= (long long)P.B * P.n_tiles) return;
+  const long long w = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;  // position in the worklist = descriptor slot
+  if (w >= (P.work ? (long long)*P.n_work : (long long)P.B * P.n_tiles)) return;
+  const long long item = P.work ? P.work[w] : w;
   const DescLayout L = desc_layout(P.max_nT, P.max_nRp);
-  unsigned char* out = P.desc + (size_t)item * L.bytes;
+  unsigned char* out = P.desc + (size_t)w * L.bytes;
   const int b = (int)(item % P.B);
   const int tile = (int)(item / P.B);
   const int d = P.tile_ds[tile];
@@ -1056,7 +1039,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     }
   };
 
-  auto fetch_desc = [&](int it, uint32_t buf) {  // thread 0: one bulk copy of the item's work descriptor
+  auto fetch_desc = [&](int it, uint32_t buf) {  // thread 0: one bulk copy of work item `it`'s descriptor
     mbar_arrive_expect_tx(&bars[2], (uint32_t)DL.bytes);
     bulk_g2s(desc_s + buf * DL.bytes, P.desc + (size_t)it * DL.bytes, (uint32_t)DL.bytes, &bars[2]);
   };
@@ -1068,7 +1051,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     if (tid == 0) {
       arm_expo(item);
       arm_epi(item);
-      fetch_desc(item, 0);
+      fetch_desc(w, 0);
     }
     __syncthreads();
     issue_expo(item);
@@ -1152,7 +1135,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         if (cbase == 0) mbar_wait(&bars[0], parity);
         if (tid == 0 && cbase + 4 >= nchunks && next < n_items) arm_expo(next);
         __syncthreads();
-        if (!desc_fetched && tid == 0 && next < n_items) fetch_desc(next, parity ^ 1u);
+        if (!desc_fetched && tid == 0 && next < n_items) fetch_desc(w, parity ^ 1u);
         desc_fetched = true;
         if (cbase + 4 >= nchunks && next < n_items) issue_expo(next);
       }
@@ -1205,7 +1188,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         if (tid == 0 && fetch_next) arm_expo(next);
         __syncthreads();
         GPY_TICK(5);
-        if (!desc_fetched && tid == 0 && next < n_items) fetch_desc(next, parity ^ 1u);
+        if (!desc_fetched && tid == 0 && next < n_items) fetch_desc(w, parity ^ 1u);
         desc_fetched = true;
         // exposure tile fully consumed: start fetching the next item's while phase 2 / the epilogue run
         if (fetch_next) issue_expo(next);

@@ -55,11 +55,19 @@ class _Likelihood:
         self.n_launches += 1
         return self.engine.stat_sum()
 
-    def fcn_batch(self, factors, chunk=512):
+    def fcn_batch(self, factors, chunk=512, base=None):
+        """``base``: the point the rows of ``factors`` are small departures from (finite differences).  It rides
+        along as vector 0 of every launch, so that the library evaluates only the tiles on which a row differs
+        from it (the items equal to vector 0's are shared, see ``dedup_*_kernel``); its value is not returned."""
         vals = self.values_from_factors(factors)
         out = np.empty(vals.shape[0], dtype=float)
+        lead = None if base is None else self.values_from_factors(np.asarray(base, dtype=float)[np.newaxis, :])
         for i in range(0, vals.shape[0], chunk):
-            out[i:i + chunk] = np.atleast_1d(self.engine.stat_sum(vals[i:i + chunk]))
+            block = vals[i:i + chunk]
+            if lead is not None:
+                out[i:i + chunk] = np.atleast_1d(self.engine.stat_sum(np.concatenate([lead, block])))[1:]
+            else:
+                out[i:i + chunk] = np.atleast_1d(self.engine.stat_sum(block))
             self.n_launches += 1
         self.n_calls += vals.shape[0]
         return out
@@ -146,7 +154,7 @@ def _gradient(like, x, f0, h, lo, hi):
     for i in range(n):
         pts[2 * i, i] += hp[i]
         pts[2 * i + 1, i] -= hm[i]
-    f = like.fcn_batch(pts)
+    f = like.fcn_batch(pts, base=x)
     fp, fm = f[0::2], f[1::2]
     with np.errstate(divide="ignore", invalid="ignore"):
         g = (fp - fm) / (hp + hm)
@@ -241,7 +249,7 @@ def _hesse(like, x, f0):
             p[i] += si * h[i]
             p[j] += sj * h[j]
             pts.append(p)
-    f = like.fcn_batch(np.array(pts)) if pts else np.zeros(0)
+    f = like.fcn_batch(np.array(pts), base=x) if pts else np.zeros(0)
     like.set_factors(x)
     hess = np.zeros((n, n))
     for i in range(n):
