@@ -35,6 +35,14 @@ WORKLOADS = {
     "c1": dict(desc="analysis_3d shape: 200x200 px, 10 reco / 20 true bins, Gaussian x PowerLaw, 1 vector per launch"),
     "c2": dict(desc="200x200 px, 10 reco / 20 true bins, 5 sources, profile scan of 256 parameter vectors per launch",
                batch=256),
+    # BASELINE.json configs[3]: joint fit of 64 observations sharded over the ranks (strong scaling: 64 / n_gpus each)
+    "c4": dict(desc="joint fit of 64 observations, 200x200 px, 10 reco / 20 true bins, shared Gaussian x PowerLaw source, "
+                    "per-observation background norm, datasets sharded over the GPUs", n_obs=64, geometry={}),
+    "c4-large": dict(desc="joint fit of 64 observations, 1000x250 px, 30 reco / 60 true bins (C3/4 size, 127 MB each), "
+                          "shared Gaussian x PowerLaw source, per-observation background norm, datasets sharded over "
+                          "the GPUs", n_obs=64,
+                     geometry=dict(width=(20.0, 5.0), n_reco=30, n_true=60, e_reco=(0.1, 100.0), e_true=(0.03, 300.0),
+                                   mask_radius=None)),
 }
 
 
@@ -58,6 +66,8 @@ def build_dataset(workload, rank=0):
         return configs.make_c1(name=f"obs-{rank:03d}")
     if workload == "c2":
         return configs.make_c2(name=f"obs-{rank:03d}")
+    if workload.startswith("c4"):  # reference arm: one observation of the joint fit (the CPU path loops over them)
+        return configs.make_c4(n_obs=w["n_obs"], indices=[rank], **w["geometry"])[0]
     rng = np.random.RandomState(1000 + rank)
     kwargs = {}
     if rank > 0:  # other observations of the same field: exposure scale U(0.5, 1.5), pointing offset N(0, 0.5 deg)
@@ -204,9 +214,168 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# C4: joint fit of 64 observations sharded over the ranks (strong scaling), evaluation rate + fit wall time
+# ------------------------------------------------------------------------------------------------------------
+def run_c4(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    torch.cuda.set_device(local_rank)
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    steps = args.steps or 300
+    warmup = 5 if args.warmup is None else max(args.warmup, 3)
+
+    from gammapy_b200 import configs
+    from gammapy_b200.distributed import ShardedDatasets, allreduce_stat, partition
+    from gammapy_b200.modeling import Fit
+
+    w = WORKLOADS[args.workload]
+    n_obs = w["n_obs"]
+    t_build = time.perf_counter()
+    mine = partition([1] * n_obs, world)[rank]
+    datasets, models = configs.make_c4(n_obs=n_obs, indices=mine, return_models=True, **w["geometry"])
+    for i, ds in zip(mine, datasets):
+        ds.fake(random_state=100 + i)  # independent seeds 100 + i
+    sharded = ShardedDatasets(datasets, global_models=models)
+    joint = sharded._get_engine()
+    engine = sharded._local_engine()
+    ctx, stream = engine.ctx, engine.ctx.stream
+    t_build = time.perf_counter() - t_build
+    base = engine.values()
+    col = [i for i, p in enumerate(engine.parameters) if p.name == "index"][0]
+    D = len(engine.datasets)
+    buf = torch.zeros(1, D, dtype=torch.float64, device=ctx.torch_device)
+
+    def step_device(k):
+        v = base.copy()
+        v[col] += 1e-3 if k % 2 == 0 else -1e-3
+        engine.stat_sum_device(v, buf)
+        if distributed:
+            with torch.cuda.stream(stream):
+                total = buf.sum(dim=1)
+            allreduce_stat(total, stream)
+
+    for k in range(warmup):
+        step_device(k)
+    stream.synchronize()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        t_wall = time.perf_counter()
+        ev0.record(stream)
+        for k in range(steps):
+            step_device(k)
+        ev1.record(stream)
+        stream.synchronize()
+        timed_wall = time.perf_counter() - t_wall
+        k = steps
+        while time.perf_counter() - t_wall < 0.4:
+            step_device(k)
+            k += 1
+            if k % 16 == 0:
+                stream.synchronize()
+        stream.synchronize()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+
+    def max_over_ranks(x):
+        if not distributed:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=ctx.torch_device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_per_step = max_over_ranks(ms) / steps
+
+    # end to end: Parameter objects -> joint stat_sum() (H2D descriptors, kernels, all-reduce, D2H), every step
+    par = engine.parameters[col]
+    v0 = par.value
+    for k in range(3):
+        sharded.stat_sum()
+    if distributed:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        par.value = v0 + (1e-3 if k % 2 == 0 else -1e-3)
+        sharded.stat_sum()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / steps)
+    par.value = v0
+
+    # joint fit from a displaced start: 5 source parameters + 64 background norms free
+    fit = None
+    if not args.no_extras:
+        start = {p: p.value for p in joint.parameters}
+        for p in joint.parameters:
+            if p.name == "index":
+                p.value += 0.2
+            elif p.name == "amplitude":
+                p.value *= 1.5
+            elif p.name == "norm":
+                p.value *= 1.1
+        if distributed:
+            dist.barrier()
+        t0 = time.perf_counter()
+        result = Fit().run(sharded)
+        fit_s = max_over_ranks(time.perf_counter() - t0)
+        free = [p for p in joint.parameters if not p.frozen]
+        fit = {"fit_s": fit_s, "nfev": int(result.nfev), "success": bool(result.success),
+               "total_stat": float(result.total_stat), "free_parameters": len(free),
+               "index": [float(free[[p.name for p in free].index("index")].value),
+                         float(free[[p.name for p in free].index("index")].error)],
+               "what": "Fit.run (batched BFGS + Hesse) on ShardedDatasets: every rank runs the optimiser on the "
+                       "all-reduced joint statistic"}
+        for p, v in start.items():
+            p.value = v
+
+    alg_bytes = sum(algorithmic_bytes(ds) for ds in datasets)
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": n_obs * 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "key": args.workload, "observations": n_obs,
+                   "per_gpu": f"{len(mine)} observations on rank 0; one NCCL all-reduce of the joint statistic per step",
+                   "l2": "per-rank inputs exceed the 126 MB L2" if alg_bytes > 2 * 126e6 else "per-rank inputs are L2-resident",
+                   "step": "one joint evaluation (all 64 observations, one parameter vector), shared spectral index moved",
+                   "value_is": "dataset evaluations/s = 64 x joint evaluations/s"},
+        "joint_evals_per_s": 1e3 / ms_per_step,
+        "gpu_launches": int(launches),
+        "clocks": dict(clocks.summary(), timed_region_s=timed_wall),
+        "e2e": {"value": n_obs / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": int(engine.n_par * 8 + D * 400), "d2h_bytes_per_step": 8,
+                "what": "ShardedDatasets.stat_sum() with Parameter objects on the host"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel": "fold_cash_kernel", "duration_us": ms_per_step * 1e3,
+                     "note": "rank 0's shard; duration = whole step incl. the all-reduce"},
+        "setup_s": t_build,
+    }
+    if fit is not None:
+        line["extras"] = {"joint_fit": fit}
+    if rank == 0:
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
 def run_ours(args):
+    if args.workload.startswith("c4"):
+        return run_c4(args)
     import torch
     import torch.distributed as dist
 

@@ -121,16 +121,28 @@ def make_c3(name="c3", width=(40.0, 10.0), n_sources=50, n_reco=30, n_true=60, *
     return ds
 
 
-def make_c4(n_obs=64, seed=100, **kwargs):
+def make_c4(n_obs=64, seed=100, indices=None, return_models=False, **kwargs):
     """Joint fit: ``n_obs`` observations of the C1 field, shared source model, per-dataset background norm,
-    exposure scale U(0.5, 1.5), pointing offsets N(0, 0.5 deg)."""
+    exposure scale U(0.5, 1.5), pointing offsets N(0, 0.5 deg).
+
+    ``indices``: build only these observations (the shard of one rank); the random draws of all ``n_obs`` are
+    made regardless, so observation ``i`` is the same dataset whichever rank builds it.  ``return_models``: also
+    return the models of ALL observations in the global order (shared source, then every background model; for
+    observations not built here a model object without data) -- what ``ShardedDatasets(global_models=...)`` needs."""
     rng = np.random.RandomState(seed)
     shared = c1_models("unused")[0]
-    datasets = []
-    for i in range(n_obs):
+    draws = [(float(rng.uniform(0.5, 1.5)), tuple(rng.normal(0, 0.5, size=2))) for _ in range(n_obs)]
+    keep = set(range(n_obs)) if indices is None else set(int(i) for i in indices)
+    datasets, backgrounds = [], []
+    for i, (scale, offset) in enumerate(draws):
         name = f"obs-{i:03d}"
-        ds = make_dataset(name=name, exposure_scale=float(rng.uniform(0.5, 1.5)),
-                          pointing_offset=tuple(rng.normal(0, 0.5, size=2)), **kwargs)
-        ds.models = [shared, FoVBackgroundModel(dataset_name=name)]
-        datasets.append(ds)
-    return Datasets(datasets)
+        bkg = FoVBackgroundModel(dataset_name=name)
+        backgrounds.append(bkg)
+        if i in keep:
+            ds = make_dataset(name=name, exposure_scale=scale, pointing_offset=offset, **kwargs)
+            ds.models = [shared, bkg]
+            datasets.append(ds)
+    out = Datasets(datasets)
+    if return_models:
+        return out, [shared] + backgrounds
+    return out

@@ -47,60 +47,141 @@ def allreduce_stat(tensor, stream=None):
     return tensor
 
 
+class _JointEngine:
+    """What ``Fit`` needs from an engine (``parameters``, ``values``, ``stat_sum``), over the datasets of ALL ranks.
+
+    The column order is the *global* one: the parameters of ``global_models`` in order, identical on every rank.
+    A rank's own engine knows a subset of them (the shared sources + its own datasets' background models);
+    ``stat_sum`` maps the global vectors to the local columns, evaluates the shard and all-reduces."""
+
+    def __init__(self, owner, global_models):
+        self.owner = owner
+        self.parameters, seen = [], set()
+        for model in global_models:
+            for par in model.parameters:
+                if id(par) not in seen:
+                    seen.add(id(par))
+                    self.parameters.append(par)
+        self.n_par = len(self.parameters)
+        self._local_cols = None
+
+    def values(self):
+        return np.array([p._value for p in self.parameters], dtype=float)
+
+    def local_columns(self):
+        """Global column of every local parameter-vector column."""
+        if self._local_cols is None:
+            where = {id(p): i for i, p in enumerate(self.parameters)}
+            local = self.owner._local_parameters()
+            missing = [p.name for p in local if id(p) not in where]
+            if missing:
+                raise ValueError(f"local parameters missing from the global model list: {missing}")
+            self._local_cols = np.array([where[id(p)] for p in local], dtype=int)
+        return self._local_cols
+
+    def stat_sum(self, values=None):
+        if values is None:
+            values = self.values()
+        values = np.ascontiguousarray(values, dtype=float)
+        v2 = values.reshape(1, -1) if values.ndim == 1 else values
+        if v2.shape[1] != self.n_par:
+            raise ValueError(f"expected {self.n_par} parameter values per vector, got {v2.shape[1]}")
+        out = self.owner._joint_stat(np.ascontiguousarray(v2[:, self.local_columns()]))
+        return float(out[0]) if values.ndim == 1 else out
+
+
 class ShardedDatasets:
     """The local shard of a joint ``Datasets`` plus the collective that completes ``stat_sum``.
 
     Every rank must hold the *same models in the same order* for the shared sources (the parameter vector is
     replicated, as the reference replicates ``models.parameters.free_parameters.value`` to its actors);
-    per-dataset background models live with their dataset and are appended after the shared block.
+    per-dataset background models live with their dataset.
+
+    ``global_models``: the models of ALL datasets of the joint fit in one order that is the same on every rank
+    (the shared sources, then every dataset's background model -- for datasets on other ranks a model object
+    without data).  With it the object is a drop-in for ``Datasets`` in ``Fit.run / optimize / covariance /
+    stat_profile``: every rank runs the same optimiser on the same all-reduced numbers and ends with the same
+    parameters.  Without it only ``stat_sum_batch`` over the local column order is available.
 
     ``local_stat`` is pluggable so the host-side logic can be exercised on CPU with gloo: it maps a
-    ``[B, n_par]`` array to the ``[B]`` local statistic.
+    ``[B, n_local]`` array to the ``[B]`` local statistic; ``local_parameters`` then names its columns.
     """
 
-    def __init__(self, local_datasets, local_stat=None):
+    def __init__(self, local_datasets, local_stat=None, global_models=None, local_parameters=None):
         import torch.distributed as dist
 
         self.datasets = local_datasets
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world_size = dist.get_world_size() if dist.is_initialized() else 1
         self._local_stat = local_stat
+        self._local_pars = local_parameters
         self._engine = None
         self._buf = None
+        self._joint = _JointEngine(self, global_models) if global_models is not None else None
+
+    # ---- Datasets protocol used by Fit -------------------------------------------------------------------
+    @property
+    def parameters(self):
+        from .modeling.parameter import Parameters
+
+        if self._joint is None:
+            raise ValueError("ShardedDatasets needs global_models to expose the joint parameter list")
+        return Parameters(self._joint.parameters)
 
     def _get_engine(self):
+        if self._joint is not None:
+            return self._joint
+        return self._local_engine()
+
+    def _local_engine(self):
         if self._engine is None:
             self._engine = self.datasets._get_engine()
         return self._engine
 
-    def stat_sum_batch(self, values):
-        """Joint statistic of ``values`` ([n_par] or [B, n_par]) over the datasets of ALL ranks."""
+    def _local_parameters(self):
+        if self._local_stat is not None:
+            if self._local_pars is None:
+                raise ValueError("local_stat needs local_parameters to name its columns")
+            return list(self._local_pars)
+        return list(self._local_engine().parameters)
+
+    # ---- evaluation ------------------------------------------------------------------------------------------
+    def _joint_stat(self, v2):
+        """[B, n_local] local-order vectors -> [B] joint statistic (all ranks call this together)."""
         import torch
 
-        values = np.ascontiguousarray(values, dtype=float)
-        v2 = values.reshape(1, -1) if values.ndim == 1 else values
         B = v2.shape[0]
         if self._local_stat is not None:  # CPU / gloo path of the host logic
             t = torch.from_numpy(np.asarray(self._local_stat(v2), dtype=float).reshape(B).copy())
             allreduce_stat(t)
-            out = t.numpy()
-        else:
-            eng = self._get_engine()
-            D = len(eng.datasets)
-            if self._buf is None or self._buf.shape != (B, D):
-                self._buf = torch.zeros(B, D, dtype=torch.float64, device=eng.ctx.torch_device)
-                self._host = torch.zeros(B, dtype=torch.float64).pin_memory()
-            eng.stat_sum_device(v2, self._buf)
-            with torch.cuda.stream(eng.ctx.stream):
-                total = self._buf[:, 0] if D == 1 else self._buf.sum(dim=1)
-                allreduce_stat(total, None)  # NCCL enqueues behind the kernels of the current (library) stream
-                self._host.copy_(total, non_blocking=True)
-            eng.ctx.stream.synchronize()
-            out = self._host.numpy().copy()
+            return t.numpy()
+        eng = self._local_engine()
+        D = len(eng.datasets)
+        if self._buf is None or self._buf.shape != (B, D):
+            self._buf = torch.zeros(B, D, dtype=torch.float64, device=eng.ctx.torch_device)
+            self._host = torch.zeros(B, dtype=torch.float64).pin_memory()
+        eng.stat_sum_device(v2, self._buf)
+        with torch.cuda.stream(eng.ctx.stream):
+            total = self._buf[:, 0] if D == 1 else self._buf.sum(dim=1)
+            allreduce_stat(total, None)  # NCCL enqueues behind the kernels of the current (library) stream
+            self._host.copy_(total, non_blocking=True)
+        eng.ctx.stream.synchronize()
+        return self._host.numpy().copy()
+
+    def stat_sum_batch(self, values):
+        """Joint statistic of ``values`` ([n] or [B, n]) over the datasets of ALL ranks; columns in the global
+        order when ``global_models`` was given, else in the local engine's order."""
+        values = np.ascontiguousarray(values, dtype=float)
+        if self._joint is not None:
+            return self._joint.stat_sum(values)
+        v2 = values.reshape(1, -1) if values.ndim == 1 else values
+        out = self._joint_stat(v2)
         return float(out[0]) if values.ndim == 1 else out
 
     def stat_sum(self):
-        """``Datasets.stat_sum`` of the joint fit with the current local Parameter values."""
+        """``Datasets.stat_sum`` of the joint fit with the current Parameter values."""
+        if self._joint is not None:
+            return self._joint.stat_sum()
         if self._local_stat is not None:
             raise ValueError("stat_sum() needs GPU datasets; use stat_sum_batch(values) with local_stat")
-        return self.stat_sum_batch(self._get_engine().values())
+        return self.stat_sum_batch(self._local_engine().values())

@@ -71,3 +71,79 @@ def test_sharded_stat_sum_gloo_world2():
     for rank, got, single in results:
         assert_allclose(got, want, rtol=1e-13)  # every rank holds the joint statistic
         assert_allclose(single, want[2], rtol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# joint FIT over two ranks: global parameter order with per-dataset background models that live on one rank
+# ---------------------------------------------------------------------------------------------------------
+def _toy_models(n_datasets):
+    from gammapy_b200.modeling.models import FoVBackgroundModel, PowerLawSpectralModel, PointSpatialModel, SkyModel
+
+    shared = SkyModel(spatial_model=PointSpatialModel(lon_0=0.0, lat_0=0.0, frame="galactic"),
+                      spectral_model=PowerLawSpectralModel(index=2.0, amplitude=1e-12, reference=1), name="src")
+    shared.spatial_model.lon_0.frozen = True
+    shared.spatial_model.lat_0.frozen = True
+    backgrounds = [FoVBackgroundModel(dataset_name=f"obs-{i}") for i in range(n_datasets)]
+    return shared, backgrounds
+
+
+def _toy_stat(i, index, amplitude, norm):
+    """Smooth stand-in for dataset i's Cash sum: minimum at index 2.3, amplitude 2e-12, norm 1 + 0.05 i."""
+    return (1 + 0.1 * i) * (50 * (index - 2.3) ** 2 + 30 * (np.log(amplitude / 2e-12)) ** 2
+                            + 400 * (norm - 1 - 0.05 * i) ** 2 + 10 * (index - 2.3) * (norm - 1 - 0.05 * i)) + i
+
+
+def _fit_worker(rank, world, port, n_datasets, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gammapy_b200.modeling import Fit
+
+        shared, backgrounds = _toy_models(n_datasets)
+        mine = partition([1] * n_datasets, world)[rank]
+        # local column order: the shared source's parameters, then the background models of the local datasets
+        local_pars = list(shared.parameters)
+        for i in mine:
+            local_pars += list(backgrounds[i].parameters)
+        names = [p.name for p in local_pars]
+        i_index, i_amp = names.index("index"), names.index("amplitude")
+        norm_cols = [k for k, p in enumerate(local_pars) if p.name == "norm"]
+
+        def local_stat(values):
+            total = np.zeros(values.shape[0])
+            for k, i in enumerate(mine):
+                total += _toy_stat(i, values[:, i_index], values[:, i_amp], values[:, norm_cols[k]])
+            return total
+
+        sharded = ShardedDatasets(None, local_stat=local_stat, global_models=[shared] + backgrounds,
+                                  local_parameters=local_pars)
+        result = Fit().run(sharded)
+        pars = sharded.parameters
+        out.put((rank, result.success, result.total_stat, [p.value for p in pars], [p.error for p in pars],
+                 [p.name for p in pars]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_joint_fit_gloo_world2():
+    world, n_datasets = 2, 5
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fit_worker, args=(r, world, port, n_datasets, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(out.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, ok0, stat0, val0, err0, names), (_, ok1, stat1, val1, err1, _) = results
+    assert ok0 and ok1
+    assert stat0 == stat1 and val0 == val1 and err0 == err1      # both ranks made identical decisions
+    got = dict(zip(names, val0))
+    assert abs(got["index"] - 2.3) < 1e-3
+    assert abs(got["amplitude"] / 2e-12 - 1) < 1e-2
+    norms = [v for n, v in zip(names, val0) if n == "norm"]
+    assert len(norms) == n_datasets
+    assert_allclose(norms, [1 + 0.05 * i for i in range(n_datasets)], atol=2e-3)
+    assert abs(stat0 - sum(range(n_datasets))) < 1e-3
