@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpy_b200.so")
 SOURCES = [os.path.join(CSRC, "gpy_b200.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "kernels.cuh"), os.path.join(HERE, "..", "include", "gpy_b200.h")]
+DEPS = SOURCES + [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "tsmap.cuh"), os.path.join(HERE, "..", "include", "gpy_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -82,6 +82,10 @@ SYMBOLS = {
     "gpy_psf_convolve": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, _P]),
     "gpy_spectral_integral": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, _P]),
     "gpy_solid_angle": (C.c_int, [_P, C.POINTER(GeomDesc), _P]),
+    "gpy_f_cash_root": (C.c_int, [_P, C.c_double, _P, _P, _P, C.c_int64, _P]),
+    "gpy_norm_bounds": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
+    "gpy_ts_map": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, _P,
+                             C.c_double, C.c_int32, C.c_double, _P]),
 }
 
 

@@ -23,6 +23,7 @@
 
 #include "../../include/gpy_b200.h"
 #include "kernels.cuh"
+#include "tsmap.cuh"
 
 namespace {
 
@@ -1329,6 +1330,112 @@ int gpy_weighted_cash_sum(gpy_context_t* c, const double* counts, const double* 
                           double* out) {
   if (!weight && n > 0) return fail(GPY_ERR_INVALID, "NULL weight");
   return cash_common(c, counts, npred, weight, n, out);
+}
+
+static int registry3(gpy_context_t* c, const double* counts, const double* background, const double* model,
+                     int64_t n, double** d_c, double** d_b, double** d_m) {
+  if (n < 0) return fail(GPY_ERR_INVALID, "negative length");
+  if (n > 0 && (!counts || !background || !model)) return fail(GPY_ERR_INVALID, "NULL array");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)std::max<int64_t>(n, 1) * sizeof(double);
+  GPY_TRY(c->scratch_a.reserve(bytes));
+  GPY_TRY(c->scratch_b.reserve(bytes));
+  GPY_TRY(c->scratch_c.reserve(bytes));
+  GPY_TRY(c->stat.reserve(4 * sizeof(double)));
+  if (n > 0) {
+    CUDA_TRY(cudaMemcpyAsync(c->scratch_a.p, counts, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->scratch_b.p, background, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->scratch_c.p, model, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  *d_c = (double*)c->scratch_a.p;
+  *d_b = (double*)c->scratch_b.p;
+  *d_m = (double*)c->scratch_c.p;
+  return GPY_OK;
+}
+
+int gpy_f_cash_root(gpy_context_t* c, double x, const double* counts, const double* background, const double* model,
+                    int64_t n, double* out) {
+  if (!c || !out) return fail(GPY_ERR_INVALID, "NULL argument to gpy_f_cash_root");
+  double *d_c, *d_b, *d_m;
+  GPY_TRY(registry3(c, counts, background, model, n, &d_c, &d_b, &d_m));
+  gpy::f_cash_root_kernel<<<1, 256, 0, c->stream>>>(x, d_c, d_b, d_m, n, (double*)c->stat.p);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, c->stat.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return GPY_OK;
+}
+
+int gpy_norm_bounds(gpy_context_t* c, const double* counts, const double* background, const double* model, int64_t n,
+                    double* out3) {
+  if (!c || !out3) return fail(GPY_ERR_INVALID, "NULL argument to gpy_norm_bounds");
+  double *d_c, *d_b, *d_m;
+  GPY_TRY(registry3(c, counts, background, model, n, &d_c, &d_b, &d_m));
+  gpy::norm_bounds_kernel<<<1, 256, 0, c->stream>>>(d_c, d_b, d_m, n, (double*)c->stat.p);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out3, c->stat.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return GPY_OK;
+}
+
+int gpy_ts_map(gpy_context_t* c, const double* counts, const double* background, const double* exposure,
+               int32_t n_planes, int32_t ny, int32_t nx, const double* kernel, int32_t ky, int32_t kx,
+               const uint8_t* mask, double rtol, int32_t max_niter, double n_sigma, double* out) {
+  if (!c || !counts || !background || !exposure || !kernel || !out)
+    return fail(GPY_ERR_INVALID, "NULL argument to gpy_ts_map");
+  if (n_planes <= 0 || ny <= 0 || nx <= 0 || ky <= 0 || kx <= 0 || ky % 2 == 0 || kx % 2 == 0)
+    return fail(GPY_ERR_INVALID, "bad shape for gpy_ts_map (kernel sides must be odd)");
+  if (max_niter < 0 || !(rtol >= 4 * std::numeric_limits<double>::epsilon()))
+    return fail(GPY_ERR_INVALID, "rtol too small (%g) or negative maxiter", rtol);  // scipy: ValueError
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t P = (size_t)ny * nx, cube = P * n_planes * sizeof(double);
+  const size_t kbytes = (size_t)n_planes * ky * kx * sizeof(double);
+  DevBuf d_in, d_k, d_mask, d_out;
+  int rc = GPY_OK;
+  auto done = [&](int r) {
+    d_in.release();
+    d_k.release();
+    d_mask.release();
+    d_out.release();
+    return r;
+  };
+  if ((rc = d_in.reserve(3 * cube))) return done(rc);
+  if ((rc = d_k.reserve(kbytes))) return done(rc);
+  if ((rc = d_out.reserve(GPY_TS_PLANES * P * sizeof(double)))) return done(rc);
+  if (mask && (rc = d_mask.reserve(P))) return done(rc);
+  uint8_t* q = (uint8_t*)d_in.p;
+  cudaError_t e = cudaMemcpyAsync(q, counts, cube, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(q + cube, background, cube, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(q + 2 * cube, exposure, cube, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_k.p, kernel, kbytes, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess && mask) e = cudaMemcpyAsync(d_mask.p, mask, P, cudaMemcpyHostToDevice, c->stream);
+  if (e != cudaSuccess) return done(fail(GPY_ERR_CUDA, "TS-map upload failed: %s", cudaGetErrorString(e)));
+  gpy::TsMapParams tp;
+  tp.counts = (const double*)q;
+  tp.background = (const double*)(q + cube);
+  tp.exposure = (const double*)(q + 2 * cube);
+  tp.kernel = (const double*)d_k.p;
+  tp.mask = mask ? (const unsigned char*)d_mask.p : nullptr;
+  tp.out = (double*)d_out.p;
+  tp.n_planes = n_planes;
+  tp.ny = ny;
+  tp.nx = nx;
+  tp.ky = ky;
+  tp.kx = kx;
+  tp.max_niter = max_niter;
+  tp.rtol = rtol;
+  tp.xtol = 2e-12;
+  tp.n_sigma = n_sigma;
+  tp.log_trunc = c->log_trunc;
+  gpy::ts_map_kernel<<<(unsigned)((P + 7) / 8), 256, 0, c->stream>>>(tp);
+  c->launches++;
+  e = cudaGetLastError();
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(out, d_out.p, GPY_TS_PLANES * P * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) return done(fail(GPY_ERR_CUDA, "TS map failed: %s", cudaGetErrorString(e)));
+  return done(GPY_OK);
 }
 
 int gpy_solid_angle(gpy_context_t* c, const gpy_geom_desc* g, double* out) {

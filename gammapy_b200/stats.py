@@ -42,6 +42,32 @@ def weighted_cash_sum_cuda(counts, npred, weight):
     return out.value
 
 
+def f_cash_root_cuda(x, counts, background, model):
+    """f_cash_root_cython (stats/fit_statistics_cython.pyx:90-121): derivative of the Cash statistic wrt the norm."""
+    counts, background, model = _as_f64(counts), _as_f64(background), _as_f64(model)
+    if not (counts.shape == background.shape == model.shape):
+        raise ValueError("counts, background and model must have the same length")
+    ctx = _lib.Context.get()
+    out = C.c_double(0.0)
+    _lib.check(ctx.lib.gpy_f_cash_root(ctx.handle, float(x), counts.ctypes.data_as(C.c_void_p),
+                                       background.ctypes.data_as(C.c_void_p), model.ctypes.data_as(C.c_void_p),
+                                       counts.size, C.byref(out)))
+    return out.value
+
+
+def norm_bounds_cuda(counts, background, model):
+    """norm_bounds_cython (.pyx:124-157): (b_min, b_max, -sn_min_total)."""
+    counts, background, model = _as_f64(counts), _as_f64(background), _as_f64(model)
+    if not (counts.shape == background.shape == model.shape):
+        raise ValueError("counts, background and model must have the same length")
+    ctx = _lib.Context.get()
+    out = (C.c_double * 3)()
+    _lib.check(ctx.lib.gpy_norm_bounds(ctx.handle, counts.ctypes.data_as(C.c_void_p),
+                                       background.ctypes.data_as(C.c_void_p), model.ctypes.data_as(C.c_void_p),
+                                       counts.size, out))
+    return out[0], out[1], out[2]
+
+
 def get_fit_statistics_compiled(backend=None):
     backend = backend or COMPILATION_BACKEND_DEFAULT
     if backend != "cuda":
@@ -50,4 +76,6 @@ def get_fit_statistics_compiled(backend=None):
         "TRUNCATION_VALUE": TRUNCATION_VALUE,
         "cash_sum_compiled": cash_sum_cuda,
         "weighted_cash_sum_compiled": weighted_cash_sum_cuda,
+        "f_cash_root_compiled": f_cash_root_cuda,
+        "norm_bounds_compiled": norm_bounds_cuda,
     }

@@ -157,6 +157,30 @@ int gpy_cash_sum(gpy_context_t* ctx, const double* counts, const double* npred, 
 int gpy_weighted_cash_sum(gpy_context_t* ctx, const double* counts, const double* npred,
                           const double* weight, int64_t n, double* out);
 
+/* f_cash_root_compiled(x, counts, background, model) and norm_bounds_compiled(counts, background, model)
+ * (stats/fit_statistics_cython.pyx:90-157): HOST float64 arrays in, HOST out (1 and 3 doubles:
+ * b_min, b_max, -sn_min_total). */
+int gpy_f_cash_root(gpy_context_t* ctx, double x, const double* counts, const double* background,
+                    const double* model, int64_t n, double* out);
+int gpy_norm_bounds(gpy_context_t* ctx, const double* counts, const double* background,
+                    const double* model, int64_t n, double* out3);
+
+/* TS map: the per-pixel one-parameter fit TSMapEstimator.estimate_flux_map distributes over processes
+ * (estimators/map/ts.py:516-531 -> _ts_value :1098-1153 -> BrentqFluxEstimator.run :1053-1095 with
+ * estimate_best_fit :819-870 on SimpleMapDataset.from_arrays :761-783), default selection, ts_threshold None.
+ *   counts / background / exposure  HOST [n_planes, ny, nx] float64 (reco-energy planes; several datasets of the
+ *                                   same image geometry are concatenated along the plane axis, as _ts_value does)
+ *   kernel                          HOST [n_planes, ky, kx] float64, ky and kx odd
+ *   mask                            HOST [ny, nx] uint8 or NULL: positions to fit (_estimate_mask_2d); others get NaN
+ *   rtol, max_niter                 scipy.optimize.brentq arguments (xtol is scipy's default 2e-12)
+ *   out                             HOST [GPY_TS_PLANES, ny, nx] float64: norm, norm_err, niter, ts, stat, stat_null,
+ *                                   success, npred, npred_excess
+ * Cutout bins outside the map are absent, which is what the reference's zero padding amounts to (:772-777). */
+#define GPY_TS_PLANES 9
+int gpy_ts_map(gpy_context_t* ctx, const double* counts, const double* background, const double* exposure,
+               int32_t n_planes, int32_t ny, int32_t nx, const double* kernel, int32_t ky, int32_t kx,
+               const uint8_t* mask, double rtol, int32_t max_niter, double n_sigma, double* out);
+
 /* Single-stage entry points (the parity tests exercise each kernel through these).
  * SpatialModel.integrate_geom on an image geometry (modeling/models/spatial.py:222-309, 609-631):
  *   spatial_params HOST in the class order above; out HOST [ny, nx] float32 (the value the PSF
