@@ -214,6 +214,58 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# TS map: per-pixel norm fits of a C3-sized image, GPU launch vs the oracle on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def ts_map_inputs(ny=500, nx=2000, k=41, seed=5):
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[:ny, :nx]
+    g = np.exp(-0.5 * ((np.arange(k) - k // 2) / 4.0) ** 2)   # PSF-like kernel, sigma 0.08 deg at 0.02 deg pixels
+    kernel = (np.outer(g, g) / np.outer(g, g).sum())[None]
+    exposure = (1e3 * np.exp(-0.5 * ((yy - ny / 2) / (0.6 * ny)) ** 2))[None]
+    background = (1.5 + np.cos(xx / 150.0) ** 2)[None]
+    counts = rng.poisson(background).astype(float)
+    for _ in range(200):  # point sources
+        j, i = rng.randint(k, ny - k), rng.randint(k, nx - k)
+        counts[0, j - k // 2:j + k // 2 + 1, i - k // 2:i + k // 2 + 1] += rng.poisson(
+            kernel[0] * rng.uniform(20, 400))
+    return counts, background, exposure, kernel
+
+
+def ts_map_bench(cpu_pixels=600, with_cpu=True):
+    import torch
+
+    from gammapy_b200.estimators import compute_ts_map
+
+    counts, background, exposure, kernel = ts_map_inputs()
+    ny, nx = counts.shape[1:]
+    compute_ts_map(counts[:, :64, :64], background[:, :64, :64], exposure[:, :64, :64], kernel)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = compute_ts_map(counts, background, exposure, kernel, rtol=0.01, max_niter=100)
+    gpu_s = time.perf_counter() - t0
+    out = {"image": f"{nx}x{ny} px, 1 plane, kernel {kernel.shape[1]}x{kernel.shape[2]}, rtol 0.01",
+           "gpu_s_incl_copies": gpu_s, "gpu_pixels_per_s": ny * nx / gpu_s,
+           "mean_niter": float(np.nanmean(res["niter"])), "max_ts": float(np.nanmax(res["ts"])),
+           "success_fraction": float(res["success"].mean())}
+    if with_cpu:
+        from oracle import cash, tsmap
+
+        rng = np.random.RandomState(0)
+        pos = [(int(rng.randint(ny)), int(rng.randint(nx))) for _ in range(cpu_pixels)]
+        t0 = time.perf_counter()
+        worst = 0.0
+        for p in pos:
+            r = tsmap.ts_value(p, counts, background, exposure, kernel, rtol=0.01, max_niter=100)
+            worst = max(worst, abs(r["ts"] - res["ts"][p]))
+        cpu_s = time.perf_counter() - t0
+        out.update({"cpu_pixels_per_s": cpu_pixels / cpu_s, "cpu_sample": f"{cpu_pixels} random pixels, 1 thread",
+                    "cpu_kind": "reference" if cash.reference_module() is not None else "port",
+                    "max_abs_ts_difference_on_sample": worst,
+                    "speedup": (ny * nx / gpu_s) / (cpu_pixels / cpu_s)})
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
 # C4: joint fit of 64 observations sharded over the ranks (strong scaling), evaluation rate + fit wall time
 # ------------------------------------------------------------------------------------------------------------
 def run_c4(args):
@@ -522,6 +574,10 @@ def run_ours(args):
             line["extras"]["fit"] = fit_wall_time(with_cpu=not args.no_cpu_baseline)
         except Exception as exc:
             line["extras"]["fit"] = {"error": repr(exc)}
+        try:
+            line["extras"]["ts_map"] = ts_map_bench(with_cpu=not args.no_cpu_baseline)
+        except Exception as exc:
+            line["extras"]["ts_map"] = {"error": repr(exc)}
     if rank == 0 and not args.no_cpu_baseline and not distributed:
         try:
             dt, sample, kind = cpu_evals(ds, steps=3, warmup=1)
