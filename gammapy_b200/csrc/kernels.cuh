@@ -338,16 +338,37 @@ __device__ __forceinline__ double log_scale(double v) {
   return log(v);
 }
 
-__global__ void spectral_flux_kernel(const FluxJob* __restrict__ jobs) {
+// One block per job.  The trapezoid segments of all bins are independent: one thread per (bin, segment) writes
+// its integral to shared memory, then one thread per bin adds its segments in node order (bit-identical to the
+// serial per-bin loop below, which remains the fallback when the segments do not fit).  seg_cap = doubles of
+// dynamic shared memory.
+__global__ void spectral_flux_kernel(const FluxJob* __restrict__ jobs, int seg_cap) {
+  extern __shared__ double seg[];
   const FluxJob job = jobs[blockIdx.x];
   __shared__ int bad;
   if (threadIdx.x == 0) bad = 0;
+  const int nseg = job.n_nodes - 1;
+  const bool staged = job.type != 0 && job.n_bins * nseg <= seg_cap;
+  if (staged) {
+    for (int w = threadIdx.x; w < job.n_bins * nseg; w += blockDim.x) {
+      const int t = w / nseg, k = w - t * nseg;
+      const double* nd = job.nodes + (size_t)t * job.n_nodes + k;
+      const double e0 = nd[0], e1 = nd[1];
+      const double y0 = spectral_eval(job.type, job.p, e0), y1 = spectral_eval(job.type, job.p, e1);
+      double index = -log_scale(y0 / y1) / log_scale(e0 / e1);
+      if (isnan(index)) index = INFINITY;
+      seg[w] = pl_integral(e0, e1, index, y0, e0);
+    }
+  }
   __syncthreads();
   for (int t = threadIdx.x; t < job.n_bins; t += blockDim.x) {
     double emin = job.edges[t], emax = job.edges[t + 1];
     double result;
     if (job.type == 0) {
       result = pl_integral(emin, emax, job.p[0], job.p[1], job.p[2]);
+    } else if (staged) {
+      result = 0.0;
+      for (int k = 0; k < nseg; ++k) result += seg[t * nseg + k];
     } else {
       // integrate_spectrum + trapz_loglog (spectral.py:103-164, utils/integrate.py:8-49)
       const double* nd = job.nodes + (size_t)t * job.n_nodes;
