@@ -68,6 +68,8 @@ SYMBOLS = {
     "gpy_init": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "gpy_finalize": (C.c_int, [_P]),
     "gpy_launch_count": (C.c_int64, [_P]),
+    "gpy_kernel_timing": (C.c_int, [_P, C.c_int32]),
+    "gpy_kernel_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "gpy_dataset_create": (C.c_int, [_P, C.POINTER(DatasetDesc), C.POINTER(_P)]),
     "gpy_dataset_destroy": (C.c_int, [_P]),
     "gpy_dataset_set_counts": (C.c_int, [_P, _P]),
@@ -160,3 +162,13 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.gpy_launch_count(self.handle))
+
+    def kernel_timing(self, enable):
+        """Bracket the fold + Cash kernel of every evaluation with CUDA events (measurement aid)."""
+        check(self.lib.gpy_kernel_timing(self.handle, int(bool(enable))))
+
+    def kernel_time(self):
+        """(summed kernel duration [ms], launches) since ``kernel_timing(True)``."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        check(self.lib.gpy_kernel_time(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)

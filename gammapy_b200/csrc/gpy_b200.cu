@@ -255,6 +255,10 @@ struct gpy_context {
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   cudaEvent_t h2d_done = nullptr;
+  cudaEvent_t t_begin = nullptr, t_end = nullptr;  // gpy_kernel_timing
+  bool timing = false, timing_pending = false;
+  double timing_ms = 0.0;
+  int64_t timing_launches = 0;
   bool h2d_pending = false;
   DevBuf zeros, desc, dedup, staging, flux, partials, stat, tiles, scratch_a, scratch_b, scratch_c;
   std::vector<gpy_dataset*> tiles_for;  // dataset list the tile table was built for
@@ -633,6 +637,17 @@ struct FluxKey {  // (dataset, source) + the bit patterns of the spectral parame
   bool operator<(const FluxKey& o) const { return std::memcmp(this, &o, sizeof(FluxKey)) < 0; }
 };
 
+int timing_collect(gpy_context* c) {  // adds the bracketed kernel of the previous evaluation to the totals
+  if (!c->timing_pending) return GPY_OK;
+  CUDA_TRY(cudaEventSynchronize(c->t_end));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, c->t_begin, c->t_end));
+  c->timing_ms += ms;
+  c->timing_launches++;
+  c->timing_pending = false;
+  return GPY_OK;
+}
+
 // Build descriptors, refresh spatial caches, launch K0 + fused fold/Cash + reduction.
 // Leaves stat[b * D + d] in c->stat (device).
 int evaluate(gpy_context* c, const EvalRequest& rq) {
@@ -999,7 +1014,15 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, gpy::kFoldThreads, lay.total));
     per_sm = std::max(per_sm, 1);
     const unsigned grid = (unsigned)std::min(n_work_host, (size_t)per_sm * c->num_sms);
+    if (c->timing) {
+      GPY_TRY(timing_collect(c));
+      CUDA_TRY(cudaEventRecord(c->t_begin, c->stream));
+    }
     kern<<<grid, gpy::kFoldThreads, lay.total, c->stream>>>(fp);
+    if (c->timing) {
+      CUDA_TRY(cudaEventRecord(c->t_end, c->stream));
+      c->timing_pending = true;
+    }
   } else {
     if (max_fold_smem > c->fold_smem_set) {
       CUDA_TRY(cudaFuncSetAttribute(gpy::fold_cash_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1011,9 +1034,11 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     gpy::fold_cash_generic_kernel<<<(unsigned)n_items, gpy::kFoldThreads, max_fold_smem, c->stream>>>(fp);
   }
   c->launches++;
-  gpy::reduce_stat_kernel<<<dim3(B, D), 256, 0, c->stream>>>((const double*)c->partials.p, fp.ds, n_tiles, D,
+  if (!rq.npred_out) {
+    gpy::reduce_stat_kernel<<<dim3(B, D), 256, 0, c->stream>>>((const double*)c->partials.p, fp.ds, n_tiles, D,
                                                               B, reduce_dup, (double*)c->stat.p);
-  c->launches++;
+    c->launches++;
+  }
   CUDA_TRY(cudaGetLastError());
   return GPY_OK;
 }
@@ -1079,12 +1104,39 @@ int gpy_finalize(gpy_context_t* c) {
   if (c->stat_pinned) cudaFreeHost(c->stat_pinned);
   if (c->nwork_pinned) cudaFreeHost(c->nwork_pinned);
   if (c->h2d_done) cudaEventDestroy(c->h2d_done);
+  if (c->t_begin) cudaEventDestroy(c->t_begin);
+  if (c->t_end) cudaEventDestroy(c->t_end);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return GPY_OK;
 }
 
 int64_t gpy_launch_count(const gpy_context_t* c) { return c ? c->launches : 0; }
+
+int gpy_kernel_timing(gpy_context_t* c, int32_t enable) {
+  if (!c) return fail(GPY_ERR_INVALID, "NULL context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (enable && !c->t_begin) {
+    CUDA_TRY(cudaEventCreate(&c->t_begin));
+    CUDA_TRY(cudaEventCreate(&c->t_end));
+  }
+  if (enable) {
+    c->timing_ms = 0.0;
+    c->timing_launches = 0;
+    c->timing_pending = false;
+  }
+  c->timing = enable != 0;
+  return GPY_OK;
+}
+
+int gpy_kernel_time(gpy_context_t* c, double* total_ms, int64_t* launches) {
+  if (!c || !total_ms || !launches) return fail(GPY_ERR_INVALID, "NULL argument to gpy_kernel_time");
+  CUDA_TRY(cudaSetDevice(c->device));
+  GPY_TRY(timing_collect(c));
+  *total_ms = c->timing_ms;
+  *launches = c->timing_launches;
+  return GPY_OK;
+}
 
 int gpy_dataset_create(gpy_context_t* c, const gpy_dataset_desc* desc, gpy_dataset_t** out) {
   if (!c || !desc || !out) return fail(GPY_ERR_INVALID, "NULL argument to gpy_dataset_create");

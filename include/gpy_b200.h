@@ -115,6 +115,12 @@ int gpy_finalize(gpy_context_t* ctx);
 /* Number of this library's kernel launches since gpy_init (bench.py "gpu_launches"). */
 int64_t gpy_launch_count(const gpy_context_t* ctx);
 
+/* Measurement aid (bench.py roofline): with enable != 0 every evaluation brackets its fold + Cash kernel with CUDA
+ * events on the library's stream; gpy_kernel_time returns the summed duration [ms] and the number of launches
+ * since the last call with enable != 0, after waiting for the stream.  Costs one host wait per evaluation while on. */
+int gpy_kernel_timing(gpy_context_t* ctx, int32_t enable);
+int gpy_kernel_time(gpy_context_t* ctx, double* total_ms, int64_t* launches);
+
 /* MapDataset.__init__ side: register the resident cubes, upload the static IRF kernels. */
 int gpy_dataset_create(gpy_context_t* ctx, const gpy_dataset_desc* desc, gpy_dataset_t** ds);
 int gpy_dataset_destroy(gpy_dataset_t* ds);
