@@ -183,6 +183,13 @@ def cpu_evals(ds, steps, warmup, max_sources=None):
         de.stat_sum()
     dt = (time.perf_counter() - t0) / steps
     used = len(de.evaluators)
+    # the same with ONE source's position moved each step (spatial model + float32-FFT PSF convolution redone for it)
+    evs = list(de.evaluators.values())
+    t0 = time.perf_counter()
+    for k in range(2):
+        evs[k % len(evs)].model["spatial"]["lon_0"] += 1e-3
+        de.stat_sum()
+    cpu_evals.one_source_moved_s = (time.perf_counter() - t0) / 2
     sample = (f"{steps} steady-state evaluations (spatial/PSF caches warm, spectral parameters of all sources moved), "
               f"{used} of {n_src} sources, float32-FFT convolution as the reference, "
               f"Cash = {'reference Cython (oracle/_ref)' if have_ref else 'numpy restatement'}")
@@ -600,6 +607,7 @@ def run_ours(args):
             dt, sample, kind = cpu_evals(ds, steps=3, warmup=1)
             line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
                                     "sample": sample,
+                                    "ms_per_eval_one_source_moved": 1e3 * getattr(cpu_evals, "one_source_moved_s", float("nan")),
                                     "note": "single Python thread (the reference's N_JOBS_DEFAULT = 1); numpy's BLAS "
                                             "may use more cores inside the edisp matmul"}
         except Exception as exc:  # never lose the GPU numbers to the checker
