@@ -266,7 +266,7 @@ struct gpy_context {
   double* stat_pinned = nullptr;
   int* nwork_pinned = nullptr;  // read-back of the batched worklist length
   size_t stat_pinned_cap = 0;
-  size_t fold_smem_set = 0, conv_smem_set = 0, tma_smem_set[2] = {0, 0};
+  size_t ts_smem_set = 0, fold_smem_set = 0, conv_smem_set = 0, tma_smem_set[2] = {0, 0};
   int tma_blocks_per_sm[2] = {0, 0};
   int num_sms = 0;
   bool force_generic = false;
@@ -1485,7 +1485,19 @@ int gpy_ts_map(gpy_context_t* c, const double* counts, const double* background,
   tp.xtol = 2e-12;
   tp.n_sigma = n_sigma;
   tp.log_trunc = c->log_trunc;
-  gpy::ts_map_kernel<<<(unsigned)((P + 7) / 8), 256, 0, c->stream>>>(tp);
+  const size_t strip_smem = gpy::ts_strip_smem_bytes(n_planes, ky, kx);
+  if (strip_smem <= 100 * 1024 && !std::getenv("GPY_TS_GLOBAL")) {  // >= 2 blocks per SM; else read through L1 / L2
+    if (strip_smem > c->ts_smem_set) {
+      cudaError_t ea = cudaFuncSetAttribute(gpy::ts_map_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)strip_smem);
+      if (ea != cudaSuccess) return done(fail(GPY_ERR_CUDA, "TS-map shared memory: %s", cudaGetErrorString(ea)));
+      c->ts_smem_set = strip_smem;
+    }
+    const unsigned strips = (unsigned)((nx + gpy::kTsStrip - 1) / gpy::kTsStrip);
+    gpy::ts_map_strip_kernel<<<strips * (unsigned)ny, 32 * gpy::kTsStrip, strip_smem, c->stream>>>(tp);
+  } else {
+    gpy::ts_map_kernel<<<(unsigned)((P + 7) / 8), 256, 0, c->stream>>>(tp);
+  }
   c->launches++;
   e = cudaGetLastError();
   if (e == cudaSuccess)

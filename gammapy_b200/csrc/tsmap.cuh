@@ -82,8 +82,34 @@ struct TsWindow {
   }
 };
 
+// The same bins read from the shared-memory copy of a strip's union window (ts_map_strip_kernel): rows of
+// `stride` = kx + kTsStrip - 1 doubles, planes and rows contiguous, zeros where the map ends (such bins drop out by
+// the all-zero rule exactly like the reference's padded maps, ts.py:772-777).
+constexpr int kTsStrip = 8;  // pixels (= warps) per block
+
+struct TsWindowSmem {
+  const double *c, *b, *e, *kern;  // shared memory
+  int lane, n_bins, kx, stride, shift;
+  template <typename F>
+  __device__ __forceinline__ void for_each(F&& body) const {
+    int dx = lane, off = lane + shift;
+    for (int k = lane; k < n_bins; k += 32) {
+      while (dx >= kx) {
+        dx -= kx;
+        off += stride - kx;
+      }
+      const double cc = c[off], bb = b[off];
+      const double m = __dmul_rn(kern[k], e[off]);
+      if (!(cc == 0.0 && bb == 0.0 && m == 0.0)) body(k, cc, bb, m);
+      dx += 32;
+      off += 32;
+    }
+  }
+};
+
 // f_cash_root_cython (.pyx:90-121): 2 sum_{m > 0} (c > 0 ? m (1 - c / (x m + b)) : m)
-__device__ __forceinline__ double ts_derivative(const TsWindow& W, double x) {
+template <class Window>
+__device__ __forceinline__ double ts_derivative(const Window& W, double x) {
   double s = 0.0;
   W.for_each([&](int, double c, double b, double m) {
     if (m > 0.0) {
@@ -111,17 +137,10 @@ __device__ __forceinline__ double cash_term(double c, double npred, double log_t
 
 __device__ __forceinline__ bool signbit_d(double v) { return __double2hiint(v) < 0; }
 
-__global__ void __launch_bounds__(256) ts_map_kernel(const TsMapParams P) {
-  const int lane = threadIdx.x & 31;
-  const long long pix = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+// The fit of one pixel by one warp; W deals the bins of its cutout to the lanes.
+template <class Window>
+__device__ __forceinline__ void ts_fit_pixel(const TsMapParams& P, const Window& W, long long pix, int lane) {
   const long long n_pix = (long long)P.ny * P.nx;
-  if (pix >= n_pix) return;
-  const double nan = __longlong_as_double(0x7ff8000000000000ll);
-  if (P.mask && !P.mask[pix]) {
-    if (lane < kTsPlanes) P.out[(size_t)lane * n_pix + pix] = nan;
-    return;
-  }
-  const TsWindow W(P, (int)(pix / P.nx), (int)(pix % P.nx), lane);
 
   // ---- norm_bounds_cython (.pyx:124-157) + the two sums estimate_best_fit tests (ts.py:836)
   double s_model = 0.0, s_counts = 0.0, sum_counts = 0.0, sum_model = 0.0, sum_bkg = 0.0;
@@ -282,6 +301,75 @@ __global__ void __launch_bounds__(256) ts_map_kernel(const TsMapParams P) {
     o[7 * n_pix] = npred;
     o[8 * n_pix] = npred - sum_bkg;
   }
+}
+
+// Any shape: every pass reads the maps through L1 / L2.
+__global__ void __launch_bounds__(256) ts_map_kernel(const TsMapParams P) {
+  const int lane = threadIdx.x & 31;
+  const long long pix = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const long long n_pix = (long long)P.ny * P.nx;
+  if (pix >= n_pix) return;
+  if (P.mask && !P.mask[pix]) {
+    if (lane < kTsPlanes) P.out[(size_t)lane * n_pix + pix] = __longlong_as_double(0x7ff8000000000000ll);
+    return;
+  }
+  const TsWindow W(P, (int)(pix / P.nx), (int)(pix % P.nx), lane);
+  ts_fit_pixel(P, W, pix, lane);
+}
+
+// Shared-memory variant: a block fits kTsStrip consecutive pixels of one row (one per warp).  The union of their
+// cutouts ([n_planes][ky][kx + kTsStrip - 1] of counts, background, exposure) and the kernel are staged once and
+// every pass of every warp reads shared memory only.  Dynamic shared memory: ts_strip_smem_bytes().
+__host__ __device__ inline size_t ts_strip_smem_bytes(int n_planes, int ky, int kx) {
+  return ((size_t)3 * n_planes * ky * (kx + kTsStrip - 1) + (size_t)n_planes * ky * kx) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(32 * kTsStrip) ts_map_strip_kernel(const TsMapParams P) {
+  extern __shared__ double ts_smem[];
+  const int strips = (P.nx + kTsStrip - 1) / kTsStrip;
+  const int j = blockIdx.x / strips, i0 = (blockIdx.x % strips) * kTsStrip;
+  const int stride = P.kx + kTsStrip - 1, rows = P.n_planes * P.ky;
+  const int plane = rows * stride;
+  double* sc = ts_smem;
+  double* sb = sc + plane;
+  double* se = sb + plane;
+  double* sk = se + plane;
+  for (int w = threadIdx.x; w < plane; w += blockDim.x) {
+    const int row = w / stride, u = w - row * stride;
+    const int e = row / P.ky, dy = row - e * P.ky;
+    const int y = j + dy - P.ky / 2, x = i0 + u - P.kx / 2;
+    double c = 0.0, b = 0.0, ex = 0.0;
+    if (y >= 0 && y < P.ny && x >= 0 && x < P.nx) {
+      const size_t o = ((size_t)e * P.ny + y) * P.nx + x;
+      c = __ldg(P.counts + o);
+      b = __ldg(P.background + o);
+      ex = __ldg(P.exposure + o);
+    }
+    sc[w] = c;
+    sb[w] = b;
+    se[w] = ex;
+  }
+  for (int w = threadIdx.x; w < rows * P.kx; w += blockDim.x) sk[w] = __ldg(P.kernel + w);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = i0 + warp;
+  if (i >= P.nx) return;
+  const long long n_pix = (long long)P.ny * P.nx, pix = (long long)j * P.nx + i;
+  if (P.mask && !P.mask[pix]) {
+    if (lane < kTsPlanes) P.out[(size_t)lane * n_pix + pix] = __longlong_as_double(0x7ff8000000000000ll);
+    return;
+  }
+  TsWindowSmem W;
+  W.c = sc;
+  W.b = sb;
+  W.e = se;
+  W.kern = sk;
+  W.lane = lane;
+  W.n_bins = rows * P.kx;
+  W.kx = P.kx;
+  W.stride = stride;
+  W.shift = warp;
+  ts_fit_pixel(P, W, pix, lane);
 }
 
 // ---- compiled-stat registry entries over caller-provided 1-D arrays (utils/compilation.py:35-87) -----------------

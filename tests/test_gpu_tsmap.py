@@ -106,3 +106,17 @@ def test_registry_is_complete_and_matches_reference(ctx):
     model = np.array([1.0, 1.0, 1.0, 1.0])
     assert_allclose(stats["norm_bounds_compiled"](counts, background, model), b_ref(counts, background, model), rtol=1e-15)
     assert stats["norm_bounds_compiled"](counts, background, model)[0] == 5.0 / 4.0 - 0.5
+
+
+def test_shared_memory_and_global_memory_kernels_agree(ctx, monkeypatch):
+    """Small kernels take the strip kernel (cutouts staged in shared memory), big ones the any-shape kernel;
+    GPY_TS_GLOBAL forces the latter: both must give the same bits (same lane dealing, same reduction order)."""
+    from gammapy_b200.estimators import RESULT_NAMES, compute_ts_map
+
+    g = np.load(GOLDEN)
+    args = (g["counts"], g["background"], g["exposure"], g["kernel"])
+    staged = compute_ts_map(*args, mask=g["mask"], rtol=1e-6)
+    monkeypatch.setenv("GPY_TS_GLOBAL", "1")
+    plain = compute_ts_map(*args, mask=g["mask"], rtol=1e-6)
+    for name in RESULT_NAMES:
+        assert np.array_equal(staged[name], plain[name], equal_nan=True), name
