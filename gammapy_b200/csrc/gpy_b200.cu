@@ -952,6 +952,19 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   const int variant = rq.npred_out ? 1 : 0;
   if (tma_ok) {
     const gpy::DescLayout dl = gpy::desc_layout(max_nT, max_nRp);
+    fp.lay_es = (unsigned)lay.es;
+    fp.lay_bs = (unsigned)lay.bs;
+    fp.lay_cs = (unsigned)lay.cs;
+    fp.lay_ms = (unsigned)lay.ms;
+    fp.lay_vs = (unsigned)lay.vs;
+    fp.lay_pdf = (unsigned)lay.pdf;
+    fp.lay_desc = (unsigned)lay.desc;
+    fp.lay_bars = (unsigned)lay.bars;
+    fp.dl_inst = dl.inst;
+    fp.dl_flux = dl.flux;
+    fp.dl_bkg = dl.bkg;
+    fp.dl_over = dl.over;
+    fp.dl_bytes = dl.bytes;
     gpy::PrepParams pp;
     pp.ds = fp.ds;
     pp.tile_ds = fp.tile_ds;

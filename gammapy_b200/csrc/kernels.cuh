@@ -452,6 +452,11 @@ struct FoldParams {
   int smem_nT, smem_nR, smem_nRp, smem_G;  // largest axes of the launch: fixed shared-memory layout (bulk-copy kernel)
   int smem_pdfc_rows, pad3_;
   const unsigned char* desc;  // [work items][desc_layout(smem_nT, smem_nRp).bytes] item descriptors (prep_items_kernel)
+  // shared-memory byte offsets (fold_tma_layout) and descriptor offsets (desc_layout), computed once on the host:
+  // as kernel parameters they are constant-bank operands instead of arithmetic the compiler rematerialises at
+  // every shared-memory access (13 % of the kernel's instructions before)
+  unsigned lay_es, lay_bs, lay_cs, lay_ms, lay_vs, lay_pdf, lay_desc, lay_bars;
+  int dl_inst, dl_flux, dl_bkg, dl_over, dl_bytes;
   const int* work;          // [*n_work] item indices to evaluate, or null: all B * n_tiles items (B == 1)
   const int* n_work;
   const float* zeros;       // >= 16 bytes of zeros: load target of (thread, source) pairs outside the cutout
@@ -964,16 +969,20 @@ __host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int
 template <bool WRITE_NPRED>
 __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const FoldParams P) {
   extern __shared__ __align__(128) unsigned char fold_raw[];
-  const FoldSmem L = fold_tma_layout(P.smem_nT, P.smem_nR, P.smem_nRp, P.smem_G, P.smem_pdfc_rows);
-  float* es = reinterpret_cast<float*>(fold_raw + L.es);
-  float* bs = reinterpret_cast<float*>(fold_raw + L.bs);
-  float* cs = reinterpret_cast<float*>(fold_raw + L.cs);
-  unsigned char* ms = fold_raw + L.ms;
-  double* vs = reinterpret_cast<double*>(fold_raw + L.vs);
-  double* pdf_s = reinterpret_cast<double*>(fold_raw + L.pdf);
-  unsigned char* desc_s = fold_raw + L.desc;
-  const DescLayout DL = desc_layout(P.smem_nT, P.smem_nRp);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + L.bars);  // [0] exposure, [1] epilogue inputs, [2] descriptor
+  float* es = reinterpret_cast<float*>(fold_raw + P.lay_es);
+  float* bs = reinterpret_cast<float*>(fold_raw + P.lay_bs);
+  float* cs = reinterpret_cast<float*>(fold_raw + P.lay_cs);
+  unsigned char* ms = fold_raw + P.lay_ms;
+  double* vs = reinterpret_cast<double*>(fold_raw + P.lay_vs);
+  double* pdf_s = reinterpret_cast<double*>(fold_raw + P.lay_pdf);
+  unsigned char* desc_s = fold_raw + P.lay_desc;
+  DescLayout DL;
+  DL.inst = P.dl_inst;
+  DL.flux = P.dl_flux;
+  DL.bkg = P.dl_bkg;
+  DL.over = P.dl_over;
+  DL.bytes = P.dl_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + P.lay_bars);  // [0] exposure, [1] epilogue inputs, [2] descriptor
   __shared__ double wsum[kFoldThreads / 32];
 
   const int tid = threadIdx.x;
