@@ -1175,6 +1175,39 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         GPY_TICK(3);
         // ---- phase 1: v[g][t][p] = 1e4 * exposure[t,p] * sum_s F_s[t] * conv_s[t,p] ----
         for (int g = 0; g < G; ++g) {
+          if (nl <= 2) {
+            // Common case (CTA uniform): at most two sources reach the tile.  All eight loads of the pass are issued
+            // before the first use, so the pass pays one memory latency instead of one per true-energy slot.
+            float4 c0[kTmaTCH / 8], c1[kTmaTCH / 8];
+#pragma unroll
+            for (int tt = 0; tt < kTmaTCH / 8; ++tt) {
+              const int tc = min(t0 + slot + 8 * tt, nT - 1);  // rows past the axis are loaded but not used
+              c0[tt] = ldg_f4_hint(cptr[0] + (size_t)tc * pstr[0], pol_keep);
+              c1[tt] = ldg_f4_hint(cptr[1] + (size_t)tc * pstr[1], pol_keep);
+            }
+#pragma unroll
+            for (int tt = 0; tt < kTmaTCH / 8; ++tt) {
+              const int tl = slot + 8 * tt, t = t0 + tl;
+              double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+              if (t < nT && qlive) {
+                const double F0 = grp[0] == g ? flux_s[t] : 0.0;
+                const double F1 = grp[1] == g ? flux_s[fstride + t] : 0.0;
+                s0 = fma(F1, (double)c1[tt].x, fma(F0, (double)c0[tt].x, s0));
+                s1 = fma(F1, (double)c1[tt].y, fma(F0, (double)c0[tt].y, s1));
+                s2 = fma(F1, (double)c1[tt].z, fma(F0, (double)c0[tt].z, s2));
+                s3 = fma(F1, (double)c1[tt].w, fma(F0, (double)c0[tt].w, s3));
+                const float4 e = *reinterpret_cast<const float4*>(es + t * kFoldTPX + 4 * q);
+                s0 = (s0 * (double)e.x) * 1e4;
+                s1 = (s1 * (double)e.y) * 1e4;
+                s2 = (s2 * (double)e.z) * 1e4;
+                s3 = (s3 * (double)e.w) * 1e4;
+              }
+              double* dst = vs + ((size_t)g * kTmaTCH + tl) * kFoldTPX + 4 * q;
+              *reinterpret_cast<double2*>(dst) = make_double2(s0, s1);
+              *reinterpret_cast<double2*>(dst + 2) = make_double2(s2, s3);
+            }
+            continue;
+          }
 #pragma unroll
           for (int tt = 0; tt < kTmaTCH / 8; ++tt) {
             const int tl = slot + 8 * tt, t = t0 + tl;
