@@ -1208,14 +1208,24 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
             }
             continue;
           }
+          float4 cg[2][kFoldLMax];
 #pragma unroll
           for (int tt = 0; tt < kTmaTCH / 8; ++tt) {
             const int tl = slot + 8 * tt, t = t0 + tl;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            // three or four sources: the loads of two slots (eight) are in flight together
+            if ((tt & 1) == 0) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int tc = min(t + 8 * u, nT - 1);
+#pragma unroll
+                for (int l = 0; l < kFoldLMax; ++l) cg[u][l] = ldg_f4_hint(cptr[l] + (size_t)tc * pstr[l], pol_keep);
+              }
+            }
             if (t < nT && qlive) {
 #pragma unroll
               for (int l = 0; l < kFoldLMax; ++l) {
-                const float4 cv = ldg_f4_hint(cptr[l] + (size_t)t * pstr[l], pol_keep);
+                const float4 cv = cg[tt & 1][l];
                 const double F = grp[l] == g ? flux_s[l * fstride + t] : 0.0;
                 s0 = fma(F, (double)cv.x, s0);
                 s1 = fma(F, (double)cv.y, s1);
