@@ -270,6 +270,8 @@ struct gpy_context {
   int tma_blocks_per_sm[2] = {0, 0};
   int num_sms = 0;
   bool force_generic = false;
+  bool no_desc_cache = false;  // GPY_NO_DESC_CACHE: run prep_items_kernel on every call
+  std::vector<uint8_t> desc_key;  // what the descriptors in `desc` were built from (empty: none)
   bool no_dedup = false;  // GPY_NO_DEDUP: evaluate every item of a batch even when identical to vector 0's
   int fold_mode = 0;  // GPY_FOLD_KERNEL: 0 auto (bulk-copy staged kernel when eligible), 2 generic
   double log_trunc = 0.0;
@@ -894,7 +896,27 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     for (int d = 0; d < D; ++d) c->tiles_ver[d] = rq.datasets[d]->version;
   }
 
-  GPY_TRY(c->flux.reserve(std::max(flux_len, (size_t)1) * sizeof(double)));
+  // background factors: one K0 job per (dataset, vector), outputs [D * B][max_nRp] at the end of the flux buffer
+  const size_t bkg_base = flux_len;
+  for (int d = 0; d < D; ++d)
+    for (int b = 0; b < B; ++b) {
+      const gpy::EvalDev& ev = evals[(size_t)d * B + b];
+      gpy::FluxJob job;
+      std::memset(&job, 0, sizeof(job));
+      job.type = gpy::kFluxJobBackground;
+      job.n_bins = max_nRp;
+      job.n_nodes = rq.datasets[d]->nR;
+      job.sanitize = ev.bkg_enabled;
+      job.p[0] = ev.bkg_norm;
+      job.p[1] = ev.bkg_tilt;
+      job.p[2] = ev.bkg_ref;
+      job.edges = (const double*)rq.datasets[d]->d_ecenter.p;
+      jobs.push_back(job);
+      job_flux_off.push_back(flux_len);
+      flux_len += max_nRp;
+    }
+  // + max_nT: the fold kernel copies flux rows in units of the launch's largest true-energy axis
+  GPY_TRY(c->flux.reserve((flux_len + (size_t)max_nT + 1) * sizeof(double)));
   GPY_TRY(c->partials.reserve((size_t)B * n_tiles * (gpy::kFoldThreads / 32) * sizeof(double)));
   GPY_TRY(c->stat.reserve((size_t)B * D * sizeof(double)));
   for (size_t i = 0; i < jobs.size(); ++i) jobs[i].out = (double*)c->flux.p + job_flux_off[i];
@@ -916,7 +938,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   if (!jobs.empty()) {
     int seg_cap = 0;  // doubles of shared memory for the per-segment integrals (falls back to the serial loop)
     for (const auto& j : jobs)
-      if (j.type != 0) seg_cap = std::max(seg_cap, j.n_bins * (j.n_nodes - 1));
+      if (j.type != 0 && j.type != gpy::kFluxJobBackground) seg_cap = std::max(seg_cap, j.n_bins * (j.n_nodes - 1));
     seg_cap = std::min(seg_cap, 5120);  // 40 KB
     gpy::spectral_flux_kernel<<<(unsigned)jobs.size(), seg_cap ? 256 : 64, (size_t)seg_cap * sizeof(double),
                                 c->stream>>>((const gpy::FluxJob*)(base + off_jb), seg_cap);
@@ -929,6 +951,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   fp.evals = (const gpy::EvalDev*)(base + off_ev);
   fp.insts = (const gpy::InstDev*)(base + off_in);
   fp.flux = (const double*)c->flux.p;
+  fp.bkgfac = (const double*)c->flux.p + bkg_base;
   fp.partials = (double*)c->partials.p;
   fp.npred_out = rq.npred_out;
   fp.B = B;
@@ -951,7 +974,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   const unsigned char* reduce_dup = nullptr;
   const int variant = rq.npred_out ? 1 : 0;
   if (tma_ok) {
-    const gpy::DescLayout dl = gpy::desc_layout(max_nT, max_nRp);
+    const gpy::DescLayout dl = gpy::desc_layout();
     fp.lay_es = (unsigned)lay.es;
     fp.lay_bs = (unsigned)lay.bs;
     fp.lay_cs = (unsigned)lay.cs;
@@ -959,10 +982,9 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     fp.lay_vs = (unsigned)lay.vs;
     fp.lay_pdf = (unsigned)lay.pdf;
     fp.lay_desc = (unsigned)lay.desc;
+    fp.lay_dyn = (unsigned)lay.dyn;
     fp.lay_bars = (unsigned)lay.bars;
     fp.dl_inst = dl.inst;
-    fp.dl_flux = dl.flux;
-    fp.dl_bkg = dl.bkg;
     fp.dl_over = dl.over;
     fp.dl_bytes = dl.bytes;
     gpy::PrepParams pp;
@@ -970,11 +992,8 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     pp.tile_ds = fp.tile_ds;
     pp.evals = fp.evals;
     pp.insts = fp.insts;
-    pp.flux = fp.flux;
     pp.B = B;
     pp.n_tiles = n_tiles;
-    pp.max_nT = max_nT;
-    pp.max_nRp = max_nRp;
     // B > 1: evaluate each distinct (tile, vector) item once (see dedup_*_kernel)
     const bool dedup = B > 1 && !c->no_dedup;
     pp.work = nullptr;
@@ -1013,8 +1032,28 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     }
     GPY_TRY(c->desc.reserve(n_work_host * (size_t)dl.bytes, c->stream));
     pp.desc = (unsigned char*)c->desc.p;
-    gpy::prep_items_kernel<<<item_blocks, 256, 0, c->stream>>>(pp);
-    c->launches++;
+    // The descriptors hold nothing that changes on a steady-state step (no fluxes, no background factors): keep
+    // them while the datasets, the source list, every cutout and every slot are what they were (B == 1 only).
+    std::vector<uint8_t> key;
+    if (!dedup) {
+      auto put = [&key](const void* src, size_t n) {
+        const uint8_t* q = (const uint8_t*)src;
+        key.insert(key.end(), q, q + n);
+      };
+      const long long head[4] = {D, B, n_tiles, (long long)(uintptr_t)c->desc.p};
+      put(head, sizeof(head));
+      for (int d = 0; d < D; ++d) {
+        const long long id[2] = {(long long)(uintptr_t)rq.datasets[d], (long long)rq.datasets[d]->version};
+        put(id, sizeof(id));
+      }
+      for (const auto& ev : evals) put(&ev.inst_begin, 2 * sizeof(int));
+      put(insts.data(), insts.size() * sizeof(gpy::InstDev));
+    }
+    if (dedup || c->no_desc_cache || key != c->desc_key) {
+      gpy::prep_items_kernel<<<item_blocks, 256, 0, c->stream>>>(pp);
+      c->launches++;
+      c->desc_key.swap(key);  // empty after a batched call: the next B == 1 call rebuilds
+    }
     fp.desc = (const unsigned char*)c->desc.p;
     auto kern = variant ? gpy::fold_cash_tma_kernel<true> : gpy::fold_cash_tma_kernel<false>;
     if (lay.total > c->tma_smem_set[variant]) {
@@ -1093,6 +1132,7 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
   c->force_generic = std::getenv("GPY_FORCE_GENERIC_FOLD") != nullptr;
   c->no_dedup = std::getenv("GPY_NO_DEDUP") != nullptr;
+  c->no_desc_cache = std::getenv("GPY_NO_DESC_CACHE") != nullptr;
   if (const char* m = std::getenv("GPY_FOLD_KERNEL")) c->fold_mode = std::atoi(m);
   if (c->fold_mode == 2) c->force_generic = true;
   {

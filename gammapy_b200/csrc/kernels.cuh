@@ -294,8 +294,10 @@ psf_conv_kernel(const float* __restrict__ image, int cy, int cx, int pitch, int 
 // ----------------------------------------------------------------------------------------------
 // K0: SpectralModel.integral over the true-energy bins (modeling/models/spectral.py:353-371)
 // ----------------------------------------------------------------------------------------------
+constexpr int kFluxJobBackground = 3;  // FluxJob::type of a background-factor job (see spectral_flux_kernel)
+
 struct FluxJob {
-  int type;      // gpy_spectral_type
+  int type;      // gpy_spectral_type, or kFluxJobBackground
   int n_bins;
   int n_nodes;
   int sanitize;         // 1: zero the vector when any bin is non-finite (likelihood path), 0: raw integrals
@@ -345,6 +347,14 @@ __device__ __forceinline__ double log_scale(double v) {
 __global__ void spectral_flux_kernel(const FluxJob* __restrict__ jobs, int seg_cap) {
   extern __shared__ double seg[];
   const FluxJob job = jobs[blockIdx.x];
+  if (job.type == kFluxJobBackground) {
+    // background factors norm * (E_c / E_0)^-tilt per reco bin (PowerLawNormSpectralModel.evaluate,
+    // spectral.py:1159-1162; FoVBackgroundModel.evaluate_geom, cube.py:737-756): p = {norm, tilt, reference},
+    // edges = reco bin centres [n_nodes], out padded with 1 to n_bins; sanitize == 0: no background model -> 1
+    for (int r = threadIdx.x; r < job.n_bins; r += blockDim.x)
+      job.out[r] = (job.sanitize && r < job.n_nodes) ? job.p[0] * pow(job.edges[r] / job.p[2], -job.p[1]) : 1.0;
+    return;
+  }
   __shared__ int bad;
   if (threadIdx.x == 0) bad = 0;
   const int nseg = job.n_nodes - 1;
@@ -455,8 +465,9 @@ struct FoldParams {
   // shared-memory byte offsets (fold_tma_layout) and descriptor offsets (desc_layout), computed once on the host:
   // as kernel parameters they are constant-bank operands instead of arithmetic the compiler rematerialises at
   // every shared-memory access (13 % of the kernel's instructions before)
-  unsigned lay_es, lay_bs, lay_cs, lay_ms, lay_vs, lay_pdf, lay_desc, lay_bars;
-  int dl_inst, dl_flux, dl_bkg, dl_over, dl_bytes;
+  unsigned lay_es, lay_bs, lay_cs, lay_ms, lay_vs, lay_pdf, lay_desc, lay_dyn, lay_bars;
+  int dl_inst, dl_over, dl_bytes;
+  const double* bkgfac;     // [n_datasets * B][smem_nRp] background factors norm (E/E0)^-tilt (K0), index d * B + b
   const int* work;          // [*n_work] item indices to evaluate, or null: all B * n_tiles items (B == 1)
   const int* n_work;
   const float* zeros;       // >= 16 bytes of zeros: load target of (thread, source) pairs outside the cutout
@@ -858,21 +869,22 @@ dedup_scatter_kernel(const unsigned char* __restrict__ dup, const int* __restric
 
 // ---- per-item work descriptors --------------------------------------------------------------------------
 // prep_items_kernel (one warp per (tile, vector) item, after K0) resolves everything an item needs besides the
-// data cubes: the sources whose cutout overlaps the tile (first kFoldLMax as InstDev copies + their spectral
-// fluxes, further ones as indices), and the background factors norm (E/E0)^-tilt.  The fold kernel fetches
+// data cubes and the per-step numbers: the sources whose cutout overlaps the tile (first kFoldLMax as InstDev copies,
+// further ones as indices).  Nothing in a descriptor depends on the spectral or background parameters -- the fold
+// kernel reads the flux vectors and background factors K0 wrote straight from global memory (a few KB, L1
+// resident) -- so the host re-runs this kernel only when a cutout, a slot or the source list changes, not on the
+// steady-state steps of a fit.  The fold kernel fetches
 // the descriptor of the NEXT item with one bulk copy while it computes the current one, so its prologue is a
 // single mbarrier wait instead of a serial list build over global memory.
 constexpr int kFoldLMax = 4;       // overlapping sources held in registers by the fold kernel
 constexpr int kDescOverflow = 60;  // further overlapping sources per item (indices; slow path)
 struct DescLayout {
-  int inst, flux, bkg, over, bytes;  // byte offsets inside a descriptor; header = int4 {nl, n_over, 0, 0}
+  int inst, over, bytes;  // byte offsets inside a descriptor; header = int4 {nl, n_over, d * B + b, 0}
 };
-__host__ __device__ inline DescLayout desc_layout(int nT, int nRp) {
+__host__ __device__ inline DescLayout desc_layout() {
   DescLayout L;
   L.inst = 16;
-  L.flux = L.inst + kFoldLMax * (int)sizeof(InstDev);
-  L.bkg = L.flux + kFoldLMax * nT * 8;
-  L.over = L.bkg + nRp * 8;
+  L.over = L.inst + kFoldLMax * (int)sizeof(InstDev);
   L.bytes = (L.over + kDescOverflow * 4 + 15) / 16 * 16;
   return L;
 }
@@ -882,11 +894,10 @@ struct PrepParams {
   const int* tile_ds;
   const EvalDev* evals;
   const InstDev* insts;
-  const double* flux;
   unsigned char* desc;  // [number of work items][desc bytes]
   const int* work;          // prep_items_kernel: items to describe ([*n_work]), or null: all of them
   const int* n_work;
-  int B, n_tiles, max_nT, max_nRp;
+  int B, n_tiles;
 };
 
 __global__ void __launch_bounds__(256) prep_items_kernel(const PrepParams P) {
@@ -894,7 +905,7 @@ __global__ void __launch_bounds__(256) prep_items_kernel(const PrepParams P) {
   const long long w = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;  // position in the worklist = descriptor slot
   if (w >= (P.work ? (long long)*P.n_work : (long long)P.B * P.n_tiles)) return;
   const long long item = P.work ? P.work[w] : w;
-  const DescLayout L = desc_layout(P.max_nT, P.max_nRp);
+  const DescLayout L = desc_layout();
   unsigned char* out = P.desc + (size_t)w * L.bytes;
   const int b = (int)(item % P.B);
   const int tile = (int)(item / P.B);
@@ -906,8 +917,6 @@ __global__ void __launch_bounds__(256) prep_items_kernel(const PrepParams P) {
   const int y_first = p0 / D.nx, y_last = (p0 + npx - 1) / D.nx;
   const int x_first = p0 - y_first * D.nx, x_last = p0 + npx - 1 - y_last * D.nx;
   InstDev* oinst = reinterpret_cast<InstDev*>(out + L.inst);
-  double* oflux = reinterpret_cast<double*>(out + L.flux);
-  double* obkg = reinterpret_cast<double*>(out + L.bkg);
   int* oover = reinterpret_cast<int*>(out + L.over);
   int n = 0;
   for (int base = 0; base < ev.inst_count; base += 32) {
@@ -931,25 +940,13 @@ __global__ void __launch_bounds__(256) prep_items_kernel(const PrepParams P) {
   }
   __syncwarp();
   const int nl = min(n, kFoldLMax);
-  if (lane == 0) *reinterpret_cast<int4*>(out) = make_int4(nl, min(max(n - kFoldLMax, 0), kDescOverflow), 0, 0);
-  // fluxes of the register-resident sources, zero rows beyond nl (row stride = max_nT)
-  for (int i = lane; i < kFoldLMax * P.max_nT; i += 32) {
-    const int l = i / P.max_nT, t = i - l * P.max_nT;
-    double v = 0.0;
-    if (l < nl && t < D.nT) v = P.flux[oinst[l].flux_off + t];
-    oflux[i] = v;
-  }
-  // background factors norm * (E_c / E_0)^-tilt (PowerLawNormSpectralModel.evaluate, spectral.py:1159-1162)
-  for (int r = lane; r < P.max_nRp; r += 32) {
-    double fac = 1.0;
-    if (ev.bkg_enabled && r < D.nR) fac = ev.bkg_norm * pow(D.ecenter[r] / ev.bkg_ref, -ev.bkg_tilt);
-    obkg[r] = fac;
-  }
+  if (lane == 0)  // header: sources in registers, overflow sources, (dataset, vector) index of the background factors
+    *reinterpret_cast<int4*>(out) = make_int4(nl, min(max(n - kFoldLMax, 0), kDescOverflow), d * P.B + b, 0);
 }
 
 constexpr int kTmaTCH = 32;  // true-energy bins per pass of the bulk-copy kernel (2 passes at nT = 60)
 struct FoldSmem {  // byte offsets of the fixed shared-memory layout
-  size_t es, bs, cs, ms, vs, pdf, desc, bars, total;
+  size_t es, bs, cs, ms, vs, pdf, desc, dyn, bars, total;
 };
 __host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int G, int pdfc_rows) {
   FoldSmem L;
@@ -960,7 +957,8 @@ __host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int
   L.ms = o;    o += ((size_t)nR * kFoldTPX + 15) / 16 * 16;
   L.vs = o;    o += (size_t)G * kTmaTCH * kFoldTPX * 8;
   L.pdf = o;   o += (size_t)pdfc_rows * 64;
-  L.desc = o;  o += (size_t)2 * desc_layout(nT, nRp).bytes;  // double buffered item descriptors
+  L.desc = o;  o += (size_t)2 * desc_layout().bytes;  // double buffered item descriptors
+  L.dyn = o;   o += (size_t)2 * (kFoldLMax * nT + nRp) * 8;  // double buffered flux rows + background factors
   L.bars = (o + 7) / 8 * 8;
   L.total = L.bars + 3 * 8;
   return L;
@@ -976,10 +974,9 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   double* vs = reinterpret_cast<double*>(fold_raw + P.lay_vs);
   double* pdf_s = reinterpret_cast<double*>(fold_raw + P.lay_pdf);
   unsigned char* desc_s = fold_raw + P.lay_desc;
+  double* dyn_s = reinterpret_cast<double*>(fold_raw + P.lay_dyn);  // [2][kFoldLMax * smem_nT + smem_nRp]
   DescLayout DL;
   DL.inst = P.dl_inst;
-  DL.flux = P.dl_flux;
-  DL.bkg = P.dl_bkg;
   DL.over = P.dl_over;
   DL.bytes = P.dl_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + P.lay_bars);  // [0] exposure, [1] epilogue inputs, [2] descriptor
@@ -1074,6 +1071,25 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     bulk_g2s(desc_s + buf * DL.bytes, P.desc + (size_t)it * DL.bytes, (uint32_t)DL.bytes, &bars[2]);
   };
 
+  // The per-step numbers of an item -- the flux vectors of its register-resident sources (zero rows beyond nl) and
+  // its background factors, both K0 output in global memory (L2 / L1 resident) -- are copied into shared memory by
+  // all threads one item ahead, during the previous item's epilogue; two CTA barriers lie between the copy and the
+  // first read.  The descriptor in buffer `buf` must have landed.
+  const int dyn_len = kFoldLMax * P.smem_nT + P.smem_nRp;
+  auto load_dyn = [&](uint32_t buf, int i) -> double {  // element i of the item whose descriptor is in `buf`
+    const unsigned char* dsc = desc_s + buf * DL.bytes;
+    const int4 head = *reinterpret_cast<const int4*>(dsc);
+    const InstDev* inst = reinterpret_cast<const InstDev*>(dsc + DL.inst);
+    const int l = (i >= P.smem_nT) + (i >= 2 * P.smem_nT) + (i >= 3 * P.smem_nT) + (i >= 4 * P.smem_nT);
+    const int t = i - l * P.smem_nT;
+    if (l == kFoldLMax) return __ldg(P.bkgfac + (size_t)head.z * P.smem_nRp + t);
+    if (l < head.x) return __ldg(P.flux + inst[l].flux_off + t);  // only t < the dataset's own nT is used
+    return 0.0;
+  };
+  auto stage_dyn = [&](uint32_t buf) {
+    for (int i = tid; i < dyn_len; i += kFoldThreads) dyn_s[buf * dyn_len + i] = load_dyn(buf, i);
+  };
+
   const int n_work = P.work ? *P.n_work : n_items;
   int w = blockIdx.x;
   int item = w < n_work ? (P.work ? P.work[w] : w) : n_items;
@@ -1086,6 +1102,9 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     __syncthreads();
     issue_expo(item);
     issue_epi(item);
+    mbar_wait(&bars[2], 0);
+    stage_dyn(0);
+    __syncthreads();
   }
   uint32_t parity = 0;
   int cur_ds = -1;
@@ -1124,9 +1143,9 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const unsigned char* dsc = desc_s + parity * DL.bytes;
     const int nl = reinterpret_cast<const int*>(dsc)[0], nover = reinterpret_cast<const int*>(dsc)[1];
     const InstDev* slist = reinterpret_cast<const InstDev*>(dsc + DL.inst);
-    const double* flux_s = reinterpret_cast<const double*>(dsc + DL.flux);  // [kFoldLMax][smem_nT]
-    const double* bkgfac = reinterpret_cast<const double*>(dsc + DL.bkg);
     const int* over = reinterpret_cast<const int*>(dsc + DL.over);
+    const double* flux_s = dyn_s + parity * dyn_len;              // [kFoldLMax][smem_nT]
+    const double* bkgfac = flux_s + kFoldLMax * P.smem_nT;        // [smem_nRp]
     const int fstride = P.smem_nT;
     GPY_TICK(0);
     GPY_TICK(1);
@@ -1324,6 +1343,15 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         }
       }
       __syncthreads();
+      // next item's per-step numbers: the loads are issued before the Cash pass and stored to shared memory after
+      // it (few registers are live here), so the pass covers their latency; the end-of-item barrier publishes them
+      const bool stage_next = cbase + 4 >= nchunks && next < n_items;
+      double dyn0 = 0.0, dyn1 = 0.0;
+      if (stage_next) {
+        mbar_wait(&bars[2], parity ^ 1u);  // the next descriptor, requested after this item's first barrier
+        if (tid < dyn_len) dyn0 = load_dyn(parity ^ 1u, tid);
+        if (tid + kFoldThreads < dyn_len) dyn1 = load_dyn(parity ^ 1u, tid + kFoldThreads);
+      }
       {
         const int nr = min(nR - r0, 32);
         for (int i = tid; i < nr * kFoldTPX; i += kFoldThreads) {
@@ -1349,6 +1377,12 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
             }
           }
         }
+      }
+      if (stage_next) {
+        double* dst = dyn_s + (parity ^ 1u) * dyn_len;
+        if (tid < dyn_len) dst[tid] = dyn0;
+        if (tid + kFoldThreads < dyn_len) dst[tid + kFoldThreads] = dyn1;
+        for (int i = tid + 2 * kFoldThreads; i < dyn_len; i += kFoldThreads) dst[i] = load_dyn(parity ^ 1u, i);  // long axes
       }
       if (cbase + 4 < nchunks) __syncthreads();  // the next sweep's phase 1 rewrites the v buffer
     }
