@@ -641,3 +641,44 @@ def test_weighted_cash_dataset(ctx):
     got = ds.stat_sum_likelihood()
     assert abs(got - want) < 1e-3
     assert_allclose(ds.stat_array().sum(), got, rtol=1e-6)
+
+
+def test_cached_work_descriptors_follow_the_state(ctx):
+    """The per-tile overlap lists are kept between calls while sources, cutouts and slots are unchanged and rebuilt
+    otherwise: a spectral step (kept), a position step (new cutout content, maybe new cutout), a per-model npred
+    (other source list), a batched call (descriptors of another shape) and back -- every result against the oracle."""
+    from gammapy_b200 import Datasets, Map, configs
+    from oracle import adapter
+
+    ds = configs.make_c2()
+    de = adapter.evaluator_for(ds, conv="exact64")
+    counts = de.fake(4)
+    ds.counts = Map.from_geom(ds._geom, data=counts, dtype=float)
+    datasets = Datasets([ds])
+
+    def check(label):
+        adapter.refresh_models(de, ds)
+        got, want = datasets.stat_sum(), de.stat_sum()
+        assert abs(got - want) < 1e-3, (label, got, want)
+        return got
+
+    base = check("first call")
+    assert datasets.stat_sum() == base                           # descriptors reused
+    ds.models["src-0"].spectral_model.index.value += 0.2
+    ds.background_model.spectral_model.norm.value = 1.07
+    check("spectral + background step")
+    ds.models["src-1"].spatial_model.lon_0.value += 0.011      # inside the cutout margin: same cutout, new cube
+    check("small move")
+    ds.models["src-2"].spatial_model.lat_0.value += 0.9        # beyond r_eval + 0.1 deg: new cutout
+    check("large move")
+    part = ds.npred_signal(model_names=["src-3"]).data           # another source list on the same handle
+    _, parts = de.npred_signal(per_model=True)
+    assert_allclose(part, parts["src-3"], rtol=1e-5, atol=1e-7 * float(parts["src-3"].max()))
+    check("after a per-model npred")
+    values, plist = datasets.parameter_vector()
+    grid = np.tile(values, (4, 1))
+    grid[1:, [i for i, p in enumerate(plist) if p.name == "amplitude"][0]] *= [1.1, 1.2, 1.3]
+    batch = datasets.stat_sum_batch(grid)
+    assert abs(batch[0] - check("after a batched call")) < 1e-6
+    ds.models["src-0"].spectral_model.amplitude.value = 0.0     # source drops out of the list
+    check("amplitude zero")
