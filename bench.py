@@ -46,6 +46,25 @@ WORKLOADS = {
 }
 
 
+def _dbg(msg):
+    if os.environ.get("GPY_BENCH_DEBUG"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
+def extra_steps(timed_wall, steps, distributed, device):
+    """Untimed steps that keep the timed loop's load up until ~0.4 s for the 50 ms clock sampler; identical on all ranks."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([timed_wall], dtype=torch.float64, device=device)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall = float(t.item())
+    if wall >= 0.4:
+        return 0
+    return int(np.ceil((0.4 - wall) / max(wall / steps, 1e-6)))
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -335,10 +354,11 @@ def run_c4(args):
         ev1.record(stream)
         stream.synchronize()
         timed_wall = time.perf_counter() - t_wall
-        k = steps
-        while time.perf_counter() - t_wall < 0.4:
+        # every rank must run the SAME number of extra steps (each step holds a collective): the count comes from
+        # the slowest rank's timed region
+        extra = extra_steps(timed_wall, steps, distributed, ctx.torch_device)
+        for k in range(steps, steps + extra):
             step_device(k)
-            k += 1
             if k % 16 == 0:
                 stream.synchronize()
         stream.synchronize()
@@ -482,12 +502,14 @@ def run_ours(args):
         if distributed:
             allreduce_stat(stat_dev, stream)
 
+    _dbg("setup done")
     for k in range(warmup):
         step_device(k)
     stream.synchronize()
     if distributed:
         dist.barrier()
     torch.cuda.synchronize()
+    _dbg("warm-up done")
     launches0 = ctx.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
@@ -500,16 +522,18 @@ def run_ours(args):
         timed_wall = time.perf_counter() - t_wall
         # nvidia-smi samples every 50 ms: when the timed region is shorter than ~0.4 s keep the very same loop
         # running (untimed) under the sampler so that the clocks line describes this workload under load
-        k = steps
-        while time.perf_counter() - t_wall < 0.4:
+        # every rank must run the SAME number of extra steps (each step holds a collective): the count comes from
+        # the slowest rank's timed region
+        extra = extra_steps(timed_wall, steps, distributed, ctx.torch_device)
+        for k in range(steps, steps + extra):
             step_device(k)
-            k += 1
             if k % 16 == 0:
                 stream.synchronize()
         stream.synchronize()
     torch.cuda.synchronize()
     if distributed:
         dist.barrier()
+    _dbg("timed loop done")
     ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
     if distributed:
@@ -528,6 +552,7 @@ def run_ours(args):
         step_device(k)
     kernel_ms, kernel_launches = ctx.kernel_time()
     ctx.kernel_timing(False)
+    _dbg("kernel timing done")
     kernel_us = 1e3 * kernel_ms / max(kernel_launches, 1)
     if distributed:
         t = torch.tensor([kernel_us], dtype=torch.float64, device=ctx.torch_device)
@@ -551,6 +576,7 @@ def run_ours(args):
             p.value = v + d
         s = sharded.stat_sum() if distributed else datasets.stat_sum()
     e2e_s = (time.perf_counter() - t0) / steps
+    _dbg("e2e loop done")
     for p, v in zip(pars, vals):
         p.value = v
     if distributed:
