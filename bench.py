@@ -611,8 +611,9 @@ def run_ours(args):
                      "step_us": ms_per_step * 1e3,
                      "note": "duration = mean of the kernel's own launches, CUDA events recorded by the library on its "
                              "stream around that launch during a repeat of the timed steps; step_us = whole step "
-                             "(K0 + prep + fold + reduce), the value above; the kernel's share of the step agrees with "
-                             "the ncu launch list (profiles/r01_launches_final_summary.txt: 91 %)"},
+                             "(K0 + fold + reduce; the work descriptors are reused while no cutout changes), the "
+                             "value above; the kernel's share of the step agrees with the ncu launch list "
+                             "(profiles/r01_launches_final_summary.txt)"},
         "setup_s": t_build,
     }
     if batch > 1:

@@ -113,8 +113,14 @@ class MapDataset:
         self._invalidate()
 
     def _data_fingerprint(self):
+        """Identity of the map arrays the HBM mirror was built from.  ``DeviceDataset`` keeps references to the
+        arrays it uploaded (``_held``), so an id cannot be reused by another array while the mirror lives."""
         maps = (self._counts, self._exposure, self._background, self._mask_safe, self._mask_fit)
-        return tuple((id(m), id(m.data), m.data.__array_interface__["data"][0]) if m is not None else None for m in maps)
+        return tuple(id(m.data) if m is not None else None for m in maps)
+
+    def _data_arrays(self):
+        maps = (self._counts, self._exposure, self._background, self._mask_safe, self._mask_fit)
+        return tuple(m.data if m is not None else None for m in maps)
 
     @property
     def _geom(self):

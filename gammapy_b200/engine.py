@@ -26,7 +26,7 @@ _SPECTRAL_ORDER = {
 
 
 def _ptr(arr):
-    return arr.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(arr.__array_interface__["data"][0])
 
 
 class DeviceDataset:
@@ -42,6 +42,7 @@ class DeviceDataset:
         self.torch = torch
         self._keep = {}
         self._uploaded = {}
+        self._held = ()
         self._build()
 
     def _to_device(self, name, arr, dtype):
@@ -115,6 +116,7 @@ class DeviceDataset:
         _lib.check(self.ctx.lib.gpy_dataset_create(self.ctx.handle, C.byref(desc), C.byref(handle)))
         self.handle = handle
         self._uploaded = ds._data_fingerprint()
+        self._held = ds._data_arrays()
 
     def _upload_counts(self):
         counts = np.asarray(self.dataset.counts.data)
@@ -128,6 +130,7 @@ class DeviceDataset:
         self.torch.cuda.synchronize(self.ctx.torch_device)
         _lib.check(self.ctx.lib.gpy_dataset_set_counts(self.handle, C.c_void_p(t.data_ptr())))
         self._uploaded = self.dataset._data_fingerprint()
+        self._held = self.dataset._data_arrays()
 
     def close(self):
         if self.handle is not None:
@@ -213,10 +216,9 @@ class LikelihoodEngine:
     # -- evaluation ----------------------------------------------------------------------------------
     def values(self):
         """Current parameter values as the [n_par] vector."""
-        out = np.zeros(self.n_par, dtype=float)
-        for i, par in enumerate(self.parameters):
-            out[i] = par._value
-        return out
+        if not self.parameters:
+            return np.zeros(self.n_par, dtype=float)
+        return np.array([par._value for par in self.parameters], dtype=float)
 
     def stat_sum(self, values=None, per_dataset=False):
         """Datasets.stat_sum for one ([n_par]) or many ([B, n_par]) parameter vectors."""

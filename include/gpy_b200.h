@@ -137,15 +137,18 @@ int gpy_dataset_source_state(const gpy_dataset_t* ds, int32_t source, gpy_source
  *   stat_per_dataset HOST [n_vec, n_datasets] or NULL
  * n_vec == 1 advances the evaluators' cache state exactly like one reference evaluation
  * (MapEvaluator.needs_update / update / parameters_spatial_changed).  n_vec > 1 evaluates each
- * vector from the current state without mutating it (profile scans, finite-difference gradients).
+ * vector from the current state without mutating it (profile scans, finite-difference gradients);
+ * work items (tile, vector) whose inputs equal those of vector 0 on the same tile are evaluated once,
+ * so put the base point of a scan or gradient first.
  */
 int gpy_stat_sum(gpy_context_t* ctx, gpy_dataset_t* const* datasets, int32_t n_datasets,
                  const double* params, int32_t n_vec, int32_t n_par, double* stat,
                  double* stat_per_dataset);
 
 /* Same evaluation, leaving the per-(vector, dataset) stats on the device:
- *   stat_device DEVICE [n_vec, n_datasets] float64.  No host synchronisation: the caller owns the
- *   stream order (e.g. an NCCL all-reduce of the buffer on the same stream). */
+ *   stat_device DEVICE [n_vec, n_datasets] float64.  No host synchronisation for n_vec == 1: the
+ *   caller owns the stream order (e.g. an NCCL all-reduce of the buffer on the same stream).  A call
+ *   with n_vec > 1 waits once, for the 4-byte length of its worklist, before it launches the fold. */
 int gpy_stat_sum_device(gpy_context_t* ctx, gpy_dataset_t* const* datasets, int32_t n_datasets,
                         const double* params, int32_t n_vec, int32_t n_par, double* stat_device);
 
