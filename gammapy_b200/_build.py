@@ -39,7 +39,8 @@ def build(force=False, verbose=False):
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libgpy_b200.so")
     with open(os.path.join(HERE, "csrc", "ptxas_info.txt"), "w") as fh:
-        fh.write(res.stderr)
+        # registers / spills / shared memory per kernel (-Xptxas -v); compile times change from build to build
+        fh.write("".join(l for l in res.stderr.splitlines(keepends=True) if "Compile time" not in l))
     return LIB
 
 
