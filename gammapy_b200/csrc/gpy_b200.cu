@@ -668,7 +668,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   std::vector<size_t> job_flux_off;
   std::map<FluxKey, size_t> flux_seen;
   size_t flux_len = 0;
-  int n_tiles = 0, max_inst = 1;
+  int n_tiles = 0, max_inst = 1, max_tile_overlap = 0;
   int max_nT = 0, max_nR = 0, max_nRp = 0, max_G = 0, max_pdfc_rows = 1;
   bool tma_ok = true;
   const bool sequential = (B == 1);
@@ -831,6 +831,26 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       }
       ev.inst_count = (int)insts.size() - ev.inst_begin;
       max_inst = std::max(max_inst, ev.inst_count);
+      // Sources that can overlap ONE tile (what a work descriptor must hold).  With few sources the count itself
+      // is the bound; otherwise the largest number of cutouts that touch the rows a tile can span.
+      if (ev.inst_count <= gpy::kFoldLMax + gpy::kDescOverflow) {
+        max_tile_overlap = std::max(max_tile_overlap, ev.inst_count);
+      } else {
+        const int ny = ds->geom.ny, span = (gpy::kFoldTPX + ds->geom.nx - 1) / ds->geom.nx;  // extra rows a tile reaches
+        std::vector<int> cover((size_t)ny + 2, 0);
+        for (int i = ev.inst_begin; i < ev.inst_begin + ev.inst_count; ++i) {
+          const int lo = std::max(insts[i].y0 - span, 0), hi = std::min(insts[i].y0 + insts[i].cy, ny);
+          if (hi > lo) {
+            cover[lo] += 1;
+            cover[hi] -= 1;
+          }
+        }
+        int run = 0;
+        for (int y = 0; y < ny; ++y) {
+          run += cover[y];
+          max_tile_overlap = std::max(max_tile_overlap, run);
+        }
+      }
       ev.differs_all = 0;
       ev.diff_begin = (int)diffs.size();
       if (b > 0) {  // which sources differ from vector 0's: merge walk over the two lists (both in source order)
@@ -869,7 +889,8 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       tma_ok = false;
   }
   const gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G, max_pdfc_rows);
-  if (lay.total > (size_t)c->max_smem_optin || c->force_generic || max_inst > gpy::kFoldLMax + gpy::kDescOverflow)
+  if (lay.total > (size_t)c->max_smem_optin || c->force_generic ||
+      max_tile_overlap > gpy::kFoldLMax + gpy::kDescOverflow)
     tma_ok = false;
   size_t max_fold_smem = 0;
   if (!tma_ok) {

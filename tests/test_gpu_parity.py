@@ -682,3 +682,15 @@ def test_cached_work_descriptors_follow_the_state(ctx):
     assert abs(batch[0] - check("after a batched call")) < 1e-6
     ds.models["src-0"].spectral_model.amplitude.value = 0.0     # source drops out of the list
     check("amplitude zero")
+
+
+def test_more_sources_than_a_descriptor_holds(ctx):
+    """70 sources on one dataset: more than the 64 a work descriptor can list, but far fewer on any one tile, so the
+    staged kernel still runs (the bound is per tile, from the cutout rows); npred and stat against the oracle."""
+    from gammapy_b200 import configs
+
+    ds = configs.make_c3(width=(8.0, 4.0), n_sources=70, n_reco=10, n_true=20)
+    assert len(ds.models) == 71
+    stat, want, npred, npred_want = _stat_pair(ds, seed=9)
+    assert_allclose(npred, npred_want, rtol=1e-5, atol=1e-12 * npred_want.max())
+    assert abs(stat - want) < 1e-3
