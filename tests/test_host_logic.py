@@ -125,3 +125,35 @@ def test_oracle_adapter_roundtrip():
     assert len(de.evaluators) == 5 and de.bkg_model is not None
     assert de.ds.exposure.shape == (20, 100, 100) and de.ds.edisp.shape == (20, 10)
     assert_allclose(de.ds.energy_center, ds._geom.axes["energy"].center)
+
+
+def test_ts_map_host_logic():
+    """Argument checks and the default position mask of the TS-map front end run before any device call."""
+    import pytest
+
+    from gammapy_b200.estimators import BrentqFluxEstimator, TSMapEstimator, compute_ts_map
+
+    counts = np.zeros((2, 5, 6))
+    with pytest.raises(ValueError):
+        compute_ts_map(counts, counts[:1], counts, np.ones((2, 3, 3)))          # shapes differ
+    with pytest.raises(ValueError):
+        compute_ts_map(counts, counts, counts, np.ones((1, 3, 3)))              # one kernel plane per map plane
+    with pytest.raises(ValueError):
+        compute_ts_map(np.zeros(5), np.zeros(5), np.zeros(5), np.ones((1, 3, 3)))
+    with pytest.raises(NotImplementedError):
+        BrentqFluxEstimator(rtol=0.01, n_sigma=1, selection_optional=["ul"])
+    with pytest.raises(NotImplementedError):
+        BrentqFluxEstimator(rtol=0.01, n_sigma=1, ts_threshold=4.0)
+    # estimators/map/ts.py:500-505: any plane selected and a positive summed background
+    mask = np.zeros((2, 5, 6), dtype=bool)
+    mask[1, 2:4, 1:5] = True
+    background = np.ones((2, 5, 6))
+    background[:, 3, 4] = 0.0
+    got = TSMapEstimator._estimate_mask_2d({"mask": mask, "background": background})
+    want = np.zeros((5, 6), dtype=bool)
+    want[2:4, 1:5] = True
+    want[3, 4] = False
+    assert np.array_equal(got, want)
+    with pytest.raises(ValueError, match="No valid positions"):
+        TSMapEstimator().estimate_flux_map({"mask": np.zeros((1, 5, 6), dtype=bool), "background": background[:1],
+                                            "counts": counts[:1], "exposure": counts[:1], "kernel": np.ones((1, 3, 3))})
