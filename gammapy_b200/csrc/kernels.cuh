@@ -1353,27 +1353,31 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         if (tid + kFoldThreads < dyn_len) dyn1 = load_dyn(parity ^ 1u, tid + kFoldThreads);
       }
       {
+        // Two neighbouring pixels per thread and iteration (npx is even: P % 16 == 0 on this path): one 128-bit load
+        // of mu, one 64-bit load of the counts, one 16-bit load of the mask.  Most bins of a gamma-ray cube hold no
+        // count, so the log is the rare branch and the pass is bound by its loads and index arithmetic.
         const int nr = min(nR - r0, 32);
-        for (int i = tid; i < nr * kFoldTPX; i += kFoldThreads) {
-          const int rr = i >> 7, lp = i & (kFoldTPX - 1);  // kFoldTPX == 128
+        const bool has_counts = D.counts != nullptr, has_mask = D.mask != nullptr;
+        const double log_trunc = P.log_trunc;
+        for (int i = tid; i < nr * (kFoldTPX / 2); i += kFoldThreads) {
+          const int rr = i >> 6, lp = (i & (kFoldTPX / 2 - 1)) * 2;  // kFoldTPX == 128
           if (lp >= npx) continue;
           const int r = r0 + rr;
-          const double mu = mus[i];
-          if (WRITE_NPRED) P.npred_out[(size_t)r * D.P + p0 + lp] = mu;
-          if (D.counts) {
-            const bool m = D.mask ? ms[r * kFoldTPX + lp] != 0 : true;
-            if (m) {
-              const double n = (double)cs[r * kFoldTPX + lp];
-              double npr, lognpr = 0.0;
-              if (mu > kTrunc) {
-                npr = mu;
-                if (n > 0.0) lognpr = log(mu);
-              } else {
-                npr = kTrunc;
-                lognpr = P.log_trunc;
+          const double2 mu2 = *reinterpret_cast<const double2*>(mus + rr * kFoldTPX + lp);
+          if (WRITE_NPRED)
+            *reinterpret_cast<double2*>(P.npred_out + (size_t)r * D.P + p0 + lp) = mu2;
+          if (has_counts) {
+            const float2 n2 = *reinterpret_cast<const float2*>(cs + r * kFoldTPX + lp);
+            const unsigned m2 = has_mask ? *reinterpret_cast<const unsigned short*>(ms + r * kFoldTPX + lp) : 0x0101u;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const double mu = u == 0 ? mu2.x : mu2.y;
+              const float nf = u == 0 ? n2.x : n2.y;
+              if ((m2 >> (8 * u)) & 0xffu) {
+                const bool big = mu > kTrunc;
+                stat += big ? mu : kTrunc;
+                if (nf > 0.f) stat -= (double)nf * (big ? log(mu) : log_trunc);
               }
-              stat += npr;
-              if (n > 0.0) stat -= n * lognpr;
             }
           }
         }
