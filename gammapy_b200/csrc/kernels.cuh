@@ -1251,19 +1251,6 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
                 s2 = fma(F, (double)cv.z, s2);
                 s3 = fma(F, (double)cv.w, s3);
               }
-              for (int o = 0; o < nover; ++o) {  // rare: more than kFoldLMax sources on one tile
-                const InstDev& in = P.insts[over[o]];
-                if (in.group != g) continue;
-                const int ly = qy - in.y0, lx = qx - in.x0a;
-                if (ly < 0 || ly >= in.cy || lx < 0 || lx >= in.pitch) continue;
-                const float4 cv = __ldg(reinterpret_cast<const float4*>(in.conv + (size_t)t * in.plane_stride +
-                                                                        ly * in.pitch + lx));
-                const double F = P.flux[in.flux_off + t];
-                s0 = fma(F, (double)cv.x, s0);
-                s1 = fma(F, (double)cv.y, s1);
-                s2 = fma(F, (double)cv.z, s2);
-                s3 = fma(F, (double)cv.w, s3);
-              }
               const float4 e = *reinterpret_cast<const float4*>(es + t * kFoldTPX + 4 * q);
               s0 = (s0 * (double)e.x) * 1e4;
               s1 = (s1 * (double)e.y) * 1e4;
@@ -1273,6 +1260,36 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
             double* dst = vs + ((size_t)g * kTmaTCH + tl) * kFoldTPX + 4 * q;
             *reinterpret_cast<double2*>(dst) = make_double2(s0, s1);
             *reinterpret_cast<double2*>(dst + 2) = make_double2(s2, s3);
+          }
+          // Further sources on this tile (dense fields: more than kFoldLMax cutouts overlap): one source at a time,
+          // its loads of the pass' four slots in flight together, added to the values this thread just stored.
+          if (qlive) {
+            for (int o = 0; o < nover; ++o) {
+              const InstDev& in = P.insts[over[o]];
+              if (in.group != g) continue;
+              const int ly = qy - in.y0, lx = qx - in.x0a;
+              if (ly < 0 || ly >= in.cy || lx < 0 || lx >= in.pitch) continue;
+              const float* base = in.conv + ly * in.pitch + lx;
+              float4 co[kTmaTCH / 8];
+#pragma unroll
+              for (int tt = 0; tt < kTmaTCH / 8; ++tt)
+                co[tt] = __ldg(reinterpret_cast<const float4*>(base + (size_t)min(t0 + slot + 8 * tt, nT - 1) * in.plane_stride));
+#pragma unroll
+              for (int tt = 0; tt < kTmaTCH / 8; ++tt) {
+                const int tl = slot + 8 * tt, t = t0 + tl;
+                if (t >= nT) continue;
+                const double F = __ldg(P.flux + in.flux_off + t);
+                const float4 e = *reinterpret_cast<const float4*>(es + t * kFoldTPX + 4 * q);
+                double* dst = vs + ((size_t)g * kTmaTCH + tl) * kFoldTPX + 4 * q;
+                double2 a = *reinterpret_cast<double2*>(dst), b2 = *reinterpret_cast<double2*>(dst + 2);
+                a.x += ((F * (double)co[tt].x) * (double)e.x) * 1e4;
+                a.y += ((F * (double)co[tt].y) * (double)e.y) * 1e4;
+                b2.x += ((F * (double)co[tt].z) * (double)e.z) * 1e4;
+                b2.y += ((F * (double)co[tt].w) * (double)e.w) * 1e4;
+                *reinterpret_cast<double2*>(dst) = a;
+                *reinterpret_cast<double2*>(dst + 2) = b2;
+              }
+            }
           }
         }
         GPY_TICK(4);
