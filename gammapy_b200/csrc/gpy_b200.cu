@@ -266,10 +266,11 @@ struct gpy_context {
   double* stat_pinned = nullptr;
   int* nwork_pinned = nullptr;  // read-back of the batched worklist length
   size_t stat_pinned_cap = 0;
-  size_t ts_smem_set = 0, fold_smem_set = 0, conv_smem_set = 0, tma_smem_set[2] = {0, 0};
+  size_t ts_smem_set = 0, fold_smem_set = 0, conv_smem_set = 0, tma_smem_set[4] = {0, 0, 0, 0};
   int tma_blocks_per_sm[2] = {0, 0};
   int num_sms = 0;
   bool force_generic = false;
+  bool static_schedule = false;  // GPY_STATIC_SCHEDULE: never claim items dynamically
   bool no_desc_cache = false;  // GPY_NO_DESC_CACHE: run prep_items_kernel on every call
   std::vector<uint8_t> desc_key;  // what the descriptors in `desc` were built from (empty: none)
   bool no_dedup = false;  // GPY_NO_DEDUP: evaluate every item of a batch even when identical to vector 0's
@@ -1076,17 +1077,26 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       c->desc_key.swap(key);  // empty after a batched call: the next B == 1 call rebuilds
     }
     fp.desc = (const unsigned char*)c->desc.p;
-    auto kern = variant ? gpy::fold_cash_tma_kernel<true> : gpy::fold_cash_tma_kernel<false>;
-    if (lay.total > c->tma_smem_set[variant]) {
+    // Items differ in cost (source-free tiles are light): with many items per CTA they are claimed dynamically.
+    // (grid <= 2 CTAs per SM; 8 items per CTA at least.)
+    const bool dynamic = B == 1 && n_work_host >= (size_t)16 * c->num_sms && !c->static_schedule;
+    auto kern = variant ? (dynamic ? gpy::fold_cash_tma_kernel<true, true> : gpy::fold_cash_tma_kernel<true, false>)
+                        : (dynamic ? gpy::fold_cash_tma_kernel<false, true> : gpy::fold_cash_tma_kernel<false, false>);
+    const int kslot = variant * 2 + (dynamic ? 1 : 0);
+    if (lay.total > c->tma_smem_set[kslot]) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
-      c->tma_smem_set[variant] = lay.total;
+      c->tma_smem_set[kslot] = lay.total;
     }
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, gpy::kFoldThreads, lay.total));
     per_sm = std::max(per_sm, 1);
     const unsigned grid = (unsigned)std::min(n_work_host, (size_t)per_sm * c->num_sms);
+    if (dynamic) {
+      fp.counter = (unsigned*)((uint8_t*)c->zeros.p + 128);
+      CUDA_TRY(cudaMemsetAsync(fp.counter, 0, sizeof(unsigned), c->stream));
+    }
     if (c->timing) {
       GPY_TRY(timing_collect(c));
       CUDA_TRY(cudaEventRecord(c->t_begin, c->stream));
@@ -1153,6 +1163,7 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
   c->force_generic = std::getenv("GPY_FORCE_GENERIC_FOLD") != nullptr;
   c->no_dedup = std::getenv("GPY_NO_DEDUP") != nullptr;
+  c->static_schedule = std::getenv("GPY_STATIC_SCHEDULE") != nullptr;
   c->no_desc_cache = std::getenv("GPY_NO_DESC_CACHE") != nullptr;
   if (const char* m = std::getenv("GPY_FOLD_KERNEL")) c->fold_mode = std::atoi(m);
   if (c->fold_mode == 2) c->force_generic = true;

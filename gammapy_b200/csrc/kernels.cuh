@@ -468,6 +468,7 @@ struct FoldParams {
   unsigned lay_es, lay_bs, lay_cs, lay_ms, lay_vs, lay_pdf, lay_desc, lay_dyn, lay_bars;
   int dl_inst, dl_over, dl_bytes;
   const double* bkgfac;     // [n_datasets * B][smem_nRp] background factors norm (E/E0)^-tilt (K0), index d * B + b
+  unsigned* counter;        // work-stealing counter (0 at launch): items beyond a CTA's first are claimed in order; null: static
   const int* work;          // [*n_work] item indices to evaluate, or null: all B * n_tiles items (B == 1)
   const int* n_work;
   const float* zeros;       // >= 16 bytes of zeros: load target of (thread, source) pairs outside the cutout
@@ -964,7 +965,7 @@ __host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int
   return L;
 }
 
-template <bool WRITE_NPRED>
+template <bool WRITE_NPRED, bool DYNAMIC>
 __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const FoldParams P) {
   extern __shared__ __align__(128) unsigned char fold_raw[];
   float* es = reinterpret_cast<float*>(fold_raw + P.lay_es);
@@ -981,6 +982,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   DL.bytes = P.dl_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + P.lay_bars);  // [0] exposure, [1] epilogue inputs, [2] descriptor
   __shared__ double wsum[kFoldThreads / 32];
+  __shared__ int2 nxt_s;  // {worklist position, item} claimed for the next iteration
 
   const int tid = threadIdx.x;
   const int n_items = P.B * P.n_tiles;
@@ -1127,8 +1129,28 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const int nT = D.nT, nR = D.nR, nRp = D.nRp, G = D.n_groups;
     const int p0 = (tile - D.tile_begin) * kFoldTPX;
     const int npx = min(kFoldTPX, (int)D.P - p0);
-    w += gridDim.x;
-    const int next = w < n_work ? (P.work ? __ldg(P.work + w) : w) : n_items;  // n_items: no further item
+    // The next item is claimed from a global counter (items differ in cost: a static round-robin leaves a tail).
+    // Thread 0 claims it here and needs it at once (it arms the next copies); the others pick it up from shared
+    // memory after the first barrier of this item, before their first use.
+    // (DYNAMIC == false: static round-robin, for few items per CTA or a batched call of many light items.)
+    int wn = w + gridDim.x;
+    int next = n_items;  // n_items: no further item
+    bool have_next = !DYNAMIC || tid == 0;
+    if (!DYNAMIC) {
+      next = wn < n_work ? (P.work ? __ldg(P.work + wn) : wn) : n_items;
+    } else if (tid == 0) {
+      wn = gridDim.x + atomicAdd(P.counter, 1u);
+      next = wn < n_work ? (P.work ? __ldg(P.work + wn) : wn) : n_items;
+      nxt_s = make_int2(wn, next);
+    }
+    auto sync_next = [&]() {  // call after a CTA barrier of this item
+      if (DYNAMIC && !have_next) {
+        const int2 v = nxt_s;
+        wn = v.x;
+        next = v.y;
+        have_next = true;
+      }
+    };
 
     if (d != cur_ds) {  // edisp matrices of this dataset (block-uniform branch)
       for (int i = tid; i < D.pdfc_rows * 8; i += kFoldThreads) pdf_s[i] = D.pdfc[i];
@@ -1184,7 +1206,8 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         if (cbase == 0) mbar_wait(&bars[0], parity);
         if (tid == 0 && cbase + 4 >= nchunks && next < n_items) arm_expo(next);
         __syncthreads();
-        if (!desc_fetched && tid == 0 && next < n_items) fetch_desc(w, parity ^ 1u);
+        sync_next();
+        if (!desc_fetched && tid == 0 && next < n_items) fetch_desc(wn, parity ^ 1u);
         desc_fetched = true;
         if (cbase + 4 >= nchunks && next < n_items) issue_expo(next);
       }
@@ -1293,11 +1316,12 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
           }
         }
         GPY_TICK(4);
-        const bool fetch_next = cbase + 4 >= nchunks && t0 + kTmaTCH >= nT && next < n_items;
-        if (tid == 0 && fetch_next) arm_expo(next);
+        if (tid == 0 && cbase + 4 >= nchunks && t0 + kTmaTCH >= nT && next < n_items) arm_expo(next);
         __syncthreads();
+        sync_next();
+        const bool fetch_next = cbase + 4 >= nchunks && t0 + kTmaTCH >= nT && next < n_items;
         GPY_TICK(5);
-        if (!desc_fetched && tid == 0 && next < n_items) fetch_desc(w, parity ^ 1u);
+        if (!desc_fetched && tid == 0 && next < n_items) fetch_desc(wn, parity ^ 1u);
         desc_fetched = true;
         // exposure tile fully consumed: start fetching the next item's while phase 2 / the epilogue run
         if (fetch_next) issue_expo(next);
@@ -1419,6 +1443,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     GPY_TICK(10);
     if (next < n_items) issue_epi(next);
     item = next;
+    w = wn;
     GPY_TICK(11);
   }
 #ifdef GPY_FOLD_TIMING
