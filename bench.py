@@ -565,7 +565,7 @@ def run_ours(args):
         kernel_us = float(t.item())
     achieved = alg_bytes / (kernel_us * 1e-6) / 1e9
     # DRAM bytes of one launch from the committed ncu --set full capture of this kernel on this workload
-    traffic = 661.1e6 if args.workload == "c3" else None  # 657.0 MB read + 4.1 MB written
+    traffic = 642.4e6 if args.workload == "c3" else None  # 637.7 MB read + 4.7 MB written
 
     # end to end through the public API: Parameter objects -> Datasets.stat_sum() -> python float
     pars = [engine.parameters[c] for c in cols]
