@@ -960,7 +960,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   if (!jobs.empty()) {
     int seg_cap = 0;  // doubles of shared memory for the per-segment integrals (falls back to the serial loop)
     for (const auto& j : jobs)
-      if (j.type != 0 && j.type != gpy::kFluxJobBackground) seg_cap = std::max(seg_cap, j.n_bins * (j.n_nodes - 1));
+      if (j.type != 0 && j.type != gpy::kFluxJobBackground) seg_cap = std::max(seg_cap, j.n_bins * (2 * j.n_nodes - 1));
     seg_cap = std::min(seg_cap, 5120);  // 40 KB
     gpy::spectral_flux_kernel<<<(unsigned)jobs.size(), seg_cap ? 256 : 64, (size_t)seg_cap * sizeof(double),
                                 c->stream>>>((const gpy::FluxJob*)(base + off_jb), seg_cap);
@@ -1698,7 +1698,7 @@ int gpy_spectral_integral(gpy_context_t* c, int32_t spectral_type, const double*
   CUDA_TRY(cudaMemcpyAsync(d_edges, edges, (n_bins + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   if (nn) CUDA_TRY(cudaMemcpyAsync(d_nodes, nodes, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(d_job, &job, sizeof(job), cudaMemcpyHostToDevice, c->stream));
-  const int seg_cap = spectral_type == GPY_SPECTRAL_PL ? 0 : std::min(n_bins * std::max(n_nodes - 1, 0), 5120);
+  const int seg_cap = spectral_type == GPY_SPECTRAL_PL ? 0 : std::min(n_bins * std::max(2 * n_nodes - 1, 0), 5120);
   gpy::spectral_flux_kernel<<<1, seg_cap ? 256 : 64, (size_t)seg_cap * sizeof(double), c->stream>>>(d_job, seg_cap);
   c->launches++;
   CUDA_TRY(cudaGetLastError());

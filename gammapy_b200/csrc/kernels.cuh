@@ -358,13 +358,18 @@ __global__ void spectral_flux_kernel(const FluxJob* __restrict__ jobs, int seg_c
   __shared__ int bad;
   if (threadIdx.x == 0) bad = 0;
   const int nseg = job.n_nodes - 1;
-  const bool staged = job.type != 0 && job.n_bins * nseg <= seg_cap;
+  // staged: the model is evaluated once per node (one thread each), then one thread per segment integrates between
+  // two stored values; the buffer holds the node values followed by the segment integrals
+  const bool staged = job.type != 0 && job.n_bins * (nseg + job.n_nodes) <= seg_cap;
+  double* yv = seg + job.n_bins * nseg;  // [n_bins][n_nodes]
   if (staged) {
+    for (int w = threadIdx.x; w < job.n_bins * job.n_nodes; w += blockDim.x) yv[w] = spectral_eval(job.type, job.p, job.nodes[w]);
+    __syncthreads();
     for (int w = threadIdx.x; w < job.n_bins * nseg; w += blockDim.x) {
       const int t = w / nseg, k = w - t * nseg;
       const double* nd = job.nodes + (size_t)t * job.n_nodes + k;
       const double e0 = nd[0], e1 = nd[1];
-      const double y0 = spectral_eval(job.type, job.p, e0), y1 = spectral_eval(job.type, job.p, e1);
+      const double y0 = yv[t * job.n_nodes + k], y1 = yv[t * job.n_nodes + k + 1];
       double index = -log_scale(y0 / y1) / log_scale(e0 / e1);
       if (isnan(index)) index = INFINITY;
       seg[w] = pl_integral(e0, e1, index, y0, e0);
