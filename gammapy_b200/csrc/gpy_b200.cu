@@ -1175,6 +1175,36 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
     }
   }
   c->log_trunc = std::log((double)(float)1e-25);  // Cython: log(<float>TRUNCATION_VALUE), .pyx:35
+  // CUDA loads a kernel's code on its first use (lazy module loading): tens of milliseconds in the middle of a fit
+  // the first time a source moves, a batched call arrives or an npred cube is asked for.  Touch every kernel now.
+  {
+    cudaFuncAttributes fa;
+    const void* kernels[] = {
+        (const void*)gpy::solid_angle_kernel,
+        (const void*)gpy::spatial_fill_kernel,
+        (const void*)gpy::spatial_oversample_kernel,
+        (const void*)gpy::psf_conv_kernel,
+        (const void*)gpy::spectral_flux_kernel,
+        (const void*)gpy::prep_items_kernel,
+        (const void*)gpy::dedup_flag_kernel,
+        (const void*)gpy::dedup_scan_kernel,
+        (const void*)gpy::dedup_scatter_kernel,
+        (const void*)gpy::fold_cash_tma_kernel<false, false>,
+        (const void*)gpy::fold_cash_tma_kernel<false, true>,
+        (const void*)gpy::fold_cash_tma_kernel<true, false>,
+        (const void*)gpy::fold_cash_tma_kernel<true, true>,
+        (const void*)gpy::fold_cash_generic_kernel,
+        (const void*)gpy::reduce_stat_kernel,
+        (const void*)gpy::cash_sum_kernel,
+        (const void*)gpy::final_sum_kernel,
+        (const void*)gpy::ts_map_kernel,
+        (const void*)gpy::ts_map_strip_kernel,
+        (const void*)gpy::f_cash_root_kernel,
+        (const void*)gpy::norm_bounds_kernel,
+    };
+    for (const void* k : kernels) (void)cudaFuncGetAttributes(&fa, k);
+    (void)cudaGetLastError();
+  }
   *out = c;
   return GPY_OK;
 }
