@@ -600,11 +600,14 @@ int get_slot(gpy_dataset* ds, Source& src, const double* sp, const Rect& rect, u
   const bool conv = ds->has_psf && src.desc.apply_psf;
   s.planes = conv ? ds->nT : 1;
   const size_t img = (size_t)rect.cy * s.pitch;
-  GPY_TRY(s.w.reserve(img * sizeof(float), c->stream));
+  // A cutout changes its size by a pixel or two as the source moves (odd npix, ceil rules, trimming at the map
+  // edge): allocate with headroom, a pool allocation that has to grow costs milliseconds in the middle of a fit.
+  const size_t img_cap = (size_t)(rect.cy + 4) * (s.pitch + 8);
+  if (img * sizeof(float) > s.w.cap) GPY_TRY(s.w.reserve(img_cap * sizeof(float), c->stream));
   GPY_TRY(compute_spatial(c, ds->geom, (const double*)ds->d_omega.p, rect, src.desc.spatial_type, sp,
                           (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f));
   if (conv) {
-    GPY_TRY(s.conv.reserve(img * ds->nT * sizeof(float), c->stream));
+    if (img * ds->nT * sizeof(float) > s.conv.cap) GPY_TRY(s.conv.reserve(img_cap * ds->nT * sizeof(float), c->stream));
     GPY_TRY(launch_conv(c, (const float*)s.w.p, rect.cy, rect.cx, s.pitch, rect.x0 - s.x0a,
                         (const float*)ds->d_kflip.p, (const gpy::ConvPlane*)ds->d_planes.p, ds->nT, ds->max_h,
                         ds->max_kw, (float*)s.conv.p));
