@@ -7,8 +7,11 @@
 //   K3+K4 fold_cash_tma_kernel (bulk-copy staged, persistent) / fold_cash_generic_kernel (any shape)
 //                              exposure x flux -> edisp contraction -> + background -> masked Cash,
 //                              fp64 accumulate, batch of parameter vectors per launch  (a2-a6, a12-a14)
+//   prep_items_kernel          per-tile work descriptors (overlap lists); cached by the host across steps
+//   dedup_*_kernel             batched calls: worklist of the (tile, vector) items that differ from vector 0
 //   reduce_stat_kernel         deterministic second stage of the stat reduction
 //   cash_sum_kernel            stand-alone (weighted) Cash for the compiled-stat registry (a3, a3')
+// The TS-map kernels and the other two registry entries live in tsmap.cuh.
 //
 // Reference citations are relative to /root/reference/gammapy.
 #pragma once
