@@ -261,6 +261,52 @@ def _hesse(like, x, f0):
     return hess
 
 
+def _brentq(f, xa, xb, xtol=2e-12, rtol=8.881784197001252e-16, maxiter=100):
+    """Brent's root bracketing as scipy.optimize.brentq implements it (what utils/roots.py:find_roots calls with
+    nbin=1).  Returns (root, iterations, converged); (nan, 0, False) when f(xa) and f(xb) do not bracket a root."""
+    xpre, xcur = float(xa), float(xb)
+    xblk = fblk = spre = scur = 0.0
+    fpre, fcur = f(xpre), f(xcur)
+    if not (np.isfinite(fpre) and np.isfinite(fcur)):
+        return np.nan, 0, False
+    if fpre == 0:
+        return xpre, 0, True
+    if fcur == 0:
+        return xcur, 0, True
+    if np.sign(fpre) == np.sign(fcur):
+        return np.nan, 0, False
+    for it in range(1, maxiter + 1):
+        if fpre != 0 and fcur != 0 and np.sign(fpre) != np.sign(fcur):
+            xblk, fblk = xpre, fpre
+            spre = scur = xcur - xpre
+        if abs(fblk) < abs(fcur):
+            xpre, xcur, xblk = xcur, xblk, xcur
+            fpre, fcur, fblk = fcur, fblk, fcur
+        delta = (xtol + rtol * abs(xcur)) / 2
+        sbis = (xblk - xcur) / 2
+        if fcur == 0 or abs(sbis) < delta:
+            return xcur, it, True
+        if abs(spre) > delta and abs(fcur) < abs(fpre):
+            if xpre == xblk:
+                stry = -fcur * (xcur - xpre) / (fcur - fpre)
+            else:
+                dpre = (fpre - fcur) / (xpre - xcur)
+                dblk = (fblk - fcur) / (xblk - xcur)
+                stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre))
+            if 2 * abs(stry) < min(abs(spre), 3 * abs(sbis) - delta):
+                spre, scur = scur, stry
+            else:
+                spre = scur = sbis
+        else:
+            spre = scur = sbis
+        xpre, fpre = xcur, fcur
+        xcur += scur if abs(scur) > delta else (delta if sbis > 0 else -delta)
+        fcur = f(xcur)
+        if not np.isfinite(fcur):
+            return np.nan, it, False
+    return xcur, maxiter, False
+
+
 class Fit:
     """Fit class (modeling/fit.py:81).  ``backend`` is informational: the optimiser is the built-in batched BFGS."""
 
@@ -317,6 +363,54 @@ class Fit:
                 p.error = float(np.sqrt(var))
         self._last_like = like
         return CovarianceResult(matrix=cov, success=success, message=message)
+
+    def confidence(self, datasets, parameter, sigma=1, reoptimize=True):
+        """fit.py:302-348 with the scipy backend's method (modeling/scipy.py:50-130): on each side of the best fit
+        the root of ``stat(x) - stat(best) - sigma**2`` between the best-fit factor and ``conf_min`` / ``conf_max``,
+        the other free parameters re-optimised at every trial value when ``reoptimize``.  Returns ``errn``, ``errp``
+        (in parameter units), ``success_*``, ``message_*``, ``nfev_*`` (solver iterations) and ``stat_null``."""
+        like = _Likelihood(datasets)
+        parameter = like.datasets.parameters[parameter] if isinstance(parameter, str) else parameter
+        if len(like.free) <= 1:
+            reoptimize = False
+        opts = dict(self.confidence_opts)
+        opts.pop("backend", None)
+        rtol = opts.get("rtol", 8.881784197001252e-16)
+        xtol = opts.get("xtol", 2e-12)
+        maxiter = opts.get("maxiter", 100)
+        all_pars = list(like.engine.parameters)
+        result = {}
+        for upper, suffix in ((False, "errn"), (True, "errp")):
+            saved = [(p, p.value, p.frozen) for p in all_pars]
+            try:
+                stat_null = like.fcn(like.factors)
+                x_best = parameter.factor
+                bound = (parameter.conf_max if upper else parameter.conf_min) / parameter.scale
+
+                def ts_diff(factor):
+                    parameter.factor = factor
+                    if reoptimize:
+                        parameter.frozen = True
+                        inner = _Likelihood(like.datasets)
+                        _, value, _, _, _ = _minimize(inner, tol=self.optimize_opts.get("tol", 0.1),
+                                                      max_iter=self.optimize_opts.get("max_iter", 200))
+                    else:
+                        value = like.engine.stat_sum()
+                    return value - stat_null - sigma ** 2
+
+                root, iterations, _ = _brentq(ts_diff, x_best, bound, xtol=xtol, rtol=rtol, maxiter=maxiter)
+                ok = bool(np.isfinite(root))
+                result[suffix] = float(np.abs(root - x_best) * parameter.scale)
+                result["nfev_" + suffix] = iterations
+                result["success_" + suffix] = ok
+                result["message_" + suffix] = ("Confidence terminated successfully." if ok else
+                                               "Confidence estimation failed. Try to set the parameter.min/max by hand.")
+                result["stat_null"] = stat_null
+            finally:  # parameters.restore_status()
+                for p, v, fr in saved:
+                    p.value, p.frozen = v, fr
+        result["success"] = result["success_errn"] and result["success_errp"]
+        return result
 
     def stat_profile(self, datasets, parameter, reoptimize=False):
         """fit.py:351-422: the joint stat on ``parameter.scan_values``, all points in one launch."""

@@ -177,6 +177,24 @@ class Parameter:
         return self.error if self.error > 0.0 else np.abs(self.value)
 
     @property
+    def conf_min(self):
+        """Lower end of the confidence search (parameter.py:385-397): the minimum if set, else a wide default."""
+        if not np.isnan(self.min):
+            return self.min
+        min_ = self.value - self._step * self.scan_n_sigma
+        large_step = np.maximum(self._step, np.abs(self.value))
+        return np.minimum(min_, -large_step * 1e5)
+
+    @property
+    def conf_max(self):
+        """Upper end of the confidence search (parameter.py:401-413)."""
+        if not np.isnan(self.max):
+            return self.max
+        max_ = self.value + self._step * self.scan_n_sigma
+        large_step = np.maximum(self._step, np.abs(self.value))
+        return np.maximum(max_, large_step * 1e5)
+
+    @property
     def scan_min(self):
         if self._scan_min is None:
             return self.value - self._step * self.scan_n_sigma

@@ -147,3 +147,38 @@ def test_sharded_joint_fit_gloo_world2():
     assert len(norms) == n_datasets
     assert_allclose(norms, [1 + 0.05 * i for i in range(n_datasets)], atol=2e-3)
     assert abs(stat0 - sum(range(n_datasets))) < 1e-3
+
+
+def test_fit_confidence_on_a_quadratic_likelihood():
+    """Fit.confidence (modeling/fit.py:302-348, scipy backend semantics) on the toy likelihood, single process:
+    profile and fixed-parameter intervals against the analytic values of the quadratic form."""
+    from gammapy_b200.modeling import Fit
+
+    shared, backgrounds = _toy_models(1)
+    local_pars = list(shared.parameters) + list(backgrounds[0].parameters)
+    names = [p.name for p in local_pars]
+    i_index, i_amp, i_norm = names.index("index"), names.index("amplitude"), names.index("norm")
+
+    def local_stat(values):
+        return _toy_stat(0, values[:, i_index], values[:, i_amp], values[:, i_norm])
+
+    sharded = ShardedDatasets(None, local_stat=local_stat, global_models=[shared] + backgrounds,
+                              local_parameters=local_pars)
+    fit = Fit()
+    result = fit.run(sharded)
+    assert result.success
+    index = shared.spectral_model.index
+    best = index.value
+    assert abs(best - 2.3) < 1e-3
+    prof = fit.confidence(sharded, index, sigma=1, reoptimize=True)
+    assert prof["success"] and prof["success_errn"] and prof["success_errp"]
+    # 50 d^2 + 400 n^2 + 10 d n minimised over n: (50 - 1/16) d^2 = 1
+    assert_allclose([prof["errn"], prof["errp"]], 1 / np.sqrt(50 - 1 / 16), rtol=2e-3)
+    fixed = fit.confidence(sharded, index, sigma=2, reoptimize=False)
+    assert_allclose([fixed["errn"], fixed["errp"]], 2 / np.sqrt(50), rtol=2e-3)
+    assert index.value == best and not index.frozen              # status restored
+    assert fixed["nfev_errp"] > 0 and abs(fixed["stat_null"]) < 1e-3
+    # an interval that does not fit inside the parameter limits is reported, not invented
+    index.max = best + 0.05
+    clipped = fit.confidence(sharded, index, sigma=1, reoptimize=False)
+    assert not clipped["success_errp"] and np.isnan(clipped["errp"]) and clipped["success_errn"]
