@@ -388,6 +388,8 @@ class Fit:
                 bound = (parameter.conf_max if upper else parameter.conf_min) / parameter.scale
 
                 def ts_diff(factor):
+                    for p, v, _ in saved:  # every trial starts from the best fit: a failed one cannot spoil the next
+                        p.value = v
                     parameter.factor = factor
                     if reoptimize:
                         parameter.frozen = True

@@ -171,3 +171,25 @@ def test_joint_fit_through_sharded_datasets(ctx):
     assert len(shard.parameters) == len(joint.parameters)
     only, _ = build(indices=[0, 2])
     assert abs(shard.stat_sum() - only.stat_sum()) < 1e-9 * abs(only.stat_sum())
+
+
+def test_confidence_interval_close_to_hesse_error(ctx):
+    """Fit.confidence on the C1 likelihood: with 1.6e5 counts the profile is parabolic, so the interval of the
+    spectral index agrees with the Hesse error; the parameters come back to the best fit."""
+    from gammapy_b200 import Map, configs
+    from gammapy_b200.modeling import Fit
+    from oracle import adapter
+
+    ds = configs.make_c1(width=(2.0, 2.0), mask_radius=0.9)
+    ds.counts = Map.from_geom(ds._geom, data=adapter.evaluator_for(ds).fake(12), dtype=float)
+    fit = Fit()
+    assert fit.run(ds).success
+    index = ds.models["model-simu"].spectral_model.index
+    best, err = index.value, index.error
+    index.min, index.max = best - 10 * err, best + 10 * err      # the search range, as the reference asks for
+    res = fit.confidence(ds, index, sigma=1, reoptimize=True)
+    assert res["success"]
+    assert_allclose([res["errn"], res["errp"]], err, rtol=0.1)
+    assert index.value == best and not index.frozen
+    fixed = fit.confidence(ds, index, sigma=1, reoptimize=False)
+    assert fixed["success"] and fixed["errp"] <= res["errp"] * 1.001   # conditional interval is the narrower one
