@@ -441,14 +441,31 @@ class Fit:
         return {f"{parameter.name}_scan": values, "stat_scan": stats, "fit_results": []}
 
     def stat_surface(self, datasets, x, y, reoptimize=False):
-        """fit.py:424-519: joint stat on the (x, y) grid, one launch (chunks of 512 vectors)."""
-        if reoptimize:
-            raise NotImplementedError("stat_surface(reoptimize=True) is not implemented")
+        """fit.py:424-519: joint stat on the (x, y) grid, one launch (chunks of 512 vectors) unless ``reoptimize``."""
         like = _Likelihood(datasets)
         pars = like.datasets.parameters
         x = pars[x] if isinstance(x, str) else x
         y = pars[y] if isinstance(y, str) else y
         xv, yv = np.asarray(x.scan_values, float), np.asarray(y.scan_values, float)
+        if reoptimize:  # fit.py:480-500: x and y frozen at each grid point, the other parameters re-fitted
+            stats, results = [], []
+            saved = [(p, p.value, p.frozen) for p in like.engine.parameters]
+            try:
+                x.frozen = y.frozen = True
+                for a, b in itertools.product(xv, yv):
+                    for p, v, _ in saved:
+                        if p is not x and p is not y:
+                            p.value = v
+                    x.value, y.value = a, b
+                    res = self.optimize(like.datasets)
+                    stats.append(res.total_stat)
+                    results.append(res)
+            finally:
+                for p, v, fr in saved:
+                    p.value, p.frozen = v, fr
+            shape = (len(xv), len(yv))
+            return {f"{x.name}_scan": xv, f"{y.name}_scan": yv, "stat_scan": np.array(stats).reshape(shape),
+                    "fit_results": np.array(results, dtype=object).reshape(shape)}
         base = like.engine.values()
         cx, cy = like.engine.parameters.index(x), like.engine.parameters.index(y)
         grid = np.tile(base, (len(xv) * len(yv), 1))

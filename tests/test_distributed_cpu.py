@@ -182,3 +182,30 @@ def test_fit_confidence_on_a_quadratic_likelihood():
     index.max = best + 0.05
     clipped = fit.confidence(sharded, index, sigma=1, reoptimize=False)
     assert not clipped["success_errp"] and np.isnan(clipped["errp"]) and clipped["success_errn"]
+
+
+def test_stat_surface_with_and_without_reoptimisation():
+    from gammapy_b200.modeling import Fit
+
+    shared, backgrounds = _toy_models(1)
+    local_pars = list(shared.parameters) + list(backgrounds[0].parameters)
+    names = [p.name for p in local_pars]
+    i_index, i_amp, i_norm = names.index("index"), names.index("amplitude"), names.index("norm")
+    sharded = ShardedDatasets(None, local_stat=lambda v: _toy_stat(0, v[:, i_index], v[:, i_amp], v[:, i_norm]),
+                              global_models=[shared] + backgrounds, local_parameters=local_pars)
+    fit = Fit()
+    assert fit.run(sharded).success
+    index, norm = shared.spectral_model.index, backgrounds[0].spectral_model.norm
+    index.scan_values = [2.2, 2.3, 2.4]
+    norm.scan_values = [0.95, 1.0]
+    amp0 = shared.spectral_model.amplitude.value
+    plain = fit.stat_surface(sharded, index, norm, reoptimize=False)
+    assert plain["stat_scan"].shape == (3, 2)
+    want = np.array([[_toy_stat(0, a, amp0, b) for b in (0.95, 1.0)] for a in (2.2, 2.3, 2.4)])
+    assert_allclose(plain["stat_scan"], want, rtol=1e-9, atol=1e-9)
+    shared.spectral_model.amplitude.value = 3e-12       # off the optimum: the re-fit must bring it back at every point
+    refit = fit.stat_surface(sharded, index, norm, reoptimize=True)
+    best = np.array([[_toy_stat(0, a, 2e-12, b) for b in (0.95, 1.0)] for a in (2.2, 2.3, 2.4)])
+    assert_allclose(refit["stat_scan"], best, atol=2e-3)
+    assert refit["fit_results"].shape == (3, 2) and all(r.success for r in refit["fit_results"].ravel())
+    assert shared.spectral_model.amplitude.value == 3e-12 and not index.frozen and not norm.frozen
