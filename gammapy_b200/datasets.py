@@ -326,6 +326,17 @@ class MapDataset:
         return f"MapDataset(name={self.name!r}, geom={self._geom!r}, models={None if self._models is None else self._models.names})"
 
 
+def _parameters_with_prior(engine):
+    """The engine's parameters that carry a prior; rescanned only after a prior was assigned somewhere."""
+    from .modeling.parameter import Parameter
+
+    cached = getattr(engine, "_prior_cache", None)
+    if cached is None or cached[0] != Parameter.prior_epoch:
+        cached = (Parameter.prior_epoch, [p for p in engine.parameters if p.prior is not None])
+        engine._prior_cache = cached
+    return cached[1]
+
+
 class Datasets(list):
     """Container of datasets with a joint likelihood (datasets/core.py:140)."""
 
@@ -375,11 +386,18 @@ class Datasets(list):
         return self._engine
 
     def stat_sum(self):
-        """Joint fit statistic (datasets/core.py:264-277); no priors on this path."""
-        return self._get_engine().stat_sum()
+        """Joint fit statistic (datasets/core.py:264-277): the likelihood of all datasets (GPU) plus the priors of
+        the parameters that carry one (host)."""
+        eng = self._get_engine()
+        value = eng.stat_sum()
+        priors = _parameters_with_prior(eng)
+        if priors:
+            value += sum(p.prior(p) for p in priors)
+        return value
 
     def stat_sum_likelihood(self):
-        return self.stat_sum()
+        """Total statistic without the priors (datasets/core.py:279-284)."""
+        return self._get_engine().stat_sum()
 
     def stat_sum_batch(self, values, per_dataset=False):
         """Joint statistic for a batch of full parameter vectors [B, n_par] in ONE launch

@@ -180,8 +180,8 @@ class ShardedDatasets:
 
     def stat_sum(self):
         """``Datasets.stat_sum`` of the joint fit with the current Parameter values."""
-        if self._joint is not None:
-            return self._joint.stat_sum()
+        if self._joint is not None:  # likelihood of all ranks + the priors (evaluated identically on every rank)
+            return self._joint.stat_sum() + sum(p.prior(p) for p in self._joint.parameters if p.prior is not None)
         if self._local_stat is not None:
             raise ValueError("stat_sum() needs GPU datasets; use stat_sum_batch(values) with local_stat")
         return self.stat_sum_batch(self._local_engine().values())

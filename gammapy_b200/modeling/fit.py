@@ -30,6 +30,7 @@ class _Likelihood:
         self.engine = datasets._get_engine()
         self.free = [p for p in self.engine.parameters if not p.frozen]
         self.cols = np.array([self.engine.parameters.index(p) for p in self.free], dtype=int)
+        self.has_priors = any(p.prior is not None for p in self.engine.parameters)
         self.n_calls = 0
         self.n_launches = 0
 
@@ -49,11 +50,29 @@ class _Likelihood:
         for p, f in zip(self.free, factors):
             p.factor = f
 
+    def _prior_terms(self, vals):
+        """Prior statistic of every row of ``vals`` [B, n_par] (datasets/core.py:266-271: added to the joint stat)."""
+        total = np.zeros(vals.shape[0])
+        for col, par in enumerate(self.engine.parameters):
+            if par.prior is not None:
+                total += par.prior.evaluate_many(vals[:, col])
+        return total
+
+    def stat_values(self, vals):
+        """Joint statistic (likelihood + priors) of full parameter-value vectors ``vals`` [B, n_par], one launch."""
+        out = np.atleast_1d(self.engine.stat_sum(vals)).astype(float)
+        if self.has_priors:
+            out = out + self._prior_terms(np.atleast_2d(vals))
+        return out
+
     def fcn(self, factors):
         self.set_factors(factors)
         self.n_calls += 1
         self.n_launches += 1
-        return self.engine.stat_sum()
+        value = self.engine.stat_sum()
+        if self.has_priors:
+            value += float(self._prior_terms(self.engine.values()[np.newaxis, :])[0])
+        return value
 
     def fcn_batch(self, factors, chunk=512, base=None):
         """``base``: the point the rows of ``factors`` are small departures from (finite differences).  It rides
@@ -69,6 +88,8 @@ class _Likelihood:
             else:
                 out[i:i + chunk] = np.atleast_1d(self.engine.stat_sum(block))
             self.n_launches += 1
+        if self.has_priors:
+            out += self._prior_terms(vals)
         self.n_calls += vals.shape[0]
         return out
 
@@ -397,7 +418,7 @@ class Fit:
                         _, value, _, _, _ = _minimize(inner, tol=self.optimize_opts.get("tol", 0.1),
                                                       max_iter=self.optimize_opts.get("max_iter", 200))
                     else:
-                        value = like.engine.stat_sum()
+                        value = like.fcn(like.factors)
                     return value - stat_null - sigma ** 2
 
                 root, iterations, _ = _brentq(ts_diff, x_best, bound, xtol=xtol, rtol=rtol, maxiter=maxiter)
@@ -437,7 +458,7 @@ class Fit:
         col = like.engine.parameters.index(parameter)
         grid = np.tile(base, (len(values), 1))
         grid[:, col] = values
-        stats = np.atleast_1d(like.engine.stat_sum(grid))
+        stats = like.stat_values(grid)
         return {f"{parameter.name}_scan": values, "stat_scan": stats, "fit_results": []}
 
     def stat_surface(self, datasets, x, y, reoptimize=False):
@@ -473,6 +494,6 @@ class Fit:
             grid[k, cx], grid[k, cy] = a, b
         stats = np.empty(len(grid))
         for i in range(0, len(grid), 512):
-            stats[i:i + 512] = np.atleast_1d(like.engine.stat_sum(grid[i:i + 512]))
+            stats[i:i + 512] = like.stat_values(grid[i:i + 512])
         return {f"{x.name}_scan": xv, f"{y.name}_scan": yv, "stat_scan": stats.reshape(len(xv), len(yv)),
                 "fit_results": []}

@@ -58,6 +58,19 @@ class Parameter:
         self.scan_n_sigma = int(scan_n_sigma)
         self.prior = prior
 
+    # every assignment of a prior bumps a class-wide counter: consumers (the likelihood engines) cache "does any of
+    # my parameters carry a prior" against it instead of scanning their parameters on every evaluation
+    prior_epoch = 0
+
+    @property
+    def prior(self):
+        return self._prior
+
+    @prior.setter
+    def prior(self, value):
+        self._prior = value
+        Parameter.prior_epoch += 1
+
     # descriptor protocol: class attributes on models are templates, instances hold their own copy
     def __get__(self, instance, owner):
         if instance is None:
@@ -370,7 +383,12 @@ class Parameters(collections.abc.Sequence):
             par.check_limits()
 
     def prior_stat_sum(self):
-        return 0.0
+        """Sum of the prior terms of the parameters that carry one (parameter.py:632-637)."""
+        total = 0.0
+        for par in self.unique_parameters:  # a linked parameter counts once
+            if par.prior is not None:
+                total += par.prior(par)
+        return total
 
     def freeze_all(self):
         for p in self._parameters:

@@ -209,3 +209,39 @@ def test_stat_surface_with_and_without_reoptimisation():
     assert_allclose(refit["stat_scan"], best, atol=2e-3)
     assert refit["fit_results"].shape == (3, 2) and all(r.success for r in refit["fit_results"].ravel())
     assert shared.spectral_model.amplitude.value == 3e-12 and not index.frozen and not norm.frozen
+
+
+def test_priors_enter_the_joint_statistic_and_the_fit():
+    """GaussianPrior / UniformPrior (modeling/models/prior.py) as -2 log pdf terms of Datasets.stat_sum
+    (datasets/core.py:264-271), seen by Fit; values against scipy.stats."""
+    from scipy import stats as sps
+
+    from gammapy_b200.modeling import Fit, GaussianPrior, Parameter, Parameters, UniformPrior
+
+    p = Parameter("x", 1.3)
+    p.prior = GaussianPrior(mu=1.0, sigma=0.2)
+    assert_allclose(p.prior(p), -2 * sps.norm(1.0, 0.2).logpdf(1.3), rtol=1e-13)
+    q = Parameter("y", 0.4)
+    q.prior = UniformPrior(min=0.0, max=2.0, weight=3)
+    assert_allclose(q.prior(q), 3 * -2 * sps.uniform(0.0, 2.0).logpdf(0.4), rtol=1e-13)
+    assert_allclose(Parameters([p, q, Parameter("z", 5.0)]).prior_stat_sum(), p.prior(p) + q.prior(q), rtol=1e-14)
+    q.value = 2.5
+    assert q.prior(q) == np.inf
+    assert_allclose(p.prior.evaluate_many([1.0, 1.3]), [-2 * sps.norm(1.0, 0.2).logpdf(1.0), p.prior(p)], rtol=1e-13)
+
+    # a Gaussian prior on the index pulls the toy fit between the likelihood optimum (2.3) and the prior mean
+    shared, backgrounds = _toy_models(1)
+    local_pars = list(shared.parameters) + list(backgrounds[0].parameters)
+    names = [pp.name for pp in local_pars]
+    i_index, i_amp, i_norm = names.index("index"), names.index("amplitude"), names.index("norm")
+    sharded = ShardedDatasets(None, local_stat=lambda v: _toy_stat(0, v[:, i_index], v[:, i_amp], v[:, i_norm]),
+                              global_models=[shared] + backgrounds, local_parameters=local_pars)
+    index = shared.spectral_model.index
+    index.prior = GaussianPrior(mu=2.0, sigma=0.1)
+    result = Fit().run(sharded)
+    assert result.success
+    # minimise (50 - 1/16) (x - 2.3)^2 + (x - 2)^2 / 0.01: weights 49.9375 and 100
+    want = (49.9375 * 2.3 + 100 * 2.0) / (49.9375 + 100)
+    assert abs(index.value - want) < 2e-3
+    assert_allclose(index.error, np.sqrt(1 / (49.9375 + 100)), rtol=2e-2)
+    assert_allclose(sharded.stat_sum(), result.total_stat, rtol=0, atol=1e-6)

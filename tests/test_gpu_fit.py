@@ -193,3 +193,25 @@ def test_confidence_interval_close_to_hesse_error(ctx):
     assert index.value == best and not index.frozen
     fixed = fit.confidence(ds, index, sigma=1, reoptimize=False)
     assert fixed["success"] and fixed["errp"] <= res["errp"] * 1.001   # conditional interval is the narrower one
+
+
+def test_prior_term_on_the_gpu_likelihood(ctx):
+    """Datasets.stat_sum = GPU likelihood + host prior terms (datasets/core.py:264-277); Fit sees the prior."""
+    from gammapy_b200 import Datasets, Map, configs
+    from gammapy_b200.modeling import Fit, GaussianPrior
+    from oracle import adapter
+
+    ds = configs.make_c1(width=(1.6, 1.6), mask_radius=0.7)
+    ds.counts = Map.from_geom(ds._geom, data=adapter.evaluator_for(ds).fake(3), dtype=float)
+    datasets = Datasets([ds])
+    plain = datasets.stat_sum()
+    assert plain == datasets.stat_sum_likelihood()
+    index = ds.models["model-simu"].spectral_model.index
+    index.prior = GaussianPrior(mu=2.5, sigma=0.05)
+    assert_allclose(datasets.stat_sum(), plain + index.prior(index), rtol=1e-14)
+    assert datasets.stat_sum_likelihood() == plain
+    free = Fit().run(datasets)
+    with_prior = index.value
+    index.prior = None
+    Fit().run(datasets)
+    assert free.success and abs(with_prior - 2.5) < abs(index.value - 2.5)   # pulled towards the prior mean
