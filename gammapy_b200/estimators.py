@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["RESULT_NAMES", "compute_ts_map", "BrentqFluxEstimator", "TSMapEstimator"]
+__all__ = ["RESULT_NAMES", "compute_ts_map", "BrentqFluxEstimator", "TSMapEstimator", "ParameterEstimator"]
 
 RESULT_NAMES = ("norm", "norm_err", "niter", "ts", "stat", "stat_null", "success", "npred", "npred_excess")
 
@@ -113,4 +113,103 @@ class TSMapEstimator:
         with np.errstate(invalid="ignore"):
             ts = result["ts"]
             result["sqrt_ts"] = np.where(ts > 0, np.sqrt(np.abs(ts)), -np.sqrt(np.abs(ts)))
+        return result
+
+
+# -------------------------------------------------------------------------------------------------------------
+# ParameterEstimator (estimators/parameter.py:20-440): best fit, delta(TS) against a null value, asymmetric
+# errors, upper limit and profile of ONE parameter, on top of Fit (whose gradients, scans and confidence searches
+# are batched GPU launches).  Works for Datasets and ShardedDatasets alike.
+# -------------------------------------------------------------------------------------------------------------
+class _restore_status:
+    """parameters.restore_status(): values and frozen flags come back on exit (modeling/parameter.py)."""
+
+    def __init__(self, parameters):
+        self.parameters = list(parameters)
+
+    def __enter__(self):
+        self.saved = [(p, p.value, p.frozen) for p in self.parameters]
+        return self
+
+    def __exit__(self, *exc):
+        for p, value, frozen in self.saved:
+            p.value, p.frozen = value, frozen
+
+
+class ParameterEstimator:
+    tag = "ParameterEstimator"
+    _available_selection_optional = ["errn-errp", "ul", "scan"]
+
+    def __init__(self, n_sigma=1, n_sigma_ul=2, null_value=1e-150, selection_optional=None, fit=None, reoptimize=True):
+        from .modeling import Fit
+
+        self.n_sigma, self.n_sigma_ul, self.null_value = n_sigma, n_sigma_ul, null_value
+        if selection_optional == "all":
+            selection_optional = list(self._available_selection_optional)
+        self.selection_optional = list(selection_optional or [])
+        unknown = set(self.selection_optional) - set(self._available_selection_optional)
+        if unknown:
+            raise NotImplementedError(f"selection_optional {sorted(unknown)} is not available here")
+        self.fit = fit if fit is not None else Fit()
+        self.reoptimize = reoptimize
+
+    @staticmethod
+    def _parameter(datasets, parameter):
+        if isinstance(parameter, str):
+            return datasets.parameters[parameter]
+        return parameter
+
+    def estimate_best_fit(self, datasets, parameter):
+        """parameter.py:108-141."""
+        result = self.fit.run(datasets)
+        return {f"{parameter.name}": parameter.value, "stat": result.optimize_result.total_stat,
+                "success": result.success, f"{parameter.name}_err": parameter.error * self.n_sigma}
+
+    def estimate_ts(self, datasets, parameter):
+        """parameter.py:143-181: stat at the null value (other parameters re-fitted when ``reoptimize``) minus the
+        best-fit stat."""
+        stat = datasets.stat_sum()
+        with _restore_status(datasets.parameters):
+            parameter.value = self.null_value
+            if self.reoptimize:
+                parameter.frozen = True
+                if any(not p.frozen for p in datasets.parameters):
+                    self.fit.optimize(datasets)
+            stat_null = datasets.stat_sum()
+        return {"ts": stat_null - stat, "stat_null": stat_null}
+
+    def estimate_errn_errp(self, datasets, parameter):
+        """parameter.py:183-219."""
+        self.fit.optimize(datasets)
+        res = self.fit.confidence(datasets, parameter, sigma=self.n_sigma, reoptimize=self.reoptimize)
+        return {f"{parameter.name}_errp": res["errp"], f"{parameter.name}_errn": res["errn"]}
+
+    def estimate_ul(self, datasets, parameter):
+        """parameter.py:258-286."""
+        self.fit.optimize(datasets)
+        res = self.fit.confidence(datasets, parameter, sigma=self.n_sigma_ul, reoptimize=self.reoptimize)
+        return {f"{parameter.name}_ul": res["errp"] + parameter.value}
+
+    def estimate_scan(self, datasets, parameter):
+        """parameter.py:221-256."""
+        self.fit.optimize(datasets)
+        profile = self.fit.stat_profile(datasets, parameter, reoptimize=self.reoptimize)
+        return {f"{parameter.name}_scan": np.asarray(parameter.scan_values, dtype=float), "stat_scan": profile["stat_scan"]}
+
+    def run(self, datasets, parameter):
+        """parameter.py:354-411 (without the per-dataset counts / npred bookkeeping)."""
+        parameter = self._parameter(datasets, parameter)
+        with _restore_status(datasets.parameters):
+            if not self.reoptimize:
+                for p in datasets.parameters:
+                    p.frozen = True
+                parameter.frozen = False
+            result = self.estimate_best_fit(datasets, parameter)
+            result.update(self.estimate_ts(datasets, parameter))
+            if "errn-errp" in self.selection_optional:
+                result.update(self.estimate_errn_errp(datasets, parameter))
+            if "ul" in self.selection_optional:
+                result.update(self.estimate_ul(datasets, parameter))
+            if "scan" in self.selection_optional:
+                result.update(self.estimate_scan(datasets, parameter))
         return result

@@ -245,3 +245,32 @@ def test_priors_enter_the_joint_statistic_and_the_fit():
     assert abs(index.value - want) < 2e-3
     assert_allclose(index.error, np.sqrt(1 / (49.9375 + 100)), rtol=2e-2)
     assert_allclose(sharded.stat_sum(), result.total_stat, rtol=0, atol=1e-6)
+
+
+def test_parameter_estimator_on_the_toy_likelihood():
+    """ParameterEstimator (estimators/parameter.py): best fit, delta(TS) against a null value, errn / errp, upper
+    limit and scan of the background norm, against the closed forms of the quadratic toy likelihood."""
+    from gammapy_b200.estimators import ParameterEstimator
+
+    shared, backgrounds = _toy_models(1)
+    local_pars = list(shared.parameters) + list(backgrounds[0].parameters)
+    names = [p.name for p in local_pars]
+    i_index, i_amp, i_norm = names.index("index"), names.index("amplitude"), names.index("norm")
+    sharded = ShardedDatasets(None, local_stat=lambda v: _toy_stat(0, v[:, i_index], v[:, i_amp], v[:, i_norm]),
+                              global_models=[shared] + backgrounds, local_parameters=local_pars)
+    norm = backgrounds[0].spectral_model.norm
+    norm.scan_values = [0.9, 1.0, 1.1]
+    norm.min, norm.max = 0.0, 3.0
+    est = ParameterEstimator(n_sigma=1, n_sigma_ul=2, null_value=0.5, selection_optional="all", reoptimize=True)
+    res = est.run(sharded, norm)
+    # profile in the norm: 400 n^2 + 10 d n + 50 d^2 minimised over d -> (400 - 0.5) n^2, n = norm - 1
+    curv = 400 - 0.5
+    assert res["success"] and abs(res["norm"] - 1.0) < 1e-3
+    assert_allclose(res["norm_err"], 1 / np.sqrt(curv), rtol=2e-2)
+    assert_allclose(res["ts"], curv * 0.25, rtol=2e-3)
+    assert_allclose([res["norm_errn"], res["norm_errp"]], 1 / np.sqrt(curv), rtol=3e-3)
+    assert_allclose(res["norm_ul"], 1.0 + 2 / np.sqrt(curv), rtol=3e-3)
+    assert_allclose(res["stat_scan"] - res["stat"], curv * np.array([0.01, 0.0, 0.01]), atol=2e-3)
+    assert not norm.frozen and norm.value == 1.0              # status restored (the value before the run)
+    fixed = ParameterEstimator(null_value=0.5, reoptimize=False).run(sharded, norm)
+    assert fixed["ts"] > 0 and "norm_ul" not in fixed
