@@ -39,8 +39,8 @@ constexpr int kMmaSubs = kFoldTPX / kMmaSub;           // sub-items per tile
 constexpr int kMmaMaxNT = 64, kMmaMaxNR = 32;          // axes this kernel handles (larger: the staged / generic kernels)
 constexpr int kMmaKSteps = kMmaMaxNT / 4;
 constexpr int kMmaNTiles = kMmaMaxNR / 8;
-// warps per CTA: 11 -> 352 threads x 168 registers, 8 -> 256 threads x 255 registers (ptxas sizes the register budget
-// for thread counts rounded up to 128)
+// consumer warps per CTA (+ 1 producer warp): 11 -> 384 threads x 168 registers, 7 -> 256 threads x 255 registers
+// (ptxas sizes the register budget for thread counts rounded up to 128)
 
 constexpr int kLogTabBytes = 128 * 16;                  // fast_log table: 128 x {1 / m_hi, log(m_hi)}
 
@@ -56,12 +56,27 @@ constexpr int kMmaGroupDoubles = kMmaKSteps * kMmaNTiles * 32;
 static_assert(sizeof(MmaTableHead) == 64, "MmaTableHead");
 
 struct MmaParams {
-  unsigned lay_tab, lay_log, lay_bars;  // shared-memory offsets behind the per-warp areas: cached table, log table, mbarriers
+  int n_stages, stage_bytes;     // ring of tile stages: [nT][512 B] exposure tile + 448 B descriptor + 64 B tile info
+  unsigned lay_tab, lay_log, lay_fs, lay_bars;  // shared-memory offsets behind the ring: cached table, log table,
+                                                // per-warp flux rows, mbarriers (+ sequence counter)
   int tab_bytes;                 // bytes of the table cached in shared memory (dataset tab_ds)
   int tab_ds;                    // dataset whose table is cached (-1: none)
   const double2* logtab;         // fast_log table (device)
   int debug_skip;                // GPY_MMA_SKIP (profiling only): 1 skips the k-loops, 2 the epilogue, 4 the exposure loads
+  long long* trace;              // GPY_MMA_TRACE (profiling only): [0] = event count, then {type, warp, seq, clock} of CTA 0
 };
+#define GPY_TRACE(type, seq)                                                                      \
+  do {                                                                                            \
+    if (M.trace && blockIdx.x == 0 && lane == 0) {                                                \
+      const unsigned long long i_ = atomicAdd(reinterpret_cast<unsigned long long*>(M.trace), 1ull); \
+      if (i_ < 60000) {                                                                           \
+        M.trace[1 + 4 * i_] = (type);                                                             \
+        M.trace[2 + 4 * i_] = warp;                                                               \
+        M.trace[3 + 4 * i_] = (seq);                                                              \
+        M.trace[4 + 4 * i_] = clock64();                                                          \
+      }                                                                                           \
+    }                                                                                             \
+  } while (0)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -116,18 +131,16 @@ struct MmaSrc {  // per-thread view of up to four sources of one pass
 // One pass over the k-steps [k_begin, k_end) (k_begin a multiple of UN) for NL sources:
 //   acc[j][n][i] += sum_t v_j[t] * B[t][8 n + 2 tg + i],   v_j[t] = exposure[t, p_j] * sum_l F_l[t] * C_l[t, p_j].
 // Everything a k-step reads sits at a compile-time offset from a per-lane pointer that advances once per loop
-// iteration (UN k-steps): the exposure tile (swizzled; two lane constants), the zero-padded flux rows fs[l][64] and the
-// dense fragment table tabg[ks][n][32] in shared memory, the cube rows t, t+1, t+8, t+9 (UN = 4) through 32-bit byte
-// steps.  The cube loads of the next iteration are issued before the DMMAs of this one (PD = UN k-steps ahead).
+// iteration (UN k-steps): the zero-padded flux rows fs[l][64] and the dense fragment table tabg[ks][n][32] in shared
+// memory, the cube rows t, t+1, t+8, t+9 (UN = 4) through 32-bit byte steps; the exposure tile [nT][128 px] is read
+// at this thread's quad (the four rows of a k-step share their banks: a 4-way conflict on one LDS.128 per k-step).  The cube loads of the next iteration are issued before the DMMAs of this one (PD = UN k-steps ahead).
 template <int NL, int UN>
 __device__ __forceinline__ void fold_pass(double (&acc)[4][kMmaNTiles][2], const MmaSrc& S, const double* fs,
                                           const unsigned char* es, const double* tabg, unsigned long long bits,
                                           int k_begin, int k_end, int nT, int g, int tg, int lane, uint64_t pol) {
   static_assert(UN == 2 || UN == 4, "k-steps per iteration");
   const int t_lane = 2 * tg;
-  // per-lane constants
-  const unsigned char* ep = es + t_lane * 128 + k_begin * 512;        // row 8 blk + 2 tg (+ h), blk = ks >> 1
-  const int ex0 = (g ^ (2 * tg)) << 4, ex1 = ((g ^ (2 * tg + 1)) << 4) + 128;
+  // per-lane constants (es: this thread's pixel quad in row 0 of the exposure tile, rows of kFoldTPX floats)
   const double* fp = fs + t_lane + k_begin * 4;
   const double* tp = tabg + (size_t)k_begin * (kMmaNTiles * 32) + lane;
   const char* cp[NL];
@@ -170,7 +183,8 @@ __device__ __forceinline__ void fold_pass(double (&acc)[4][kMmaNTiles][2], const
     for (int u = 0; u < UN; ++u) {
       const unsigned m = (unsigned)(mb >> (4 * u)) & 15u;
       const int blk = u >> 1, h = u & 1;
-      const float4 e = *reinterpret_cast<const float4*>(ep + blk * 1024 + (h ? ex1 : ex0));
+      // (rows past the axis read the last row: finite, and their flux is zero)
+      const float4 e = *reinterpret_cast<const float4*>(es + min(t0 + blk * 8 + h, nT - 1) * (kFoldTPX * 4));
       double bfr[kMmaNTiles];
 #pragma unroll
       for (int n = 0; n < kMmaNTiles; ++n) bfr[n] = tp[(u * kMmaNTiles + n) * 32];
@@ -200,7 +214,6 @@ __device__ __forceinline__ void fold_pass(double (&acc)[4][kMmaNTiles][2], const
         }
       }
     }
-    ep += UN * 512;
     fp += UN * 4;
     tp += UN * kMmaNTiles * 32;
     t0 += 4 * UN;
@@ -325,9 +338,9 @@ enum : int {
   kHdrHasSrc = 1, kHdrHasBkg = 2, kHdrHasCounts = 4, kHdrHasMask = 8,
 };
 
-// Per-tile information a warp keeps in shared memory (two slots: the tile it works on and the next one).
+// Per-tile information in a stage of the ring.
 struct MmaTileInfo {
-  int w, tile, b, d;            // work position (descriptor slot), tile, parameter vector, dataset
+  int w, tile, b, d;            // work position (descriptor slot; -1: no work left), tile, parameter vector, dataset
   int evalidx, nsrc, src_mask, pt;  // (dataset, vector) index; overlapping sources; bit 4 sub + l: source l reaches
                                     // sub-item sub; first pixel of the tile in its dataset
   int nx, nT, nR, Pn;
@@ -335,280 +348,309 @@ struct MmaTileInfo {
 };
 static_assert(sizeof(MmaTileInfo) == 64, "MmaTileInfo");
 
-// per-warp shared memory: two exposure buffers, two descriptors, two tile infos, the flux rows of a pass
-constexpr int kWpExp = 0;                              // [2][64][128 B], SWIZZLE_128B
-constexpr int kWpDesc = 2 * kMmaMaxNT * 128;           // [2][448 B]
-constexpr int kWpInfo = kWpDesc + 2 * 448;             // [2] MmaTileInfo
-constexpr int kWpFs = kWpInfo + 2 * 64;                // [2][64] doubles
-constexpr int kWarpBytes = kWpFs + 2 * kMmaMaxNT * 8;
-static_assert(kWarpBytes == 18432, "per-warp layout");
-
-// One CTA per SM, NC self-sufficient warps.  A warp claims tiles (128 pixels x one parameter vector) from a global
-// counter two tiles ahead, and walks the four 32-pixel sub-items of each: while it folds one sub-item it has the
-// exposure tile of the next one in flight (its own 2-D tensor-map TMA load into the other of its two buffers) and the
-// background / counts / mask boxes of the next one on their way to L2 (TMA prefetch).  No warp waits for another one.
+// One CTA per SM: NC consumer warps + 1 producer warp, no CTA barrier after start-up.
+//   * The producer claims tiles (128 pixels x one parameter vector) from a global counter two tiles ahead, reads their
+//     work descriptors one tile ahead, and fills the stages of a shared-memory ring: the exposure tile [nT][128 px]
+//     by ONE 2-D tensor-map TMA load (512-byte rows: fewer, longer DRAM bursts and a quarter of the TMA instructions
+//     of per-sub-item boxes), the descriptor and the tile info; the background / counts / mask boxes of the tile are
+//     sent towards L2 with TMA prefetches at the same time.
+//   * Consumer warps take (tile, sub-item) pairs in sequence order from a shared counter; a stage is free again when
+//     the four sub-items of its tile are past their k-loops (empty barrier, count 4).
 template <bool WRITE_NPRED, bool DYNAMIC, int NC>
-__global__ void __launch_bounds__(NC * 32, 1) fold_cash_mma_kernel(const FoldParams P, const MmaParams M) {
+__global__ void __launch_bounds__((NC + 1) * 32, 1) fold_cash_mma_kernel(const FoldParams P, const MmaParams M) {
   // sources per pass over the k-steps and k-steps per loop iteration (= prefetch distance of the cube loads): ONE
   // variant of the pass, so that the hot code of all warps fits the 32 KB instruction cache; the register budget of
   // the 11-warp configuration only holds the loads of two k-steps
-  constexpr int kPassSources = 2, kPassUnroll = NC <= 8 ? 4 : 2;
+  constexpr int kPassSources = 2, kPassUnroll = NC <= 7 ? 4 : 2;
+  constexpr int kThreads = (NC + 1) * 32;
   extern __shared__ __align__(1024) unsigned char mma_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned char* wp = mma_smem + (size_t)warp * kWarpBytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(mma_smem + M.lay_bars) + 2 * warp;  // this warp's two buffers
+  const int S = M.n_stages, stage_bytes = M.stage_bytes, exp_bytes = M.stage_bytes - 512;
+  uint64_t* full = reinterpret_cast<uint64_t*>(mma_smem + M.lay_bars);
+  uint64_t* empty = full + S;
+  int* seq_next = reinterpret_cast<int*>(empty + S);
   unsigned char* tab_s = mma_smem + M.lay_tab;
   const double2* logtab = reinterpret_cast<const double2*>(mma_smem + M.lay_log);
-  double* fs = reinterpret_cast<double*>(wp + kWpFs);
+  double* fs = reinterpret_cast<double*>(mma_smem + M.lay_fs) + warp * (kPassSources * kMmaMaxNT);
 
-  // start-up: zero the exposure buffers (rows a dataset's boxes never write must read as finite numbers), tables
-  for (int i = tid; i < NC * kWarpBytes / 16; i += NC * 32) reinterpret_cast<int4*>(mma_smem)[i] = make_int4(0, 0, 0, 0);
+  // start-up: tables, barriers
   if (M.tab_ds >= 0) {
     const int4* src = reinterpret_cast<const int4*>(P.ds[M.tab_ds].mma_table);
-    for (int i = tid; i < M.tab_bytes / 16; i += NC * 32) reinterpret_cast<int4*>(tab_s)[i] = src[i];
+    for (int i = tid; i < M.tab_bytes / 16; i += kThreads) reinterpret_cast<int4*>(tab_s)[i] = src[i];
   }
-  for (int i = tid; i < kLogTabBytes / 16; i += NC * 32)
+  for (int i = tid; i < kLogTabBytes / 16; i += kThreads)
     reinterpret_cast<int4*>(mma_smem + M.lay_log)[i] = reinterpret_cast<const int4*>(M.logtab)[i];
-  if (lane == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kMmaSubs);
+    }
+    *seq_next = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic zero fill before the async-proxy (TMA) writes
   __syncthreads();
 
   const int n_items = P.B * P.n_tiles;
   const int n_work = P.work ? *P.n_work : n_items;
   const int n_chunks = P.dl_bytes / 16;
+
+  if (warp == NC) {
+    // ------------------------------------------------------------------------------------------------ producer
+    const uint64_t pol_stream = l2_policy_evict_first();
+    auto claim = [&](int cur) -> int {  // a work position after `cur` (warp uniform)
+      if (!DYNAMIC) return cur + (int)gridDim.x;
+      int nxt = 0;
+      if (lane == 0) nxt = (int)gridDim.x + (int)atomicAdd(P.counter, 1u);
+      return __shfl_sync(0xffffffffu, nxt, 0);
+    };
+    auto load_desc = [&](int pos) -> int4 {  // one 16-byte chunk of the work descriptor per lane
+      int4 v = make_int4(0, 0, 0, 0);
+      if (pos < n_work && lane < n_chunks) v = __ldg(reinterpret_cast<const int4*>(P.desc + (size_t)pos * P.dl_bytes) + lane);
+      return v;
+    };
+    int stage = 0;
+    uint32_t empty_par = 1;
+    bool first_lap = true;
+    auto next_stage = [&]() {
+      if (++stage == S) {
+        stage = 0;
+        empty_par ^= 1u;
+        first_lap = false;
+      }
+    };
+    // Everything with a long latency is requested one iteration (tile) before it is used: the claim of the tile after
+    // next (the atomic's result stays in lane 0 until the next iteration broadcasts it), the next tile's descriptor,
+    // item and dataset index.  The dataset's fields are re-read only when the dataset changes.
+    auto claim_async = [&]() -> int {  // lane 0: the claimed position; other lanes: garbage until claim_get
+      int nxt = 0;
+      if (DYNAMIC && lane == 0) nxt = (int)gridDim.x + (int)atomicAdd(P.counter, 1u);
+      return nxt;
+    };
+    auto claim_get = [&](int pending, int cur) -> int {
+      return DYNAMIC ? __shfl_sync(0xffffffffu, pending, 0) : cur + (int)gridDim.x;
+    };
+    auto load_item = [&](int pos) -> int { return pos < n_work ? (P.work ? __ldg(P.work + pos) : pos) : 0; };
+    int w_cur = (int)blockIdx.x;
+    int w_next = w_cur < n_work ? claim(w_cur) : w_cur;
+    int pending = claim_async();  // the tile after next
+    int4 dv = load_desc(w_cur);
+    int item = load_item(w_cur);
+    int d = w_cur < n_work ? __ldg(P.tile_ds + item / P.B) : 0;
+    int item_next = load_item(w_next);
+    int cached_d = -1;
+    int nx = 1, Pn = 0, nT = 0, nR = 0, tile_begin = 0, G = 1, dflags = 0;
+    const unsigned char* tm = nullptr;
+    while (w_cur < n_work) {
+      const int4 dv_next = load_desc(w_next);
+      const int d_next = w_next < n_work ? __ldg(P.tile_ds + item_next / P.B) : 0;
+      const int b = item % P.B, tile = item / P.B;
+      if (d != cached_d) {
+        const DatasetDev& D = P.ds[d];
+        nx = D.nx;
+        Pn = (int)D.P;
+        nT = D.nT;
+        nR = D.nR;
+        tile_begin = D.tile_begin;
+        G = D.n_groups;
+        const bool has_counts = D.counts != nullptr;
+        dflags = ((D.background != nullptr && P.include_background) ? kHdrHasBkg : 0) | (has_counts ? kHdrHasCounts : 0) |
+                 ((has_counts && D.mask != nullptr) ? kHdrHasMask : 0);
+        tm = reinterpret_cast<const unsigned char*>(D.tmaps);
+        cached_d = d;
+      }
+      const int nl = __shfl_sync(0xffffffffu, dv.x, 0), nover = __shfl_sync(0xffffffffu, dv.y, 0);
+      const int evalidx = __shfl_sync(0xffffffffu, dv.z, 0);
+      const int pt = (tile - tile_begin) * kFoldTPX;
+      // which sub-items does a source reach?  lane = 4 sub + l tests source l (first 16 bytes of its InstDev: the
+      // cutout rectangle) against sub-item sub
+      unsigned src_mask;
+      {
+        const int l = lane & 3, sub = (lane >> 2) & 3;
+        const int srcl = (P.dl_inst + l * (int)sizeof(InstDev)) / 16;
+        const int rx = __shfl_sync(0xffffffffu, dv.x, srcl), ry = __shfl_sync(0xffffffffu, dv.y, srcl);
+        const int rw = __shfl_sync(0xffffffffu, dv.z, srcl), rh = __shfl_sync(0xffffffffu, dv.w, srcl);
+        const int p0 = pt + sub * kMmaSub, p1 = min(p0 + kMmaSub, Pn) - 1;
+        const int y_first = p0 / nx, y_last = p1 / nx;
+        const int x_first = p0 - y_first * nx, x_last = p1 - y_last * nx;
+        bool ov = lane < 16 && l < nl && p0 < Pn && ry <= y_last && ry + rh > y_first;
+        if (ov && y_first == y_last) ov = rx <= x_last && rx + rw > x_first;
+        src_mask = __ballot_sync(0xffffffffu, ov);
+        if (nover > 0) src_mask = 0xffffu;
+        if (M.debug_skip & 4) src_mask = 0u;
+      }
+      unsigned char* st = mma_smem + (size_t)stage * stage_bytes;
+      GPY_TRACE(1, w_cur);
+      if (!first_lap) mbar_wait(&empty[stage], empty_par);
+      GPY_TRACE(2, w_cur);
+      if (lane < n_chunks) *reinterpret_cast<int4*>(st + exp_bytes + 16 * lane) = dv;
+      if (lane == 28) *reinterpret_cast<int4*>(st + exp_bytes + 448) = make_int4(w_cur, tile, b, d);
+      if (lane == 29) *reinterpret_cast<int4*>(st + exp_bytes + 464) = make_int4(evalidx, nl + nover, (int)src_mask, pt);
+      if (lane == 30) *reinterpret_cast<int4*>(st + exp_bytes + 480) = make_int4(nx, nT, nR, Pn);
+      if (lane == 31) *reinterpret_cast<int4*>(st + exp_bytes + 496) = make_int4(G, dflags, 0, 0);
+      __syncwarp();
+      if (lane == 0) {
+        if (!(M.debug_skip & 8)) {  // epilogue inputs towards L2; the consumers read them straight from global memory
+          if (dflags & kHdrHasBkg) tma_prefetch_2d(tm + 128, pt, 0);
+          if (dflags & kHdrHasCounts) tma_prefetch_2d(tm + 256, pt, 0);
+          if (dflags & kHdrHasMask) tma_prefetch_2d(tm + 384, pt, 0);
+        }
+        if (src_mask) {
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)nT * (kFoldTPX * 4));
+          tma_load_2d(st, tm, pt, 0, &full[stage], pol_stream);
+        } else {
+          mbar_arrive(&full[stage]);
+        }
+      }
+      GPY_TRACE(3, w_cur);
+      next_stage();
+      w_cur = w_next;
+      w_next = claim_get(pending, w_next);
+      pending = claim_async();
+      dv = dv_next;
+      item = item_next;
+      d = d_next;
+      item_next = load_item(w_next);
+    }
+    // sentinel tiles: one sequence number per consumer warp
+    for (int k = 0; k < (NC + kMmaSubs - 1) / kMmaSubs; ++k) {
+      unsigned char* st = mma_smem + (size_t)stage * stage_bytes;
+      if (!first_lap) mbar_wait(&empty[stage], empty_par);
+      if (lane == 0) {
+        *reinterpret_cast<int4*>(st + exp_bytes + 448) = make_int4(-1, 0, 0, 0);
+        mbar_arrive(&full[stage]);
+      }
+      __syncwarp();
+      next_stage();
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------------------------------------- consumers
   const int g = lane >> 2, tg = lane & 3;
   const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   const double log_trunc = P.log_trunc;
-  const int n_warps_total = (int)gridDim.x * NC;
+  for (;;) {
+    int seq = 0;
+    if (lane == 0) seq = atomicAdd(seq_next, 1);
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    const int tseq = seq >> 2, sub = seq & 3;
+    const int s = tseq % S;
+    unsigned char* st = mma_smem + (size_t)s * stage_bytes;
+    GPY_TRACE(10, seq);
+    mbar_wait(&full[s], (uint32_t)(tseq / S) & 1u);
+    GPY_TRACE(11, seq);
+    const MmaTileInfo ti = *reinterpret_cast<const MmaTileInfo*>(st + exp_bytes + 448);
+    if (ti.w < 0) break;  // no work left (nobody reuses a sentinel stage)
+    const int nx = ti.nx, nT = ti.nT, nR = ti.nR, Pn = ti.Pn;
+    const int p0 = ti.pt + sub * kMmaSub;
+    if (p0 >= Pn) {  // the dataset ends inside this tile
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      continue;
+    }
+    const int npx = min(kMmaSub, Pn - p0);
+    const bool qlive = 4 * g < npx;
 
-  auto claim = [&](int cur) -> int {  // a work position after `cur` (warp uniform)
-    if (!DYNAMIC) return cur + n_warps_total;
-    int nxt = 0;
-    if (lane == 0) nxt = n_warps_total + (int)atomicAdd(P.counter, 1u);
-    return __shfl_sync(0xffffffffu, nxt, 0);
-  };
-  auto load_desc = [&](int pos) -> int4 {  // one 16-byte chunk of the work descriptor per lane
-    int4 v = make_int4(0, 0, 0, 0);
-    if (pos < n_work && lane < n_chunks) v = __ldg(reinterpret_cast<const int4*>(P.desc + (size_t)pos * P.dl_bytes) + lane);
-    return v;
-  };
-  // descriptor registers -> shared-memory slot, tile info computed by the whole warp (warp uniform values)
-  auto install_tile = [&](int pos, const int4& dv, int slot) {
-    if (lane < n_chunks) *reinterpret_cast<int4*>(wp + kWpDesc + slot * 448 + 16 * lane) = dv;
-    const int item = P.work ? __ldg(P.work + pos) : pos;
-    const int b = item % P.B, tile = item / P.B;
-    const int d = __ldg(P.tile_ds + tile);
-    const DatasetDev& D = P.ds[d];
-    const int nx = D.nx, Pn = (int)D.P;
-    const int nl = __shfl_sync(0xffffffffu, dv.x, 0), nover = __shfl_sync(0xffffffffu, dv.y, 0);
-    const int evalidx = __shfl_sync(0xffffffffu, dv.z, 0);
-    const int pt = (tile - D.tile_begin) * kFoldTPX;
-    // which sub-items does a source reach?  lane = 4 sub + l tests source l (first 16 bytes of its InstDev: the
-    // cutout rectangle) against sub-item sub
-    const int l = lane & 3, sub = (lane >> 2) & 3;
-    const int srcl = (P.dl_inst + l * (int)sizeof(InstDev)) / 16;
-    const int rx = __shfl_sync(0xffffffffu, dv.x, srcl), ry = __shfl_sync(0xffffffffu, dv.y, srcl);
-    const int rw = __shfl_sync(0xffffffffu, dv.z, srcl), rh = __shfl_sync(0xffffffffu, dv.w, srcl);
-    const int p0 = pt + sub * kMmaSub, p1 = min(p0 + kMmaSub, Pn) - 1;
-    const int y_first = p0 / nx, y_last = p1 / nx;
-    const int x_first = p0 - y_first * nx, x_last = p1 - y_last * nx;
-    bool ov = lane < 16 && l < nl && p0 < Pn && ry <= y_last && ry + rh > y_first;
-    if (ov && y_first == y_last) ov = rx <= x_last && rx + rw > x_first;
-    unsigned src_mask = __ballot_sync(0xffffffffu, ov);
-    if (nover > 0) src_mask = 0xffffu;
-    if (lane == 0) {
-      const bool has_counts = D.counts != nullptr;
-      MmaTileInfo ti;
-      ti.w = pos;
-      ti.tile = tile;
-      ti.b = b;
-      ti.d = d;
-      ti.evalidx = evalidx;
-      ti.nsrc = nl + nover;
-      ti.src_mask = (int)src_mask;
-      ti.pt = pt;
-      ti.nx = nx;
-      ti.nT = D.nT;
-      ti.nR = D.nR;
-      ti.Pn = Pn;
-      ti.G = D.n_groups;
-      ti.dflags = ((D.background != nullptr && P.include_background) ? kHdrHasBkg : 0) | (has_counts ? kHdrHasCounts : 0) |
-                  ((has_counts && D.mask != nullptr) ? kHdrHasMask : 0);
-      ti.pad0_ = ti.pad1_ = 0;
-      *reinterpret_cast<MmaTileInfo*>(wp + kWpInfo + slot * 64) = ti;
+    double acc[4][kMmaNTiles][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int n = 0; n < kMmaNTiles; ++n) acc[j][n][0] = acc[j][n][1] = 0.0;
+
+    if (((ti.src_mask >> (4 * sub)) & 15) != 0 && !(M.debug_skip & 1)) {
+      const unsigned char* es = st + sub * (kMmaSub * 4) + g * 16;  // this thread's quad in row 0 of the exposure tile
+      const unsigned char* dsc = st + exp_bytes;
+      const int ntot = ti.nsrc;
+      const InstDev* slist = reinterpret_cast<const InstDev*>(dsc + P.dl_inst);
+      const int* over = reinterpret_cast<const int*>(dsc + P.dl_over);
+      const unsigned char* tab = ti.d == M.tab_ds ? tab_s : reinterpret_cast<const unsigned char*>(P.ds[ti.d].mma_table);
+      const MmaTableHead* th = reinterpret_cast<const MmaTableHead*>(tab);
+      const double* frag_all = reinterpret_cast<const double*>(tab + sizeof(MmaTableHead));
+      const int pq = p0 + 4 * g;
+      const int qy = pq / nx, qx = pq - qy * nx;
+      const float* zf = P.zeros;
+      for (int gi = 0; gi < ti.G; ++gi) {
+        const unsigned long long bits = th->bits[gi];
+        const int ks_lo = th->ks_lo[gi], ks_hi = th->ks_hi[gi];
+        const double* tabg = frag_all + (size_t)gi * kMmaGroupDoubles;
+        int idx = 0;
+        while (idx < ntot) {
+          MmaSrc src;
+          int foff[kPassSources];
+          int na = 0;
+#pragma unroll
+          for (int l = 0; l < kPassSources; ++l) {
+            src.cptr[l] = zf;
+            src.pstr[l] = 0;
+            foff[l] = -1;
+            const InstDev* in = nullptr;
+            while (idx < ntot) {  // next source of this edisp group (warp uniform)
+              const InstDev* cand = idx < kFoldLMax ? slist + idx : P.insts + over[idx - kFoldLMax];
+              ++idx;
+              if (ti.G == 1 || cand->group == gi) {
+                in = cand;
+                break;
+              }
+            }
+            if (in) {
+              ++na;
+              foff[l] = in->flux_off;
+              const int ly = qy - in->y0, lx = qx - in->x0a;
+              if (qlive && ly >= 0 && ly < in->cy && lx >= 0 && lx < in->pitch) {
+                src.cptr[l] = in->conv + ly * in->pitch + lx;
+                src.pstr[l] = in->plane_stride;
+              }
+            }
+          }
+          if (na == 0) break;
+          // this pass' flux rows, zero padded to 64 true bins, into the warp's scratch
+          __syncwarp();
+#pragma unroll
+          for (int l = 0; l < kPassSources; ++l) {  // (rows without a source multiply zeros: any finite value will do)
+            fs[l * kMmaMaxNT + lane] = l < na && lane < nT ? __ldg(P.flux + foff[l] + lane) : 0.0;
+            fs[l * kMmaMaxNT + 32 + lane] = l < na && lane + 32 < nT ? __ldg(P.flux + foff[l] + 32 + lane) : 0.0;
+          }
+          __syncwarp();
+          fold_pass<kPassSources, kPassUnroll>(acc, src, fs, es, tabg, bits, ks_lo & ~(kPassUnroll - 1), ks_hi, nT, g, tg,
+                                               lane, pol_keep);
+        }
+      }
     }
     __syncwarp();
-  };
-  // Start the loads of sub-item `sub` of the tile in `slot`: exposure into buffer `buf` (if a source reaches the
-  // sub-item), epilogue inputs towards L2.  Returns whether the exposure is on its way.
-  auto issue_sub = [&](int slot, int sub, int buf) -> bool {
-    const MmaTileInfo& ti = *reinterpret_cast<const MmaTileInfo*>(wp + kWpInfo + slot * 64);
-    const int p0 = ti.pt + sub * kMmaSub;
-    const bool has_src = ((ti.src_mask >> (4 * sub)) & 15) != 0 && !(M.debug_skip & 4);
-    __syncwarp();  // every lane is done reading the buffer's previous contents
-    if (lane == 0) {
-      const unsigned char* tm = reinterpret_cast<const unsigned char*>(P.ds[ti.d].tmaps_mma);
-      if (!(M.debug_skip & 8)) {
-        if (ti.dflags & kHdrHasBkg) tma_prefetch_2d(tm + 128, p0, 0);
-        if (ti.dflags & kHdrHasCounts) tma_prefetch_2d(tm + 256, p0, 0);
-        if (ti.dflags & kHdrHasMask) tma_prefetch_2d(tm + 384, p0, 0);
+    if (lane == 0) mbar_arrive(&empty[s]);  // this sub-item is done with the stage (exposure tile, descriptor, info)
+    GPY_TRACE(12, seq);
+
+    // ---- epilogue: background model, clip, Cash.  Thread: pixels p0 + 4g + j, reco bins 8n + 2tg + i.  Its inputs
+    // come straight from global memory (the producer's TMA prefetch put them in L2), two n-tiles (four rows) a round.
+    if (M.debug_skip & 2) continue;
+    EpiArgs ea;
+    ea.bkgp = P.ds[ti.d].background;
+    ea.cntp = P.ds[ti.d].counts;
+    ea.mskp = P.ds[ti.d].mask;
+    ea.bf = P.bkgfac + (size_t)ti.evalidx * P.smem_nRp;
+    ea.npred_out = P.npred_out;
+    ea.logtab = logtab;
+    ea.log_trunc = log_trunc;
+    ea.pol = pol_stream;
+    ea.Pn = Pn;
+    ea.col = qlive ? p0 + 4 * g : p0;
+    ea.nR = nR;
+    ea.live = qlive;
+    ea.tg = tg;
+    ea.flags = ti.dflags;
+    ea.include_background = P.include_background;
+    double stat = mma_epilogue<WRITE_NPRED, true>(acc, ea);
+    if (!WRITE_NPRED) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) stat += __shfl_xor_sync(0xffffffffu, stat, o);
+      if (!(fabs(stat) <= 1.7976931348623157e308)) {  // warp uniform; inf / nan inputs: the reference's log decides
+        stat = mma_epilogue<WRITE_NPRED, false>(acc, ea);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) stat += __shfl_xor_sync(0xffffffffu, stat, o);
       }
-      if (has_src) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive_expect_tx(&full[buf], (uint32_t)ti.nT * 128u);
-        tma_load_2d(wp + kWpExp + buf * (kMmaMaxNT * 128), tm, p0, 0, &full[buf], pol_stream);
-      }
+      if (lane == 0) P.partials[((size_t)ti.b * P.n_tiles + ti.tile) * kMmaSubs + sub] = stat;
     }
-    return has_src;
-  };
-
-  // ---- prologue: this warp's first two tiles
-  int w_cur = (int)blockIdx.x * NC + warp;
-  if (w_cur >= n_work) return;
-  int w_next = claim(w_cur);
-  int slot = 0, buf = 0;
-  uint32_t par0 = 0, par1 = 0;  // parity of the next completion of full[0] / full[1]
-  install_tile(w_cur, load_desc(w_cur), 0);
-  int4 dv_next = load_desc(w_next);
-  bool cur_has_exp = issue_sub(0, 0, 0);
-
-  for (;;) {
-    // the tile after next is claimed now: its position is needed one tile later
-    const int w_after = w_next < n_work ? claim(w_next) : w_next;
-    const MmaTileInfo ti = *reinterpret_cast<const MmaTileInfo*>(wp + kWpInfo + slot * 64);
-    const int nx = ti.nx, nT = ti.nT, nR = ti.nR, Pn = ti.Pn;
-    bool more = true;
-#pragma unroll 1
-    for (int sub = 0; sub < kMmaSubs; ++sub) {
-      const int p0 = ti.pt + sub * kMmaSub;
-      if (p0 >= Pn) break;
-      const int npx = min(kMmaSub, Pn - p0);
-      // next sub-item (of this tile or of the next one): start its loads
-      bool next_has_exp = false;
-      if (sub + 1 < kMmaSubs && p0 + kMmaSub < Pn) {
-        next_has_exp = issue_sub(slot, sub + 1, buf ^ 1);
-      } else if (w_next < n_work) {
-        install_tile(w_next, dv_next, slot ^ 1);
-        next_has_exp = issue_sub(slot ^ 1, 0, buf ^ 1);
-      } else {
-        more = false;
-      }
-      const unsigned char* es = wp + kWpExp + buf * (kMmaMaxNT * 128);
-      const bool qlive = 4 * g < npx;
-
-      double acc[4][kMmaNTiles][2];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int n = 0; n < kMmaNTiles; ++n) acc[j][n][0] = acc[j][n][1] = 0.0;
-
-      if (cur_has_exp) {
-        mbar_wait(&full[buf], buf ? par1 : par0);
-        if (buf) par1 ^= 1u; else par0 ^= 1u;
-      }
-      if (cur_has_exp && !(M.debug_skip & 1)) {
-        const unsigned char* dsc = wp + kWpDesc + slot * 448;
-        const int ntot = ti.nsrc;
-        const InstDev* slist = reinterpret_cast<const InstDev*>(dsc + P.dl_inst);
-        const int* over = reinterpret_cast<const int*>(dsc + P.dl_over);
-        const unsigned char* tab = ti.d == M.tab_ds ? tab_s : reinterpret_cast<const unsigned char*>(P.ds[ti.d].mma_table);
-        const MmaTableHead* th = reinterpret_cast<const MmaTableHead*>(tab);
-        const double* frag_all = reinterpret_cast<const double*>(tab + sizeof(MmaTableHead));
-        const int pq = p0 + 4 * g;
-        const int qy = pq / nx, qx = pq - qy * nx;
-        const float* zf = P.zeros;
-        for (int gi = 0; gi < ti.G; ++gi) {
-          const unsigned long long bits = th->bits[gi];
-          const int ks_lo = th->ks_lo[gi], ks_hi = th->ks_hi[gi];
-          const double* tabg = frag_all + (size_t)gi * kMmaGroupDoubles;
-          int idx = 0;
-          while (idx < ntot) {
-            MmaSrc src;
-            int foff[kPassSources];
-            int na = 0;
-#pragma unroll
-            for (int l = 0; l < kPassSources; ++l) {
-              src.cptr[l] = zf;
-              src.pstr[l] = 0;
-              foff[l] = -1;
-              const InstDev* in = nullptr;
-              while (idx < ntot) {  // next source of this edisp group (warp uniform)
-                const InstDev* cand = idx < kFoldLMax ? slist + idx : P.insts + over[idx - kFoldLMax];
-                ++idx;
-                if (ti.G == 1 || cand->group == gi) {
-                  in = cand;
-                  break;
-                }
-              }
-              if (in) {
-                ++na;
-                foff[l] = in->flux_off;
-                const int ly = qy - in->y0, lx = qx - in->x0a;
-                if (qlive && ly >= 0 && ly < in->cy && lx >= 0 && lx < in->pitch) {
-                  src.cptr[l] = in->conv + ly * in->pitch + lx;
-                  src.pstr[l] = in->plane_stride;
-                }
-              }
-            }
-            if (na == 0) break;
-            // this pass' flux rows, zero padded to 64 true bins, into the warp's scratch
-            __syncwarp();
-#pragma unroll
-            for (int l = 0; l < kPassSources; ++l) {  // (rows without a source multiply zeros: any finite value will do)
-              fs[l * kMmaMaxNT + lane] = l < na && lane < nT ? __ldg(P.flux + foff[l] + lane) : 0.0;
-              fs[l * kMmaMaxNT + 32 + lane] = l < na && lane + 32 < nT ? __ldg(P.flux + foff[l] + 32 + lane) : 0.0;
-            }
-            __syncwarp();
-            fold_pass<kPassSources, kPassUnroll>(acc, src, fs, es, tabg, bits, ks_lo & ~(kPassUnroll - 1), ks_hi, nT, g, tg,
-                                                 lane, pol_keep);
-          }
-        }
-      }
-
-      // ---- epilogue: background model, clip, Cash.  Thread: pixels p0 + 4g + j, reco bins 8n + 2tg + i.  Its inputs
-      // come straight from global memory (this warp's TMA prefetch put them in L2 one sub-item ago), two n-tiles
-      // (four rows) a round.
-      if (!(M.debug_skip & 2)) {
-        EpiArgs ea;
-        ea.bkgp = P.ds[ti.d].background;
-        ea.cntp = P.ds[ti.d].counts;
-        ea.mskp = P.ds[ti.d].mask;
-        ea.bf = P.bkgfac + (size_t)ti.evalidx * P.smem_nRp;
-        ea.npred_out = P.npred_out;
-        ea.logtab = logtab;
-        ea.log_trunc = log_trunc;
-        ea.pol = pol_stream;
-        ea.Pn = Pn;
-        ea.col = qlive ? p0 + 4 * g : p0;
-        ea.nR = nR;
-        ea.live = qlive;
-        ea.tg = tg;
-        ea.flags = ti.dflags;
-        ea.include_background = P.include_background;
-        double stat = mma_epilogue<WRITE_NPRED, true>(acc, ea);
-        if (!WRITE_NPRED) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) stat += __shfl_xor_sync(0xffffffffu, stat, o);
-          if (!(fabs(stat) <= 1.7976931348623157e308)) {  // warp uniform; inf / nan inputs: the reference's log decides
-            stat = mma_epilogue<WRITE_NPRED, false>(acc, ea);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) stat += __shfl_xor_sync(0xffffffffu, stat, o);
-          }
-          if (lane == 0) P.partials[((size_t)ti.b * P.n_tiles + ti.tile) * kMmaSubs + sub] = stat;
-        }
-      }
-      cur_has_exp = next_has_exp;
-      buf ^= 1;
-    }
-    if (!more) break;
-    slot ^= 1;
-    w_cur = w_next;
-    w_next = w_after;
-    dv_next = load_desc(w_next);
+    GPY_TRACE(13, seq);
   }
 }
 

@@ -1183,20 +1183,39 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       GPY_TRY(ensure_logtab(c));
       mp.logtab = (const double2*)c->logtab.p;
       if (const char* m = std::getenv("GPY_MMA_SKIP")) mp.debug_skip = std::atoi(m);
-      const int mma_nc = c->mma_warps == 11 ? 11 : 8;
-      const size_t warps_bytes = (size_t)mma_nc * gpy::kWarpBytes;
-      if (warps_bytes + mp.tab_bytes + gpy::kLogTabBytes + 256 > (size_t)c->max_smem_optin) {
-        mp.tab_ds = -1;  // (two edisp groups with 11 warps: the tables are read through L1 instead)
-        mp.tab_bytes = 0;
+      const char* trace_path = std::getenv("GPY_MMA_TRACE");
+      if (trace_path) {
+        GPY_TRY(c->scratch_c.reserve((1 + 4 * 60000) * sizeof(long long)));
+        CUDA_TRY(cudaMemsetAsync(c->scratch_c.p, 0, sizeof(long long), c->stream));
+        mp.trace = (long long*)c->scratch_c.p;
       }
-      mp.lay_tab = (unsigned)warps_bytes;
+      const int mma_nc = c->mma_warps == 11 ? 11 : 7;
+      const size_t fs_bytes = (size_t)(mma_nc + 1) * 2 * gpy::kMmaMaxNT * sizeof(double);
+      mp.stage_bytes = (max_nT * gpy::kFoldTPX * 4 + 512 + 127) / 128 * 128;
+      auto fits = [&](int stages) {
+        return (size_t)stages * mp.stage_bytes + mp.tab_bytes + gpy::kLogTabBytes + fs_bytes +
+                   (2 * (size_t)stages + 2) * sizeof(uint64_t) + 64 <= (size_t)c->max_smem_optin;
+      };
+      int stages = c->mma_stages > 0 ? c->mma_stages : 8;
+      while (stages > 0 && !fits(stages)) --stages;
+      if (stages * gpy::kMmaSubs < mma_nc + gpy::kMmaSubs) {  // consumers may not run a lap ahead of a stage's barrier
+        mp.tab_ds = -1;  // make room: the edisp tables are then read through L1
+        mp.tab_bytes = 0;
+        stages = c->mma_stages > 0 ? c->mma_stages : 8;
+        while (stages > 0 && !fits(stages)) --stages;
+      }
+      if (stages * gpy::kMmaSubs < mma_nc + gpy::kMmaSubs)
+        return fail(GPY_ERR_UNSUPPORTED, "not enough shared memory for the fold pipeline (%d stages)", stages);
+      mp.n_stages = stages;
+      mp.lay_tab = (unsigned)((size_t)stages * mp.stage_bytes);
       mp.lay_log = (unsigned)((mp.lay_tab + mp.tab_bytes + 15) / 16 * 16);
-      mp.lay_bars = mp.lay_log + gpy::kLogTabBytes;
-      const size_t smem = (size_t)mp.lay_bars + 2 * (size_t)mma_nc * sizeof(uint64_t);
+      mp.lay_fs = mp.lay_log + gpy::kLogTabBytes;
+      mp.lay_bars = mp.lay_fs + (unsigned)fs_bytes;
+      const size_t smem = (size_t)mp.lay_bars + (2 * (size_t)stages + 2) * sizeof(uint64_t);
       parts_per_tile = gpy::kMmaSubs;
       GPY_TRY(c->partials.reserve((size_t)B * n_tiles * gpy::kMmaSubs * sizeof(double)));
       fp.partials = (double*)c->partials.p;
-      const bool dynamic = n_work_host >= (size_t)4 * c->num_sms * mma_nc && !c->static_schedule;
+      const bool dynamic = n_work_host >= (size_t)4 * c->num_sms && !c->static_schedule;
       const bool wide = c->mma_warps == 11;
       using MmaKern = void (*)(const gpy::FoldParams, const gpy::MmaParams);
       MmaKern kern;
@@ -1204,8 +1223,8 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         kern = variant ? (dynamic ? gpy::fold_cash_mma_kernel<true, true, 11> : gpy::fold_cash_mma_kernel<true, false, 11>)
                        : (dynamic ? gpy::fold_cash_mma_kernel<false, true, 11> : gpy::fold_cash_mma_kernel<false, false, 11>);
       else
-        kern = variant ? (dynamic ? gpy::fold_cash_mma_kernel<true, true, 8> : gpy::fold_cash_mma_kernel<true, false, 8>)
-                       : (dynamic ? gpy::fold_cash_mma_kernel<false, true, 8> : gpy::fold_cash_mma_kernel<false, false, 8>);
+        kern = variant ? (dynamic ? gpy::fold_cash_mma_kernel<true, true, 7> : gpy::fold_cash_mma_kernel<true, false, 7>)
+                       : (dynamic ? gpy::fold_cash_mma_kernel<false, true, 7> : gpy::fold_cash_mma_kernel<false, false, 7>);
       const int kslot = (wide ? 4 : 0) + variant * 2 + (dynamic ? 1 : 0);
       if (smem > c->mma_smem_set[kslot]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1213,13 +1232,24 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
                                       cudaSharedmemCarveoutMaxShared));
         c->mma_smem_set[kslot] = smem;
       }
-      const unsigned grid = (unsigned)std::min((n_work_host + mma_nc - 1) / mma_nc, (size_t)c->num_sms);
+      const unsigned grid = (unsigned)std::min(n_work_host, (size_t)c->num_sms);
       if (dynamic) {
         fp.counter = (unsigned*)((uint8_t*)c->zeros.p + 128);
         CUDA_TRY(cudaMemsetAsync(fp.counter, 0, sizeof(unsigned), c->stream));
       }
       if (c->timing) CUDA_TRY(cudaEventRecord(c->t_begin, c->stream));
-      kern<<<grid, mma_nc * 32, smem, c->stream>>>(fp, mp);
+      kern<<<grid, (mma_nc + 1) * 32, smem, c->stream>>>(fp, mp);
+      if (trace_path) {  // profiling only: dump the event list of CTA 0 of this launch
+        std::vector<long long> ev(1 + 4 * 60000);
+        CUDA_TRY(cudaMemcpyAsync(ev.data(), mp.trace, ev.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (FILE* fh = std::fopen(trace_path, "w")) {
+          const long long n = std::min<long long>(ev[0], 60000);
+          for (long long i = 0; i < n; ++i)
+            std::fprintf(fh, "%lld %lld %lld %lld\n", ev[1 + 4 * i], ev[2 + 4 * i], ev[3 + 4 * i], ev[4 + 4 * i]);
+          std::fclose(fh);
+        }
+      }
       if (c->timing) {
         CUDA_TRY(cudaEventRecord(c->t_end, c->stream));
         c->timing_pending = true;
@@ -1313,7 +1343,7 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
   c->no_desc_cache = std::getenv("GPY_NO_DESC_CACHE") != nullptr;
   if (const char* m = std::getenv("GPY_FOLD_KERNEL")) c->fold_mode = std::atoi(m);
   if (c->fold_mode == 2) c->force_generic = true;
-  if (const char* m = std::getenv("GPY_MMA_WARPS")) c->mma_warps = std::atoi(m) == 11 ? 11 : 8;
+  if (const char* m = std::getenv("GPY_MMA_WARPS")) c->mma_warps = std::atoi(m) == 11 ? 11 : 7;
   if (const char* m = std::getenv("GPY_MMA_STAGES")) c->mma_stages = std::atoi(m);
   {
     cudaMemPool_t pool;
@@ -1341,10 +1371,10 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
         (const void*)gpy::fold_cash_tma_kernel<false, true>,
         (const void*)gpy::fold_cash_tma_kernel<true, false>,
         (const void*)gpy::fold_cash_tma_kernel<true, true>,
-        (const void*)gpy::fold_cash_mma_kernel<false, false, 8>,
-        (const void*)gpy::fold_cash_mma_kernel<false, true, 8>,
-        (const void*)gpy::fold_cash_mma_kernel<true, false, 8>,
-        (const void*)gpy::fold_cash_mma_kernel<true, true, 8>,
+        (const void*)gpy::fold_cash_mma_kernel<false, false, 7>,
+        (const void*)gpy::fold_cash_mma_kernel<false, true, 7>,
+        (const void*)gpy::fold_cash_mma_kernel<true, false, 7>,
+        (const void*)gpy::fold_cash_mma_kernel<true, true, 7>,
         (const void*)gpy::fold_cash_mma_kernel<false, false, 11>,
         (const void*)gpy::fold_cash_mma_kernel<false, true, 11>,
         (const void*)gpy::fold_cash_mma_kernel<true, false, 11>,
