@@ -23,7 +23,6 @@
 
 #include "../../include/gpy_b200.h"
 #include "kernels.cuh"
-#include "fold_mma.cuh"
 #include "tsmap.cuh"
 
 namespace {
@@ -268,10 +267,6 @@ struct gpy_context {
   int* nwork_pinned = nullptr;  // read-back of the batched worklist length
   size_t stat_pinned_cap = 0;
   size_t ts_smem_set = 0, fold_smem_set = 0, conv_smem_set = 0, tma_smem_set[4] = {0, 0, 0, 0};
-  size_t mma_smem_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int mma_stages = 0;  // GPY_MMA_STAGES: cap on the stages of the exposure ring (0: as many as fit)
-  DevBuf logtab;       // fast_log table of fold_cash_mma_kernel
-  int mma_warps = 11;  // GPY_MMA_WARPS: warps per CTA of fold_cash_mma_kernel (8 or 11)
   int tma_blocks_per_sm[2] = {0, 0};
   int num_sms = 0;
   bool force_generic = false;
@@ -279,7 +274,7 @@ struct gpy_context {
   bool no_desc_cache = false;  // GPY_NO_DESC_CACHE: run prep_items_kernel on every call
   std::vector<uint8_t> desc_key;  // what the descriptors in `desc` were built from (empty: none)
   bool no_dedup = false;  // GPY_NO_DEDUP: evaluate every item of a batch even when identical to vector 0's
-  int fold_mode = 0;  // GPY_FOLD_KERNEL: 0 auto (DMMA pipeline kernel, else staged kernel, else generic), 1 staged, 2 generic
+  int fold_mode = 0;  // GPY_FOLD_KERNEL: 0 auto (bulk-copy staged kernel when eligible), 2 generic
   double log_trunc = 0.0;
   int max_smem_optin = 0;
 };
@@ -298,10 +293,6 @@ struct gpy_dataset {
   DevBuf d_tmaps;             // 4 CUtensorMap: exposure, background, counts, mask (2-D [rows][P] tensors, box [rows][128])
   std::vector<DevBuf> retired_tmaps;  // earlier map blocks: a rewritten map gets a NEW address (descriptor caches)
   bool has_tmaps = false;
-  DevBuf d_tmaps_mma;         // the same four cubes with [rows][32 px] boxes, SWIZZLE_128B (fold_cash_mma_kernel)
-  bool has_tmaps_mma = false;
-  DevBuf d_mma_table;         // MmaTableHead + B fragments (fold_mma.cuh)
-  size_t mma_table_bytes = 0;
   std::vector<gpy::ConvPlane> planes;
   int max_h = 0, max_kw = 4;
   bool has_psf = false, has_diag = false;
@@ -510,18 +501,16 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-bool encode_map(CUtensorMap* out, const void* base, bool is_u8, size_t P, int rows, int box_px = gpy::kFoldTPX,
-                bool swizzle128 = false) {
+bool encode_map(CUtensorMap* out, const void* base, bool is_u8, size_t P, int rows) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn || !base || rows > 256) return false;
   const size_t esz = is_u8 ? 1 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)P, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)(P * esz)};
-  cuuint32_t box[2] = {(cuuint32_t)box_px, (cuuint32_t)rows};
+  cuuint32_t box[2] = {(cuuint32_t)gpy::kFoldTPX, (cuuint32_t)rows};
   cuuint32_t estr[2] = {1, 1};
   return fn(out, is_u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
-            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -529,7 +518,6 @@ bool encode_map(CUtensorMap* out, const void* base, bool is_u8, size_t P, int ro
 // 1-D bulk copies) or the driver entry point is missing.
 int build_tmaps(gpy_dataset* ds) {
   ds->has_tmaps = false;
-  ds->has_tmaps_mma = false;
   const size_t P = (size_t)ds->geom.nx * ds->geom.ny;
   if (P % 16 != 0 || ds->geom.nx % 4 != 0 || P < (size_t)gpy::kFoldTPX) return GPY_OK;
   alignas(64) CUtensorMap maps[4];
@@ -546,64 +534,7 @@ int build_tmaps(gpy_dataset* ds) {
   CUDA_TRY(cudaMemcpyAsync(ds->d_tmaps.p, maps, sizeof(maps), cudaMemcpyHostToDevice, ds->ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ds->ctx->stream));
   ds->has_tmaps = true;
-  // fold_cash_mma_kernel: [rows][32 px] boxes; the float cubes land 128-byte swizzled (bank-conflict-free fragment reads)
-  if (ds->nT <= gpy::kMmaMaxNT && ds->nR <= gpy::kMmaMaxNR) {
-    alignas(64) CUtensorMap m2[4];
-    std::memset(m2, 0, sizeof(m2));
-    bool ok = encode_map(&m2[0], ds->exposure, false, P, ds->nT, gpy::kMmaSub, true);
-    if (ok && ds->background) ok = encode_map(&m2[1], ds->background, false, P, ds->nR, gpy::kMmaSub, true);
-    if (ok && ds->counts) ok = encode_map(&m2[2], ds->counts, false, P, ds->nR, gpy::kMmaSub, true);
-    if (ok && ds->mask) ok = encode_map(&m2[3], ds->mask, true, P, ds->nR, gpy::kMmaSub, false);
-    if (ok) {
-      if (ds->d_tmaps_mma.p) {
-        ds->retired_tmaps.push_back(ds->d_tmaps_mma);
-        ds->d_tmaps_mma = DevBuf();
-      }
-      GPY_TRY(ds->d_tmaps_mma.reserve(sizeof(m2)));
-      CUDA_TRY(cudaMemcpyAsync(ds->d_tmaps_mma.p, m2, sizeof(m2), cudaMemcpyHostToDevice, ds->ctx->stream));
-      CUDA_TRY(cudaStreamSynchronize(ds->ctx->stream));
-      ds->has_tmaps_mma = true;
-    }
-  }
   return GPY_OK;
-}
-
-// Edisp matrices in DMMA B-fragment order (fold_mma.cuh): for every k-step ks (true bins 8 (ks >> 1) + (ks & 1) + 2 tg)
-// and n-tile n (reco bins 8 n + g) with a non-zero coefficient, 32 doubles in lane order (lane = 4 g + tg), scaled by
-// the cm2 -> m2 factor 1e4 of apply_exposure (evaluator.py:351).
-void build_mma_table(int nT, int nR, const double* const* groups, int n_groups, std::vector<uint8_t>& out) {
-  gpy::MmaTableHead head;
-  std::memset(&head, 0, sizeof(head));
-  head.n_groups = n_groups;
-  std::vector<double> frag((size_t)n_groups * gpy::kMmaGroupDoubles, 0.0);
-  for (int gi = 0; gi < n_groups; ++gi) {
-    const double* pdf = groups[gi];
-    int lo = gpy::kMmaKSteps, hi = 0;
-    for (int ks = 0; ks < gpy::kMmaKSteps; ++ks) {
-      unsigned m = 0;
-      for (int n = 0; n < gpy::kMmaNTiles; ++n) {
-        bool any = false;
-        for (int lane = 0; lane < 32; ++lane) {
-          const int t = 8 * (ks >> 1) + (ks & 1) + 2 * (lane & 3), r = 8 * n + (lane >> 2);
-          const double v = t < nT && r < nR ? pdf[(size_t)t * nR + r] : 0.0;
-          if (v != 0.0) any = true;  // NaN counts as non-zero
-          frag[(((size_t)gi * gpy::kMmaKSteps + ks) * gpy::kMmaNTiles + n) * 32 + lane] = 1e4 * v;
-        }
-        if (any) m |= 1u << n;
-      }
-      head.bits[gi] |= (unsigned long long)m << (4 * ks);
-      if (m) {
-        lo = std::min(lo, ks);
-        hi = std::max(hi, ks + 1);
-      }
-    }
-    if (lo > hi) lo = hi = 0;
-    head.ks_lo[gi] = lo;
-    head.ks_hi[gi] = hi;
-  }
-  out.resize(sizeof(head) + frag.size() * sizeof(double));
-  std::memcpy(out.data(), &head, sizeof(head));
-  std::memcpy(out.data() + sizeof(head), frag.data(), frag.size() * sizeof(double));
 }
 
 // MapEvaluator.update geometry (evaluator.py:174-243) for spatial parameters `sp`.
@@ -691,22 +622,6 @@ int get_slot(gpy_dataset* ds, Source& src, const double* sp, const Rect& rect, u
   return GPY_OK;
 }
 
-// fast_log table (fold_mma.cuh): for the top 7 mantissa bits i, c_i = 1 / m_hi rounded to double with
-// m_hi = 1 + (i + 0.5) / 128, and l_i = -log(c_i) evaluated in extended precision.
-int ensure_logtab(gpy_context* c) {
-  if (c->logtab.p) return GPY_OK;
-  double tab[256];
-  for (int i = 0; i < 128; ++i) {
-    const double ci = 1.0 / (1.0 + (i + 0.5) / 128.0);
-    tab[2 * i] = ci;
-    tab[2 * i + 1] = (double)(-std::log((long double)ci));
-  }
-  GPY_TRY(c->logtab.reserve(sizeof(tab)));
-  CUDA_TRY(cudaMemcpyAsync(c->logtab.p, tab, sizeof(tab), cudaMemcpyHostToDevice, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));  // stack array
-  return GPY_OK;
-}
-
 struct EvalRequest {
   gpy_dataset* const* datasets;
   int n_datasets;
@@ -759,7 +674,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   size_t flux_len = 0;
   int n_tiles = 0, max_inst = 1, max_tile_overlap = 0;
   int max_nT = 0, max_nR = 0, max_nRp = 0, max_G = 0, max_pdfc_rows = 1;
-  bool tma_ok = true, mma_ok = c->fold_mode == 0;
+  bool tma_ok = true;
   const bool sequential = (B == 1);
   const uint64_t call_id = ++c->stamp;
 
@@ -799,9 +714,6 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     max_pdfc_rows = std::max(max_pdfc_rows, dd.pdfc_rows);
     dd.ecenter = (const double*)ds->d_ecenter.p;
     dd.tmaps = ds->has_tmaps ? ds->d_tmaps.p : nullptr;
-    dd.tmaps_mma = ds->has_tmaps_mma ? ds->d_tmaps_mma.p : nullptr;
-    dd.mma_table = ds->mma_table_bytes ? ds->d_mma_table.p : nullptr;
-    if (!ds->has_tmaps_mma || !ds->mma_table_bytes) mma_ok = false;
     if (!rq.npred_out && !ds->counts) return fail(GPY_ERR_INVALID, "dataset %d has no counts: stat undefined", d);
 
     for (int b = 0; b < B; ++b) {
@@ -981,9 +893,9 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       tma_ok = false;
   }
   const gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G, max_pdfc_rows);
-  if (c->force_generic || max_tile_overlap > gpy::kFoldLMax + gpy::kDescOverflow) tma_ok = false;
-  if (!tma_ok) mma_ok = false;
-  if (!mma_ok && lay.total > (size_t)c->max_smem_optin) tma_ok = false;
+  if (lay.total > (size_t)c->max_smem_optin || c->force_generic ||
+      max_tile_overlap > gpy::kFoldLMax + gpy::kDescOverflow)
+    tma_ok = false;
   size_t max_fold_smem = 0;
   if (!tma_ok) {
     for (int d = 0; d < D; ++d)
@@ -1086,7 +998,6 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   const size_t n_items = (size_t)B * n_tiles;
   const unsigned char* reduce_dup = nullptr;
   const int variant = rq.npred_out ? 1 : 0;
-  int parts_per_tile = 1;
   if (tma_ok) {
     const gpy::DescLayout dl = gpy::desc_layout();
     fp.lay_es = (unsigned)lay.es;
@@ -1169,92 +1080,6 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       c->desc_key.swap(key);  // empty after a batched call: the next B == 1 call rebuilds
     }
     fp.desc = (const unsigned char*)c->desc.p;
-    if (c->timing) {
-      GPY_TRY(timing_collect(c));
-    }
-    if (mma_ok) {
-      // DMMA pipeline kernel: one CTA per SM, stages of 32-pixel sub-items.  The table of the first dataset is
-      // cached in shared memory (other datasets of a joint launch read theirs through L1).
-      gpy::MmaParams mp;
-      std::memset(&mp, 0, sizeof(mp));
-      mp.tab_ds = 0;
-      // (only the groups in use are cached: the diagonal-response matrices follow the dataset's own in the table)
-      mp.tab_bytes = (int)(sizeof(gpy::MmaTableHead) + (size_t)rq.datasets[0]->groups_used * gpy::kMmaGroupDoubles * sizeof(double));
-      GPY_TRY(ensure_logtab(c));
-      mp.logtab = (const double2*)c->logtab.p;
-      if (const char* m = std::getenv("GPY_MMA_SKIP")) mp.debug_skip = std::atoi(m);
-      const char* trace_path = std::getenv("GPY_MMA_TRACE");
-      if (trace_path) {
-        GPY_TRY(c->scratch_c.reserve((1 + 4 * 60000) * sizeof(long long)));
-        CUDA_TRY(cudaMemsetAsync(c->scratch_c.p, 0, sizeof(long long), c->stream));
-        mp.trace = (long long*)c->scratch_c.p;
-      }
-      const int mma_nc = c->mma_warps == 11 ? 11 : 7;
-      const size_t fs_bytes = (size_t)(mma_nc + 1) * 2 * gpy::kMmaMaxNT * sizeof(double);
-      mp.stage_bytes = (max_nT * gpy::kFoldTPX * 4 + 512 + 127) / 128 * 128;
-      auto fits = [&](int stages) {
-        return (size_t)stages * mp.stage_bytes + mp.tab_bytes + gpy::kLogTabBytes + fs_bytes +
-                   (2 * (size_t)stages + 2) * sizeof(uint64_t) + 64 <= (size_t)c->max_smem_optin;
-      };
-      int stages = c->mma_stages > 0 ? c->mma_stages : 8;
-      while (stages > 0 && !fits(stages)) --stages;
-      if (stages * gpy::kMmaSubs < mma_nc + gpy::kMmaSubs) {  // consumers may not run a lap ahead of a stage's barrier
-        mp.tab_ds = -1;  // make room: the edisp tables are then read through L1
-        mp.tab_bytes = 0;
-        stages = c->mma_stages > 0 ? c->mma_stages : 8;
-        while (stages > 0 && !fits(stages)) --stages;
-      }
-      if (stages * gpy::kMmaSubs < mma_nc + gpy::kMmaSubs)
-        return fail(GPY_ERR_UNSUPPORTED, "not enough shared memory for the fold pipeline (%d stages)", stages);
-      mp.n_stages = stages;
-      mp.lay_tab = (unsigned)((size_t)stages * mp.stage_bytes);
-      mp.lay_log = (unsigned)((mp.lay_tab + mp.tab_bytes + 15) / 16 * 16);
-      mp.lay_fs = mp.lay_log + gpy::kLogTabBytes;
-      mp.lay_bars = mp.lay_fs + (unsigned)fs_bytes;
-      const size_t smem = (size_t)mp.lay_bars + (2 * (size_t)stages + 2) * sizeof(uint64_t);
-      parts_per_tile = gpy::kMmaSubs;
-      GPY_TRY(c->partials.reserve((size_t)B * n_tiles * gpy::kMmaSubs * sizeof(double)));
-      fp.partials = (double*)c->partials.p;
-      const bool dynamic = n_work_host >= (size_t)4 * c->num_sms && !c->static_schedule;
-      const bool wide = c->mma_warps == 11;
-      using MmaKern = void (*)(const gpy::FoldParams, const gpy::MmaParams);
-      MmaKern kern;
-      if (wide)
-        kern = variant ? (dynamic ? gpy::fold_cash_mma_kernel<true, true, 11> : gpy::fold_cash_mma_kernel<true, false, 11>)
-                       : (dynamic ? gpy::fold_cash_mma_kernel<false, true, 11> : gpy::fold_cash_mma_kernel<false, false, 11>);
-      else
-        kern = variant ? (dynamic ? gpy::fold_cash_mma_kernel<true, true, 7> : gpy::fold_cash_mma_kernel<true, false, 7>)
-                       : (dynamic ? gpy::fold_cash_mma_kernel<false, true, 7> : gpy::fold_cash_mma_kernel<false, false, 7>);
-      const int kslot = (wide ? 4 : 0) + variant * 2 + (dynamic ? 1 : 0);
-      if (smem > c->mma_smem_set[kslot]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-        c->mma_smem_set[kslot] = smem;
-      }
-      const unsigned grid = (unsigned)std::min(n_work_host, (size_t)c->num_sms);
-      if (dynamic) {
-        fp.counter = (unsigned*)((uint8_t*)c->zeros.p + 128);
-        CUDA_TRY(cudaMemsetAsync(fp.counter, 0, sizeof(unsigned), c->stream));
-      }
-      if (c->timing) CUDA_TRY(cudaEventRecord(c->t_begin, c->stream));
-      kern<<<grid, (mma_nc + 1) * 32, smem, c->stream>>>(fp, mp);
-      if (trace_path) {  // profiling only: dump the event list of CTA 0 of this launch
-        std::vector<long long> ev(1 + 4 * 60000);
-        CUDA_TRY(cudaMemcpyAsync(ev.data(), mp.trace, ev.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        if (FILE* fh = std::fopen(trace_path, "w")) {
-          const long long n = std::min<long long>(ev[0], 60000);
-          for (long long i = 0; i < n; ++i)
-            std::fprintf(fh, "%lld %lld %lld %lld\n", ev[1 + 4 * i], ev[2 + 4 * i], ev[3 + 4 * i], ev[4 + 4 * i]);
-          std::fclose(fh);
-        }
-      }
-      if (c->timing) {
-        CUDA_TRY(cudaEventRecord(c->t_end, c->stream));
-        c->timing_pending = true;
-      }
-    } else {
     // Items differ in cost (source-free tiles are light): with many items per CTA they are claimed dynamically.
     // (grid <= 2 CTAs per SM; 8 items per CTA at least.)
     const bool dynamic = B == 1 && n_work_host >= (size_t)16 * c->num_sms && !c->static_schedule;
@@ -1275,12 +1100,14 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       fp.counter = (unsigned*)((uint8_t*)c->zeros.p + 128);
       CUDA_TRY(cudaMemsetAsync(fp.counter, 0, sizeof(unsigned), c->stream));
     }
-    if (c->timing) CUDA_TRY(cudaEventRecord(c->t_begin, c->stream));
+    if (c->timing) {
+      GPY_TRY(timing_collect(c));
+      CUDA_TRY(cudaEventRecord(c->t_begin, c->stream));
+    }
     kern<<<grid, gpy::kFoldThreads, lay.total, c->stream>>>(fp);
     if (c->timing) {
       CUDA_TRY(cudaEventRecord(c->t_end, c->stream));
       c->timing_pending = true;
-    }
     }
   } else {
     if (max_fold_smem > c->fold_smem_set) {
@@ -1295,7 +1122,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   c->launches++;
   if (!rq.npred_out) {
     gpy::reduce_stat_kernel<<<dim3(B, D), 256, 0, c->stream>>>((const double*)c->partials.p, fp.ds, n_tiles, D,
-                                                              B, reduce_dup, (double*)c->stat.p, parts_per_tile);
+                                                              B, reduce_dup, (double*)c->stat.p);
     c->launches++;
   }
   CUDA_TRY(cudaGetLastError());
@@ -1343,8 +1170,6 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
   c->no_desc_cache = std::getenv("GPY_NO_DESC_CACHE") != nullptr;
   if (const char* m = std::getenv("GPY_FOLD_KERNEL")) c->fold_mode = std::atoi(m);
   if (c->fold_mode == 2) c->force_generic = true;
-  if (const char* m = std::getenv("GPY_MMA_WARPS")) c->mma_warps = std::atoi(m) == 11 ? 11 : 7;
-  if (const char* m = std::getenv("GPY_MMA_STAGES")) c->mma_stages = std::atoi(m);
   {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -1371,14 +1196,6 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
         (const void*)gpy::fold_cash_tma_kernel<false, true>,
         (const void*)gpy::fold_cash_tma_kernel<true, false>,
         (const void*)gpy::fold_cash_tma_kernel<true, true>,
-        (const void*)gpy::fold_cash_mma_kernel<false, false, 7>,
-        (const void*)gpy::fold_cash_mma_kernel<false, true, 7>,
-        (const void*)gpy::fold_cash_mma_kernel<true, false, 7>,
-        (const void*)gpy::fold_cash_mma_kernel<true, true, 7>,
-        (const void*)gpy::fold_cash_mma_kernel<false, false, 11>,
-        (const void*)gpy::fold_cash_mma_kernel<false, true, 11>,
-        (const void*)gpy::fold_cash_mma_kernel<true, false, 11>,
-        (const void*)gpy::fold_cash_mma_kernel<true, true, 11>,
         (const void*)gpy::fold_cash_generic_kernel,
         (const void*)gpy::reduce_stat_kernel,
         (const void*)gpy::cash_sum_kernel,
@@ -1399,7 +1216,7 @@ int gpy_finalize(gpy_context_t* c) {
   if (!c) return GPY_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->logtab, &c->zeros, &c->desc, &c->dedup, &c->staging, &c->flux, &c->partials, &c->stat, &c->tiles, &c->scratch_a, &c->scratch_b, &c->scratch_c})
+  for (DevBuf* b : {&c->zeros, &c->desc, &c->dedup, &c->staging, &c->flux, &c->partials, &c->stat, &c->tiles, &c->scratch_a, &c->scratch_b, &c->scratch_c})
     b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->stat_pinned) cudaFreeHost(c->stat_pinned);
@@ -1516,13 +1333,6 @@ int gpy_dataset_create(gpy_context_t* c, const gpy_dataset_desc* desc, gpy_datas
   if ((rc = upload_to(ds->d_pdfc, pdfc.data(), pdfc.size() * sizeof(double), s))) return cleanup(rc);
   if ((rc = upload_to(ds->d_edisp, ed.data(), ed.size() * sizeof(double), s))) return cleanup(rc);
   if ((rc = upload_to(ds->d_band, band.data(), band.size() * sizeof(int), s))) return cleanup(rc);
-  std::vector<uint8_t> mma_table;
-  if (ds->nT <= gpy::kMmaMaxNT && ds->nR <= gpy::kMmaMaxNR) {
-    const double* groups[2] = {desc->edisp, desc->edisp_diagonal};
-    build_mma_table(ds->nT, ds->nR, groups, ds->n_groups, mma_table);
-    ds->mma_table_bytes = mma_table.size();
-    if ((rc = upload_to(ds->d_mma_table, mma_table.data(), mma_table.size(), s))) return cleanup(rc);
-  }
   std::vector<float> kflip;
   if (desc->psf_kernel) {
     ds->has_psf = true;
@@ -1548,7 +1358,7 @@ int gpy_dataset_destroy(gpy_dataset_t* ds) {
   cudaSetDevice(ds->ctx->device);
   cudaStreamSynchronize(ds->ctx->stream);
   for (DevBuf* b : {&ds->d_edges, &ds->d_nodes, &ds->d_ecenter, &ds->d_edisp, &ds->d_band, &ds->d_pdfc, &ds->d_tmaps, &ds->d_omega, &ds->d_kflip,
-                    &ds->d_planes, &ds->d_tmaps_mma, &ds->d_mma_table})
+                    &ds->d_planes})
     b->release();
   for (auto& src : ds->sources)
     for (auto& sl : src.slots) {

@@ -436,8 +436,6 @@ struct DatasetDev {
   int pad2_;
   const double* ecenter;    // [nR]
   const void* tmaps;        // 4 CUtensorMap (exposure, background, counts, mask; 128 B each) or null: 1-D bulk copies
-  const void* tmaps_mma;    // 4 CUtensorMap of the same cubes with [rows][32 px] boxes (fold_cash_mma_kernel) or null
-  const void* mma_table;    // MmaTableHead + B fragments of the edisp matrices (fold_mma.cuh) or null
 };
 
 struct InstDev {  // one source in one parameter vector
@@ -1466,21 +1464,16 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
 // Second stage: stat[b, d] = 2 * sum of the tile partials of dataset d, fixed summation order.
 __global__ void __launch_bounds__(256)
 reduce_stat_kernel(const double* __restrict__ partials, const DatasetDev* __restrict__ ds, int n_tiles,
-                   int n_datasets, int B, const unsigned char* __restrict__ dup, double* __restrict__ stat,
-                   int parts_per_tile) {
+                   int n_datasets, int B, const unsigned char* __restrict__ dup, double* __restrict__ stat) {
   __shared__ double sm[256];
   const int b = blockIdx.x, d = blockIdx.y;
-  const int begin = ds[d].tile_begin;
-  // partials per dataset: one per tile (staged / generic kernels) or one per sub-item of kFoldTPX / parts_per_tile
-  // pixels that exists (fold_cash_mma_kernel)
-  const int sub_px = kFoldTPX / parts_per_tile;
-  const int n = (int)((ds[d].P + sub_px - 1) / sub_px);
+  const int begin = ds[d].tile_begin, n = ds[d].n_tiles;
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) {
-    const int tile = begin + i / parts_per_tile;
+    const int tile = begin + i;
     // items identical to vector 0 on this tile were not evaluated: read the partial of (tile, 0)
     const int bb = (dup && dup[(size_t)tile * B + b]) ? 0 : b;
-    s += partials[((size_t)bb * n_tiles + begin) * parts_per_tile + i];
+    s += partials[(size_t)bb * n_tiles + tile];
   }
   sm[threadIdx.x] = s;
   __syncthreads();
