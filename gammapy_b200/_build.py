@@ -1,4 +1,6 @@
-"""Compile ``libgpy_b200.so`` (sm_100a) in-tree with nvcc; no JIT cache, the .so travels with the repo."""
+"""Compile ``libgpy_b200.so`` (sm_100a) in-tree with nvcc, on first use or when a source is newer (no JIT cache).
+
+The built library is git-ignored (history stays source-only) but is part of the working tree ``gpurun`` ships."""
 import os
 import subprocess
 

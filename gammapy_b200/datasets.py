@@ -401,8 +401,19 @@ class Datasets(list):
 
     def stat_sum_batch(self, values, per_dataset=False):
         """Joint statistic for a batch of full parameter vectors [B, n_par] in ONE launch
-        (what ``Fit.stat_profile`` / ``stat_surface`` loop over, modeling/fit.py:351-519)."""
-        return self._get_engine().stat_sum(values, per_dataset=per_dataset)
+        (what ``Fit.stat_profile`` / ``stat_surface`` loop over, modeling/fit.py:351-519).  Like ``stat_sum`` it
+        includes the parameters' priors (datasets/core.py:264-277), evaluated on the host per vector; with
+        ``per_dataset=True`` the likelihood terms alone are returned, one column per dataset."""
+        eng = self._get_engine()
+        out = eng.stat_sum(values, per_dataset=per_dataset)
+        if not per_dataset and any(p.prior is not None for p in eng.parameters):
+            vals = np.atleast_2d(np.asarray(values, dtype=float))
+            prior = np.zeros(vals.shape[0])
+            for col, par in enumerate(eng.parameters):
+                if par.prior is not None:
+                    prior += par.prior.evaluate_many(vals[:, col])
+            out = out + (float(prior[0]) if np.ndim(out) == 0 else prior)
+        return out
 
     def parameter_vector(self):
         eng = self._get_engine()

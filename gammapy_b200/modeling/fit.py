@@ -178,7 +178,7 @@ def _gradient(like, x, f0, h, lo, hi):
     f = like.fcn_batch(pts, base=x)
     fp, fm = f[0::2], f[1::2]
     with np.errstate(divide="ignore", invalid="ignore"):
-        g = (fp - fm) / (hp + hm)
+        g = (fp - fm) / (hp + hm)  # one-sided when hp or hm is 0 (the point itself is evaluated: f0)
         g2 = 2 * (hm * fp + hp * fm - (hp + hm) * f0) / (hp * hm * (hp + hm))
     one_sided = (hp == 0) | (hm == 0)
     g = np.where(np.isfinite(g), g, 0.0)
@@ -204,17 +204,27 @@ def _minimize(like, tol=0.1, max_iter=200, store_trace=False):
     H = np.diag(diag)
     alphas = np.array([1.0, 0.5, 0.25, 0.1, 0.03, 0.01, 1e-3, 1.5, 2.0, 4.0])
     message, success = "maximum number of iterations reached", False
+    span = np.where(np.isfinite(hi - lo), hi - lo, 1.0)
     for it in range(max_iter):
-        edm = 0.5 * float(g @ H @ g)
+        # Active set: a component sitting on a limit whose descent direction points out of the box is blocked.  It
+        # leaves the gradient, the metric and the EDM (Minuit gets the same effect from its sin-transform, where
+        # the internal derivative vanishes on a limit); it is released as soon as its gradient turns inward.
+        blocked = ((x <= lo + 1e-12 * span) & (g > 0)) | ((x >= hi - 1e-12 * span) & (g < 0))
+        gp = np.where(blocked, 0.0, g)
+        Hp = H.copy()
+        Hp[blocked, :] = 0.0
+        Hp[:, blocked] = 0.0
+        edm = 0.5 * float(gp @ Hp @ gp)
         if store_trace:
             trace.append((it, f, x.copy()))
         if edm < edm_goal and it > 0:
             success, message = True, f"Optimization terminated successfully (EDM = {edm:.3g})."
             break
-        p = -H @ g
-        if not np.all(np.isfinite(p)) or g @ p >= 0:
+        p = -Hp @ gp
+        if not np.all(np.isfinite(p)) or gp @ p >= 0:
             H = np.diag(diag)
-            p = -H @ g
+            Hp = np.diag(np.where(blocked, 0.0, diag))
+            p = -Hp @ gp
         cand = np.clip(x[np.newaxis, :] + alphas[:, np.newaxis] * p[np.newaxis, :], lo, hi)
         fc = like.fcn_batch(cand)
         fc = np.where(np.isfinite(fc), fc, np.inf)
@@ -236,6 +246,9 @@ def _minimize(like, tol=0.1, max_iter=200, store_trace=False):
         h = np.maximum(0.1 * np.sqrt(np.abs(np.diag(H))), 1e-8 * np.maximum(np.abs(x_new), 1.0))
         g_new, g2 = _gradient(like, x_new, f_new, h, lo, hi)
         s, y = x_new - x, g_new - g
+        # the metric learns from the free components only (a clipped step says nothing about the curvature there)
+        s = np.where(blocked, 0.0, s)
+        y = np.where(blocked, 0.0, y)
         sy = float(s @ y)
         if sy > 1e-12 * np.linalg.norm(s) * np.linalg.norm(y):
             rho = 1.0 / sy
@@ -247,7 +260,9 @@ def _minimize(like, tol=0.1, max_iter=200, store_trace=False):
 
 
 def _hesse(like, x, f0):
-    """Symmetric finite-difference Hessian in factor space; 1 + 2n + 2n(n-1) points, batched."""
+    """Finite-difference Hessian in factor space, batched.  Central differences (1 + 2n + 2n(n-1) points) where the
+    box leaves room on both sides; a parameter on (or within a step of) a limit uses the inward one-sided stencils
+    f(x), f(x + a), f(x + 2a) and, for the mixed terms, the forward formula, so no point leaves the limits."""
     n = len(x)
     lo, hi = _bounds(like)
     h = _steps(like)
@@ -255,30 +270,49 @@ def _hesse(like, x, f0):
     g, g2 = _gradient(like, x, f0, h, lo, hi)
     good = np.isfinite(g2) & (g2 > 0)
     h = np.where(good, np.sqrt(2.0 * 0.1 / np.where(good, g2, 1.0)), h)
-    h = np.minimum(h, np.minimum(hi - x, x - lo) * 0.5 + (~np.isfinite(hi - x + x - lo)) * 0)
-    h = np.where(h > 0, h, _steps(like))
+    room_p, room_m = hi - x, x - lo
+    central = (room_p >= h) & (room_m >= h)
+    # one-sided: direction with more room, step such that x + 2 a stays inside
+    sign = np.where(room_p >= room_m, 1.0, -1.0)
+    room = np.maximum(room_p, room_m)
+    a = np.where(central, h, sign * np.minimum(h, 0.5 * room))
+    a = np.where(a == 0, _steps(like), a)
     pts = []
     for i in range(n):
-        for s in (+1, -1):
+        for k in ((+1, -1) if central[i] else (1, 2)):
             p = x.copy()
-            p[i] += s * h[i]
+            p[i] += k * a[i]
             pts.append(p)
     pairs = list(itertools.combinations(range(n), 2))
     for i, j in pairs:
-        for si, sj in ((1, 1), (1, -1), (-1, 1), (-1, -1)):
+        if central[i] and central[j]:
+            combos = ((1, 1), (1, -1), (-1, 1), (-1, -1))
+        else:
+            combos = ((1, 1),)
+        for si, sj in combos:
             p = x.copy()
-            p[i] += si * h[i]
-            p[j] += sj * h[j]
+            p[i] += si * a[i]
+            p[j] += sj * a[j]
             pts.append(p)
     f = like.fcn_batch(np.array(pts), base=x) if pts else np.zeros(0)
     like.set_factors(x)
     hess = np.zeros((n, n))
+    f1 = np.zeros(n)  # f(x + a_i e_i)
     for i in range(n):
-        hess[i, i] = (f[2 * i] - 2 * f0 + f[2 * i + 1]) / (h[i] * h[i])
-    base = 2 * n
-    for k, (i, j) in enumerate(pairs):
-        fpp, fpm, fmp, fmm = f[base + 4 * k: base + 4 * k + 4]
-        hess[i, j] = hess[j, i] = (fpp - fpm - fmp + fmm) / (4 * h[i] * h[j])
+        if central[i]:
+            hess[i, i] = (f[2 * i] - 2 * f0 + f[2 * i + 1]) / (a[i] * a[i])
+        else:
+            hess[i, i] = (f0 - 2 * f[2 * i] + f[2 * i + 1]) / (a[i] * a[i])
+        f1[i] = f[2 * i]
+    k = 2 * n
+    for i, j in pairs:
+        if central[i] and central[j]:
+            fpp, fpm, fmp, fmm = f[k: k + 4]
+            hess[i, j] = hess[j, i] = (fpp - fpm - fmp + fmm) / (4 * a[i] * a[j])
+            k += 4
+        else:
+            hess[i, j] = hess[j, i] = (f[k] - f1[i] - f1[j] + f0) / (a[i] * a[j])
+            k += 1
     return hess
 
 

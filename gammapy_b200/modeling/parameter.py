@@ -353,7 +353,12 @@ class Parameters(collections.abc.Sequence):
 
     def __getitem__(self, key):
         if isinstance(key, (np.ndarray, list)):
-            return Parameters([self[int(k)] if not isinstance(k, (bool, np.bool_)) else None for k in key])
+            arr = np.asarray(key)
+            if arr.dtype == bool:  # boolean mask, as the reference's Parameters.__getitem__ on a numpy mask
+                if arr.shape != (len(self._parameters),):
+                    raise IndexError(f"boolean mask of length {arr.size} for {len(self._parameters)} parameters")
+                return Parameters([p for p, keep in zip(self._parameters, arr) if keep])
+            return Parameters([self[k if isinstance(k, str) else int(k)] for k in key])
         if isinstance(key, slice):
             return Parameters(self._parameters[key])
         return self._parameters[self.index(key)]

@@ -8,6 +8,14 @@ DEG = np.pi / 180.0
 
 _ENERGY_TO_TEV = {"ev": 1e-12, "kev": 1e-9, "mev": 1e-6, "gev": 1e-3, "tev": 1.0, "pev": 1e3}
 _ANGLE_TO_DEG = {"deg": 1.0, "rad": 180.0 / np.pi, "arcmin": 1.0 / 60.0, "arcsec": 1.0 / 3600.0}
+# The package's fixed unit system (include/gpy_b200.h): units are labels, not conversions, so every other spelling of
+# a flux / inverse-energy / exposure unit is converted here or refused -- never kept silently.
+_FLUX_TO_CANONICAL = {  # -> cm-2 s-1 TeV-1
+    "cm-2 s-1 tev-1": 1.0, "1 / (cm2 s tev)": 1.0, "cm-2 s-1 gev-1": 1e3, "cm-2 s-1 mev-1": 1e6,
+    "cm-2 s-1 kev-1": 1e9, "m-2 s-1 tev-1": 1e-4, "m-2 s-1 gev-1": 1e-1, "m-2 s-1 mev-1": 1e2,
+}
+_INVERSE_ENERGY_TO_CANONICAL = {"tev-1": 1.0, "1 / tev": 1.0, "gev-1": 1e3, "mev-1": 1e6, "kev-1": 1e9, "pev-1": 1e-3}
+_PASS_THROUGH_UNITS = {"", "tev", "deg", "m2 s", "cm2 s", "sr-1", "1 / sr", "sr", "s", "m2"}
 _NUM = re.compile(r"^\s*([-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?|nan|inf|-inf)\s*(.*)$")
 
 
@@ -43,6 +51,16 @@ def parse_quantity(value, kind=None):
         return value * _ENERGY_TO_TEV[key], "TeV"
     if key in _ANGLE_TO_DEG and key != "deg":
         return value * _ANGLE_TO_DEG[key], "deg"
+    norm = " ".join(key.split())
+    if norm in _FLUX_TO_CANONICAL:
+        return value * _FLUX_TO_CANONICAL[norm], "cm-2 s-1 TeV-1"
+    if norm in _INVERSE_ENERGY_TO_CANONICAL:
+        return value * _INVERSE_ENERGY_TO_CANONICAL[norm], "TeV-1"
+    if norm == "cm2 s":
+        return value * 1e-4, "m2 s"
+    if norm not in _PASS_THROUGH_UNITS:
+        raise ValueError(f"Unit {unit!r} is not one this package converts (TeV, deg, cm-2 s-1 TeV-1, TeV-1, m2 s and "
+                         "their common multiples): refusing to keep it as a label")
     return value, unit
 
 

@@ -157,3 +157,55 @@ def test_ts_map_host_logic():
     with pytest.raises(ValueError, match="No valid positions"):
         TSMapEstimator().estimate_flux_map({"mask": np.zeros((1, 5, 6), dtype=bool), "background": background[:1],
                                             "counts": counts[:1], "exposure": counts[:1], "kernel": np.ones((1, 3, 3))})
+
+
+def test_fit_with_the_minimum_on_a_parameter_limit():
+    """a fit whose unconstrained minimum lies outside a limit must end ON the limit with success, the
+    other parameters at the constrained optimum, and Hesse must not evaluate points outside the limits."""
+    from gammapy_b200.distributed import ShardedDatasets
+    from gammapy_b200.modeling import Fit
+    from gammapy_b200.modeling.models import PowerLawSpectralModel, PointSpatialModel, SkyModel
+
+    model = SkyModel(spatial_model=PointSpatialModel(lon_0=0.0, lat_0=0.0, frame="galactic"),
+                     spectral_model=PowerLawSpectralModel(index=2.0, amplitude=1e-12, reference=1), name="src")
+    for name in ("lon_0", "lat_0"):
+        getattr(model.spatial_model, name).frozen = True
+    index, amplitude = model.spectral_model.index, model.spectral_model.amplitude
+    index.min, index.max = 2.5, 4.0      # the unconstrained minimum (index = 2.0) lies below the limit
+    index.value = 3.0
+    pars = list(model.parameters)
+    names = [p.name for p in pars]
+    seen = []
+
+    def local_stat(values):
+        seen.append(values[:, names.index("index")].copy())
+        i, a = values[:, names.index("index")], np.log(values[:, names.index("amplitude")] / 2e-12)
+        return 40 * (i - 2.0) ** 2 + 30 * a ** 2 + 24 * (i - 2.0) * a
+
+    sharded = ShardedDatasets(None, local_stat=local_stat, global_models=[model], local_parameters=pars)
+    result = Fit().run(sharded)
+    assert result.success, result.message
+    assert index.value == pytest.approx(2.5, abs=1e-9)
+    # constrained optimum in log-amplitude: 60 a + 24 (2.5 - 2.0) = 0
+    # (the EDM goal 2e-4 stops within 30 d^2 < 2e-4, i.e. |d| < 2.6e-3 = 0.014 sigma of the optimum)
+    assert np.log(amplitude.value / 2e-12) == pytest.approx(-0.2, abs=3e-3)
+    assert min(float(v.min()) for v in seen) >= 2.5 - 1e-12
+    assert max(float(v.max()) for v in seen) <= 4.0 + 1e-12
+    assert np.isfinite(amplitude.error) and amplitude.error > 0
+
+
+def test_units_are_converted_or_refused_and_boolean_masks_select():
+    from gammapy_b200.modeling.parameter import Parameter, Parameters
+    from gammapy_b200.utils import parse_quantity
+
+    assert parse_quantity("1e-9 cm-2 s-1 GeV-1") == (pytest.approx(1e-6), "cm-2 s-1 TeV-1")
+    assert parse_quantity("2 m-2 s-1 TeV-1") == (pytest.approx(2e-4), "cm-2 s-1 TeV-1")
+    assert parse_quantity("0.1 GeV-1") == (pytest.approx(100.0), "TeV-1")
+    assert parse_quantity("3 cm2 s") == (pytest.approx(3e-4), "m2 s")
+    with pytest.raises(ValueError):
+        parse_quantity("1 erg-1 cm-2 s-1")
+    pars = Parameters([Parameter("a", 1.0), Parameter("b", 2.0), Parameter("c", 3.0)])
+    assert pars[np.array([True, False, True])].names == ["a", "c"]
+    assert pars[[0, 2]].names == ["a", "c"]
+    with pytest.raises(IndexError):
+        pars[np.array([True, False])]
