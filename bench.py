@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- npred + Cash evaluations/s on the Galactic-plane survey MapDataset (BASELINE.json configs[2]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c3-small|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c3-flat|c3-small|c1|c2|c4|c4-large|c5-one]
 
 A *step* is one full likelihood evaluation (one parameter vector, every source's spectral parameters moved,
 spatial / PSF caches warm exactly as in the reference's steady-state Minuit step) of one MapDataset per GPU.
@@ -31,6 +31,11 @@ WORKLOADS = {
                desc="Galactic-plane survey MapDataset 2000x500 px, 30 reco / 60 true bins, 50 sources"),
     "c3-small": dict(width=(10.0, 5.0), n_sources=12, n_reco=30, n_true=60,
                      desc="reduced survey MapDataset 500x250 px, 30 reco / 60 true bins, 12 sources (debug)"),
+    # the same shape with exposure / background flat along the plane (falloff in latitude only): every low-energy bin of
+    # the map holds counts, so the Cash pass takes a log for most bins
+    "c3-flat": dict(width=(40.0, 10.0), n_sources=50, n_reco=30, n_true=60, falloff="latitude",
+                    desc="Galactic-plane survey MapDataset 2000x500 px, 30 reco / 60 true bins, 50 sources, exposure and "
+                         "background flat in longitude (dense counts)"),
     # one dataset of BASELINE.json configs[4] (CTAO-like resolution, 4000x1000 px, 2.04 GB of cubes): secondary measurement
     "c5-one": dict(width=(80.0, 20.0), n_sources=100, n_reco=30, n_true=60,
                    desc="one CTAO-resolution MapDataset 4000x1000 px, 30 reco / 60 true bins, 100 sources (one of the "
@@ -48,6 +53,39 @@ WORKLOADS = {
                      geometry=dict(width=(20.0, 5.0), n_reco=30, n_true=60, e_reco=(0.1, 100.0), e_true=(0.03, 300.0),
                                    mask_radius=None)),
 }
+
+
+def config_for(workload):
+    """The `config` object of the JSON line: identical in the repo arm and the reference arm (the driver compares them)."""
+    w = WORKLOADS[workload]
+    cfg = {"workload": w["desc"], "key": workload,
+           "per_gpu": "one observation (MapDataset) per GPU; joint fit over n_gpus observations",
+           "step": "one parameter vector, spectral shape parameters of all sources moved, spatial/PSF caches warm",
+           "l2": "inputs per evaluation exceed the 126 MB L2: no flush needed" if workload in ("c3", "c5-one", "c3-flat")
+                 else "L2-resident workload (secondary measurement, no flush)"}
+    if w.get("batch", 1) > 1:
+        cfg["vectors_per_launch"] = w["batch"]
+    return cfg
+
+
+def committed_traffic(workload):
+    """DRAM bytes of one launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    `ncu --set full` capture of this kernel on this workload (profiles/r02_fold_ncu_summary.txt; a run under ncu is
+    never a bench value, so the capture is a separate, committed run of the same command).  None when there is none."""
+    if workload != "c3":
+        return None, None
+    path = os.path.join(ROOT, "profiles", "r02_fold_ncu_summary.txt")
+    try:
+        total = 0.0
+        with open(path) as fh:
+            for line in fh:
+                parts = line.split()
+                if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[parts[2]]
+                    total += float(parts[1]) * scale
+        return (total or None), "profiles/r02_fold_ncu_summary.txt"
+    except OSError:
+        return None, None
 
 
 def _dbg(msg):
@@ -95,6 +133,8 @@ def build_dataset(workload, rank=0):
     kwargs = {}
     if rank > 0:  # other observations of the same field: exposure scale U(0.5, 1.5), pointing offset N(0, 0.5 deg)
         kwargs = dict(exposure_scale=float(rng.uniform(0.5, 1.5)), pointing_offset=tuple(rng.normal(0, 0.5, size=2)))
+    if "falloff" in w:
+        kwargs["falloff"] = w["falloff"]
     return configs.make_c3(name=f"obs-{rank:03d}", width=w["width"], n_sources=w["n_sources"], n_reco=w["n_reco"],
                            n_true=w["n_true"], **kwargs)
 
@@ -188,15 +228,17 @@ def cpu_evals(ds, steps, warmup, max_sources=None):
     models = list(ds.models)
     de = adapter.evaluator_for(ds, conv="fft32")
     n_src = len(de.evaluators)
+    used_all = True
     if max_sources is not None and n_src > max_sources:
         keep = list(de.evaluators)[:max_sources]
         de.evaluators = {k: de.evaluators[k] for k in keep}
+        used_all = False
     if ds.counts is None:
         de.fake(0)
     kind = "port"  # numpy restatement of the evaluator; the Cash loop is the reference's own compiled Cython
     have_ref = cash.reference_module() is not None
     for _ in range(max(warmup, 1)):  # cold evaluation fills the spatial / PSF caches like the reference
-        de.stat_sum()
+        cpu_evals.stat_at_start = de.stat_sum() if used_all else None
     t0 = time.perf_counter()
     for k in range(steps):
         for ev in de.evaluators.values():
@@ -220,6 +262,33 @@ def cpu_evals(ds, steps, warmup, max_sources=None):
     return dt, sample, kind
 
 
+def parity_check(ds, gpu_stat):
+    """The headline configuration itself against the oracle, on the same counts and parameter values: the
+    exact-arithmetic oracle npred (float64 convolution of the same float32 operands) with the Cash sum in extended
+    precision is the number the 1e-3 budget is checked against; the reference-arithmetic oracle (float32 FFT, serial
+    double Cash) carries its own ~3e-3 of rounding at this size (tests/test_gpu_headline_parity.py)."""
+    from oracle import adapter
+
+    de = adapter.evaluator_for(ds, conv="exact64")
+    npred = de.npred()
+    counts = np.asarray(ds.counts.data, dtype=float)
+    mask = de.ds.mask
+    mu = np.where(npred > 1e-25, npred, 1e-25)
+    log_mu = np.where(npred > 1e-25, np.log(mu), np.log(np.float64(np.float32(1e-25))))
+    terms = mu - np.where(counts > 0, counts * log_mu, 0.0)
+    if mask is not None:
+        terms = terms[np.asarray(mask, bool)]
+    exact = 2.0 * float(np.sum(terms.astype(np.longdouble)))
+    gpu_npred = ds.npred().data
+    rel = float(np.max(np.abs(gpu_npred - npred) / np.maximum(np.abs(npred), 1e-300)))
+    return {"stat_oracle_exact": exact, "abs_diff_exact": abs(gpu_stat - exact), "npred_max_rel_err": rel,
+            "tolerance": {"npred_rel": 1e-5, "stat_abs": 1e-3},
+            "ok": bool(rel < 1e-5 and abs(gpu_stat - exact) < 1e-3),
+            "what": "stat_gpu = Datasets.stat_sum(); stat_oracle = oracle with the reference's own arithmetic (float32-FFT "
+                    "convolution, Cython Cash); stat_oracle_exact = oracle with float64 convolution + extended-precision "
+                    "Cash sum; npred_max_rel_err = per-bin, GPU cube vs exact oracle cube; full workload, same counts"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -234,7 +303,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload]["desc"], "key": args.workload},
+        "config": config_for(args.workload),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle restatement of gammapy's arithmetic without astropy Quantity/Map overhead: a lower bound on "
@@ -456,6 +525,100 @@ def run_c4(args):
 # ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
+def timed_blocks(step, steps, blocks, stream, distributed, device):
+    """`blocks` back-to-back blocks of exactly `steps` steps, each bracketed by CUDA events on the library's stream
+    (+ barrier and device synchronize on both sides of the whole series); returns the per-block milliseconds (max
+    over ranks per block) and the wall-clock seconds of the series.  The reported step time is the MEDIAN block:
+    with the driver's `--steps 20` one block is a 6 ms region, which a single stray host stall can double."""
+    import torch
+    import torch.distributed as dist
+
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(blocks)]
+    k = 0
+    t_wall = time.perf_counter()
+    for e0, e1 in evs:
+        e0.record(stream)
+        for _ in range(steps):
+            step(k)
+            k += 1
+        e1.record(stream)
+    stream.synchronize()
+    wall = time.perf_counter() - t_wall
+    ms = torch.tensor([e0.elapsed_time(e1) for e0, e1 in evs], dtype=torch.float64, device=device)
+    if distributed:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return [float(x) for x in ms.tolist()], wall
+
+
+def c4_large_extras(world, rank, steps=40):
+    """BASELINE.json configs[3] inside the default run: the 64-observation joint fit (c4-large geometry) sharded over
+    the ranks, strong scaling -- joint evaluations/s at this N, so that the driver's N = 1, 2, 4, 8 records hold the
+    strong-scaling series (the headline `value` stays one C3 observation per GPU, weak scaling)."""
+    import torch
+    import torch.distributed as dist
+
+    from gammapy_b200 import configs
+    from gammapy_b200.distributed import ShardedDatasets, allreduce_stat, partition
+
+    w = WORKLOADS["c4-large"]
+    n_obs = w["n_obs"]
+    distributed = world > 1
+    mine = partition([1] * n_obs, world)[rank]
+    datasets, models = configs.make_c4(n_obs=n_obs, indices=mine, return_models=True, **w["geometry"])
+    for i, ds in zip(mine, datasets):
+        ds.fake(random_state=100 + i)
+    sharded = ShardedDatasets(datasets, global_models=models)
+    engine = sharded._local_engine()
+    ctx, stream = engine.ctx, engine.ctx.stream
+    base = engine.values()
+    col = [i for i, p in enumerate(engine.parameters) if p.name == "index"][0]
+    D = len(engine.datasets)
+    buf = torch.zeros(1, D, dtype=torch.float64, device=ctx.torch_device)
+
+    def step(k):
+        v = base.copy()
+        v[col] += 1e-3 if k % 2 == 0 else -1e-3
+        engine.stat_sum_device(v, buf)
+        if distributed:
+            with torch.cuda.stream(stream):
+                total = buf.sum(dim=1)
+            allreduce_stat(total, stream)
+
+    for k in range(5):
+        step(k)
+    stream.synchronize()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms, _ = timed_blocks(step, steps, 3, stream, distributed, ctx.torch_device)
+    ms_per_eval = float(np.median(ms)) / steps
+    # end to end: Parameter objects -> joint stat_sum() (H2D descriptors, kernels, all-reduce, D2H)
+    par = engine.parameters[col]
+    v0 = par.value
+    for k in range(3):
+        sharded.stat_sum()
+    if distributed:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        par.value = v0 + (1e-3 if k % 2 == 0 else -1e-3)
+        sharded.stat_sum()
+    e2e_s = (time.perf_counter() - t0) / steps
+    par.value = v0
+    if distributed:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=ctx.torch_device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    alg = sum(algorithmic_bytes(ds) for ds in datasets)
+    out = {"workload": w["desc"], "scaling": "strong", "observations": n_obs, "observations_on_rank0": len(mine),
+           "ms_per_joint_eval": ms_per_eval, "joint_evals_per_s": 1e3 / ms_per_eval,
+           "dataset_evals_per_s": n_obs * 1e3 / ms_per_eval, "e2e_ms_per_joint_eval": e2e_s * 1e3,
+           "rank0_GBps_algorithmic": alg / (ms_per_eval * 1e-3) / 1e9, "steps": steps, "blocks_ms": ms}
+    del sharded, datasets
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     if args.workload.startswith("c4"):
         return run_c4(args)
@@ -471,6 +634,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     steps = args.steps or 1000
     warmup = 5 if args.warmup is None else max(args.warmup, 3)
+    blocks = 5
 
     from gammapy_b200 import Datasets, Map
     from gammapy_b200.distributed import ShardedDatasets, allreduce_stat
@@ -515,21 +679,14 @@ def run_ours(args):
     torch.cuda.synchronize()
     _dbg("warm-up done")
     launches0 = ctx.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
-        t_wall = time.perf_counter()
-        ev0.record(stream)
-        for k in range(steps):
-            step_device(k)
-        ev1.record(stream)
-        stream.synchronize()
-        timed_wall = time.perf_counter() - t_wall
-        # nvidia-smi samples every 50 ms: when the timed region is shorter than ~0.4 s keep the very same loop
-        # running (untimed) under the sampler so that the clocks line describes this workload under load
-        # every rank must run the SAME number of extra steps (each step holds a collective): the count comes from
-        # the slowest rank's timed region
-        extra = extra_steps(timed_wall, steps, distributed, ctx.torch_device)
-        for k in range(steps, steps + extra):
+        block_ms, timed_wall = timed_blocks(step_device, steps, blocks, stream, distributed, ctx.torch_device)
+        launches = (ctx.launch_count - launches0) // blocks
+        # nvidia-smi samples every 50 ms: when the timed series is shorter than ~0.4 s keep the very same loop
+        # running (untimed) under the sampler so that the clocks line describes this workload under load; every
+        # rank must run the SAME number of extra steps (each step holds a collective)
+        extra = extra_steps(timed_wall, steps * blocks, distributed, ctx.torch_device)
+        for k in range(extra):
             step_device(k)
             if k % 16 == 0:
                 stream.synchronize()
@@ -538,12 +695,7 @@ def run_ours(args):
     if distributed:
         dist.barrier()
     _dbg("timed loop done")
-    ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count - launches0
-    if distributed:
-        t = torch.tensor([ms], dtype=torch.float64, device=ctx.torch_device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = float(np.median(block_ms))
     ms_per_step = ms / steps
     value = world * batch * 1e3 / ms_per_step  # dataset evaluations (parameter vectors) per second, all ranks
 
@@ -552,7 +704,7 @@ def run_ours(args):
     alg_bytes = algorithmic_bytes(ds)
     peak, peak_src = measured_peak()
     ctx.kernel_timing(True)
-    for k in range(steps):
+    for k in range(max(steps, 50)):
         step_device(k)
     kernel_ms, kernel_launches = ctx.kernel_time()
     ctx.kernel_timing(False)
@@ -564,23 +716,27 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         kernel_us = float(t.item())
     achieved = alg_bytes / (kernel_us * 1e-6) / 1e9
-    # DRAM bytes of one launch from the committed ncu --set full capture of this kernel on this workload
-    traffic = 642.4e6 if args.workload == "c3" else None  # 637.7 MB read + 4.7 MB written
+    traffic, traffic_src = committed_traffic(args.workload)
 
-    # end to end through the public API: Parameter objects -> Datasets.stat_sum() -> python float
+    # end to end through the public API: Parameter objects -> Datasets.stat_sum() -> python float.  The very call
+    # that is timed is warmed up first (at N > 1 that is ShardedDatasets.stat_sum: its device / pinned buffers).
     pars = [engine.parameters[c] for c in cols]
     vals = [p.value for p in pars]
-    for k in range(3):
-        datasets.stat_sum()
+    api = sharded if distributed else datasets
+    for k in range(5):
+        api.stat_sum()
     if distributed:
         dist.barrier()
-    t0 = time.perf_counter()
-    for k in range(steps):
-        d = 1e-3 if k % 2 == 0 else -1e-3
-        for p, v in zip(pars, vals):
-            p.value = v + d
-        s = sharded.stat_sum() if distributed else datasets.stat_sum()
-    e2e_s = (time.perf_counter() - t0) / steps
+    e2e_blocks = []
+    for _ in range(blocks):
+        t0 = time.perf_counter()
+        for k in range(steps):
+            d = 1e-3 if k % 2 == 0 else -1e-3
+            for p, v in zip(pars, vals):
+                p.value = v + d
+            s = api.stat_sum()
+        e2e_blocks.append((time.perf_counter() - t0) / steps)
+    e2e_s = float(np.median(e2e_blocks))
     _dbg("e2e loop done")
     for p, v in zip(pars, vals):
         p.value = v
@@ -590,27 +746,27 @@ def run_ours(args):
         e2e_s = float(t.item())
     h2d_bytes = int(engine.n_par * 8 + 64 * (len(ds._source_names) + 4) + 80 * len(ds._source_names))
     e2e = {"value": world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
-           "ms_per_step": e2e_s * 1e3,
+           "ms_per_step": e2e_s * 1e3, "blocks_ms_per_step": [x * 1e3 for x in e2e_blocks],
            "what": "Datasets.stat_sum() with Parameter objects on the host: parameter vector + descriptor block copied "
                    "H2D from pinned memory, Cash sum copied D2H, every step; the cubes are dataset state resident in "
-                   "HBM exactly as the reference keeps them in host RAM between Minuit steps"}
+                   "HBM exactly as the reference keeps them in host RAM between Minuit steps; median of "
+                   f"{blocks} blocks of {steps} steps"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload]["desc"], "key": args.workload,
-                   "per_gpu": "one observation (MapDataset) per GPU; joint fit over n_gpus observations",
-                   "l2": (f"inputs per evaluation ({algorithmic_bytes(ds) / 1e6:.0f} MB) exceed the 126 MB L2: no flush needed"
-                          if algorithmic_bytes(ds) > 2 * 126e6 else "L2-resident workload (secondary measurement, no flush)"),
-                   "step": "one parameter vector, spectral shape parameters of all sources moved, spatial/PSF caches warm"},
+        "config": config_for(args.workload),
+        "timing": {"blocks": blocks, "block_ms": block_ms, "reported": "median block / steps",
+                   "note": f"{blocks} back-to-back blocks of exactly {steps} steps, each bracketed by CUDA events on the "
+                           "library's stream, max over ranks per block"},
         "gpu_launches": int(launches),
         "clocks": dict(clocks.summary(), timed_region_s=timed_wall,
-                       note="sampled over the timed loop and, if shorter than 0.4 s, its untimed continuation"),
+                       note="sampled over the timed blocks and, if shorter than 0.4 s, their untimed continuation"),
         "e2e": e2e,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, "
-                                                         "profiles/r01_fold_final_ncu_summary.txt)",
+                     "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum "
+                                                         f"of the committed capture {traffic_src})",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "kernel": "fold_cash_tma_kernel", "duration_us": kernel_us, "launches_timed": int(kernel_launches),
                      "step_us": ms_per_step * 1e3,
@@ -618,14 +774,16 @@ def run_ours(args):
                              "stream around that launch during a repeat of the timed steps; step_us = whole step "
                              "(K0 + fold + reduce; the work descriptors are reused while no cutout changes), the "
                              "value above; the kernel's share of the step agrees with the ncu launch list "
-                             "(profiles/r01_launches_final_summary.txt)"},
+                             "(profiles/r02_launches_summary.txt)"},
         "setup_s": t_build,
     }
-    if batch > 1:
-        line["config"]["vectors_per_launch"] = batch
-        line["e2e"]["value"] *= 1  # the public-API loop above evaluates one vector per call
     if rank == 0 and not args.no_extras and not distributed and args.workload.startswith("c3"):
         line["extras"] = extras(engine, datasets, ds, base, cols)
+        line["extras"]["fraction_of_bins_with_counts"] = float((ds.counts.data > 0).mean())
+        try:
+            line["extras"]["c3_flat"] = c3_flat_extras()
+        except Exception as exc:
+            line["extras"]["c3_flat"] = {"error": repr(exc)}
         try:
             line["extras"]["fit"] = fit_wall_time(with_cpu=not args.no_cpu_baseline)
         except Exception as exc:
@@ -636,15 +794,32 @@ def run_ours(args):
             line["extras"]["ts_map"] = {"error": repr(exc)}
     if rank == 0 and not args.no_cpu_baseline and not distributed:
         try:
+            # parity of the headline configuration itself: the oracle (reference arithmetic: float32-FFT convolution,
+            # reference Cython Cash) on the same counts and parameter values as the GPU
+            gpu_stat = datasets.stat_sum()
             dt, sample, kind = cpu_evals(ds, steps=3, warmup=1)
             line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
                                     "sample": sample,
                                     "ms_per_eval_one_source_moved": 1e3 * getattr(cpu_evals, "one_source_moved_s", float("nan")),
                                     "note": "single Python thread (the reference's N_JOBS_DEFAULT = 1); numpy's BLAS "
                                             "may use more cores inside the edisp matmul"}
+            oracle_stat = getattr(cpu_evals, "stat_at_start", None)
+            if oracle_stat is not None:
+                line["parity"] = dict(parity_check(ds, gpu_stat), stat_gpu=gpu_stat, stat_oracle=oracle_stat,
+                                      abs_diff=abs(gpu_stat - oracle_stat))
         except Exception as exc:  # never lose the GPU numbers to the checker
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {exc}"}
+    # BASELINE.json configs[3] at this N (every rank takes part)
+    if not args.no_extras and args.workload == "c3":
+        del datasets, engine, sharded, api
+        ds = None
+        torch.cuda.empty_cache()
+        try:
+            c4 = c4_large_extras(world, rank)
+        except Exception as exc:
+            c4 = {"error": repr(exc)}
+        line.setdefault("extras", {})["c4_large"] = c4
     if rank == 0:
         print(json.dumps(line))
     if distributed:
@@ -710,6 +885,46 @@ def extras(engine, datasets, ds, base, cols):
     engine.stat_sum_device(grid, sd)  # builds the PSF-convolved cubes of the displaced positions once
     ms = timed(lambda k: engine.stat_sum_device(grid, sd), 3)
     out["fd_gradient"] = {"parameters": len(gcols), "vectors_per_launch": int(grid.shape[0]), "ms_per_gradient": ms}
+    return out
+
+
+def c3_flat_extras(steps=100):
+    """The C3 shape with dense counts (`c3-flat`): whole step and fold kernel alone, same measurement as the headline."""
+    import torch
+
+    from gammapy_b200 import Datasets
+
+    ds = build_dataset("c3-flat")
+    datasets = Datasets([ds])
+    ds.fake(random_state=2)
+    engine = datasets._get_engine()
+    ctx, stream = engine.ctx, engine.ctx.stream
+    base = engine.values()
+    cols = spectral_columns(engine)
+    stat_dev = torch.zeros(1, 1, dtype=torch.float64, device=ctx.torch_device)
+
+    def step(k):
+        v = base.copy()
+        v[cols] += 1e-3 if k % 2 == 0 else -1e-3
+        engine.stat_sum_device(v, stat_dev)
+
+    for k in range(5):
+        step(k)
+    stream.synchronize()
+    ms, _ = timed_blocks(step, steps, 3, stream, False, ctx.torch_device)
+    ctx.kernel_timing(True)
+    for k in range(steps):
+        step(k)
+    kernel_ms, n = ctx.kernel_time()
+    ctx.kernel_timing(False)
+    kernel_us = 1e3 * kernel_ms / max(n, 1)
+    peak, _ = measured_peak()
+    counts = ds.counts.data
+    out = {"workload": WORKLOADS["c3-flat"]["desc"], "ms_per_step": float(np.median(ms)) / steps, "fold_kernel_us": kernel_us,
+           "roofline_frac": algorithmic_bytes(ds) / (kernel_us * 1e-6) / 1e9 / peak,
+           "fraction_of_bins_with_counts": float((counts > 0).mean())}
+    del datasets, engine, ds
+    torch.cuda.empty_cache()
     return out
 
 
