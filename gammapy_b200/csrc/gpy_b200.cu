@@ -277,6 +277,36 @@ struct gpy_context {
   int fold_mode = 0;  // GPY_FOLD_KERNEL: 0 auto (bulk-copy staged kernel when eligible), 2 generic
   double log_trunc = 0.0;
   int max_smem_optin = 0;
+  // ---- steady-state replay (evaluate_replay): the step of a fit whose spatial parameters did not move -------------
+  struct Replay {
+    bool valid = false;
+    bool disabled = false;             // GPY_NO_REPLAY
+    std::vector<gpy_dataset*> datasets;
+    std::vector<uint64_t> versions;
+    int n_par = 0, include_background = 0;
+    std::vector<int> spatial_cols;     // parameter columns whose values the cached work depends on ...
+    std::vector<double> spatial_vals;  // ... and their values at capture time (bitwise)
+    std::vector<int> amp_cols;         // amplitude columns: a source leaves the list when its amplitude is exactly 0
+    std::vector<uint8_t> amp_zero;
+    cudaGraphExec_t exec = nullptr;    // built at the first replay after a capture (a step that moves a source never pays)
+    bool exec_valid = false;
+    // launch parameters of the captured step
+    unsigned k0_blocks = 0, k0_threads = 0;
+    int k0_seg_cap = 0;
+    const gpy::FluxJob* k0_jobs = nullptr;
+    void (*fold_kernel)(const gpy::FoldParams) = nullptr;
+    unsigned fold_grid = 0;
+    size_t fold_smem = 0;
+    gpy::FoldParams fold_params;
+    int n_tiles = 0;
+    int kernels = 0;                   // kernel launches inside the graph
+    DevBuf d_params;
+    double* pinned = nullptr;          // ring of parameter vectors
+    std::vector<cudaEvent_t> slot_done;
+    int slot = 0;
+    size_t pinned_doubles = 0;
+    int64_t replays = 0;
+  } replay;
 };
 
 struct gpy_dataset {
@@ -656,9 +686,88 @@ int timing_collect(gpy_context* c) {  // adds the bracketed kernel of the previo
 
 // Build descriptors, refresh spatial caches, launch K0 + fused fold/Cash + reduction.
 // Leaves stat[b * D + d] in c->stat (device).
+constexpr int kReplaySlots = 32;
+
+// Steady-state step of a fit: same datasets, one parameter vector, no spatial parameter moved and no amplitude
+// crossing zero since the captured call.  Then nothing the host packs changes but the spectral / background values,
+// which K0 reads from the parameter vector itself (FluxJob::pidx): the step is one small H2D copy plus the replay of a
+// CUDA graph holding K0, the work-counter reset, the fold kernel and the reduction.  Returns true when it ran.
+int evaluate_replay(gpy_context* c, const EvalRequest& rq, bool* done) {
+  *done = false;
+  gpy_context::Replay& R = c->replay;
+  if (!R.valid || R.disabled || c->timing || rq.n_vec != 1 || rq.npred_out || rq.source_enable ||
+      rq.n_datasets != (int)R.datasets.size() || rq.n_par != R.n_par || rq.include_background != R.include_background)
+    return GPY_OK;
+  for (int d = 0; d < rq.n_datasets; ++d)
+    if (rq.datasets[d] != R.datasets[d] || rq.datasets[d]->version != R.versions[d]) return GPY_OK;
+  for (size_t i = 0; i < R.spatial_cols.size(); ++i)
+    if (std::memcmp(&rq.params[R.spatial_cols[i]], &R.spatial_vals[i], sizeof(double)) != 0) return GPY_OK;
+  for (size_t i = 0; i < R.amp_cols.size(); ++i)
+    if ((rq.params[R.amp_cols[i]] == 0.0) != (R.amp_zero[i] != 0)) return GPY_OK;
+  if (!R.exec_valid) {  // second step in a row with the same spatial parameters: worth a graph
+    if (R.exec) {
+      cudaGraphExecDestroy(R.exec);
+      R.exec = nullptr;
+    }
+    cudaGraph_t graph = nullptr;
+    const int D = rq.n_datasets;
+    CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    R.kernels = 0;
+    if (R.k0_blocks) {
+      gpy::spectral_flux_kernel<<<R.k0_blocks, R.k0_threads, (size_t)R.k0_seg_cap * sizeof(double), c->stream>>>(
+          R.k0_jobs, R.k0_seg_cap, (const double*)R.d_params.p);
+      R.kernels++;
+    }
+    if (R.fold_params.counter) cudaMemsetAsync(R.fold_params.counter, 0, sizeof(unsigned), c->stream);
+    R.fold_kernel<<<R.fold_grid, gpy::kFoldThreads, R.fold_smem, c->stream>>>(R.fold_params);
+    gpy::reduce_stat_kernel<<<dim3(1, D), 256, 0, c->stream>>>((const double*)c->partials.p, R.fold_params.ds, R.n_tiles, D, 1,
+                                                              nullptr, (double*)c->stat.p);
+    R.kernels += 2;
+    cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+    if (ce != cudaSuccess || !graph) {
+      (void)cudaGetLastError();
+      R.valid = false;  // capture not possible here (e.g. the caller is itself capturing): ordinary path
+      return GPY_OK;
+    }
+    ce = cudaGraphInstantiate(&R.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+      (void)cudaGetLastError();
+      R.exec = nullptr;
+      R.valid = false;
+      return GPY_OK;
+    }
+    R.exec_valid = true;
+  }
+  const int slot = R.slot;
+  R.slot = (R.slot + 1) % kReplaySlots;
+  CUDA_TRY(cudaEventSynchronize(R.slot_done[slot]));  // the copy that last used this slot (32 calls ago) has run
+  double* host = R.pinned + (size_t)slot * R.pinned_doubles;
+  std::memcpy(host, rq.params, (size_t)rq.n_par * sizeof(double));
+  CUDA_TRY(cudaMemcpyAsync(R.d_params.p, host, (size_t)rq.n_par * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaEventRecord(R.slot_done[slot], c->stream));
+  CUDA_TRY(cudaGraphLaunch(R.exec, c->stream));
+  c->launches += R.kernels;
+  R.replays++;
+  *done = true;
+  return GPY_OK;
+}
+
 int evaluate(gpy_context* c, const EvalRequest& rq) {
   const int D = rq.n_datasets, B = rq.n_vec;
   if (D <= 0 || B <= 0) return fail(GPY_ERR_INVALID, "need at least one dataset and one parameter vector");
+  {
+    bool done = false;
+    GPY_TRY(evaluate_replay(c, rq, &done));
+    if (done) return GPY_OK;
+    c->replay.valid = false;  // whatever follows may move buffers the captured graph points into
+  }
+  unsigned k0_blocks = 0, k0_threads = 0;
+  int k0_seg_cap = 0;
+  const gpy::FluxJob* k0_jobs = nullptr;
+  std::vector<int> replay_spatial_cols, replay_amp_cols;
+  void (*replay_kernel)(const gpy::FoldParams) = nullptr;
+  unsigned replay_grid = 0;
   if (c->h2d_pending) {
     CUDA_TRY(cudaEventSynchronize(c->h2d_done));
     c->h2d_pending = false;
@@ -741,6 +850,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         for (int k = 0; k < nsp; ++k) {
           GPY_TRY(check_par(src.desc.spatial_par[k], rq.n_par, "a spatial parameter"));
           sp[k] = pv[src.desc.spatial_par[k]];
+          if (b == 0) replay_spatial_cols.push_back(src.desc.spatial_par[k]);
         }
         for (int k = 0; k < nsc; ++k) {
           GPY_TRY(check_par(src.desc.spectral_par[k], rq.n_par, "a spectral parameter"));
@@ -790,6 +900,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         if (rq.source_enable && !rq.source_enable[si]) continue;
         // _compute_npred: amplitude == 0 -> zeros (evaluator.py:385-389)
         const int amp_idx = src.desc.spectral_type == GPY_SPECTRAL_LP ? 0 : 1;
+        if (b == 0 && !(rq.source_enable && !rq.source_enable[si])) replay_amp_cols.push_back(src.desc.spectral_par[amp_idx]);
         if (sc[amp_idx] == 0.0) continue;
         Slot* slot = nullptr;
         GPY_TRY(get_slot(ds, src, sp, rect, call_id, &slot));
@@ -824,6 +935,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
           job.n_nodes = ds->n_nodes;
           job.sanitize = 1;
           for (int k = 0; k < 5; ++k) job.p[k] = sc[k];
+          for (int k = 0; k < 5; ++k) job.pidx[k] = k < nsc ? src.desc.spectral_par[k] : -1;
           job.edges = (const double*)ds->d_edges.p;
           job.nodes = (const double*)ds->d_nodes.p;
           jobs.push_back(job);
@@ -935,6 +1047,12 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       job.p[0] = ev.bkg_norm;
       job.p[1] = ev.bkg_tilt;
       job.p[2] = ev.bkg_ref;
+      for (int k = 0; k < 5; ++k) job.pidx[k] = -1;
+      if (ev.bkg_enabled) {
+        job.pidx[0] = rq.datasets[d]->bkg.par_norm;
+        job.pidx[1] = rq.datasets[d]->bkg.par_tilt;
+        job.pidx[2] = rq.datasets[d]->bkg.par_reference;
+      }
       job.edges = (const double*)rq.datasets[d]->d_ecenter.p;
       jobs.push_back(job);
       job_flux_off.push_back(flux_len);
@@ -966,8 +1084,12 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       if (j.type != 0 && j.type != gpy::kFluxJobBackground) seg_cap = std::max(seg_cap, j.n_bins * (2 * j.n_nodes - 1));
     seg_cap = std::min(seg_cap, 5120);  // 40 KB
     gpy::spectral_flux_kernel<<<(unsigned)jobs.size(), seg_cap ? 256 : 64, (size_t)seg_cap * sizeof(double),
-                                c->stream>>>((const gpy::FluxJob*)(base + off_jb), seg_cap);
+                                c->stream>>>((const gpy::FluxJob*)(base + off_jb), seg_cap, nullptr);
     c->launches++;
+    k0_blocks = (unsigned)jobs.size();
+    k0_threads = seg_cap ? 256 : 64;
+    k0_seg_cap = seg_cap;
+    k0_jobs = (const gpy::FluxJob*)(base + off_jb);
   }
   gpy::FoldParams fp;
   std::memset(&fp, 0, sizeof(fp));
@@ -1105,6 +1227,8 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       CUDA_TRY(cudaEventRecord(c->t_begin, c->stream));
     }
     kern<<<grid, gpy::kFoldThreads, lay.total, c->stream>>>(fp);
+    replay_kernel = kern;
+    replay_grid = grid;
     if (c->timing) {
       CUDA_TRY(cudaEventRecord(c->t_end, c->stream));
       c->timing_pending = true;
@@ -1126,6 +1250,43 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     c->launches++;
   }
   CUDA_TRY(cudaGetLastError());
+  // Remember what this step launched: if the next call only moves spectral / background parameters it is replayed.
+  gpy_context::Replay& R = c->replay;
+  if (tma_ok && replay_kernel && B == 1 && !rq.npred_out && !rq.source_enable && !R.disabled && !c->timing) {
+    R.datasets.assign(rq.datasets, rq.datasets + D);
+    R.versions.resize(D);
+    for (int d = 0; d < D; ++d) R.versions[d] = rq.datasets[d]->version;
+    R.n_par = rq.n_par;
+    R.include_background = rq.include_background;
+    R.spatial_cols.swap(replay_spatial_cols);
+    R.spatial_vals.resize(R.spatial_cols.size());
+    for (size_t i = 0; i < R.spatial_cols.size(); ++i) R.spatial_vals[i] = rq.params[R.spatial_cols[i]];
+    R.amp_cols.swap(replay_amp_cols);
+    R.amp_zero.resize(R.amp_cols.size());
+    for (size_t i = 0; i < R.amp_cols.size(); ++i) R.amp_zero[i] = rq.params[R.amp_cols[i]] == 0.0;
+    R.k0_blocks = k0_blocks;
+    R.k0_threads = k0_threads;
+    R.k0_seg_cap = k0_seg_cap;
+    R.k0_jobs = k0_jobs;
+    R.fold_kernel = replay_kernel;
+    R.fold_grid = replay_grid;
+    R.fold_smem = lay.total;
+    R.fold_params = fp;
+    R.n_tiles = n_tiles;
+    R.exec_valid = false;
+    if ((size_t)rq.n_par > R.pinned_doubles || !R.pinned) {
+      if (R.pinned) cudaFreeHost(R.pinned);
+      R.pinned = nullptr;
+      R.pinned_doubles = std::max((size_t)rq.n_par, (size_t)64);
+      CUDA_TRY(cudaMallocHost((void**)&R.pinned, R.pinned_doubles * kReplaySlots * sizeof(double)));
+    }
+    if (R.slot_done.empty()) {
+      R.slot_done.resize(kReplaySlots);
+      for (auto& e : R.slot_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    GPY_TRY(R.d_params.reserve(R.pinned_doubles * sizeof(double)));
+    R.valid = true;
+  }
   return GPY_OK;
 }
 
@@ -1168,6 +1329,7 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
   c->no_dedup = std::getenv("GPY_NO_DEDUP") != nullptr;
   c->static_schedule = std::getenv("GPY_STATIC_SCHEDULE") != nullptr;
   c->no_desc_cache = std::getenv("GPY_NO_DESC_CACHE") != nullptr;
+  c->replay.disabled = std::getenv("GPY_NO_REPLAY") != nullptr;
   if (const char* m = std::getenv("GPY_FOLD_KERNEL")) c->fold_mode = std::atoi(m);
   if (c->fold_mode == 2) c->force_generic = true;
   {
@@ -1219,6 +1381,10 @@ int gpy_finalize(gpy_context_t* c) {
   for (DevBuf* b : {&c->zeros, &c->desc, &c->dedup, &c->staging, &c->flux, &c->partials, &c->stat, &c->tiles, &c->scratch_a, &c->scratch_b, &c->scratch_c})
     b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->replay.exec) cudaGraphExecDestroy(c->replay.exec);
+  if (c->replay.pinned) cudaFreeHost(c->replay.pinned);
+  for (cudaEvent_t e : c->replay.slot_done) cudaEventDestroy(e);
+  c->replay.d_params.release();
   if (c->stat_pinned) cudaFreeHost(c->stat_pinned);
   if (c->nwork_pinned) cudaFreeHost(c->nwork_pinned);
   if (c->h2d_done) cudaEventDestroy(c->h2d_done);
@@ -1725,6 +1891,7 @@ int gpy_spectral_integral(gpy_context_t* c, int32_t spectral_type, const double*
   job.n_bins = n_bins;
   job.n_nodes = n_nodes;
   for (int k = 0; k < n_spectral_params(spectral_type); ++k) job.p[k] = sp[k];
+  for (int k = 0; k < 5; ++k) job.pidx[k] = -1;
   job.edges = d_edges;
   job.nodes = d_nodes;
   job.out = d_out;
@@ -1732,7 +1899,7 @@ int gpy_spectral_integral(gpy_context_t* c, int32_t spectral_type, const double*
   if (nn) CUDA_TRY(cudaMemcpyAsync(d_nodes, nodes, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(d_job, &job, sizeof(job), cudaMemcpyHostToDevice, c->stream));
   const int seg_cap = spectral_type == GPY_SPECTRAL_PL ? 0 : std::min(n_bins * std::max(2 * n_nodes - 1, 0), 5120);
-  gpy::spectral_flux_kernel<<<1, seg_cap ? 256 : 64, (size_t)seg_cap * sizeof(double), c->stream>>>(d_job, seg_cap);
+  gpy::spectral_flux_kernel<<<1, seg_cap ? 256 : 64, (size_t)seg_cap * sizeof(double), c->stream>>>(d_job, seg_cap, nullptr);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(out, d_out, n_bins * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

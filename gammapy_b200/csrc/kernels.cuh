@@ -304,6 +304,8 @@ struct FluxJob {
   int n_bins;
   int n_nodes;
   int sanitize;         // 1: zero the vector when any bin is non-finite (likelihood path), 0: raw integrals
+  int pidx[5];          // columns of p[] in the caller's parameter vector (steady-state replay reads them from there)
+  int pad_;
   double p[5];          // parameter values in the reference class order
   const double* edges;  // [n_bins + 1]
   const double* nodes;  // [n_bins, n_nodes]
@@ -347,9 +349,16 @@ __device__ __forceinline__ double log_scale(double v) {
 // its integral to shared memory, then one thread per bin adds its segments in node order (bit-identical to the
 // serial per-bin loop below, which remains the fallback when the segments do not fit).  seg_cap = doubles of
 // dynamic shared memory.
-__global__ void spectral_flux_kernel(const FluxJob* __restrict__ jobs, int seg_cap) {
+// params: null, or the caller's parameter vector on the device: the job's values are then read from it (pidx), so a
+// replayed launch (CUDA graph of the steady-state step, see evaluate_replay) only needs the new vector.
+__global__ void spectral_flux_kernel(const FluxJob* __restrict__ jobs, int seg_cap, const double* __restrict__ params) {
   extern __shared__ double seg[];
-  const FluxJob job = jobs[blockIdx.x];
+  FluxJob job = jobs[blockIdx.x];
+  if (params) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      if (job.pidx[k] >= 0) job.p[k] = params[job.pidx[k]];
+  }
   if (job.type == kFluxJobBackground) {
     // background factors norm * (E_c / E_0)^-tilt per reco bin (PowerLawNormSpectralModel.evaluate,
     // spectral.py:1159-1162; FoVBackgroundModel.evaluate_geom, cube.py:737-756): p = {norm, tilt, reference},

@@ -694,3 +694,43 @@ def test_more_sources_than_a_descriptor_holds(ctx):
     stat, want, npred, npred_want = _stat_pair(ds, seed=9)
     assert_allclose(npred, npred_want, rtol=1e-5, atol=1e-12 * npred_want.max())
     assert abs(stat - want) < 1e-3
+
+
+def test_steady_state_replay_matches_the_oracle_and_the_batched_path(ctx):
+    """A run of single-vector calls that only move spectral / background parameters is replayed from a CUDA graph
+    (K0 reads the parameter vector on the device): every value equals the batched evaluation of the same vectors bit
+    for bit and the oracle within tolerance; a spatial move in between falls back to the full path and back."""
+    from gammapy_b200 import Datasets, Map, configs
+    from oracle import adapter
+
+    ds = configs.make_c2()
+    de = adapter.evaluator_for(ds, conv="exact64")
+    ds.counts = Map.from_geom(ds._geom, data=de.fake(7), dtype=float)
+    datasets = Datasets([ds])
+    values, plist = datasets.parameter_vector()
+    names = [p.name for p in plist]
+    i_index, i_norm, i_amp = names.index("index"), names.index("norm"), names.index("amplitude")
+    grid = np.tile(values, (6, 1))
+    grid[1:, i_index] += [0.05, -0.07, 0.11, 0.02, -0.03]
+    grid[2:, i_norm] *= [1.02, 0.97, 1.05, 1.01]
+    grid[4, i_amp] = 0.0           # a source drops out: not replayable, full path
+    batch = datasets.stat_sum_batch(grid)
+    launches = []
+    for k in range(6):
+        for p, v in zip(plist, grid[k]):
+            p.value = v
+        before = ctx.launch_count
+        got = datasets.stat_sum()
+        launches.append(ctx.launch_count - before)
+        assert got == batch[k], k
+        adapter.refresh_models(de, ds)
+        assert abs(got - de.stat_sum()) < 1e-3, k
+    assert launches[2] == 3 and launches[3] == 3   # K0 + fold + reduce, replayed
+    plist[names.index("lon_0")].value += 0.013      # a position moves: spatial model + PSF stencil run again
+    adapter.refresh_models(de, ds)
+    assert abs(datasets.stat_sum() - de.stat_sum()) < 1e-3
+    plist[i_index].value += 0.01
+    adapter.refresh_models(de, ds)
+    assert abs(datasets.stat_sum() - de.stat_sum()) < 1e-3
+    for p, v in zip(plist, values):
+        p.value = v
