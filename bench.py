@@ -405,11 +405,10 @@ def run_c4(args):
     def step_device(k):
         v = base.copy()
         v[col] += 1e-3 if k % 2 == 0 else -1e-3
-        engine.stat_sum_device(v, buf)
         if distributed:
-            with torch.cuda.stream(stream):
-                total = buf.sum(dim=1)
-            allreduce_stat(total, stream)
+            sharded.joint_stat_device(v, buf)
+        else:
+            engine.stat_sum_device(v, buf)
 
     for k in range(warmup):
         step_device(k)
@@ -578,11 +577,10 @@ def c4_large_extras(world, rank, steps=40):
     def step(k):
         v = base.copy()
         v[col] += 1e-3 if k % 2 == 0 else -1e-3
-        engine.stat_sum_device(v, buf)
         if distributed:
-            with torch.cuda.stream(stream):
-                total = buf.sum(dim=1)
-            allreduce_stat(total, stream)
+            sharded.joint_stat_device(v, buf)
+        else:
+            engine.stat_sum_device(v, buf)
 
     for k in range(5):
         step(k)
@@ -666,9 +664,10 @@ def run_ours(args):
     stream = ctx.stream
 
     def step_device(k):
-        engine.stat_sum_device(vector(k), stat_dev)
-        if distributed:
-            allreduce_stat(stat_dev, stream)
+        if distributed:  # this rank's observation + the all-reduce of the joint statistic (NVLink one-shot, else NCCL)
+            sharded.joint_stat_device(vector(k), stat_dev)
+        else:
+            engine.stat_sum_device(vector(k), stat_dev)
 
     _dbg("setup done")
     for k in range(warmup):
@@ -761,6 +760,9 @@ def run_ours(args):
                    "note": f"{blocks} back-to-back blocks of exactly {steps} steps, each bracketed by CUDA events on the "
                            "library's stream, max over ranks per block"},
         "gpu_launches": int(launches),
+        "collective": (None if not distributed else
+                       "one-shot all-reduce over NVLink peer memory inside the library's last kernel (gpy_stat_sum_joint_device)"
+                       if getattr(sharded, "_peer", None) else "ncclAllReduce of the joint statistic (torch.distributed), 8 bytes per step"),
         "clocks": dict(clocks.summary(), timed_region_s=timed_wall,
                        note="sampled over the timed blocks and, if shorter than 0.4 s, their untimed continuation"),
         "e2e": e2e,

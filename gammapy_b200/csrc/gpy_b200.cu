@@ -277,6 +277,10 @@ struct gpy_context {
   int fold_mode = 0;  // GPY_FOLD_KERNEL: 0 auto (bulk-copy staged kernel when eligible), 2 generic
   double log_trunc = 0.0;
   int max_smem_optin = 0;
+  // ---- joint fits over ranks: one-shot all-reduce over NVLink peer memory (gpy_peer_reduce_init) ------------------
+  gpy::PeerReduceParams peer{};
+  bool peer_on = false;
+  DevBuf peer_seq;
   // ---- steady-state replay (evaluate_replay): the step of a fit whose spatial parameters did not move -------------
   struct Replay {
     bool valid = false;
@@ -284,6 +288,7 @@ struct gpy_context {
     std::vector<gpy_dataset*> datasets;
     std::vector<uint64_t> versions;
     int n_par = 0, include_background = 0;
+    double* joint_out = nullptr;       // the captured step ends with the peer all-reduce into this buffer (or null)
     std::vector<int> spatial_cols;     // parameter columns whose values the cached work depends on ...
     std::vector<double> spatial_vals;  // ... and their values at capture time (bitwise)
     std::vector<int> amp_cols;         // amplitude columns: a source leaves the list when its amplitude is exactly 0
@@ -660,6 +665,7 @@ struct EvalRequest {
   const uint8_t* source_enable;  // single-dataset npred only
   int include_background;
   double* npred_out;  // device
+  double* joint_out = nullptr;  // device [n_vec]: all-reduce of the statistic over the ranks (gpy_stat_sum_joint_device)
 };
 
 int check_par(int idx, int n_par, const char* what) {
@@ -696,7 +702,8 @@ int evaluate_replay(gpy_context* c, const EvalRequest& rq, bool* done) {
   *done = false;
   gpy_context::Replay& R = c->replay;
   if (!R.valid || R.disabled || c->timing || rq.n_vec != 1 || rq.npred_out || rq.source_enable ||
-      rq.n_datasets != (int)R.datasets.size() || rq.n_par != R.n_par || rq.include_background != R.include_background)
+      rq.n_datasets != (int)R.datasets.size() || rq.n_par != R.n_par || rq.include_background != R.include_background ||
+      rq.joint_out != R.joint_out)
     return GPY_OK;
   for (int d = 0; d < rq.n_datasets; ++d)
     if (rq.datasets[d] != R.datasets[d] || rq.datasets[d]->version != R.versions[d]) return GPY_OK;
@@ -723,6 +730,12 @@ int evaluate_replay(gpy_context* c, const EvalRequest& rq, bool* done) {
     gpy::reduce_stat_kernel<<<dim3(1, D), 256, 0, c->stream>>>((const double*)c->partials.p, R.fold_params.ds, R.n_tiles, D, 1,
                                                               nullptr, (double*)c->stat.p);
     R.kernels += 2;
+    if (R.joint_out) {
+      gpy::PeerReduceParams q = c->peer;
+      q.n_datasets = D;
+      gpy::peer_allreduce_kernel<<<1, 256, 0, c->stream>>>(q, (const double*)c->stat.p, 1, R.joint_out);
+      R.kernels++;
+    }
     cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
     if (ce != cudaSuccess || !graph) {
       (void)cudaGetLastError();
@@ -1249,6 +1262,12 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
                                                               B, reduce_dup, (double*)c->stat.p);
     c->launches++;
   }
+  if (rq.joint_out && !rq.npred_out) {
+    gpy::PeerReduceParams q = c->peer;
+    q.n_datasets = D;
+    gpy::peer_allreduce_kernel<<<1, 256, 0, c->stream>>>(q, (const double*)c->stat.p, B, rq.joint_out);
+    c->launches++;
+  }
   CUDA_TRY(cudaGetLastError());
   // Remember what this step launched: if the next call only moves spectral / background parameters it is replayed.
   gpy_context::Replay& R = c->replay;
@@ -1258,6 +1277,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     for (int d = 0; d < D; ++d) R.versions[d] = rq.datasets[d]->version;
     R.n_par = rq.n_par;
     R.include_background = rq.include_background;
+    R.joint_out = rq.joint_out;
     R.spatial_cols.swap(replay_spatial_cols);
     R.spatial_vals.resize(R.spatial_cols.size());
     for (size_t i = 0; i < R.spatial_cols.size(); ++i) R.spatial_vals[i] = rq.params[R.spatial_cols[i]];
@@ -1360,6 +1380,7 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
         (const void*)gpy::fold_cash_tma_kernel<true, true>,
         (const void*)gpy::fold_cash_generic_kernel,
         (const void*)gpy::reduce_stat_kernel,
+        (const void*)gpy::peer_allreduce_kernel,
         (const void*)gpy::cash_sum_kernel,
         (const void*)gpy::final_sum_kernel,
         (const void*)gpy::ts_map_kernel,
@@ -1378,7 +1399,7 @@ int gpy_finalize(gpy_context_t* c) {
   if (!c) return GPY_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->zeros, &c->desc, &c->dedup, &c->staging, &c->flux, &c->partials, &c->stat, &c->tiles, &c->scratch_a, &c->scratch_b, &c->scratch_c})
+  for (DevBuf* b : {&c->peer_seq, &c->zeros, &c->desc, &c->dedup, &c->staging, &c->flux, &c->partials, &c->stat, &c->tiles, &c->scratch_a, &c->scratch_b, &c->scratch_c})
     b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->replay.exec) cudaGraphExecDestroy(c->replay.exec);
@@ -1598,6 +1619,42 @@ int gpy_stat_sum_device(gpy_context_t* c, gpy_dataset_t* const* datasets, int32_
   GPY_TRY(evaluate(c, rq));
   CUDA_TRY(cudaMemcpyAsync(stat_device, c->stat.p, (size_t)n_vec * n_datasets * sizeof(double),
                            cudaMemcpyDeviceToDevice, c->stream));
+  return GPY_OK;
+}
+
+int gpy_peer_reduce_init(gpy_context_t* c, void* const* peer_buffers, int32_t rank, int32_t world, int32_t capacity) {
+  if (!c || !peer_buffers) return fail(GPY_ERR_INVALID, "NULL argument to gpy_peer_reduce_init");
+  if (world < 1 || world > gpy::kPeerMaxWorld || rank < 0 || rank >= world || capacity < 1)
+    return fail(GPY_ERR_INVALID, "bad rank / world / capacity (%d / %d / %d)", rank, world, capacity);
+  CUDA_TRY(cudaSetDevice(c->device));
+  for (int r = 0; r < world; ++r) {
+    if (!peer_buffers[r]) return fail(GPY_ERR_INVALID, "peer buffer %d is NULL", r);
+    c->peer.bufs[r] = (double*)peer_buffers[r];
+  }
+  c->peer.rank = rank;
+  c->peer.world = world;
+  c->peer.cap = capacity;
+  GPY_TRY(c->peer_seq.reserve(sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemsetAsync(c->peer_seq.p, 0, sizeof(unsigned long long), c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->peer.seq = (unsigned long long*)c->peer_seq.p;
+  c->peer_on = true;
+  return GPY_OK;
+}
+
+int64_t gpy_peer_reduce_bytes(int32_t world, int32_t capacity) {
+  return (int64_t)2 * world * ((int64_t)capacity + 1) * (int64_t)sizeof(double);
+}
+
+int gpy_stat_sum_joint_device(gpy_context_t* c, gpy_dataset_t* const* datasets, int32_t n_datasets, const double* params,
+                              int32_t n_vec, int32_t n_par, double* joint_device) {
+  if (!c || !datasets || !params || !joint_device) return fail(GPY_ERR_INVALID, "NULL argument to gpy_stat_sum_joint_device");
+  if (!c->peer_on) return fail(GPY_ERR_INVALID, "gpy_peer_reduce_init has not been called on this context");
+  if (n_vec > c->peer.cap) return fail(GPY_ERR_INVALID, "%d parameter vectors exceed the peer-reduce capacity %d", n_vec, c->peer.cap);
+  CUDA_TRY(cudaSetDevice(c->device));
+  EvalRequest rq{datasets, n_datasets, params, n_vec, n_par, nullptr, 1, nullptr};
+  rq.joint_out = joint_device;  // the all-reduce is the last kernel of the evaluation (inside the replayed graph too)
+  GPY_TRY(evaluate(c, rq));
   return GPY_OK;
 }
 

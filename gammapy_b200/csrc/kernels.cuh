@@ -1494,6 +1494,77 @@ reduce_stat_kernel(const double* __restrict__ partials, const DatasetDev* __rest
 }
 
 // ----------------------------------------------------------------------------------------------
+// Joint fits over ranks (datasets/actors.py:84-87, 168-173: the sum of the per-actor statistics): one-shot all-reduce
+// of the B local statistics over NVLink peer memory.  Every rank owns a buffer that all ranks have mapped
+// (symmetric memory); layout per parity p in {0, 1} and source rank r:  double vals[cap], then one 64-bit flag.
+// A launch (one per evaluation, the same count on every rank) takes the next sequence number from a device-local
+// counter, stores its own values into slot (seq & 1, rank) of EVERY rank's buffer, publishes them with a
+// system-scope release store of seq into the slot's flag, then waits on its own buffer until all flags of this
+// parity show seq and adds the values in rank order (the same sum on every rank, bit for bit).  Two parities
+// suffice: nobody can write seq + 2 before everybody has read seq (they all wait for everybody's seq + 1).
+// ----------------------------------------------------------------------------------------------
+constexpr int kPeerMaxWorld = 16;
+struct PeerReduceParams {
+  double* bufs[kPeerMaxWorld];   // this process' mappings of the ranks' buffers
+  unsigned long long* seq;       // device-local sequence counter
+  int rank, world, cap;          // cap: values per slot
+  int n_datasets;
+};
+
+__device__ __forceinline__ size_t peer_slot(const PeerReduceParams& Q, int parity, int r) {
+  return ((size_t)parity * Q.world + r) * (size_t)(Q.cap + 1);
+}
+
+__global__ void __launch_bounds__(256)
+peer_allreduce_kernel(const PeerReduceParams Q, const double* __restrict__ stat /* [B, n_datasets] */, int B,
+                      double* __restrict__ out /* [B] */) {
+  __shared__ unsigned long long seq_s;
+  if (threadIdx.x == 0) seq_s = *Q.seq + 1ull;
+  __syncthreads();
+  const unsigned long long seq = seq_s;
+  const int parity = (int)(seq & 1ull);
+  // local totals in dataset order (Datasets.stat_sum), stored into every rank's slot of this rank
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    double t = 0.0;
+    for (int d = 0; d < Q.n_datasets; ++d) t += stat[(size_t)b * Q.n_datasets + d];
+    for (int q = 0; q < Q.world; ++q) Q.bufs[q][peer_slot(Q, parity, Q.rank) + b] = t;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < Q.world) {
+    unsigned long long* flag = reinterpret_cast<unsigned long long*>(Q.bufs[threadIdx.x] + peer_slot(Q, parity, Q.rank) + Q.cap);
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+  }
+  // wait for every rank's values of this sequence number (bounded: a rank that never launches must not hang the GPU)
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  if (threadIdx.x < Q.world) {
+    const unsigned long long* flag =
+        reinterpret_cast<const unsigned long long*>(Q.bufs[Q.rank] + peer_slot(Q, parity, threadIdx.x) + Q.cap);
+    unsigned long long t0, now, seen;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+      if (seen >= seq) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > 5000000000ull) {  // 5 s
+        bad = 1;
+        break;
+      }
+      __nanosleep(20);
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    double t = 0.0;
+    for (int r = 0; r < Q.world; ++r) t += Q.bufs[Q.rank][peer_slot(Q, parity, r) + b];
+    out[b] = bad ? __longlong_as_double(0x7ff8000000000000LL) : t;
+  }
+  if (threadIdx.x == 0) *Q.seq = seq;
+}
+
+// ----------------------------------------------------------------------------------------------
 // Stand-alone Cash sums (stats/fit_statistics_cython.pyx:17-85) over already-masked 1-D fp64 arrays.
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

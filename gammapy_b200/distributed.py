@@ -8,7 +8,11 @@ evaluation, never per dataset.
 """
 import numpy as np
 
-__all__ = ["partition", "allreduce_stat", "ShardedDatasets"]
+import os
+
+__all__ = ["partition", "allreduce_stat", "ShardedDatasets", "PeerReduce"]
+
+PEER_REDUCE_CAPACITY = 1024  # parameter vectors per evaluation the NVLink one-shot reduce is sized for
 
 
 def partition(sizes, world_size):
@@ -45,6 +49,62 @@ def allreduce_stat(tensor, stream=None):
     else:
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
     return tensor
+
+
+class PeerReduce:
+    """One-shot all-reduce of the joint statistic over NVLink peer memory (``gpy_peer_reduce_init``): every rank's
+    buffer is symmetric memory mapped by all ranks (``torch.distributed._symmetric_memory``), the library's last
+    kernel of an evaluation stores this rank's sums into every peer and adds the peers' in rank order.
+
+    ``PeerReduce.for_context(ctx)`` returns the per-context instance or ``None`` when the process group has one rank,
+    symmetric memory is unavailable (then NCCL does the all-reduce) or ``GPY_PEER_REDUCE=0``.  Collective: all ranks
+    must call it at the same point."""
+
+    _by_ctx = {}
+
+    def __init__(self, ctx, handle, tensor):
+        self.ctx, self.handle, self.tensor = ctx, handle, tensor
+
+    @classmethod
+    def for_context(cls, ctx):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        key = id(ctx)
+        if key in cls._by_ctx:
+            return cls._by_ctx[key]
+        inst = None
+        ok = (dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl"
+              and os.environ.get("GPY_PEER_REDUCE", "1") != "0")
+        if ok:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                world, rank = dist.get_world_size(), dist.get_rank()
+                nbytes = int(ctx.lib.gpy_peer_reduce_bytes(world, PEER_REDUCE_CAPACITY))
+                t = symm_mem.empty(nbytes // 8, dtype=torch.float64, device=ctx.torch_device)
+                t.zero_()
+                hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+                torch.cuda.synchronize()
+                dist.barrier()  # every rank's buffer is zero before anybody's first evaluation
+                ptrs = (C.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+                from . import _lib
+
+                _lib.check(ctx.lib.gpy_peer_reduce_init(ctx.handle, ptrs, rank, world, PEER_REDUCE_CAPACITY))
+                inst = cls(ctx, hdl, t)
+            except Exception as exc:  # no symmetric memory on this system: NCCL path
+                if os.environ.get("GPY_PEER_REDUCE_DEBUG"):
+                    print(f"[gammapy_b200] peer reduce unavailable: {exc!r}")
+                inst = None
+            # all ranks must agree (a rank on the NCCL path would wait for a collective the others never issue)
+            flag = torch.tensor([1 if inst is not None else 0], device=ctx.torch_device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                inst = None
+        cls._by_ctx[key] = inst
+        return inst
 
 
 class _JointEngine:
@@ -117,6 +177,8 @@ class ShardedDatasets:
         self._local_pars = local_parameters
         self._engine = None
         self._buf = None
+        self._peer = False       # PeerReduce, None (NCCL path) or False (not decided yet: first GPU evaluation)
+        self._joint_out = None
         self._joint = _JointEngine(self, global_models) if global_models is not None else None
 
     # ---- Datasets protocol used by Fit -------------------------------------------------------------------
@@ -166,13 +228,40 @@ class ShardedDatasets:
                 self._buf = torch.empty(cap, D, dtype=torch.float64, device=eng.ctx.torch_device)
             self._host = torch.empty(cap, dtype=torch.float64).pin_memory()
         buf, host = self._buf[:B], self._host[:B]
+        with torch.cuda.stream(eng.ctx.stream):
+            total = self.joint_stat_device(v2, buf)
+            host.copy_(total, non_blocking=True)
+        eng.ctx.stream.synchronize()
+        return host.numpy().copy()
+
+    def joint_stat_device(self, values, scratch=None):
+        """Asynchronous joint statistic of ``values`` ([n_local] or [B, n_local]): returns a CUDA tensor [B] that holds,
+        in the library's stream order, the sum over the datasets of all ranks.  With NVLink peer memory the library's
+        own last kernel does the all-reduce (``gpy_stat_sum_joint_device``); otherwise one NCCL all-reduce follows
+        the evaluation on the same stream.  ``scratch``: optional CUDA float64 buffer [>= B, n_local_datasets]."""
+        import torch
+
+        eng = self._local_engine()
+        v2 = np.ascontiguousarray(values, dtype=float).reshape(-1, eng.n_par)
+        B, D = v2.shape[0], len(eng.datasets)
+        if self._peer is False:
+            self._peer = PeerReduce.for_context(eng.ctx)
+        if self._peer is not None and B <= PEER_REDUCE_CAPACITY:
+            if self._joint_out is None or self._joint_out.shape[0] < B:
+                with torch.cuda.stream(eng.ctx.stream):
+                    self._joint_out = torch.empty(max(B, 64), dtype=torch.float64, device=eng.ctx.torch_device)
+            out = self._joint_out[:B]
+            eng.stat_sum_joint_device(v2, out)
+            return out
+        if scratch is None or scratch.shape[0] < B or scratch.shape[1] != D:
+            with torch.cuda.stream(eng.ctx.stream):
+                scratch = torch.empty(B, D, dtype=torch.float64, device=eng.ctx.torch_device)
+        buf = scratch[:B]
         eng.stat_sum_device(v2, buf)
         with torch.cuda.stream(eng.ctx.stream):
             total = buf[:, 0].contiguous() if D == 1 else buf.sum(dim=1)
             allreduce_stat(total, None)  # NCCL enqueues behind the kernels of the current (library) stream
-            host.copy_(total, non_blocking=True)
-        eng.ctx.stream.synchronize()
-        return host.numpy().copy()
+        return total
 
     def stat_sum_batch(self, values):
         """Joint statistic of ``values`` ([n] or [B, n]) over the datasets of ALL ranks; columns in the global

@@ -246,6 +246,14 @@ class LikelihoodEngine:
         _lib.check(self.ctx.lib.gpy_stat_sum_device(self.ctx.handle, self._handles, len(self.datasets), _ptr(v2),
                                                     v2.shape[0], self.n_par, C.c_void_p(out.data_ptr())))
 
+    def stat_sum_joint_device(self, values, out):
+        """Asynchronous joint statistic over the ranks of a sharded fit into the CUDA tensor ``out`` [B] float64: this
+        rank's datasets + the one-shot all-reduce over NVLink peer memory (``gpy_stat_sum_joint_device``)."""
+        v2 = np.ascontiguousarray(values, dtype=float).reshape(-1, self.n_par)
+        self._claim()
+        _lib.check(self.ctx.lib.gpy_stat_sum_joint_device(self.ctx.handle, self._handles, len(self.datasets), _ptr(v2),
+                                                          v2.shape[0], self.n_par, C.c_void_p(out.data_ptr())))
+
     def npred(self, index, values=None, source_enable=None, include_background=True):
         """npred cube of dataset ``index`` as a float64 numpy array."""
         import torch

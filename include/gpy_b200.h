@@ -152,6 +152,24 @@ int gpy_stat_sum(gpy_context_t* ctx, gpy_dataset_t* const* datasets, int32_t n_d
 int gpy_stat_sum_device(gpy_context_t* ctx, gpy_dataset_t* const* datasets, int32_t n_datasets,
                         const double* params, int32_t n_vec, int32_t n_par, double* stat_device);
 
+/* Joint fits over ranks, one process per GPU -- replaces the reference's sum over Ray actors
+ * (datasets/actors.py:84-87 `sum(ray.get([actor.stat_sum(...)]))`, 168-173) by a one-shot all-reduce over NVLink peer
+ * memory that runs as the last kernel of the evaluation (no NCCL launch, no host involvement).
+ *
+ * gpy_peer_reduce_bytes: size of the buffer every rank must provide for `world` ranks and batches of up to `capacity`
+ *   parameter vectors.
+ * gpy_peer_reduce_init: peer_buffers[r] = this process' device mapping of rank r's buffer (symmetric memory: CUDA
+ *   IPC / VMM handles, e.g. torch.distributed._symmetric_memory buffer_ptrs), all zero-filled and all ranks
+ *   synchronised before the first evaluation.  Every rank must then issue the same sequence of
+ *   gpy_stat_sum_joint_device calls.
+ * gpy_stat_sum_joint_device: as gpy_stat_sum_device, then joint_device DEVICE [n_vec] float64 = sum over ranks of
+ *   (sum over this rank's datasets, in dataset order), ranks added in rank order: bit-identical on every rank.  A rank
+ *   that waits longer than 5 s for a peer writes NaN instead of hanging the device. */
+int64_t gpy_peer_reduce_bytes(int32_t world, int32_t capacity);
+int gpy_peer_reduce_init(gpy_context_t* ctx, void* const* peer_buffers, int32_t rank, int32_t world, int32_t capacity);
+int gpy_stat_sum_joint_device(gpy_context_t* ctx, gpy_dataset_t* const* datasets, int32_t n_datasets,
+                              const double* params, int32_t n_vec, int32_t n_par, double* joint_device);
+
 /* MapDataset.npred (datasets/map.py:775-788) / npred_signal (:824-880) for one parameter vector.
  *   source_enable HOST [n_sources] or NULL (all): npred_signal(model_names=...)
  *   include_background: add npred_background (:790-813) and clip negatives to 0 (:787)
