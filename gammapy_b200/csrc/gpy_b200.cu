@@ -1125,11 +1125,20 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   fp.smem_nRp = max_nRp;
   fp.smem_G = max_G;
   fp.smem_pdfc_rows = max_pdfc_rows;
-  if (!c->zeros.p) {
-    GPY_TRY(c->zeros.reserve(256));
+  if (!c->zeros.p) {  // [0, 128) zeros, [128, 132) work counter, [256, 2304) fast_log table
+    GPY_TRY(c->zeros.reserve(256 + 128 * 16));
     CUDA_TRY(cudaMemsetAsync(c->zeros.p, 0, 256, c->stream));
+    static double tab[256];
+    for (int i = 0; i < 128; ++i) {
+      const double inv = 1.0 / (1.0 + (i + 0.5) / 128.0);
+      tab[2 * i] = inv;
+      tab[2 * i + 1] = -std::log(inv);
+    }
+    CUDA_TRY(cudaMemcpyAsync((uint8_t*)c->zeros.p + 256, tab, sizeof(tab), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
   }
   fp.zeros = (const float*)c->zeros.p;
+  fp.logtab = (const double2*)((const uint8_t*)c->zeros.p + 256);
   const size_t n_items = (size_t)B * n_tiles;
   const unsigned char* reduce_dup = nullptr;
   const int variant = rq.npred_out ? 1 : 0;

@@ -491,6 +491,7 @@ struct FoldParams {
   const float* zeros;       // >= 16 bytes of zeros: load target of (thread, source) pairs outside the cutout
   int pad_;
   double log_trunc;         // log((double)(float)1e-25): Cython narrows the constant to C float
+  const double2* logtab;    // fast_log table, 128 entries
 };
 
 constexpr int kFoldTPX = 128;      // pixels per tile
@@ -962,7 +963,29 @@ __global__ void __launch_bounds__(256) prep_items_kernel(const PrepParams P) {
     *reinterpret_cast<int4*>(out) = make_int4(nl, min(max(n - kFoldLMax, 0), kDescOverflow), d * P.B + b, 0);
 }
 
+#ifndef GPY_FAST_LOG
+#define GPY_FAST_LOG 1
+#endif
+// log(x) for normal finite x > 0: x = 2^e m, m in [1, 2); m = m_hi (1 + r) with 1 / m_hi from a table indexed by the
+// top 7 mantissa bits, |r| < 2^-8; log(x) = e ln2 + log(m_hi) + log1p(r), log1p by its degree-7 Taylor polynomial
+// (|error| < 1e-17 absolute + the table's rounding, ~1e-16).  Straight-line code: calls interleave, unlike libdevice's
+// log with its data-dependent branches.  Table: double2 {1 / m_hi, -log(1 / m_hi)} x 128 (built by the host).
+__device__ __forceinline__ double fast_log(double x, const double2* __restrict__ tab) {
+  const long long ix = __double_as_longlong(x);
+  const int e = (int)(ix >> 52) - 1023;
+  const double2 t = tab[(int)(ix >> 45) & 127];
+  const double m = __longlong_as_double((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const double r = fma(m, t.x, -1.0);
+  const double r2 = r * r;
+  const double a = fma(r, 1.0 / 3.0, -0.5), b = fma(r, 0.2, -0.25), c = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+  double q = fma(r2, c, b);
+  q = fma(r2, q, a);
+  const double p = fma(r2, q, r);
+  return fma((double)e, 0.6931471805599453, t.y) + p;
+}
+
 constexpr int kTmaTCH = 32;  // true-energy bins per pass of the bulk-copy kernel (2 passes at nT = 60)
+constexpr int kBandSmem = 128;  // ints of the band table kept in shared memory (larger tables are read from global)
 struct FoldSmem {  // byte offsets of the fixed shared-memory layout
   size_t es, bs, cs, ms, vs, pdf, desc, dyn, bars, total;
 };
@@ -978,7 +1001,7 @@ __host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int
   L.desc = o;  o += (size_t)2 * desc_layout().bytes;  // double buffered item descriptors
   L.dyn = o;   o += (size_t)2 * (kFoldLMax * nT + nRp) * 8;  // double buffered flux rows + background factors
   L.bars = (o + 7) / 8 * 8;
-  L.total = L.bars + 3 * 8;
+  L.total = L.bars + 4 * 8;
   return L;
 }
 
@@ -997,9 +1020,15 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   DL.inst = P.dl_inst;
   DL.over = P.dl_over;
   DL.bytes = P.dl_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + P.lay_bars);  // [0] exposure, [1] epilogue inputs, [2] descriptor
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fold_raw + P.lay_bars);  // [0] exposure, [1] epilogue inputs, [2], [3] descriptor buffers
   __shared__ double wsum[kFoldThreads / 32];
-  __shared__ int2 nxt_s;  // {worklist position, item} claimed for the next iteration
+  __shared__ int2 nxt_s;         // {worklist position, item} claimed for the iteration after the next
+  __shared__ DatasetDev Ds;      // table entry of the dataset the current item belongs to: no global loads per item
+  __shared__ int band_s[kBandSmem];
+#if GPY_FAST_LOG
+  __shared__ double2 logtab_s[128];
+  if (threadIdx.x < 128) logtab_s[threadIdx.x] = P.logtab[threadIdx.x];  // published by the barrier behind the mbarrier initialisation
+#endif
 
   const int tid = threadIdx.x;
   const int n_items = P.B * P.n_tiles;
@@ -1009,85 +1038,101 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
+  // Geometry of a work item without touching global memory: the table entry of the current dataset lives in shared
+  // memory (Ds); only an item of ANOTHER dataset (the CTA crosses a dataset boundary) reads the table in global memory.
+  auto geom = [&](int item, int& p0, int& npx) -> const DatasetDev* {
+    const int tile = DYNAMIC ? item : item / P.B;  // dynamic launches have B == 1
+    const DatasetDev* Dn = &Ds;
+    if (tile < Ds.tile_begin || tile >= Ds.tile_begin + Ds.n_tiles) Dn = P.ds + P.tile_ds[tile];
+    p0 = (tile - Dn->tile_begin) * kFoldTPX;
+    npx = min(kFoldTPX, (int)Dn->P - p0);
+    return Dn;
+  };
   // producers: thread 0 arms the mbarrier with the byte count BEFORE a CTA barrier, then every warp issues its
   // share of the 1-D bulk copies (one 512-byte row segment per lane), so the ~70-cycle issue cost of a copy is
-  // spread over the 8 warps instead of sitting on warp 0's critical path.
+  // spread over the 8 warps instead of sitting on warp 0's critical path.  With tensor maps thread 0 arms and issues
+  // one 2-D tensor copy per cube in issue_*.
   auto arm_expo = [&](int item) {
-    const int tile = item / P.B;
-    const DatasetDev& D = P.ds[P.tile_ds[tile]];
-    const int p0 = (tile - D.tile_begin) * kFoldTPX;
-    const int npx = min(kFoldTPX, (int)D.P - p0);
-    if (!D.tmaps) mbar_arrive_expect_tx(&bars[0], (uint32_t)npx * 4u * (uint32_t)D.nT);
+    int p0, npx;
+    const DatasetDev* D = geom(item, p0, npx);
+    if (!D->tmaps) mbar_arrive_expect_tx(&bars[0], (uint32_t)npx * 4u * (uint32_t)D->nT);
   };
   auto issue_expo = [&](int item) {
-    const int tile = item / P.B;
-    const DatasetDev& D = P.ds[P.tile_ds[tile]];
-    const int p0 = (tile - D.tile_begin) * kFoldTPX;
-    const int npx = min(kFoldTPX, (int)D.P - p0);
+    int p0, npx;
+    const DatasetDev* D = geom(item, p0, npx);
     const uint32_t row = (uint32_t)npx * 4u;
-    if (D.tmaps) {  // one 2-D tensor copy of the whole [nT][128] box (out-of-range columns are zero filled)
+    if (D->tmaps) {  // one 2-D tensor copy of the whole [nT][128] box (out-of-range columns are zero filled)
       if (tid == 0) {
-        mbar_arrive_expect_tx(&bars[0], (uint32_t)kFoldTPX * 4u * (uint32_t)D.nT);
-        tma_load_2d(es, D.tmaps, p0, 0, &bars[0], pol_stream);
+        mbar_arrive_expect_tx(&bars[0], (uint32_t)kFoldTPX * 4u * (uint32_t)D->nT);
+        tma_load_2d(es, D->tmaps, p0, 0, &bars[0], pol_stream);
       }
       return;
     }
-    const int t = (tid & 31) * (kFoldThreads / 32) + (tid >> 5);  // row handled by this lane
-    if (t < D.nT) bulk_g2s_hint(es + t * kFoldTPX, D.exposure + (size_t)t * D.P + p0, row, &bars[0], pol_stream);
-    for (int t2 = t + kFoldThreads; t2 < D.nT; t2 += kFoldThreads)
-      bulk_g2s_hint(es + t2 * kFoldTPX, D.exposure + (size_t)t2 * D.P + p0, row, &bars[0], pol_stream);
+    const int nT = D->nT;
+    const float* expo = D->exposure;
+    const size_t PP = (size_t)D->P;
+    for (int t = (tid & 31) * (kFoldThreads / 32) + (tid >> 5); t < nT; t += kFoldThreads)  // row handled by this lane
+      bulk_g2s_hint(es + t * kFoldTPX, expo + (size_t)t * PP + p0, row, &bars[0], pol_stream);
   };
   auto arm_epi = [&](int item) {
-    const int tile = item / P.B;
-    const DatasetDev& D = P.ds[P.tile_ds[tile]];
-    const int p0 = (tile - D.tile_begin) * kFoldTPX;
-    const int npx = min(kFoldTPX, (int)D.P - p0);
+    int p0, npx;
+    const DatasetDev* D = geom(item, p0, npx);
     const uint32_t row = (uint32_t)npx * 4u;
     uint32_t total = 0;
-    if (D.tmaps) return;  // armed together with the tensor copies, after the barrier
-    if (D.background && P.include_background) total += row * (uint32_t)D.nR;
-    if (D.counts) total += row * (uint32_t)D.nR;
-    if (D.counts && D.mask) total += (uint32_t)npx * (uint32_t)D.nR;
+    if (D->tmaps) return;  // armed together with the tensor copies, after the barrier
+    if (D->background && P.include_background) total += row * (uint32_t)D->nR;
+    if (D->counts) total += row * (uint32_t)D->nR;
+    if (D->counts && D->mask) total += (uint32_t)npx * (uint32_t)D->nR;
     mbar_arrive_expect_tx(&bars[1], total);
   };
   auto issue_epi = [&](int item) {
-    const int tile = item / P.B;
-    const DatasetDev& D = P.ds[P.tile_ds[tile]];
-    const int p0 = (tile - D.tile_begin) * kFoldTPX;
-    const int npx = min(kFoldTPX, (int)D.P - p0);
+    int p0, npx;
+    const DatasetDev* D = geom(item, p0, npx);
     const uint32_t row = (uint32_t)npx * 4u;
-    const bool has_bkg = D.background && P.include_background;
-    if (D.tmaps) {
+    const bool has_bkg = D->background && P.include_background;
+    if (D->tmaps) {
       if (tid == 0) {
-        const unsigned char* tm = reinterpret_cast<const unsigned char*>(D.tmaps);
+        const unsigned char* tm = reinterpret_cast<const unsigned char*>(D->tmaps);
+        const bool has_counts = D->counts != nullptr, has_mask = has_counts && D->mask;
+        const uint32_t nR = (uint32_t)D->nR;
         uint32_t total = 0;
-        if (has_bkg) total += (uint32_t)kFoldTPX * 4u * (uint32_t)D.nR;
-        if (D.counts) total += (uint32_t)kFoldTPX * 4u * (uint32_t)D.nR;
-        if (D.counts && D.mask) total += (uint32_t)kFoldTPX * (uint32_t)D.nR;
+        if (has_bkg) total += (uint32_t)kFoldTPX * 4u * nR;
+        if (has_counts) total += (uint32_t)kFoldTPX * 4u * nR;
+        if (has_mask) total += (uint32_t)kFoldTPX * nR;
         mbar_arrive_expect_tx(&bars[1], total);
         if (has_bkg) tma_load_2d(bs, tm + 128, p0, 0, &bars[1], pol_stream);
-        if (D.counts) tma_load_2d(cs, tm + 256, p0, 0, &bars[1], pol_stream);
-        if (D.counts && D.mask) tma_load_2d(ms, tm + 384, p0, 0, &bars[1], pol_stream);
+        if (has_counts) tma_load_2d(cs, tm + 256, p0, 0, &bars[1], pol_stream);
+        if (has_mask) tma_load_2d(ms, tm + 384, p0, 0, &bars[1], pol_stream);
       }
       return;
     }
     // copy index i = 3 r + which, spread over (lane, warp) like the exposure rows
-    for (int i = (tid & 31) * (kFoldThreads / 32) + (tid >> 5); i < 3 * D.nR; i += kFoldThreads) {
+    const int nR = D->nR;
+    const float* bkg = D->background;
+    const float* cnt = D->counts;
+    const uint8_t* msk = D->mask;
+    const size_t PP = (size_t)D->P;
+    for (int i = (tid & 31) * (kFoldThreads / 32) + (tid >> 5); i < 3 * nR; i += kFoldThreads) {
       const int r = i / 3, which = i - 3 * r;
-      const size_t off = (size_t)r * D.P + p0;
-      if (which == 0 && has_bkg) bulk_g2s_hint(bs + r * kFoldTPX, D.background + off, row, &bars[1], pol_stream);
-      if (which == 1 && D.counts) bulk_g2s_hint(cs + r * kFoldTPX, D.counts + off, row, &bars[1], pol_stream);
-      if (which == 2 && D.counts && D.mask) bulk_g2s_hint(ms + r * kFoldTPX, D.mask + off, (uint32_t)npx, &bars[1], pol_stream);
+      const size_t off = (size_t)r * PP + p0;
+      if (which == 0 && has_bkg) bulk_g2s_hint(bs + r * kFoldTPX, bkg + off, row, &bars[1], pol_stream);
+      if (which == 1 && cnt) bulk_g2s_hint(cs + r * kFoldTPX, cnt + off, row, &bars[1], pol_stream);
+      if (which == 2 && cnt && msk) bulk_g2s_hint(ms + r * kFoldTPX, msk + off, (uint32_t)npx, &bars[1], pol_stream);
     }
   };
 
+  // One mbarrier per descriptor buffer: a buffer's next phase (the item after the next) is requested at the top of
+  // the next item, after the end-of-item barrier behind which every thread has tested the current phase -- so the
+  // request can go out at the very top of an item.  (With one barrier for both buffers a request issued before the
+  // item's first CTA barrier could complete two phases ahead of a slow thread, whose parity wait then never returns.)
   auto fetch_desc = [&](int it, uint32_t buf) {  // thread 0: one bulk copy of work item `it`'s descriptor
-    mbar_arrive_expect_tx(&bars[2], (uint32_t)DL.bytes);
-    bulk_g2s(desc_s + buf * DL.bytes, P.desc + (size_t)it * DL.bytes, (uint32_t)DL.bytes, &bars[2]);
+    mbar_arrive_expect_tx(&bars[2 + buf], (uint32_t)DL.bytes);
+    bulk_g2s(desc_s + buf * DL.bytes, P.desc + (size_t)it * DL.bytes, (uint32_t)DL.bytes, &bars[2 + buf]);
   };
 
   // The per-step numbers of an item -- the flux vectors of its register-resident sources (zero rows beyond nl) and
@@ -1110,26 +1155,65 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   };
 
   const int n_work = P.work ? *P.n_work : n_items;
+  auto item_at = [&](int pos) -> int { return pos < n_work ? (P.work ? __ldg(P.work + pos) : pos) : n_items; };
+  auto desc_nl = [&](int pos) -> int {  // number of register-resident sources of the item at worklist position pos
+    return __ldg(reinterpret_cast<const int*>(P.desc + (size_t)pos * DL.bytes));
+  };
+  // (Re)load the dataset table entry, its band-compressed edisp matrices and band table.  Block uniform.
+  auto load_dataset = [&](int tile) {
+    const int* src = reinterpret_cast<const int*>(P.ds + P.tile_ds[tile]);
+    if (tid < (int)(sizeof(DatasetDev) / 4)) reinterpret_cast<int*>(&Ds)[tid] = src[tid];
+    __syncthreads();
+    const double* pdfc = Ds.pdfc;
+    for (int i = tid; i < Ds.pdfc_rows * 8; i += kFoldThreads) pdf_s[i] = pdfc[i];
+    const int nb = min(Ds.n_groups * (Ds.nRp >> 3) * 4, kBandSmem);
+    const int* band = Ds.band;
+    for (int i = tid; i < nb; i += kFoldThreads) band_s[i] = band[i];
+  };
+
+  // Items are claimed two ahead: `item` is being computed, `next` has its copies in flight, and the claim of the one
+  // after (an atomic on a global counter: ~1 us round trip) is issued at the top of an item and consumed at its end.
   int w = blockIdx.x;
-  int item = w < n_work ? (P.work ? P.work[w] : w) : n_items;
-  if (item < n_items) {
+  int item = item_at(w);
+  if (item >= n_items) return;
+  int wn, next;
+  if (!DYNAMIC) {
+    wn = w + gridDim.x;
+    next = item_at(wn);
+  } else {
     if (tid == 0) {
-      arm_expo(item);
+      const int c = gridDim.x + atomicAdd(P.counter, 1u);
+      nxt_s = make_int2(c, item_at(c));
+    }
+  }
+  load_dataset(DYNAMIC ? item : item / P.B);
+  __syncthreads();  // Ds, nxt_s
+  if (DYNAMIC) {
+    const int2 v = nxt_s;
+    wn = v.x;
+    next = v.y;
+  }
+  {
+    const bool expo_first = desc_nl(w) > 0;  // source-free tiles do not fetch their exposure
+    if (tid == 0) {
+      if (expo_first) arm_expo(item);
       arm_epi(item);
       fetch_desc(w, 0);
     }
     __syncthreads();
-    issue_expo(item);
+    if (expo_first) issue_expo(item);
     issue_epi(item);
     mbar_wait(&bars[2], 0);
     stage_dyn(0);
     __syncthreads();
   }
-  uint32_t parity = 0;
-  int cur_ds = -1;
+  uint32_t it = 0;       // items done by this CTA: descriptor buffer it & 1, its mbarrier phase (it >> 1) & 1
+  uint32_t eparity = 0;  // phase of the exposure barrier: flips on items that have sources only
 #ifdef GPY_FOLD_TIMING
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
+  long long cls_cyc[4] = {0, 0, 0, 0};
+  int cls_n[4] = {0, 0, 0, 0};
 #define GPY_TICK(i) do { if (tid == 0) { long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } } while (0)
 #else
 #define GPY_TICK(i) do { } while (0)
@@ -1138,47 +1222,35 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   const int q = tid & 31, slot = tid >> 5;   // phase 1: 32 pixel quads x 8 energy slots
   const int pp = tid & 63, cslot = tid >> 6;  // phase 2: 64 pixel pairs x 4 reco-chunk slots
 
-  for (; item < n_items; parity ^= 1u) {
-    const int b = item % P.B;
-    const int tile = item / P.B;
-    const int d = P.tile_ds[tile];
-    const DatasetDev D = P.ds[d];
-    const int nT = D.nT, nR = D.nR, nRp = D.nRp, G = D.n_groups;
-    const int p0 = (tile - D.tile_begin) * kFoldTPX;
-    const int npx = min(kFoldTPX, (int)D.P - p0);
-    // The next item is claimed from a global counter (items differ in cost: a static round-robin leaves a tail).
-    // Thread 0 claims it here and needs it at once (it arms the next copies); the others pick it up from shared
-    // memory after the first barrier of this item, before their first use.
-    // (DYNAMIC == false: static round-robin, for few items per CTA or a batched call of many light items.)
-    int wn = w + gridDim.x;
-    int next = n_items;  // n_items: no further item
-    bool have_next = !DYNAMIC || tid == 0;
+  for (;; ++it) {
+    const uint32_t parity = it & 1u;          // descriptor / per-step-number buffer of this item
+    const uint32_t dphase = (it >> 1) & 1u;   // phase of that buffer's mbarrier
+    const int b = DYNAMIC ? 0 : item % P.B;
+    const int tile = DYNAMIC ? item : item / P.B;
+    // claim the item after the next (consumed at the end of this item) and look up whether the next one has sources
+    int wnn = 0, nn = n_items;
     if (!DYNAMIC) {
-      next = wn < n_work ? (P.work ? __ldg(P.work + wn) : wn) : n_items;
+      wnn = wn + gridDim.x;
+      nn = item_at(wnn);
     } else if (tid == 0) {
-      wn = gridDim.x + atomicAdd(P.counter, 1u);
-      next = wn < n_work ? (P.work ? __ldg(P.work + wn) : wn) : n_items;
-      nxt_s = make_int2(wn, next);
+      wnn = gridDim.x + atomicAdd(P.counter, 1u);
     }
-    auto sync_next = [&]() {  // call after a CTA barrier of this item
-      if (DYNAMIC && !have_next) {
-        const int2 v = nxt_s;
-        wn = v.x;
-        next = v.y;
-        have_next = true;
-      }
-    };
-
-    if (d != cur_ds) {  // edisp matrices of this dataset (block-uniform branch)
-      for (int i = tid; i < D.pdfc_rows * 8; i += kFoldThreads) pdf_s[i] = D.pdfc[i];
-      cur_ds = d;
+    const bool expo_next = next < n_items && desc_nl(wn) > 0;
+    if (tid == 0 && next < n_items) fetch_desc(wn, parity ^ 1u);
+    if (tile < Ds.tile_begin || tile >= Ds.tile_begin + Ds.n_tiles) {  // block uniform: first item of another dataset
+      __syncthreads();  // nobody still reads the old entry (issue_epi of this item at the end of the last one)
+      load_dataset(tile);
+      __syncthreads();
     }
-    // work descriptor of this item (prefetched); start fetching the next one into the other buffer
-    // The fetch of the NEXT descriptor is issued after the first CTA barrier of this item (below): by then every
-    // thread has observed the completion of this phase.  Issuing it earlier lets the barrier run two phases ahead
-    // of a slow thread, whose parity wait would then never return.
-    mbar_wait(&bars[2], parity);
-    bool desc_fetched = false;
+    const int nT = Ds.nT, nR = Ds.nR, nRp = Ds.nRp, G = Ds.n_groups, nx = Ds.nx;
+    const int p0 = (tile - Ds.tile_begin) * kFoldTPX;
+    const int npx = min(kFoldTPX, (int)Ds.P - p0);
+    const bool has_bkg = Ds.background && P.include_background, has_counts = Ds.counts != nullptr,
+               has_mask = Ds.mask != nullptr, use_tmaps = Ds.tmaps != nullptr;
+    const int nchunks = nRp >> 3;
+    const int* band = G * nchunks * 4 <= kBandSmem ? band_s : Ds.band;
+    // work descriptor of this item (requested at the top of the previous item)
+    mbar_wait(&bars[2 + parity], dphase);
     const unsigned char* dsc = desc_s + parity * DL.bytes;
     const int nl = reinterpret_cast<const int*>(dsc)[0], nover = reinterpret_cast<const int*>(dsc)[1];
     const InstDev* slist = reinterpret_cast<const InstDev*>(dsc + DL.inst);
@@ -1188,11 +1260,14 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const int fstride = P.smem_nT;
     GPY_TICK(0);
     GPY_TICK(1);
+#ifdef GPY_FOLD_TIMING
+    const long long t_item0 = clock64();
+#endif
     // this thread's pixel quad and, per overlapping source, a pointer into its cutout; outside the cutout the
     // pointer targets a zero word with stride 0, so phase 1 is branch free and its loads can all be in flight
     const int pq = p0 + 4 * q;
     const bool qlive = 4 * q < npx;
-    const int qy = pq / D.nx, qx = pq - qy * D.nx;
+    const int qy = pq / nx, qx = pq - qy * nx;
     const float* cptr[kFoldLMax];
     int pstr[kFoldLMax], grp[kFoldLMax];
 #pragma unroll
@@ -1210,7 +1285,6 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         }
       }
     }
-    const int nchunks = nRp >> 3;
     double stat = 0.0;
     for (int cbase = 0; cbase < nchunks; cbase += 4) {  // one pass for nR <= 32
       const int c = cbase + cslot;
@@ -1218,19 +1292,12 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.0;
 
-      if (nl == 0) {
-        // no source reaches this tile: npred = background only.  Keep the exposure pipeline in step.
-        if (cbase == 0) mbar_wait(&bars[0], parity);
-        if (tid == 0 && cbase + 4 >= nchunks && next < n_items) arm_expo(next);
-        __syncthreads();
-        sync_next();
-        if (!desc_fetched && tid == 0 && next < n_items) fetch_desc(wn, parity ^ 1u);
-        desc_fetched = true;
-        if (cbase + 4 >= nchunks && next < n_items) issue_expo(next);
-      }
+      // No source reaches this tile: npred = background only; its exposure was never requested, so the buffer is
+      // free for the next item's (armed here, issued behind the first barrier of the item).
+      if (nl == 0 && cbase == 0 && expo_next && tid == 0) arm_expo(next);
       for (int t0 = 0; t0 < (nl > 0 ? nT : 0); t0 += kTmaTCH) {
         GPY_TICK(2);
-        if (cbase == 0 && t0 == 0) mbar_wait(&bars[0], parity);  // exposure tile has landed
+        if (cbase == 0 && t0 == 0) mbar_wait(&bars[0], eparity);  // exposure tile has landed
         GPY_TICK(3);
         // ---- phase 1: v[g][t][p] = 1e4 * exposure[t,p] * sum_s F_s[t] * conv_s[t,p] ----
         for (int g = 0; g < G; ++g) {
@@ -1333,20 +1400,17 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
           }
         }
         GPY_TICK(4);
-        if (tid == 0 && cbase + 4 >= nchunks && t0 + kTmaTCH >= nT && next < n_items) arm_expo(next);
+        const bool fetch_next = cbase + 4 >= nchunks && t0 + kTmaTCH >= nT && expo_next;
+        if (tid == 0 && fetch_next) arm_expo(next);
         __syncthreads();
-        sync_next();
-        const bool fetch_next = cbase + 4 >= nchunks && t0 + kTmaTCH >= nT && next < n_items;
         GPY_TICK(5);
-        if (!desc_fetched && tid == 0 && next < n_items) fetch_desc(wn, parity ^ 1u);
-        desc_fetched = true;
         // exposure tile fully consumed: start fetching the next item's while phase 2 / the epilogue run
         if (fetch_next) issue_expo(next);
         GPY_TICK(6);
         // ---- phase 2: acc[r] += pdf[t][r] * v[t][p] over the non-zero band ----
         if (c < nchunks) {
           for (int g = 0; g < G; ++g) {
-            const int4 bnd = *reinterpret_cast<const int4*>(D.band + (g * nchunks + c) * 4);
+            const int4 bnd = *reinterpret_cast<const int4*>(band + (g * nchunks + c) * 4);
             const int blo = bnd.x, bhi = bnd.y;
             const int tlo = max(blo, t0), thi = min(bhi, t0 + kTmaTCH);
             const double* vrow = vs + (size_t)g * kTmaTCH * kFoldTPX + 2 * pp;
@@ -1382,7 +1446,6 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
       const int r0 = 8 * cbase;
       double* mus = vs;
       if (c < nchunks && 2 * pp < npx) {
-        const bool has_bkg = D.background && P.include_background;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int r = 8 * c + j;
@@ -1401,12 +1464,13 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         }
       }
       __syncthreads();
+      if (nl == 0 && cbase == 0 && expo_next) issue_expo(next);
       // next item's per-step numbers: the loads are issued before the Cash pass and stored to shared memory after
       // it (few registers are live here), so the pass covers their latency; the end-of-item barrier publishes them
       const bool stage_next = cbase + 4 >= nchunks && next < n_items;
       double dyn0 = 0.0, dyn1 = 0.0;
       if (stage_next) {
-        mbar_wait(&bars[2], parity ^ 1u);  // the next descriptor, requested after this item's first barrier
+        mbar_wait(&bars[2 + (parity ^ 1u)], ((it + 1u) >> 1) & 1u);  // the next descriptor, requested at the top of this item
         if (tid < dyn_len) dyn0 = load_dyn(parity ^ 1u, tid);
         if (tid + kFoldThreads < dyn_len) dyn1 = load_dyn(parity ^ 1u, tid + kFoldThreads);
       }
@@ -1415,15 +1479,45 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         // of mu, one 64-bit load of the counts, one 16-bit load of the mask.  Most bins of a gamma-ray cube hold no
         // count, so the log is the rare branch and the pass is bound by its loads and index arithmetic.
         const int nr = min(nR - r0, 32);
-        const bool has_counts = D.counts != nullptr, has_mask = D.mask != nullptr;
         const double log_trunc = P.log_trunc;
+#if GPY_FAST_LOG
+        // The trip count is warp uniform (nr * 64 items, 32 consecutive ones per warp), so the warp can vote: the two
+        // logs run only when some lane holds a count, as straight-line code for both pixels at once (fast_log: no
+        // data-dependent branch, the two dependency chains interleave).  Separate accumulators for the mu and the
+        // n log mu terms halve the fp64 add chain.
+        double stat_mu = 0.0, stat_nl = 0.0;
+        for (int i = tid; i < nr * (kFoldTPX / 2); i += kFoldThreads) {
+          const int rr = i >> 6, lp = (i & (kFoldTPX / 2 - 1)) * 2;  // kFoldTPX == 128
+          const bool live = lp < npx;
+          const int r = r0 + rr;
+          const double2 mu2 = *reinterpret_cast<const double2*>(mus + rr * kFoldTPX + lp);
+          if (WRITE_NPRED && live)
+            *reinterpret_cast<double2*>(P.npred_out + (size_t)r * (size_t)Ds.P + p0 + lp) = mu2;
+          if (has_counts) {
+            const float2 n2 = *reinterpret_cast<const float2*>(cs + r * kFoldTPX + lp);
+            const unsigned m2 = has_mask ? *reinterpret_cast<const unsigned short*>(ms + r * kFoldTPX + lp) : 0x0101u;
+            const bool on0 = live && (m2 & 0xffu), on1 = live && (m2 >> 8);
+            const bool big0 = mu2.x > kTrunc, big1 = mu2.y > kTrunc;
+            const double a0 = big0 ? mu2.x : kTrunc, a1 = big1 ? mu2.y : kTrunc;
+            stat_mu += (on0 ? a0 : 0.0) + (on1 ? a1 : 0.0);
+            const bool need0 = on0 && n2.x > 0.f, need1 = on1 && n2.y > 0.f;
+            if (__any_sync(0xffffffffu, need0 || need1)) {
+              double l0 = fast_log(a0, logtab_s), l1 = fast_log(a1, logtab_s);
+              l0 = big0 ? (a0 <= 1.7976931348623157e308 ? l0 : a0) : log_trunc;  // log(inf) = inf
+              l1 = big1 ? (a1 <= 1.7976931348623157e308 ? l1 : a1) : log_trunc;
+              stat_nl += (need0 ? (double)n2.x * l0 : 0.0) + (need1 ? (double)n2.y * l1 : 0.0);
+            }
+          }
+        }
+        stat += stat_mu - stat_nl;
+#else
         for (int i = tid; i < nr * (kFoldTPX / 2); i += kFoldThreads) {
           const int rr = i >> 6, lp = (i & (kFoldTPX / 2 - 1)) * 2;  // kFoldTPX == 128
           if (lp >= npx) continue;
           const int r = r0 + rr;
           const double2 mu2 = *reinterpret_cast<const double2*>(mus + rr * kFoldTPX + lp);
           if (WRITE_NPRED)
-            *reinterpret_cast<double2*>(P.npred_out + (size_t)r * D.P + p0 + lp) = mu2;
+            *reinterpret_cast<double2*>(P.npred_out + (size_t)r * (size_t)Ds.P + p0 + lp) = mu2;
           if (has_counts) {
             const float2 n2 = *reinterpret_cast<const float2*>(cs + r * kFoldTPX + lp);
             const unsigned m2 = has_mask ? *reinterpret_cast<const unsigned short*>(ms + r * kFoldTPX + lp) : 0x0101u;
@@ -1439,6 +1533,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
             }
           }
         }
+#endif
       }
       if (stage_next) {
         double* dst = dyn_s + (parity ^ 1u) * dyn_len;
@@ -1452,21 +1547,44 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) stat += __shfl_xor_sync(0xffffffffu, stat, o);
     if ((tid & 31) == 0) wsum[tid >> 5] = stat;
-    if (tid == 0 && next < n_items) arm_epi(next);
+    if (tid == 0) {
+      if (next < n_items) arm_epi(next);
+      if (DYNAMIC) nxt_s = make_int2(wnn, item_at(wnn));
+    }
     __syncthreads();  // every warp is past its epilogue reads; list / bkgfac reuse in the next item
     if (tid == 0)     // fixed summation order; no warp can rewrite wsum before passing a barrier with thread 0
       P.partials[(size_t)b * P.n_tiles + tile] =
           ((wsum[0] + wsum[1]) + (wsum[2] + wsum[3])) + ((wsum[4] + wsum[5]) + (wsum[6] + wsum[7]));
     GPY_TICK(10);
     if (next < n_items) issue_epi(next);
+    if (nl > 0) eparity ^= 1u;
+    if (DYNAMIC) {  // no thread can pass the next end-of-item barrier (where thread 0 rewrites nxt_s) before this read
+      const int2 v = nxt_s;
+      wnn = v.x;
+      nn = v.y;
+    }
+    const bool done = next >= n_items;
     item = next;
     w = wn;
+    next = nn;
+    wn = wnn;
     GPY_TICK(11);
+#ifdef GPY_FOLD_TIMING
+    {
+      const int k = nl == 0 ? 0 : nl <= 2 ? 1 : nover == 0 ? 2 : 3;
+      cls_cyc[k] += clock64() - t_item0;
+      cls_n[k]++;
+    }
+#endif
+    if (done) break;
   }
 #ifdef GPY_FOLD_TIMING
   if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 100))
     printf("[fold timing] block %d: list %lld | sync-after-list %lld | misc %lld | expo wait %lld | phase1 %lld | phase syncs %lld | issue expo %lld | phase2 %lld | epi wait %lld | epilogue %lld | end barrier %lld | issue epi %lld\n",
            blockIdx.x, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7], tacc[8], tacc[9], tacc[10], tacc[11]);
+  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 100 || blockIdx.x == 201))
+    printf("[fold classes] block %d: no-source %d items %lld cyc | 1-2 sources %d items %lld cyc | 3-4 sources %d items %lld cyc | >4 sources %d items %lld cyc\n",
+           blockIdx.x, cls_n[0], cls_cyc[0], cls_n[1], cls_cyc[1], cls_n[2], cls_cyc[2], cls_n[3], cls_cyc[3]);
 #endif
 }
 
