@@ -789,6 +789,9 @@ __device__ __forceinline__ float4 ldg_f4_hint(const float* p, uint64_t pol) {
                : "l"(p), "l"(pol));
   return v;
 }
+__device__ __forceinline__ void prefetch_l2_keep(const void* p) {
+  asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
@@ -963,6 +966,12 @@ __global__ void __launch_bounds__(256) prep_items_kernel(const PrepParams P) {
     *reinterpret_cast<int4*>(out) = make_int4(nl, min(max(n - kFoldLMax, 0), kDescOverflow), d * P.B + b, 0);
 }
 
+#ifndef GPY_ABLATE  // profiling only (wrong results): 1 slot-cube loads hit a zero word, 2 no phase 2, 4 no Cash pass
+#define GPY_ABLATE 0
+#endif
+#ifndef GPY_PF_PASS
+#define GPY_PF_PASS 0
+#endif
 #ifndef GPY_FAST_LOG
 #define GPY_FAST_LOG 1
 #endif
@@ -1057,7 +1066,11 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   // share of the 1-D bulk copies (one 512-byte row segment per lane), so the ~70-cycle issue cost of a copy is
   // spread over the 8 warps instead of sitting on warp 0's critical path.  With tensor maps thread 0 arms and issues
   // one 2-D tensor copy per cube in issue_*.
+  // Producer duties sit on lane 0 of three different warps, so their issue costs (an expect_tx + tensor copy is a
+  // few hundred cycles) run side by side instead of queueing on one thread that the other 255 then wait for.
+  constexpr int kEpiTid = 32, kClaimTid = 64, kExpoTid = 96;
   auto arm_expo = [&](int item) {
+    if (tid != kExpoTid) return;
     int p0, npx;
     const DatasetDev* D = geom(item, p0, npx);
     if (!D->tmaps) mbar_arrive_expect_tx(&bars[0], (uint32_t)npx * 4u * (uint32_t)D->nT);
@@ -1067,7 +1080,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const DatasetDev* D = geom(item, p0, npx);
     const uint32_t row = (uint32_t)npx * 4u;
     if (D->tmaps) {  // one 2-D tensor copy of the whole [nT][128] box (out-of-range columns are zero filled)
-      if (tid == 0) {
+      if (tid == kExpoTid) {
         mbar_arrive_expect_tx(&bars[0], (uint32_t)kFoldTPX * 4u * (uint32_t)D->nT);
         tma_load_2d(es, D->tmaps, p0, 0, &bars[0], pol_stream);
       }
@@ -1080,6 +1093,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
       bulk_g2s_hint(es + t * kFoldTPX, expo + (size_t)t * PP + p0, row, &bars[0], pol_stream);
   };
   auto arm_epi = [&](int item) {
+    if (tid != kEpiTid) return;
     int p0, npx;
     const DatasetDev* D = geom(item, p0, npx);
     const uint32_t row = (uint32_t)npx * 4u;
@@ -1096,7 +1110,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const uint32_t row = (uint32_t)npx * 4u;
     const bool has_bkg = D->background && P.include_background;
     if (D->tmaps) {
-      if (tid == 0) {
+      if (tid == kEpiTid) {
         const unsigned char* tm = reinterpret_cast<const unsigned char*>(D->tmaps);
         const bool has_counts = D->counts != nullptr, has_mask = has_counts && D->mask;
         const uint32_t nR = (uint32_t)D->nR;
@@ -1130,7 +1144,8 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   // the next item, after the end-of-item barrier behind which every thread has tested the current phase -- so the
   // request can go out at the very top of an item.  (With one barrier for both buffers a request issued before the
   // item's first CTA barrier could complete two phases ahead of a slow thread, whose parity wait then never returns.)
-  auto fetch_desc = [&](int it, uint32_t buf) {  // thread 0: one bulk copy of work item `it`'s descriptor
+  auto fetch_desc = [&](int it, uint32_t buf) {  // one thread: one bulk copy of work item `it`'s descriptor
+    if (tid != kClaimTid) return;
     mbar_arrive_expect_tx(&bars[2 + buf], (uint32_t)DL.bytes);
     bulk_g2s(desc_s + buf * DL.bytes, P.desc + (size_t)it * DL.bytes, (uint32_t)DL.bytes, &bars[2 + buf]);
   };
@@ -1159,6 +1174,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   auto desc_nl = [&](int pos) -> int {  // number of register-resident sources of the item at worklist position pos
     return __ldg(reinterpret_cast<const int*>(P.desc + (size_t)pos * DL.bytes));
   };
+  const int* zero_i = reinterpret_cast<const int*>(P.zeros);
   // (Re)load the dataset table entry, its band-compressed edisp matrices and band table.  Block uniform.
   auto load_dataset = [&](int tile) {
     const int* src = reinterpret_cast<const int*>(P.ds + P.tile_ds[tile]);
@@ -1171,6 +1187,41 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     for (int i = tid; i < nb; i += kFoldThreads) band_s[i] = band[i];
   };
 
+  // Per-thread view of an item's sources: this thread's pixel quad and, per overlapping source, a pointer into its
+  // cutout; outside the cutout the pointer targets a zero word with stride 0, so phase 1 is branch free and its loads
+  // can all be in flight.
+  const int q = tid & 31, slot = tid >> 5;   // phase 1: 32 pixel quads x 8 energy slots
+  const int pp = tid & 63, cslot = tid >> 6;  // phase 2: 64 pixel pairs x 4 reco-chunk slots
+  // pointer / plane stride of source l of the descriptor in buffer `buf` at this thread's quad of item `which`
+  auto quad_view = [&](uint32_t buf, int which, const float* (&cptr)[kFoldLMax], int (&pstr)[kFoldLMax],
+                       int (&grp)[kFoldLMax], bool& qlive, int& qy, int& qx, int lmax) -> const DatasetDev* {
+    int p0, npx;
+    const DatasetDev* D = geom(which, p0, npx);
+    const unsigned char* dsc = desc_s + buf * DL.bytes;
+    const int nl = reinterpret_cast<const int*>(dsc)[0];
+    const InstDev* slist = reinterpret_cast<const InstDev*>(dsc + DL.inst);
+    const int nx = D->nx;
+    const int pq = p0 + 4 * q;
+    qlive = 4 * q < npx;
+    qy = pq / nx;
+    qx = pq - qy * nx;
+#pragma unroll
+    for (int l = 0; l < kFoldLMax; ++l) {
+      cptr[l] = P.zeros;
+      pstr[l] = 0;
+      grp[l] = 0;
+      if (l < lmax && l < nl && qlive) {
+        const InstDev& in = slist[l];
+        const int ly = qy - in.y0, lx = qx - in.x0a;
+        grp[l] = in.group;
+        if (ly >= 0 && ly < in.cy && lx >= 0 && lx < in.pitch && !(GPY_ABLATE & 1)) {
+          cptr[l] = in.conv + ly * in.pitch + lx;
+          pstr[l] = in.plane_stride;
+        }
+      }
+    }
+    return D;
+  };
   // Items are claimed two ahead: `item` is being computed, `next` has its copies in flight, and the claim of the one
   // after (an atomic on a global counter: ~1 us round trip) is issued at the top of an item and consumed at its end.
   int w = blockIdx.x;
@@ -1181,7 +1232,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     wn = w + gridDim.x;
     next = item_at(wn);
   } else {
-    if (tid == 0) {
+    if (tid == kClaimTid) {
       const int c = gridDim.x + atomicAdd(P.counter, 1u);
       nxt_s = make_int2(c, item_at(c));
     }
@@ -1195,11 +1246,9 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   }
   {
     const bool expo_first = desc_nl(w) > 0;  // source-free tiles do not fetch their exposure
-    if (tid == 0) {
-      if (expo_first) arm_expo(item);
-      arm_epi(item);
-      fetch_desc(w, 0);
-    }
+    if (expo_first) arm_expo(item);
+    arm_epi(item);
+    fetch_desc(w, 0);
     __syncthreads();
     if (expo_first) issue_expo(item);
     issue_epi(item);
@@ -1210,7 +1259,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   uint32_t it = 0;       // items done by this CTA: descriptor buffer it & 1, its mbarrier phase (it >> 1) & 1
   uint32_t eparity = 0;  // phase of the exposure barrier: flips on items that have sources only
 #ifdef GPY_FOLD_TIMING
-  long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
   long long cls_cyc[4] = {0, 0, 0, 0};
   int cls_n[4] = {0, 0, 0, 0};
@@ -1219,24 +1268,25 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
 #define GPY_TICK(i) do { } while (0)
 #endif
 
-  const int q = tid & 31, slot = tid >> 5;   // phase 1: 32 pixel quads x 8 energy slots
-  const int pp = tid & 63, cslot = tid >> 6;  // phase 2: 64 pixel pairs x 4 reco-chunk slots
-
   for (;; ++it) {
     const uint32_t parity = it & 1u;          // descriptor / per-step-number buffer of this item
     const uint32_t dphase = (it >> 1) & 1u;   // phase of that buffer's mbarrier
     const int b = DYNAMIC ? 0 : item % P.B;
     const int tile = DYNAMIC ? item : item / P.B;
     // claim the item after the next (consumed at the end of this item) and look up whether the next one has sources
+    // (nothing may depend on the two results here: their consumers sit behind the phases, so the ~1 us round trips
+    // are off the critical path)
     int wnn = 0, nn = n_items;
+    unsigned claim_raw = 0;
     if (!DYNAMIC) {
       wnn = wn + gridDim.x;
       nn = item_at(wnn);
-    } else if (tid == 0) {
-      wnn = gridDim.x + atomicAdd(P.counter, 1u);
+    } else if (tid == kClaimTid) {
+      claim_raw = atomicAdd(P.counter, 1u);
     }
-    const bool expo_next = next < n_items && desc_nl(wn) > 0;
-    if (tid == 0 && next < n_items) fetch_desc(wn, parity ^ 1u);
+    const int nl_next = __ldg(next < n_items ? reinterpret_cast<const int*>(P.desc + (size_t)wn * DL.bytes) : zero_i);
+#define expo_next (nl_next > 0)
+    if (next < n_items) fetch_desc(wn, parity ^ 1u);
     if (tile < Ds.tile_begin || tile >= Ds.tile_begin + Ds.n_tiles) {  // block uniform: first item of another dataset
       __syncthreads();  // nobody still reads the old entry (issue_epi of this item at the end of the last one)
       load_dataset(tile);
@@ -1263,28 +1313,10 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
 #ifdef GPY_FOLD_TIMING
     const long long t_item0 = clock64();
 #endif
-    // this thread's pixel quad and, per overlapping source, a pointer into its cutout; outside the cutout the
-    // pointer targets a zero word with stride 0, so phase 1 is branch free and its loads can all be in flight
-    const int pq = p0 + 4 * q;
-    const bool qlive = 4 * q < npx;
-    const int qy = pq / nx, qx = pq - qy * nx;
     const float* cptr[kFoldLMax];
-    int pstr[kFoldLMax], grp[kFoldLMax];
-#pragma unroll
-    for (int l = 0; l < kFoldLMax; ++l) {
-      cptr[l] = P.zeros;
-      pstr[l] = 0;
-      grp[l] = 0;
-      if (l < nl && qlive) {
-        const InstDev& in = slist[l];
-        const int ly = qy - in.y0, lx = qx - in.x0a;
-        grp[l] = in.group;
-        if (ly >= 0 && ly < in.cy && lx >= 0 && lx < in.pitch) {
-          cptr[l] = in.conv + ly * in.pitch + lx;
-          pstr[l] = in.plane_stride;
-        }
-      }
-    }
+    int pstr[kFoldLMax], grp[kFoldLMax], qy, qx;
+    bool qlive;
+    quad_view(parity, item, cptr, pstr, grp, qlive, qy, qx, kFoldLMax);
     double stat = 0.0;
     for (int cbase = 0; cbase < nchunks; cbase += 4) {  // one pass for nR <= 32
       const int c = cbase + cslot;
@@ -1294,7 +1326,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
 
       // No source reaches this tile: npred = background only; its exposure was never requested, so the buffer is
       // free for the next item's (armed here, issued behind the first barrier of the item).
-      if (nl == 0 && cbase == 0 && expo_next && tid == 0) arm_expo(next);
+      if (nl == 0 && cbase == 0 && expo_next) arm_expo(next);
       for (int t0 = 0; t0 < (nl > 0 ? nT : 0); t0 += kTmaTCH) {
         GPY_TICK(2);
         if (cbase == 0 && t0 == 0) mbar_wait(&bars[0], eparity);  // exposure tile has landed
@@ -1401,14 +1433,14 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         }
         GPY_TICK(4);
         const bool fetch_next = cbase + 4 >= nchunks && t0 + kTmaTCH >= nT && expo_next;
-        if (tid == 0 && fetch_next) arm_expo(next);
+        if (fetch_next) arm_expo(next);
         __syncthreads();
         GPY_TICK(5);
         // exposure tile fully consumed: start fetching the next item's while phase 2 / the epilogue run
         if (fetch_next) issue_expo(next);
         GPY_TICK(6);
         // ---- phase 2: acc[r] += pdf[t][r] * v[t][p] over the non-zero band ----
-        if (c < nchunks) {
+        if (c < nchunks && !(GPY_ABLATE & 2)) {
           for (int g = 0; g < G; ++g) {
             const int4 bnd = *reinterpret_cast<const int4*>(band + (g * nchunks + c) * 4);
             const int blo = bnd.x, bhi = bnd.y;
@@ -1464,6 +1496,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         }
       }
       __syncthreads();
+      GPY_TICK(12);
       if (nl == 0 && cbase == 0 && expo_next) issue_expo(next);
       // next item's per-step numbers: the loads are issued before the Cash pass and stored to shared memory after
       // it (few registers are live here), so the pass covers their latency; the end-of-item barrier publishes them
@@ -1474,6 +1507,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         if (tid < dyn_len) dyn0 = load_dyn(parity ^ 1u, tid);
         if (tid + kFoldThreads < dyn_len) dyn1 = load_dyn(parity ^ 1u, tid + kFoldThreads);
       }
+      GPY_TICK(13);
       {
         // Two neighbouring pixels per thread and iteration (npx is even: P % 16 == 0 on this path): one 128-bit load
         // of mu, one 64-bit load of the counts, one 16-bit load of the mask.  Most bins of a gamma-ray cube hold no
@@ -1486,7 +1520,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         // data-dependent branch, the two dependency chains interleave).  Separate accumulators for the mu and the
         // n log mu terms halve the fp64 add chain.
         double stat_mu = 0.0, stat_nl = 0.0;
-        for (int i = tid; i < nr * (kFoldTPX / 2); i += kFoldThreads) {
+        for (int i = tid; i < ((GPY_ABLATE & 4) ? 0 : nr * (kFoldTPX / 2)); i += kFoldThreads) {
           const int rr = i >> 6, lp = (i & (kFoldTPX / 2 - 1)) * 2;  // kFoldTPX == 128
           const bool live = lp < npx;
           const int r = r0 + rr;
@@ -1535,6 +1569,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         }
 #endif
       }
+      GPY_TICK(14);
       if (stage_next) {
         double* dst = dyn_s + (parity ^ 1u) * dyn_len;
         if (tid < dyn_len) dst[tid] = dyn0;
@@ -1547,9 +1582,10 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) stat += __shfl_xor_sync(0xffffffffu, stat, o);
     if ((tid & 31) == 0) wsum[tid >> 5] = stat;
-    if (tid == 0) {
-      if (next < n_items) arm_epi(next);
-      if (DYNAMIC) nxt_s = make_int2(wnn, item_at(wnn));
+    if (next < n_items) arm_epi(next);
+    if (DYNAMIC && tid == kClaimTid) {
+      const int c = gridDim.x + claim_raw;
+      nxt_s = make_int2(c, item_at(c));
     }
     __syncthreads();  // every warp is past its epilogue reads; list / bkgfac reuse in the next item
     if (tid == 0)     // fixed summation order; no warp can rewrite wsum before passing a barrier with thread 0
@@ -1578,10 +1614,11 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
 #endif
     if (done) break;
   }
+#undef expo_next
 #ifdef GPY_FOLD_TIMING
   if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 100))
-    printf("[fold timing] block %d: list %lld | sync-after-list %lld | misc %lld | expo wait %lld | phase1 %lld | phase syncs %lld | issue expo %lld | phase2 %lld | epi wait %lld | epilogue %lld | end barrier %lld | issue epi %lld\n",
-           blockIdx.x, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7], tacc[8], tacc[9], tacc[10], tacc[11]);
+    printf("[fold timing] block %d: list %lld | sync-after-list %lld | misc %lld | expo wait %lld | phase1 %lld | phase syncs %lld | issue expo %lld | phase2 %lld | epi wait %lld | park+barrier %lld | stage-next issue %lld | cash %lld | dyn store %lld | end barrier %lld | issue epi %lld\n",
+           blockIdx.x, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7], tacc[8], tacc[12], tacc[13], tacc[14], tacc[9], tacc[10], tacc[11]);
   if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 100 || blockIdx.x == 201))
     printf("[fold classes] block %d: no-source %d items %lld cyc | 1-2 sources %d items %lld cyc | 3-4 sources %d items %lld cyc | >4 sources %d items %lld cyc\n",
            blockIdx.x, cls_n[0], cls_cyc[0], cls_n[1], cls_cyc[1], cls_n[2], cls_cyc[2], cls_n[3], cls_cyc[3]);
