@@ -47,6 +47,9 @@ class OracleDatasets:
     def _get_engine(self):
         return self._engine
 
+    def stat_sum(self):
+        return self._engine.stat_sum()
+
     @property
     def parameters(self):
         return self.ds.models.parameters.unique_parameters
@@ -215,3 +218,64 @@ def test_prior_term_on_the_gpu_likelihood(ctx):
     index.prior = None
     Fit().run(datasets)
     assert free.success and abs(with_prior - 2.5) < abs(index.value - 2.5)   # pulled towards the prior mean
+
+
+def test_stat_array_per_bin_vs_oracle(ctx):
+    """SURVEY 8 a3'': ``MapDataset.stat_array`` (stats/fit_statistics.py:29-79, 295-298: per-bin Cash, no ``n > 0``
+    guard, truncation at 1e-25) from the GPU npred cube against ``oracle.cash.cash`` of the oracle's npred, bin by bin;
+    a zero-exposure corner puts bins on the truncation branch."""
+    from gammapy_b200 import Map, configs
+    from oracle import adapter, cash
+
+    ds = configs.make_c1(width=(2.0, 2.0), mask_radius=0.9)
+    ds.exposure.data[:, :12, :12] = 0.0
+    ds.background.data[:, :12, :12] = 0.0
+    ds.exposure = ds.exposure  # re-register the edited cubes
+    ds.background = ds.background
+    de = adapter.evaluator_for(ds, conv="exact64")
+    counts = de.fake(3)
+    ds.counts = Map.from_geom(ds._geom, data=counts, dtype=float)
+    want = cash.cash(counts, de.npred())
+    got = ds.stat_array()
+    assert got.shape == want.shape
+    assert np.all(want[:, :12, :12] == 2e-25)  # truncation branch: counts are 0 there, stat = 2 * 1e-25
+    # |d stat| = 2 |1 - n / mu| |d mu|: relative to the per-bin scale 2 (mu + n |log mu|)
+    scale = 2 * (np.maximum(de.npred(), 1e-25) + counts * np.abs(np.log(np.maximum(de.npred(), 1e-25))))
+    assert np.max(np.abs(got - want) / scale) < 1e-6
+    assert abs(got[ds.mask.data.astype(bool)].sum() - ds.stat_sum()) < 1e-3 + 1e-12 * abs(ds.stat_sum())
+
+
+def test_parameter_estimator_gpu_vs_oracle(ctx):
+    """SURVEY 8f N3 (estimators/parameter.py:108-286): best fit, delta(TS) against the null value, asymmetric errors and
+    upper limit of the source amplitude, GPU likelihood vs the oracle likelihood under the same estimator code."""
+    from gammapy_b200 import Datasets, Map, configs
+    from gammapy_b200.estimators import ParameterEstimator
+    from oracle import adapter
+
+    ds = configs.make_c1(width=(2.0, 2.0), mask_radius=0.9)
+    de = adapter.evaluator_for(ds, conv="exact64")
+    counts = de.fake(11)
+    de.ds.counts = counts
+    ds.counts = Map.from_geom(ds._geom, data=counts, dtype=float)
+    m = ds.models["model-simu"]
+    for p in (m.spatial_model.lon_0, m.spatial_model.lat_0, m.spatial_model.sigma):
+        p.frozen = True  # spectral fit: amplitude, index, background norm
+
+    def run(datasets):
+        m.spectral_model.amplitude.value = 1.2e-11
+        m.spectral_model.index.value = 2.9
+        ds.background_model.spectral_model.norm.value = 1.03
+        est = ParameterEstimator(selection_optional=["errn-errp", "ul"], null_value=0.0)
+        return est.run(datasets, m.spectral_model.amplitude)
+
+    gpu = run(Datasets([ds]))
+    cpu = run(OracleDatasets(ds, de))
+    print(gpu, cpu)
+    assert gpu["success"] and cpu["success"]
+    err = gpu["amplitude_err"]
+    assert abs(gpu["amplitude"] - cpu["amplitude"]) < 0.01 * err
+    assert_allclose(err, cpu["amplitude_err"], rtol=2e-2)
+    assert abs(gpu["stat"] - cpu["stat"]) < 1e-3
+    assert abs(gpu["ts"] - cpu["ts"]) < 2e-3
+    for key in ("amplitude_errp", "amplitude_errn", "amplitude_ul"):
+        assert_allclose(gpu[key], cpu[key], rtol=2e-2)
