@@ -60,6 +60,14 @@ class SourceState(C.Structure):
     ]
 
 
+class IrfMapsDesc(C.Structure):
+    _fields_ = [
+        ("nx", C.c_int32), ("ny", C.c_int32),
+        ("binsz", C.c_double), ("crval_lon", C.c_double), ("crpix_x", C.c_double), ("crpix_y", C.c_double),
+        ("n_rad", C.c_int32), ("rad_edges", C.c_void_p), ("psf_map", C.c_void_p), ("edisp_map", C.c_void_p),
+    ]
+
+
 # every symbol include/gpy_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -75,6 +83,9 @@ SYMBOLS = {
     "gpy_dataset_set_counts": (C.c_int, [_P, _P]),
     "gpy_dataset_set_models": (C.c_int, [_P, C.POINTER(SourceDesc), C.c_int32, C.POINTER(BackgroundDesc)]),
     "gpy_dataset_source_state": (C.c_int, [_P, C.c_int32, C.POINTER(SourceState)]),
+    "gpy_dataset_set_irf_maps": (C.c_int, [_P, C.POINTER(IrfMapsDesc)]),
+    "gpy_dataset_source_psf_kernel": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                                C.POINTER(C.c_int32)]),
     "gpy_stat_sum": (C.c_int, [_P, C.POINTER(_P), C.c_int32, _P, C.c_int32, C.c_int32, _P, _P]),
     "gpy_stat_sum_device": (C.c_int, [_P, C.POINTER(_P), C.c_int32, _P, C.c_int32, C.c_int32, _P]),
     "gpy_peer_reduce_bytes": (C.c_int64, [C.c_int32, C.c_int32]),

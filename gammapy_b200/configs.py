@@ -49,6 +49,36 @@ def make_dataset(width=(4.0, 4.0), binsz=0.02, n_reco=10, n_true=20, e_reco=(0.1
     return ds
 
 
+def zoned_irfs(ds, binsz_irf=1.0, psf_scale=(1.0, 1.8), edisp_sigma=(0.10, 0.22), edisp_bias=(0.0, 0.06)):
+    """Replace the IRFs of ``ds`` by maps on a coarse spatial grid with two zones split at the map's central meridian
+    (lon > centre: zone 0, else zone 1): the PSF width and the edisp resolution / bias differ between the zones, with
+    one transition column of IRF pixels in between for the (bilinear) PSF lookup.  Position-dependent IRFs as
+    ``PSFMap`` / ``EDispKernelMap`` of a real DL4 dataset carry them."""
+    geom = ds._geom
+    e_true = ds.exposure.geom.axes["energy_true"]
+    e_reco = geom.axes["energy"]
+    c = geom.center_skydir
+    ig = WcsGeom.create(skydir=(c.lon, c.lat), binsz=binsz_irf, width=tuple(geom.width), frame=geom.frame, proj="CAR")
+    coords = ig.get_coord()
+    dlon = (coords["lon"] - c.lon + 180.0) % 360.0 - 180.0
+    zone = np.where(dlon > 0, 0, 1)  # (ny, nx)
+    base = ds.psf  # position-independent Gaussian PSF of make_dataset
+    psf = np.empty(base.data.shape + zone.shape)
+    sig0 = np.exp(np.interp(np.log(e_true.center), np.log([e_true.edges[0], e_true.edges[-1]]), np.log([0.12, 0.04])))
+    rad_axis = base.rad_axis
+    for z in (0, 1):
+        prof = PSFMap.from_gauss(energy_axis_true=e_true, rad_axis=rad_axis, sigma=sig0 * psf_scale[z]).data
+        psf[..., zone == z] = prof[..., None]
+    ds.psf = PSFMap(e_true, rad_axis, psf, geom=ig)
+    ed = np.empty((e_true.nbin, e_reco.nbin) + zone.shape)
+    for z in (0, 1):
+        k = EDispKernelMap.from_gauss(energy_axis=e_reco, energy_axis_true=e_true, sigma=edisp_sigma[z],
+                                      bias=edisp_bias[z]).kernel.pdf_matrix
+        ed[..., zone == z] = k[..., None]
+    ds.edisp = EDispKernelMap(data=ed, geom=ig, axes=[e_true, e_reco])
+    return ds
+
+
 def c1_models(dataset_name="c1"):
     """analysis_3d tutorial shape: one Gaussian x PowerLaw + FoV background (simulate_3d.py:102-134)."""
     spatial = GaussianSpatialModel(lon_0="0.2 deg", lat_0="0.1 deg", sigma="0.3 deg", frame=FRAME)

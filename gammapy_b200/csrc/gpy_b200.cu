@@ -24,6 +24,7 @@
 #include "../../include/gpy_b200.h"
 #include "kernels.cuh"
 #include "tsmap.cuh"
+#include "irf.cuh"
 
 namespace {
 
@@ -242,6 +243,26 @@ struct Source {
   std::vector<Slot> slots = std::vector<Slot>(kSlotsPerSource);
   int last_f = 0;
   int n_spatial_evals = 0;
+  // position-dependent IRFs (gpy_dataset_set_irf_maps): this evaluator's own PSF kernel and edisp matrix, looked up
+  // at the source position by MapEvaluator.update (evaluator.py:196-227)
+  DevBuf p_kflip, p_planes, p_raw, p_kernel, p_jobs;
+  std::vector<gpy::ConvPlane> planes;
+  int psf_k = 0, max_h = 0, max_kw = 4;
+  int edisp_pix = -1;    // IRF pixel (iy * nx + ix) whose matrix this evaluator uses
+  int n_irf_updates = 0;
+  void release_irf() {
+    for (DevBuf* b : {&p_kflip, &p_planes, &p_raw, &p_kernel, &p_jobs}) b->release();
+  }
+};
+
+struct IrfMaps {  // PSFMap / EDispKernelMap with a spatial grid (host copies; the maps are small)
+  bool has_psf = false, has_edisp = false;
+  GeomH geom{0, 0, 0.0, 0.0, 0.0, 0.0};
+  int n_rad = 0;
+  std::vector<double> rad_edges, rad_center;
+  std::vector<float> psf;     // [nT][n_rad][ny][nx]
+  std::vector<double> edisp;  // [nT][nR][ny][nx]
+  DevBuf d_rad_center;
 };
 
 }  // namespace
@@ -324,7 +345,6 @@ struct gpy_dataset {
   const float* weight = nullptr;
   std::vector<uint8_t> mask_image;  // empty = all true
   DevBuf d_edges, d_nodes, d_ecenter, d_edisp, d_band, d_pdfc, d_omega, d_kflip, d_planes;
-  int pdfc_rows[2] = {0, 0};  // band-compressed rows when 1 / 2 edisp groups are in use
   DevBuf d_tmaps;             // 4 CUtensorMap: exposure, background, counts, mask (2-D [rows][P] tensors, box [rows][128])
   std::vector<DevBuf> retired_tmaps;  // earlier map blocks: a rewritten map gets a NEW address (descriptor caches)
   bool has_tmaps = false;
@@ -334,6 +354,10 @@ struct gpy_dataset {
   int groups_used = 1;  // 2 when some source opts out of the edisp (diagonal response)
   std::vector<Source> sources;
   gpy_background_desc bkg{0, -1, -1, -1};
+  IrfMaps irf;
+  std::vector<double> h_edisp, h_diag;  // host copies of the static matrices (group tables are rebuilt from them)
+  std::vector<int> group_codes;         // matrix behind every edisp group: -2 dataset edisp, -1 diagonal, >= 0 IRF pixel
+  std::vector<int> pdfc_rows_cum;       // band-compressed rows up to and including group g
 };
 
 namespace {
@@ -572,10 +596,224 @@ int build_tmaps(gpy_dataset* ds) {
   return GPY_OK;
 }
 
+// Edisp groups of a dataset: matrices [G][nT][nRp] with the reco axis zero padded to a multiple of 8, the non-zero
+// band of every (group, reco chunk) and the band-compressed copy the staged fold kernel keeps in shared memory.
+// `mats[g]` is a HOST [nT][nR] matrix.
+int build_edisp_tables(gpy_dataset* ds, const std::vector<const double*>& mats) {
+  const int G = (int)mats.size(), nT = ds->nT, nR = ds->nR, nRp = ds->nRp;
+  const int nchunks = nRp / 8;
+  std::vector<double> ed((size_t)G * nT * nRp, 0.0);
+  std::vector<int> band((size_t)G * nchunks * 4, 0);
+  std::vector<double> pdfc;
+  ds->pdfc_rows_cum.assign(G, 0);
+  for (int gi = 0; gi < G; ++gi) {
+    const double* src = mats[gi];
+    auto at = [&](int t, int r) { return src[(size_t)t * nR + r]; };
+    for (int t = 0; t < nT; ++t)
+      for (int r = 0; r < nR; ++r) ed[((size_t)gi * nT + t) * nRp + r] = at(t, r);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      int lo = nT, hi = 0;
+      for (int t = 0; t < nT; ++t)
+        for (int r = 8 * ch; r < std::min(8 * ch + 8, nR); ++r) {
+          double v = at(t, r);
+          if (v != 0.0) {  // NaN counts as non-zero
+            lo = std::min(lo, t);
+            hi = std::max(hi, t + 1);
+          }
+        }
+      if (lo > hi) lo = hi = 0;
+      int* b4 = &band[((size_t)gi * nchunks + ch) * 4];
+      b4[0] = lo;
+      b4[1] = hi;
+      b4[2] = (int)(pdfc.size() / 8);  // first row of this chunk in the band-compressed matrix
+      for (int t = lo; t < hi; ++t)
+        for (int j = 0; j < 8; ++j) {
+          const int r = 8 * ch + j;
+          pdfc.push_back(r < nR ? at(t, r) : 0.0);
+        }
+    }
+    ds->pdfc_rows_cum[gi] = (int)(pdfc.size() / 8);
+  }
+  if (pdfc.empty()) pdfc.resize(8, 0.0);
+  cudaStream_t s = ds->ctx->stream;
+  // new buffers: kernels of earlier calls may still read the old tables (stream order frees them afterwards)
+  DevBuf n_pdfc, n_ed, n_band;
+  GPY_TRY(n_pdfc.reserve(pdfc.size() * sizeof(double), s));
+  GPY_TRY(n_ed.reserve(ed.size() * sizeof(double), s));
+  GPY_TRY(n_band.reserve(band.size() * sizeof(int), s));
+  CUDA_TRY(cudaMemcpyAsync(n_pdfc.p, pdfc.data(), pdfc.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(n_ed.p, ed.data(), ed.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(n_band.p, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));  // the staging vectors go out of scope
+  ds->d_pdfc.release();
+  ds->d_edisp.release();
+  ds->d_band.release();
+  ds->d_pdfc = n_pdfc;
+  ds->d_edisp = n_ed;
+  ds->d_band = n_band;
+  ds->n_groups = G;
+  return GPY_OK;
+}
+
+// ---- IRF lookup at a source position -------------------------------------------------------------
+// Fractional pixel of the IRF grid, clamped to the grid (PSFMap._get_nearest_valid_position keeps the lookup inside).
+void irf_pixel(const IrfMaps& m, double lon, double lat, double& px, double& py) {
+  world_to_pix(m.geom, lon, lat, px, py);
+  px = std::min(std::max(px, 0.0), m.geom.nx - 1.0);
+  py = std::min(std::max(py, 0.0), m.geom.ny - 1.0);
+}
+
+// PSF.containment_radius (irf/psf/core.py:39-87) on the profile of one position: containment = cumulative sum of
+// psf * bin width * 2 pi rad (IRF.cumsum, irf/core.py:358-390) at the upper bin edges, linear interpolation with 0
+// outside the nodes, argmin of |containment - fraction| on the 20 x upsampled rad axis.
+void containment_radius_h(const IrfMaps& m, const std::vector<double>& profile, int nT, double fraction,
+                          std::vector<double>& out) {
+  const int n = m.n_rad, factor = 20, n_up = n * factor;
+  const std::vector<double>& e = m.rad_edges;
+  out.assign(nT, 0.0);
+  std::vector<double> cum(n);
+  const double step = (e[n] - e[0]) / n_up;
+  for (int t = 0; t < nT; ++t) {
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) {
+      acc += profile[(size_t)t * n + k] * ((e[k + 1] - e[k]) * kDegH) * (2 * M_PI * m.rad_center[k] * kDegH);
+      cum[k] = acc;
+    }
+    double best = std::numeric_limits<double>::infinity(), best_rad = 0.0;
+    int seg = 0;
+    for (int i = 0; i < n_up; ++i) {
+      const double lo = i == 0 ? e[0] : e[0] + i * step, hi = i + 1 == n_up ? e[n] : e[0] + (i + 1) * step;
+      const double rad = 0.5 * (lo + hi);
+      double cont;  // np.interp(rad, nodes = edges[1:], cum, left=0, right=0)
+      if (rad < e[1] || rad > e[n]) {
+        cont = 0.0;
+      } else {
+        while (seg + 2 < n + 1 && rad > e[seg + 2]) ++seg;  // nodes[seg] = e[seg + 1] <= rad <= nodes[seg + 1]
+        if (seg + 1 >= n) {
+          cont = cum[n - 1];
+        } else {
+          const double x0 = e[seg + 1], x1 = e[seg + 2];
+          cont = cum[seg] + (cum[seg + 1] - cum[seg]) * ((rad - x0) / (x1 - x0));
+        }
+      }
+      const double dist = std::fabs(cont - fraction);
+      if (dist < best) {  // np.argmin: first minimum
+        best = dist;
+        best_rad = rad;
+      }
+    }
+    out[t] = best_rad;
+  }
+}
+
+// PSFMap.get_psf_kernel(position, geom, containment=0.999) (irf/psf/map.py:249-337) for one evaluator: profile and
+// containment radii on the host (a few thousand numbers), the oversampled kernel images, their normalisation and the
+// stencil layout on the device (psf_extract_kernel).
+int extract_psf(gpy_dataset* ds, Source& src, double lon, double lat) {
+  gpy_context* c = ds->ctx;
+  const IrfMaps& m = ds->irf;
+  const int nT = ds->nT, n = m.n_rad, inx = m.geom.nx, iny = m.geom.ny;
+  double px, py;
+  irf_pixel(m, lon, lat, px, py);
+  const int x0 = (int)std::min(std::floor(px), (double)std::max(inx - 2, 0));
+  const int y0 = (int)std::min(std::floor(py), (double)std::max(iny - 2, 0));
+  const int x1 = std::min(x0 + 1, inx - 1), y1 = std::min(y0 + 1, iny - 1);
+  const double tx = px - x0, ty = py - y0;
+  std::vector<double> profile((size_t)nT * n);
+  const size_t plane = (size_t)inx * iny;
+  for (int t = 0; t < nT; ++t)
+    for (int k = 0; k < n; ++k) {
+      const float* q = m.psf.data() + ((size_t)t * n + k) * plane;
+      profile[(size_t)t * n + k] = (1 - ty) * ((1 - tx) * (double)q[(size_t)y0 * inx + x0] + tx * (double)q[(size_t)y0 * inx + x1]) +
+                                   ty * ((1 - tx) * (double)q[(size_t)y1 * inx + x0] + tx * (double)q[(size_t)y1 * inx + x1]);
+    }
+  std::vector<double> r999, r68;
+  containment_radius_h(m, profile, nT, 0.999, r999);
+  containment_radius_h(m, profile, nT, 0.68, r68);
+  const double binsz = ds->geom.binsz;
+  const double max_radius = *std::max_element(r999.begin(), r999.end());
+  const int K = (int)round_up_to_odd(2 * max_radius / binsz);
+  std::vector<gpy::PsfPlaneJob> jobs(nT);
+  std::vector<int> raw_off(nT);
+  src.planes.assign(nT, gpy::ConvPlane{0, 4, 0, 0});
+  int koff = 0, roff = 0;
+  src.max_h = 0;
+  src.max_kw = 4;
+  for (int t = 0; t < nT; ++t) {
+    const double base = 2 * r68[t] / binsz;
+    // np.minimum(int(np.ceil(precision_factor / base_factor)), PSF_MAX_OVERSAMPLING); base 0 -> ceil(inf) raises in
+    // the reference (OverflowError): refuse it here as well
+    if (!(base > 0)) return fail(GPY_ERR_INVALID, "PSF map: zero 68 %% containment radius in true-energy bin %d", t);
+    const int f = (int)std::min(std::ceil(12.0 / base), 4.0);
+    const int nt = std::min((int)round_up_to_odd(2 * r999[t] / binsz), K);
+    const int h = (nt - 1) / 2, kw = (nt + 3) / 4 * 4;
+    jobs[t] = gpy::PsfPlaneJob{nt, f, koff, kw};
+    src.planes[t] = gpy::ConvPlane{h, kw, koff, 0};
+    raw_off[t] = roff;
+    koff += nt * kw;
+    roff += nt * nt;
+    src.max_h = std::max(src.max_h, h);
+    src.max_kw = std::max(src.max_kw, kw);
+  }
+  src.psf_k = K;
+  cudaStream_t st = c->stream;
+  // fresh buffers every time: slots convolved with the previous kernel may still be read by queued launches
+  for (DevBuf* b : {&src.p_kflip, &src.p_planes, &src.p_raw, &src.p_kernel, &src.p_jobs}) {
+    if (b->p) CUDA_TRY(cudaStreamSynchronize(st));
+    b->release();
+  }
+  const size_t job_bytes = jobs.size() * sizeof(gpy::PsfPlaneJob), off_bytes = raw_off.size() * sizeof(int),
+               prof_bytes = profile.size() * sizeof(double);
+  const size_t o_off = (job_bytes + 15) / 16 * 16, o_prof = (o_off + off_bytes + 15) / 16 * 16;
+  std::vector<uint8_t> blob(o_prof + prof_bytes);
+  std::memcpy(blob.data(), jobs.data(), job_bytes);
+  std::memcpy(blob.data() + o_off, raw_off.data(), off_bytes);
+  std::memcpy(blob.data() + o_prof, profile.data(), prof_bytes);
+  GPY_TRY(upload_to(src.p_jobs, blob.data(), blob.size(), st));
+  GPY_TRY(upload_to(src.p_planes, src.planes.data(), src.planes.size() * sizeof(gpy::ConvPlane), st));
+  GPY_TRY(src.p_kflip.reserve((size_t)std::max(koff, 1) * sizeof(float)));
+  GPY_TRY(src.p_raw.reserve((size_t)std::max(roff, 1) * sizeof(double)));
+  GPY_TRY(src.p_kernel.reserve((size_t)nT * K * K * sizeof(float)));
+  CUDA_TRY(cudaMemsetAsync(src.p_kflip.p, 0, (size_t)std::max(koff, 1) * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(src.p_kernel.p, 0, (size_t)nT * K * K * sizeof(float), st));
+  gpy::PsfExtractParams q;
+  q.jobs = (const gpy::PsfPlaneJob*)src.p_jobs.p;
+  q.raw_off = (const int*)((const uint8_t*)src.p_jobs.p + o_off);
+  q.profile = (const double*)((const uint8_t*)src.p_jobs.p + o_prof);
+  q.rad_center = (const double*)m.d_rad_center.p;
+  q.n_rad = n;
+  q.n_planes = nT;
+  q.binsz = binsz;
+  // centre of the kernel geometry = centre of the dataset geometry (geom.to_odd_npix keeps center_skydir)
+  q.lon_c = ds->geom.crval_lon - binsz * ((ds->geom.nx - 1) / 2.0 + 1.0 - ds->geom.crpix_x);
+  q.lat_c = binsz * ((ds->geom.ny - 1) / 2.0 + 1.0 - ds->geom.crpix_y);
+  q.raw = (double*)src.p_raw.p;
+  q.kflip = (float*)src.p_kflip.p;
+  q.kernel = (float*)src.p_kernel.p;
+  q.K = K;
+  gpy::psf_extract_kernel<<<nT, 256, (2 * n + 256) * sizeof(double), st>>>(q);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(st));  // the host blob goes out of scope
+  src.n_irf_updates++;
+  return GPY_OK;
+}
+
+// EDispKernelMap.get_edisp_kernel(position) (irf/edisp/map.py:369-401 -> to_region_nd_map with a point region:
+// interp_by_coord(method="nearest")): the matrix of the nearest IRF pixel.
+int edisp_pixel_at(const IrfMaps& m, double lon, double lat) {
+  double px, py;
+  irf_pixel(m, lon, lat, px, py);
+  const int i = std::min(std::max((int)std::floor(px + 0.5), 0), m.geom.nx - 1);
+  const int j = std::min(std::max((int)std::floor(py + 0.5), 0), m.geom.ny - 1);
+  return j * m.geom.nx + i;
+}
+
 // MapEvaluator.update geometry (evaluator.py:174-243) for spatial parameters `sp`.
 int evaluator_update(const gpy_dataset* ds, const Source& src, const double* sp, Rect& rect, bool& contributes) {
   const int type = src.desc.spatial_type;
-  const double psf_width = ds->has_psf ? ds->geom.binsz * ds->psf_k : 0.0;  // np.max(kernel geom width)
+  const int psf_k = ds->irf.has_psf ? src.psf_k : ds->psf_k;  // this evaluator's own kernel when the PSF map has a grid
+  const double psf_width = ds->has_psf ? ds->geom.binsz * psf_k : 0.0;  // np.max(kernel geom width)
   const double radius = evaluation_radius(type, sp);
   const double cutout_width = psf_width + 2 * (radius + kCutoutMargin);  // evaluator.py:169-172
   // SkyModel.contributes(mask, margin=psf_width) (cube.py:246-286)
@@ -643,9 +881,14 @@ int get_slot(gpy_dataset* ds, Source& src, const double* sp, const Rect& rect, u
                           (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f));
   if (conv) {
     if (img * ds->nT * sizeof(float) > s.conv.cap) GPY_TRY(s.conv.reserve(img_cap * ds->nT * sizeof(float), c->stream));
-    GPY_TRY(launch_conv(c, (const float*)s.w.p, rect.cy, rect.cx, s.pitch, rect.x0 - s.x0a,
-                        (const float*)ds->d_kflip.p, (const gpy::ConvPlane*)ds->d_planes.p, ds->nT, ds->max_h,
-                        ds->max_kw, (float*)s.conv.p));
+    if (ds->irf.has_psf)
+      GPY_TRY(launch_conv(c, (const float*)s.w.p, rect.cy, rect.cx, s.pitch, rect.x0 - s.x0a,
+                          (const float*)src.p_kflip.p, (const gpy::ConvPlane*)src.p_planes.p, ds->nT, src.max_h,
+                          src.max_kw, (float*)s.conv.p));
+    else
+      GPY_TRY(launch_conv(c, (const float*)s.w.p, rect.cy, rect.cx, s.pitch, rect.x0 - s.x0a,
+                          (const float*)ds->d_kflip.p, (const gpy::ConvPlane*)ds->d_planes.p, ds->nT, ds->max_h,
+                          ds->max_kw, (float*)s.conv.p));
   }
   s.key.assign(sp, sp + nsp);
   s.valid = true;
@@ -819,7 +1062,6 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     dd.nT = ds->nT;
     dd.nR = ds->nR;
     dd.nRp = ds->nRp;
-    dd.n_groups = ds->groups_used;
     dd.P = (long long)ds->geom.nx * ds->geom.ny;
     dd.tile_begin = n_tiles;
     dd.n_tiles = (int)((dd.P + gpy::kFoldTPX - 1) / gpy::kFoldTPX);
@@ -829,11 +1071,6 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     dd.counts = rq.npred_out ? nullptr : ds->counts;
     dd.mask = ds->mask;
     dd.weight = ds->weight;
-    dd.edisp = (const double*)ds->d_edisp.p;
-    dd.band = (const int*)ds->d_band.p;
-    dd.pdfc = (const double*)ds->d_pdfc.p;
-    dd.pdfc_rows = ds->pdfc_rows[ds->groups_used - 1];
-    max_pdfc_rows = std::max(max_pdfc_rows, dd.pdfc_rows);
     dd.ecenter = (const double*)ds->d_ecenter.p;
     dd.tmaps = ds->has_tmaps ? ds->d_tmaps.p : nullptr;
     if (!rq.npred_out && !ds->counts) return fail(GPY_ERR_INVALID, "dataset %d has no counts: stat undefined", d);
@@ -895,6 +1132,19 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
           }
         }
         if (needs_update) {
+          if (ds->irf.has_psf || ds->irf.has_edisp) {
+            // the evaluator looks its IRFs up at the new position (evaluator.py:196-227) before sizing its cutout
+            if (!sequential)
+              return fail(GPY_ERR_UNSUPPORTED,
+                          "a vector of a batched call moves a source beyond its IRF support (MapEvaluator.update): "
+                          "evaluate that point as a single vector first");
+            if (ds->irf.has_edisp) src.edisp_pix = edisp_pixel_at(ds->irf, sp[0], sp[1]);
+            if (ds->irf.has_psf) {  // (whatever apply_irf says: update() looks the kernel up, the width uses it)
+              GPY_TRY(extract_psf(ds, src, sp[0], sp[1]));
+              for (auto& sl : src.slots) sl.valid = false;  // convolved with the previous kernel
+              ds->version = ++c->stamp;
+            }
+          }
           GPY_TRY(evaluator_update(ds, src, sp, rect, contributes));
           initialised = true;
         }
@@ -927,6 +1177,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         in.pitch = slot->pitch;
         in.planes = slot->planes;
         in.group = (src.desc.apply_edisp || !ds->has_diag) ? 0 : 1;
+        if (ds->irf.has_edisp) in.group = (src.desc.apply_edisp || !ds->has_diag) ? src.edisp_pix : -1;  // matrix code, remapped below
         in.plane_stride = slot->planes == 1 ? 0 : rect.cy * slot->pitch;
         in.conv = (const float*)(slot->planes == 1 ? slot->w.p : slot->conv.p);
         // Equal spectral tuples of one source across the vectors of a batch share one flux vector: K0 integrates it
@@ -1007,6 +1258,49 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       }
       ev.diff_count = (int)diffs.size() - ev.diff_begin;
     }
+    if (ds->irf.has_edisp) {
+      // Position-dependent edisp: the instances carry the code of their matrix (nearest IRF pixel, -1 diagonal).  The
+      // distinct codes of this call are the dataset's edisp groups; the tables are rebuilt when the set changes.
+      const size_t i0 = (size_t)evals[(size_t)d * B].inst_begin;
+      std::vector<int> codes;
+      for (size_t i = i0; i < insts.size(); ++i)
+        if (std::find(codes.begin(), codes.end(), insts[i].group) == codes.end()) codes.push_back(insts[i].group);
+      std::sort(codes.begin(), codes.end());
+      if (!codes.empty()) {
+        if (codes.size() > 4)
+          return fail(GPY_ERR_UNSUPPORTED, "the sources of dataset %d use %zu different edisp matrices (IRF pixels); "
+                      "at most 4 per dataset are supported", d, codes.size());
+        if (codes != ds->group_codes) {
+          const size_t plane = (size_t)ds->irf.geom.nx * ds->irf.geom.ny;
+          // one strided view per group would need per-group strides: gather the matrices contiguously instead
+          std::vector<std::vector<double>> gathered(codes.size());
+          std::vector<const double*> mats(codes.size());
+          for (size_t g = 0; g < codes.size(); ++g) {
+            if (codes[g] < 0) {
+              mats[g] = ds->h_diag.data();
+            } else {
+              gathered[g].resize((size_t)ds->nT * ds->nR);
+              for (int t = 0; t < ds->nT; ++t)
+                for (int r = 0; r < ds->nR; ++r)
+                  gathered[g][(size_t)t * ds->nR + r] = ds->irf.edisp[((size_t)t * ds->nR + r) * plane + codes[g]];
+              mats[g] = gathered[g].data();
+            }
+          }
+          GPY_TRY(build_edisp_tables(ds, mats));
+          ds->group_codes = codes;
+          ds->version = ++c->stamp;
+        }
+        ds->groups_used = (int)codes.size();
+        for (size_t i = i0; i < insts.size(); ++i)
+          insts[i].group = (int)(std::find(codes.begin(), codes.end(), insts[i].group) - codes.begin());
+      }
+    }
+    dd.n_groups = ds->groups_used;
+    dd.edisp = (const double*)ds->d_edisp.p;
+    dd.band = (const int*)ds->d_band.p;
+    dd.pdfc = (const double*)ds->d_pdfc.p;
+    dd.pdfc_rows = ds->pdfc_rows_cum[ds->groups_used - 1];
+    max_pdfc_rows = std::max(max_pdfc_rows, dd.pdfc_rows);
     max_nT = std::max(max_nT, ds->nT);
     max_nR = std::max(max_nR, ds->nR);
     max_nRp = std::max(max_nRp, ds->nRp);
@@ -1493,42 +1787,15 @@ int gpy_dataset_create(gpy_context_t* c, const gpy_dataset_desc* desc, gpy_datas
   if ((rc = upload_to(ds->d_edges, desc->energy_true_edges, (ds->nT + 1) * sizeof(double), s))) return cleanup(rc);
   if ((rc = upload_to(ds->d_ecenter, desc->energy_reco_center, ds->nR * sizeof(double), s))) return cleanup(rc);
   if ((rc = upload_to(ds->d_nodes, desc->nodes, (size_t)ds->nT * ds->n_nodes * sizeof(double), s))) return cleanup(rc);
-  // edisp groups, reco axis zero padded to a multiple of 8, and the non-zero band per reco chunk
-  const int nchunks = ds->nRp / 8;
-  std::vector<double> ed((size_t)ds->n_groups * ds->nT * ds->nRp, 0.0);
-  std::vector<int> band((size_t)ds->n_groups * nchunks * 4, 0);
-  std::vector<double> pdfc;
-  for (int gi = 0; gi < ds->n_groups; ++gi) {
-    const double* src = gi == 0 ? desc->edisp : desc->edisp_diagonal;
-    for (int t = 0; t < ds->nT; ++t)
-      for (int r = 0; r < ds->nR; ++r) ed[((size_t)gi * ds->nT + t) * ds->nRp + r] = src[(size_t)t * ds->nR + r];
-    for (int ch = 0; ch < nchunks; ++ch) {
-      int lo = ds->nT, hi = 0;
-      for (int t = 0; t < ds->nT; ++t)
-        for (int r = 8 * ch; r < std::min(8 * ch + 8, ds->nR); ++r) {
-          double v = src[(size_t)t * ds->nR + r];
-          if (v != 0.0) {  // NaN counts as non-zero
-            lo = std::min(lo, t);
-            hi = std::max(hi, t + 1);
-          }
-        }
-      if (lo > hi) lo = hi = 0;
-      int* b4 = &band[((size_t)gi * nchunks + ch) * 4];
-      b4[0] = lo;
-      b4[1] = hi;
-      b4[2] = (int)(pdfc.size() / 8);  // first row of this chunk in the band-compressed matrix
-      for (int t = lo; t < hi; ++t)
-        for (int j = 0; j < 8; ++j) {
-          const int r = 8 * ch + j;
-          pdfc.push_back(r < ds->nR ? src[(size_t)t * ds->nR + r] : 0.0);
-        }
-    }
-    ds->pdfc_rows[gi] = (int)(pdfc.size() / 8);
+  ds->h_edisp.assign(desc->edisp, desc->edisp + (size_t)ds->nT * ds->nR);
+  ds->group_codes.assign(1, -2);
+  std::vector<const double*> mats{ds->h_edisp.data()};
+  if (ds->has_diag) {
+    ds->h_diag.assign(desc->edisp_diagonal, desc->edisp_diagonal + (size_t)ds->nT * ds->nR);
+    ds->group_codes.push_back(-1);
+    mats.push_back(ds->h_diag.data());
   }
-  if (pdfc.empty()) pdfc.resize(8, 0.0);
-  if ((rc = upload_to(ds->d_pdfc, pdfc.data(), pdfc.size() * sizeof(double), s))) return cleanup(rc);
-  if ((rc = upload_to(ds->d_edisp, ed.data(), ed.size() * sizeof(double), s))) return cleanup(rc);
-  if ((rc = upload_to(ds->d_band, band.data(), band.size() * sizeof(int), s))) return cleanup(rc);
+  if ((rc = build_edisp_tables(ds, mats))) return cleanup(rc);
   std::vector<float> kflip;
   if (desc->psf_kernel) {
     ds->has_psf = true;
@@ -1556,6 +1823,8 @@ int gpy_dataset_destroy(gpy_dataset_t* ds) {
   for (DevBuf* b : {&ds->d_edges, &ds->d_nodes, &ds->d_ecenter, &ds->d_edisp, &ds->d_band, &ds->d_pdfc, &ds->d_tmaps, &ds->d_omega, &ds->d_kflip,
                     &ds->d_planes})
     b->release();
+  ds->irf.d_rad_center.release();
+  for (auto& src : ds->sources) src.release_irf();
   for (auto& src : ds->sources)
     for (auto& sl : src.slots) {
       sl.w.release();
@@ -1586,11 +1855,13 @@ int gpy_dataset_set_models(gpy_dataset_t* ds, const gpy_source_desc* sources, in
   }
   cudaSetDevice(ds->ctx->device);
   cudaStreamSynchronize(ds->ctx->stream);
-  for (auto& src : ds->sources)
+  for (auto& src : ds->sources) {
     for (auto& sl : src.slots) {
       sl.w.release();
       sl.conv.release();
     }
+    src.release_irf();
+  }
   ds->sources.clear();
   ds->sources.resize(n_sources);
   ds->groups_used = 1;
@@ -1602,6 +1873,67 @@ int gpy_dataset_set_models(gpy_dataset_t* ds, const gpy_source_desc* sources, in
     ds->bkg = *background;
   else
     ds->bkg = gpy_background_desc{0, -1, -1, -1};
+  return GPY_OK;
+}
+
+int gpy_dataset_set_irf_maps(gpy_dataset_t* ds, const gpy_irf_maps_desc* desc) {
+  if (!ds || !desc) return fail(GPY_ERR_INVALID, "NULL argument to gpy_dataset_set_irf_maps");
+  if (!desc->psf_map && !desc->edisp_map) return fail(GPY_ERR_INVALID, "neither a PSF map nor an edisp map given");
+  if (desc->nx <= 0 || desc->ny <= 0 || !(desc->binsz > 0))
+    return fail(GPY_ERR_INVALID, "bad IRF grid %d x %d, binsz %g", desc->nx, desc->ny, desc->binsz);
+  if (desc->psf_map && (desc->n_rad < 2 || !desc->rad_edges))
+    return fail(GPY_ERR_INVALID, "a PSF map needs rad_edges with at least two bins");
+  gpy_context* c = ds->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  IrfMaps& m = ds->irf;
+  m.geom = GeomH{desc->nx, desc->ny, desc->binsz, desc->crval_lon, desc->crpix_x, desc->crpix_y};
+  const size_t plane = (size_t)desc->nx * desc->ny;
+  m.has_psf = desc->psf_map != nullptr;
+  m.has_edisp = desc->edisp_map != nullptr;
+  if (m.has_psf) {
+    m.n_rad = desc->n_rad;
+    m.rad_edges.assign(desc->rad_edges, desc->rad_edges + desc->n_rad + 1);
+    m.rad_center.resize(desc->n_rad);
+    for (int k = 0; k < desc->n_rad; ++k) {
+      if (!(m.rad_edges[k + 1] > m.rad_edges[k])) return fail(GPY_ERR_INVALID, "rad_edges must increase");
+      m.rad_center[k] = 0.5 * (m.rad_edges[k] + m.rad_edges[k + 1]);
+    }
+    m.psf.assign(desc->psf_map, desc->psf_map + (size_t)ds->nT * desc->n_rad * plane);
+    GPY_TRY(upload_to(m.d_rad_center, m.rad_center.data(), m.rad_center.size() * sizeof(double), c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    ds->has_psf = true;
+  }
+  if (m.has_edisp) m.edisp.assign(desc->edisp_map, desc->edisp_map + (size_t)ds->nT * ds->nR * plane);
+  // every evaluator looks its IRFs up again at its next evaluation (as after MapDataset.models = ...)
+  for (auto& src : ds->sources) {
+    src.initialised = false;
+    src.contributes = true;
+    src.has_cached_spatial = false;
+    src.cached_lon = src.cached_lat = 0.0;
+    for (auto& sl : src.slots) sl.valid = false;
+  }
+  ds->version = ++c->stamp;
+  return GPY_OK;
+}
+
+int gpy_dataset_source_psf_kernel(const gpy_dataset_t* ds, int32_t source, float* kernel, int32_t capacity, int32_t* k,
+                                  int32_t* edisp_pixel, int32_t* n_updates) {
+  if (!ds || !k) return fail(GPY_ERR_INVALID, "NULL argument");
+  if (source < 0 || source >= (int)ds->sources.size()) return fail(GPY_ERR_INVALID, "source index out of range");
+  const Source& s = ds->sources[source];
+  *k = ds->irf.has_psf ? s.psf_k : ds->psf_k;
+  if (edisp_pixel) *edisp_pixel = ds->irf.has_edisp ? s.edisp_pix : -1;
+  if (n_updates) *n_updates = s.n_irf_updates;
+  if (kernel) {
+    if (!ds->irf.has_psf || !s.p_kernel.p)
+      return fail(GPY_ERR_INVALID, "source %d has no position-dependent PSF kernel (yet)", source);
+    const size_t n = (size_t)ds->nT * s.psf_k * s.psf_k;
+    if ((size_t)capacity < n) return fail(GPY_ERR_INVALID, "kernel buffer too small: %d < %zu floats", capacity, n);
+    CUDA_TRY(cudaSetDevice(ds->ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(kernel, s.p_kernel.p, n * sizeof(float), cudaMemcpyDeviceToHost, ds->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ds->ctx->stream));
+  }
   return GPY_OK;
 }
 

@@ -298,6 +298,14 @@ class MapDataset:
         eng = self._get_engine()
         return eng.source_state(0, self._source_names.index(model_name))
 
+    def evaluator_irf(self, model_name, with_kernel=True):
+        """IRFs one model's evaluator looked up at its position (datasets with a PSFMap / EDispKernelMap on a spatial
+        grid; MapEvaluator.update, datasets/evaluator.py:196-227): dict with the PSF kernel ``(nT, K, K)``, its side
+        ``k``, the IRF pixel ``edisp_pixel`` (iy * nx + ix) of the edisp matrix and the number of look-ups."""
+        self._get_engine()
+        kernel, k, pix, n = self._device.source_irf(self._source_names.index(model_name), with_kernel)
+        return {"psf_kernel": kernel, "k": k, "edisp_pixel": pix, "n_updates": n}
+
     # -- construction --------------------------------------------------------------------------------------------------
     @classmethod
     def create(cls, geom, energy_axis_true=None, migra_axis=None, rad_axis=None, binsz_irf=0.2,

@@ -90,7 +90,9 @@ class DeviceDataset:
             desc.mask = self._to_device("mask", mdata, np.uint8).data_ptr()
             host["mask_image"] = np.ascontiguousarray(np.logical_or.reduce(mdata, axis=0), dtype=np.uint8)
             desc.mask_image = _ptr(host["mask_image"])
-        psf_kernel = ds._psf_kernel_for_evaluators()
+        psf_by_position = ds.psf is not None and not getattr(ds.psf, "has_single_spatial_bin", True)
+        edisp_by_position = ds.edisp is not None and not getattr(ds.edisp, "has_single_spatial_bin", True)
+        psf_kernel = None if psf_by_position else ds._psf_kernel_for_evaluators()
         if psf_kernel is not None:
             kdata = np.ascontiguousarray(psf_kernel.data, dtype=np.float32)  # ndmap.py:961
             if kdata.ndim != 3 or kdata.shape[0] != e_true.nbin or kdata.shape[1] != kdata.shape[2]:
@@ -115,8 +117,50 @@ class DeviceDataset:
         handle = C.c_void_p()
         _lib.check(self.ctx.lib.gpy_dataset_create(self.ctx.handle, C.byref(desc), C.byref(handle)))
         self.handle = handle
+        if psf_by_position or edisp_by_position:
+            self._set_irf_maps(ds, psf_by_position, edisp_by_position, e_true, e_reco)
         self._uploaded = ds._data_fingerprint()
         self._held = ds._data_arrays()
+
+    def _set_irf_maps(self, ds, psf_by_position, edisp_by_position, e_true, e_reco):
+        """PSFMap / EDispKernelMap with a spatial grid: the evaluators look their IRFs up at the source position
+        (``gpy_dataset_set_irf_maps``; MapEvaluator.update, datasets/evaluator.py:196-227)."""
+        grids = [m.geom for m, on in ((ds.psf, psf_by_position), (ds.edisp, edisp_by_position)) if on]
+        ig = grids[0]
+        if len(grids) == 2 and grids[1] != ig:
+            raise NotImplementedError("PSF map and edisp map must share their image geometry")
+        if ig.frame != ds._geom.frame:
+            raise NotImplementedError("IRF maps must be in the frame of the dataset geometry")
+        m = _lib.IrfMapsDesc()
+        m.nx, m.ny, m.binsz = ig.npix[0], ig.npix[1], ig.binsz
+        m.crval_lon, m.crpix_x, m.crpix_y = ig.crval[0], ig.crpix[0], ig.crpix[1]
+        keep = {}
+        if psf_by_position:
+            if ds.psf.energy_axis_true.nbin != e_true.nbin:
+                raise ValueError("PSF map energy axis does not match the exposure")
+            keep["rad"] = np.ascontiguousarray(ds.psf.rad_axis.edges, dtype=float)
+            keep["psf"] = np.ascontiguousarray(ds.psf.data, dtype=np.float32)
+            m.n_rad, m.rad_edges, m.psf_map = ds.psf.rad_axis.nbin, _ptr(keep["rad"]), _ptr(keep["psf"])
+        if edisp_by_position:
+            if ds.edisp.data.shape[:2] != (e_true.nbin, e_reco.nbin):
+                raise ValueError("edisp map axes do not match the dataset")
+            keep["edisp"] = np.ascontiguousarray(ds.edisp.data, dtype=float)
+            m.edisp_map = _ptr(keep["edisp"])
+        _lib.check(self.ctx.lib.gpy_dataset_set_irf_maps(self.handle, C.byref(m)))
+
+    def source_irf(self, source, with_kernel=True):
+        """(PSF kernel (nT, K, K) float32 or None, K, IRF pixel of the edisp matrix, number of IRF look-ups) of one
+        evaluator of a dataset with position-dependent IRFs (``gpy_dataset_source_psf_kernel``)."""
+        k, pix, n = C.c_int32(0), C.c_int32(-1), C.c_int32(0)
+        _lib.check(self.ctx.lib.gpy_dataset_source_psf_kernel(self.handle, source, None, 0, C.byref(k), C.byref(pix),
+                                                              C.byref(n)))
+        kernel = None
+        if with_kernel and k.value > 0 and n.value > 0:
+            nT = self.dataset.exposure.geom.axes["energy_true"].nbin
+            kernel = np.zeros((nT, k.value, k.value), dtype=np.float32)
+            _lib.check(self.ctx.lib.gpy_dataset_source_psf_kernel(self.handle, source, _ptr(kernel), kernel.size,
+                                                                  C.byref(k), C.byref(pix), C.byref(n)))
+        return kernel, k.value, pix.value, n.value
 
     def _upload_counts(self):
         counts = np.asarray(self.dataset.counts.data)

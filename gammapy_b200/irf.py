@@ -5,7 +5,10 @@ Reference: irf/psf/map.py (PSFMap.from_gauss :397-448, get_psf_kernel :249-337, 
 :23-37), irf/psf/kernel.py (PSFKernel :12-126), irf/psf/core.py (containment_radius :39-87),
 irf/edisp/map.py (EDispKernelMap, get_overlap_fraction :11-20), irf/edisp/kernel.py (EDispKernel).
 
-PSFMap here is position independent (one radial profile per true energy, as ``from_gauss`` makes it).
+A PSFMap / EDispKernelMap is position independent (one radial profile per true energy / one matrix, as ``from_gauss``
+makes them) or carries a spatial grid (``geom``: a CAR image geometry, data with two trailing (lat, lon) axes); the
+evaluators then look their IRFs up at the source position -- on the device, ``gpy_dataset_set_irf_maps`` -- and the
+methods here are the host mirror of that lookup (bilinear profile, nearest-pixel matrix).
 ``EDispKernel.from_gauss`` uses the closed-form Gaussian migration integral per (true, reco) bin rather
 than the reference's 200-bin migra interpolation (irf/edisp/core.py:88-136 + makers/utils.py:345-388);
 its output is the static matrix both this package and the oracle consume.
@@ -71,16 +74,56 @@ class PSFKernel:
         return cls(Map.from_geom(g.to_cube(axes) if axes else g, data=data, dtype=float))
 
 
+def _irf_pixel(geom, lon, lat):
+    """Fractional pixel of (lon, lat) [deg] in the IRF image grid, clamped to the grid
+    (``PSFMap._get_nearest_valid_position`` keeps the lookup inside the map)."""
+    dlon = (lon - geom.crval[0] + 180.0) % 360.0 - 180.0
+    px = dlon / (-geom.binsz) + geom.crpix[0] - 1.0
+    py = lat / geom.binsz + geom.crpix[1] - 1.0
+    return float(np.clip(px, 0.0, geom.npix[0] - 1.0)), float(np.clip(py, 0.0, geom.npix[1] - 1.0))
+
+
 class PSFMap:
-    """Position-independent PSF: radial profile ``psf(energy_true, rad)`` in sr-1 (irf/psf/map.py)."""
+    """PSF radial profile ``psf(energy_true, rad)`` in sr-1 (irf/psf/map.py): one for the whole field
+    (``data`` (nT, nrad)) or one per pixel of the image geometry ``geom`` (``data`` (nT, nrad, ny, nx))."""
 
     energy_name = "energy_true"
 
-    def __init__(self, energy_axis_true, rad_axis, data):
+    def __init__(self, energy_axis_true, rad_axis, data, geom=None):
         self.energy_axis_true = energy_axis_true
         self.rad_axis = rad_axis
-        self.data = np.asarray(data, dtype=float)  # (nT, nrad) at rad_axis.center
-        self.has_single_spatial_bin = True
+        self.data = np.asarray(data, dtype=float)  # at rad_axis.center
+        self.geom = None if geom is None else geom.to_image()
+        if self.data.ndim == 4:
+            if self.geom is None:
+                raise ValueError("a PSF map with spatial axes needs its image geometry")
+            if self.data.shape[2:] != (self.geom.npix[1], self.geom.npix[0]):
+                raise ValueError("PSF map data do not match the image geometry")
+        elif self.data.ndim != 2:
+            raise ValueError("PSF map data must be (n_energy_true, n_rad[, ny, nx])")
+        if self.data.shape[:2] != (energy_axis_true.nbin, rad_axis.nbin):
+            raise ValueError("PSF map data do not match the energy / rad axes")
+        self.has_single_spatial_bin = self.data.ndim == 2
+
+    def at_position(self, position=None):
+        """Position-independent PSFMap with the profile at ``position`` ((lon, lat) [deg]; default: the grid centre):
+        bilinear in the IRF pixel grid (``Map.interp_by_coord(method="linear")``, irf/psf/map.py:154-170, 310-320)."""
+        if self.has_single_spatial_bin:
+            return self
+        if position is None:
+            c = self.geom.center_skydir
+            position = (c.lon, c.lat)
+        lon, lat = (position.lon, position.lat) if hasattr(position, "lon") else position
+        px, py = _irf_pixel(self.geom, float(lon), float(lat))
+        ny, nx = self.data.shape[2:]
+        x0 = int(min(np.floor(px), max(nx - 2, 0)))
+        y0 = int(min(np.floor(py), max(ny - 2, 0)))
+        x1, y1 = min(x0 + 1, nx - 1), min(y0 + 1, ny - 1)
+        tx, ty = px - x0, py - y0
+        d = self.data
+        prof = ((1 - ty) * ((1 - tx) * d[..., y0, x0] + tx * d[..., y0, x1])
+                + ty * ((1 - tx) * d[..., y1, x0] + tx * d[..., y1, x1]))
+        return PSFMap(self.energy_axis_true, self.rad_axis, prof)
 
     @classmethod
     def from_gauss(cls, energy_axis_true, rad_axis=None, sigma=0.1, geom=None):
@@ -124,7 +167,9 @@ class PSFMap:
         return rad[idx]
 
     def get_psf_kernel(self, geom, position=None, max_radius=None, containment=0.999, precision_factor=12):
-        """irf/psf/map.py:249-337 for a position-independent PSF."""
+        """irf/psf/map.py:249-337 (host mirror; the evaluators of a dataset do this lookup on the device)."""
+        if not self.has_single_spatial_bin:
+            return self.at_position(position).get_psf_kernel(geom, None, max_radius, containment, precision_factor)
         geom = geom.to_image()
         radii = self.containment_radius(containment)
         if max_radius is None:
@@ -203,10 +248,23 @@ class EDispKernel:
 
 
 class EDispKernelMap:
-    """Position-independent EDispKernelMap (irf/edisp/map.py): one kernel for the whole field."""
+    """EDispKernelMap (irf/edisp/map.py): one kernel for the whole field, or -- ``data`` (nT, nR, ny, nx) on the image
+    geometry ``geom`` -- one per IRF pixel; ``get_edisp_kernel(position)`` then returns the nearest pixel's."""
 
-    def __init__(self, kernel):
+    def __init__(self, kernel=None, data=None, geom=None, axes=None):
         self.kernel = kernel
+        self.data = None if data is None else np.asarray(data, dtype=float)
+        self.geom = None if geom is None else geom.to_image()
+        self.axes = axes  # [energy_axis_true, energy_axis] of a map with a spatial grid
+        if self.data is not None:
+            if self.geom is None or axes is None or self.data.ndim != 4:
+                raise ValueError("an edisp kernel map with spatial axes needs data (nT, nR, ny, nx), geom and axes")
+            if self.data.shape != (axes[0].nbin, axes[1].nbin, self.geom.npix[1], self.geom.npix[0]):
+                raise ValueError("edisp kernel map data do not match the axes / image geometry")
+
+    @property
+    def has_single_spatial_bin(self):
+        return self.data is None
 
     @classmethod
     def from_diagonal_response(cls, energy_axis, energy_axis_true, geom=None):
@@ -221,7 +279,18 @@ class EDispKernelMap:
         return cls(edisp)
 
     def get_edisp_kernel(self, position=None, energy_axis=None):
-        """irf/edisp/map.py:369-401."""
+        """irf/edisp/map.py:369-401 (``to_region_nd_map`` of a point: the nearest IRF pixel)."""
+        if self.data is not None:
+            if energy_axis is not None and not energy_axis == self.axes[1]:
+                raise ValueError("EDispKernelMap: reco energy axis does not match the dataset geometry")
+            if position is None:
+                c = self.geom.center_skydir
+                position = (c.lon, c.lat)
+            lon, lat = (position.lon, position.lat) if hasattr(position, "lon") else position
+            px, py = _irf_pixel(self.geom, float(lon), float(lat))
+            i = int(np.clip(np.floor(px + 0.5), 0, self.geom.npix[0] - 1))
+            j = int(np.clip(np.floor(py + 0.5), 0, self.geom.npix[1] - 1))
+            return EDispKernel(list(self.axes), self.data[:, :, j, i])
         if energy_axis is not None and not energy_axis == self.kernel.axes["energy"]:
             raise ValueError("EDispKernelMap: reco energy axis does not match the dataset geometry")
         return self.kernel

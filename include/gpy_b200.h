@@ -131,6 +131,34 @@ int gpy_dataset_set_models(gpy_dataset_t* ds, const gpy_source_desc* sources, in
                            const gpy_background_desc* background);
 int gpy_dataset_source_state(const gpy_dataset_t* ds, int32_t source, gpy_source_state* out);
 
+/* Position-dependent IRFs: PSFMap / EDispKernelMap with a spatial grid (irf/psf/map.py, irf/edisp/map.py).  Once set,
+ * every evaluator looks its own IRFs up at the source position whenever MapEvaluator.update runs
+ * (datasets/evaluator.py:174-243, i.e. at the first evaluation and when the source has drifted further than
+ * evaluation_radius + 0.1 deg from the position of the last lookup, :465-481):
+ *   - PSFMap.get_psf_kernel(position, geom, containment=0.999) (irf/psf/map.py:249-337): radial profile interpolated
+ *     bilinearly in the IRF grid at the position (clamped to the grid), containment radii from the cumulative profile
+ *     (irf/psf/core.py:39-87), per-plane cut and <= 4 x oversampling (irf/psf/map.py:23-37), block sum, plane
+ *     normalisation (irf/psf/kernel.py:70-80) -- profile and radii on the host, the kernel images on the device;
+ *   - EDispKernelMap.get_edisp_kernel(position) (irf/edisp/map.py:369-401): the matrix of the nearest IRF pixel.
+ *     The sources of one dataset may use at most 4 different matrices at a time (GPY_ERR_UNSUPPORTED beyond).
+ * psf_map / edisp_map are HOST arrays, copied.  The psf_kernel / edisp of gpy_dataset_desc are then unused for the
+ * respective IRF (edisp_diagonal still serves apply_irf["edisp"] = False).  A batched call (n_vec > 1) whose vector
+ * would trigger such a lookup fails with GPY_ERR_UNSUPPORTED: evaluate that point as a single vector first. */
+typedef struct {
+  int32_t nx, ny;            /* IRF image grid (CAR about the equator, as gpy_geom_desc) */
+  double binsz, crval_lon, crpix_x, crpix_y;
+  int32_t n_rad;             /* rad bins of the PSF map */
+  const double* rad_edges;   /* HOST [n_rad + 1] deg, increasing */
+  const float* psf_map;      /* HOST [n_true, n_rad, ny, nx] sr-1 at the rad bin centres, or NULL */
+  const double* edisp_map;   /* HOST [n_true, n_reco, ny, nx] EDispKernelMap data, or NULL */
+} gpy_irf_maps_desc;
+int gpy_dataset_set_irf_maps(gpy_dataset_t* ds, const gpy_irf_maps_desc* desc);
+/* Inspection (tests): the kernel an evaluator currently uses.  *k = its side; kernel HOST [n_true, k, k] or NULL
+ * (capacity in floats); *edisp_pixel = iy * nx + ix of the IRF pixel of its edisp matrix (-1 without an edisp map);
+ * *n_updates = how often its IRFs were looked up.  The two last pointers may be NULL. */
+int gpy_dataset_source_psf_kernel(const gpy_dataset_t* ds, int32_t source, float* kernel, int32_t capacity, int32_t* k,
+                                  int32_t* edisp_pixel, int32_t* n_updates);
+
 /* Datasets.stat_sum (datasets/core.py:264-277) for a batch of parameter vectors.
  *   params  HOST [n_vec, n_par] parameter VALUES (not factors); shared by all datasets.
  *   stat    HOST [n_vec]        sum over datasets (summed in dataset order, as the Python loop does)

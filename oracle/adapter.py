@@ -31,7 +31,21 @@ def dataset_to_oracle(ds):
     geom = ds._geom
     e_true = ds.exposure.geom.axes["energy_true"]
     e_reco = geom.axes["energy"]
-    psf = ds._psf_kernel_for_evaluators()
+    psf_by_position = ds.psf is not None and not getattr(ds.psf, "has_single_spatial_bin", True)
+    edisp_by_position = ds.edisp is not None and not getattr(ds.edisp, "has_single_spatial_bin", True)
+    psf = None if psf_by_position else ds._psf_kernel_for_evaluators()
+    irf = {}
+    if psf_by_position or edisp_by_position:
+        from .irf import IrfGeom
+
+        ig = (ds.psf if psf_by_position else ds.edisp).geom
+        irf["irf_geom"] = IrfGeom(ig.npix[0], ig.npix[1], ig.binsz, ig.crval[0], ig.crpix[0], ig.crpix[1])
+        if psf_by_position:
+            # the library holds the map in float32 (gpy_irf_maps_desc.psf_map): same numbers on both sides
+            irf["psf_map"] = np.asarray(ds.psf.data, dtype=np.float32).astype(float)
+            irf["rad_edges"] = np.asarray(ds.psf.rad_axis.edges, dtype=float)
+        if edisp_by_position:
+            irf["edisp_map"] = np.asarray(ds.edisp.data, dtype=float)
     if ds.edisp is not None:
         edisp = np.asarray(ds.edisp.get_edisp_kernel(energy_axis=e_reco).pdf_matrix, dtype=float)
     else:
@@ -45,7 +59,7 @@ def dataset_to_oracle(ds):
         counts=None if ds.counts is None else np.asarray(ds.counts.data),
         mask_safe=None if ds.mask_safe is None else np.asarray(ds.mask_safe.data),
         mask_fit=None if ds.mask_fit is None else np.asarray(ds.mask_fit.data),
-        psf_kernel=None if psf is None else np.asarray(psf.data, dtype=float), edisp=edisp, name=ds.name,
+        psf_kernel=None if psf is None else np.asarray(psf.data, dtype=float), edisp=edisp, name=ds.name, **irf,
     )
 
 

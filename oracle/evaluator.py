@@ -25,6 +25,7 @@ variants used to measure the reference's own float32 noise floor.
 import numpy as np
 import scipy.signal
 from . import cash as _cash
+from . import irf as _irf
 from . import spatial as _spatial
 from . import spectral as _spectral
 from .wcs import DEG, NoOverlapError, angular_separation
@@ -37,7 +38,8 @@ class Dataset:
     """Plain-array stand-in for the MapDataset attributes the path reads."""
 
     def __init__(self, geom, energy_edges, energy_true_edges, exposure, background=None, counts=None,
-                 mask_safe=None, mask_fit=None, psf_kernel=None, edisp=None, energy_center=None, name="ds"):
+                 mask_safe=None, mask_fit=None, psf_kernel=None, edisp=None, energy_center=None, name="ds",
+                 psf_map=None, rad_edges=None, edisp_map=None, irf_geom=None):
         self.geom = geom
         self.energy_edges = np.asarray(energy_edges, float)
         self.energy_true_edges = np.asarray(energy_true_edges, float)
@@ -53,6 +55,9 @@ class Dataset:
         self.psf_kernel = psf_kernel
         self.edisp = edisp
         self.name = name
+        # position-dependent IRFs (oracle/irf.py): PSF map (nT, nrad, ny, nx) on rad_edges, edisp map (nT, nR, ny, nx),
+        # both on the IRF image grid irf_geom (oracle.irf.IrfGeom)
+        self.psf_map, self.rad_edges, self.edisp_map, self.irf_geom = psf_map, rad_edges, edisp_map, irf_geom
 
     @property
     def mask(self):
@@ -162,6 +167,13 @@ class Evaluator:
         s = self.model["spatial"]
         self.psf = ds.psf_kernel
         self.edisp = ds.edisp
+        position = (s["lon_0"], s["lat_0"])
+        if ds.edisp_map is not None:  # evaluator.py:196-204: edisp.get_edisp_kernel(position=self.position)
+            self.edisp = _irf.edisp_kernel_at(ds.edisp_map, ds.irf_geom, position)
+        if ds.psf_map is not None:    # evaluator.py:206-227: psf.get_psf_kernel(position, geom, containment=0.999)
+            self.psf = _irf.psf_kernel_at(ds.psf_map, ds.rad_edges, ds.irf_geom, position, ds.geom.binsz,
+                                          tuple(ds.geom.center_skydir))
+            self.n_irf_updates = getattr(self, "n_irf_updates", 0) + 1
         psf_width = 0.0
         if self.psf is not None:
             psf_width = ds.geom.binsz * self.psf.shape[-1]  # np.max(kernel geom width) = cdelt * npix

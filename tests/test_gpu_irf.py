@@ -1,0 +1,121 @@
+"""IRF kernel extraction at the source position (PSFMap.get_psf_kernel irf/psf/map.py:249-337,
+EDispKernelMap.get_edisp_kernel irf/edisp/map.py:369-401) with the refresh-on-drift logic of MapEvaluator.update
+(datasets/evaluator.py:174-243, 465-481), GPU vs the oracle restatement (oracle/irf.py; parity unpinned beyond the
+position-independent limit, which tests/test_oracle_irf.py ties to the kernel the reference's own npred golden pins)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _zoned(models, **kw):
+    from gammapy_b200 import configs
+
+    ds = configs.make_dataset(width=(4.0, 2.0), n_reco=6, n_true=12, mask_radius=None, **kw)
+    configs.zoned_irfs(ds)
+    ds.models = models
+    return ds
+
+
+def _point(lon, lat, name="src", amplitude=2e-11):
+    from gammapy_b200 import configs
+    from gammapy_b200.modeling.models import PointSpatialModel, PowerLawSpectralModel, SkyModel
+
+    return SkyModel(spatial_model=PointSpatialModel(lon_0=lon, lat_0=lat, frame=configs.FRAME),
+                    spectral_model=PowerLawSpectralModel(index=2.2, amplitude=amplitude, reference=1), name=name)
+
+
+def _check(ds, de, rtol=1e-5):
+    got, want = ds.npred().data, de.npred()
+    rel = np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300))
+    assert rel < rtol, rel
+    return got
+
+
+def test_kernel_follows_the_source_across_a_zone_boundary(ctx):
+    from gammapy_b200.modeling.models import FoVBackgroundModel
+    from oracle import adapter, irf as oirf
+
+    src = _point(1.0, 0.1)
+    ds = _zoned([src, FoVBackgroundModel(dataset_name="c1")])
+    de = adapter.evaluator_for(ds, conv="exact64")
+    od = de.ds
+    a = _check(ds, de)
+    st = ds.evaluator_irf("src")
+    want = oirf.psf_kernel_at(od.psf_map, od.rad_edges, od.irf_geom, (1.0, 0.1), od.geom.binsz, tuple(od.geom.center_skydir))
+    assert st["n_updates"] == 1 and st["k"] == want.shape[-1]
+    np.testing.assert_allclose(st["psf_kernel"], want, rtol=0, atol=2e-7 * want.max())
+    np.testing.assert_allclose(st["psf_kernel"].sum(axis=(1, 2)), 1.0, rtol=1e-5)
+    pix_a = st["edisp_pixel"]
+
+    # a small step (inside evaluation_radius + 0.1 deg of the last lookup): no new lookup on either side
+    src.spatial_model.lon_0.value = 0.95
+    adapter.refresh_models(de, ds)
+    _check(ds, de)
+    assert ds.evaluator_irf("src", with_kernel=False)["n_updates"] == 1
+    assert de.evaluators["src"].n_irf_updates == 1
+
+    # across the meridian into the other zone: wider PSF, another edisp matrix
+    src.spatial_model.lon_0.value = -1.0
+    adapter.refresh_models(de, ds)
+    b = _check(ds, de)
+    st2 = ds.evaluator_irf("src")
+    want2 = oirf.psf_kernel_at(od.psf_map, od.rad_edges, od.irf_geom, (-1.0, 0.1), od.geom.binsz, tuple(od.geom.center_skydir))
+    assert st2["n_updates"] == 2 and de.evaluators["src"].n_irf_updates == 2
+    assert st2["k"] == want2.shape[-1] and st2["k"] > st["k"]
+    np.testing.assert_allclose(st2["psf_kernel"], want2, rtol=0, atol=2e-7 * want2.max())
+    assert st2["edisp_pixel"] != pix_a
+    assert abs(a.sum() - b.sum()) > 1e-3 * a.sum()  # the zones really differ (edisp bias moves counts across the axis edge)
+
+    # in the transition column the profile is the bilinear mix of the two zones
+    src.spatial_model.lon_0.value = 0.2
+    src.spatial_model.lat_0.value = -0.3
+    adapter.refresh_models(de, ds)
+    _check(ds, de)
+    st3 = ds.evaluator_irf("src")
+    want3 = oirf.psf_kernel_at(od.psf_map, od.rad_edges, od.irf_geom, (0.2, -0.3), od.geom.binsz, tuple(od.geom.center_skydir))
+    assert st3["k"] == want3.shape[-1]
+    np.testing.assert_allclose(st3["psf_kernel"], want3, rtol=0, atol=2e-7 * want3.max())
+
+
+def test_two_sources_in_two_zones_and_the_statistic(ctx):
+    """Two evaluators with their own PSF kernel and edisp matrix in one dataset (two edisp groups in the fold kernel),
+    an extended source among them; npred per bin and the Cash statistic against the oracle."""
+    from gammapy_b200 import Map, configs
+    from gammapy_b200.modeling.models import FoVBackgroundModel, GaussianSpatialModel, PowerLawSpectralModel, SkyModel
+    from oracle import adapter
+
+    g = SkyModel(spatial_model=GaussianSpatialModel(lon_0=-1.1, lat_0=-0.2, sigma=0.15, frame=configs.FRAME),
+                 spectral_model=PowerLawSpectralModel(index=2.6, amplitude=3e-11, reference=1), name="gauss")
+    ds = _zoned([_point(1.2, 0.3, "point"), g, FoVBackgroundModel(dataset_name="c1")])
+    de = adapter.evaluator_for(ds, conv="exact64")
+    _check(ds, de)
+    assert ds.evaluator_irf("point", False)["edisp_pixel"] != ds.evaluator_irf("gauss", False)["edisp_pixel"]
+    assert ds.evaluator_irf("point", False)["k"] < ds.evaluator_irf("gauss", False)["k"]
+    counts = de.fake(5)
+    ds.counts = Map.from_geom(ds._geom, data=counts, dtype=float)
+    assert abs(ds.stat_sum() - de.stat_sum()) < 1e-3
+    # steady state: a spectral step re-uses the kernels and the convolved cubes
+    ds.models["point"].spectral_model.index.value = 2.4
+    adapter.refresh_models(de, ds)
+    assert abs(ds.stat_sum() - de.stat_sum()) < 1e-3
+    assert ds.evaluator_irf("point", False)["n_updates"] == 1
+
+
+def test_batched_call_refuses_a_lookup(ctx):
+    from gammapy_b200 import Map
+    from gammapy_b200.modeling.models import FoVBackgroundModel
+
+    src = _point(1.0, 0.0)
+    ds = _zoned([src, FoVBackgroundModel(dataset_name="c1")])
+    ds.counts = Map.from_geom(ds._geom, data=np.zeros(ds._geom.data_shape), dtype=float)
+    eng = ds._get_engine()
+    base = eng.values()
+    ds.stat_sum()
+    col = [i for i, p in enumerate(eng.parameters) if p.name == "lon_0"][0]
+    grid = np.tile(base, (3, 1))
+    grid[1, col] += 0.01   # inside the support: fine
+    assert np.all(np.isfinite(eng.stat_sum(grid[:2])))
+    grid[2, col] -= 2.0    # would need MapEvaluator.update with a new IRF lookup
+    with pytest.raises(NotImplementedError):
+        eng.stat_sum(grid)

@@ -1,0 +1,62 @@
+"""oracle/irf.py (IRF kernel extraction at a position) on the CPU: the position-independent limit must reproduce the
+kernel of the host builder the reference's ``test_npred_psf_after_edisp`` golden pins (tests/test_oracle_kat.py), a
+map whose pixels all hold the same profile must give that kernel at every position, and the nearest-pixel / bilinear
+rules are checked on a two-zone map."""
+import numpy as np
+
+from gammapy_b200 import configs
+from oracle import adapter, irf as oirf
+
+
+def _dataset():
+    return configs.make_dataset(width=(4.0, 2.0), n_reco=5, n_true=8, mask_radius=None)
+
+
+def test_position_independent_limit_equals_the_host_builder():
+    ds = _dataset()
+    want = ds.psf.get_psf_kernel(ds.exposure.geom, containment=0.999).data
+    od = adapter.dataset_to_oracle(ds)
+    got = oirf.psf_kernel_at(ds.psf.data, ds.psf.rad_axis.edges, None, (0.7, -0.2), od.geom.binsz,
+                             tuple(od.geom.center_skydir))
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+    # a map with the same profile in every pixel: any position gives that kernel
+    configs.zoned_irfs(ds, psf_scale=(1.0, 1.0), edisp_sigma=(0.15, 0.15), edisp_bias=(0.0, 0.0))
+    od = adapter.dataset_to_oracle(ds)
+    for pos in [(1.3, 0.4), (0.0, 0.0), (-1.9, -0.9), (5.0, 3.0)]:  # the last one is clamped to the grid
+        k = oirf.psf_kernel_at(od.psf_map, od.rad_edges, od.irf_geom, pos, od.geom.binsz, tuple(od.geom.center_skydir))
+        np.testing.assert_allclose(k, want, rtol=0, atol=3e-7 * want.max())  # the map is held in float32
+    np.testing.assert_allclose(k.sum(axis=(1, 2)), 1.0, rtol=1e-12)
+
+
+def test_two_zones_nearest_pixel_and_bilinear_profile():
+    ds = _dataset()
+    configs.zoned_irfs(ds)
+    od = adapter.dataset_to_oracle(ds)
+    ig = od.irf_geom
+    assert (ig.nx, ig.ny) == (4, 2)
+    # nearest IRF pixel for the edisp: pixel centres at lon = +1.5, +0.5, -0.5, -1.5 (CAR: lon decreases with x)
+    m_left = oirf.edisp_kernel_at(od.edisp_map, ig, (1.4, 0.4))
+    m_right = oirf.edisp_kernel_at(od.edisp_map, ig, (-0.6, -0.4))
+    np.testing.assert_array_equal(m_left, od.edisp_map[:, :, 1, 0])
+    np.testing.assert_array_equal(m_right, od.edisp_map[:, :, 0, 2])
+    assert np.abs(m_left - m_right).max() > 0.05
+    # host mirror of the product (EDispKernelMap.get_edisp_kernel) follows the same rule
+    np.testing.assert_array_equal(ds.edisp.get_edisp_kernel(position=(1.4, 0.4)).pdf_matrix, m_left)
+    # PSF profile: zone values at the pixel centres, their mean half-way between the two central columns
+    p0 = oirf.psf_profile_at(od.psf_map, ig, 0.5, 0.0)
+    p1 = oirf.psf_profile_at(od.psf_map, ig, -0.5, 0.0)
+    pm = oirf.psf_profile_at(od.psf_map, ig, 0.0, 0.0)
+    np.testing.assert_allclose(pm, 0.5 * (p0 + p1), rtol=1e-12)
+    np.testing.assert_allclose(ds.psf.at_position((0.0, 0.0)).data, pm, rtol=1e-6)
+    # containment radius grows with the zone's PSF width, kernels are normalised per plane
+    r0 = oirf.containment_radius(p0, od.rad_edges, 0.68)
+    r1 = oirf.containment_radius(p1, od.rad_edges, 0.68)
+    assert np.all(r1 > 1.5 * r0)
+    k1 = oirf.psf_kernel_at(od.psf_map, od.rad_edges, ig, (-1.0, 0.0), od.geom.binsz, tuple(od.geom.center_skydir))
+    k0 = oirf.psf_kernel_at(od.psf_map, od.rad_edges, ig, (1.0, 0.0), od.geom.binsz, tuple(od.geom.center_skydir))
+    assert k1.shape[-1] > k0.shape[-1]
+    np.testing.assert_allclose(k1.sum(axis=(1, 2)), 1.0, rtol=1e-12)
+    # product host mirror == oracle (independent code paths)
+    want = ds.psf.get_psf_kernel(ds.exposure.geom, position=(-1.0, 0.0)).data
+    np.testing.assert_allclose(k1, want, rtol=0, atol=3e-7 * want.max())
