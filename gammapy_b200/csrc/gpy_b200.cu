@@ -250,6 +250,7 @@ struct Source {
   int psf_k = 0, max_h = 0, max_kw = 4;
   int edisp_pix = -1;    // IRF pixel (iy * nx + ix) whose matrix this evaluator uses
   int n_irf_updates = 0;
+  double lookup_lon = 0.0, lookup_lat = 0.0;  // position of the last lookup (radians)
   void release_irf() {
     for (DevBuf* b : {&p_kflip, &p_planes, &p_raw, &p_kernel, &p_jobs}) b->release();
   }
@@ -1134,15 +1135,28 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         if (needs_update) {
           if (ds->irf.has_psf || ds->irf.has_edisp) {
             // the evaluator looks its IRFs up at the new position (evaluator.py:196-227) before sizing its cutout
-            if (!sequential)
-              return fail(GPY_ERR_UNSUPPORTED,
-                          "a vector of a batched call moves a source beyond its IRF support (MapEvaluator.update): "
-                          "evaluate that point as a single vector first");
-            if (ds->irf.has_edisp) src.edisp_pix = edisp_pixel_at(ds->irf, sp[0], sp[1]);
-            if (ds->irf.has_psf) {  // (whatever apply_irf says: update() looks the kernel up, the width uses it)
-              GPY_TRY(extract_psf(ds, src, sp[0], sp[1]));
-              for (auto& sl : src.slots) sl.valid = false;  // convolved with the previous kernel
-              ds->version = ++c->stamp;
+            if (!sequential) {
+              // A batched call does not advance the evaluators: its vectors use the IRFs of the last lookup as long
+              // as they stay within that lookup's support (evaluation_radius + margin of ITS position -- the
+              // reference's _cached_position starts at (0, 0), which would otherwise make every first spatial step a
+              // new lookup); beyond it the point has to be evaluated as a single vector first.
+              const double sep = angular_separation_h(sp[0] * kDegH, sp[1] * kDegH, src.lookup_lon, src.lookup_lat);
+              if (src.n_irf_updates == 0 ||
+                  sep > (evaluation_radius(src.desc.spatial_type, sp) + kCutoutMargin) * kDegH)
+                return fail(GPY_ERR_UNSUPPORTED,
+                            "a vector of a batched call moves a source beyond its IRF support (MapEvaluator.update): "
+                            "evaluate that point as a single vector first");
+            } else {
+              if (ds->irf.has_edisp) src.edisp_pix = edisp_pixel_at(ds->irf, sp[0], sp[1]);
+              if (ds->irf.has_psf) {  // (whatever apply_irf says: update() looks the kernel up, the width uses it)
+                GPY_TRY(extract_psf(ds, src, sp[0], sp[1]));
+                for (auto& sl : src.slots) sl.valid = false;  // convolved with the previous kernel
+                ds->version = ++c->stamp;
+              } else {
+                src.n_irf_updates++;
+              }
+              src.lookup_lon = sp[0] * kDegH;
+              src.lookup_lat = sp[1] * kDegH;
             }
           }
           GPY_TRY(evaluator_update(ds, src, sp, rect, contributes));
