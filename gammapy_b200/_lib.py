@@ -36,6 +36,8 @@ class DatasetDesc(C.Structure):
         ("nodes", C.c_void_p),
         ("n_nodes", C.c_int32),
         ("weight", C.c_void_p),
+        ("compact", C.c_int32),
+        ("mask_row_bytes", C.c_int64),
     ]
 
 

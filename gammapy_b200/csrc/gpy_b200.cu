@@ -344,6 +344,8 @@ struct gpy_dataset {
   const float *exposure = nullptr, *background = nullptr, *counts = nullptr;
   const uint8_t* mask = nullptr;
   const float* weight = nullptr;
+  int compact = 0;            // C5 storage: counts uint16, mask bit-packed with rows of mask_row_bytes
+  int64_t mask_row_bytes = 0;
   std::vector<uint8_t> mask_image;  // empty = all true
   DevBuf d_edges, d_nodes, d_ecenter, d_edisp, d_band, d_pdfc, d_omega, d_kflip, d_planes;
   DevBuf d_tmaps;             // 4 CUtensorMap: exposure, background, counts, mask (2-D [rows][P] tensors, box [rows][128])
@@ -561,17 +563,19 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-bool encode_map(CUtensorMap* out, const void* base, bool is_u8, size_t P, int rows) {
+// esz: element size 4 (float32), 2 (uint16) or 1 (uint8); `inner` elements per row, rows `row_bytes` apart, box of
+// `box_inner` elements x all rows.
+bool encode_map(CUtensorMap* out, const void* base, int esz, size_t inner, size_t row_bytes, int rows, int box_inner) {
   EncodeTiledFn fn = encode_tiled_fn();
-  if (!fn || !base || rows > 256) return false;
-  const size_t esz = is_u8 ? 1 : 4;
-  cuuint64_t dims[2] = {(cuuint64_t)P, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)(P * esz)};
-  cuuint32_t box[2] = {(cuuint32_t)gpy::kFoldTPX, (cuuint32_t)rows};
+  if (!fn || !base || rows > 256 || row_bytes % 16 != 0) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)rows};
   cuuint32_t estr[2] = {1, 1};
-  return fn(out, is_u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
-            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  const CUtensorMapDataType dt = esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  return fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // (Re)build the dataset's tensor maps; leaves has_tmaps false when the shape is not eligible (the kernel then uses
@@ -582,10 +586,17 @@ int build_tmaps(gpy_dataset* ds) {
   if (P % 16 != 0 || ds->geom.nx % 4 != 0 || P < (size_t)gpy::kFoldTPX) return GPY_OK;
   alignas(64) CUtensorMap maps[4];
   std::memset(maps, 0, sizeof(maps));
-  if (!encode_map(&maps[0], ds->exposure, false, P, ds->nT)) return GPY_OK;
-  if (ds->background && !encode_map(&maps[1], ds->background, false, P, ds->nR)) return GPY_OK;
-  if (ds->counts && !encode_map(&maps[2], ds->counts, false, P, ds->nR)) return GPY_OK;
-  if (ds->mask && !encode_map(&maps[3], ds->mask, true, P, ds->nR)) return GPY_OK;
+  const int TPX = gpy::kFoldTPX;
+  if (!encode_map(&maps[0], ds->exposure, 4, P, P * 4, ds->nT, TPX)) return GPY_OK;
+  if (ds->background && !encode_map(&maps[1], ds->background, 4, P, P * 4, ds->nR, TPX)) return GPY_OK;
+  if (!ds->compact) {
+    if (ds->counts && !encode_map(&maps[2], ds->counts, 4, P, P * 4, ds->nR, TPX)) return GPY_OK;
+    if (ds->mask && !encode_map(&maps[3], ds->mask, 1, P, P, ds->nR, TPX)) return GPY_OK;
+  } else {  // uint16 counts; mask bits: 16 bytes per tile and row
+    if (ds->counts && !encode_map(&maps[2], ds->counts, 2, P, P * 2, ds->nR, TPX)) return GPY_OK;
+    if (ds->mask && !encode_map(&maps[3], ds->mask, 1, (size_t)ds->mask_row_bytes, (size_t)ds->mask_row_bytes, ds->nR, TPX / 8))
+      return GPY_OK;
+  }
   if (ds->d_tmaps.p) {  // never rewrite a tensor map in place: the GPU may hold the old one in its descriptor cache
     ds->retired_tmaps.push_back(ds->d_tmaps);
     ds->d_tmaps = DevBuf();
@@ -1040,7 +1051,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   size_t flux_len = 0;
   int n_tiles = 0, max_inst = 1, max_tile_overlap = 0;
   int max_nT = 0, max_nR = 0, max_nRp = 0, max_G = 0, max_pdfc_rows = 1;
-  bool tma_ok = true;
+  bool tma_ok = true, all_compact = true;
   const bool sequential = (B == 1);
   const uint64_t call_id = ++c->stamp;
 
@@ -1071,6 +1082,9 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     dd.background = ds->background;
     dd.counts = rq.npred_out ? nullptr : ds->counts;
     dd.mask = ds->mask;
+    dd.compact = ds->compact;
+    dd.mask_row_bytes = (int)ds->mask_row_bytes;
+    all_compact = all_compact && ds->compact;
     dd.weight = ds->weight;
     dd.ecenter = (const double*)ds->d_ecenter.p;
     dd.tmaps = ds->has_tmaps ? ds->d_tmaps.p : nullptr;
@@ -1325,7 +1339,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         !al16(ds->mask) || ds->weight != nullptr || P64 * (size_t)std::max(ds->nT, ds->nR) > (size_t)INT32_MAX)
       tma_ok = false;
   }
-  const gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G, max_pdfc_rows);
+  const gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G, max_pdfc_rows, all_compact);
   if (lay.total > (size_t)c->max_smem_optin || c->force_generic ||
       max_tile_overlap > gpy::kFoldLMax + gpy::kDescOverflow)
     tma_ok = false;
@@ -1786,6 +1800,17 @@ int gpy_dataset_create(gpy_context_t* c, const gpy_dataset_desc* desc, gpy_datas
   ds->background = desc->background;
   ds->counts = desc->counts;
   ds->mask = desc->mask;
+  ds->compact = desc->compact;
+  ds->mask_row_bytes = desc->mask_row_bytes;
+  if (ds->compact) {
+    const bool bad_rows = desc->mask && (desc->mask_row_bytes % 16 != 0 || desc->mask_row_bytes * 8 < (int64_t)g.nx * g.ny);
+    if (ds->compact != 1 || desc->weight || bad_rows) {
+      delete ds;
+      if (desc->weight) return fail(GPY_ERR_UNSUPPORTED, "float weights (cash_weighted) with the compact storage format");
+      return fail(GPY_ERR_INVALID, "compact must be 0 or 1; compact mask rows must be a multiple of 16 bytes and hold "
+                  "ny * nx bits (compact %d, mask_row_bytes %lld)", desc->compact, (long long)desc->mask_row_bytes);
+    }
+  }
   ds->weight = desc->weight;
   ds->version = ++c->stamp;
   const size_t P = (size_t)g.nx * g.ny;

@@ -442,7 +442,9 @@ struct DatasetDev {
                             // of the chunk in the band-compressed matrix, pad
   const double* pdfc;       // band-compressed edisp: for every (group, chunk) the rows [lo, hi) x 8 reco bins, contiguous
   int pdfc_rows;            // total rows (of 8 doubles) in pdfc
-  int pad2_;
+  int compact;              // 1: counts are uint16 [nR, P], mask is bit-packed (bit p & 7 of byte p >> 3, little endian)
+                            //    with rows of mask_row_bytes (a multiple of 16, zero padded) -- the C5 storage format
+  int mask_row_bytes, pad3_;
   const double* ecenter;    // [nR]
   const void* tmaps;        // 4 CUtensorMap (exposure, background, counts, mask; 128 B each) or null: 1-D bulk copies
 };
@@ -700,9 +702,13 @@ __global__ void __launch_bounds__(kFoldThreads, GPY_FOLD_MINBLOCKS) fold_cash_ge
           }
           if (P.npred_out) P.npred_out[idx] = mu;
           if (D.counts) {
-            const bool m = D.mask ? (__ldg(D.mask + idx) != 0) : true;
+            bool m = true;
+            if (D.mask)
+              m = D.compact ? ((__ldg(D.mask + (size_t)r * D.mask_row_bytes + ((p0 + lp) >> 3)) >> ((p0 + lp) & 7)) & 1) != 0
+                            : __ldg(D.mask + idx) != 0;
             if (m) {
-              const double n = (double)__ldg(D.counts + idx);
+              const double n = D.compact ? (double)__ldg(reinterpret_cast<const unsigned short*>(D.counts) + idx)
+                                         : (double)__ldg(D.counts + idx);
               double npr, lognpr = 0.0;
               if (mu > kTrunc) {
                 npr = mu;
@@ -972,9 +978,6 @@ __global__ void __launch_bounds__(256) prep_items_kernel(const PrepParams P) {
 #ifndef GPY_PF_PASS
 #define GPY_PF_PASS 0
 #endif
-#ifndef GPY_FAST_LOG
-#define GPY_FAST_LOG 1
-#endif
 // log(x) for normal finite x > 0: x = 2^e m, m in [1, 2); m = m_hi (1 + r) with 1 / m_hi from a table indexed by the
 // top 7 mantissa bits, |r| < 2^-8; log(x) = e ln2 + log(m_hi) + log1p(r), log1p by its degree-7 Taylor polynomial
 // (|error| < 1e-17 absolute + the table's rounding, ~1e-16).  Straight-line code: calls interleave, unlike libdevice's
@@ -998,13 +1001,13 @@ constexpr int kBandSmem = 128;  // ints of the band table kept in shared memory 
 struct FoldSmem {  // byte offsets of the fixed shared-memory layout
   size_t es, bs, cs, ms, vs, pdf, desc, dyn, bars, total;
 };
-__host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int G, int pdfc_rows) {
-  FoldSmem L;
+__host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int G, int pdfc_rows, bool compact = false) {
+  FoldSmem L;  // compact: every dataset of the launch stores uint16 counts and a bit-packed mask
   size_t o = 0;
   L.es = o;    o += (size_t)nT * kFoldTPX * 4;
   L.bs = o;    o += (size_t)nR * kFoldTPX * 4;
-  L.cs = o;    o += (size_t)nR * kFoldTPX * 4;
-  L.ms = o;    o += ((size_t)nR * kFoldTPX + 15) / 16 * 16;
+  L.cs = o;    o += (size_t)nR * kFoldTPX * (compact ? 2 : 4);
+  L.ms = o;    o += compact ? (size_t)nR * 16 : ((size_t)nR * kFoldTPX + 15) / 16 * 16;
   L.vs = o;    o += (size_t)G * kTmaTCH * kFoldTPX * 8;
   L.pdf = o;   o += (size_t)pdfc_rows * 64;
   L.desc = o;  o += (size_t)2 * desc_layout().bytes;  // double buffered item descriptors
@@ -1034,10 +1037,8 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   __shared__ int2 nxt_s;         // {worklist position, item} claimed for the iteration after the next
   __shared__ DatasetDev Ds;      // table entry of the dataset the current item belongs to: no global loads per item
   __shared__ int band_s[kBandSmem];
-#if GPY_FAST_LOG
   __shared__ double2 logtab_s[128];
   if (threadIdx.x < 128) logtab_s[threadIdx.x] = P.logtab[threadIdx.x];  // published by the barrier behind the mbarrier initialisation
-#endif
 
   const int tid = threadIdx.x;
   const int n_items = P.B * P.n_tiles;
@@ -1100,8 +1101,8 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     uint32_t total = 0;
     if (D->tmaps) return;  // armed together with the tensor copies, after the barrier
     if (D->background && P.include_background) total += row * (uint32_t)D->nR;
-    if (D->counts) total += row * (uint32_t)D->nR;
-    if (D->counts && D->mask) total += (uint32_t)npx * (uint32_t)D->nR;
+    if (D->counts) total += (D->compact ? row / 2u : row) * (uint32_t)D->nR;
+    if (D->counts && D->mask) total += (D->compact ? 16u : (uint32_t)npx) * (uint32_t)D->nR;
     mbar_arrive_expect_tx(&bars[1], total);
   };
   auto issue_epi = [&](int item) {
@@ -1116,12 +1117,13 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         const uint32_t nR = (uint32_t)D->nR;
         uint32_t total = 0;
         if (has_bkg) total += (uint32_t)kFoldTPX * 4u * nR;
-        if (has_counts) total += (uint32_t)kFoldTPX * 4u * nR;
-        if (has_mask) total += (uint32_t)kFoldTPX * nR;
+        const bool cmp = D->compact != 0;
+        if (has_counts) total += (uint32_t)kFoldTPX * (cmp ? 2u : 4u) * nR;
+        if (has_mask) total += (cmp ? 16u : (uint32_t)kFoldTPX) * nR;
         mbar_arrive_expect_tx(&bars[1], total);
         if (has_bkg) tma_load_2d(bs, tm + 128, p0, 0, &bars[1], pol_stream);
         if (has_counts) tma_load_2d(cs, tm + 256, p0, 0, &bars[1], pol_stream);
-        if (has_mask) tma_load_2d(ms, tm + 384, p0, 0, &bars[1], pol_stream);
+        if (has_mask) tma_load_2d(ms, tm + 384, cmp ? p0 >> 3 : p0, 0, &bars[1], pol_stream);  // 16 bytes of bits per row
       }
       return;
     }
@@ -1131,12 +1133,21 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const float* cnt = D->counts;
     const uint8_t* msk = D->mask;
     const size_t PP = (size_t)D->P;
+    const bool cmp = D->compact != 0;
     for (int i = (tid & 31) * (kFoldThreads / 32) + (tid >> 5); i < 3 * nR; i += kFoldThreads) {
       const int r = i / 3, which = i - 3 * r;
       const size_t off = (size_t)r * PP + p0;
       if (which == 0 && has_bkg) bulk_g2s_hint(bs + r * kFoldTPX, bkg + off, row, &bars[1], pol_stream);
-      if (which == 1 && cnt) bulk_g2s_hint(cs + r * kFoldTPX, cnt + off, row, &bars[1], pol_stream);
-      if (which == 2 && cnt && msk) bulk_g2s_hint(ms + r * kFoldTPX, msk + off, (uint32_t)npx, &bars[1], pol_stream);
+      if (!cmp) {
+        if (which == 1 && cnt) bulk_g2s_hint(cs + r * kFoldTPX, cnt + off, row, &bars[1], pol_stream);
+        if (which == 2 && cnt && msk) bulk_g2s_hint(ms + r * kFoldTPX, msk + off, (uint32_t)npx, &bars[1], pol_stream);
+      } else {
+        if (which == 1 && cnt)
+          bulk_g2s_hint(reinterpret_cast<unsigned short*>(cs) + r * kFoldTPX,
+                        reinterpret_cast<const unsigned short*>(cnt) + off, row / 2u, &bars[1], pol_stream);
+        if (which == 2 && cnt && msk)
+          bulk_g2s_hint(ms + r * 16, msk + (size_t)r * D->mask_row_bytes + (p0 >> 3), 16u, &bars[1], pol_stream);
+      }
     }
   };
 
@@ -1296,7 +1307,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const int p0 = (tile - Ds.tile_begin) * kFoldTPX;
     const int npx = min(kFoldTPX, (int)Ds.P - p0);
     const bool has_bkg = Ds.background && P.include_background, has_counts = Ds.counts != nullptr,
-               has_mask = Ds.mask != nullptr, use_tmaps = Ds.tmaps != nullptr;
+               has_mask = Ds.mask != nullptr, cmp = Ds.compact != 0;
     const int nchunks = nRp >> 3;
     const int* band = G * nchunks * 4 <= kBandSmem ? band_s : Ds.band;
     // work descriptor of this item (requested at the top of the previous item)
@@ -1514,7 +1525,6 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         // count, so the log is the rare branch and the pass is bound by its loads and index arithmetic.
         const int nr = min(nR - r0, 32);
         const double log_trunc = P.log_trunc;
-#if GPY_FAST_LOG
         // The trip count is warp uniform (nr * 64 items, 32 consecutive ones per warp), so the warp can vote: the two
         // logs run only when some lane holds a count, as straight-line code for both pixels at once (fast_log: no
         // data-dependent branch, the two dependency chains interleave).  Separate accumulators for the mu and the
@@ -1528,8 +1538,17 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
           if (WRITE_NPRED && live)
             *reinterpret_cast<double2*>(P.npred_out + (size_t)r * (size_t)Ds.P + p0 + lp) = mu2;
           if (has_counts) {
-            const float2 n2 = *reinterpret_cast<const float2*>(cs + r * kFoldTPX + lp);
-            const unsigned m2 = has_mask ? *reinterpret_cast<const unsigned short*>(ms + r * kFoldTPX + lp) : 0x0101u;
+            float2 n2;
+            unsigned m2;
+            if (!cmp) {
+              n2 = *reinterpret_cast<const float2*>(cs + r * kFoldTPX + lp);
+              m2 = has_mask ? *reinterpret_cast<const unsigned short*>(ms + r * kFoldTPX + lp) : 0x0101u;
+            } else {  // uint16 counts, one mask bit per bin (lp is even: both bits sit in one byte)
+              const unsigned nn = *reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned short*>(cs) + r * kFoldTPX + lp);
+              n2 = make_float2((float)(nn & 0xffffu), (float)(nn >> 16));
+              const unsigned mb = has_mask ? (unsigned)ms[r * 16 + (lp >> 3)] >> (lp & 7) : 3u;
+              m2 = (mb & 1u) | ((mb & 2u) << 7);
+            }
             const bool on0 = live && (m2 & 0xffu), on1 = live && (m2 >> 8);
             const bool big0 = mu2.x > kTrunc, big1 = mu2.y > kTrunc;
             const double a0 = big0 ? mu2.x : kTrunc, a1 = big1 ? mu2.y : kTrunc;
@@ -1544,30 +1563,6 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
           }
         }
         stat += stat_mu - stat_nl;
-#else
-        for (int i = tid; i < nr * (kFoldTPX / 2); i += kFoldThreads) {
-          const int rr = i >> 6, lp = (i & (kFoldTPX / 2 - 1)) * 2;  // kFoldTPX == 128
-          if (lp >= npx) continue;
-          const int r = r0 + rr;
-          const double2 mu2 = *reinterpret_cast<const double2*>(mus + rr * kFoldTPX + lp);
-          if (WRITE_NPRED)
-            *reinterpret_cast<double2*>(P.npred_out + (size_t)r * (size_t)Ds.P + p0 + lp) = mu2;
-          if (has_counts) {
-            const float2 n2 = *reinterpret_cast<const float2*>(cs + r * kFoldTPX + lp);
-            const unsigned m2 = has_mask ? *reinterpret_cast<const unsigned short*>(ms + r * kFoldTPX + lp) : 0x0101u;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const double mu = u == 0 ? mu2.x : mu2.y;
-              const float nf = u == 0 ? n2.x : n2.y;
-              if ((m2 >> (8 * u)) & 0xffu) {
-                const bool big = mu > kTrunc;
-                stat += big ? mu : kTrunc;
-                if (nf > 0.f) stat -= (double)nf * (big ? log(mu) : log_trunc);
-              }
-            }
-          }
-        }
-#endif
       }
       GPY_TICK(14);
       if (stage_next) {

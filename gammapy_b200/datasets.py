@@ -29,10 +29,12 @@ class MapDataset:
     stat_type = "cash"
 
     def __init__(self, models=None, counts=None, exposure=None, background=None, psf=None, edisp=None,
-                 mask_safe=None, mask_fit=None, gti=None, meta_table=None, name=None, meta=None, stat_type="cash"):
+                 mask_safe=None, mask_fit=None, gti=None, meta_table=None, name=None, meta=None, stat_type="cash",
+                 storage="float32"):
         if stat_type not in ("cash", "cash_weighted"):
             raise NotImplementedError("only stat_type 'cash' and 'cash_weighted' are on the accelerated path")
         self.stat_type = stat_type
+        self.storage = storage
         self._name = name if name is not None else f"dataset-{next(_ds_counter):04d}"
         self._device = None
         self._engine = None
@@ -51,6 +53,24 @@ class MapDataset:
         self.meta = meta
         self._models = None
         self.models = models
+
+    @property
+    def storage(self):
+        """HBM layout of the counts and the mask: ``"float32"`` (counts float32, mask one byte per bin) or
+        ``"compact"`` (counts uint16 -- refused above 65535 --, mask one bit per bin): the format of stacked fits with
+        hundreds of datasets per GPU (BASELINE.json configs[4]).  Exposure maps that are the same ``Map`` object in
+        several datasets are uploaded once either way."""
+        return self._storage
+
+    @storage.setter
+    def storage(self, value):
+        if value not in ("float32", "compact"):
+            raise ValueError("storage must be 'float32' or 'compact'")
+        if value == "compact" and self.stat_type == "cash_weighted":
+            raise NotImplementedError("float mask weights cannot be bit-packed: 'compact' needs stat_type='cash'")
+        if getattr(self, "_storage", value) != value and getattr(self, "_device", None) is not None:
+            self._invalidate()
+        self._storage = value
 
     # -- map attributes: setters invalidate the device mirror ------------------------------------------------
     def _invalidate(self, counts_only=False):

@@ -45,9 +45,28 @@ class DeviceDataset:
         self._held = ()
         self._build()
 
-    def _to_device(self, name, arr, dtype):
+    _shared = {}  # (device, id of the source array) -> (weakref to the array, tensor): one upload per shared map
+
+    def _to_device(self, name, arr, dtype, share=False):
+        """HBM copy of ``arr``.  ``share``: datasets holding the very same numpy array (one exposure map for the
+        observations of one pointing grid) get the same tensor."""
+        import weakref
+
+        key = (self.ctx.device, id(arr), np.dtype(dtype).str)
+        if share:
+            hit = DeviceDataset._shared.get(key)
+            if hit is not None and hit[0]() is arr:
+                self._keep[name] = hit[1]
+                return hit[1]
         t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(self.ctx.torch_device)
         self._keep[name] = t
+        if share:
+            for k in [k for k, v in DeviceDataset._shared.items() if v[0]() is None]:
+                del DeviceDataset._shared[k]
+            try:
+                DeviceDataset._shared[key] = (weakref.ref(arr), t)
+            except TypeError:
+                pass
         return t
 
     def _build(self):
@@ -71,7 +90,7 @@ class DeviceDataset:
         desc.energy_reco_center = _ptr(host["ecenter"])
         desc.nodes = _ptr(host["nodes"])
         desc.n_nodes = host["nodes"].shape[1]
-        desc.exposure = self._to_device("exposure", ds.exposure.data, np.float32).data_ptr()
+        desc.exposure = self._to_device("exposure", ds.exposure.data, np.float32, share=True).data_ptr()
         if ds.background is not None:
             desc.background = self._to_device("background", ds.background.data, np.float32).data_ptr()
         if ds.counts is not None:
@@ -87,9 +106,20 @@ class DeviceDataset:
                 mdata = ~(mdata == False)  # noqa: E712
             elif ds.stat_type == "cash_weighted":
                 desc.weight = self._to_device("weight", mdata, np.float32).data_ptr()
-            desc.mask = self._to_device("mask", mdata, np.uint8).data_ptr()
+            if ds.storage == "compact":
+                # one bit per bin, bit (p & 7) of byte (p >> 3) for pixel p = y nx + x, rows padded to 16 bytes
+                P = mdata.shape[1] * mdata.shape[2]
+                row_bytes = (P + 127) // 128 * 16
+                bits = np.zeros((mdata.shape[0], row_bytes), dtype=np.uint8)
+                packed = np.packbits(mdata.reshape(mdata.shape[0], P).astype(bool), axis=1, bitorder="little")
+                bits[:, :packed.shape[1]] = packed
+                desc.mask = self._to_device("mask", bits, np.uint8).data_ptr()
+                desc.mask_row_bytes = row_bytes
+            else:
+                desc.mask = self._to_device("mask", mdata, np.uint8).data_ptr()
             host["mask_image"] = np.ascontiguousarray(np.logical_or.reduce(mdata, axis=0), dtype=np.uint8)
             desc.mask_image = _ptr(host["mask_image"])
+        desc.compact = int(ds.storage == "compact")
         psf_by_position = ds.psf is not None and not getattr(ds.psf, "has_single_spatial_bin", True)
         edisp_by_position = ds.edisp is not None and not getattr(ds.edisp, "has_single_spatial_bin", True)
         psf_kernel = None if psf_by_position else ds._psf_kernel_for_evaluators()
@@ -164,6 +194,11 @@ class DeviceDataset:
 
     def _upload_counts(self):
         counts = np.asarray(self.dataset.counts.data)
+        if self.dataset.storage == "compact":
+            c16 = counts.astype(np.uint16)
+            if not np.array_equal(c16, counts):
+                raise ValueError("compact storage holds integer counts in [0, 65535] only")
+            return self._to_device("counts", c16, np.uint16)
         c32 = counts.astype(np.float32)
         if not np.array_equal(c32, counts, equal_nan=True):
             raise NotImplementedError("counts are not exactly representable in float32")

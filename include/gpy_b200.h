@@ -74,6 +74,13 @@ typedef struct {
   const float* weight;               /* DEVICE [n_reco, ny, nx] or NULL: float mask of stat_type "cash_weighted"
                                         (WeightedCashFitStatistic, stats/fit_statistics.py:301-329); bins with
                                         weight 0 are excluded, `mask` must then be (weight != 0) */
+  int32_t compact;                   /* 0: counts float32, mask uint8 (above).  1: the storage format of stacked fits
+                                        with many datasets per GPU (BASELINE.json configs[4]): `counts` points to
+                                        DEVICE uint16 [n_reco, ny, nx] (counts above 65535 cannot be stored: the
+                                        caller must refuse them), `mask` to DEVICE bytes [n_reco, mask_row_bytes]
+                                        holding one bit per bin, bit (p & 7) of byte (p >> 3) for pixel p = y nx + x,
+                                        rows zero padded.  Same statistic: counts are integers either way. */
+  int64_t mask_row_bytes;            /* compact: bytes per mask row, a multiple of 16, >= ceil(ny nx / 8) */
 } gpy_dataset_desc;
 
 /* One SkyModel: where its parameters sit in the parameter vector handed to gpy_stat_sum / gpy_npred.
@@ -124,7 +131,8 @@ int gpy_kernel_time(gpy_context_t* ctx, double* total_ms, int64_t* launches);
 /* MapDataset.__init__ side: register the resident cubes, upload the static IRF kernels. */
 int gpy_dataset_create(gpy_context_t* ctx, const gpy_dataset_desc* desc, gpy_dataset_t** ds);
 int gpy_dataset_destroy(gpy_dataset_t* ds);
-/* Replace the counts cube pointer (MapDataset.fake overwrites counts, datasets/map.py:1538-1554). */
+/* Replace the counts cube pointer (MapDataset.fake overwrites counts, datasets/map.py:1538-1554); same element type as
+ * at creation (float32, or uint16 for a compact dataset). */
 int gpy_dataset_set_counts(gpy_dataset_t* ds, const float* counts_device);
 /* MapDataset.models setter (datasets/map.py:674-694): one evaluator per SkyModel, caches reset. */
 int gpy_dataset_set_models(gpy_dataset_t* ds, const gpy_source_desc* sources, int32_t n_sources,

@@ -61,4 +61,5 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.SourceDesc) == 4 * (2 + 6 + 5 + 2)
     assert C.sizeof(_lib.BackgroundDesc) == 16
     assert C.sizeof(_lib.SourceState) == 32
-    assert C.sizeof(_lib.DatasetDesc) == 48 + 8 * 8 + 8 + 8 * 3 + 8 + 8
+    assert C.sizeof(_lib.DatasetDesc) == 48 + 8 * 8 + 8 + 8 * 3 + 8 + 8 + 8 + 8  # ... weight, compact (padded), mask_row_bytes
+    assert C.sizeof(_lib.IrfMapsDesc) == 8 + 4 * 8 + 8 + 3 * 8
