@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- npred + Cash evaluations/s on the Galactic-plane survey MapDataset (BASELINE.json configs[2]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c3-flat|c3-small|c1|c2|c4|c4-large|c5-one]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c3-flat|c3-small|c1|c2|c4|c4-large|c5-one|c5 [--datasets N]]
 
 A *step* is one full likelihood evaluation (one parameter vector, every source's spectral parameters moved,
 spatial / PSF caches warm exactly as in the reference's steady-state Minuit step) of one MapDataset per GPU.
@@ -40,6 +40,11 @@ WORKLOADS = {
     "c5-one": dict(width=(80.0, 20.0), n_sources=100, n_reco=30, n_true=60,
                    desc="one CTAO-resolution MapDataset 4000x1000 px, 30 reco / 60 true bins, 100 sources (one of the "
                         "stacked-fit datasets)"),
+    # BASELINE.json configs[4]: stacked fit of many datasets per GPU in the compact storage format (uint16 counts, bit-packed
+    # mask, one exposure map shared by the datasets of the pointing grid); --datasets N of them on this GPU
+    "c5": dict(width=(80.0, 20.0), n_sources=100, n_reco=30, n_true=60,
+               desc="stacked fit: N CTAO-resolution MapDatasets 4000x1000 px, 30 reco / 60 true bins, 100 shared sources, "
+                    "per-dataset background norm, compact storage (uint16 counts, bit mask, shared exposure)"),
     # BASELINE.json configs[0] / configs[1]: L2-resident (6.8 MB), launch-latency bound; secondary measurements
     "c1": dict(desc="analysis_3d shape: 200x200 px, 10 reco / 20 true bins, Gaussian x PowerLaw, 1 vector per launch"),
     "c2": dict(desc="200x200 px, 10 reco / 20 true bins, 5 sources, profile scan of 256 parameter vectors per launch",
@@ -114,6 +119,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--datasets", type=int, default=8, help="datasets on this GPU (workload c5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     return ap.parse_args()
@@ -521,6 +527,122 @@ def run_c4(args):
         dist.destroy_process_group()
 
 
+def run_c5(args):
+    """Stacked fit of `--datasets` C5-shaped datasets on ONE GPU in the compact storage format.  Builder-run secondary
+    line (the driver's line stays C3): per-dataset HBM footprint, joint evaluation time, how many fit 180 GB."""
+    import torch
+
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("workload c5 is a single-GPU measurement (datasets shard over ranks as in c4)")
+    torch.cuda.set_device(0)
+    from gammapy_b200 import Datasets, Map, configs
+    from gammapy_b200.modeling.models import FoVBackgroundModel
+
+    w = WORKLOADS["c5"]
+    n_ds = int(args.datasets)
+    steps = args.steps or 20
+    warmup = 3 if args.warmup is None else max(args.warmup, 3)
+    t_build = time.perf_counter()
+    first = configs.make_c3(name="stack-000", width=w["width"], n_sources=w["n_sources"], n_reco=w["n_reco"],
+                            n_true=w["n_true"])
+    first.fake(random_state=500)
+    sources = [m for m in first.models if not isinstance(m, FoVBackgroundModel)]
+    datasets = [first]
+    rng = np.random.RandomState(501)
+    for i in range(1, n_ds):
+        name = f"stack-{i:03d}"
+        ds = configs.MapDataset(name=name, exposure=first.exposure, psf=first.psf, edisp=first.edisp,
+                                mask_safe=first.mask_safe, mask_fit=first.mask_fit)
+        scale = np.float32(rng.uniform(0.7, 1.3))
+        ds.background = Map.from_geom(first._geom, data=first.background.data * scale)
+        # distinct integer counts without another 120 M Poisson draws on the host: the first cube shifted in longitude
+        ds.counts = Map.from_geom(first._geom, data=np.roll(first.counts.data, 7 * i, axis=2), dtype=float)
+        ds.models = sources + [FoVBackgroundModel(dataset_name=name)]
+        datasets.append(ds)
+    for ds in datasets:
+        ds.storage = "compact"
+    joint = Datasets(datasets)
+    engine = joint._get_engine()
+    ctx, stream = engine.ctx, engine.ctx.stream
+    ref = joint.stat_sum()
+    t_build = time.perf_counter() - t_build
+    base = engine.values()
+    cols = spectral_columns(engine)
+    buf = torch.zeros(1, n_ds, dtype=torch.float64, device=ctx.torch_device)
+
+    def step(k):
+        v = base.copy()
+        v[cols] += 1e-3 if k % 2 == 0 else -1e-3
+        engine.stat_sum_device(v, buf)
+
+    for k in range(warmup):
+        step(k)
+    stream.synchronize()
+    launches0 = ctx.launch_count
+    ms_blocks = []
+    with ClockSampler(0) as clocks:
+        for _ in range(3):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            for k in range(steps):
+                step(k)
+            ev1.record(stream)
+            stream.synchronize()
+            ms_blocks.append(ev0.elapsed_time(ev1) / steps)
+    launches = (ctx.launch_count - launches0) // 3
+    ms_per_step = float(np.median(ms_blocks))
+    ctx.kernel_timing(True)
+    for k in range(5):
+        step(k)
+    kms, kn = ctx.kernel_time()
+    ctx.kernel_timing(False)
+    # end to end: Parameter objects on the host -> joint stat_sum()
+    pars = [engine.parameters[c] for c in cols]
+    v0 = [p.value for p in pars]
+    for k in range(2):
+        joint.stat_sum()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        for p, v in zip(pars, v0):
+            p.value = v + (1e-3 if k % 2 == 0 else -1e-3)
+        joint.stat_sum()
+    e2e_s = (time.perf_counter() - t0) / steps
+    for p, v in zip(pars, v0):
+        p.value = v
+    nR, ny, nx = first.data_shape
+    nT, P = first.exposure.data.shape[0], ny * nx
+    per_ds = 4 * nR * P + 2 * nR * P + nR * ((P + 127) // 128 * 16)   # background f32 + counts u16 + mask bits
+    shared = 4 * nT * P
+    alg = n_ds * (per_ds + shared)  # every dataset's evaluation reads the (shared) exposure once
+    free, total = torch.cuda.mem_get_info()
+    used = total - free
+    peak, peak_src = measured_peak()
+    kernel_us = kms / max(kn, 1) * 1e3
+    line = {
+        "metric": METRIC, "value": n_ds * 1e3 / ms_per_step, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": w["desc"], "key": "c5", "datasets": n_ds,
+                   "l2": "inputs per evaluation exceed the 126 MB L2: no flush needed",
+                   "step": "one joint evaluation (all datasets, one parameter vector), spectral shape of all sources moved",
+                   "value_is": "dataset evaluations/s = datasets x joint evaluations/s"},
+        "joint_evals_per_s": 1e3 / ms_per_step, "blocks_ms_per_step": ms_blocks, "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "e2e": {"value": n_ds / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": int(engine.n_par * 8 + n_ds * 400), "d2h_bytes_per_step": 8 * n_ds,
+                "what": "Datasets.stat_sum() with Parameter objects on the host"},
+        "roofline": {"bound": "hbm", "achieved": alg / (kernel_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg / (kernel_us * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg, "kernel": "fold_cash_tma_kernel", "duration_us": kernel_us,
+                     "note": "compact format: 4 nT P (shared exposure, read once per dataset) + 4 nR P + 2 nR P + nR P / 8"},
+        "memory": {"bytes_per_dataset": per_ds, "shared_exposure_bytes": shared, "device_bytes_in_use": int(used),
+                   "datasets_that_fit_180GB": int((180e9 - shared) // (per_ds + (used - shared - n_ds * per_ds) / n_ds)),
+                   "note": "in use = cubes + per-source PSF-convolved slot cubes + work descriptors of this process"},
+        "joint_stat": ref, "setup_s": t_build,
+    }
+    print(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
@@ -618,6 +740,8 @@ def c4_large_extras(world, rank, steps=40):
 
 
 def run_ours(args):
+    if args.workload == "c5":
+        return run_c5(args)
     if args.workload.startswith("c4"):
         return run_c4(args)
     import torch
