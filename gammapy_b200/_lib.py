@@ -96,6 +96,7 @@ SYMBOLS = {
     "gpy_npred": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P]),
     "gpy_cash_sum": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "gpy_weighted_cash_sum": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
+    "gpy_wstat_sum_device": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, C.c_int64, _P, _P]),
     "gpy_integrate_geom": (C.c_int, [_P, C.POINTER(GeomDesc), C.c_int32, _P, _P, C.POINTER(C.c_int32)]),
     "gpy_psf_convolve": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, _P]),
     "gpy_spectral_integral": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, _P]),

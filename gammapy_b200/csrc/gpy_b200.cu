@@ -1713,6 +1713,8 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
         (const void*)gpy::reduce_stat_kernel,
         (const void*)gpy::peer_allreduce_kernel,
         (const void*)gpy::cash_sum_kernel,
+        (const void*)gpy::wstat_sum_kernel<float>,
+        (const void*)gpy::wstat_sum_kernel<double>,
         (const void*)gpy::final_sum_kernel,
         (const void*)gpy::ts_map_kernel,
         (const void*)gpy::ts_map_strip_kernel,
@@ -2108,6 +2110,32 @@ int gpy_weighted_cash_sum(gpy_context_t* c, const double* counts, const double* 
                           double* out) {
   if (!weight && n > 0) return fail(GPY_ERR_INVALID, "NULL weight");
   return cash_common(c, counts, npred, weight, n, out);
+}
+
+// WStatFitStatistic.stat_sum_dataset (stats/fit_statistics.py:332-361) on DEVICE arrays.
+int gpy_wstat_sum_device(gpy_context_t* c, const void* n_on, const void* n_off, const void* alpha, int32_t float64_inputs,
+                         const double* mu_sig, const uint8_t* mask, int64_t n, double* stat_per_bin, double* out) {
+  if (!c || !out) return fail(GPY_ERR_INVALID, "NULL argument to gpy_wstat_sum_device");
+  if (n < 0) return fail(GPY_ERR_INVALID, "negative length");
+  if (n > 0 && (!n_on || !n_off || !alpha || !mu_sig)) return fail(GPY_ERR_INVALID, "NULL array");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int blocks = (int)std::min<int64_t>(std::max<int64_t>((n + 255) / 256, 1), (int64_t)c->num_sms * 8);
+  GPY_TRY(c->partials.reserve((size_t)blocks * sizeof(double), c->stream));
+  GPY_TRY(c->stat.reserve(4 * sizeof(double)));
+  if (float64_inputs)
+    gpy::wstat_sum_kernel<double><<<blocks, 256, 0, c->stream>>>((const double*)n_on, (const double*)n_off,
+                                                                (const double*)alpha, mu_sig, mask, n, stat_per_bin,
+                                                                (double*)c->partials.p);
+  else
+    gpy::wstat_sum_kernel<float><<<blocks, 256, 0, c->stream>>>((const float*)n_on, (const float*)n_off,
+                                                               (const float*)alpha, mu_sig, mask, n, stat_per_bin,
+                                                               (double*)c->partials.p);
+  gpy::final_sum_kernel<<<1, 256, 0, c->stream>>>((const double*)c->partials.p, blocks, 1.0, (double*)c->stat.p);
+  c->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, c->stat.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return GPY_OK;
 }
 
 static int registry3(gpy_context_t* c, const double* counts, const double* background, const double* model,

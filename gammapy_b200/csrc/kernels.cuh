@@ -1751,6 +1751,56 @@ cash_sum_kernel(const double* __restrict__ counts, const double* __restrict__ np
   if (threadIdx.x == 0) partials[blockIdx.x] = sm[0];
 }
 
+// ----------------------------------------------------------------------------------------------
+// WStat (stats/fit_statistics.py:142-252, WStatFitStatistic :332-361): ON counts with a Poisson OFF measurement.
+//   mu_bkg = (C + D) / (2 alpha (alpha + 1)),  C = alpha (n_on + n_off) - (1 + alpha) mu_sig,
+//                                               D = sqrt(C^2 + 4 alpha (alpha + 1) n_off mu_sig)      (:221-236)
+//   stat = 2 (mu_sig + (1 + alpha) mu_bkg - [n_on != 0] n_on log(mu_sig + alpha mu_bkg) - [n_off != 0] n_off log(mu_bkg))
+//          + 2 ([n_on != 0] -n_on (1 - log n_on) + [n_off != 0] -n_off (1 - log n_off))                (:142-218, 239-252)
+// then np.nan_to_num per bin (:349) and the sum over the bins where `mask` is true.  Inputs are device arrays: ON / OFF
+// counts and alpha float32 or float64 (TI), mu_sig float64 (the npred_signal cube), mask uint8 or null.
+// Products the reference rounds separately are kept apart (__dmul_rn / __dadd_rn): no FMA contraction.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ double wstat_bin(double n_on, double n_off, double alpha, double mu_sig) {
+  const double a1 = __dadd_rn(alpha, 1.0);
+  const double C = __dadd_rn(__dmul_rn(alpha, __dadd_rn(n_on, n_off)), -__dmul_rn(__dadd_rn(1.0, alpha), mu_sig));
+  const double four = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(4.0, alpha), a1), n_off), mu_sig);
+  const double D = sqrt(__dadd_rn(__dmul_rn(C, C), four));
+  const double mu_bkg = __ddiv_rn(__dadd_rn(C, D), __dmul_rn(__dmul_rn(2.0, alpha), a1));
+  const double term1 = __dadd_rn(mu_sig, __dmul_rn(__dadd_rn(1.0, alpha), mu_bkg));
+  const double term2 = n_on == 0.0 ? 0.0 : __dmul_rn(-n_on, log(__dadd_rn(mu_sig, __dmul_rn(alpha, mu_bkg))));
+  const double term3 = n_off == 0.0 ? 0.0 : __dmul_rn(-n_off, log(mu_bkg));
+  double stat = __dmul_rn(2.0, __dadd_rn(__dadd_rn(term1, term2), term3));
+  double gof = 0.0;
+  gof = __dadd_rn(gof, n_on == 0.0 ? 0.0 : __dmul_rn(-n_on, __dadd_rn(1.0, -log(n_on))));
+  gof = __dadd_rn(gof, n_off == 0.0 ? 0.0 : __dmul_rn(-n_off, __dadd_rn(1.0, -log(n_off))));
+  stat = __dadd_rn(stat, __dmul_rn(2.0, gof));
+  if (isnan(stat)) return 0.0;  // np.nan_to_num
+  if (isinf(stat)) return stat > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+  return stat;
+}
+
+template <typename TI>
+__global__ void __launch_bounds__(256)
+wstat_sum_kernel(const TI* __restrict__ n_on, const TI* __restrict__ n_off, const TI* __restrict__ alpha,
+                 const double* __restrict__ mu_sig, const unsigned char* __restrict__ mask, long long n,
+                 double* __restrict__ per_bin, double* __restrict__ partials) {
+  __shared__ double sm[256];
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const double v = wstat_bin((double)n_on[i], (double)n_off[i], (double)alpha[i], mu_sig[i]);
+    if (per_bin) per_bin[i] = v;
+    if (!mask || mask[i]) s += v;
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = sm[0];
+}
+
 __global__ void __launch_bounds__(256)
 final_sum_kernel(const double* __restrict__ partials, int n, double scale, double* __restrict__ out) {
   __shared__ double sm[256];

@@ -15,7 +15,7 @@ from .modeling.models import FoVBackgroundModel, Models, SkyModel
 from .modeling.parameter import Parameters
 from .utils import get_random_state
 
-__all__ = ["MapDataset", "Datasets"]
+__all__ = ["MapDataset", "MapDatasetOnOff", "Datasets"]
 
 _ds_counter = itertools.count()
 PSF_CONTAINMENT = 0.999  # datasets/evaluator.py:16
@@ -354,6 +354,109 @@ class MapDataset:
         return f"MapDataset(name={self.name!r}, geom={self._geom!r}, models={None if self._models is None else self._models.names})"
 
 
+class MapDatasetOnOff(MapDataset):
+    """ON / OFF map dataset with the WStat statistic (datasets/map.py:2554-2700, stats/fit_statistics.py:332-361):
+    the background is not modelled but measured -- ``counts_off`` in an OFF region of relative acceptance
+    ``acceptance_off / acceptance`` -- and profiled out bin by bin.  ``npred_signal`` comes from the fold kernel
+    (no background term), the statistic from ``wstat_sum_kernel`` on the same device arrays."""
+
+    tag = "MapDatasetOnOff"
+
+    def __init__(self, counts_off=None, acceptance=None, acceptance_off=None, **kwargs):
+        if kwargs.get("background") is not None:
+            raise ValueError("MapDatasetOnOff takes no background model map: the OFF counts are the background")
+        kwargs.setdefault("stat_type", "cash")  # for the parent's checks; this class overrides every stat method
+        super().__init__(**kwargs)
+        self.stat_type = "wstat"
+        self.counts_off = counts_off
+        geom = self._geom
+        ones = np.ones(geom.data_shape)
+        self.acceptance = acceptance if acceptance is not None else Map.from_geom(geom, data=ones.copy(), dtype=float)
+        self.acceptance_off = (acceptance_off if acceptance_off is not None
+                               else Map.from_geom(geom, data=ones.copy(), dtype=float))
+        self._onoff_dev = None
+
+    @property
+    def alpha(self):
+        """Exposure ratio between the ON and the OFF region (datasets/map.py:2661-2677): acceptance / acceptance_off,
+        0 where the OFF acceptance is 0 (np.nan_to_num of the division)."""
+        with np.errstate(invalid="ignore", divide="ignore"):
+            data = np.nan_to_num(np.asarray(self.acceptance.data, float) / np.asarray(self.acceptance_off.data, float))
+        return Map.from_geom(self._geom, data=data, dtype=float)
+
+    def npred_background(self):
+        """Profile-likelihood background in the ON region, alpha * mu_bkg (datasets/map.py:2679-2700,
+        stats/fit_statistics.py:221-236), from the GPU's npred_signal."""
+        n_on, n_off = np.asarray(self._counts.data, float), np.asarray(self.counts_off.data, float)
+        alpha, mu_sig = self.alpha.data, self.npred_signal().data
+        c = alpha * (n_on + n_off) - (1 + alpha) * mu_sig
+        d = np.sqrt(c ** 2 + 4 * alpha * (alpha + 1) * n_off * mu_sig)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mu_bkg = np.nan_to_num((c + d) / (2 * alpha * (alpha + 1)))
+        return Map.from_geom(self._geom, data=alpha * mu_bkg, dtype=float)
+
+    def _device_arrays(self):
+        import torch
+
+        eng = self._get_engine()
+        key = (id(self._counts.data), id(self.counts_off.data), id(self.acceptance.data), id(self.acceptance_off.data),
+               None if self.mask is None else id(self.mask.data))
+        if self._onoff_dev is None or self._onoff_dev[0] != key:
+            dev = eng.ctx.torch_device
+            f64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)  # noqa: E731
+            mask = None if self.mask is None else torch.from_numpy(
+                np.ascontiguousarray(np.asarray(self.mask.data) != 0, dtype=np.uint8)).to(dev)
+            self._onoff_dev = (key, f64(self._counts.data), f64(self.counts_off.data), f64(self.alpha.data), mask,
+                               (self._counts.data, self.counts_off.data, self.acceptance.data, self.acceptance_off.data))
+        return self._onoff_dev[1:5]
+
+    def _wstat(self, return_array, values=None):
+        from . import stats
+
+        if self.counts_off is None:
+            return (0.0, np.zeros(self._geom.data_shape)) if return_array else 0.0
+        n_on, n_off, alpha, mask = self._device_arrays()
+        mu_sig = self._get_engine().npred_device(0, values=values, include_background=False)
+        return stats.wstat_sum_cuda(n_on, n_off, alpha, mu_sig, mask=mask, return_array=return_array)
+
+    def _fit_engine(self):
+        """What ``Fit`` needs (parameters, values, stat_sum of one or many parameter vectors) with WStat as the
+        statistic: every vector is one npred_signal evaluation + one ``wstat_sum_kernel`` launch."""
+        ds = self
+
+        class _OnOffEngine:
+            def __init__(self):
+                self.inner = ds._get_engine()
+                self.parameters = self.inner.parameters
+                self.n_par = self.inner.n_par
+                self.ctx = self.inner.ctx
+
+            def values(self):
+                return self.inner.values()
+
+            def stat_sum(self, values=None):
+                if values is None:
+                    return ds._wstat(False)
+                values = np.asarray(values, dtype=float)
+                if values.ndim == 1:
+                    return ds._wstat(False, values)
+                return np.array([ds._wstat(False, v) for v in values])
+
+        return _OnOffEngine()
+
+    def stat_sum_likelihood(self):
+        """``WStatFitStatistic.stat_sum_dataset`` (stats/fit_statistics.py:351-361)."""
+        if self._counts is None:
+            raise ValueError("MapDatasetOnOff has no counts")
+        return self._wstat(False)
+
+    stat_sum = stat_sum_likelihood
+
+    def stat_array(self):
+        """``WStatFitStatistic.stat_array_dataset`` (stats/fit_statistics.py:335-349)."""
+        return self._wstat(True)[1]
+
+
 def _parameters_with_prior(engine):
     """The engine's parameters that carry a prior; rescanned only after a prior was assigned somewhere."""
     from .modeling.parameter import Parameter
@@ -366,6 +469,7 @@ def _parameters_with_prior(engine):
 
 
 class Datasets(list):
+    # (MapDatasetOnOff members are refused in _get_engine: the joint engine evaluates Cash)
     """Container of datasets with a joint likelihood (datasets/core.py:140)."""
 
     def __init__(self, datasets=None):
@@ -406,6 +510,9 @@ class Datasets(list):
     def _get_engine(self):
         from .engine import LikelihoodEngine
 
+        if any(getattr(d, "stat_type", "cash") == "wstat" for d in self):
+            raise NotImplementedError("joint fits with MapDatasetOnOff members: the joint engine evaluates Cash; "
+                                      "fit an ON/OFF dataset on its own (Fit.run(dataset))")
         stale = self._engine is None or self._engine._signature != LikelihoodEngine.signature(self)
         if not stale:
             stale = any(d._device is None or d._device._uploaded != d._data_fingerprint() for d in self)

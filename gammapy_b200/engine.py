@@ -335,6 +335,10 @@ class LikelihoodEngine:
 
     def npred(self, index, values=None, source_enable=None, include_background=True):
         """npred cube of dataset ``index`` as a float64 numpy array."""
+        return self.npred_device(index, values, source_enable, include_background).cpu().numpy()
+
+    def npred_device(self, index, values=None, source_enable=None, include_background=True):
+        """npred cube of dataset ``index`` as a float64 CUDA tensor (complete when the call returns)."""
         import torch
 
         if values is None:
@@ -349,7 +353,8 @@ class LikelihoodEngine:
         _lib.check(self.ctx.lib.gpy_npred(self.ctx.handle, ds._device.handle, _ptr(values), self.n_par,
                                           _ptr(en) if en is not None else None, int(include_background),
                                           C.c_void_p(out.data_ptr())))
-        return out.cpu().numpy()
+        self.ctx.stream.synchronize()
+        return out
 
     def source_state(self, index, source):
         st = _lib.SourceState()

@@ -22,12 +22,14 @@ class _Likelihood:
     def __init__(self, datasets):
         from ..datasets import Datasets, MapDataset
 
-        if isinstance(datasets, MapDataset):
+        if hasattr(datasets, "_fit_engine"):  # a dataset with its own statistic (MapDatasetOnOff: WStat)
+            pass
+        elif isinstance(datasets, MapDataset):
             datasets = Datasets([datasets])
         elif not isinstance(datasets, Datasets) and not hasattr(datasets, "_get_engine"):
             datasets = Datasets(list(datasets))
         self.datasets = datasets
-        self.engine = datasets._get_engine()
+        self.engine = datasets._fit_engine() if hasattr(datasets, "_fit_engine") else datasets._get_engine()
         self.free = [p for p in self.engine.parameters if not p.frozen]
         self.cols = np.array([self.engine.parameters.index(p) for p in self.free], dtype=int)
         self.has_priors = any(p.prior is not None for p in self.engine.parameters)

@@ -42,6 +42,46 @@ def weighted_cash_sum_cuda(counts, npred, weight):
     return out.value
 
 
+def wstat_sum_cuda(n_on, n_off, alpha, mu_sig, mask=None, return_array=False):
+    """``WStatFitStatistic.stat_sum_dataset`` (stats/fit_statistics.py:332-361): sum over the masked bins of
+    ``np.nan_to_num(wstat(n_on, n_off, alpha, mu_sig))`` (:142-252) on the GPU.  Arrays of one shape: numpy (copied to
+    the device as float64) or CUDA torch tensors (ON / OFF / alpha float32 or float64, ``mu_sig`` float64, ``mask``
+    uint8 / bool).  ``return_array``: also the per-bin statistic (``stat_array_dataset``) as a numpy array."""
+    import torch
+
+    ctx = _lib.Context.get()
+    dev = ctx.torch_device
+
+    def to_dev(a, dtype=None):
+        if isinstance(a, torch.Tensor):
+            t = a.to(dev)
+            return t.contiguous() if dtype is None else t.to(dtype).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64 if dtype is None else None)).to(dev) \
+            if dtype is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dtype).contiguous()
+
+    t_on, t_off, t_al = to_dev(n_on), to_dev(n_off), to_dev(alpha)
+    kinds = {t.dtype for t in (t_on, t_off, t_al)}
+    if kinds == {torch.float32}:
+        f64 = 0
+    else:
+        t_on, t_off, t_al = (t.to(torch.float64).contiguous() for t in (t_on, t_off, t_al))
+        f64 = 1
+    t_mu = to_dev(mu_sig, torch.float64)
+    if not (t_on.shape == t_off.shape == t_al.shape == t_mu.shape):
+        raise ValueError("n_on, n_off, alpha and mu_sig must have the same shape")
+    t_mask = None if mask is None else to_dev(mask, torch.uint8)
+    if t_mask is not None and t_mask.shape != t_on.shape:
+        raise ValueError("mask must have the shape of the counts")
+    per_bin = torch.empty(t_on.shape, dtype=torch.float64, device=dev) if return_array else None
+    torch.cuda.current_stream(dev).synchronize()  # the library runs on its own stream
+    out = C.c_double(0.0)
+    _lib.check(ctx.lib.gpy_wstat_sum_device(
+        ctx.handle, C.c_void_p(t_on.data_ptr()), C.c_void_p(t_off.data_ptr()), C.c_void_p(t_al.data_ptr()), f64,
+        C.c_void_p(t_mu.data_ptr()), C.c_void_p(t_mask.data_ptr()) if t_mask is not None else None, t_on.numel(),
+        C.c_void_p(per_bin.data_ptr()) if per_bin is not None else None, C.byref(out)))
+    return (out.value, per_bin.cpu().numpy()) if return_array else out.value
+
+
 def f_cash_root_cuda(x, counts, background, model):
     """f_cash_root_cython (stats/fit_statistics_cython.pyx:90-121): derivative of the Cash statistic wrt the norm."""
     counts, background, model = _as_f64(counts), _as_f64(background), _as_f64(model)

@@ -220,6 +220,15 @@ int gpy_cash_sum(gpy_context_t* ctx, const double* counts, const double* npred, 
 int gpy_weighted_cash_sum(gpy_context_t* ctx, const double* counts, const double* npred,
                           const double* weight, int64_t n, double* out);
 
+/* WStatFitStatistic.stat_sum_dataset (stats/fit_statistics.py:332-361) = sum over the masked bins of
+ * np.nan_to_num(wstat(n_on, n_off, alpha, mu_sig)) (:142-252: profile-likelihood background :221-236, goodness-of-fit
+ * terms :239-252) -- the statistic of MapDatasetOnOff (datasets/map.py:2554).  All arrays DEVICE, length n:
+ *   n_on, n_off, alpha  float32 (float64_inputs == 0) or float64;  mu_sig float64 (npred_signal, e.g. the output of
+ *   gpy_npred without background);  mask uint8 or NULL;  stat_per_bin DEVICE float64 [n] or NULL (stat_array_dataset);
+ *   out HOST: the sum.  Waits for the result. */
+int gpy_wstat_sum_device(gpy_context_t* ctx, const void* n_on, const void* n_off, const void* alpha, int32_t float64_inputs,
+                         const double* mu_sig, const uint8_t* mask, int64_t n, double* stat_per_bin, double* out);
+
 /* f_cash_root_compiled(x, counts, background, model) and norm_bounds_compiled(counts, background, model)
  * (stats/fit_statistics_cython.pyx:90-157): HOST float64 arrays in, HOST out (1 and 3 doubles:
  * b_min, b_max, -sn_min_total). */
