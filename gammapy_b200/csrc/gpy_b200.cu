@@ -288,7 +288,7 @@ struct gpy_context {
   double* stat_pinned = nullptr;
   int* nwork_pinned = nullptr;  // read-back of the batched worklist length
   size_t stat_pinned_cap = 0;
-  size_t ts_smem_set = 0, fold_smem_set = 0, conv_smem_set = 0, tma_smem_set[4] = {0, 0, 0, 0};
+  size_t ts_smem_set = 0, fold_smem_set = 0, conv_smem_set = 0, tma_smem_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int tma_blocks_per_sm[2] = {0, 0};
   int num_sms = 0;
   bool force_generic = false;
@@ -1051,7 +1051,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   size_t flux_len = 0;
   int n_tiles = 0, max_inst = 1, max_tile_overlap = 0;
   int max_nT = 0, max_nR = 0, max_nRp = 0, max_G = 0, max_pdfc_rows = 1;
-  bool tma_ok = true, all_compact = true;
+  bool tma_ok = true, all_compact = true, any_compact = false;
   const bool sequential = (B == 1);
   const uint64_t call_id = ++c->stamp;
 
@@ -1085,6 +1085,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     dd.compact = ds->compact;
     dd.mask_row_bytes = (int)ds->mask_row_bytes;
     all_compact = all_compact && ds->compact;
+    any_compact = any_compact || ds->compact;
     dd.weight = ds->weight;
     dd.ecenter = (const double*)ds->d_ecenter.p;
     dd.tmaps = ds->has_tmaps ? ds->d_tmaps.p : nullptr;
@@ -1340,6 +1341,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       tma_ok = false;
   }
   const gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G, max_pdfc_rows, all_compact);
+  if (any_compact && !all_compact) tma_ok = false;  // mixed storage formats in one launch: the any-shape kernel
   if (lay.total > (size_t)c->max_smem_optin || c->force_generic ||
       max_tile_overlap > gpy::kFoldLMax + gpy::kDescOverflow)
     tma_ok = false;
@@ -1549,9 +1551,14 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     // Items differ in cost (source-free tiles are light): with many items per CTA they are claimed dynamically.
     // (grid <= 2 CTAs per SM; 8 items per CTA at least.)
     const bool dynamic = B == 1 && n_work_host >= (size_t)16 * c->num_sms && !c->static_schedule;
-    auto kern = variant ? (dynamic ? gpy::fold_cash_tma_kernel<true, true> : gpy::fold_cash_tma_kernel<true, false>)
-                        : (dynamic ? gpy::fold_cash_tma_kernel<false, true> : gpy::fold_cash_tma_kernel<false, false>);
-    const int kslot = variant * 2 + (dynamic ? 1 : 0);
+    using FoldKernel = void (*)(const gpy::FoldParams);
+    static const FoldKernel kTable[8] = {
+        gpy::fold_cash_tma_kernel<false, false, false>, gpy::fold_cash_tma_kernel<false, true, false>,
+        gpy::fold_cash_tma_kernel<true, false, false>,  gpy::fold_cash_tma_kernel<true, true, false>,
+        gpy::fold_cash_tma_kernel<false, false, true>,  gpy::fold_cash_tma_kernel<false, true, true>,
+        gpy::fold_cash_tma_kernel<true, false, true>,   gpy::fold_cash_tma_kernel<true, true, true>};
+    const int kslot = (all_compact ? 4 : 0) + variant * 2 + (dynamic ? 1 : 0);
+    FoldKernel kern = kTable[kslot];
     if (lay.total > c->tma_smem_set[kslot]) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -1705,10 +1712,14 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
         (const void*)gpy::dedup_flag_kernel,
         (const void*)gpy::dedup_scan_kernel,
         (const void*)gpy::dedup_scatter_kernel,
-        (const void*)gpy::fold_cash_tma_kernel<false, false>,
-        (const void*)gpy::fold_cash_tma_kernel<false, true>,
-        (const void*)gpy::fold_cash_tma_kernel<true, false>,
-        (const void*)gpy::fold_cash_tma_kernel<true, true>,
+        (const void*)gpy::fold_cash_tma_kernel<false, false, false>,
+        (const void*)gpy::fold_cash_tma_kernel<false, true, false>,
+        (const void*)gpy::fold_cash_tma_kernel<true, false, false>,
+        (const void*)gpy::fold_cash_tma_kernel<true, true, false>,
+        (const void*)gpy::fold_cash_tma_kernel<false, false, true>,
+        (const void*)gpy::fold_cash_tma_kernel<false, true, true>,
+        (const void*)gpy::fold_cash_tma_kernel<true, false, true>,
+        (const void*)gpy::fold_cash_tma_kernel<true, true, true>,
         (const void*)gpy::fold_cash_generic_kernel,
         (const void*)gpy::reduce_stat_kernel,
         (const void*)gpy::peer_allreduce_kernel,

@@ -1017,7 +1017,9 @@ __host__ __device__ inline FoldSmem fold_tma_layout(int nT, int nR, int nRp, int
   return L;
 }
 
-template <bool WRITE_NPRED, bool DYNAMIC>
+// COMPACT: every dataset of the launch stores uint16 counts and a bit-packed mask (DatasetDev::compact).  A template
+// parameter, not a run-time flag: the block-uniform branch in the Cash pass cost 7 % of the kernel.
+template <bool WRITE_NPRED, bool DYNAMIC, bool COMPACT>
 __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const FoldParams P) {
   extern __shared__ __align__(128) unsigned char fold_raw[];
   float* es = reinterpret_cast<float*>(fold_raw + P.lay_es);
@@ -1101,8 +1103,8 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     uint32_t total = 0;
     if (D->tmaps) return;  // armed together with the tensor copies, after the barrier
     if (D->background && P.include_background) total += row * (uint32_t)D->nR;
-    if (D->counts) total += (D->compact ? row / 2u : row) * (uint32_t)D->nR;
-    if (D->counts && D->mask) total += (D->compact ? 16u : (uint32_t)npx) * (uint32_t)D->nR;
+    if (D->counts) total += (COMPACT ? row / 2u : row) * (uint32_t)D->nR;
+    if (D->counts && D->mask) total += (COMPACT ? 16u : (uint32_t)npx) * (uint32_t)D->nR;
     mbar_arrive_expect_tx(&bars[1], total);
   };
   auto issue_epi = [&](int item) {
@@ -1117,7 +1119,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
         const uint32_t nR = (uint32_t)D->nR;
         uint32_t total = 0;
         if (has_bkg) total += (uint32_t)kFoldTPX * 4u * nR;
-        const bool cmp = D->compact != 0;
+        constexpr bool cmp = COMPACT;
         if (has_counts) total += (uint32_t)kFoldTPX * (cmp ? 2u : 4u) * nR;
         if (has_mask) total += (cmp ? 16u : (uint32_t)kFoldTPX) * nR;
         mbar_arrive_expect_tx(&bars[1], total);
@@ -1133,7 +1135,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const float* cnt = D->counts;
     const uint8_t* msk = D->mask;
     const size_t PP = (size_t)D->P;
-    const bool cmp = D->compact != 0;
+    constexpr bool cmp = COMPACT;
     for (int i = (tid & 31) * (kFoldThreads / 32) + (tid >> 5); i < 3 * nR; i += kFoldThreads) {
       const int r = i / 3, which = i - 3 * r;
       const size_t off = (size_t)r * PP + p0;
@@ -1307,7 +1309,8 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
     const int p0 = (tile - Ds.tile_begin) * kFoldTPX;
     const int npx = min(kFoldTPX, (int)Ds.P - p0);
     const bool has_bkg = Ds.background && P.include_background, has_counts = Ds.counts != nullptr,
-               has_mask = Ds.mask != nullptr, cmp = Ds.compact != 0;
+               has_mask = Ds.mask != nullptr;
+    constexpr bool cmp = COMPACT;
     const int nchunks = nRp >> 3;
     const int* band = G * nchunks * 4 <= kBandSmem ? band_s : Ds.band;
     // work descriptor of this item (requested at the top of the previous item)
