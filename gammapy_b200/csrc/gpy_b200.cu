@@ -161,7 +161,8 @@ double evaluation_bin_size_min(int type, const double* sp) {  // spatial.py:568-
 
 // DiskSpatialModel._evaluate_norm_factor (spatial.py:951-969).  The reference integrates with
 // scipy.integrate.quad; the integrand is smooth and pi-periodic, so a composite Gauss-Legendre rule
-// converges to double precision (checked against quad in tests/test_spatial_gpu.py).
+// converges to double precision (the oracle integrates with scipy's quad: tests/test_gpu_parity.py, case
+// "disk-elongated").
 double disk_norm_factor(double r0, double e) {
   double semi_minor = r0 * std::sqrt(1 - e * e);
   double A = 1 / (std::sin(r0) * std::sin(r0));

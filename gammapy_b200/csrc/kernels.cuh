@@ -899,11 +899,10 @@ dedup_scatter_kernel(const unsigned char* __restrict__ dup, const int* __restric
 // prep_items_kernel (one warp per (tile, vector) item, after K0) resolves everything an item needs besides the
 // data cubes and the per-step numbers: the sources whose cutout overlaps the tile (first kFoldLMax as InstDev copies,
 // further ones as indices).  Nothing in a descriptor depends on the spectral or background parameters -- the fold
-// kernel reads the flux vectors and background factors K0 wrote straight from global memory (a few KB, L1
-// resident) -- so the host re-runs this kernel only when a cutout, a slot or the source list changes, not on the
-// steady-state steps of a fit.  The fold kernel fetches
-// the descriptor of the NEXT item with one bulk copy while it computes the current one, so its prologue is a
-// single mbarrier wait instead of a serial list build over global memory.
+// kernel stages the flux vectors and background factors K0 wrote (a few KB) in shared memory one item ahead -- so
+// the host re-runs this kernel only when a cutout, a slot or the source list changes, not on the steady-state steps
+// of a fit.  The fold kernel fetches the descriptor of the NEXT item with one bulk copy while it computes the
+// current one, so its prologue is a single mbarrier wait instead of a serial list build over global memory.
 constexpr int kFoldLMax = 4;       // overlapping sources held in registers by the fold kernel
 constexpr int kDescOverflow = 60;  // further overlapping sources per item (indices; slow path)
 struct DescLayout {
