@@ -633,7 +633,7 @@ def run_c5(args):
                 "what": "Datasets.stat_sum() with Parameter objects on the host"},
         "roofline": {"bound": "hbm", "achieved": alg / (kernel_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg / (kernel_us * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg, "kernel": "fold_cash_tma_kernel", "duration_us": kernel_us,
+                     "algorithmic_bytes_per_launch": alg, "kernel": "fold_cash_t64_kernel", "duration_us": kernel_us,
                      "note": "compact format: 4 nT P (shared exposure, read once per dataset) + 4 nR P + 2 nR P + nR P / 8"},
         "memory": {"bytes_per_dataset": per_ds, "shared_exposure_bytes": shared, "device_bytes_in_use": int(used),
                    "datasets_that_fit_180GB": int((180e9 - shared) // (per_ds + (used - shared - n_ds * per_ds) / n_ds)),
@@ -894,7 +894,7 @@ def run_ours(args):
                      "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum "
                                                          f"of the committed capture {traffic_src})",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                     "kernel": "fold_cash_tma_kernel", "duration_us": kernel_us, "launches_timed": int(kernel_launches),
+                     "kernel": "fold_cash_t64_kernel", "duration_us": kernel_us, "launches_timed": int(kernel_launches),
                      "step_us": ms_per_step * 1e3,
                      "note": "duration = mean of the kernel's own launches, CUDA events recorded by the library on its "
                              "stream around that launch during a repeat of the timed steps; step_us = whole step "

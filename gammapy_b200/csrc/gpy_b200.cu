@@ -25,6 +25,7 @@
 #include "kernels.cuh"
 #include "tsmap.cuh"
 #include "irf.cuh"
+#include "fold_t64.cuh"
 
 namespace {
 
@@ -289,11 +290,14 @@ struct gpy_context {
   double* stat_pinned = nullptr;
   int* nwork_pinned = nullptr;  // read-back of the batched worklist length
   size_t stat_pinned_cap = 0;
-  size_t ts_smem_set = 0, fold_smem_set = 0, conv_smem_set = 0, tma_smem_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  size_t ts_smem_set = 0, fold_smem_set = 0, conv_smem_set = 0, tma_smem_set[24] = {0};
   int tma_blocks_per_sm[2] = {0, 0};
   int num_sms = 0;
   bool force_generic = false;
   bool static_schedule = false;  // GPY_STATIC_SCHEDULE: never claim items dynamically
+  int t64_stages = 1;            // GPY_FOLD_T64 = 1 (three CTAs per SM, single-buffered inputs) or 2 (two CTAs, double-buffered)
+  bool use_t64 = true;           // GPY_FOLD_T64=0 switches the 64-pixel sub-tile kernel off (default: used whenever the launch is eligible)
+  int max_ctas_per_sm = 0;       // GPY_FOLD_CTAS_PER_SM (profiling): cap on resident fold CTAs per SM, 0 = occupancy limit
   bool no_desc_cache = false;  // GPY_NO_DESC_CACHE: run prep_items_kernel on every call
   std::vector<uint8_t> desc_key;  // what the descriptors in `desc` were built from (empty: none)
   bool no_dedup = false;  // GPY_NO_DEDUP: evaluate every item of a batch even when identical to vector 0's
@@ -351,7 +355,7 @@ struct gpy_dataset {
   DevBuf d_edges, d_nodes, d_ecenter, d_edisp, d_band, d_pdfc, d_omega, d_kflip, d_planes;
   DevBuf d_tmaps;             // 4 CUtensorMap: exposure, background, counts, mask (2-D [rows][P] tensors, box [rows][128])
   std::vector<DevBuf> retired_tmaps;  // earlier map blocks: a rewritten map gets a NEW address (descriptor caches)
-  bool has_tmaps = false;
+  bool has_tmaps = false, has_tmaps64 = false;
   std::vector<gpy::ConvPlane> planes;
   int max_h = 0, max_kw = 4;
   bool has_psf = false, has_diag = false;
@@ -585,7 +589,7 @@ int build_tmaps(gpy_dataset* ds) {
   ds->has_tmaps = false;
   const size_t P = (size_t)ds->geom.nx * ds->geom.ny;
   if (P % 16 != 0 || ds->geom.nx % 4 != 0 || P < (size_t)gpy::kFoldTPX) return GPY_OK;
-  alignas(64) CUtensorMap maps[4];
+  alignas(64) CUtensorMap maps[8];  // [0, 4): 128-pixel boxes, [4, 8): 64-pixel boxes (fold_cash_t64_kernel)
   std::memset(maps, 0, sizeof(maps));
   const int TPX = gpy::kFoldTPX;
   if (!encode_map(&maps[0], ds->exposure, 4, P, P * 4, ds->nT, TPX)) return GPY_OK;
@@ -598,6 +602,15 @@ int build_tmaps(gpy_dataset* ds) {
     if (ds->mask && !encode_map(&maps[3], ds->mask, 1, (size_t)ds->mask_row_bytes, (size_t)ds->mask_row_bytes, ds->nR, TPX / 8))
       return GPY_OK;
   }
+  ds->has_tmaps64 = encode_map(&maps[4], ds->exposure, 4, P, P * 4, ds->nT, TPX / 2) &&
+                    (!ds->background || encode_map(&maps[5], ds->background, 4, P, P * 4, ds->nR, TPX / 2));
+  if (ds->has_tmaps64 && !ds->compact)
+    ds->has_tmaps64 = (!ds->counts || encode_map(&maps[6], ds->counts, 4, P, P * 4, ds->nR, TPX / 2)) &&
+                      (!ds->mask || encode_map(&maps[7], ds->mask, 1, P, P, ds->nR, TPX / 2));
+  else if (ds->has_tmaps64)
+    ds->has_tmaps64 = (!ds->counts || encode_map(&maps[6], ds->counts, 2, P, P * 2, ds->nR, TPX / 2)) &&
+                      (!ds->mask || encode_map(&maps[7], ds->mask, 1, (size_t)ds->mask_row_bytes, (size_t)ds->mask_row_bytes,
+                                               ds->nR, TPX / 8));
   if (ds->d_tmaps.p) {  // never rewrite a tensor map in place: the GPU may hold the old one in its descriptor cache
     ds->retired_tmaps.push_back(ds->d_tmaps);
     ds->d_tmaps = DevBuf();
@@ -1341,8 +1354,13 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         !al16(ds->mask) || ds->weight != nullptr || P64 * (size_t)std::max(ds->nT, ds->nR) > (size_t)INT32_MAX)
       tma_ok = false;
   }
-  const gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G, max_pdfc_rows, all_compact);
+  gpy::FoldSmem lay = gpy::fold_tma_layout(max_nT, max_nR, max_nRp, max_G, max_pdfc_rows, all_compact);
   if (any_compact && !all_compact) tma_ok = false;  // mixed storage formats in one launch: the any-shape kernel
+  // 64-pixel sub-tile kernel (three CTAs per SM): tensor maps everywhere, one edisp group, nT <= 64, nR <= 32
+  bool t64 = c->use_t64 && tma_ok && max_G == 1 && max_nT <= 64 && max_nRp <= 32;
+  for (int d = 0; d < D && t64; ++d) t64 = rq.datasets[d]->has_tmaps && rq.datasets[d]->has_tmaps64;
+  const int t64_stages = c->t64_stages;
+  if (t64) lay = gpy::fold_t64_layout(max_nT, max_nR, max_nRp, max_pdfc_rows, all_compact, t64_stages);
   if (lay.total > (size_t)c->max_smem_optin || c->force_generic ||
       max_tile_overlap > gpy::kFoldLMax + gpy::kDescOverflow)
     tma_ok = false;
@@ -1451,7 +1469,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   fp.smem_G = max_G;
   fp.smem_pdfc_rows = max_pdfc_rows;
   if (!c->zeros.p) {  // [0, 128) zeros, [128, 132) work counter, [256, 2304) fast_log table
-    GPY_TRY(c->zeros.reserve(256 + 128 * 16));
+    GPY_TRY(c->zeros.reserve(256 + 128 * 16 + 64 * 16));
     CUDA_TRY(cudaMemsetAsync(c->zeros.p, 0, 256, c->stream));
     static double tab[256];
     for (int i = 0; i < 128; ++i) {
@@ -1460,10 +1478,18 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
       tab[2 * i + 1] = -std::log(inv);
     }
     CUDA_TRY(cudaMemcpyAsync((uint8_t*)c->zeros.p + 256, tab, sizeof(tab), cudaMemcpyHostToDevice, c->stream));
+    static double tab64[128];
+    for (int i = 0; i < 64; ++i) {
+      const double inv = 1.0 / (1.0 + (i + 0.5) / 64.0);
+      tab64[2 * i] = inv;
+      tab64[2 * i + 1] = -std::log(inv);
+    }
+    CUDA_TRY(cudaMemcpyAsync((uint8_t*)c->zeros.p + 256 + 2048, tab64, sizeof(tab64), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
   }
   fp.zeros = (const float*)c->zeros.p;
   fp.logtab = (const double2*)((const uint8_t*)c->zeros.p + 256);
+  fp.logtab64 = (const double2*)((const uint8_t*)c->zeros.p + 256 + 2048);
   const size_t n_items = (size_t)B * n_tiles;
   const unsigned char* reduce_dup = nullptr;
   const int variant = rq.npred_out ? 1 : 0;
@@ -1558,8 +1584,17 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
         gpy::fold_cash_tma_kernel<true, false, false>,  gpy::fold_cash_tma_kernel<true, true, false>,
         gpy::fold_cash_tma_kernel<false, false, true>,  gpy::fold_cash_tma_kernel<false, true, true>,
         gpy::fold_cash_tma_kernel<true, false, true>,   gpy::fold_cash_tma_kernel<true, true, true>};
-    const int kslot = (all_compact ? 4 : 0) + variant * 2 + (dynamic ? 1 : 0);
-    FoldKernel kern = kTable[kslot];
+    static const FoldKernel kTable64[16] = {
+        gpy::fold_cash_t64_kernel<false, false, false, 1>, gpy::fold_cash_t64_kernel<false, true, false, 1>,
+        gpy::fold_cash_t64_kernel<true, false, false, 1>,  gpy::fold_cash_t64_kernel<true, true, false, 1>,
+        gpy::fold_cash_t64_kernel<false, false, true, 1>,  gpy::fold_cash_t64_kernel<false, true, true, 1>,
+        gpy::fold_cash_t64_kernel<true, false, true, 1>,   gpy::fold_cash_t64_kernel<true, true, true, 1>,
+        gpy::fold_cash_t64_kernel<false, false, false, 2>, gpy::fold_cash_t64_kernel<false, true, false, 2>,
+        gpy::fold_cash_t64_kernel<true, false, false, 2>,  gpy::fold_cash_t64_kernel<true, true, false, 2>,
+        gpy::fold_cash_t64_kernel<false, false, true, 2>,  gpy::fold_cash_t64_kernel<false, true, true, 2>,
+        gpy::fold_cash_t64_kernel<true, false, true, 2>,   gpy::fold_cash_t64_kernel<true, true, true, 2>};
+    const int kslot = (t64 ? 8 * t64_stages : 0) + (all_compact ? 4 : 0) + variant * 2 + (dynamic ? 1 : 0);
+    FoldKernel kern = t64 ? kTable64[kslot - 8] : kTable[kslot];
     if (lay.total > c->tma_smem_set[kslot]) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -1569,6 +1604,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, gpy::kFoldThreads, lay.total));
     per_sm = std::max(per_sm, 1);
+    if (c->max_ctas_per_sm > 0) per_sm = std::min(per_sm, c->max_ctas_per_sm);
     const unsigned grid = (unsigned)std::min(n_work_host, (size_t)per_sm * c->num_sms);
     if (dynamic) {
       fp.counter = (unsigned*)((uint8_t*)c->zeros.p + 128);
@@ -1687,6 +1723,11 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
   c->force_generic = std::getenv("GPY_FORCE_GENERIC_FOLD") != nullptr;
   c->no_dedup = std::getenv("GPY_NO_DEDUP") != nullptr;
   c->static_schedule = std::getenv("GPY_STATIC_SCHEDULE") != nullptr;
+  if (const char* e = std::getenv("GPY_FOLD_T64")) {
+    c->use_t64 = std::atoi(e) != 0;
+    c->t64_stages = std::atoi(e) == 2 ? 2 : 1;
+  }
+  if (const char* e = std::getenv("GPY_FOLD_CTAS_PER_SM")) c->max_ctas_per_sm = std::atoi(e);
   c->no_desc_cache = std::getenv("GPY_NO_DESC_CACHE") != nullptr;
   c->replay.disabled = std::getenv("GPY_NO_REPLAY") != nullptr;
   if (const char* m = std::getenv("GPY_FOLD_KERNEL")) c->fold_mode = std::atoi(m);
@@ -1721,6 +1762,22 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
         (const void*)gpy::fold_cash_tma_kernel<false, true, true>,
         (const void*)gpy::fold_cash_tma_kernel<true, false, true>,
         (const void*)gpy::fold_cash_tma_kernel<true, true, true>,
+        (const void*)gpy::fold_cash_t64_kernel<false, false, false, 1>,
+        (const void*)gpy::fold_cash_t64_kernel<false, false, false, 2>,
+        (const void*)gpy::fold_cash_t64_kernel<false, true, false, 1>,
+        (const void*)gpy::fold_cash_t64_kernel<false, true, false, 2>,
+        (const void*)gpy::fold_cash_t64_kernel<true, false, false, 1>,
+        (const void*)gpy::fold_cash_t64_kernel<true, false, false, 2>,
+        (const void*)gpy::fold_cash_t64_kernel<true, true, false, 1>,
+        (const void*)gpy::fold_cash_t64_kernel<true, true, false, 2>,
+        (const void*)gpy::fold_cash_t64_kernel<false, false, true, 1>,
+        (const void*)gpy::fold_cash_t64_kernel<false, false, true, 2>,
+        (const void*)gpy::fold_cash_t64_kernel<false, true, true, 1>,
+        (const void*)gpy::fold_cash_t64_kernel<false, true, true, 2>,
+        (const void*)gpy::fold_cash_t64_kernel<true, false, true, 1>,
+        (const void*)gpy::fold_cash_t64_kernel<true, false, true, 2>,
+        (const void*)gpy::fold_cash_t64_kernel<true, true, true, 1>,
+        (const void*)gpy::fold_cash_t64_kernel<true, true, true, 2>,
         (const void*)gpy::fold_cash_generic_kernel,
         (const void*)gpy::reduce_stat_kernel,
         (const void*)gpy::peer_allreduce_kernel,

@@ -494,6 +494,7 @@ struct FoldParams {
   int pad_;
   double log_trunc;         // log((double)(float)1e-25): Cython narrows the constant to C float
   const double2* logtab;    // fast_log table, 128 entries
+  const double2* logtab64;  // 64-entry variant (fold_cash_t64_kernel)
 };
 
 constexpr int kFoldTPX = 128;      // pixels per tile
@@ -1037,7 +1038,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
   __shared__ double wsum[kFoldThreads / 32];
   __shared__ int2 nxt_s;         // {worklist position, item} claimed for the iteration after the next
   __shared__ DatasetDev Ds;      // table entry of the dataset the current item belongs to: no global loads per item
-  __shared__ int band_s[kBandSmem];
+  __shared__ __align__(16) int band_s[kBandSmem];  // read as int4
   __shared__ double2 logtab_s[128];
   if (threadIdx.x < 128) logtab_s[threadIdx.x] = P.logtab[threadIdx.x];  // published by the barrier behind the mbarrier initialisation
 

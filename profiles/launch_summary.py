@@ -16,7 +16,7 @@ print("# includes the one-off cold evaluation (spatial_fill + psf_conv launches 
 for k, v in sorted(rows.items(), key=lambda kv: -sum(kv[1])):
     print(f"{k[:60]:60s} n={len(v):4d} total={sum(v):10.1f}us mean={sum(v) / len(v):9.2f}us share={100 * sum(v) / tot:5.1f}%")
 steady = {k: sum(v) / len(v) for k, v in rows.items()
-          if "fold_cash_tma_kernel<0" in k or "reduce_stat" in k or "spectral_flux" in k}
+          if "fold_cash_tma_kernel<0" in k or "fold_cash_t64_kernel<0" in k or "reduce_stat" in k or "spectral_flux" in k}
 s = sum(steady.values())
 print("# steady-state step (one launch of each; prep_items_kernel only runs when a cutout or the source list changes): " +
       ", ".join(f"{k.split('::')[-1][:26]} {v:.1f}us ({100 * v / s:.1f}%)" for k, v in steady.items()))

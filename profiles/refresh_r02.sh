@@ -3,7 +3,7 @@
 #   gpurun_out/fold_r02.ncu-rep, gpurun_out/psf_r02.ncu-rep, gpurun_out/launches_r02.csv
 set -e
 (
-  echo "# ncu --set full --clock-control none --import-source on, fold_cash_tma_kernel<0,1,0> as shipped at the end of round 2 (C3, B = 1)"
+  echo "# ncu --set full --clock-control none --import-source on, fold_cash_t64_kernel<0,1,0,1> as shipped at the end of round 2 (C3, B = 1)"
   echo "# command: python bench.py --steps 3 --warmup 3 --no-extras --no-cpu-baseline, 5th launch of the kernel (profiles/capture_r02.sh)"
   python profiles/ncu_summary.py gpurun_out/fold_r02.ncu-rep
   python profiles/ncu_lines.py gpurun_out/fold_r02.ncu-rep 30
