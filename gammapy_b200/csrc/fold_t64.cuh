@@ -22,6 +22,9 @@
 
 namespace gpy {
 
+#ifndef GPY_T64_P2_PAIR  // phase 2: thread = two pixels x four reco bins (else one pixel x eight)
+#define GPY_T64_P2_PAIR 1
+#endif
 constexpr int kT64 = 64;          // pixels per sub-tile
 constexpr int kT64Slots = 16;     // true-energy slots of phase 1 (256 threads / 16 quads)
 constexpr int kT64Rows = 4;       // rows per thread: t = slot + 16 k
@@ -212,7 +215,11 @@ __global__ void __launch_bounds__(kFoldThreads, STAGES == 1 ? 3 : 2) fold_cash_t
   uint32_t ksub = 0;      // sub-tiles done by this CTA: stage ksub & 1 when double buffered
 
   const int q = tid & 15, slot = tid >> 4;    // phase 1: 16 pixel quads x 16 energy slots
+#if GPY_T64_P2_PAIR
+  const int px = (tid & 31) * 2, cslot = tid >> 6, rh = ((tid >> 5) & 1) * 4;  // phase 2: 32 pixel pairs x 4 reco chunks x 2 halves of a chunk
+#else
   const int px = tid & 63, cslot = tid >> 6;  // phase 2: 64 pixels x 4 reco chunks
+#endif
 
   for (;; ++it) {
     const uint32_t parity = it & 1u;
@@ -381,6 +388,21 @@ __global__ void __launch_bounds__(kFoldThreads, STAGES == 1 ? 3 : 2) fold_cash_t
           const int4 bnd = *reinterpret_cast<const int4*>(band_s + cslot * 4);
           const double* vrow = vs + px;
           const double* prow = pdf_s + (bnd.z - bnd.x) * 8;
+#if GPY_T64_P2_PAIR
+          for (int t = bnd.x; t < bnd.y; ++t) {  // two pixels x four reco bins: three 128-bit loads per eight FMAs
+            const double2 v = *reinterpret_cast<const double2*>(vrow + t * kT64);
+            const double2 m0 = *reinterpret_cast<const double2*>(prow + t * 8 + rh);
+            const double2 m1 = *reinterpret_cast<const double2*>(prow + t * 8 + rh + 2);
+            acc[0] = fma(v.x, m0.x, acc[0]);
+            acc[1] = fma(v.x, m0.y, acc[1]);
+            acc[2] = fma(v.x, m1.x, acc[2]);
+            acc[3] = fma(v.x, m1.y, acc[3]);
+            acc[4] = fma(v.y, m0.x, acc[4]);
+            acc[5] = fma(v.y, m0.y, acc[5]);
+            acc[6] = fma(v.y, m1.x, acc[6]);
+            acc[7] = fma(v.y, m1.y, acc[7]);
+          }
+#else
           for (int t = bnd.x; t < bnd.y; ++t) {
             const double v = vrow[t * kT64];
             const double2 m0 = *reinterpret_cast<const double2*>(prow + t * 8);
@@ -396,6 +418,7 @@ __global__ void __launch_bounds__(kFoldThreads, STAGES == 1 ? 3 : 2) fold_cash_t
             acc[6] = fma(v, m3.x, acc[6]);
             acc[7] = fma(v, m3.y, acc[7]);
           }
+#endif
         }
         __syncthreads();  // v is rewritten by the parking step
       } else if (!DB && expo_after) {
@@ -406,6 +429,26 @@ __global__ void __launch_bounds__(kFoldThreads, STAGES == 1 ? 3 : 2) fold_cash_t
       mbar_wait(&bars[2 + st], (sparity >> st) & 1u);
       sparity ^= 1u << st;
       double* mus = vs;
+#if GPY_T64_P2_PAIR
+      if (cslot < nchunks && px < npxh) {  // (npxh is even: P % 16 == 0 on the tensor-map path)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = 8 * cslot + rh + j;
+          if (r >= nR) break;
+          double mu0 = acc[j], mu1 = acc[4 + j];
+          if (P.include_background) {
+            if (has_bkg) {
+              const float2 bg = *reinterpret_cast<const float2*>(bs + r * kT64 + px);
+              mu0 += (double)bg.x * bkgfac[r];
+              mu1 += (double)bg.y * bkgfac[r];
+            }
+            if (mu0 < 0.0) mu0 = 0.0;  // npred_total.data[npred_total.data < 0.0] = 0 (map.py:787)
+            if (mu1 < 0.0) mu1 = 0.0;
+          }
+          *reinterpret_cast<double2*>(mus + r * kT64 + px) = make_double2(mu0, mu1);
+        }
+      }
+#else
       if (cslot < nchunks && px < npxh) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -419,6 +462,7 @@ __global__ void __launch_bounds__(kFoldThreads, STAGES == 1 ? 3 : 2) fold_cash_t
           mus[r * kT64 + px] = mu;
         }
       }
+#endif
       __syncthreads();
       const bool stage_next = last_sub && next < n_items;
       double dyn0 = 0.0, dyn1 = 0.0;
