@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(kFoldThreads, STAGES == 1 ? 3 : 2) fold_cash_t
         // ---- phase 1: v[t][p] = 1e4 * exposure[t,p] * sum_s F_s[t] * conv_s[t,p], all true bins in one pass ----
         if (nl <= 2) {
 #pragma unroll
-          constexpr int RB = DB ? 4 : 2;  // rows in flight (two loads each): the register budget of the variant
+          constexpr int RB = DB ? 4 : 2;  // rows in flight (two loads each); four instead of two: no gain at three CTAs per SM
           for (int kb = 0; kb < kT64Rows; kb += RB) {
             float4 c0[RB], c1[RB];
 #pragma unroll
