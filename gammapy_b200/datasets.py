@@ -318,6 +318,32 @@ class MapDataset:
         eng = self._get_engine()
         return eng.source_state(0, self._source_names.index(model_name))
 
+    # -- on-disk format (datasets/map.py:1556-1780; gammapy_b200/fitsio.py) ---------------------------------------------
+    def to_hdulist(self):
+        from . import fitsio
+
+        return fitsio.dataset_to_hdus(self)
+
+    @classmethod
+    def from_hdulist(cls, hdulist, name=None):
+        from . import fitsio
+
+        return fitsio.dataset_from_hdus(hdulist, name=name)
+
+    def write(self, filename, overwrite=False):
+        """Write the maps and IRFs as one GADF FITS file (``MapDataset.write``, datasets/map.py:1741-1780); models are
+        not part of the file, as in the reference."""
+        from . import fitsio
+
+        fitsio.write_hdus(str(filename), self.to_hdulist(), overwrite=overwrite)
+
+    @classmethod
+    def read(cls, filename, name=None):
+        """``MapDataset.read`` (datasets/map.py:1702-1739)."""
+        from . import fitsio
+
+        return cls.from_hdulist(fitsio.read_hdus(str(filename)), name=name)
+
     def evaluator_irf(self, model_name, with_kernel=True):
         """IRFs one model's evaluator looked up at its position (datasets with a PSFMap / EDispKernelMap on a spatial
         grid; MapEvaluator.update, datasets/evaluator.py:196-227): dict with the PSF kernel ``(nT, K, K)``, its side
