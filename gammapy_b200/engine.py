@@ -289,6 +289,9 @@ class LikelihoodEngine:
         """The C handle of a dataset holds ONE model table: (re)install this engine's parameter columns when
         another engine (e.g. ``MapDataset.npred`` vs ``Datasets.stat_sum``) configured it last."""
         for ds in self.datasets:
+            if ds._device is None:
+                raise RuntimeError("stale LikelihoodEngine: the dataset's maps or storage format changed after the engine "
+                                   "was built; get a new one (Datasets._get_engine / MapDataset._get_engine)")
             if ds._device.models_owner is not self:
                 self._set_models(ds, ds._device)
 

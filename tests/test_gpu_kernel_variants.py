@@ -1,0 +1,65 @@
+"""The fold + Cash path has three staged kernels: the 64-pixel sub-tile kernel (default when eligible), the 128-pixel
+kernel (GPY_FOLD_T64=0; also what launches with two edisp groups or long axes use) and the double-buffered 64-pixel
+variant (GPY_FOLD_T64=2), plus the any-shape kernel (GPY_FOLD_KERNEL=2).  The choice is made per context from the
+environment, so every variant runs in its own process on the same seeded dataset; all must agree with the oracle and
+with each other (the per-tile partial sums are added in the same fixed order: only the in-tile order differs)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r"""
+import json, sys
+sys.path.insert(0, %r)
+import numpy as np
+from gammapy_b200 import Map, configs
+from oracle import adapter
+out = {}
+for key, make in (("c2", lambda: configs.make_c2(width=(4.0, 4.0), mask_radius=1.2)),
+                  ("c3s", lambda: configs.make_c3(width=(6.0, 3.0), n_sources=9))):
+    ds = make()
+    de = adapter.evaluator_for(ds, conv="exact64")
+    ds.counts = Map.from_geom(ds._geom, data=de.fake(4), dtype=float)
+    stat = ds.stat_sum()
+    npred = ds.npred().data
+    want = de.npred()
+    eng = ds._get_engine()
+    grid = np.tile(eng.values(), (3, 1))
+    col = [i for i, p in enumerate(eng.parameters) if p.name in ("index", "alpha")][0]
+    grid[:, col] += [0.0, 0.05, 0.1]
+    scan = [float(v) for v in eng.stat_sum(grid)]
+    ds.storage = "compact"  # (rebuilds the HBM mirror: the engine above is stale from here on)
+    out[key] = {"stat": stat, "oracle": de.stat_sum(), "rel": float(np.max(np.abs(npred - want) / np.maximum(want, 1e-300))),
+                "scan": scan, "compact": ds.stat_sum()}
+print("RESULT " + json.dumps(out))
+""" % ROOT
+
+
+def _run(env):
+    e = dict(os.environ)
+    e.update(env)
+    res = subprocess.run([sys.executable, "-c", SCRIPT], capture_output=True, text=True, env=e, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    return json.loads(line[7:])
+
+
+def test_every_staged_kernel_variant_agrees(ctx):
+    runs = {name: _run(env) for name, env in (("t64", {"GPY_FOLD_T64": "1"}), ("t128", {"GPY_FOLD_T64": "0"}),
+                                              ("t64-double-buffered", {"GPY_FOLD_T64": "2"}),
+                                              ("any-shape", {"GPY_FOLD_KERNEL": "2"}))}
+    for name, out in runs.items():
+        for key, r in out.items():
+            assert abs(r["stat"] - r["oracle"]) < 1e-3, (name, key, r)
+            assert r["rel"] < 1e-5, (name, key, r)
+            assert r["compact"] == r["stat"], (name, key, r)       # same counts and mask, other storage format
+            assert r["scan"][0] == r["stat"], (name, key, r)       # batched call, vector 0 = the single evaluation
+    ref = runs["t64"]
+    for name, out in runs.items():
+        for key, r in out.items():
+            assert abs(r["stat"] - ref[key]["stat"]) < 1e-6 * abs(r["stat"]) + 1e-6, (name, key)
