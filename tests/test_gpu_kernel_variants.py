@@ -63,3 +63,22 @@ def test_every_staged_kernel_variant_agrees(ctx):
     for name, out in runs.items():
         for key, r in out.items():
             assert abs(r["stat"] - ref[key]["stat"]) < 1e-6 * abs(r["stat"]) + 1e-6, (name, key)
+
+
+@pytest.mark.parametrize("n_reco,n_true", [(36, 70), (12, 66), (34, 40)])
+def test_long_axes_use_the_128_pixel_kernel(ctx, n_reco, n_true):
+    """More than 32 reco bins (two sweeps over the reco chunks) or more than 64 true bins (three phase-1 passes): outside
+    the 64-pixel kernel's shapes, served by the 128-pixel kernel; per-bin npred and the statistic against the oracle."""
+    import numpy as np
+
+    from gammapy_b200 import Map, configs
+    from oracle import adapter
+
+    ds = configs.make_dataset(width=(3.0, 2.0), n_reco=n_reco, n_true=n_true, e_reco=(0.1, 100.0), e_true=(0.03, 300.0),
+                              mask_radius=0.8, name="long")
+    ds.models = configs.c2_models("long")
+    de = adapter.evaluator_for(ds, conv="exact64")
+    got, want = ds.npred().data, de.npred()
+    assert np.max(np.abs(got - want) / np.maximum(want, 1e-300)) < 1e-5
+    ds.counts = Map.from_geom(ds._geom, data=de.fake(9), dtype=float)
+    assert abs(ds.stat_sum() - de.stat_sum()) < 1e-3
