@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["RESULT_NAMES", "compute_ts_map", "BrentqFluxEstimator", "TSMapEstimator", "ParameterEstimator"]
+__all__ = ["RESULT_NAMES", "compute_ts_map", "BrentqFluxEstimator", "TSMapEstimator", "ParameterEstimator", "FluxPointsEstimator"]
 
 RESULT_NAMES = ("norm", "norm_err", "niter", "ts", "stat", "stat_null", "success", "npred", "npred_excess")
 
@@ -213,3 +213,110 @@ class ParameterEstimator:
             if "scan" in self.selection_optional:
                 result.update(self.estimate_scan(datasets, parameter))
         return result
+
+
+# -------------------------------------------------------------------------------------------------------------
+# FluxPointsEstimator (estimators/points/sed.py:41-300, estimators/flux.py): one norm fit of the source per energy
+# group.  The reference slices the datasets to the group (Datasets.slice_by_energy) and scales the source's spectrum
+# with a norm parameter (ScaleSpectralModel); here the fit mask is restricted to the group's reco bins -- the same
+# likelihood terms, on the resident cubes -- and the norm is the source's amplitude in units of its reference value
+# (the amplitude is a pure scale factor of all three spectral models).  Every fit is ParameterEstimator on the GPU
+# likelihood.
+# -------------------------------------------------------------------------------------------------------------
+class FluxPointsEstimator:
+    tag = "FluxPointsEstimator"
+
+    def __init__(self, energy_edges, source=0, n_sigma=1, n_sigma_ul=2, selection_optional=None, fit=None, reoptimize=False):
+        self.energy_edges = np.asarray(energy_edges, dtype=float)
+        if self.energy_edges.ndim != 1 or len(self.energy_edges) < 2 or np.any(np.diff(self.energy_edges) <= 0):
+            raise ValueError("energy_edges must be an increasing 1-D array of at least two values [TeV]")
+        self.source = source
+        self.reoptimize = reoptimize
+        self._estimator = ParameterEstimator(n_sigma=n_sigma, n_sigma_ul=n_sigma_ul, null_value=0.0,
+                                             selection_optional=selection_optional, fit=fit, reoptimize=True)
+
+    def _source_model(self, datasets):
+        from .modeling.models import SkyModel
+
+        sky = [m for ds in datasets for m in (ds.models or []) if isinstance(m, SkyModel)]
+        unique = list({id(m): m for m in sky}.values())
+        if isinstance(self.source, str):
+            found = [m for m in unique if m.name == self.source]
+            if not found:
+                raise KeyError(self.source)
+            return found[0]
+        return unique[self.source]
+
+    @staticmethod
+    def _group(axis, emin, emax):
+        """Reco bins of ``axis`` inside [emin, emax] (the bins Datasets.slice_by_energy keeps: edges matched to 1e-3)."""
+        edges = axis.edges
+        lo = np.isclose(edges[:-1], emin, rtol=1e-3) | (edges[:-1] > emin)
+        hi = np.isclose(edges[1:], emax, rtol=1e-3) | (edges[1:] < emax)
+        return lo & hi
+
+    def run(self, datasets):
+        from .datasets import Datasets, MapDataset
+        from .maps import Map
+
+        if isinstance(datasets, MapDataset):
+            datasets = Datasets([datasets])
+        model = self._source_model(datasets)
+        amplitude = model.spectral_model.amplitude
+        amp_ref = amplitude.value
+        if not amp_ref > 0:
+            raise ValueError("the source needs a positive reference amplitude")
+        saved_masks = [ds.mask_fit for ds in datasets]
+        rows = []
+        try:
+            for emin, emax in zip(self.energy_edges[:-1], self.energy_edges[1:]):
+                groups = [self._group(ds._geom.axes["energy"], emin, emax) for ds in datasets]
+                contributing = [g for g in groups if np.any(g)]
+                e_lo = min(ds._geom.axes["energy"].edges[:-1][g].min() for ds, g in zip(datasets, groups) if np.any(g)) \
+                    if contributing else emin
+                e_hi = max(ds._geom.axes["energy"].edges[1:][g].max() for ds, g in zip(datasets, groups) if np.any(g)) \
+                    if contributing else emax
+                e_ref = float(np.sqrt(e_lo * e_hi))
+                ref_dnde = float(model.spectral_model(e_ref))
+                row = {"e_ref": e_ref, "e_min": float(e_lo), "e_max": float(e_hi), "ref_dnde": ref_dnde}
+                if not contributing:
+                    row.update({"norm": np.nan, "norm_err": np.nan, "ts": np.nan, "stat": np.nan, "stat_null": np.nan,
+                                "success": False})
+                    rows.append(row)
+                    continue
+                for ds, g, base in zip(datasets, groups, saved_masks):
+                    sel = np.zeros(ds._geom.data_shape, dtype=bool)
+                    sel[g] = True
+                    if base is not None:
+                        sel &= np.asarray(base.data, dtype=bool)
+                    ds.mask_fit = Map.from_geom(ds._geom, data=sel, dtype=bool)
+                pars = list(datasets.parameters)
+                with _restore_status(pars):
+                    for p in pars:  # the spectral shape of the source is fixed; other parameters only with reoptimize
+                        if p is not amplitude and (not self.reoptimize or any(p is q for q in model.parameters)):
+                            p.frozen = True
+                    amplitude.frozen = False
+                    res = self._estimator.run(datasets, amplitude)
+                row.update({"norm": res["amplitude"] / amp_ref, "norm_err": res["amplitude_err"] / amp_ref, "ts": res["ts"],
+                            "stat": res["stat"], "stat_null": res["stat_null"], "success": bool(res["success"])})
+                for key in ("amplitude_errn", "amplitude_errp", "amplitude_ul"):
+                    if key in res:
+                        row[key.replace("amplitude", "norm")] = res[key] / amp_ref
+                rows.append(row)
+        finally:
+            for ds, base in zip(datasets, saved_masks):
+                ds.mask_fit = base
+            amplitude.value = amp_ref
+        out = {k: np.array([r.get(k, np.nan) for r in rows]) for k in rows[0]}
+        for r in rows:
+            for k in r:
+                if k not in out:
+                    out[k] = np.array([q.get(k, np.nan) for q in rows])
+        with np.errstate(invalid="ignore"):
+            out["sqrt_ts"] = np.where(out["ts"] > 0, np.sqrt(np.abs(out["ts"])), -np.sqrt(np.abs(out["ts"])))
+        out["dnde"] = out["norm"] * out["ref_dnde"]
+        out["dnde_err"] = out["norm_err"] * out["ref_dnde"]
+        for key in ("norm_errn", "norm_errp", "norm_ul"):
+            if key in out:
+                out[key.replace("norm", "dnde")] = out[key] * out["ref_dnde"]
+        return out

@@ -279,3 +279,47 @@ def test_parameter_estimator_gpu_vs_oracle(ctx):
     assert abs(gpu["ts"] - cpu["ts"]) < 2e-3
     for key in ("amplitude_errp", "amplitude_errn", "amplitude_ul"):
         assert_allclose(gpu[key], cpu[key], rtol=2e-2)
+
+
+def test_flux_points_gpu_vs_oracle_profile(ctx):
+    """SURVEY 8f N3 (estimators/points/sed.py:41-300): one norm fit of the source per energy group, all other parameters
+    fixed.  Checked against an independent computation: the oracle's signal and background cubes, the Cash sum over the
+    group's masked bins as a function of the norm, minimised with scipy."""
+    import scipy.optimize
+
+    from gammapy_b200 import Map, configs
+    from gammapy_b200.estimators import FluxPointsEstimator
+    from oracle import adapter, cash
+
+    ds = configs.make_c1(width=(2.0, 2.0), mask_radius=0.9)
+    de = adapter.evaluator_for(ds, conv="exact64")
+    counts = de.fake(21)
+    ds.counts = Map.from_geom(ds._geom, data=counts, dtype=float)
+    axis = ds._geom.axes["energy"]
+    edges = axis.edges[::2]  # five groups of two reco bins
+    amp0 = ds.models["model-simu"].spectral_model.amplitude.value
+    fpe = FluxPointsEstimator(energy_edges=edges, source="model-simu", selection_optional=["ul"])
+    got = fpe.run(ds)
+    assert ds.models["model-simu"].spectral_model.amplitude.value == amp0 and ds.mask_fit is not None
+    assert np.all(got["success"]) and got["norm"].shape == (5,)
+    np.testing.assert_allclose(got["e_min"], edges[:-1], rtol=1e-12)
+    np.testing.assert_allclose(got["e_ref"], np.sqrt(edges[:-1] * edges[1:]), rtol=1e-12)
+    signal, _ = de.npred_signal(per_model=True)
+    bkg = de.npred_background()
+    mask = np.asarray(ds.mask.data, bool)
+    for k in range(5):
+        sel = np.zeros_like(mask)
+        sel[2 * k:2 * k + 2] = True
+        sel &= mask
+
+        def stat(norm):
+            mu = np.maximum(norm * signal + bkg, 0.0)
+            return cash.cash_sum(counts[sel], mu[sel])
+
+        best = scipy.optimize.minimize_scalar(stat, bracket=(0.5, 1.5), tol=1e-12)
+        assert abs(got["norm"][k] - best.x) < 0.02 * got["norm_err"][k], (k, got["norm"][k], best.x, got["norm_err"][k])
+        assert abs(got["ts"][k] - (stat(0.0) - best.fun)) < 2e-2 + 1e-6 * abs(got["ts"][k])
+        assert got["norm_ul"][k] > got["norm"][k] + got["norm_err"][k]
+        assert_allclose(got["dnde"][k], got["norm"][k] * got["ref_dnde"][k])
+    # the simulated source has norm 1: the points scatter around it
+    assert np.all(np.abs(got["norm"] - 1.0) < 5 * got["norm_err"])
