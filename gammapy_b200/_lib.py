@@ -16,7 +16,11 @@ class GeomDesc(C.Structure):
     _fields_ = [
         ("nx", C.c_int32), ("ny", C.c_int32), ("n_true", C.c_int32), ("n_reco", C.c_int32),
         ("binsz", C.c_double), ("crval_lon", C.c_double), ("crpix_x", C.c_double), ("crpix_y", C.c_double),
+        ("crval_lat", C.c_double), ("proj", C.c_int32), ("pad_", C.c_int32),
     ]
+
+
+PROJECTIONS = {"CAR": 0, "TAN": 1}
 
 
 class DatasetDesc(C.Structure):

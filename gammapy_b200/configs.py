@@ -14,7 +14,7 @@ FRAME = "galactic"
 
 def make_dataset(width=(4.0, 4.0), binsz=0.02, n_reco=10, n_true=20, e_reco=(0.1, 10.0), e_true=(0.03, 30.0),
                  name="c1", exposure_scale=1.0, pointing_offset=(0.0, 0.0), mask_radius=1.8, skydir=(0.0, 0.0),
-                 falloff="radial"):
+                 falloff="radial", proj="CAR"):
     """One MapDataset with smooth synthetic IRFs (no models, no counts).
 
     ``falloff``: "radial" = exp(-(theta / 2 deg)^2 / 2) about the pointing (one observation, SURVEY.md §8d);
@@ -22,7 +22,7 @@ def make_dataset(width=(4.0, 4.0), binsz=0.02, n_reco=10, n_true=20, e_reco=(0.1
     low-energy bin of the map holds counts)."""
     energy_axis = MapAxis.from_energy_bounds(e_reco[0], e_reco[1], nbin=n_reco, unit="TeV")
     energy_axis_true = MapAxis.from_energy_bounds(e_true[0], e_true[1], nbin=n_true, unit="TeV", name="energy_true")
-    geom = WcsGeom.create(skydir=skydir, binsz=binsz, width=width, frame=FRAME, proj="CAR", axes=[energy_axis])
+    geom = WcsGeom.create(skydir=skydir, binsz=binsz, width=width, frame=FRAME, proj=proj, axes=[energy_axis])
     ds = MapDataset.create(geom=geom, energy_axis_true=energy_axis_true, name=name)
     center = (skydir[0] + pointing_offset[0], skydir[1] + pointing_offset[1])
     if falloff == "latitude":

@@ -67,7 +67,15 @@ constexpr int kSlotsHardCap = 96;      // beyond this the per-call extras are tr
 struct GeomH {
   int nx, ny;
   double binsz, crval_lon, crpix_x, crpix_y;
+  double crval_lat = 0.0;
+  int proj = 0;  // gpy_projection: 0 CAR about the equator, 1 TAN about (crval_lon, crval_lat)
 };
+GeomH geom_from_desc(const gpy_geom_desc& g) {
+  GeomH h{g.nx, g.ny, g.binsz, g.crval_lon, g.crpix_x, g.crpix_y};
+  h.crval_lat = g.crval_lat;
+  h.proj = g.proj;
+  return h;
+}
 
 struct Rect {
   int x0 = 0, y0 = 0, cx = 0, cy = 0;
@@ -84,6 +92,19 @@ double py_mod(double a, double b) {  // Python float %
 
 void world_to_pix(const GeomH& g, double lon, double lat, double& px, double& py) {
   // wcs_world2pix(lon, lat, 0): pix = img / cdelt + crpix - 1 (wcslib linx2p simple path)
+  if (g.proj == 1) {  // TAN (gnomonic, FITS WCS paper II eq. 54 with the native pole at the reference point)
+    const double dl = (lon - g.crval_lon) * kDegH, la = lat * kDegH, lp = g.crval_lat * kDegH;
+    const double s = std::sin(la) * std::sin(lp) + std::cos(la) * std::cos(lp) * std::cos(dl);
+    if (!(s > 0)) {  // behind the tangent plane
+      px = py = std::numeric_limits<double>::quiet_NaN();
+      return;
+    }
+    const double x = (std::cos(la) * std::sin(dl) / s) / kDegH;
+    const double y = ((std::sin(la) * std::cos(lp) - std::cos(la) * std::sin(lp) * std::cos(dl)) / s) / kDegH;
+    px = x / (-g.binsz) + g.crpix_x - 1.0;
+    py = y / g.binsz + g.crpix_y - 1.0;
+    return;
+  }
   double dlon = py_mod(lon - g.crval_lon + 180.0, 360.0) - 180.0;
   px = dlon / (-g.binsz) + g.crpix_x - 1.0;
   py = lat / g.binsz + g.crpix_y - 1.0;
@@ -408,7 +429,7 @@ int upload_to(DevBuf& buf, const void* src, size_t bytes, cudaStream_t s) {
   return GPY_OK;
 }
 
-gpy::WcsDev wcs_of(const GeomH& g) { return gpy::WcsDev{g.crval_lon, g.binsz, g.crpix_x, g.crpix_y}; }
+gpy::WcsDev wcs_of(const GeomH& g) { return gpy::WcsDev{g.crval_lon, g.binsz, g.crpix_x, g.crpix_y, g.crval_lat, g.proj}; }
 
 // ---- K1 + K2 into a slot ---------------------------------------------------------------------
 // SpatialModel.integrate_geom on the evaluator geometry `rect` of dataset geometry `pg`, then
@@ -481,7 +502,7 @@ int compute_spatial(gpy_context* c, const GeomH& pg, const double* omega, const 
       j.icy = inner.cy;
       GeomH cg = sub_geom(eg, inner);
       // WcsGeom.upsample + get_resampled_wcs: crpix' = (crpix - 0.5) * f + 0.5, cdelt' = cdelt / f
-      j.wcs_up.crval_lon = cg.crval_lon;
+      j.wcs_up = wcs_of(cg);  // (projection and reference point)
       j.wcs_up.binsz = cg.binsz / f;
       j.wcs_up.crpix_x = (cg.crpix_x - 0.5) * f + 0.5;
       j.wcs_up.crpix_y = (cg.crpix_y - 0.5) * f + 0.5;
@@ -1849,6 +1870,9 @@ int gpy_dataset_create(gpy_context_t* c, const gpy_dataset_desc* desc, gpy_datas
   if (!c || !desc || !out) return fail(GPY_ERR_INVALID, "NULL argument to gpy_dataset_create");
   *out = nullptr;
   const gpy_geom_desc& g = desc->geom;
+  if (g.proj != 0 && g.proj != 1) return fail(GPY_ERR_UNSUPPORTED, "projection code %d (0 CAR, 1 TAN)", g.proj);
+  if (g.proj == 0 && g.crval_lat != 0.0)
+    return fail(GPY_ERR_UNSUPPORTED, "CAR with a reference latitude != 0 is an oblique projection in wcslib: not supported");
   if (g.nx <= 0 || g.ny <= 0 || g.n_true <= 0 || g.n_reco <= 0 || !(g.binsz > 0))
     return fail(GPY_ERR_INVALID, "invalid geometry (nx=%d ny=%d n_true=%d n_reco=%d binsz=%g)", g.nx, g.ny, g.n_true,
                 g.n_reco, g.binsz);
@@ -1862,7 +1886,7 @@ int gpy_dataset_create(gpy_context_t* c, const gpy_dataset_desc* desc, gpy_datas
   CUDA_TRY(cudaSetDevice(c->device));
   gpy_dataset* ds = new gpy_dataset();
   ds->ctx = c;
-  ds->geom = GeomH{g.nx, g.ny, g.binsz, g.crval_lon, g.crpix_x, g.crpix_y};
+  ds->geom = geom_from_desc(g);
   ds->nT = g.n_true;
   ds->nR = g.n_reco;
   ds->nRp = (g.n_reco + 7) / 8 * 8;
@@ -1991,6 +2015,8 @@ int gpy_dataset_set_irf_maps(gpy_dataset_t* ds, const gpy_irf_maps_desc* desc) {
   if (!desc->psf_map && !desc->edisp_map) return fail(GPY_ERR_INVALID, "neither a PSF map nor an edisp map given");
   if (desc->nx <= 0 || desc->ny <= 0 || !(desc->binsz > 0))
     return fail(GPY_ERR_INVALID, "bad IRF grid %d x %d, binsz %g", desc->nx, desc->ny, desc->binsz);
+  if (desc->psf_map && ds->geom.proj != 0)
+    return fail(GPY_ERR_UNSUPPORTED, "PSF kernel extraction at the source position is implemented for CAR geometries only");
   if (desc->psf_map && (desc->n_rad < 2 || !desc->rad_edges))
     return fail(GPY_ERR_INVALID, "a PSF map needs rad_edges with at least two bins");
   gpy_context* c = ds->ctx;
@@ -2330,7 +2356,7 @@ int gpy_solid_angle(gpy_context_t* c, const gpy_geom_desc* g, double* out) {
   CUDA_TRY(cudaSetDevice(c->device));
   const size_t P = (size_t)g->nx * g->ny;
   GPY_TRY(c->scratch_a.reserve(P * sizeof(double)));
-  GeomH gh{g->nx, g->ny, g->binsz, g->crval_lon, g->crpix_x, g->crpix_y};
+  GeomH gh = geom_from_desc(*g);
   gpy::solid_angle_kernel<<<dim3((g->nx + 127) / 128, g->ny), 128, 0, c->stream>>>(wcs_of(gh), g->nx, g->ny,
                                                                                     (double*)c->scratch_a.p);
   c->launches++;
@@ -2346,7 +2372,7 @@ int gpy_integrate_geom(gpy_context_t* c, const gpy_geom_desc* g, int32_t spatial
   if (spatial_type < 0 || spatial_type > 2) return fail(GPY_ERR_UNSUPPORTED, "unsupported spatial model type %d", spatial_type);
   CUDA_TRY(cudaSetDevice(c->device));
   const size_t P = (size_t)g->nx * g->ny;
-  GeomH gh{g->nx, g->ny, g->binsz, g->crval_lon, g->crpix_x, g->crpix_y};
+  GeomH gh = geom_from_desc(*g);
   GPY_TRY(c->scratch_a.reserve(P * sizeof(double)));
   const int pitch = (g->nx + 3) / 4 * 4;
   GPY_TRY(c->scratch_b.reserve((size_t)pitch * g->ny * sizeof(float)));

@@ -32,10 +32,31 @@ constexpr double kEdge95 = 2.326174307353347;  // modeling/models/spatial.py:974
 // ----------------------------------------------------------------------------------------------
 struct WcsDev {
   double crval_lon, binsz, crpix_x, crpix_y;
+  double crval_lat;
+  int proj;  // 0 CAR about the equator, 1 TAN about (crval_lon, crval_lat)
 };
 
 __device__ __forceinline__ void pix_to_world_deg(const WcsDev& w, double px, double py, double& lon,
                                                  double& lat) {
+  if (w.proj == 1) {
+    // TAN (FITS WCS paper II, Calabretta & Greisen 2002): R = (180 / pi) cot(theta), x = R sin(phi), y = -R cos(phi)
+    // (eqs. 54, 14, 15), native pole at the reference point, LONPOLE = 180 deg, spherical rotation eq. (2)
+    const double x = -w.binsz * (px + 1.0 - w.crpix_x), y = w.binsz * (py + 1.0 - w.crpix_y);
+    const double r = hypot(x, y);
+    if (r == 0.0) {
+      lon = w.crval_lon;
+      lat = w.crval_lat;
+      return;
+    }
+    const double phi = atan2(x, -y), theta = atan2(180.0 / 3.141592653589793, r);
+    double st, ct, sp, cp, sd, cd;
+    sincos(theta, &st, &ct);
+    sincos(w.crval_lat * kDeg, &sp, &cp);
+    sincos(phi - 3.141592653589793, &sd, &cd);
+    lat = asin(fmin(fmax(st * sp + ct * cp * cd, -1.0), 1.0)) / kDeg;
+    lon = w.crval_lon + atan2(-ct * sd, st * cp - ct * sp * cd) / kDeg;
+    return;
+  }
   lon = __dadd_rn(w.crval_lon, __dmul_rn(-w.binsz, __dadd_rn(__dadd_rn(px, 1.0), -w.crpix_x)));
   lat = __dmul_rn(w.binsz, __dadd_rn(__dadd_rn(py, 1.0), -w.crpix_y));
 }

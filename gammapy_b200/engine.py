@@ -77,7 +77,7 @@ class DeviceDataset:
         e_true = ds.exposure.geom.axes["energy_true"]
         e_reco = geom.axes["energy"]
         g = _lib.GeomDesc(geom.npix[0], geom.npix[1], e_true.nbin, e_reco.nbin, geom.binsz, geom.crval[0],
-                          geom.crpix[0], geom.crpix[1])
+                          geom.crpix[0], geom.crpix[1], geom.crval[1], _lib.PROJECTIONS[geom.projection], 0)
         if ds.exposure.geom.to_image() != geom.to_image():
             raise NotImplementedError("exposure and counts must share the image geometry")
         desc = _lib.DatasetDesc()
@@ -161,6 +161,8 @@ class DeviceDataset:
             raise NotImplementedError("PSF map and edisp map must share their image geometry")
         if ig.frame != ds._geom.frame:
             raise NotImplementedError("IRF maps must be in the frame of the dataset geometry")
+        if ig.projection != "CAR":
+            raise NotImplementedError("IRF maps on a CAR grid only")
         m = _lib.IrfMapsDesc()
         m.nx, m.ny, m.binsz = ig.npix[0], ig.npix[1], ig.binsz
         m.crval_lon, m.crpix_x, m.crpix_y = ig.crval[0], ig.crpix[0], ig.crpix[1]

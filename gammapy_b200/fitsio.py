@@ -261,6 +261,7 @@ def read_hdus(path):
 
 # ---- maps <-> HDUs ---------------------------------------------------------------------------------------------------------
 _CTYPE = {"galactic": ("GLON-CAR", "GLAT-CAR"), "icrs": ("RA---CAR", "DEC--CAR")}
+_CTYPE_TAN = {"galactic": ("GLON-TAN", "GLAT-TAN"), "icrs": ("RA---TAN", "DEC--TAN")}
 
 
 def _axis_columns(ax):
@@ -272,12 +273,13 @@ def map_to_hdus(m, hdu):
     """``WcsNDMap.to_hdulist(hdu=...)`` without the primary: the image HDU and, for a cube, its BANDS table."""
     geom = m.geom
     hdu = hdu.upper()
-    ctype = _CTYPE.get(geom.frame)
+    ctype = (_CTYPE_TAN if geom.projection == "TAN" else _CTYPE).get(geom.frame)
     if ctype is None:
         raise NotImplementedError(f"FITS header for frame {geom.frame!r}")
     header = {"WCSAXES": 2, "CRPIX1": geom.crpix[0], "CRPIX2": geom.crpix[1], "CDELT1": -geom.binsz, "CDELT2": geom.binsz,
               "CUNIT1": "deg", "CUNIT2": "deg", "CTYPE1": ctype[0], "CTYPE2": ctype[1], "CRVAL1": geom.crval[0],
-              "CRVAL2": geom.crval[1], "LONPOLE": 0.0, "LATPOLE": 90.0}
+              "CRVAL2": geom.crval[1], "LONPOLE": 180.0 if geom.projection == "TAN" else 0.0,
+              "LATPOLE": geom.crval[1] if geom.projection == "TAN" else 90.0}
     shape = ",".join(str(n) for n in (geom.npix[0], geom.npix[1]) + tuple(ax.nbin for ax in geom.axes))
     header["WCSSHAPE"] = f"({shape})"
     if getattr(m, "unit", ""):
@@ -308,9 +310,11 @@ def map_from_hdus(hdus, hdu, axis_names=None):
     by_name = {h.name: h for h in hdus}
     image = by_name[hdu.upper()]
     h = image.header
-    frame = {v[0]: k for k, v in _CTYPE.items()}.get(str(h.get("CTYPE1", "")).strip())
+    ctype1 = str(h.get("CTYPE1", "")).strip()
+    proj = "TAN" if ctype1.endswith("TAN") else "CAR"
+    frame = {v[0]: k for k, v in (_CTYPE_TAN if proj == "TAN" else _CTYPE).items()}.get(ctype1)
     if frame is None:
-        raise NotImplementedError(f"projection / frame {h.get('CTYPE1')!r} (CAR images in galactic or icrs only)")
+        raise NotImplementedError(f"projection / frame {h.get('CTYPE1')!r} (CAR or TAN images in galactic or icrs only)")
     if abs(abs(h["CDELT1"]) - abs(h["CDELT2"])) > 1e-12 * abs(h["CDELT2"]):
         raise NotImplementedError("square pixels only")
     data = image.data
@@ -341,7 +345,7 @@ def map_from_hdus(hdus, hdu, axis_names=None):
         for ax, new in zip(axes, axis_names):
             ax.name = new
     geom = WcsGeom((nx, ny), abs(h["CDELT2"]), (h["CRVAL1"], h["CRVAL2"]), (h["CRPIX1"], h["CRPIX2"]), frame=frame,
-                   axes=axes)
+                   axes=axes, proj=proj)
     m = Map.from_geom(geom, data=data, dtype=data.dtype, unit=str(h.get("BUNIT", "")))
     return m
 

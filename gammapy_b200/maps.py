@@ -196,7 +196,9 @@ def round_up_to_odd(f):
 
 
 class WcsGeom:
-    """WCS map geometry (maps/wcs/geom.py:294-417), CAR projection, crval latitude 0, square pixels."""
+    """WCS map geometry (maps/wcs/geom.py:294-417), square pixels: CAR about the equator (crval latitude 0, as
+    ``WcsGeom.create`` builds it) or TAN about any reference point (gnomonic; FITS WCS paper II, Calabretta & Greisen 2002,
+    eqs. 5, 54, 55 with the native pole at the reference point and LONPOLE = 180 deg)."""
 
     def __init__(self, npix, binsz, crval, crpix, frame="icrs", axes=None, proj="CAR"):
         self._npix = (int(npix[0]), int(npix[1]))
@@ -206,9 +208,9 @@ class WcsGeom:
         self.frame = frame
         self.projection = proj
         self.axes = MapAxes(axes or [])
-        if proj != "CAR":
-            raise NotImplementedError(f"gammapy_b200 implements the CAR projection only, got {proj!r}")
-        if self._crval[1] != 0.0:
+        if proj not in ("CAR", "TAN"):
+            raise NotImplementedError(f"gammapy_b200 implements the CAR and TAN projections only, got {proj!r}")
+        if proj == "CAR" and self._crval[1] != 0.0:
             raise NotImplementedError(
                 "CAR with a reference latitude != 0 is an oblique projection in wcslib; "
                 "gammapy_b200 supports CAR geometries centred on latitude 0 only"
@@ -217,6 +219,10 @@ class WcsGeom:
     @classmethod
     def create(cls, npix=None, binsz=0.5, proj="CAR", frame="icrs", refpix=None, axes=None, skydir=None, width=None):
         crval = as_lonlat(skydir)
+        if proj == "CAR" and crval[1] != 0.0:
+            raise NotImplementedError(
+                "a CAR geometry centred off the equator (the reference keeps crval latitude 0 and shifts crpix, "
+                "maps/wcs/geom.py:401-413: pixels are then not square on the sky); use proj='TAN' for such fields")
         if isinstance(skydir, SkyCoord):
             frame = skydir.frame
         bx, by = _pair(binsz)
@@ -299,22 +305,37 @@ class WcsGeom:
 
     def __eq__(self, other):
         return (isinstance(other, WcsGeom) and self._npix == other._npix and self._binsz == other._binsz
-                and np.allclose(self._crval, other._crval) and np.allclose(self._crpix, other._crpix)
+                and self.projection == other.projection and np.allclose(self._crval, other._crval) and np.allclose(self._crpix, other._crpix)
                 and len(self.axes) == len(other.axes) and all(a == b for a, b in zip(self.axes, other.axes)))
 
     def is_aligned(self, other):
-        if self._binsz != other._binsz or not np.allclose(self._crval, other._crval):
+        if self._binsz != other._binsz or self.projection != other.projection or not np.allclose(self._crval, other._crval):
             return False
         d = np.array(self._crpix) - np.array(other._crpix)
         return bool(np.allclose(d, np.round(d)))
 
     # -- coordinates ---------------------------------------------------------------------------------
     def pix_to_coord(self, pix):
-        """wcs_pix2world(px, py, 0) for CAR about the equator (+ non-spatial axes)."""
+        """wcs_pix2world(px, py, 0) (+ non-spatial axes)."""
         px = np.asarray(pix[0], dtype=float)
         py = np.asarray(pix[1], dtype=float)
-        lon = self._crval[0] + (-self._binsz) * (px + 1.0 - self._crpix[0])
-        lat = self._binsz * (py + 1.0 - self._crpix[1])
+        if self.projection == "TAN":
+            x = (-self._binsz) * (px + 1.0 - self._crpix[0])
+            y = self._binsz * (py + 1.0 - self._crpix[1])
+            x, y = np.broadcast_arrays(x, y)
+            r = np.hypot(x, y)
+            phi = np.arctan2(x, -y)
+            theta = np.arctan2(180.0 / np.pi, r)
+            dphi = phi - np.pi  # LONPOLE = 180 deg
+            lat_p = self._crval[1] * DEG
+            st, ct = np.sin(theta), np.cos(theta)
+            lat = np.arcsin(np.clip(st * np.sin(lat_p) + ct * np.cos(lat_p) * np.cos(dphi), -1.0, 1.0))
+            lon = self._crval[0] + np.arctan2(-ct * np.sin(dphi), st * np.cos(lat_p) - ct * np.sin(lat_p) * np.cos(dphi)) / DEG
+            lon = np.where(r == 0.0, self._crval[0], lon)
+            lat = np.where(r == 0.0, self._crval[1], lat / DEG)
+        else:
+            lon = self._crval[0] + (-self._binsz) * (px + 1.0 - self._crpix[0])
+            lat = self._binsz * (py + 1.0 - self._crpix[1])
         out = [lon, lat]
         for ax, p in zip(self.axes, pix[2:]):
             out.append(ax.pix_to_coord(p))
@@ -325,9 +346,21 @@ class WcsGeom:
             coords = (coords.lon, coords.lat)
         lon = np.asarray(coords[0], dtype=float)
         lat = np.asarray(coords[1], dtype=float)
-        dlon = (lon - self._crval[0] + 180.0) % 360.0 - 180.0
-        px = dlon / (-self._binsz) + self._crpix[0] - 1.0
-        py = lat / self._binsz + self._crpix[1] - 1.0
+        if self.projection == "TAN":
+            dl = (lon - self._crval[0]) * DEG
+            la, lat_p = lat * DEG, self._crval[1] * DEG
+            # gnomonic: x = cos(lat) sin(dlon) / s, y = (sin(lat) cos(lat_p) - cos(lat) sin(lat_p) cos(dlon)) / s with
+            # s = sin(theta) = cos of the angular distance to the reference point (s <= 0: behind the tangent plane)
+            s_ = np.sin(la) * np.sin(lat_p) + np.cos(la) * np.cos(lat_p) * np.cos(dl)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                x = np.where(s_ > 0, (np.cos(la) * np.sin(dl) / s_) / DEG, np.nan)
+                y = np.where(s_ > 0, ((np.sin(la) * np.cos(lat_p) - np.cos(la) * np.sin(lat_p) * np.cos(dl)) / s_) / DEG, np.nan)
+            px = x / (-self._binsz) + self._crpix[0] - 1.0
+            py = y / self._binsz + self._crpix[1] - 1.0
+        else:
+            dlon = (lon - self._crval[0] + 180.0) % 360.0 - 180.0
+            px = dlon / (-self._binsz) + self._crpix[0] - 1.0
+            py = lat / self._binsz + self._crpix[1] - 1.0
         out = [px, py]
         for ax, c in zip(self.axes, coords[2:]):
             out.append(ax.coord_to_pix(c))
@@ -341,6 +374,18 @@ class WcsGeom:
         else:
             x, y = np.arange(nx, dtype=float), np.arange(ny, dtype=float)
         nd = len(self.axes) + 2
+        if self.projection == "TAN":  # not separable: full (ny, nx) images of both coordinates
+            lon, lat = self.pix_to_coord((x[np.newaxis, :], y[:, np.newaxis]))[:2]
+            shape2 = [1] * (nd - 2) + [len(y), len(x)]
+            coords = {"lon": lon.reshape(shape2), "lat": lat.reshape(shape2)}
+            for i, ax in enumerate(self.axes):
+                shape = [1] * nd
+                shape[nd - 3 - i] = -1
+                coords[ax.name] = ax.center.reshape(shape)
+            if not sparse:
+                full = self.data_shape if mode != "edges" else tuple(ax.nbin for ax in reversed(self.axes)) + (len(y), len(x))
+                coords = {k: np.broadcast_to(v, full) if k in ("lon", "lat") else v for k, v in coords.items()}
+            return coords
         lon, lat = self.pix_to_coord((x, y))[:2]
         shape_x = [1] * nd
         shape_x[-1] = -1

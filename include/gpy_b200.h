@@ -12,8 +12,8 @@
  *   - cubes are C-order (energy, lat(y), lon(x)), x fastest, as numpy / gammapy Map.data.
  *   - "DEVICE" pointers are CUDA device memory owned by the caller (e.g. torch tensors) and must
  *     outlive the dataset handle; "HOST" pointers are read during the call only.
- *   - image WCS: CAR projection about the equator (crval latitude 0), square pixels
- *     (maps/wcs/geom.py:294-417: crpix = (n+1)/2, cdelt = (-binsz, +binsz)).
+ *   - image WCS: square pixels, cdelt = (-binsz, +binsz), CAR about the equator or TAN (gpy_projection;
+ *     maps/wcs/geom.py:294-417).
  *   - every function returns 0 on success, a negative gpy_status otherwise; gpy_last_error() gives
  *     the message of the last failure on the calling thread.  There is no CPU fallback: without a
  *     CUDA device gpy_init fails with GPY_ERR_CUDA.
@@ -46,6 +46,10 @@ typedef enum { GPY_SPECTRAL_PL = 0, GPY_SPECTRAL_LP = 1, GPY_SPECTRAL_ECPL = 2 }
 typedef struct gpy_context gpy_context_t;
 typedef struct gpy_dataset gpy_dataset_t;
 
+/* Image projections: CAR about the equator (what WcsGeom.create builds for proj="CAR": crval latitude 0, the field's
+ * latitude carried by crpix, maps/wcs/geom.py:401-413) and TAN (gnomonic) about any reference point. */
+typedef enum { GPY_PROJ_CAR = 0, GPY_PROJ_TAN = 1 } gpy_projection;
+
 /* WcsGeom of the counts cube (maps/wcs/geom.py:294-417) reduced to what the path reads. */
 typedef struct {
   int32_t nx, ny;           /* image size in pixels (lon, lat) */
@@ -53,6 +57,9 @@ typedef struct {
   double binsz;             /* deg */
   double crval_lon;         /* deg; crval latitude must be 0 */
   double crpix_x, crpix_y;  /* FITS 1-based reference pixel */
+  double crval_lat;         /* deg; 0 for CAR */
+  int32_t proj;             /* gpy_projection */
+  int32_t pad_;
 } gpy_geom_desc;
 
 /* The MapDataset attributes the path consumes (datasets/map.py:410; §8 a4-a6, a17 of SURVEY.md). */

@@ -12,7 +12,8 @@ _SPECTRAL = {"PowerLawSpectralModel": "pl", "LogParabolaSpectralModel": "lp", "E
 
 
 def geom_to_oracle(geom):
-    return ImageGeom(geom.npix[0], geom.npix[1], geom.binsz, geom.crval[0], geom.crpix[0], geom.crpix[1], geom.crval[1])
+    return ImageGeom(geom.npix[0], geom.npix[1], geom.binsz, geom.crval[0], geom.crpix[0], geom.crpix[1], geom.crval[1],
+                     proj=geom.projection)
 
 
 def model_to_oracle(model):

@@ -84,22 +84,29 @@ def overlap_slices(large_shape, small_shape, position, mode="trim"):
 
 
 class ImageGeom:
-    """2-D CAR WCS image geometry; (nx, ny) pixels of ``binsz`` deg, 0-based pixel coords."""
+    """2-D WCS image geometry; (nx, ny) pixels of ``binsz`` deg, 0-based pixel coords.  ``proj``: "CAR" about the
+    equator, or "TAN" about (crval_lon, crval_lat), restated from the FITS WCS paper II (Calabretta & Greisen 2002) in its
+    native-spherical-coordinate form: eq. (54) R = (180/pi) cot(theta), eq. (14)-(15) x = R sin(phi), y = -R cos(phi), and
+    the spherical rotation eq. (2) / (5) with the native pole at the reference point and LONPOLE = 180 deg.  wcslib
+    itself cannot be run here: **parity unpinned** for TAN beyond the analytic checks of tests/test_host_logic.py."""
 
-    def __init__(self, nx, ny, binsz, crval_lon, crpix_x, crpix_y, crval_lat=0.0):
-        if crval_lat != 0.0:
+    def __init__(self, nx, ny, binsz, crval_lon, crpix_x, crpix_y, crval_lat=0.0, proj="CAR"):
+        if proj not in ("CAR", "TAN"):
+            raise NotImplementedError(f"oracle: projection {proj!r}")
+        if proj == "CAR" and crval_lat != 0.0:
             raise NotImplementedError("oracle: CAR restated only for crval latitude 0 (oblique otherwise)")
+        self.proj = proj
         self.nx = int(nx)
         self.ny = int(ny)
         self.binsz = float(binsz)
         self.crval_lon = float(crval_lon)
-        self.crval_lat = 0.0
+        self.crval_lat = float(crval_lat)
         self.crpix_x = float(crpix_x)
         self.crpix_y = float(crpix_y)
 
     # -- construction ---------------------------------------------------------------------
     @classmethod
-    def create(cls, skydir=(0.0, 0.0), binsz=0.5, width=None, npix=None):
+    def create(cls, skydir=(0.0, 0.0), binsz=0.5, width=None, npix=None, proj="CAR"):
         """maps/wcs/geom.py:294-417 (square pixels only)."""
         if npix is None:
             if not isinstance(width, (tuple, list)):
@@ -111,11 +118,11 @@ class ImageGeom:
         elif not isinstance(npix, (tuple, list)):
             npix = (int(npix), int(npix))
         nx, ny = int(npix[0]), int(npix[1])
-        return cls(nx, ny, binsz, skydir[0], (nx + 1) / 2.0, (ny + 1) / 2.0, skydir[1])
+        return cls(nx, ny, binsz, skydir[0], (nx + 1) / 2.0, (ny + 1) / 2.0, skydir[1], proj=proj)
 
     def copy(self, **kw):
         d = dict(nx=self.nx, ny=self.ny, binsz=self.binsz, crval_lon=self.crval_lon,
-                 crpix_x=self.crpix_x, crpix_y=self.crpix_y)
+                 crpix_x=self.crpix_x, crpix_y=self.crpix_y, crval_lat=self.crval_lat, proj=self.proj)
         d.update(kw)
         return ImageGeom(**d)
 
@@ -147,6 +154,21 @@ class ImageGeom:
         """wcs_pix2world(px, py, 0) in deg."""
         px = np.asarray(px, dtype=float)
         py = np.asarray(py, dtype=float)
+        if self.proj == "TAN":
+            x = (-self.binsz) * (px + 1.0 - self.crpix_x)
+            y = self.binsz * (py + 1.0 - self.crpix_y)
+            x, y = np.broadcast_arrays(x, y)
+            r_theta = np.sqrt(x * x + y * y)
+            phi = np.arctan2(x, -y)                            # eq. (14), (15)
+            theta = np.arctan2(180.0 / np.pi, r_theta)         # eq. (55)
+            phi_p, delta_p = np.pi, self.crval_lat * DEG
+            delta = np.arcsin(np.clip(np.sin(theta) * np.sin(delta_p)
+                                      + np.cos(theta) * np.cos(delta_p) * np.cos(phi - phi_p), -1, 1))   # eq. (2)
+            alpha = self.crval_lon * DEG + np.arctan2(
+                -np.cos(theta) * np.sin(phi - phi_p),
+                np.sin(theta) * np.cos(delta_p) - np.cos(theta) * np.sin(delta_p) * np.cos(phi - phi_p))
+            at_ref = r_theta == 0
+            return (np.where(at_ref, self.crval_lon, alpha / DEG), np.where(at_ref, self.crval_lat, delta / DEG))
         lon = self.crval_lon + (-self.binsz) * (px + 1.0 - self.crpix_x)
         lat = self.binsz * (py + 1.0 - self.crpix_y)
         lon, lat = np.broadcast_arrays(lon, lat)
@@ -154,6 +176,16 @@ class ImageGeom:
 
     def world_to_pix(self, lon, lat):
         """wcs_world2pix(lon, lat, 0); longitude difference wrapped into [-180, 180)."""
+        if self.proj == "TAN":
+            alpha, delta = np.asarray(lon, dtype=float) * DEG, np.asarray(lat, dtype=float) * DEG
+            alpha_p, delta_p, phi_p = self.crval_lon * DEG, self.crval_lat * DEG, np.pi
+            phi = phi_p + np.arctan2(-np.cos(delta) * np.sin(alpha - alpha_p),
+                                     np.sin(delta) * np.cos(delta_p) - np.cos(delta) * np.sin(delta_p) * np.cos(alpha - alpha_p))  # eq. (5)
+            theta = np.arcsin(np.clip(np.sin(delta) * np.sin(delta_p) + np.cos(delta) * np.cos(delta_p) * np.cos(alpha - alpha_p), -1, 1))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                r_theta = np.where(theta > 0, (180.0 / np.pi) / np.tan(theta), np.nan)   # eq. (54)
+            x, y = r_theta * np.sin(phi), -r_theta * np.cos(phi)
+            return x / (-self.binsz) + self.crpix_x - 1.0, y / self.binsz + self.crpix_y - 1.0
         dlon = (np.asarray(lon, dtype=float) - self.crval_lon + 180.0) % 360.0 - 180.0
         px = dlon / (-self.binsz) + self.crpix_x - 1.0
         py = np.asarray(lat, dtype=float) / self.binsz + self.crpix_y - 1.0
@@ -174,7 +206,7 @@ class ImageGeom:
         """maps/wcs/geom.py:766-771 + maps/wcs/geom.py get_resampled_wcs (crpix'=(crpix-0.5)*f+0.5, cdelt/=f)."""
         return ImageGeom(
             self.nx * factor, self.ny * factor, self.binsz / factor, self.crval_lon,
-            (self.crpix_x - 0.5) * factor + 0.5, (self.crpix_y - 0.5) * factor + 0.5,
+            (self.crpix_x - 0.5) * factor + 0.5, (self.crpix_y - 0.5) * factor + 0.5, self.crval_lat, proj=self.proj,
         )
 
     def to_odd_npix(self, max_radius=None):
@@ -185,7 +217,7 @@ class ImageGeom:
             width = 2 * max_radius
         width_npix = width / self.binsz
         npix = int(round_up_to_odd(np.float64(width_npix)))
-        return ImageGeom.create(skydir=self.center_skydir, binsz=self.binsz, npix=npix)
+        return ImageGeom.create(skydir=self.center_skydir, binsz=self.binsz, npix=npix, proj=self.proj)
 
     def cutout_info(self, position, width, mode="trim", odd_npix=False, min_npix=1):
         """maps/wcs/geom.py:886-930 -> (cutout geom, parent (y, x) slices).
@@ -205,7 +237,7 @@ class ImageGeom:
         ys, xs = slices_large
         geom = ImageGeom(
             xs.stop - xs.start, ys.stop - ys.start, self.binsz, self.crval_lon,
-            self.crpix_x - xs.start, self.crpix_y - ys.start,
+            self.crpix_x - xs.start, self.crpix_y - ys.start, self.crval_lat, proj=self.proj,
         )
         return geom, (ys, xs)
 

@@ -57,9 +57,9 @@ def test_struct_layout_matches_header():
 
     from gammapy_b200 import _lib
 
-    assert C.sizeof(_lib.GeomDesc) == 48
+    assert C.sizeof(_lib.GeomDesc) == 64
     assert C.sizeof(_lib.SourceDesc) == 4 * (2 + 6 + 5 + 2)
     assert C.sizeof(_lib.BackgroundDesc) == 16
     assert C.sizeof(_lib.SourceState) == 32
-    assert C.sizeof(_lib.DatasetDesc) == 48 + 8 * 8 + 8 + 8 * 3 + 8 + 8 + 8 + 8  # ... weight, compact (padded), mask_row_bytes
+    assert C.sizeof(_lib.DatasetDesc) == 64 + 8 * 8 + 8 + 8 * 3 + 8 + 8 + 8 + 8  # ... weight, compact (padded), mask_row_bytes
     assert C.sizeof(_lib.IrfMapsDesc) == 8 + 4 * 8 + 8 + 3 * 8

@@ -82,3 +82,38 @@ def test_long_axes_use_the_128_pixel_kernel(ctx, n_reco, n_true):
     assert np.max(np.abs(got - want) / np.maximum(want, 1e-300)) < 1e-5
     ds.counts = Map.from_geom(ds._geom, data=de.fake(9), dtype=float)
     assert abs(ds.stat_sum() - de.stat_sum()) < 1e-3
+
+
+@pytest.mark.parametrize("skydir", [(30.0, 40.0), (300.0, -62.0)])
+def test_tan_projection_dataset_vs_oracle(ctx, skydir):
+    """A dataset on a TAN (gnomonic) geometry off the equator: model coordinates, solid angles, cutouts and the PSF kernel
+    geometry follow the projection on the device (pix_to_world_deg), on the host (world_to_pix) and in the oracle
+    (oracle/wcs.py, written from the FITS WCS paper in its other form); five sources of every spatial type."""
+    import numpy as np
+
+    from gammapy_b200 import Map, configs
+    from gammapy_b200.modeling.models import FoVBackgroundModel
+    from oracle import adapter
+
+    ds = configs.make_dataset(width=(4.0, 3.0), skydir=skydir, proj="TAN", mask_radius=1.3, name="tan")
+    models = configs.c2_models("tan")
+    for m in models:
+        if not isinstance(m, FoVBackgroundModel):  # the ring of sources, re-centred on the field
+            m.spatial_model.lon_0.value = skydir[0] + m.spatial_model.lon_0.value / np.cos(np.radians(skydir[1]))
+            m.spatial_model.lat_0.value = skydir[1] + m.spatial_model.lat_0.value
+    ds.models = models
+    de = adapter.evaluator_for(ds, conv="exact64")
+    got, want = ds.npred().data, de.npred()
+    assert np.max(np.abs(got - want) / np.maximum(want, 1e-300)) < 1e-5
+    for m in models:
+        if not isinstance(m, FoVBackgroundModel):
+            st = ds.evaluator_state(m.name)
+            ys, xs = de.evaluators[m.name].slices
+            assert (st["x0"], st["y0"], st["cx"], st["cy"]) == (xs.start, ys.start, xs.stop - xs.start, ys.stop - ys.start)
+    ds.counts = Map.from_geom(ds._geom, data=de.fake(6), dtype=float)
+    assert abs(ds.stat_sum() - de.stat_sum()) < 1e-3
+    # a source moves: new cutout, same agreement
+    models[1].spatial_model.lon_0.value += 0.4
+    models[1].spatial_model.lat_0.value -= 0.3
+    adapter.refresh_models(de, ds)
+    assert abs(ds.stat_sum() - de.stat_sum()) < 1e-3

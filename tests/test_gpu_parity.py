@@ -66,7 +66,8 @@ def test_cash_sum_edge_cases(ctx):
 def _geom_desc(geom):
     from gammapy_b200 import _lib
 
-    return _lib.GeomDesc(geom.nx, geom.ny, 1, 1, geom.binsz, geom.crval_lon, geom.crpix_x, geom.crpix_y)
+    return _lib.GeomDesc(geom.nx, geom.ny, 1, 1, geom.binsz, geom.crval_lon, geom.crpix_x, geom.crpix_y, geom.crval_lat,
+                         _lib.PROJECTIONS[geom.proj], 0)
 
 
 def test_solid_angle(ctx):

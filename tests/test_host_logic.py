@@ -37,8 +37,9 @@ def test_wcs_geom_matches_oracle_geometry():
     assert geom.to_odd_npix(max_radius=0.66).npix == (67, 67)
     with pytest.raises(NotImplementedError):
         WcsGeom.create(skydir=(10, 5), binsz=0.1, width=1)
+    assert WcsGeom.create(skydir=(10, 5), binsz=0.1, width=1, proj="TAN").crval == (10.0, 5.0)
     with pytest.raises(NotImplementedError):
-        WcsGeom.create(binsz=0.1, width=1, proj="TAN")
+        WcsGeom.create(binsz=0.1, width=1, proj="AIT")
 
 
 def test_parameter_factor_scale_contract():
