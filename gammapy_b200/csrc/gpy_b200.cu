@@ -434,8 +434,9 @@ gpy::WcsDev wcs_of(const GeomH& g) { return gpy::WcsDev{g.crval_lon, g.binsz, g.
 // ---- K1 + K2 into a slot ---------------------------------------------------------------------
 // SpatialModel.integrate_geom on the evaluator geometry `rect` of dataset geometry `pg`, then
 // WcsNDMap.convolve.  `omega` is the parent solid-angle image (device).
+// rows_out[2] (optional): the rows [r0, r1) of the cutout outside of which the image is exactly zero.
 int compute_spatial(gpy_context* c, const GeomH& pg, const double* omega, const Rect& rect, int type,
-                    const double* sp, float* w_out, int pitch, int xpad, int* f_out) {
+                    const double* sp, float* w_out, int pitch, int xpad, int* f_out, int* rows_out = nullptr) {
   GeomH eg = sub_geom(pg, rect);
   gpy::SpatialJob j;
   std::memset(&j, 0, sizeof(j));
@@ -510,6 +511,18 @@ int compute_spatial(gpy_context* c, const GeomH& pg, const double* omega, const 
   }
   j.f = f;
   if (f_out) *f_out = f;
+  if (rows_out) {
+    rows_out[0] = 0;
+    rows_out[1] = rect.cy;
+    if (type == GPY_SPATIAL_POINT && std::isfinite(j.py0)) {  // weights (1 - |y - py0|)+: rows within one pixel of py0
+      rows_out[0] = std::max(0, (int)std::ceil(j.py0 - 1.0));
+      rows_out[1] = std::min(rect.cy, (int)std::floor(j.py0 + 1.0) + 1);
+    } else if (type != GPY_SPATIAL_POINT && f > 1) {          // zeros outside the oversampled inner cutout
+      rows_out[0] = std::max(0, j.iy0);
+      rows_out[1] = std::min(rect.cy, j.iy0 + j.icy);
+    }
+    if (rows_out[1] < rows_out[0]) rows_out[1] = rows_out[0];
+  }
   dim3 grid((pitch + 127) / 128, rect.cy);
   gpy::spatial_fill_kernel<<<grid, 128, 0, c->stream>>>(j);
   c->launches++;
@@ -528,7 +541,8 @@ size_t conv_smem_bytes(int h, int kw) {
 }
 
 int launch_conv(gpy_context* c, const float* image, int cy, int cx, int pitch, int xpad, const float* kflip,
-                const gpy::ConvPlane* planes_dev, int n_planes, int max_h, int max_kw, float* out) {
+                const gpy::ConvPlane* planes_dev, int n_planes, int max_h, int max_kw, float* out, int row0 = 0,
+                int row1 = 1 << 30) {
   size_t smem = conv_smem_bytes(max_h, max_kw);
   if (smem > (size_t)c->max_smem_optin)
     return fail(GPY_ERR_UNSUPPORTED, "PSF kernel too large for the shared-memory stencil (half width %d)", max_h);
@@ -538,7 +552,7 @@ int launch_conv(gpy_context* c, const float* image, int cy, int cx, int pitch, i
   }
   dim3 grid((pitch + gpy::kConvTX - 1) / gpy::kConvTX, (cy + gpy::kConvTY - 1) / gpy::kConvTY, n_planes);
   gpy::psf_conv_kernel<<<grid, gpy::kConvThreads, smem, c->stream>>>(image, cy, cx, pitch, xpad, kflip, planes_dev,
-                                                                     out, (size_t)cy * pitch);
+                                                                     out, (size_t)cy * pitch, row0, std::min(row1, cy));
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return GPY_OK;
@@ -924,18 +938,19 @@ int get_slot(gpy_dataset* ds, Source& src, const double* sp, const Rect& rect, u
   // edge): allocate with headroom, a pool allocation that has to grow costs milliseconds in the middle of a fit.
   const size_t img_cap = (size_t)(rect.cy + 4) * (s.pitch + 8);
   if (img * sizeof(float) > s.w.cap) GPY_TRY(s.w.reserve(img_cap * sizeof(float), c->stream));
+  int wrows[2] = {0, rect.cy};
   GPY_TRY(compute_spatial(c, ds->geom, (const double*)ds->d_omega.p, rect, src.desc.spatial_type, sp,
-                          (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f));
+                          (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f, wrows));
   if (conv) {
     if (img * ds->nT * sizeof(float) > s.conv.cap) GPY_TRY(s.conv.reserve(img_cap * ds->nT * sizeof(float), c->stream));
     if (ds->irf.has_psf)
       GPY_TRY(launch_conv(c, (const float*)s.w.p, rect.cy, rect.cx, s.pitch, rect.x0 - s.x0a,
                           (const float*)src.p_kflip.p, (const gpy::ConvPlane*)src.p_planes.p, ds->nT, src.max_h,
-                          src.max_kw, (float*)s.conv.p));
+                          src.max_kw, (float*)s.conv.p, wrows[0], wrows[1]));
     else
       GPY_TRY(launch_conv(c, (const float*)s.w.p, rect.cy, rect.cx, s.pitch, rect.x0 - s.x0a,
                           (const float*)ds->d_kflip.p, (const gpy::ConvPlane*)ds->d_planes.p, ds->nT, ds->max_h,
-                          ds->max_kw, (float*)s.conv.p));
+                          ds->max_kw, (float*)s.conv.p, wrows[0], wrows[1]));
   }
   s.key.assign(sp, sp + nsp);
   s.valid = true;

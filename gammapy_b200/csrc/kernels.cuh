@@ -247,7 +247,10 @@ constexpr int kConvTX = 64, kConvTY = 32, kConvThreads = 256;
 __global__ void __launch_bounds__(kConvThreads)
 psf_conv_kernel(const float* __restrict__ image, int cy, int cx, int pitch, int xpad,
                 const float* __restrict__ kflip, const ConvPlane* __restrict__ planes,
-                float* __restrict__ out, size_t plane_stride) {
+                float* __restrict__ out, size_t plane_stride, int row0, int row1) {
+  // [row0, row1): rows of `image` that can hold a non-zero (a point source fills two rows, an oversampled model its
+  // inner cutout).  Stencil rows that only see zeros are skipped -- they would add 0 * k = 0 to every sum --, so a
+  // point source costs 2 of the 2 h + 1 rows and output tiles beyond the kernel's reach are written as zeros at once.
   extern __shared__ __align__(16) float conv_smem[];
   const ConvPlane pl = planes[blockIdx.z];
   const int h = pl.h, kw = pl.kw, nrow = 2 * h + 1;
@@ -257,6 +260,14 @@ psf_conv_kernel(const float* __restrict__ image, int cy, int cx, int pitch, int 
   float* k_s = conv_smem + (size_t)srows * spitch;  // [nrow][kw]
   const int tx0 = blockIdx.x * kConvTX, ty0 = blockIdx.y * kConvTY;
   const int tid = threadIdx.x;
+  if (ty0 - h >= row1 || ty0 + kConvTY + h <= row0) {  // block uniform: no input row of this tile can be non-zero
+    const int y = ty0 + (tid >> 3);
+    if (y < cy) {
+      float* o = out + blockIdx.z * plane_stride + (size_t)y * pitch + tx0;
+      for (int k = (tid & 7); k < kConvTX && tx0 + k < pitch; k += 8) o[k] = 0.f;
+    }
+    return;
+  }
 
   for (int i = tid; i < nrow * kw; i += kConvThreads) k_s[i] = kflip[pl.koff + i];
   for (int i = tid; i < srows * spitch; i += kConvThreads) {
@@ -271,7 +282,9 @@ psf_conv_kernel(const float* __restrict__ image, int cy, int cx, int pitch, int 
   const int tx = tid & 7, ly = tid >> 3;
   const int xa = 4 * tx, xb = 32 + 4 * tx;
   double acc_a[4] = {0, 0, 0, 0}, acc_b[4] = {0, 0, 0, 0};
-  for (int i = 0; i < nrow; ++i) {
+  // stencil row i reads image row ty0 - h + ly + i
+  const int i_lo = max(0, row0 - (ty0 - h + ly)), i_hi = min(nrow, row1 - (ty0 - h + ly));
+  for (int i = i_lo; i < i_hi; ++i) {
     const float* r = in_s + (size_t)(ly + i) * spitch;
     const float* kr = k_s + (size_t)i * kw;
     float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
