@@ -318,6 +318,16 @@ struct gpy_context {
   bool static_schedule = false;  // GPY_STATIC_SCHEDULE: never claim items dynamically
   int t64_stages = 1;            // GPY_FOLD_T64 = 1 (three CTAs per SM, single-buffered inputs) or 2 (two CTAs, double-buffered)
   bool use_t64 = true;           // GPY_FOLD_T64=0 switches the 64-pixel sub-tile kernel off (default: used whenever the launch is eligible)
+  // Side streams for the per-source spatial work (integrate_geom + PSF stencil) of an evaluation that moves several
+  // sources: the chains of different sources are independent and each stencil launch is only ~3 waves, so they run side
+  // by side; forked from / joined into the library's stream with events (work_stream / join_side_streams).
+  static constexpr int kSideStreams = 4;
+  cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t side_done[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork_ev = nullptr;
+  bool side_used[kSideStreams] = {false, false, false, false};
+  int side_next = 0;
+  bool use_side_streams = true;  // GPY_SIDE_STREAMS=0: everything on the library's stream
   int max_ctas_per_sm = 0;       // GPY_FOLD_CTAS_PER_SM (profiling): cap on resident fold CTAs per SM, 0 = occupancy limit
   bool no_desc_cache = false;  // GPY_NO_DESC_CACHE: run prep_items_kernel on every call
   std::vector<uint8_t> desc_key;  // what the descriptors in `desc` were built from (empty: none)
@@ -431,12 +441,39 @@ int upload_to(DevBuf& buf, const void* src, size_t bytes, cudaStream_t s) {
 
 gpy::WcsDev wcs_of(const GeomH& g) { return gpy::WcsDev{g.crval_lon, g.binsz, g.crpix_x, g.crpix_y, g.crval_lat, g.proj}; }
 
+// Stream for one source's spatial chain: a side stream that first waits for everything queued on the library's stream
+// so far (allocations of this call, kernels of the previous evaluation that still read a recycled slot).
+int work_stream(gpy_context* c, cudaStream_t* out) {
+  if (!c->use_side_streams || !c->side[0]) {
+    *out = c->stream;
+    return GPY_OK;
+  }
+  const int i = c->side_next++ % gpy_context::kSideStreams;
+  CUDA_TRY(cudaEventRecord(c->fork_ev, c->stream));
+  CUDA_TRY(cudaStreamWaitEvent(c->side[i], c->fork_ev, 0));
+  c->side_used[i] = true;
+  *out = c->side[i];
+  return GPY_OK;
+}
+// The library's stream waits for the side streams used since the last join.
+int join_side_streams(gpy_context* c) {
+  for (int i = 0; i < gpy_context::kSideStreams; ++i)
+    if (c->side_used[i]) {
+      CUDA_TRY(cudaEventRecord(c->side_done[i], c->side[i]));
+      CUDA_TRY(cudaStreamWaitEvent(c->stream, c->side_done[i], 0));
+      c->side_used[i] = false;
+    }
+  return GPY_OK;
+}
+
 // ---- K1 + K2 into a slot ---------------------------------------------------------------------
 // SpatialModel.integrate_geom on the evaluator geometry `rect` of dataset geometry `pg`, then
 // WcsNDMap.convolve.  `omega` is the parent solid-angle image (device).
 // rows_out[2] (optional): the rows [r0, r1) of the cutout outside of which the image is exactly zero.
 int compute_spatial(gpy_context* c, const GeomH& pg, const double* omega, const Rect& rect, int type,
-                    const double* sp, float* w_out, int pitch, int xpad, int* f_out, int* rows_out = nullptr) {
+                    const double* sp, float* w_out, int pitch, int xpad, int* f_out, int* rows_out = nullptr,
+                    cudaStream_t stream = nullptr) {
+  if (!stream) stream = c->stream;
   GeomH eg = sub_geom(pg, rect);
   gpy::SpatialJob j;
   std::memset(&j, 0, sizeof(j));
@@ -524,12 +561,12 @@ int compute_spatial(gpy_context* c, const GeomH& pg, const double* omega, const 
     if (rows_out[1] < rows_out[0]) rows_out[1] = rows_out[0];
   }
   dim3 grid((pitch + 127) / 128, rect.cy);
-  gpy::spatial_fill_kernel<<<grid, 128, 0, c->stream>>>(j);
+  gpy::spatial_fill_kernel<<<grid, 128, 0, stream>>>(j);
   c->launches++;
   if (type != GPY_SPATIAL_POINT && f > 1) {
     long long warps = (long long)j.icx * j.icy;
     int blocks = (int)((warps * 32 + 255) / 256);
-    gpy::spatial_oversample_kernel<<<blocks, 256, 0, c->stream>>>(j);
+    gpy::spatial_oversample_kernel<<<blocks, 256, 0, stream>>>(j);
     c->launches++;
   }
   CUDA_TRY(cudaGetLastError());
@@ -542,7 +579,8 @@ size_t conv_smem_bytes(int h, int kw) {
 
 int launch_conv(gpy_context* c, const float* image, int cy, int cx, int pitch, int xpad, const float* kflip,
                 const gpy::ConvPlane* planes_dev, int n_planes, int max_h, int max_kw, float* out, int row0 = 0,
-                int row1 = 1 << 30) {
+                int row1 = 1 << 30, cudaStream_t stream = nullptr) {
+  if (!stream) stream = c->stream;
   size_t smem = conv_smem_bytes(max_h, max_kw);
   if (smem > (size_t)c->max_smem_optin)
     return fail(GPY_ERR_UNSUPPORTED, "PSF kernel too large for the shared-memory stencil (half width %d)", max_h);
@@ -551,7 +589,7 @@ int launch_conv(gpy_context* c, const float* image, int cy, int cx, int pitch, i
     c->conv_smem_set = smem;
   }
   dim3 grid((pitch + gpy::kConvTX - 1) / gpy::kConvTX, (cy + gpy::kConvTY - 1) / gpy::kConvTY, n_planes);
-  gpy::psf_conv_kernel<<<grid, gpy::kConvThreads, smem, c->stream>>>(image, cy, cx, pitch, xpad, kflip, planes_dev,
+  gpy::psf_conv_kernel<<<grid, gpy::kConvThreads, smem, stream>>>(image, cy, cx, pitch, xpad, kflip, planes_dev,
                                                                      out, (size_t)cy * pitch, row0, std::min(row1, cy));
   c->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -939,18 +977,21 @@ int get_slot(gpy_dataset* ds, Source& src, const double* sp, const Rect& rect, u
   const size_t img_cap = (size_t)(rect.cy + 4) * (s.pitch + 8);
   if (img * sizeof(float) > s.w.cap) GPY_TRY(s.w.reserve(img_cap * sizeof(float), c->stream));
   int wrows[2] = {0, rect.cy};
+  const size_t conv_bytes = img * ds->nT * sizeof(float);
+  if (conv && conv_bytes > s.conv.cap) GPY_TRY(s.conv.reserve(img_cap * ds->nT * sizeof(float), c->stream));
+  cudaStream_t ws;
+  GPY_TRY(work_stream(c, &ws));  // (after the allocations above: they are ordered on the library's stream)
   GPY_TRY(compute_spatial(c, ds->geom, (const double*)ds->d_omega.p, rect, src.desc.spatial_type, sp,
-                          (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f, wrows));
+                          (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f, wrows, ws));
   if (conv) {
-    if (img * ds->nT * sizeof(float) > s.conv.cap) GPY_TRY(s.conv.reserve(img_cap * ds->nT * sizeof(float), c->stream));
     if (ds->irf.has_psf)
       GPY_TRY(launch_conv(c, (const float*)s.w.p, rect.cy, rect.cx, s.pitch, rect.x0 - s.x0a,
                           (const float*)src.p_kflip.p, (const gpy::ConvPlane*)src.p_planes.p, ds->nT, src.max_h,
-                          src.max_kw, (float*)s.conv.p, wrows[0], wrows[1]));
+                          src.max_kw, (float*)s.conv.p, wrows[0], wrows[1], ws));
     else
       GPY_TRY(launch_conv(c, (const float*)s.w.p, rect.cy, rect.cx, s.pitch, rect.x0 - s.x0a,
                           (const float*)ds->d_kflip.p, (const gpy::ConvPlane*)ds->d_planes.p, ds->nT, ds->max_h,
-                          ds->max_kw, (float*)s.conv.p, wrows[0], wrows[1]));
+                          ds->max_kw, (float*)s.conv.p, wrows[0], wrows[1], ws));
   }
   s.key.assign(sp, sp + nsp);
   s.valid = true;
@@ -1080,6 +1121,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     if (done) return GPY_OK;
     c->replay.valid = false;  // whatever follows may move buffers the captured graph points into
   }
+  GPY_TRY(join_side_streams(c));  // (only non-empty after a call that failed half-way)
   unsigned k0_blocks = 0, k0_threads = 0;
   int k0_seg_cap = 0;
   const gpy::FluxJob* k0_jobs = nullptr;
@@ -1529,6 +1571,7 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   const size_t n_items = (size_t)B * n_tiles;
   const unsigned char* reduce_dup = nullptr;
   const int variant = rq.npred_out ? 1 : 0;
+  GPY_TRY(join_side_streams(c));  // the spatial chains of the sources that moved end here; K0 ran beside them
   if (tma_ok) {
     const gpy::DescLayout dl = gpy::desc_layout();
     fp.lay_es = (unsigned)lay.es;
@@ -1754,6 +1797,18 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
     c->own_stream = true;
   }
   cudaEventCreateWithFlags(&c->h2d_done, cudaEventDisableTiming);
+  if (const char* e = std::getenv("GPY_SIDE_STREAMS")) c->use_side_streams = std::atoi(e) != 0;
+  if (c->use_side_streams) {
+    cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming);
+    for (int i = 0; i < gpy_context::kSideStreams; ++i) {
+      if (cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c->side_done[i], cudaEventDisableTiming) != cudaSuccess) {
+        (void)cudaGetLastError();
+        c->use_side_streams = false;
+        break;
+      }
+    }
+  }
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
   c->force_generic = std::getenv("GPY_FORCE_GENERIC_FOLD") != nullptr;
@@ -1849,6 +1904,14 @@ int gpy_finalize(gpy_context_t* c) {
   if (c->h2d_done) cudaEventDestroy(c->h2d_done);
   if (c->t_begin) cudaEventDestroy(c->t_begin);
   if (c->t_end) cudaEventDestroy(c->t_end);
+  for (int i = 0; i < gpy_context::kSideStreams; ++i) {
+    if (c->side[i]) {
+      cudaStreamSynchronize(c->side[i]);
+      cudaStreamDestroy(c->side[i]);
+    }
+    if (c->side_done[i]) cudaEventDestroy(c->side_done[i]);
+  }
+  if (c->fork_ev) cudaEventDestroy(c->fork_ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return GPY_OK;

@@ -117,3 +117,50 @@ def test_tan_projection_dataset_vs_oracle(ctx, skydir):
     models[1].spatial_model.lat_0.value -= 0.3
     adapter.refresh_models(de, ds)
     assert abs(ds.stat_sum() - de.stat_sum()) < 1e-3
+
+
+SIDE_SCRIPT = r"""
+import json, sys
+sys.path.insert(0, %r)
+import numpy as np
+from gammapy_b200 import Map, configs
+from oracle import adapter
+ds = configs.make_c3(width=(6.0, 3.0), n_sources=9)
+de = adapter.evaluator_for(ds, conv="exact64")
+ds.counts = Map.from_geom(ds._geom, data=de.fake(4), dtype=float)
+first = ds.stat_sum()
+for m in ds.models:                      # every source moves: nine spatial chains in one evaluation
+    sm = getattr(m, "spatial_model", None)
+    if sm is not None:
+        sm.lon_0.value += 0.013
+        sm.lat_0.value -= 0.007
+moved = ds.stat_sum()
+de2 = adapter.evaluator_for(ds, conv="exact64")
+eng = ds._get_engine()
+v = eng.values()
+cols = [i for i, p in enumerate(eng.parameters) if p.name == "lon_0"]
+grid = np.tile(v, (1 + len(cols), 1))
+for k, c in enumerate(cols):
+    grid[1 + k, c] += 2e-3               # batched call: nine displaced cubes built side by side
+scan = [float(x) for x in eng.stat_sum(grid)]
+print("RESULT " + json.dumps({"first": first, "moved": moved, "oracle_moved": de2.stat_sum(), "scan": scan}))
+""" % ROOT
+
+
+def test_side_streams_do_not_change_the_result(ctx):
+    """The spatial chains (integrate_geom + PSF stencil) of the sources that moved run on side streams forked from and
+    joined into the library's stream (work_stream / join_side_streams in gpy_b200.cu): same bits as everything on one
+    stream (GPY_SIDE_STREAMS=0), and the moved evaluation agrees with the oracle at the new positions."""
+    runs = {}
+    for name, env in (("side", {"GPY_SIDE_STREAMS": "1"}), ("single", {"GPY_SIDE_STREAMS": "0"})):
+        e = dict(os.environ)
+        e.update(env)
+        res = subprocess.run([sys.executable, "-c", SIDE_SCRIPT], capture_output=True, text=True, env=e, timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        runs[name] = json.loads([l for l in res.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert runs["side"] == runs["single"]
+    r = runs["side"]
+    assert r["moved"] != r["first"]
+    assert abs(r["moved"] - r["oracle_moved"]) < 1e-3 * max(1.0, abs(r["oracle_moved"]) * 1e-6), r
+    assert r["scan"][0] == r["moved"]
+    assert len(set(r["scan"])) == len(r["scan"])
