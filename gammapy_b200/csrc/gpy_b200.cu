@@ -318,16 +318,18 @@ struct gpy_context {
   bool static_schedule = false;  // GPY_STATIC_SCHEDULE: never claim items dynamically
   int t64_stages = 1;            // GPY_FOLD_T64 = 1 (three CTAs per SM, single-buffered inputs) or 2 (two CTAs, double-buffered)
   bool use_t64 = true;           // GPY_FOLD_T64=0 switches the 64-pixel sub-tile kernel off (default: used whenever the launch is eligible)
-  // Side streams for the per-source spatial work (integrate_geom + PSF stencil) of an evaluation that moves several
-  // sources: the chains of different sources are independent and each stencil launch is only ~3 waves, so they run side
-  // by side; forked from / joined into the library's stream with events (work_stream / join_side_streams).
-  static constexpr int kSideStreams = 4;
-  cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t side_done[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t fork_ev = nullptr;
-  bool side_used[kSideStreams] = {false, false, false, false};
-  int side_next = 0;
-  bool use_side_streams = true;  // GPY_SIDE_STREAMS=0: everything on the library's stream
+  // Spatial chains (integrate_geom + PSF stencil) of the slots this evaluation has to fill: queued by get_slot, packed
+  // into the descriptor blob and run as three launches for all of them before the fold (flush in evaluate_impl).
+  struct PendingSpatial {
+    gpy::SpatialBatchJob job;
+    bool oversample;
+    size_t conv_smem;
+    Source* src;
+    size_t slot;  // index into src->slots
+  };
+  std::vector<PendingSpatial> pending;
+  size_t conv_batch_smem_set = 0;
+  bool batch_spatial = true;  // GPY_SPATIAL_BATCH=0: three launches per moved source instead (A/B, tests)
   int max_ctas_per_sm = 0;       // GPY_FOLD_CTAS_PER_SM (profiling): cap on resident fold CTAs per SM, 0 = occupancy limit
   bool no_desc_cache = false;  // GPY_NO_DESC_CACHE: run prep_items_kernel on every call
   std::vector<uint8_t> desc_key;  // what the descriptors in `desc` were built from (empty: none)
@@ -441,39 +443,13 @@ int upload_to(DevBuf& buf, const void* src, size_t bytes, cudaStream_t s) {
 
 gpy::WcsDev wcs_of(const GeomH& g) { return gpy::WcsDev{g.crval_lon, g.binsz, g.crpix_x, g.crpix_y, g.crval_lat, g.proj}; }
 
-// Stream for one source's spatial chain: a side stream that first waits for everything queued on the library's stream
-// so far (allocations of this call, kernels of the previous evaluation that still read a recycled slot).
-int work_stream(gpy_context* c, cudaStream_t* out) {
-  if (!c->use_side_streams || !c->side[0]) {
-    *out = c->stream;
-    return GPY_OK;
-  }
-  const int i = c->side_next++ % gpy_context::kSideStreams;
-  CUDA_TRY(cudaEventRecord(c->fork_ev, c->stream));
-  CUDA_TRY(cudaStreamWaitEvent(c->side[i], c->fork_ev, 0));
-  c->side_used[i] = true;
-  *out = c->side[i];
-  return GPY_OK;
-}
-// The library's stream waits for the side streams used since the last join.
-int join_side_streams(gpy_context* c) {
-  for (int i = 0; i < gpy_context::kSideStreams; ++i)
-    if (c->side_used[i]) {
-      CUDA_TRY(cudaEventRecord(c->side_done[i], c->side[i]));
-      CUDA_TRY(cudaStreamWaitEvent(c->stream, c->side_done[i], 0));
-      c->side_used[i] = false;
-    }
-  return GPY_OK;
-}
-
 // ---- K1 + K2 into a slot ---------------------------------------------------------------------
 // SpatialModel.integrate_geom on the evaluator geometry `rect` of dataset geometry `pg`, then
 // WcsNDMap.convolve.  `omega` is the parent solid-angle image (device).
 // rows_out[2] (optional): the rows [r0, r1) of the cutout outside of which the image is exactly zero.
 int compute_spatial(gpy_context* c, const GeomH& pg, const double* omega, const Rect& rect, int type,
                     const double* sp, float* w_out, int pitch, int xpad, int* f_out, int* rows_out = nullptr,
-                    cudaStream_t stream = nullptr) {
-  if (!stream) stream = c->stream;
+                    gpy::SpatialJob* job_out = nullptr) {  // job_out: describe the work instead of launching it
   GeomH eg = sub_geom(pg, rect);
   gpy::SpatialJob j;
   std::memset(&j, 0, sizeof(j));
@@ -560,13 +536,17 @@ int compute_spatial(gpy_context* c, const GeomH& pg, const double* omega, const 
     }
     if (rows_out[1] < rows_out[0]) rows_out[1] = rows_out[0];
   }
+  if (job_out) {
+    *job_out = j;
+    return GPY_OK;
+  }
   dim3 grid((pitch + 127) / 128, rect.cy);
-  gpy::spatial_fill_kernel<<<grid, 128, 0, stream>>>(j);
+  gpy::spatial_fill_kernel<<<grid, 128, 0, c->stream>>>(j);
   c->launches++;
   if (type != GPY_SPATIAL_POINT && f > 1) {
     long long warps = (long long)j.icx * j.icy;
     int blocks = (int)((warps * 32 + 255) / 256);
-    gpy::spatial_oversample_kernel<<<blocks, 256, 0, stream>>>(j);
+    gpy::spatial_oversample_kernel<<<blocks, 256, 0, c->stream>>>(j);
     c->launches++;
   }
   CUDA_TRY(cudaGetLastError());
@@ -579,8 +559,7 @@ size_t conv_smem_bytes(int h, int kw) {
 
 int launch_conv(gpy_context* c, const float* image, int cy, int cx, int pitch, int xpad, const float* kflip,
                 const gpy::ConvPlane* planes_dev, int n_planes, int max_h, int max_kw, float* out, int row0 = 0,
-                int row1 = 1 << 30, cudaStream_t stream = nullptr) {
-  if (!stream) stream = c->stream;
+                int row1 = 1 << 30) {
   size_t smem = conv_smem_bytes(max_h, max_kw);
   if (smem > (size_t)c->max_smem_optin)
     return fail(GPY_ERR_UNSUPPORTED, "PSF kernel too large for the shared-memory stencil (half width %d)", max_h);
@@ -589,7 +568,7 @@ int launch_conv(gpy_context* c, const float* image, int cy, int cx, int pitch, i
     c->conv_smem_set = smem;
   }
   dim3 grid((pitch + gpy::kConvTX - 1) / gpy::kConvTX, (cy + gpy::kConvTY - 1) / gpy::kConvTY, n_planes);
-  gpy::psf_conv_kernel<<<grid, gpy::kConvThreads, smem, stream>>>(image, cy, cx, pitch, xpad, kflip, planes_dev,
+  gpy::psf_conv_kernel<<<grid, gpy::kConvThreads, smem, c->stream>>>(image, cy, cx, pitch, xpad, kflip, planes_dev,
                                                                      out, (size_t)cy * pitch, row0, std::min(row1, cy));
   c->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -977,21 +956,46 @@ int get_slot(gpy_dataset* ds, Source& src, const double* sp, const Rect& rect, u
   const size_t img_cap = (size_t)(rect.cy + 4) * (s.pitch + 8);
   if (img * sizeof(float) > s.w.cap) GPY_TRY(s.w.reserve(img_cap * sizeof(float), c->stream));
   int wrows[2] = {0, rect.cy};
-  const size_t conv_bytes = img * ds->nT * sizeof(float);
-  if (conv && conv_bytes > s.conv.cap) GPY_TRY(s.conv.reserve(img_cap * ds->nT * sizeof(float), c->stream));
-  cudaStream_t ws;
-  GPY_TRY(work_stream(c, &ws));  // (after the allocations above: they are ordered on the library's stream)
+  if (conv && img * ds->nT * sizeof(float) > s.conv.cap)
+    GPY_TRY(s.conv.reserve(img_cap * ds->nT * sizeof(float), c->stream));
+  if (c->batch_spatial) {  // queued: evaluate_impl runs the chains of all the slots of this call in three launches
+    gpy_context::PendingSpatial ps;
+    std::memset(&ps.job, 0, sizeof(ps.job));
+    GPY_TRY(compute_spatial(c, ds->geom, (const double*)ds->d_omega.p, rect, src.desc.spatial_type, sp,
+                            (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f, wrows, &ps.job.j));
+    ps.oversample = src.desc.spatial_type != GPY_SPATIAL_POINT && s.f > 1;
+    ps.job.fill_gx = (s.pitch + 127) / 128;
+    ps.conv_smem = 0;
+    if (conv) {
+      const int max_h = ds->irf.has_psf ? src.max_h : ds->max_h, max_kw = ds->irf.has_psf ? src.max_kw : ds->max_kw;
+      ps.conv_smem = conv_smem_bytes(max_h, max_kw);
+      if (ps.conv_smem > (size_t)c->max_smem_optin)
+        return fail(GPY_ERR_UNSUPPORTED, "PSF kernel too large for the shared-memory stencil (half width %d)", max_h);
+      ps.job.kflip = (const float*)(ds->irf.has_psf ? src.p_kflip.p : ds->d_kflip.p);
+      ps.job.planes = (const gpy::ConvPlane*)(ds->irf.has_psf ? src.p_planes.p : ds->d_planes.p);
+      ps.job.conv_out = (float*)s.conv.p;
+      ps.job.n_planes = ds->nT;
+      ps.job.conv_gx = (s.pitch + gpy::kConvTX - 1) / gpy::kConvTX;
+      ps.job.conv_gy = (rect.cy + gpy::kConvTY - 1) / gpy::kConvTY;
+      ps.job.row0 = wrows[0];
+      ps.job.row1 = std::min(wrows[1], rect.cy);
+    }
+    ps.src = &src;
+    ps.slot = (size_t)(&s - src.slots.data());
+    c->pending.push_back(ps);
+  } else {
   GPY_TRY(compute_spatial(c, ds->geom, (const double*)ds->d_omega.p, rect, src.desc.spatial_type, sp,
-                          (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f, wrows, ws));
+                          (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f, wrows));
   if (conv) {
     if (ds->irf.has_psf)
       GPY_TRY(launch_conv(c, (const float*)s.w.p, rect.cy, rect.cx, s.pitch, rect.x0 - s.x0a,
                           (const float*)src.p_kflip.p, (const gpy::ConvPlane*)src.p_planes.p, ds->nT, src.max_h,
-                          src.max_kw, (float*)s.conv.p, wrows[0], wrows[1], ws));
+                          src.max_kw, (float*)s.conv.p, wrows[0], wrows[1]));
     else
       GPY_TRY(launch_conv(c, (const float*)s.w.p, rect.cy, rect.cx, s.pitch, rect.x0 - s.x0a,
                           (const float*)ds->d_kflip.p, (const gpy::ConvPlane*)ds->d_planes.p, ds->nT, ds->max_h,
-                          ds->max_kw, (float*)s.conv.p, wrows[0], wrows[1], ws));
+                          ds->max_kw, (float*)s.conv.p, wrows[0], wrows[1]));
+  }
   }
   s.key.assign(sp, sp + nsp);
   s.valid = true;
@@ -1112,7 +1116,7 @@ int evaluate_replay(gpy_context* c, const EvalRequest& rq, bool* done) {
   return GPY_OK;
 }
 
-int evaluate(gpy_context* c, const EvalRequest& rq) {
+int evaluate_impl(gpy_context* c, const EvalRequest& rq) {
   const int D = rq.n_datasets, B = rq.n_vec;
   if (D <= 0 || B <= 0) return fail(GPY_ERR_INVALID, "need at least one dataset and one parameter vector");
   {
@@ -1121,7 +1125,6 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
     if (done) return GPY_OK;
     c->replay.valid = false;  // whatever follows may move buffers the captured graph points into
   }
-  GPY_TRY(join_side_streams(c));  // (only non-empty after a call that failed half-way)
   unsigned k0_blocks = 0, k0_threads = 0;
   int k0_seg_cap = 0;
   const gpy::FluxJob* k0_jobs = nullptr;
@@ -1504,6 +1507,38 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   size_t off_in = pk.add(insts.data(), insts.size() * sizeof(gpy::InstDev));
   size_t off_jb = pk.add(jobs.data(), jobs.size() * sizeof(gpy::FluxJob));
   size_t off_df = pk.add(diffs.data(), diffs.size() * sizeof(int));
+  // spatial chains queued by get_slot: job records + the first block of each job in the three grids
+  const int n_sp = (int)c->pending.size();
+  size_t off_sp = 0, off_first = 0, sp_conv_smem = 0;
+  int sp_fill = 0, sp_over = 0, sp_conv = 0;
+  if (n_sp) {
+    std::vector<gpy::SpatialBatchJob> sj((size_t)n_sp);
+    std::vector<int> first(3 * ((size_t)n_sp + 1));
+    int* f_fill = first.data();
+    int* f_over = f_fill + n_sp + 1;
+    int* f_conv = f_over + n_sp + 1;
+    for (int k = 0; k < n_sp; ++k) {
+      const gpy_context::PendingSpatial& ps = c->pending[(size_t)k];
+      sj[(size_t)k] = ps.job;
+      f_fill[k] = sp_fill;
+      f_over[k] = sp_over;
+      f_conv[k] = sp_conv;
+      const long long nf = (long long)ps.job.fill_gx * ps.job.j.ecy;
+      const long long no = ps.oversample ? ((long long)ps.job.j.icx * ps.job.j.icy * 32 + 255) / 256 : 0;
+      const long long nc = (long long)ps.job.conv_gx * ps.job.conv_gy * ps.job.n_planes;
+      if (sp_fill + nf > INT32_MAX || sp_over + no > INT32_MAX || sp_conv + nc > INT32_MAX)
+        return fail(GPY_ERR_UNSUPPORTED, "too many spatial cubes to build in one evaluation (%d)", n_sp);
+      sp_fill += (int)nf;
+      sp_over += (int)no;
+      sp_conv += (int)nc;
+      sp_conv_smem = std::max(sp_conv_smem, ps.conv_smem);
+    }
+    f_fill[n_sp] = sp_fill;
+    f_over[n_sp] = sp_over;
+    f_conv[n_sp] = sp_conv;
+    off_sp = pk.add(sj.data(), sj.size() * sizeof(gpy::SpatialBatchJob));
+    off_first = pk.add(first.data(), first.size() * sizeof(int));
+  }
   GPY_TRY(ensure_pinned(c, pk.bytes.size()));
   std::memcpy(c->pinned, pk.bytes.data(), pk.bytes.size());
   GPY_TRY(c->staging.reserve(pk.bytes.size()));
@@ -1511,6 +1546,30 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   CUDA_TRY(cudaEventRecord(c->h2d_done, c->stream));
   c->h2d_pending = true;
   uint8_t* base = (uint8_t*)c->staging.p;
+
+  if (n_sp) {
+    const gpy::SpatialBatchJob* sj = (const gpy::SpatialBatchJob*)(base + off_sp);
+    const int* first = (const int*)(base + off_first);
+    gpy::spatial_fill_batch_kernel<<<(unsigned)sp_fill, 128, 0, c->stream>>>(sj, first, n_sp);
+    c->launches++;
+    if (sp_over) {
+      // (jobs without an oversampled inner cutout own no block of this grid: the search skips their empty ranges)
+      gpy::spatial_oversample_batch_kernel<<<(unsigned)sp_over, 256, 0, c->stream>>>(sj, first + n_sp + 1, n_sp);
+      c->launches++;
+    }
+    if (sp_conv) {
+      if (sp_conv_smem > c->conv_batch_smem_set) {
+        CUDA_TRY(cudaFuncSetAttribute(gpy::psf_conv_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sp_conv_smem));
+        c->conv_batch_smem_set = sp_conv_smem;
+      }
+      gpy::psf_conv_batch_kernel<<<(unsigned)sp_conv, gpy::kConvThreads, sp_conv_smem, c->stream>>>(
+          sj, first + 2 * ((size_t)n_sp + 1), n_sp);
+      c->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    c->pending.clear();
+  }
 
   if (!jobs.empty()) {
     int seg_cap = 0;  // doubles of shared memory for the per-segment integrals (falls back to the serial loop)
@@ -1571,7 +1630,6 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   const size_t n_items = (size_t)B * n_tiles;
   const unsigned char* reduce_dup = nullptr;
   const int variant = rq.npred_out ? 1 : 0;
-  GPY_TRY(join_side_streams(c));  // the spatial chains of the sources that moved end here; K0 ran beside them
   if (tma_ok) {
     const gpy::DescLayout dl = gpy::desc_layout();
     fp.lay_es = (unsigned)lay.es;
@@ -1764,6 +1822,16 @@ int evaluate(gpy_context* c, const EvalRequest& rq) {
   return GPY_OK;
 }
 
+int evaluate(gpy_context* c, const EvalRequest& rq) {
+  c->pending.clear();
+  const int rc = evaluate_impl(c, rq);
+  if (!c->pending.empty()) {  // failed before the queued spatial chains were launched: those slots hold nothing
+    for (auto& ps : c->pending) ps.src->slots[ps.slot].valid = false;
+    c->pending.clear();
+  }
+  return rc;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -1797,21 +1865,10 @@ int gpy_init(int device, void* stream, gpy_context_t** out) {
     c->own_stream = true;
   }
   cudaEventCreateWithFlags(&c->h2d_done, cudaEventDisableTiming);
-  if (const char* e = std::getenv("GPY_SIDE_STREAMS")) c->use_side_streams = std::atoi(e) != 0;
-  if (c->use_side_streams) {
-    cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming);
-    for (int i = 0; i < gpy_context::kSideStreams; ++i) {
-      if (cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking) != cudaSuccess ||
-          cudaEventCreateWithFlags(&c->side_done[i], cudaEventDisableTiming) != cudaSuccess) {
-        (void)cudaGetLastError();
-        c->use_side_streams = false;
-        break;
-      }
-    }
-  }
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
   c->force_generic = std::getenv("GPY_FORCE_GENERIC_FOLD") != nullptr;
+  if (const char* e = std::getenv("GPY_SPATIAL_BATCH")) c->batch_spatial = std::atoi(e) != 0;
   c->no_dedup = std::getenv("GPY_NO_DEDUP") != nullptr;
   c->static_schedule = std::getenv("GPY_STATIC_SCHEDULE") != nullptr;
   if (const char* e = std::getenv("GPY_FOLD_T64")) {
@@ -1904,14 +1961,6 @@ int gpy_finalize(gpy_context_t* c) {
   if (c->h2d_done) cudaEventDestroy(c->h2d_done);
   if (c->t_begin) cudaEventDestroy(c->t_begin);
   if (c->t_end) cudaEventDestroy(c->t_end);
-  for (int i = 0; i < gpy_context::kSideStreams; ++i) {
-    if (c->side[i]) {
-      cudaStreamSynchronize(c->side[i]);
-      cudaStreamDestroy(c->side[i]);
-    }
-    if (c->side_done[i]) cudaEventDestroy(c->side_done[i]);
-  }
-  if (c->fork_ev) cudaEventDestroy(c->fork_ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return GPY_OK;

@@ -173,9 +173,8 @@ __device__ __forceinline__ double eval_spatial(const SpatialJob& j, double lon_d
 }
 
 // One thread per output element (padded pitch): zero padding, point weights, f == 1 evaluation.
-__global__ void spatial_fill_kernel(SpatialJob j) {
-  int xp = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = blockIdx.y;
+__device__ __forceinline__ void spatial_fill_body(const SpatialJob& j, int bx, int y) {
+  int xp = bx * blockDim.x + threadIdx.x;
   if (xp >= j.pitch || y >= j.ecy) return;
   int x = xp - j.xpad;
   float v = 0.f;
@@ -197,11 +196,12 @@ __global__ void spatial_fill_kernel(SpatialJob j) {
   }
   j.out[(size_t)y * j.pitch + xp] = v;
 }
+__global__ void spatial_fill_kernel(SpatialJob j) { spatial_fill_body(j, blockIdx.x, blockIdx.y); }
 
 // f > 1: one warp per inner-cutout pixel, lanes stride the f*f sub-pixels; the block sum is rounded
 // to float32 by the stack into the float32 map (spatial.py:295-296, ndmap.py:1170), then * solid angle.
-__global__ void spatial_oversample_kernel(SpatialJob j) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__device__ __forceinline__ void spatial_oversample_body(const SpatialJob& j, int bx) {
+  int warp = (bx * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= j.icx * j.icy) return;
   int ix = warp % j.icx, iy = warp / j.icx;
@@ -226,6 +226,7 @@ __global__ void spatial_oversample_kernel(SpatialJob j) {
     j.out[(size_t)y * j.pitch + j.xpad + x] = (float)((double)s32 * omega);
   }
 }
+__global__ void spatial_oversample_kernel(SpatialJob j) { spatial_oversample_body(j, blockIdx.x); }
 
 // ----------------------------------------------------------------------------------------------
 // K2: WcsNDMap.convolve(PSFKernel), mode "same" (maps/wcs/ndmap.py:920-1010) as a direct stencil.
@@ -244,26 +245,26 @@ struct ConvPlane {
 
 constexpr int kConvTX = 64, kConvTY = 32, kConvThreads = 256;
 
-__global__ void __launch_bounds__(kConvThreads)
-psf_conv_kernel(const float* __restrict__ image, int cy, int cx, int pitch, int xpad,
-                const float* __restrict__ kflip, const ConvPlane* __restrict__ planes,
-                float* __restrict__ out, size_t plane_stride, int row0, int row1) {
+__device__ __forceinline__ void
+psf_conv_body(const float* __restrict__ image, int cy, int cx, int pitch, int xpad,
+              const float* __restrict__ kflip, const ConvPlane* __restrict__ planes,
+              float* __restrict__ out, size_t plane_stride, int row0, int row1, int bx, int by, int bz) {
   // [row0, row1): rows of `image` that can hold a non-zero (a point source fills two rows, an oversampled model its
   // inner cutout).  Stencil rows that only see zeros are skipped -- they would add 0 * k = 0 to every sum --, so a
   // point source costs 2 of the 2 h + 1 rows and output tiles beyond the kernel's reach are written as zeros at once.
   extern __shared__ __align__(16) float conv_smem[];
-  const ConvPlane pl = planes[blockIdx.z];
+  const ConvPlane pl = planes[bz];
   const int h = pl.h, kw = pl.kw, nrow = 2 * h + 1;
   const int spitch = kConvTX + kw;        // multiple of 4
   const int srows = kConvTY + 2 * h;
   float* in_s = conv_smem;                // [srows][spitch]
   float* k_s = conv_smem + (size_t)srows * spitch;  // [nrow][kw]
-  const int tx0 = blockIdx.x * kConvTX, ty0 = blockIdx.y * kConvTY;
+  const int tx0 = bx * kConvTX, ty0 = by * kConvTY;
   const int tid = threadIdx.x;
   if (ty0 - h >= row1 || ty0 + kConvTY + h <= row0) {  // block uniform: no input row of this tile can be non-zero
     const int y = ty0 + (tid >> 3);
     if (y < cy) {
-      float* o = out + blockIdx.z * plane_stride + (size_t)y * pitch + tx0;
+      float* o = out + bz * plane_stride + (size_t)y * pitch + tx0;
       for (int k = (tid & 7); k < kConvTX && tx0 + k < pitch; k += 8) o[k] = 0.f;
     }
     return;
@@ -318,7 +319,7 @@ psf_conv_kernel(const float* __restrict__ image, int cy, int cx, int pitch, int 
   }
   const int y = ty0 + ly;
   if (y < cy) {
-    float* o = out + blockIdx.z * plane_stride + (size_t)y * pitch;
+    float* o = out + bz * plane_stride + (size_t)y * pitch;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       int xpa = tx0 + xa + k, xpb = tx0 + xb + k;
@@ -326,6 +327,87 @@ psf_conv_kernel(const float* __restrict__ image, int cy, int cx, int pitch, int 
       if (xpb < pitch) o[xpb] = (xpb >= xpad && xpb < xpad + cx) ? (float)acc_b[k] : 0.f;
     }
   }
+}
+__global__ void __launch_bounds__(kConvThreads)
+psf_conv_kernel(const float* __restrict__ image, int cy, int cx, int pitch, int xpad,
+                const float* __restrict__ kflip, const ConvPlane* __restrict__ planes,
+                float* __restrict__ out, size_t plane_stride, int row0, int row1) {
+  psf_conv_body(image, cy, cx, pitch, xpad, kflip, planes, out, plane_stride, row0, row1, blockIdx.x, blockIdx.y,
+                blockIdx.z);
+}
+
+// ----------------------------------------------------------------------------------------------
+// K1 + K2 of every source an evaluation moved, as three launches instead of three per source.  An evaluation that
+// moves S sources (a position fit's gradient, the first evaluation of a fit) has S independent chains of small
+// kernels; launched one by one they are bound by launch latency and fill a fraction of the GPU each.  Here the
+// blocks of all chains form one grid per stage: block -> job by binary search in the prefix sums of the jobs'
+// block counts (a few hundred entries at most), the job record is copied to shared memory, and the block then
+// runs the body of the per-source kernel unchanged -- same arithmetic, same bits.
+// ----------------------------------------------------------------------------------------------
+struct SpatialBatchJob {
+  SpatialJob j;
+  // PSF stencil of this job (n_planes == 0: none); image = j.out
+  const float* kflip;
+  const ConvPlane* planes;
+  float* conv_out;
+  int n_planes;
+  int conv_gx, conv_gy;  // stencil tiles per plane
+  int row0, row1;        // rows of the image that can hold a non-zero
+  int fill_gx;           // blocks per row of the fill stage
+  int pad_[2];
+};
+
+// first[k] = first block of job k in this stage's grid, first[n] = grid size
+__device__ __forceinline__ int batch_find_job(const int* __restrict__ first, int n, int block) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(first + mid) <= block)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  return lo;
+}
+
+template <typename T>
+__device__ __forceinline__ void batch_load_job(T* dst, const T* __restrict__ src, int* job_s, const int* first, int n) {
+  static_assert(sizeof(T) % sizeof(int) == 0, "job records are copied as ints");
+  if (threadIdx.x == 0) *job_s = batch_find_job(first, n, blockIdx.x);
+  __syncthreads();
+  const int* q = reinterpret_cast<const int*>(src + *job_s);
+  int* d = reinterpret_cast<int*>(dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(T) / sizeof(int)); i += blockDim.x) d[i] = __ldg(q + i);
+  __syncthreads();
+}
+
+__global__ void spatial_fill_batch_kernel(const SpatialBatchJob* __restrict__ jobs, const int* __restrict__ first, int n) {
+  __shared__ SpatialBatchJob js;
+  __shared__ int job_s;
+  batch_load_job(&js, jobs, &job_s, first, n);
+  const int local = blockIdx.x - __ldg(first + job_s);
+  spatial_fill_body(js.j, local % js.fill_gx, local / js.fill_gx);
+}
+
+__global__ void spatial_oversample_batch_kernel(const SpatialBatchJob* __restrict__ jobs, const int* __restrict__ first,
+                                                int n) {
+  __shared__ SpatialBatchJob js;
+  __shared__ int job_s;
+  batch_load_job(&js, jobs, &job_s, first, n);
+  spatial_oversample_body(js.j, blockIdx.x - __ldg(first + job_s));
+}
+
+__global__ void __launch_bounds__(kConvThreads)
+psf_conv_batch_kernel(const SpatialBatchJob* __restrict__ jobs, const int* __restrict__ first, int n) {
+  __shared__ SpatialBatchJob js;
+  __shared__ int job_s;
+  batch_load_job(&js, jobs, &job_s, first, n);
+  const int local = blockIdx.x - __ldg(first + job_s);
+  const int per_plane = js.conv_gx * js.conv_gy;
+  const int bz = local / per_plane, rem = local - bz * per_plane;
+  const SpatialJob& j = js.j;
+  psf_conv_body(j.out, j.ecy, j.ecx, j.pitch, j.xpad, js.kflip, js.planes, js.conv_out, (size_t)j.ecy * j.pitch, js.row0,
+                js.row1, rem % js.conv_gx, rem / js.conv_gx, bz);
 }
 
 // ----------------------------------------------------------------------------------------------

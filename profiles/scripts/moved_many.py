@@ -1,5 +1,5 @@
-"""Evaluations that move many sources at once, with and without the side streams (GPY_SIDE_STREAMS, read at context
-creation): every source of C3 shifted (50 spatial chains), one source shifted, and a central-difference gradient
+"""Evaluations that move many sources at once, with the spatial chains of all moved sources in three launches (default)
+and with three launches per source (GPY_SPATIAL_BATCH=0, read at context creation): every source of C3 shifted (50 spatial chains), one source shifted, and a central-difference gradient
 over the 100 position parameters at a new point (201 vectors, 200 displaced cubes to build).  Run once per setting; prints wall time per call after a synchronize."""
 import os, sys, time
 sys.path.insert(0, os.getcwd())
@@ -54,7 +54,7 @@ def fd_gradient(r):
     eng.stat_sum_device(V, batch_out)
 
 
-label = "side streams " + os.environ.get("GPY_SIDE_STREAMS", "1")
+label = "batched spatial launches " + os.environ.get("GPY_SPATIAL_BATCH", "1")
 for name, fn, reps in (("all 50 sources moved", move_all, 12), ("one source moved", move_one, 50),
                        (f"position gradient ({2 * len(free) + 1} vectors)", fd_gradient, 6)):
     fn(-1)

@@ -141,18 +141,19 @@ v = eng.values()
 cols = [i for i, p in enumerate(eng.parameters) if p.name == "lon_0"]
 grid = np.tile(v, (1 + len(cols), 1))
 for k, c in enumerate(cols):
-    grid[1 + k, c] += 2e-3               # batched call: nine displaced cubes built side by side
+    grid[1 + k, c] += 2e-3               # batched call: nine displaced cubes built by the same three launches
 scan = [float(x) for x in eng.stat_sum(grid)]
 print("RESULT " + json.dumps({"first": first, "moved": moved, "oracle_moved": de2.stat_sum(), "scan": scan}))
 """ % ROOT
 
 
-def test_side_streams_do_not_change_the_result(ctx):
-    """The spatial chains (integrate_geom + PSF stencil) of the sources that moved run on side streams forked from and
-    joined into the library's stream (work_stream / join_side_streams in gpy_b200.cu): same bits as everything on one
-    stream (GPY_SIDE_STREAMS=0), and the moved evaluation agrees with the oracle at the new positions."""
+def test_batched_spatial_launches_do_not_change_the_result(ctx):
+    """The spatial chains (integrate_geom + PSF stencil) of all the sources an evaluation moved run as three launches
+    (spatial_fill_batch_kernel, spatial_oversample_batch_kernel, psf_conv_batch_kernel: block -> job table): same bits as
+    three launches per source (GPY_SPATIAL_BATCH=0), and the moved evaluation agrees with the oracle at the new
+    positions."""
     runs = {}
-    for name, env in (("side", {"GPY_SIDE_STREAMS": "1"}), ("single", {"GPY_SIDE_STREAMS": "0"})):
+    for name, env in (("side", {"GPY_SPATIAL_BATCH": "1"}), ("single", {"GPY_SPATIAL_BATCH": "0"})):
         e = dict(os.environ)
         e.update(env)
         res = subprocess.run([sys.executable, "-c", SIDE_SCRIPT], capture_output=True, text=True, env=e, timeout=600)
