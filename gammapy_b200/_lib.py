@@ -70,6 +70,7 @@ class IrfMapsDesc(C.Structure):
     _fields_ = [
         ("nx", C.c_int32), ("ny", C.c_int32),
         ("binsz", C.c_double), ("crval_lon", C.c_double), ("crpix_x", C.c_double), ("crpix_y", C.c_double),
+        ("crval_lat", C.c_double), ("proj", C.c_int32),
         ("n_rad", C.c_int32), ("rad_edges", C.c_void_p), ("psf_map", C.c_void_p), ("edisp_map", C.c_void_p),
     ]
 

@@ -58,7 +58,9 @@ def zoned_irfs(ds, binsz_irf=1.0, psf_scale=(1.0, 1.8), edisp_sigma=(0.10, 0.22)
     e_true = ds.exposure.geom.axes["energy_true"]
     e_reco = geom.axes["energy"]
     c = geom.center_skydir
-    ig = WcsGeom.create(skydir=(c.lon, c.lat), binsz=binsz_irf, width=tuple(geom.width), frame=geom.frame, proj="CAR")
+    # (as MapDatasetMaker builds them: the dataset's projection about the dataset's centre, coarser pixels)
+    ig = WcsGeom.create(skydir=(c.lon, c.lat), binsz=binsz_irf, width=tuple(geom.width), frame=geom.frame,
+                        proj=geom.projection)
     coords = ig.get_coord()
     dlon = (coords["lon"] - c.lon + 180.0) % 360.0 - 180.0
     zone = np.where(dlon > 0, 0, 1)  # (ny, nx)

@@ -68,7 +68,7 @@ struct GeomH {
   int nx, ny;
   double binsz, crval_lon, crpix_x, crpix_y;
   double crval_lat = 0.0;
-  int proj = 0;  // gpy_projection: 0 CAR about the equator, 1 TAN about (crval_lon, crval_lat)
+  int proj = 0;  // gpy_projection: 0 CAR, 1 TAN, both about (crval_lon, crval_lat)
 };
 GeomH geom_from_desc(const gpy_geom_desc& g) {
   GeomH h{g.nx, g.ny, g.binsz, g.crval_lon, g.crpix_x, g.crpix_y};
@@ -103,6 +103,14 @@ void world_to_pix(const GeomH& g, double lon, double lat, double& px, double& py
     const double y = ((std::sin(la) * std::cos(lp) - std::cos(la) * std::sin(lp) * std::cos(dl)) / s) / kDegH;
     px = x / (-g.binsz) + g.crpix_x - 1.0;
     py = y / g.binsz + g.crpix_y - 1.0;
+    return;
+  }
+  if (g.crval_lat != 0.0) {  // oblique plate carree (see WcsDev): tilt back by crval_lat, native (phi, theta) = (x, y)
+    const double dl = (lon - g.crval_lon) * kDegH, la = lat * kDegH, l0 = g.crval_lat * kDegH;
+    const double xs = std::cos(la) * std::cos(dl), ys = std::cos(la) * std::sin(dl), zs = std::sin(la);
+    const double x = xs * std::cos(l0) + zs * std::sin(l0), z = -xs * std::sin(l0) + zs * std::cos(l0);
+    px = (std::atan2(ys, x) / kDegH) / (-g.binsz) + g.crpix_x - 1.0;
+    py = (std::atan2(z, std::hypot(x, ys)) / kDegH) / g.binsz + g.crpix_y - 1.0;
     return;
   }
   double dlon = py_mod(lon - g.crval_lon + 180.0, 360.0) - 180.0;
@@ -862,9 +870,8 @@ int extract_psf(gpy_dataset* ds, Source& src, double lon, double lat) {
   q.n_rad = n;
   q.n_planes = nT;
   q.binsz = binsz;
-  // centre of the kernel geometry = centre of the dataset geometry (geom.to_odd_npix keeps center_skydir)
-  q.lon_c = ds->geom.crval_lon - binsz * ((ds->geom.nx - 1) / 2.0 + 1.0 - ds->geom.crpix_x);
-  q.lat_c = binsz * ((ds->geom.ny - 1) / 2.0 + 1.0 - ds->geom.crpix_y);
+  q.proj = ds->geom.proj;
+  q.pad_ = 0;
   q.raw = (double*)src.p_raw.p;
   q.kflip = (float*)src.p_kflip.p;
   q.kernel = (float*)src.p_kernel.p;
@@ -1998,8 +2005,8 @@ int gpy_dataset_create(gpy_context_t* c, const gpy_dataset_desc* desc, gpy_datas
   *out = nullptr;
   const gpy_geom_desc& g = desc->geom;
   if (g.proj != 0 && g.proj != 1) return fail(GPY_ERR_UNSUPPORTED, "projection code %d (0 CAR, 1 TAN)", g.proj);
-  if (g.proj == 0 && g.crval_lat != 0.0)
-    return fail(GPY_ERR_UNSUPPORTED, "CAR with a reference latitude != 0 is an oblique projection in wcslib: not supported");
+  if (g.proj == 0 && !(g.crval_lat > -90.0 && g.crval_lat < 90.0))
+    return fail(GPY_ERR_INVALID, "CAR: reference latitude %g outside (-90, 90) deg", g.crval_lat);
   if (g.nx <= 0 || g.ny <= 0 || g.n_true <= 0 || g.n_reco <= 0 || !(g.binsz > 0))
     return fail(GPY_ERR_INVALID, "invalid geometry (nx=%d ny=%d n_true=%d n_reco=%d binsz=%g)", g.nx, g.ny, g.n_true,
                 g.n_reco, g.binsz);
@@ -2142,8 +2149,7 @@ int gpy_dataset_set_irf_maps(gpy_dataset_t* ds, const gpy_irf_maps_desc* desc) {
   if (!desc->psf_map && !desc->edisp_map) return fail(GPY_ERR_INVALID, "neither a PSF map nor an edisp map given");
   if (desc->nx <= 0 || desc->ny <= 0 || !(desc->binsz > 0))
     return fail(GPY_ERR_INVALID, "bad IRF grid %d x %d, binsz %g", desc->nx, desc->ny, desc->binsz);
-  if (desc->psf_map && ds->geom.proj != 0)
-    return fail(GPY_ERR_UNSUPPORTED, "PSF kernel extraction at the source position is implemented for CAR geometries only");
+  if (desc->proj != 0 && desc->proj != 1) return fail(GPY_ERR_UNSUPPORTED, "projection code %d (0 CAR, 1 TAN)", desc->proj);
   if (desc->psf_map && (desc->n_rad < 2 || !desc->rad_edges))
     return fail(GPY_ERR_INVALID, "a PSF map needs rad_edges with at least two bins");
   gpy_context* c = ds->ctx;
@@ -2151,6 +2157,8 @@ int gpy_dataset_set_irf_maps(gpy_dataset_t* ds, const gpy_irf_maps_desc* desc) {
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   IrfMaps& m = ds->irf;
   m.geom = GeomH{desc->nx, desc->ny, desc->binsz, desc->crval_lon, desc->crpix_x, desc->crpix_y};
+  m.geom.crval_lat = desc->crval_lat;
+  m.geom.proj = desc->proj;
   const size_t plane = (size_t)desc->nx * desc->ny;
   m.has_psf = desc->psf_map != nullptr;
   m.has_edisp = desc->edisp_map != nullptr;

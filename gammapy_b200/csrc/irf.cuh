@@ -21,7 +21,11 @@ struct PsfExtractParams {
   const double* rad_center;  // [n_rad] deg
   int n_rad, n_planes;
   double binsz;              // deg, pixel size of the kernel geometry
-  double lon_c, lat_c;       // deg: centre of the kernel geometry (= centre of the dataset geometry)
+  int proj;                  // gpy_projection of the dataset geometry: the kernel geometry is WcsGeom.create(skydir =
+                             // its centre, proj) (geom.to_odd_npix, maps/wcs/geom.py:1106-1138), so a pixel's offset
+                             // from the centre pixel IS its native coordinate and its separation from the centre does
+                             // not depend on where on the sky the centre lies
+  int pad_;
   double* raw;               // scratch [sum n^2] doubles: block sums before normalisation, plane t at raw_off[t]
   const int* raw_off;        // [n_planes]
   float* kflip;              // output planes (flipped, padded rows), zero initialised by the caller
@@ -49,16 +53,17 @@ __global__ void __launch_bounds__(256) psf_extract_kernel(const PsfExtractParams
   const double step = Q.binsz / f;
   const double half = (m - 1) / 2.0;
   double* raw = Q.raw + Q.raw_off[t];
-  const double lonc = Q.lon_c * kDeg, latc = Q.lat_c * kDeg;
   double local = 0.0;
   for (int p = threadIdx.x; p < n * n; p += blockDim.x) {
     const int iy = p / n, ix = p - iy * n;
     double s = 0.0;
     for (int sy = 0; sy < f; ++sy) {
-      const double lat = __dadd_rn(Q.lat_c, __dmul_rn((double)(iy * f + sy) - half, step));
+      const double y = __dmul_rn((double)(iy * f + sy) - half, step);
       for (int sx = 0; sx < f; ++sx) {
-        const double lon = __dadd_rn(Q.lon_c, -__dmul_rn((double)(ix * f + sx) - half, step));
-        const double rad = angular_separation(lon * kDeg, lat * kDeg, lonc, latc) / kDeg;
+        const double x = -__dmul_rn((double)(ix * f + sx) - half, step);
+        // CAR: native (phi, theta) = (x, y), separation from the native origin; TAN: the plane radius is cot(theta)
+        const double rad = Q.proj == 1 ? atan(hypot(x, y) * kDeg) / kDeg
+                                       : angular_separation(x * kDeg, y * kDeg, 0.0, 0.0) / kDeg;
         // np.searchsorted(centers, rad) - 1 clipped to [0, n_rad - 2]
         int lo = 0, hi = Q.n_rad;
         while (lo < hi) {

@@ -29,11 +29,17 @@ constexpr double kEdge95 = 2.326174307353347;  // modeling/models/spatial.py:974
 // ----------------------------------------------------------------------------------------------
 // WCS: CAR about the equator.  lon = crval + cdelt_x (i + 1 - crpix_x), lat = cdelt_y (j + 1 - crpix_y)
 // (maps/wcs/geom.py:401-413; wcslib linp2x simple path).  No FMA contraction: keep numpy's rounding.
+// CAR about a reference point off the equator (WcsGeom.create sets CRVAL = skydir, geom.py:370-410) is an oblique
+// plate carree: native (phi, theta) = (x, y), the native origin sits at the reference point and -- with the default
+// LONPOLE (0 deg for delta_0 >= 0, else 180 deg) and LATPOLE (+90 deg), FITS WCS paper II section 2.4 and eqs. 8-10 --
+// the native pole lies on the reference meridian, so the spherical rotation (eq. 2) is a tilt of the native equator's
+// origin up to latitude delta_0: rotate the unit vector about the y axis by delta_0, then add alpha_0.
+// TAN about any reference point: gnomonic, native pole at the reference point.
 // ----------------------------------------------------------------------------------------------
 struct WcsDev {
   double crval_lon, binsz, crpix_x, crpix_y;
   double crval_lat;
-  int proj;  // 0 CAR about the equator, 1 TAN about (crval_lon, crval_lat)
+  int proj;  // 0 CAR about (crval_lon, crval_lat) (crval_lat == 0: the separable equatorial form), 1 TAN
 };
 
 __device__ __forceinline__ void pix_to_world_deg(const WcsDev& w, double px, double py, double& lon,
@@ -59,6 +65,15 @@ __device__ __forceinline__ void pix_to_world_deg(const WcsDev& w, double px, dou
   }
   lon = __dadd_rn(w.crval_lon, __dmul_rn(-w.binsz, __dadd_rn(__dadd_rn(px, 1.0), -w.crpix_x)));
   lat = __dmul_rn(w.binsz, __dadd_rn(__dadd_rn(py, 1.0), -w.crpix_y));
+  if (w.crval_lat != 0.0) {  // oblique plate carree: (lon - crval_lon, lat) so far are the native (phi, theta)
+    double sp, cp, st, ct, s0, c0;
+    sincos((lon - w.crval_lon) * kDeg, &sp, &cp);
+    sincos(lat * kDeg, &st, &ct);
+    sincos(w.crval_lat * kDeg, &s0, &c0);
+    const double x = ct * cp * c0 - st * s0, y = ct * sp, z = ct * cp * s0 + st * c0;
+    lon = w.crval_lon + atan2(y, x) / kDeg;
+    lat = atan2(z, hypot(x, y)) / kDeg;
+  }
 }
 
 // astropy.coordinates.angular_separation (Vincenty), radians.

@@ -161,11 +161,10 @@ class DeviceDataset:
             raise NotImplementedError("PSF map and edisp map must share their image geometry")
         if ig.frame != ds._geom.frame:
             raise NotImplementedError("IRF maps must be in the frame of the dataset geometry")
-        if ig.projection != "CAR":
-            raise NotImplementedError("IRF maps on a CAR grid only")
         m = _lib.IrfMapsDesc()
         m.nx, m.ny, m.binsz = ig.npix[0], ig.npix[1], ig.binsz
         m.crval_lon, m.crpix_x, m.crpix_y = ig.crval[0], ig.crpix[0], ig.crpix[1]
+        m.crval_lat, m.proj = ig.crval[1], _lib.PROJECTIONS[ig.projection]
         keep = {}
         if psf_by_position:
             if ds.psf.energy_axis_true.nbin != e_true.nbin:

@@ -269,6 +269,14 @@ def _axis_columns(ax):
     return ("ENERGY", "E_MIN", "E_MAX") if name == "ENERGY" else (name, name + "_MIN", name + "_MAX")
 
 
+def _default_lonpole(proj, crval_lat):
+    """LONPOLE when the header does not give it (FITS WCS paper II section 2.4): 180 deg for a zenithal projection
+    (theta_0 = 90 deg), for CAR (theta_0 = 0) 0 deg if delta_0 >= theta_0 else 180 deg.  The only value the kernels know."""
+    if proj == "TAN":
+        return 180.0
+    return 0.0 if crval_lat >= 0.0 else 180.0
+
+
 def map_to_hdus(m, hdu):
     """``WcsNDMap.to_hdulist(hdu=...)`` without the primary: the image HDU and, for a cube, its BANDS table."""
     geom = m.geom
@@ -278,8 +286,9 @@ def map_to_hdus(m, hdu):
         raise NotImplementedError(f"FITS header for frame {geom.frame!r}")
     header = {"WCSAXES": 2, "CRPIX1": geom.crpix[0], "CRPIX2": geom.crpix[1], "CDELT1": -geom.binsz, "CDELT2": geom.binsz,
               "CUNIT1": "deg", "CUNIT2": "deg", "CTYPE1": ctype[0], "CTYPE2": ctype[1], "CRVAL1": geom.crval[0],
-              "CRVAL2": geom.crval[1], "LONPOLE": 180.0 if geom.projection == "TAN" else 0.0,
-              "LATPOLE": geom.crval[1] if geom.projection == "TAN" else 90.0}
+              "CRVAL2": geom.crval[1], "LONPOLE": _default_lonpole(geom.projection, geom.crval[1]),
+              # the native pole's latitude: the reference point for TAN, 90 - |delta_0| on the reference meridian for CAR
+              "LATPOLE": geom.crval[1] if geom.projection == "TAN" else 90.0 - abs(geom.crval[1])}
     shape = ",".join(str(n) for n in (geom.npix[0], geom.npix[1]) + tuple(ax.nbin for ax in geom.axes))
     header["WCSSHAPE"] = f"({shape})"
     if getattr(m, "unit", ""):
@@ -317,6 +326,8 @@ def map_from_hdus(hdus, hdu, axis_names=None):
         raise NotImplementedError(f"projection / frame {h.get('CTYPE1')!r} (CAR or TAN images in galactic or icrs only)")
     if abs(abs(h["CDELT1"]) - abs(h["CDELT2"])) > 1e-12 * abs(h["CDELT2"]):
         raise NotImplementedError("square pixels only")
+    if "LONPOLE" in h and abs((float(h["LONPOLE"]) - _default_lonpole(proj, float(h["CRVAL2"])) + 180.0) % 360.0 - 180.0) > 1e-9:
+        raise NotImplementedError(f"LONPOLE = {h['LONPOLE']} is not the default of this projection (a rotated image)")
     data = image.data
     ny, nx = data.shape[-2:]
     axes = []

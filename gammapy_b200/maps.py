@@ -1,8 +1,8 @@
 """Host-side map containers mirroring the subset of ``gammapy.maps`` the likelihood path touches.
 
 Reference: maps/axes.py (MapAxis), maps/wcs/geom.py (WcsGeom), maps/core.py + maps/wcs/ndmap.py (Map).
-Geometries are CAR images about the equator with square pixels (the projection the CUDA kernels
-implement); data live in numpy arrays on the host and are mirrored to HBM by ``MapDataset``.
+Geometries are CAR (plate carree about any reference point) or TAN images with square pixels (the projections the
+CUDA kernels implement); data live in numpy arrays on the host and are mirrored to HBM by ``MapDataset``.
 """
 import copy as _copy
 
@@ -196,9 +196,11 @@ def round_up_to_odd(f):
 
 
 class WcsGeom:
-    """WCS map geometry (maps/wcs/geom.py:294-417), square pixels: CAR about the equator (crval latitude 0, as
-    ``WcsGeom.create`` builds it) or TAN about any reference point (gnomonic; FITS WCS paper II, Calabretta & Greisen 2002,
-    eqs. 5, 54, 55 with the native pole at the reference point and LONPOLE = 180 deg)."""
+    """WCS map geometry (maps/wcs/geom.py:294-417), square pixels, CRVAL = ``skydir`` as ``WcsGeom.create`` sets it
+    (geom.py:370-410): CAR (plate carree; separable about the equator, oblique about any other reference point: the
+    native origin is tilted up to the reference latitude, which is what the default LONPOLE / LATPOLE of FITS WCS paper
+    II, Calabretta & Greisen 2002, section 2.4 and eqs. 8-10 give) or TAN (gnomonic, eqs. 5, 54, 55 with the native pole
+    at the reference point and LONPOLE = 180 deg)."""
 
     def __init__(self, npix, binsz, crval, crpix, frame="icrs", axes=None, proj="CAR"):
         self._npix = (int(npix[0]), int(npix[1]))
@@ -210,19 +212,12 @@ class WcsGeom:
         self.axes = MapAxes(axes or [])
         if proj not in ("CAR", "TAN"):
             raise NotImplementedError(f"gammapy_b200 implements the CAR and TAN projections only, got {proj!r}")
-        if proj == "CAR" and self._crval[1] != 0.0:
-            raise NotImplementedError(
-                "CAR with a reference latitude != 0 is an oblique projection in wcslib; "
-                "gammapy_b200 supports CAR geometries centred on latitude 0 only"
-            )
+        if proj == "CAR" and not -90.0 < self._crval[1] < 90.0:
+            raise ValueError("CAR: reference latitude must lie inside (-90, 90) deg")
 
     @classmethod
     def create(cls, npix=None, binsz=0.5, proj="CAR", frame="icrs", refpix=None, axes=None, skydir=None, width=None):
         crval = as_lonlat(skydir)
-        if proj == "CAR" and crval[1] != 0.0:
-            raise NotImplementedError(
-                "a CAR geometry centred off the equator (the reference keeps crval latitude 0 and shifts crpix, "
-                "maps/wcs/geom.py:401-413: pixels are then not square on the sky); use proj='TAN' for such fields")
         if isinstance(skydir, SkyCoord):
             frame = skydir.frame
         bx, by = _pair(binsz)
@@ -336,6 +331,15 @@ class WcsGeom:
         else:
             lon = self._crval[0] + (-self._binsz) * (px + 1.0 - self._crpix[0])
             lat = self._binsz * (py + 1.0 - self._crpix[1])
+            if self._crval[1] != 0.0:  # oblique: (lon - crval, lat) are the native (phi, theta); tilt by the reference latitude
+                lon, lat = np.broadcast_arrays(lon, lat)
+                phi, theta, lat0 = (lon - self._crval[0]) * DEG, lat * DEG, self._crval[1] * DEG
+                ct = np.cos(theta)
+                xs = ct * np.cos(phi) * np.cos(lat0) - np.sin(theta) * np.sin(lat0)
+                ys = ct * np.sin(phi)
+                zs = ct * np.cos(phi) * np.sin(lat0) + np.sin(theta) * np.cos(lat0)
+                lon = self._crval[0] + np.arctan2(ys, xs) / DEG
+                lat = np.arctan2(zs, np.hypot(xs, ys)) / DEG
         out = [lon, lat]
         for ax, p in zip(self.axes, pix[2:]):
             out.append(ax.pix_to_coord(p))
@@ -357,6 +361,13 @@ class WcsGeom:
                 y = np.where(s_ > 0, ((np.sin(la) * np.cos(lat_p) - np.cos(la) * np.sin(lat_p) * np.cos(dl)) / s_) / DEG, np.nan)
             px = x / (-self._binsz) + self._crpix[0] - 1.0
             py = y / self._binsz + self._crpix[1] - 1.0
+        elif self._crval[1] != 0.0:  # oblique CAR: tilt back by the reference latitude, pixel = native (phi, theta) / cdelt
+            dl, la, lat0 = (lon - self._crval[0]) * DEG, lat * DEG, self._crval[1] * DEG
+            xs, ys, zs = np.cos(la) * np.cos(dl), np.cos(la) * np.sin(dl), np.sin(la)
+            xn = xs * np.cos(lat0) + zs * np.sin(lat0)
+            zn = -xs * np.sin(lat0) + zs * np.cos(lat0)
+            px = (np.arctan2(ys, xn) / DEG) / (-self._binsz) + self._crpix[0] - 1.0
+            py = (np.arctan2(zn, np.hypot(xn, ys)) / DEG) / self._binsz + self._crpix[1] - 1.0
         else:
             dlon = (lon - self._crval[0] + 180.0) % 360.0 - 180.0
             px = dlon / (-self._binsz) + self._crpix[0] - 1.0
@@ -374,7 +385,7 @@ class WcsGeom:
         else:
             x, y = np.arange(nx, dtype=float), np.arange(ny, dtype=float)
         nd = len(self.axes) + 2
-        if self.projection == "TAN":  # not separable: full (ny, nx) images of both coordinates
+        if self.projection == "TAN" or self._crval[1] != 0.0:  # not separable: full (ny, nx) images of both coordinates
             lon, lat = self.pix_to_coord((x[np.newaxis, :], y[:, np.newaxis]))[:2]
             shape2 = [1] * (nd - 2) + [len(y), len(x)]
             coords = {"lon": lon.reshape(shape2), "lat": lat.reshape(shape2)}

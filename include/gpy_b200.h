@@ -46,8 +46,9 @@ typedef enum { GPY_SPECTRAL_PL = 0, GPY_SPECTRAL_LP = 1, GPY_SPECTRAL_ECPL = 2 }
 typedef struct gpy_context gpy_context_t;
 typedef struct gpy_dataset gpy_dataset_t;
 
-/* Image projections: CAR about the equator (what WcsGeom.create builds for proj="CAR": crval latitude 0, the field's
- * latitude carried by crpix, maps/wcs/geom.py:401-413) and TAN (gnomonic) about any reference point. */
+/* Image projections, both about the reference point (crval_lon, crval_lat) = the skydir WcsGeom.create is given
+ * (maps/wcs/geom.py:370-410), with the default LONPOLE / LATPOLE: CAR (plate carree; the separable linear map when
+ * crval_lat == 0, the oblique projection of wcslib otherwise) and TAN (gnomonic). */
 typedef enum { GPY_PROJ_CAR = 0, GPY_PROJ_TAN = 1 } gpy_projection;
 
 /* WcsGeom of the counts cube (maps/wcs/geom.py:294-417) reduced to what the path reads. */
@@ -55,9 +56,9 @@ typedef struct {
   int32_t nx, ny;           /* image size in pixels (lon, lat) */
   int32_t n_true, n_reco;   /* energy_true / energy bins */
   double binsz;             /* deg */
-  double crval_lon;         /* deg; crval latitude must be 0 */
+  double crval_lon;         /* deg */
   double crpix_x, crpix_y;  /* FITS 1-based reference pixel */
-  double crval_lat;         /* deg; 0 for CAR */
+  double crval_lat;         /* deg; CAR: inside (-90, 90) */
   int32_t proj;             /* gpy_projection */
   int32_t pad_;
 } gpy_geom_desc;
@@ -160,8 +161,10 @@ int gpy_dataset_source_state(const gpy_dataset_t* ds, int32_t source, gpy_source
  * respective IRF (edisp_diagonal still serves apply_irf["edisp"] = False).  A batched call (n_vec > 1) whose vector
  * would trigger such a lookup fails with GPY_ERR_UNSUPPORTED: evaluate that point as a single vector first. */
 typedef struct {
-  int32_t nx, ny;            /* IRF image grid (CAR about the equator, as gpy_geom_desc) */
+  int32_t nx, ny;            /* IRF image grid (same conventions as gpy_geom_desc) */
   double binsz, crval_lon, crpix_x, crpix_y;
+  double crval_lat;          /* reference latitude, deg */
+  int32_t proj;              /* gpy_projection */
   int32_t n_rad;             /* rad bins of the PSF map */
   const double* rad_edges;   /* HOST [n_rad + 1] deg, increasing */
   const float* psf_map;      /* HOST [n_true, n_rad, ny, nx] sr-1 at the rad bin centres, or NULL */

@@ -40,7 +40,8 @@ def dataset_to_oracle(ds):
         from .irf import IrfGeom
 
         ig = (ds.psf if psf_by_position else ds.edisp).geom
-        irf["irf_geom"] = IrfGeom(ig.npix[0], ig.npix[1], ig.binsz, ig.crval[0], ig.crpix[0], ig.crpix[1])
+        irf["irf_geom"] = IrfGeom(ig.npix[0], ig.npix[1], ig.binsz, ig.crval[0], ig.crpix[0], ig.crpix[1],
+                                  crval_lat=ig.crval[1], proj=ig.projection)
         if psf_by_position:
             # the library holds the map in float32 (gpy_irf_maps_desc.psf_map): same numbers on both sides
             irf["psf_map"] = np.asarray(ds.psf.data, dtype=np.float32).astype(float)

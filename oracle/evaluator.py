@@ -172,7 +172,7 @@ class Evaluator:
             self.edisp = _irf.edisp_kernel_at(ds.edisp_map, ds.irf_geom, position)
         if ds.psf_map is not None:    # evaluator.py:206-227: psf.get_psf_kernel(position, geom, containment=0.999)
             self.psf = _irf.psf_kernel_at(ds.psf_map, ds.rad_edges, ds.irf_geom, position, ds.geom.binsz,
-                                          tuple(ds.geom.center_skydir))
+                                          tuple(ds.geom.center_skydir), proj=ds.geom.proj)
             self.n_irf_updates = getattr(self, "n_irf_updates", 0) + 1
         psf_width = 0.0
         if self.psf is not None:

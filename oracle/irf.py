@@ -24,22 +24,18 @@ Follows (paths relative to /root/reference/gammapy):
 """
 import numpy as np
 
-from .wcs import DEG, angular_separation
+from .wcs import DEG, ImageGeom, angular_separation
 
 PSF_MAX_OVERSAMPLING = 4  # irf/psf/map.py:20
 
 
-class IrfGeom:
-    """CAR image grid of an IRF map (reference latitude 0): pixel (i, j) centre at
-    lon = crval_lon - binsz (i + 1 - crpix_x), lat = binsz (j + 1 - crpix_y)."""
-
-    def __init__(self, nx, ny, binsz, crval_lon, crpix_x, crpix_y):
-        self.nx, self.ny, self.binsz = int(nx), int(ny), float(binsz)
-        self.crval_lon, self.crpix_x, self.crpix_y = float(crval_lon), float(crpix_x), float(crpix_y)
+class IrfGeom(ImageGeom):
+    """Image grid of an IRF map: an ``ImageGeom`` (CAR or TAN about its reference point; about the equator pixel (i, j)
+    has its centre at lon = crval_lon - binsz (i + 1 - crpix_x), lat = binsz (j + 1 - crpix_y))."""
 
     def coord_to_pix(self, lon, lat):
-        dlon = (lon - self.crval_lon + 180.0) % 360.0 - 180.0
-        return dlon / (-self.binsz) + self.crpix_x - 1.0, lat / self.binsz + self.crpix_y - 1.0
+        px, py = self.world_to_pix(lon, lat)
+        return float(px), float(py)
 
 
 def _clamped_bilinear(data, px, py):
@@ -95,8 +91,12 @@ def _interp_rad_linear(profile_t, centers, rad):
     return profile_t[idx] * (1 - t) + profile_t[idx + 1] * t
 
 
-def psf_kernel_at(psf_map, rad_edges, irf_geom, position, binsz, center, containment=0.999, precision_factor=12):
-    """(nT, K, K) kernel at ``position`` (lon, lat) [deg] for a map of pixel size ``binsz`` whose centre is ``center``."""
+def psf_kernel_at(psf_map, rad_edges, irf_geom, position, binsz, center, containment=0.999, precision_factor=12,
+                  proj="CAR"):
+    """(nT, K, K) kernel at ``position`` (lon, lat) [deg] for a map of pixel size ``binsz`` and projection ``proj`` whose
+    centre is ``center``: every plane on ``geom.to_odd_npix(max_radius=radii[t]).upsample(factor)``, i.e. a geometry
+    created about ``center`` in the map's projection (maps/wcs/geom.py:1106-1138), rad = separation of its pixel
+    centres from ``center`` (irf/psf/map.py:310-318)."""
     profile = psf_profile_at(psf_map, irf_geom, position[0], position[1])
     edges = np.asarray(rad_edges, dtype=float)
     centers = 0.5 * (edges[:-1] + edges[1:])
@@ -112,11 +112,8 @@ def psf_kernel_at(psf_map, rad_edges, irf_geom, position, binsz, center, contain
         with np.errstate(divide="ignore"):
             factor = int(min(int(np.ceil(precision_factor / base)) if base > 0 else PSF_MAX_OVERSAMPLING, PSF_MAX_OVERSAMPLING))
         n = round_up_to_odd(np.float64(2 * radii[t] / binsz))
-        m = n * factor
-        step = binsz / factor
-        off = (np.arange(m) - (m - 1) / 2.0) * step
-        lon = lon_c - off[np.newaxis, :]
-        lat = lat_c + off[:, np.newaxis]
+        cut = ImageGeom.create(skydir=(lon_c, lat_c), binsz=binsz, npix=(n, n), proj=proj).upsample(factor)
+        lon, lat = cut.get_coord()
         rad = angular_separation(lon * DEG, lat * DEG, lon_c * DEG, lat_c * DEG) / DEG
         vals = np.clip(_interp_rad_linear(profile[t], centers, rad.ravel()).reshape(rad.shape), 0, np.inf)
         img = vals.reshape(n, factor, n, factor).sum(axis=(1, 3))

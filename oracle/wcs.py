@@ -1,4 +1,4 @@
-"""Oracle: WCS image geometry (CAR about the equator), spherical trig, cutouts.
+"""Oracle: WCS image geometry (CAR, TAN), spherical trig, cutouts.
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
@@ -18,7 +18,11 @@ from the published formulas where it lives in astropy/wcslib
 CAR with ``crval = (lon0, 0)`` is the plain linear map
 ``lon = lon0 + cdelt_x (i + 1 - crpix_x)``, ``lat = cdelt_y (j + 1 - crpix_y)``
 (wcslib: native pole at delta_p = 90 deg reduces the spherical rotation to a
-longitude offset).  Off-equator CAR is an oblique projection and is refused.
+longitude offset).  CAR about a reference point off the equator -- what
+``WcsGeom.create(skydir=(lon, lat != 0))`` builds, geom.py:370-410 -- is an oblique
+plate carree: restated from FITS WCS paper II in its general form (native pole from
+eqs. 8-10 with the default LONPOLE / LATPOLE, rotations eqs. 2 and 5), parity
+unpinned like TAN (wcslib cannot be run here).
 """
 import numpy as np
 
@@ -84,8 +88,9 @@ def overlap_slices(large_shape, small_shape, position, mode="trim"):
 
 
 class ImageGeom:
-    """2-D WCS image geometry; (nx, ny) pixels of ``binsz`` deg, 0-based pixel coords.  ``proj``: "CAR" about the
-    equator, or "TAN" about (crval_lon, crval_lat), restated from the FITS WCS paper II (Calabretta & Greisen 2002) in its
+    """2-D WCS image geometry; (nx, ny) pixels of ``binsz`` deg, 0-based pixel coords.  ``proj``: "CAR" (about the
+    equator the separable linear map; about any other reference point the oblique plate carree, see ``_car_pole``), or
+    "TAN" about (crval_lon, crval_lat), restated from the FITS WCS paper II (Calabretta & Greisen 2002) in its
     native-spherical-coordinate form: eq. (54) R = (180/pi) cot(theta), eq. (14)-(15) x = R sin(phi), y = -R cos(phi), and
     the spherical rotation eq. (2) / (5) with the native pole at the reference point and LONPOLE = 180 deg.  wcslib
     itself cannot be run here: **parity unpinned** for TAN beyond the analytic checks of tests/test_host_logic.py."""
@@ -93,8 +98,8 @@ class ImageGeom:
     def __init__(self, nx, ny, binsz, crval_lon, crpix_x, crpix_y, crval_lat=0.0, proj="CAR"):
         if proj not in ("CAR", "TAN"):
             raise NotImplementedError(f"oracle: projection {proj!r}")
-        if proj == "CAR" and crval_lat != 0.0:
-            raise NotImplementedError("oracle: CAR restated only for crval latitude 0 (oblique otherwise)")
+        if proj == "CAR" and not -90.0 < crval_lat < 90.0:
+            raise ValueError("oracle: CAR reference latitude must lie inside (-90, 90) deg")
         self.proj = proj
         self.nx = int(nx)
         self.ny = int(ny)
@@ -150,6 +155,28 @@ class ImageGeom:
         return float(lon), float(lat)
 
     # -- transforms ------------------------------------------------------------------------
+    def _car_pole(self):
+        """(alpha_p, delta_p, phi_p) in radians of an oblique plate carree (theta_0 = phi_0 = 0), FITS WCS paper II
+        section 2.4: LONPOLE defaults to 0 deg when delta_0 >= theta_0 and to 180 deg otherwise; eq. (8)
+        delta_p = arg(cos(theta_0) cos(phi_p - phi_0), sin(theta_0)) +- acos(sin(delta_0) / sqrt(1 - cos^2(theta_0)
+        sin^2(phi_p - phi_0))), the solution nearer LATPOLE (default +90 deg) when both are valid; eqs. (9), (10)
+        sin(alpha_0 - alpha_p) = sin(phi_p - phi_0) cos(theta_0) / cos(delta_0),
+        cos(alpha_0 - alpha_p) = (sin(theta_0) - sin(delta_p) sin(delta_0)) / (cos(delta_p) cos(delta_0))."""
+        delta_0, theta_0, phi_0 = self.crval_lat * DEG, 0.0, 0.0
+        phi_p = 0.0 if delta_0 >= theta_0 else np.pi
+        u = np.arctan2(np.sin(theta_0), np.cos(theta_0) * np.cos(phi_p - phi_0))
+        v = np.arccos(np.sin(delta_0) / np.sqrt(1.0 - (np.cos(theta_0) * np.sin(phi_p - phi_0)) ** 2))
+        candidates = []
+        for cand in (u + v, u - v):
+            cand = (cand + np.pi) % (2 * np.pi) - np.pi        # into [-180, 180) deg
+            if -np.pi / 2 - 1e-12 <= cand <= np.pi / 2 + 1e-12:
+                candidates.append(cand)
+        delta_p = min(candidates, key=lambda c: abs(np.pi / 2 - c))
+        s = np.sin(phi_p - phi_0) * np.cos(theta_0) / np.cos(delta_0)
+        c = (np.sin(theta_0) - np.sin(delta_p) * np.sin(delta_0)) / (np.cos(delta_p) * np.cos(delta_0))
+        alpha_p = self.crval_lon * DEG - np.arctan2(s, c)
+        return alpha_p, delta_p, phi_p
+
     def pix_to_world(self, px, py):
         """wcs_pix2world(px, py, 0) in deg."""
         px = np.asarray(px, dtype=float)
@@ -169,6 +196,19 @@ class ImageGeom:
                 np.sin(theta) * np.cos(delta_p) - np.cos(theta) * np.sin(delta_p) * np.cos(phi - phi_p))
             at_ref = r_theta == 0
             return (np.where(at_ref, self.crval_lon, alpha / DEG), np.where(at_ref, self.crval_lat, delta / DEG))
+        if self.crval_lat != 0.0:   # oblique plate carree: eqs. (83), (84) phi = x, theta = y, then the rotation eq. (2)
+            phi = (-self.binsz) * (px + 1.0 - self.crpix_x) * DEG
+            theta = self.binsz * (py + 1.0 - self.crpix_y) * DEG
+            phi, theta = np.broadcast_arrays(phi, theta)
+            alpha_p, delta_p, phi_p = self._car_pole()
+            delta = np.arcsin(np.clip(np.sin(theta) * np.sin(delta_p)
+                                      + np.cos(theta) * np.cos(delta_p) * np.cos(phi - phi_p), -1, 1))
+            alpha = alpha_p + np.arctan2(
+                -np.cos(theta) * np.sin(phi - phi_p),
+                np.sin(theta) * np.cos(delta_p) - np.cos(theta) * np.sin(delta_p) * np.cos(phi - phi_p))
+            # the celestial longitude on the branch next to the reference longitude (a map does not straddle +-180 deg of it)
+            lon = self.crval_lon + ((alpha / DEG - self.crval_lon + 180.0) % 360.0 - 180.0)
+            return lon, delta / DEG
         lon = self.crval_lon + (-self.binsz) * (px + 1.0 - self.crpix_x)
         lat = self.binsz * (py + 1.0 - self.crpix_y)
         lon, lat = np.broadcast_arrays(lon, lat)
@@ -186,6 +226,14 @@ class ImageGeom:
                 r_theta = np.where(theta > 0, (180.0 / np.pi) / np.tan(theta), np.nan)   # eq. (54)
             x, y = r_theta * np.sin(phi), -r_theta * np.cos(phi)
             return x / (-self.binsz) + self.crpix_x - 1.0, y / self.binsz + self.crpix_y - 1.0
+        if self.crval_lat != 0.0:   # oblique plate carree: inverse rotation eq. (5), then x = phi, y = theta
+            alpha, delta = np.asarray(lon, dtype=float) * DEG, np.asarray(lat, dtype=float) * DEG
+            alpha_p, delta_p, phi_p = self._car_pole()
+            phi = phi_p + np.arctan2(-np.cos(delta) * np.sin(alpha - alpha_p),
+                                     np.sin(delta) * np.cos(delta_p) - np.cos(delta) * np.sin(delta_p) * np.cos(alpha - alpha_p))
+            theta = np.arcsin(np.clip(np.sin(delta) * np.sin(delta_p) + np.cos(delta) * np.cos(delta_p) * np.cos(alpha - alpha_p), -1, 1))
+            phi = (phi + np.pi) % (2 * np.pi) - np.pi
+            return (phi / DEG) / (-self.binsz) + self.crpix_x - 1.0, (theta / DEG) / self.binsz + self.crpix_y - 1.0
         dlon = (np.asarray(lon, dtype=float) - self.crval_lon + 180.0) % 360.0 - 180.0
         px = dlon / (-self.binsz) + self.crpix_x - 1.0
         py = np.asarray(lat, dtype=float) / self.binsz + self.crpix_y - 1.0

@@ -62,4 +62,4 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.BackgroundDesc) == 16
     assert C.sizeof(_lib.SourceState) == 32
     assert C.sizeof(_lib.DatasetDesc) == 64 + 8 * 8 + 8 + 8 * 3 + 8 + 8 + 8 + 8  # ... weight, compact (padded), mask_row_bytes
-    assert C.sizeof(_lib.IrfMapsDesc) == 8 + 4 * 8 + 8 + 3 * 8
+    assert C.sizeof(_lib.IrfMapsDesc) == 8 + 5 * 8 + 8 + 3 * 8  # nx, ny; binsz .. crval_lat; proj, n_rad; three pointers

@@ -78,3 +78,34 @@ def test_map_dataset_round_trip(tmp_path, zoned):
     assert set(hdus["COUNTS_BANDS"].data) == {"CHANNEL", "ENERGY", "E_MIN", "E_MAX"}
     assert hdus["COUNTS"].header["BANDSHDU"] == "COUNTS_BANDS" and hdus["COUNTS"].header["CTYPE1"] == "GLON-CAR"
     assert hdus["PSF_BANDS"].data["CHANNEL"].size == ds.psf.data.shape[0] * ds.psf.data.shape[1]
+
+
+@pytest.mark.parametrize("proj,skydir", [("CAR", (83.63, 22.01)), ("CAR", (266.4, -29.0)), ("TAN", (30.0, 40.0))])
+def test_off_equator_geometry_round_trip(tmp_path, proj, skydir):
+    """CRVAL2, the projection code and the pole keywords of an oblique CAR / TAN image survive the round trip; the pole
+    keywords are the defaults of FITS WCS paper II (the only ones the kernels implement), anything else is refused."""
+    ds = configs.zoned_irfs(configs.make_dataset(width=(3.0, 1.6), n_reco=5, n_true=8, mask_radius=0.7, skydir=skydir,
+                                                 proj=proj, name="off"))
+    path = str(tmp_path / "off.fits")
+    ds.write(path)
+    back = MapDataset.read(path)
+    assert back._geom == ds._geom and back._geom.projection == proj and back._geom.crval == ds._geom.crval
+    assert back.psf.geom == ds.psf.geom and back.psf.geom.projection == proj
+    _assert_same_map(ds.exposure, back.exposure)
+    a, b = ds._geom.to_image().get_coord(), back._geom.to_image().get_coord()
+    np.testing.assert_array_equal(a["lon"], b["lon"])
+    np.testing.assert_array_equal(a["lat"], b["lat"])
+    hdus = fitsio.read_hdus(path)
+    h = {x.name: x for x in hdus}["COUNTS"].header
+    assert h["CTYPE1"] == ("GLON-" + proj) and h["CRVAL2"] == ds._geom.crval[1]
+    if proj == "CAR":
+        assert h["LONPOLE"] == (0.0 if skydir[1] >= 0 else 180.0) and h["LATPOLE"] == pytest.approx(90.0 - abs(skydir[1]))
+    else:
+        assert h["LONPOLE"] == 180.0 and h["LATPOLE"] == pytest.approx(skydir[1])
+    # a rotated image (non-default LONPOLE) is not something the kernels can evaluate: refuse to read it
+    for x in hdus:
+        if x.name == "COUNTS":
+            x.header["LONPOLE"] = 90.0
+    fitsio.write_hdus(str(tmp_path / "rot.fits"), hdus)
+    with pytest.raises(NotImplementedError):
+        MapDataset.read(str(tmp_path / "rot.fits"))

@@ -129,3 +129,41 @@ def test_batched_call_refuses_a_lookup(ctx):
     grid[2, col] -= 2.0    # would need MapEvaluator.update with a new IRF lookup
     with pytest.raises(NotImplementedError):
         eng.stat_sum(grid)
+
+
+@pytest.mark.parametrize("proj,skydir", [("CAR", (83.63, 22.01)), ("TAN", (266.4, -29.0))])
+def test_irf_lookup_off_the_equator(ctx, proj, skydir):
+    """IRF maps and dataset on an oblique CAR / TAN geometry (what MapDatasetMaker produces for a field off the
+    equator): the lookup pixel follows the IRF grid's projection, the kernel geometry is created about the dataset's
+    centre in the dataset's projection (geom.to_odd_npix, maps/wcs/geom.py:1106-1138), so its pixel separations are
+    those of the native coordinates -- not those of an equatorial grid at that latitude."""
+    from gammapy_b200 import Map, configs
+    from gammapy_b200.modeling.models import FoVBackgroundModel, GaussianSpatialModel, PowerLawSpectralModel, SkyModel
+    from oracle import adapter, irf as oirf
+
+    cosb = np.cos(np.radians(skydir[1]))
+    p_pos = (skydir[0] + 1.2 / cosb, skydir[1] + 0.3)
+    g_pos = (skydir[0] - 1.1 / cosb, skydir[1] - 0.2)
+    g = SkyModel(spatial_model=GaussianSpatialModel(lon_0=g_pos[0], lat_0=g_pos[1], sigma=0.15, frame=configs.FRAME),
+                 spectral_model=PowerLawSpectralModel(index=2.6, amplitude=3e-11, reference=1), name="gauss")
+    ds = _zoned([_point(p_pos[0], p_pos[1], "point"), g, FoVBackgroundModel(dataset_name="c1")], skydir=skydir, proj=proj)
+    assert ds.psf.geom.projection == proj and ds.psf.geom.crval[1] == pytest.approx(skydir[1])
+    de = adapter.evaluator_for(ds, conv="exact64")
+    od = de.ds
+    _check(ds, de)
+    for name, pos in (("point", p_pos), ("gauss", g_pos)):
+        st = ds.evaluator_irf(name)
+        want = oirf.psf_kernel_at(od.psf_map, od.rad_edges, od.irf_geom, pos, od.geom.binsz, tuple(od.geom.center_skydir),
+                                  proj=proj)
+        assert st["k"] == want.shape[-1] and st["n_updates"] == 1
+        np.testing.assert_allclose(st["psf_kernel"], want, rtol=0, atol=2e-7 * want.max())
+    assert ds.evaluator_irf("point", False)["edisp_pixel"] != ds.evaluator_irf("gauss", False)["edisp_pixel"]
+    assert ds.evaluator_irf("point", False)["k"] < ds.evaluator_irf("gauss", False)["k"]
+    ds.counts = Map.from_geom(ds._geom, data=de.fake(5), dtype=float)
+    assert abs(ds.stat_sum() - de.stat_sum()) < 1e-3
+    # the point source crosses into the other zone
+    ds.models["point"].spatial_model.lon_0.value = skydir[0] - 0.9 / cosb
+    adapter.refresh_models(de, ds)
+    assert abs(ds.stat_sum() - de.stat_sum()) < 1e-3
+    assert ds.evaluator_irf("point", False)["edisp_pixel"] == ds.evaluator_irf("gauss", False)["edisp_pixel"] or \
+        ds.evaluator_irf("point", False)["k"] == ds.evaluator_irf("gauss", False)["k"]

@@ -384,7 +384,7 @@ def test_errors_are_loud(ctx):
     from gammapy_b200 import GaussianSpatialModel, MapAxis, PowerLawSpectralModel, SkyModel, WcsGeom, configs
 
     with pytest.raises(NotImplementedError):
-        WcsGeom.create(skydir=(0, 10), binsz=0.1, width=2)  # oblique CAR
+        WcsGeom.create(skydir=(0, 10), binsz=0.1, width=2, proj="AIT")
     ds = configs.make_dataset(width=(1.0, 1.0), mask_radius=None)
     bad = SkyModel(spatial_model=GaussianSpatialModel(frame="icrs"), spectral_model=PowerLawSpectralModel(), name="x")
     ds.models = [bad]
