@@ -81,6 +81,40 @@ def zoned_irfs(ds, binsz_irf=1.0, psf_scale=(1.0, 1.8), edisp_sigma=(0.10, 0.22)
     return ds
 
 
+def graded_irfs(ds, binsz_irf=0.5, psf_scale=(1.0, 1.6), edisp_sigma=(0.10, 0.20), edisp_bias=(0.0, 0.05)):
+    """Replace the IRFs of ``ds`` by maps on a spatial grid of ``binsz_irf`` pixels whose PSF width and energy resolution /
+    bias grow smoothly with the offset from the map centre, as they do across the field of view of a real observation
+    (``MapDatasetMaker`` fills ``PSFMap`` / ``EDispKernelMap`` per IRF pixel): EVERY IRF pixel has its own edisp matrix, so
+    every evaluator gets a matrix of its own (irf/edisp/map.py:369-401, nearest pixel) and a PSF kernel interpolated
+    between its four neighbours."""
+    geom = ds._geom
+    e_true = ds.exposure.geom.axes["energy_true"]
+    e_reco = geom.axes["energy"]
+    c = geom.center_skydir
+    ig = WcsGeom.create(skydir=(c.lon, c.lat), binsz=binsz_irf, width=tuple(geom.width), frame=geom.frame,
+                        proj=geom.projection)
+    offset = ig.separation((c.lon, c.lat))  # (ny, nx) deg
+    u = offset / max(float(offset.max()), 1e-12)
+    # break the circular symmetry so that no two IRF pixels share their numbers
+    yy, xx = np.mgrid[0:ig.npix[1], 0:ig.npix[0]]
+    u = np.clip(u + 0.01 * ((3 * xx + 7 * yy) % 11) / 11.0, 0.0, 1.0)
+    rad_axis = ds.psf.rad_axis
+    sig0 = np.exp(np.interp(np.log(e_true.center), np.log([e_true.edges[0], e_true.edges[-1]]), np.log([0.12, 0.04])))
+    psf = np.empty(ds.psf.data.shape + u.shape)
+    ed = np.empty((e_true.nbin, e_reco.nbin) + u.shape)
+    for j in range(u.shape[0]):
+        for i in range(u.shape[1]):
+            w = float(u[j, i])
+            scale = psf_scale[0] + w * (psf_scale[1] - psf_scale[0])
+            psf[..., j, i] = PSFMap.from_gauss(energy_axis_true=e_true, rad_axis=rad_axis, sigma=sig0 * scale).data
+            ed[..., j, i] = EDispKernelMap.from_gauss(
+                energy_axis=e_reco, energy_axis_true=e_true, sigma=edisp_sigma[0] + w * (edisp_sigma[1] - edisp_sigma[0]),
+                bias=edisp_bias[0] + w * (edisp_bias[1] - edisp_bias[0])).kernel.pdf_matrix
+    ds.psf = PSFMap(e_true, rad_axis, psf, geom=ig)
+    ds.edisp = EDispKernelMap(data=ed, geom=ig, axes=[e_true, e_reco])
+    return ds
+
+
 def c1_models(dataset_name="c1"):
     """analysis_3d tutorial shape: one Gaussian x PowerLaw + FoV background (simulate_3d.py:102-134)."""
     spatial = GaussianSpatialModel(lon_0="0.2 deg", lat_0="0.1 deg", sigma="0.3 deg", frame=FRAME)

@@ -1398,9 +1398,6 @@ int evaluate_impl(gpy_context* c, const EvalRequest& rq) {
         if (std::find(codes.begin(), codes.end(), insts[i].group) == codes.end()) codes.push_back(insts[i].group);
       std::sort(codes.begin(), codes.end());
       if (!codes.empty()) {
-        if (codes.size() > 4)
-          return fail(GPY_ERR_UNSUPPORTED, "the sources of dataset %d use %zu different edisp matrices (IRF pixels); "
-                      "at most 4 per dataset are supported", d, codes.size());
         if (codes != ds->group_codes) {
           const size_t plane = (size_t)ds->irf.geom.nx * ds->irf.geom.ny;
           // one strided view per group would need per-group strides: gather the matrices contiguously instead
@@ -1455,7 +1452,7 @@ int evaluate_impl(gpy_context* c, const EvalRequest& rq) {
   size_t max_fold_smem = 0;
   if (!tma_ok) {
     for (int d = 0; d < D; ++d)
-      max_fold_smem = std::max(max_fold_smem, gpy::fold_smem_bytes(rq.datasets[d]->groups_used, rq.datasets[d]->nT,
+      max_fold_smem = std::max(max_fold_smem, gpy::fold_smem_bytes(rq.datasets[d]->nT,
                                                                    rq.datasets[d]->nRp, max_inst));
     if (max_fold_smem > (size_t)c->max_smem_optin)
       return fail(GPY_ERR_UNSUPPORTED,

@@ -637,9 +637,10 @@ constexpr int kFoldTCH = 16;       // true-energy bins staged in shared memory p
 
 // Shared memory of one block: v chunk [G][TCH][TPX] f64, pdf [G][nT][nRp] f64, bkgfac [nRp], scratch [8],
 // overlap list [max_inst] InstDev.
-__host__ __device__ inline size_t fold_smem_bytes(int G, int nT, int nRp, int max_inst) {
-  return ((size_t)G * kFoldTCH * kFoldTPX + (size_t)G * nT * nRp + nRp + 8) * sizeof(double) +
-         (size_t)max_inst * sizeof(InstDev);
+// (one edisp matrix resident at a time, whatever the number of matrices of the dataset: see the kernel)
+__host__ __device__ inline size_t fold_smem_bytes(int nT, int nRp, int max_inst) {
+  return ((size_t)kFoldTCH * kFoldTPX + (size_t)nT * nRp + nRp + 8) * sizeof(double) +
+         (size_t)max_inst * (sizeof(InstDev) + sizeof(int));
 }
 
 __device__ __forceinline__ double block_sum_256(double v, double* scratch) {
@@ -663,6 +664,11 @@ __device__ __forceinline__ double block_sum_256(double v, double* scratch) {
 //   phase 2: thread (pixel pair, reco chunk of 8) accumulates acc[r] += pdf[t][r] * v[t][p] over the
 //     non-zero band of the edisp matrix; accumulators stay in registers across the passes;
 //   epilogue: + background * norm (E/E0)^-tilt, clip, masked Cash term, block reduction.
+// Edisp matrices ("groups": with position-dependent IRFs every evaluator has the matrix of its nearest IRF pixel,
+// irf/edisp/map.py:369-401, so a dataset can hold as many matrices as it has sources): the tile works through the
+// distinct matrices of ITS overlapping sources one after the other -- matrix into shared memory, phase 1 and phase 2 of
+// the sources that use it, accumulators kept -- so shared memory does not grow with the number of matrices, and a
+// tile no source reaches goes straight to the epilogue.
 __global__ void __launch_bounds__(kFoldThreads, GPY_FOLD_MINBLOCKS) fold_cash_generic_kernel(const FoldParams P) {
   extern __shared__ __align__(16) double fold_smem[];
   const int b = blockIdx.x % P.B;
@@ -670,19 +676,19 @@ __global__ void __launch_bounds__(kFoldThreads, GPY_FOLD_MINBLOCKS) fold_cash_ge
   const int d = P.tile_ds[tile];
   const DatasetDev D = P.ds[d];
   const EvalDev ev = P.evals[(size_t)d * P.B + b];
-  const int nT = D.nT, nR = D.nR, nRp = D.nRp, G = D.n_groups;
+  const int nT = D.nT, nR = D.nR, nRp = D.nRp;
   const long long p0 = (long long)(tile - D.tile_begin) * kFoldTPX;
   const int npx = (int)min((long long)kFoldTPX, D.P - p0);
   const int tid = threadIdx.x;
 
-  double* vs = fold_smem;                                      // [G][TCH][TPX]
-  double* pdf_s = vs + (size_t)G * kFoldTCH * kFoldTPX;        // [G][nT][nRp]
-  double* bkgfac = pdf_s + (size_t)G * nT * nRp;               // [nRp]
+  double* vs = fold_smem;                                      // [TCH][TPX]
+  double* pdf_s = vs + (size_t)kFoldTCH * kFoldTPX;            // [nT][nRp]: the matrix being worked on
+  double* bkgfac = pdf_s + (size_t)nT * nRp;                   // [nRp]
   double* scratch = bkgfac + nRp;                              // [8]
   InstDev* slist = reinterpret_cast<InstDev*>(scratch + 8);    // [max_inst]
-  __shared__ int n_list;
+  int* glist = reinterpret_cast<int*>(slist + P.max_inst);     // [max_inst]: distinct matrices of slist, ascending
+  __shared__ int n_list, n_glist;
 
-  for (int i = tid; i < G * nT * nRp; i += kFoldThreads) pdf_s[i] = D.edisp[i];
   if (tid < nRp) {
     double fac = 1.0;
     if (ev.bkg_enabled && tid < nR)  // PowerLawNormSpectralModel.evaluate (spectral.py:1159-1162)
@@ -708,10 +714,24 @@ __global__ void __launch_bounds__(kFoldThreads, GPY_FOLD_MINBLOCKS) fold_cash_ge
       if (ov) slist[n + __popc(m & ((1u << tid) - 1u))] = in;
       n += __popc(m);
     }
-    if (tid == 0) n_list = n;
+    if (tid == 0) {
+      n_list = n;
+      int ng = 0;
+      for (int l = 0; l < n; ++l) {  // sorted insertion of the distinct group indices (a handful per tile)
+        const int g = slist[l].group;
+        int k = 0;
+        while (k < ng && glist[k] < g) ++k;
+        if (k < ng && glist[k] == g) continue;
+        for (int m = ng; m > k; --m) glist[m] = glist[m - 1];
+        glist[k] = g;
+        ++ng;
+      }
+      n_glist = ng;
+    }
   }
   __syncthreads();
-  const int nl = n_list;
+  const int nl = n_list, ngl = n_glist;
+  int loaded = -1;  // matrix currently in pdf_s
 
   // phase-1 coordinates: 32 pixel quads x 8 energy slots
   const int q = tid & 31, slot = tid >> 5;
@@ -736,9 +756,17 @@ __global__ void __launch_bounds__(kFoldThreads, GPY_FOLD_MINBLOCKS) fold_cash_ge
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.0;
 
+    for (int lg = 0; lg < ngl; ++lg) {
+    const int g = glist[lg];
+    if (g != loaded) {  // (block uniform; the previous user of pdf_s finished behind the barrier that ends its pass)
+      const double* src = D.edisp + (size_t)g * nT * nRp;
+      for (int i = tid; i < nT * nRp; i += kFoldThreads) pdf_s[i] = __ldg(src + i);
+      loaded = g;
+      // (visible to phase 2 through the barrier after phase 1)
+    }
     for (int t0 = 0; t0 < nT; t0 += kFoldTCH) {
       // ---- phase 1 ----
-      for (int g = 0; g < G; ++g) {
+      {
 #pragma unroll
         for (int tt = 0; tt < kFoldTCH / 8; ++tt) {
           const int tl = slot + 8 * tt, t = t0 + tl;
@@ -785,7 +813,7 @@ __global__ void __launch_bounds__(kFoldThreads, GPY_FOLD_MINBLOCKS) fold_cash_ge
                 if (qy[k] >= 0) s[k] = (s[k] * (double)__ldg(erow + k)) * 1e4;
             }
           }
-          double* dst = vs + ((size_t)g * kFoldTCH + tl) * kFoldTPX + 4 * q;
+          double* dst = vs + (size_t)tl * kFoldTPX + 4 * q;
           *reinterpret_cast<double2*>(dst) = make_double2(s[0], s[1]);
           *reinterpret_cast<double2*>(dst + 2) = make_double2(s[2], s[3]);
         }
@@ -793,11 +821,11 @@ __global__ void __launch_bounds__(kFoldThreads, GPY_FOLD_MINBLOCKS) fold_cash_ge
       __syncthreads();
       // ---- phase 2 ----
       if (c < nchunks) {
-        for (int g = 0; g < G; ++g) {
+        {
           const int blo = D.band[(g * nchunks + c) * 4], bhi = D.band[(g * nchunks + c) * 4 + 1];
           const int tlo = max(blo, t0), thi = min(bhi, t0 + kFoldTCH);
-          const double* vrow = vs + (size_t)g * kFoldTCH * kFoldTPX + 2 * pp;
-          const double* prow = pdf_s + (size_t)g * nT * nRp + 8 * c;
+          const double* vrow = vs + 2 * pp;
+          const double* prow = pdf_s + 8 * c;
           for (int t = tlo; t < thi; ++t) {
             const double2 v = *reinterpret_cast<const double2*>(vrow + (size_t)(t - t0) * kFoldTPX);
             const double2 m0 = *reinterpret_cast<const double2*>(prow + (size_t)t * nRp);
@@ -814,6 +842,7 @@ __global__ void __launch_bounds__(kFoldThreads, GPY_FOLD_MINBLOCKS) fold_cash_ge
         }
       }
       __syncthreads();
+    }
     }
 
     // ---- epilogue for reco chunk c: background, clip, Cash ----

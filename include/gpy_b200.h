@@ -156,7 +156,9 @@ int gpy_dataset_source_state(const gpy_dataset_t* ds, int32_t source, gpy_source
  *     (irf/psf/core.py:39-87), per-plane cut and <= 4 x oversampling (irf/psf/map.py:23-37), block sum, plane
  *     normalisation (irf/psf/kernel.py:70-80) -- profile and radii on the host, the kernel images on the device;
  *   - EDispKernelMap.get_edisp_kernel(position) (irf/edisp/map.py:369-401): the matrix of the nearest IRF pixel.
- *     The sources of one dataset may use at most 4 different matrices at a time (GPY_ERR_UNSUPPORTED beyond).
+ *     Any number of matrices per dataset (one per source in the limit); the staged fold kernels serve launches whose
+ *     matrices fit their shared memory (one for the 64-pixel kernel, two or three for the 128-pixel one), beyond that
+ *     the any-shape kernel runs, which works through the matrices of each tile's own sources one at a time.
  * psf_map / edisp_map are HOST arrays, copied.  The psf_kernel / edisp of gpy_dataset_desc are then unused for the
  * respective IRF (edisp_diagonal still serves apply_irf["edisp"] = False).  A batched call (n_vec > 1) whose vector
  * would trigger such a lookup fails with GPY_ERR_UNSUPPORTED: evaluate that point as a single vector first. */

@@ -167,3 +167,40 @@ def test_irf_lookup_off_the_equator(ctx, proj, skydir):
     assert abs(ds.stat_sum() - de.stat_sum()) < 1e-3
     assert ds.evaluator_irf("point", False)["edisp_pixel"] == ds.evaluator_irf("gauss", False)["edisp_pixel"] or \
         ds.evaluator_irf("point", False)["k"] == ds.evaluator_irf("gauss", False)["k"]
+
+
+@pytest.mark.parametrize("n_reco,n_true", [(6, 12), (30, 60)])
+def test_every_source_with_its_own_edisp_matrix(ctx, n_reco, n_true):
+    """IRF maps that vary from IRF pixel to IRF pixel (graded_irfs: what MapDatasetMaker fills for a real observation):
+    nine sources, nine PSF kernels, as many edisp matrices as the sources occupy IRF pixels -- more than any staged fold
+    kernel holds, so the any-shape kernel runs and works through the matrices of each tile's own sources one at a time.
+    npred per bin, the statistic, a moved source and a batched scan against the oracle."""
+    from gammapy_b200 import Map, configs
+    from oracle import adapter
+
+    ds = configs.make_c3(width=(6.0, 3.0), n_sources=9, n_reco=n_reco, n_true=n_true)
+    configs.graded_irfs(ds)
+    de = adapter.evaluator_for(ds, conv="exact64")
+    _check(ds, de)
+    names = [m.name for m in ds.models if getattr(m, "spatial_model", None) is not None]
+    pixels = {ds.evaluator_irf(n, False)["edisp_pixel"] for n in names}
+    assert len(pixels) >= 6, pixels
+    ds.counts = Map.from_geom(ds._geom, data=de.fake(3), dtype=float)
+    want = de.stat_sum()
+    assert abs(ds.stat_sum() - want) < 1e-3
+    # a spectral step (steady state) and a source that moves into another IRF pixel
+    ds.models[names[0]].spectral_model.parameters["amplitude"].value *= 1.3
+    adapter.refresh_models(de, ds)
+    assert abs(ds.stat_sum() - de.stat_sum()) < 1e-3
+    ds.models[names[1]].spatial_model.lon_0.value += 0.6
+    adapter.refresh_models(de, ds)
+    assert abs(ds.stat_sum() - de.stat_sum()) < 1e-3
+    for n in names:  # the same evaluators looked their IRFs up again on both sides (the drift rule of MapEvaluator.update)
+        assert ds.evaluator_irf(n, False)["n_updates"] == de.evaluators[n].n_irf_updates, n
+    # batched scan from this state: vector 0 is the single evaluation, the others move a spectral parameter
+    eng = ds._get_engine()
+    grid = np.tile(eng.values(), (3, 1))
+    col = [i for i, p in enumerate(eng.parameters) if p.name in ("index", "alpha")][0]
+    grid[:, col] += [0.0, 0.05, 0.1]
+    scan = eng.stat_sum(grid)
+    assert abs(scan[0] - de.stat_sum()) < 1e-3 and scan[1] != scan[0] and scan[2] != scan[1]
