@@ -10,6 +10,8 @@ import numpy as np
 
 import os
 
+from .modeling.parameter import bind_mirror, release_mirror
+
 __all__ = ["partition", "allreduce_stat", "ShardedDatasets", "PeerReduce"]
 
 PEER_REDUCE_CAPACITY = 1024  # parameter vectors per evaluation the NVLink one-shot reduce is sized for
@@ -124,9 +126,16 @@ class _JointEngine:
                     self.parameters.append(par)
         self.n_par = len(self.parameters)
         self._local_cols = None
+        self._vec = bind_mirror(self.parameters)
 
     def values(self):
-        return np.array([p._value for p in self.parameters], dtype=float)
+        return self._vec.copy()
+
+    def __del__(self):
+        try:
+            release_mirror(self.parameters, self._vec)
+        except Exception:
+            pass
 
     def local_columns(self):
         """Global column of every local parameter-vector column."""

@@ -9,6 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
+from .modeling.parameter import bind_mirror, release_mirror
 from .modeling.models import (DiskSpatialModel, ExpCutoffPowerLawSpectralModel, FoVBackgroundModel,
                               GaussianSpatialModel, LogParabolaSpectralModel, PointSpatialModel,
                               PowerLawSpectralModel, SkyModel, integration_nodes)
@@ -240,6 +241,10 @@ class LikelihoodEngine:
                         self._col[id(par)] = len(self.parameters)
                         self.parameters.append(par)
         self.n_par = max(len(self.parameters), 1)
+        self._vec = bind_mirror(self.parameters)  # kept equal to the parameter values by their setters
+        self._vec_ptr = _ptr(self._vec)
+        self._stat1 = np.empty(1, dtype=float)
+        self._stat1_ptr = _ptr(self._stat1)
         for ds in self.datasets:
             dev = ds._device_dataset(self.ctx)
             self._set_models(ds, dev)
@@ -301,10 +306,23 @@ class LikelihoodEngine:
         """Current parameter values as the [n_par] vector."""
         if not self.parameters:
             return np.zeros(self.n_par, dtype=float)
-        return np.array([par._value for par in self.parameters], dtype=float)
+        return self._vec.copy()
+
+    def __del__(self):
+        try:
+            release_mirror(self.parameters, self._vec)
+        except Exception:
+            pass
 
     def stat_sum(self, values=None, per_dataset=False):
         """Datasets.stat_sum for one ([n_par]) or many ([B, n_par]) parameter vectors."""
+        if values is None and not per_dataset and self.parameters:
+            # the step of a fit: the bound vector goes out as it is (the library copies it before it returns), the
+            # result comes back into a one-element array kept for the purpose
+            self._claim()
+            _lib.check(self.ctx.lib.gpy_stat_sum(self.ctx.handle, self._handles, len(self.datasets), self._vec_ptr, 1,
+                                                 self.n_par, self._stat1_ptr, None))
+            return float(self._stat1[0])
         if values is None:
             values = self.values()
         values = np.ascontiguousarray(values, dtype=float)

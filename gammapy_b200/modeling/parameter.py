@@ -26,8 +26,33 @@ def _scale_fn(name):
     raise ValueError(f"Not a valid value scaling mode: '{name}'.")
 
 
+def bind_mirror(parameters):
+    """A float64 vector that the ``value`` / ``factor`` setters of ``parameters`` keep equal to the parameter values from
+    now on: a likelihood engine reads its parameter vector from it instead of walking hundreds of Parameter objects on
+    every evaluation of a fit (16 us of a 300 us step at 415 parameters)."""
+    vec = np.array([p._value for p in parameters], dtype=float)
+    for i, p in enumerate(parameters):
+        p._mirrors = p._mirrors + ((vec, i),)
+    return vec
+
+
+def release_mirror(parameters, vec):
+    for p in parameters:
+        p._mirrors = tuple(m for m in p._mirrors if m[0] is not vec)
+
+
 class Parameter:
     """A model parameter (modeling/parameter.py:40-600)."""
+
+    _mirrors = ()  # (vector, index) pairs of the engines this parameter is bound to (bind_mirror)
+
+    def __getstate__(self):  # copies and pickles are not bound to anybody's vector
+        state = dict(self.__dict__)
+        state.pop("_mirrors", None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
 
     def __init__(self, name, value, unit="", scale=1, min=np.nan, max=np.nan, frozen=False, error=0,
                  scan_min=None, scan_max=None, scan_n_values=11, scan_n_sigma=2, scan_values=None,
@@ -112,8 +137,13 @@ class Parameter:
 
     @value.setter
     def value(self, val):
-        self._value = float(val)
-        self._factor = self.transform(val)
+        # the reference computes the factor here (parameter.py:229-233); it is computed when first read instead, with the
+        # same scale (the scale only changes through autoscale / reset_autoscale, which set the factor themselves): an
+        # optimiser step writes hundreds of values whose factors nobody reads
+        self._value = v = float(val)
+        self._factor = None
+        for vec, i in self._mirrors:
+            vec[i] = v
 
     @property
     def quantity(self):
@@ -125,12 +155,17 @@ class Parameter:
 
     @property
     def factor(self):
-        return self._factor
+        f = self._factor
+        if f is None:
+            f = self._factor = self.transform(self._value)
+        return f
 
     @factor.setter
     def factor(self, val):
         self._factor = float(val)
-        self._value = float(self.inverse_transform(self._factor))
+        self._value = v = float(self.inverse_transform(self._factor))
+        for vec, i in self._mirrors:
+            vec[i] = v
 
     @property
     def scale(self):

@@ -209,3 +209,38 @@ def test_units_are_converted_or_refused_and_boolean_masks_select():
     assert pars[[0, 2]].names == ["a", "c"]
     with pytest.raises(IndexError):
         pars[np.array([True, False])]
+
+
+def test_parameter_lazy_factor_and_engine_mirror():
+    """The value setter leaves the factor to be computed when first read (same scale as the reference's eager
+    computation, modeling/parameter.py:229-233) and keeps the vectors of the engines the parameter is bound to equal to
+    the value; copies and pickles of a bound parameter are bound to nobody."""
+    import copy
+    import pickle
+
+    from gammapy_b200.modeling.parameter import bind_mirror, release_mirror
+
+    p = Parameter("amplitude", "3e-12 cm-2 s-1 TeV-1")
+    q = Parameter("index", 2.0)
+    vec = bind_mirror([p, q])
+    other = bind_mirror([q])
+    assert vec.tolist() == [3e-12, 2.0] and other.tolist() == [2.0]
+    p.value = 5e-12
+    q.value = 2.5
+    assert vec.tolist() == [5e-12, 2.5] and other.tolist() == [2.5]
+    assert p.factor == 5e-12 and p.scale == 1.0
+    p.autoscale()  # scale10: factor in [1, 10), value unchanged
+    assert p.scale == 1e-12 and p.factor == pytest.approx(5.0) and p.value == 5e-12 == vec[0]
+    p.value = 7e-12  # factor follows with the scale it has now
+    assert p.factor == pytest.approx(7.0)
+    p.factor = 2.0
+    assert p.value == pytest.approx(2e-12) and vec[0] == p.value
+    p.reset_autoscale()
+    assert p.scale == 1.0 and p.factor == p.value
+    for clone in (copy.copy(p), copy.deepcopy(p), pickle.loads(pickle.dumps(p))):
+        assert clone._mirrors == () and clone.value == p.value and clone.factor == p.factor
+        clone.value = 1.0
+        assert vec[0] == p.value != 1.0
+    release_mirror([p, q], vec)
+    q.value = 3.0
+    assert vec[1] == 2.5 and other[0] == 3.0 and p._mirrors == ()
