@@ -11,8 +11,9 @@ set -e
   python profiles/ncu_sass.py gpurun_out/fold_r02.ncu-rep 16
 ) > profiles/r02_fold_ncu_summary.txt
 (
-  echo "# ncu --set full --clock-control none --import-source on, psf_conv_kernel (K2) as shipped in round 2: one source of C3 (cutout ~ 150 x 150 px, 60 planes,"
-  echo "# kernel half widths 33 .. 11 px), command: python bench.py --steps 3 --warmup 3 --no-extras --no-cpu-baseline, 21st launch (profiles/capture_r02.sh)"
+  echo "# ncu --set full --clock-control none --import-source on, psf_conv_batch_kernel (K2) as shipped at the end of round 2: the PSF stencil of all 50 sources"
+  echo "# of C3 in one launch (cutouts ~ 150 x 150 px, 60 planes each, kernel half widths 33 .. 11 px), command: python bench.py --steps 3 --warmup 3"
+  echo "# --no-extras --no-cpu-baseline, first launch (profiles/capture_r02.sh)"
   python profiles/ncu_summary.py gpurun_out/psf_r02.ncu-rep
   python profiles/ncu_lines.py gpurun_out/psf_r02.ncu-rep 12
 ) > profiles/r02_psf_conv_ncu_summary.txt
