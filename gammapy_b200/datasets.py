@@ -344,6 +344,10 @@ class MapDataset:
 
         return cls.from_hdulist(fitsio.read_hdus(str(filename)), name=name)
 
+    def to_dict(self):
+        """Entry of the datasets index file (datasets/core.py:67-71)."""
+        return {"name": self.name, "type": self.tag, "filename": self.name.replace(" ", "_") + ".fits"}
+
     def evaluator_irf(self, model_name, with_kernel=True):
         """IRFs one model's evaluator looked up at its position (datasets with a PSFMap / EDispKernelMap on a spatial
         grid; MapEvaluator.update, datasets/evaluator.py:196-227): dict with the PSF kernel ``(nT, K, K)``, its side
@@ -532,6 +536,58 @@ class Datasets(list):
     @property
     def parameters(self):
         return self.models.parameters.unique_parameters
+
+    def write(self, filename, filename_models=None, overwrite=False):
+        """``Datasets.write`` (datasets/core.py:479-528): a YAML index ``{datasets: [{name, type, filename}]}``, one FITS
+        file per dataset next to it and, when asked for, the models YAML (``Models.write``)."""
+        import os
+
+        import yaml
+
+        from .modeling.io import YAML_FORMAT
+
+        path = str(filename)
+        folder = os.path.dirname(os.path.abspath(path))
+        os.makedirs(folder, exist_ok=True)
+        if os.path.exists(path) and not overwrite:
+            raise OSError(f"File exists already: {path}")
+        entries = []
+        for d in self:
+            entry = d.to_dict()
+            d.write(os.path.join(folder, entry["filename"]), overwrite=overwrite)
+            entries.append(entry)
+        with open(path, "w") as fh:
+            fh.write(yaml.safe_dump({"datasets": entries}, **YAML_FORMAT))
+        if filename_models:
+            self.models.write(filename_models, overwrite=overwrite)
+
+    @classmethod
+    def read(cls, filename, filename_models=None):
+        """``Datasets.read`` (datasets/core.py:435-477): the datasets of a YAML index (file names relative to it) and,
+        when given, their models (``datasets.models = Models.read(...)``: every dataset picks the models that name it
+        or name no dataset)."""
+        import os
+
+        import yaml
+
+        path = str(filename)
+        with open(path) as fh:
+            index = yaml.safe_load(fh.read())
+        folder = os.path.dirname(os.path.abspath(path))
+        kinds = {MapDataset.tag: MapDataset, MapDatasetOnOff.tag: MapDatasetOnOff}
+        datasets = []
+        for entry in index["datasets"]:
+            if entry["type"] not in kinds:
+                raise NotImplementedError(f"dataset type {entry['type']!r} is outside the accelerated path "
+                                          f"(available: {sorted(kinds)})")
+            fname = entry["filename"]
+            if os.path.exists(os.path.join(folder, fname)):
+                fname = os.path.join(folder, fname)
+            datasets.append(kinds[entry["type"]].read(fname, name=entry["name"]))
+        out = cls(datasets)
+        if filename_models:
+            out.models = Models.read(filename_models)
+        return out
 
     def _get_engine(self):
         from .engine import LikelihoodEngine

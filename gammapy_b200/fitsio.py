@@ -379,6 +379,10 @@ def dataset_to_hdus(ds):
         m = getattr(ds, attr)
         if m is not None:
             hdus += map_to_hdus(m, attr)
+    for attr in ("counts_off", "acceptance", "acceptance_off"):  # MapDatasetOnOff.to_hdulist (datasets/map.py:3038-3075)
+        m = getattr(ds, attr, None)
+        if m is not None:
+            hdus += map_to_hdus(m, attr)
     geom = ds._geom.to_image()
     if ds.edisp is not None:
         ed = ds.edisp
@@ -437,4 +441,12 @@ def dataset_from_hdus(hdus, name=None):
             m = map_from_hdus(hdus, attr)
             m.data = m.data.astype(bool)
             kwargs[attr] = m
+    if "COUNTS_OFF" in names or "ACCEPTANCE" in names:  # MapDatasetOnOff.from_hdulist (datasets/map.py:3077-3160)
+        from .datasets import MapDatasetOnOff
+
+        for attr in ("counts_off", "acceptance", "acceptance_off"):
+            if attr.upper() in names:
+                kwargs[attr] = map_from_hdus(hdus, attr)
+        kwargs.pop("background", None)
+        return MapDatasetOnOff(**kwargs)
     return MapDataset(**kwargs)

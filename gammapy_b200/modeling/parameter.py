@@ -45,6 +45,7 @@ class Parameter:
     """A model parameter (modeling/parameter.py:40-600)."""
 
     _mirrors = ()  # (vector, index) pairs of the engines this parameter is bound to (bind_mirror)
+    _link_label_io = None  # serialisation label of a parameter shared between models (modeling/io.py)
 
     def __getstate__(self):  # copies and pickles are not bound to anybody's vector
         state = dict(self.__dict__)
