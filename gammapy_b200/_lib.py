@@ -16,11 +16,26 @@ class GeomDesc(C.Structure):
     _fields_ = [
         ("nx", C.c_int32), ("ny", C.c_int32), ("n_true", C.c_int32), ("n_reco", C.c_int32),
         ("binsz", C.c_double), ("crval_lon", C.c_double), ("crpix_x", C.c_double), ("crpix_y", C.c_double),
-        ("crval_lat", C.c_double), ("proj", C.c_int32), ("pad_", C.c_int32),
+        ("crval_lat", C.c_double), ("proj", C.c_int32), ("frame", C.c_int32),
     ]
 
 
 PROJECTIONS = {"CAR": 0, "TAN": 1}
+FRAMES = {"galactic": 0, "icrs": 1}
+
+
+def frame_code(frame):
+    try:
+        return FRAMES[frame]
+    except KeyError:
+        raise NotImplementedError(f"celestial frame {frame!r} (implemented: {sorted(FRAMES)})") from None
+
+
+def geom_desc(geom, n_true=1, n_reco=1):
+    """``gpy_geom_desc`` of a WcsGeom."""
+    g = geom.to_image() if len(geom.axes) else geom
+    return GeomDesc(g.npix[0], g.npix[1], n_true, n_reco, g.binsz, g.crval[0], g.crpix[0], g.crpix[1], g.crval[1],
+                    PROJECTIONS[g.projection], frame_code(g.frame))
 
 
 class DatasetDesc(C.Structure):
@@ -49,7 +64,7 @@ class SourceDesc(C.Structure):
     _fields_ = [
         ("spatial_type", C.c_int32), ("spectral_type", C.c_int32),
         ("spatial_par", C.c_int32 * 6), ("spectral_par", C.c_int32 * 5),
-        ("apply_psf", C.c_int32), ("apply_edisp", C.c_int32),
+        ("apply_psf", C.c_int32), ("apply_edisp", C.c_int32), ("frame", C.c_int32),
     ]
 
 
@@ -102,7 +117,7 @@ SYMBOLS = {
     "gpy_cash_sum": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "gpy_weighted_cash_sum": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     "gpy_wstat_sum_device": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, C.c_int64, _P, _P]),
-    "gpy_integrate_geom": (C.c_int, [_P, C.POINTER(GeomDesc), C.c_int32, _P, _P, C.POINTER(C.c_int32)]),
+    "gpy_integrate_geom": (C.c_int, [_P, C.POINTER(GeomDesc), C.c_int32, C.c_int32, _P, _P, C.POINTER(C.c_int32)]),
     "gpy_psf_convolve": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, _P]),
     "gpy_spectral_integral": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, _P]),
     "gpy_solid_angle": (C.c_int, [_P, C.POINTER(GeomDesc), _P]),
@@ -132,7 +147,7 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.gpy_abi_version() != 1:
+    if lib.gpy_abi_version() != 2:
         raise GpyError("libgpy_b200.so ABI version mismatch")
     _LIB = lib
     return lib

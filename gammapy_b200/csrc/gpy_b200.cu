@@ -69,12 +69,74 @@ struct GeomH {
   double binsz, crval_lon, crpix_x, crpix_y;
   double crval_lat = 0.0;
   int proj = 0;  // gpy_projection: 0 CAR, 1 TAN, both about (crval_lon, crval_lat)
+  int frame = 0;  // gpy_frame of the world coordinates
 };
 GeomH geom_from_desc(const gpy_geom_desc& g) {
   GeomH h{g.nx, g.ny, g.binsz, g.crval_lon, g.crpix_x, g.crpix_y};
   h.crval_lat = g.crval_lat;
   h.proj = g.proj;
+  h.frame = g.frame;
   return h;
+}
+
+// ---- celestial frames: ICRS <-> Galactic as astropy defines it (see gpy_frame in the header) -------------------
+struct FrameRotation {
+  double icrs_to_gal[9];
+  FrameRotation() {
+    auto rot = [](double deg, char axis, double m[9]) {  // astropy rotation_matrix: passive rotation about an axis
+      const double a = deg * M_PI / 180.0, c = std::cos(a), s = std::sin(a);
+      const double x[9] = {1, 0, 0, 0, c, s, 0, -s, c}, y[9] = {c, 0, -s, 0, 1, 0, s, 0, c}, z[9] = {c, s, 0, -s, c, 0, 0, 0, 1};
+      std::memcpy(m, axis == 'x' ? x : axis == 'y' ? y : z, sizeof(x));
+    };
+    auto mul = [](const double a[9], const double b[9], double out[9]) {
+      double t[9];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) t[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+      std::memcpy(out, t, sizeof(t));
+    };
+    double a[9], b[9], bias[9], gal[9];
+    // ICRS -> FK5 (J2000): frame bias of USNO circular 179, eta0 = -19.9 mas, xi0 = 9.1 mas, da0 = -22.9 mas
+    rot(19.9 / 3600000.0, 'x', a);
+    rot(9.1 / 3600000.0, 'y', b);
+    mul(a, b, bias);
+    rot(-22.9 / 3600000.0, 'z', b);
+    mul(bias, b, bias);
+    // FK5 (J2000) -> Galactic: north galactic pole (192.8594812065348, 27.12825118085622) deg, lon0 122.9319185680026 deg
+    rot(180.0 - 122.9319185680026, 'z', a);
+    rot(90.0 - 27.12825118085622, 'y', b);
+    mul(a, b, gal);
+    rot(192.8594812065348, 'z', b);
+    mul(gal, b, gal);
+    mul(gal, bias, icrs_to_gal);
+  }
+};
+const FrameRotation kFrames;
+
+bool valid_frame(int f) { return f == GPY_FRAME_GALACTIC || f == GPY_FRAME_ICRS; }
+
+// Matrix taking unit vectors of frame `from` to frame `to` (row major); false when the frames are the same.
+bool frame_matrix(int from, int to, double m[9]) {
+  if (from == to) return false;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      m[3 * i + j] = from == GPY_FRAME_ICRS ? kFrames.icrs_to_gal[3 * i + j] : kFrames.icrs_to_gal[3 * j + i];
+  return true;
+}
+
+// (lon, lat) in deg of frame `from` expressed in frame `to`.
+void frame_convert(int from, int to, double lon, double lat, double& lon_out, double& lat_out) {
+  double m[9];
+  if (!frame_matrix(from, to, m)) {
+    lon_out = lon;
+    lat_out = lat;
+    return;
+  }
+  const double lo = lon * M_PI / 180.0, la = lat * M_PI / 180.0;
+  const double x = std::cos(la) * std::cos(lo), y = std::cos(la) * std::sin(lo), z = std::sin(la);
+  const double x2 = m[0] * x + m[1] * y + m[2] * z, y2 = m[3] * x + m[4] * y + m[5] * z, z2 = m[6] * x + m[7] * y + m[8] * z;
+  lon_out = std::atan2(y2, x2) * 180.0 / M_PI;
+  if (lon_out < 0) lon_out += 360.0;
+  lat_out = std::atan2(z2, std::hypot(x2, y2)) * 180.0 / M_PI;
 }
 
 struct Rect {
@@ -457,7 +519,8 @@ gpy::WcsDev wcs_of(const GeomH& g) { return gpy::WcsDev{g.crval_lon, g.binsz, g.
 // rows_out[2] (optional): the rows [r0, r1) of the cutout outside of which the image is exactly zero.
 int compute_spatial(gpy_context* c, const GeomH& pg, const double* omega, const Rect& rect, int type,
                     const double* sp, float* w_out, int pitch, int xpad, int* f_out, int* rows_out = nullptr,
-                    gpy::SpatialJob* job_out = nullptr) {  // job_out: describe the work instead of launching it
+                    gpy::SpatialJob* job_out = nullptr,  // job_out: describe the work instead of launching it
+                    int model_frame = -1) {              // gpy_frame of sp (lon_0, lat_0, phi); -1: the map's
   GeomH eg = sub_geom(pg, rect);
   gpy::SpatialJob j;
   std::memset(&j, 0, sizeof(j));
@@ -474,9 +537,16 @@ int compute_spatial(gpy_context* c, const GeomH& pg, const double* omega, const 
   j.out = w_out;
   j.lon0 = sp[0] * kDegH;
   j.lat0 = sp[1] * kDegH;
+  // the position in the map's frame (pixel arithmetic: skycoord_to_pixel) and, for a model in another frame, the
+  // rotation that takes map coordinates to the model's
+  double mlon = sp[0], mlat = sp[1];
+  if (model_frame >= 0 && model_frame != pg.frame) {
+    frame_convert(model_frame, pg.frame, sp[0], sp[1], mlon, mlat);
+    j.rotate = frame_matrix(pg.frame, model_frame, j.rot) ? 1 : 0;
+  }
   int f = 1;
   if (type == GPY_SPATIAL_POINT) {
-    world_to_pix(eg, sp[0], sp[1], j.px0, j.py0);
+    world_to_pix(eg, mlon, mlat, j.px0, j.py0);
   } else {
     const double pix_scale = pg.binsz;
     const double radius = evaluation_radius(type, sp);
@@ -484,7 +554,7 @@ int compute_spatial(gpy_context* c, const GeomH& pg, const double* omega, const 
     Rect inner;
     // try: wcs_geom.cutout(position, 2 * max(r_eval, pix_scale)) (spatial.py:255-264)
     double width = 2 * (radius > pix_scale || std::isnan(radius) ? radius : pix_scale);  // np.maximum
-    CutStatus cs = cutout_rect(eg, sp[0], sp[1], width, false, inner);
+    CutStatus cs = cutout_rect(eg, mlon, mlat, width, false, inner);
     if (cs != CUT_OK) {
       f = 1;
       have_f = true;
@@ -903,7 +973,9 @@ int evaluator_update(const gpy_dataset* ds, const Source& src, const double* sp,
   const double cutout_width = psf_width + 2 * (radius + kCutoutMargin);  // evaluator.py:169-172
   // SkyModel.contributes(mask, margin=psf_width) (cube.py:246-286)
   Rect mrect;
-  CutStatus cs = cutout_rect(ds->geom, sp[0], sp[1], 2 * radius + kCutoutMargin + psf_width, false, mrect);
+  double mlon, mlat;  // model.position in the map's frame
+  frame_convert(src.desc.frame, ds->geom.frame, sp[0], sp[1], mlon, mlat);
+  CutStatus cs = cutout_rect(ds->geom, mlon, mlat, 2 * radius + kCutoutMargin + psf_width, false, mrect);
   contributes = false;
   if (cs == CUT_OK) {
     if (ds->mask_image.empty()) {
@@ -920,7 +992,7 @@ int evaluator_update(const gpy_dataset* ds, const Source& src, const double* sp,
     }
   }
   if (!contributes) return GPY_OK;
-  cs = cutout_rect(ds->geom, sp[0], sp[1], cutout_width, true, rect);
+  cs = cutout_rect(ds->geom, mlon, mlat, cutout_width, true, rect);
   if (cs == CUT_VALUE_ERROR)
     return fail(GPY_ERR_INVALID, "non-finite source position / size in MapEvaluator.update (Cutout2D raises ValueError)");
   if (cs == CUT_NO_OVERLAP)
@@ -969,7 +1041,7 @@ int get_slot(gpy_dataset* ds, Source& src, const double* sp, const Rect& rect, u
     gpy_context::PendingSpatial ps;
     std::memset(&ps.job, 0, sizeof(ps.job));
     GPY_TRY(compute_spatial(c, ds->geom, (const double*)ds->d_omega.p, rect, src.desc.spatial_type, sp,
-                            (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f, wrows, &ps.job.j));
+                            (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f, wrows, &ps.job.j, src.desc.frame));
     ps.oversample = src.desc.spatial_type != GPY_SPATIAL_POINT && s.f > 1;
     ps.job.fill_gx = (s.pitch + 127) / 128;
     ps.conv_smem = 0;
@@ -992,7 +1064,7 @@ int get_slot(gpy_dataset* ds, Source& src, const double* sp, const Rect& rect, u
     c->pending.push_back(ps);
   } else {
   GPY_TRY(compute_spatial(c, ds->geom, (const double*)ds->d_omega.p, rect, src.desc.spatial_type, sp,
-                          (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f, wrows));
+                          (float*)s.w.p, s.pitch, rect.x0 - s.x0a, &s.f, wrows, nullptr, src.desc.frame));
   if (conv) {
     if (ds->irf.has_psf)
       GPY_TRY(launch_conv(c, (const float*)s.w.p, rect.cy, rect.cx, s.pitch, rect.x0 - s.x0a,
@@ -1264,9 +1336,11 @@ int evaluate_impl(gpy_context* c, const EvalRequest& rq) {
                             "a vector of a batched call moves a source beyond its IRF support (MapEvaluator.update): "
                             "evaluate that point as a single vector first");
             } else {
-              if (ds->irf.has_edisp) src.edisp_pix = edisp_pixel_at(ds->irf, sp[0], sp[1]);
+              double mlon, mlat;  // the IRF maps live in the dataset's frame
+              frame_convert(src.desc.frame, ds->geom.frame, sp[0], sp[1], mlon, mlat);
+              if (ds->irf.has_edisp) src.edisp_pix = edisp_pixel_at(ds->irf, mlon, mlat);
               if (ds->irf.has_psf) {  // (whatever apply_irf says: update() looks the kernel up, the width uses it)
-                GPY_TRY(extract_psf(ds, src, sp[0], sp[1]));
+                GPY_TRY(extract_psf(ds, src, mlon, mlat));
                 for (auto& sl : src.slots) sl.valid = false;  // convolved with the previous kernel
                 ds->version = ++c->stamp;
               } else {
@@ -2002,6 +2076,7 @@ int gpy_dataset_create(gpy_context_t* c, const gpy_dataset_desc* desc, gpy_datas
   *out = nullptr;
   const gpy_geom_desc& g = desc->geom;
   if (g.proj != 0 && g.proj != 1) return fail(GPY_ERR_UNSUPPORTED, "projection code %d (0 CAR, 1 TAN)", g.proj);
+  if (!valid_frame(g.frame)) return fail(GPY_ERR_UNSUPPORTED, "celestial frame code %d (0 galactic, 1 icrs)", g.frame);
   if (g.proj == 0 && !(g.crval_lat > -90.0 && g.crval_lat < 90.0))
     return fail(GPY_ERR_INVALID, "CAR: reference latitude %g outside (-90, 90) deg", g.crval_lat);
   if (g.nx <= 0 || g.ny <= 0 || g.n_true <= 0 || g.n_reco <= 0 || !(g.binsz > 0))
@@ -2117,6 +2192,8 @@ int gpy_dataset_set_models(gpy_dataset_t* ds, const gpy_source_desc* sources, in
       return fail(GPY_ERR_UNSUPPORTED, "source %d: unsupported spatial model type %d", i, sources[i].spatial_type);
     if (sources[i].spectral_type < 0 || sources[i].spectral_type > 2)
       return fail(GPY_ERR_UNSUPPORTED, "source %d: unsupported spectral model type %d", i, sources[i].spectral_type);
+    if (!valid_frame(sources[i].frame))
+      return fail(GPY_ERR_UNSUPPORTED, "source %d: celestial frame code %d (0 galactic, 1 icrs)", i, sources[i].frame);
   }
   cudaSetDevice(ds->ctx->device);
   cudaStreamSynchronize(ds->ctx->stream);
@@ -2498,9 +2575,10 @@ int gpy_solid_angle(gpy_context_t* c, const gpy_geom_desc* g, double* out) {
   return GPY_OK;
 }
 
-int gpy_integrate_geom(gpy_context_t* c, const gpy_geom_desc* g, int32_t spatial_type, const double* sp, float* out,
-                       int32_t* oversampling) {
+int gpy_integrate_geom(gpy_context_t* c, const gpy_geom_desc* g, int32_t spatial_type, int32_t model_frame,
+                       const double* sp, float* out, int32_t* oversampling) {
   if (!c || !g || !sp || !out) return fail(GPY_ERR_INVALID, "NULL argument to gpy_integrate_geom");
+  if (!valid_frame(g->frame) || !valid_frame(model_frame)) return fail(GPY_ERR_UNSUPPORTED, "celestial frame code (0 galactic, 1 icrs)");
   if (spatial_type < 0 || spatial_type > 2) return fail(GPY_ERR_UNSUPPORTED, "unsupported spatial model type %d", spatial_type);
   CUDA_TRY(cudaSetDevice(c->device));
   const size_t P = (size_t)g->nx * g->ny;
@@ -2518,7 +2596,7 @@ int gpy_integrate_geom(gpy_context_t* c, const gpy_geom_desc* g, int32_t spatial
   full.cy = g->ny;
   int f = 0;
   GPY_TRY(compute_spatial(c, gh, (const double*)c->scratch_a.p, full, spatial_type, sp, (float*)c->scratch_b.p, pitch, 0,
-                          &f));
+                          &f, nullptr, nullptr, model_frame));
   if (oversampling) *oversampling = f;
   CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)g->nx * sizeof(float), c->scratch_b.p, (size_t)pitch * sizeof(float),
                              (size_t)g->nx * sizeof(float), g->ny, cudaMemcpyDeviceToHost, c->stream));

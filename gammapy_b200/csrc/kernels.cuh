@@ -157,7 +157,25 @@ struct SpatialJob {
   double px0, py0;     // point source: position in evaluator pixel coordinates
   const double* solid_angle;  // parent [ny, nx] sr
   float* out;          // [ecy, pitch]
+  // The model's frame differs from the map's (SpatialModel.evaluate_geom: geom.get_coord(frame=self.frame),
+  // spatial.py:196-220): pixel coordinates are rotated into the model frame before the model is evaluated, so
+  // lon0 / lat0 / phi keep their meaning.  rot = map frame -> model frame, row major.
+  int rotate, pad2_;
+  double rot[9];
 };
+
+__device__ __forceinline__ void to_model_frame(const SpatialJob& j, double& lon_deg, double& lat_deg) {
+  if (!j.rotate) return;
+  double sl, cl, sb, cb;
+  sincos(lon_deg * kDeg, &sl, &cl);
+  sincos(lat_deg * kDeg, &sb, &cb);
+  const double x = cb * cl, y = cb * sl, z = sb;
+  const double x2 = j.rot[0] * x + j.rot[1] * y + j.rot[2] * z;
+  const double y2 = j.rot[3] * x + j.rot[4] * y + j.rot[5] * z;
+  const double z2 = j.rot[6] * x + j.rot[7] * y + j.rot[8] * z;
+  lon_deg = atan2(y2, x2) / kDeg;
+  lat_deg = atan2(z2, hypot(x2, y2)) / kDeg;
+}
 
 __device__ __forceinline__ double sigma_eff_dev(const SpatialJob& j, double lon, double lat) {
   // compute_sigma_eff (spatial.py:57-67)
@@ -204,6 +222,7 @@ __device__ __forceinline__ void spatial_fill_body(const SpatialJob& j, int bx, i
     } else if (j.f == 1) {
       double lon, lat;
       pix_to_world_deg(j.wcs_e, (double)x, (double)y, lon, lat);
+      to_model_frame(j, lon, lat);
       double g = eval_spatial(j, lon, lat);
       double omega = j.solid_angle[(size_t)(j.ey0 + y) * j.parent_nx + (j.ex0 + x)];
       v = (float)(g * omega);  // float64 result, cast at the convolution input (ndmap.py:984)
@@ -226,6 +245,7 @@ __device__ __forceinline__ void spatial_oversample_body(const SpatialJob& j, int
     int sx = k % f, sy = k / f;
     double lon, lat;
     pix_to_world_deg(j.wcs_up, (double)(ix * f + sx), (double)(iy * f + sy), lon, lat);
+    to_model_frame(j, lon, lat);
     double g = eval_spatial(j, lon, lat);
     // numpy: evaluate(...) / f**2 is a true division per element
     g = __ddiv_rn(g, (double)ff);

@@ -77,8 +77,7 @@ class DeviceDataset:
             raise ValueError("MapDataset geometry without a frame")
         e_true = ds.exposure.geom.axes["energy_true"]
         e_reco = geom.axes["energy"]
-        g = _lib.GeomDesc(geom.npix[0], geom.npix[1], e_true.nbin, e_reco.nbin, geom.binsz, geom.crval[0],
-                          geom.crpix[0], geom.crpix[1], geom.crval[1], _lib.PROJECTIONS[geom.projection], 0)
+        g = _lib.geom_desc(geom, e_true.nbin, e_reco.nbin)
         if ds.exposure.geom.to_image() != geom.to_image():
             raise NotImplementedError("exposure and counts must share the image geometry")
         desc = _lib.DatasetDesc()
@@ -265,10 +264,6 @@ class LikelihoodEngine:
                 continue
             if not isinstance(model, SkyModel):
                 raise NotImplementedError(f"{type(model).__name__} is outside the accelerated path")
-            if model.frame != ds._geom.frame:
-                raise NotImplementedError(
-                    f"model frame {model.frame!r} differs from the geometry frame {ds._geom.frame!r}: "
-                    "frame transforms are outside the accelerated path")
             if not model.apply_irf.get("exposure", True):
                 raise NotImplementedError("apply_irf['exposure']=False is outside the accelerated path")
             try:
@@ -284,6 +279,7 @@ class LikelihoodEngine:
                 d.spectral_par[k] = self._col[id(getattr(model.spectral_model, pnames[k]))] if k < len(pnames) else -1
             d.apply_psf = int(bool(model.apply_irf.get("psf", True)))
             d.apply_edisp = int(bool(model.apply_irf.get("edisp", True)))
+            d.frame = _lib.frame_code(model.frame)  # (a frame other than the map's: coordinates are rotated on the device)
             srcs.append(d)
             names.append(model.name)
         arr = (_lib.SourceDesc * max(len(srcs), 1))(*srcs)

@@ -347,6 +347,7 @@ class WcsGeom:
 
     def coord_to_pix(self, coords):
         if isinstance(coords, SkyCoord):
+            coords = coords.transform_to(self.frame)  # (wcs_utils.skycoord_to_pixel brings the position into the map frame)
             coords = (coords.lon, coords.lat)
         lon = np.asarray(coords[0], dtype=float)
         lat = np.asarray(coords[1], dtype=float)
@@ -414,7 +415,7 @@ class WcsGeom:
 
     def separation(self, center):
         """Angular separation [deg] of every pixel centre from ``center`` (maps/wcs/geom.py:868-884)."""
-        lon0, lat0 = as_lonlat(center)
+        lon0, lat0 = as_lonlat(center.transform_to(self.frame) if isinstance(center, SkyCoord) else center)
         c = self.to_image().get_coord()
         return angular_separation(c["lon"] * DEG, c["lat"] * DEG, lon0 * DEG, lat0 * DEG) / DEG
 
@@ -475,7 +476,7 @@ class WcsGeom:
         if odd_npix:
             width_npix = round_up_to_odd(width_npix)
         shape = (int(np.round(width_npix[1])), int(np.round(width_npix[0])))
-        lon, lat = as_lonlat(position)
+        lon, lat = as_lonlat(position.transform_to(self.frame) if isinstance(position, SkyCoord) else position)
         px, py = self.coord_to_pix((lon, lat))[:2]
         pos = (float(py), float(px))
         if not all(np.isfinite(pos)):

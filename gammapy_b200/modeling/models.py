@@ -210,21 +210,19 @@ class SpatialModel(ModelBase):
         """``SpatialModel.integrate_geom`` (spatial.py:222-309) on an image geometry, CUDA kernel K1.
 
         Returns the float32 image the PSF convolution consumes (ndmap.py:984)."""
-        from .._lib import Context, GeomDesc, check
+        from .._lib import Context, check, frame_code, geom_desc
         from ..maps import Map
 
         if oversampling_factor is not None:
             raise NotImplementedError("integrate_geom: the oversampling factor is chosen as the reference does")
-        if geom.frame != self.frame:
-            raise NotImplementedError("model frame and geometry frame differ: frame transforms are out of scope")
         g = geom.to_image()
-        desc = GeomDesc(g.npix[0], g.npix[1], 1, 1, g.binsz, g.crval[0], g.crpix[0], g.crpix[1])
+        desc = geom_desc(g)
         pars = np.array([p.value for p in self.parameters], dtype=float)
         out = np.empty(g.data_shape, dtype=np.float32)
         f = C.c_int32(0)
         ctx = Context.get()
-        check(ctx.lib.gpy_integrate_geom(ctx.handle, C.byref(desc), self._gpy_type, pars.ctypes.data_as(C.c_void_p),
-                                         out.ctypes.data_as(C.c_void_p), C.byref(f)))
+        check(ctx.lib.gpy_integrate_geom(ctx.handle, C.byref(desc), self._gpy_type, frame_code(self.frame),
+                                         pars.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.byref(f)))
         m = Map.from_geom(g, data=out, unit="" if self._gpy_type == 0 else "")
         m.meta["oversampling_factor"] = int(f.value)
         return m

@@ -88,6 +88,57 @@ def position_angle(lon1, lat1, lon2, lat2):
     return np.arctan2(y, x)
 
 
+# -- celestial frames ----------------------------------------------------------------------------------------------
+# ICRS <-> Galactic as astropy does it (coordinates/builtin_frames: icrs_fk5_transforms.py, galactic_transforms.py,
+# galactic.py): ICRS -> FK5(J2000) by the frame-bias matrix of USNO circular 179 (eta0 = -19.9 mas, xi0 = 9.1 mas,
+# da0 = -22.9 mas), FK5(J2000) -> Galactic by the rotation that puts the north galactic pole
+# (ra, dec) = (192.8594812065348, 27.12825118085622) deg on the z axis with the longitude zero point
+# lon0 = 122.9319185680026 deg.  rotation_matrix(angle, axis) there is the passive rotation (coordinates of a fixed
+# vector in the rotated basis).  The numbers are restated from the published astropy source (astropy itself cannot be
+# imported here): parity unpinned beyond the positions of the galactic centre and pole checked in the tests.
+FRAMES = ("galactic", "icrs")
+
+
+def _rot(angle_deg, axis):
+    a = np.radians(angle_deg)
+    c, s = np.cos(a), np.sin(a)
+    if axis == "x":
+        return np.array([[1.0, 0.0, 0.0], [0.0, c, s], [0.0, -s, c]])
+    if axis == "y":
+        return np.array([[c, 0.0, -s], [0.0, 1.0, 0.0], [s, 0.0, c]])
+    return np.array([[c, s, 0.0], [-s, c, 0.0], [0.0, 0.0, 1.0]])
+
+
+_ICRS_TO_FK5 = _rot(19.9 / 3600000.0, "x") @ _rot(9.1 / 3600000.0, "y") @ _rot(-22.9 / 3600000.0, "z")
+_FK5_TO_GAL = _rot(180.0 - 122.9319185680026, "z") @ _rot(90.0 - 27.12825118085622, "y") @ _rot(192.8594812065348, "z")
+ICRS_TO_GALACTIC = _FK5_TO_GAL @ _ICRS_TO_FK5
+
+
+def frame_matrix(src, dst):
+    """3 x 3 matrix taking unit vectors of frame ``src`` to frame ``dst`` (None when they are the same frame)."""
+    if src == dst:
+        return None
+    if (src, dst) == ("icrs", "galactic"):
+        return ICRS_TO_GALACTIC
+    if (src, dst) == ("galactic", "icrs"):
+        return ICRS_TO_GALACTIC.T
+    raise NotImplementedError(f"frame transform {src!r} -> {dst!r} (frames: {FRAMES})")
+
+
+def transform_lonlat(lon, lat, src, dst):
+    """(lon, lat) in deg from frame ``src`` to frame ``dst``; lon in [0, 360)."""
+    m = frame_matrix(src, dst)
+    lon, lat = np.asarray(lon, dtype=float), np.asarray(lat, dtype=float)
+    if m is None:
+        return lon, lat
+    lo, la = lon * DEG, lat * DEG
+    x, y, z = np.cos(la) * np.cos(lo), np.cos(la) * np.sin(lo), np.sin(la)
+    x2 = m[0, 0] * x + m[0, 1] * y + m[0, 2] * z
+    y2 = m[1, 0] * x + m[1, 1] * y + m[1, 2] * z
+    z2 = m[2, 0] * x + m[2, 1] * y + m[2, 2] * z
+    return np.arctan2(y2, x2) / DEG % 360.0, np.arctan2(z2, np.hypot(x2, y2)) / DEG
+
+
 class SkyCoord:
     """Minimal (lon, lat) in degrees with a frame label; enough for map centres and model positions."""
 
@@ -104,8 +155,19 @@ class SkyCoord:
     l = ra = property(lambda self: self.lon)
     b = dec = property(lambda self: self.lat)
 
+    def transform_to(self, frame):
+        if frame == self.frame:
+            return self
+        lon, lat = transform_lonlat(self.lon, self.lat, self.frame, frame)
+        return SkyCoord(lon, lat, frame=frame)
+
+    galactic = property(lambda self: self.transform_to("galactic"))
+    icrs = property(lambda self: self.transform_to("icrs"))
+
     def separation(self, other):
-        """Separation in deg."""
+        """Separation in deg (``other`` is brought into this frame first, as astropy does)."""
+        if isinstance(other, SkyCoord) and other.frame != self.frame:
+            other = other.transform_to(self.frame)
         return angular_separation(self.lon * DEG, self.lat * DEG, np.asarray(other.lon) * DEG,
                                   np.asarray(other.lat) * DEG) / DEG
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GPY_ABI_VERSION 1
+#define GPY_ABI_VERSION 2
 
 typedef enum {
   GPY_OK = 0,
@@ -50,6 +50,12 @@ typedef struct gpy_dataset gpy_dataset_t;
  * (maps/wcs/geom.py:370-410), with the default LONPOLE / LATPOLE: CAR (plate carree; the separable linear map when
  * crval_lat == 0, the oblique projection of wcslib otherwise) and TAN (gnomonic). */
 typedef enum { GPY_PROJ_CAR = 0, GPY_PROJ_TAN = 1 } gpy_projection;
+/* Celestial frames of map geometries and spatial models.  A model in another frame than the map is evaluated as the
+ * reference does (SpatialModel.evaluate_geom: geom.get_coord(frame=model.frame), modeling/models/spatial.py:196-220;
+ * the position goes through skycoord_to_pixel for cutouts and IRF lookups): pixel coordinates are rotated into the model
+ * frame on the device, the position into the map frame on the host.  ICRS <-> Galactic as astropy defines it (frame
+ * bias ICRS -> FK5 J2000 of USNO circular 179, then the IAU 1958 pole and zero point precessed to J2000). */
+typedef enum { GPY_FRAME_GALACTIC = 0, GPY_FRAME_ICRS = 1 } gpy_frame;
 
 /* WcsGeom of the counts cube (maps/wcs/geom.py:294-417) reduced to what the path reads. */
 typedef struct {
@@ -60,7 +66,7 @@ typedef struct {
   double crpix_x, crpix_y;  /* FITS 1-based reference pixel */
   double crval_lat;         /* deg; CAR: inside (-90, 90) */
   int32_t proj;             /* gpy_projection */
-  int32_t pad_;
+  int32_t frame;            /* gpy_frame */
 } gpy_geom_desc;
 
 /* The MapDataset attributes the path consumes (datasets/map.py:410; §8 a4-a6, a17 of SURVEY.md). */
@@ -104,6 +110,7 @@ typedef struct {
   int32_t spectral_par[5];  /* column of each spectral parameter */
   int32_t apply_psf;        /* SkyModel.apply_irf["psf"]   (modeling/models/cube.py) */
   int32_t apply_edisp;      /* SkyModel.apply_irf["edisp"] : 0 -> diagonal response (evaluator.py:371-377) */
+  int32_t frame;            /* gpy_frame of the spatial model (lon_0, lat_0, phi are in this frame) */
 } gpy_source_desc;
 
 /* FoVBackgroundModel with PowerLawNormSpectralModel (modeling/models/cube.py:622-756, spectral.py:1134-1162). */
@@ -269,7 +276,7 @@ int gpy_ts_map(gpy_context_t* ctx, const double* counts, const double* backgroun
  * SpatialModel.integrate_geom on an image geometry (modeling/models/spatial.py:222-309, 609-631):
  *   spatial_params HOST in the class order above; out HOST [ny, nx] float32 (the value the PSF
  *   convolution consumes, maps/wcs/ndmap.py:984); oversampling: factor used. */
-int gpy_integrate_geom(gpy_context_t* ctx, const gpy_geom_desc* geom, int32_t spatial_type,
+int gpy_integrate_geom(gpy_context_t* ctx, const gpy_geom_desc* geom, int32_t spatial_type, int32_t model_frame,
                        const double* spatial_params, float* out, int32_t* oversampling);
 /* WcsNDMap.convolve(PSFKernel) of one image with n_planes kernels, mode "same" (maps/wcs/ndmap.py:920-1010):
  *   image HOST [ny, nx] float32, kernel HOST [n_planes, k, k] float32, out HOST [n_planes, ny, nx] float32. */

@@ -16,12 +16,13 @@ def geom_to_oracle(geom):
                      proj=geom.projection)
 
 
-def model_to_oracle(model):
+def model_to_oracle(model, map_frame=None):
     if type(model).__name__ == "FoVBackgroundModel":
         spec = {"type": "pl-norm", **{p.name: p.value for p in model.spectral_model.parameters}}
         return {"type": "fov-bkg", "name": model.name, "spectral": spec}
     spatial = {"type": _SPATIAL[type(model.spatial_model).__name__],
-               **{p.name: p.value for p in model.spatial_model.parameters}}
+               **{p.name: p.value for p in model.spatial_model.parameters},
+               "frame": model.spatial_model.frame, "map_frame": map_frame}
     spectral = {"type": _SPECTRAL[type(model.spectral_model).__name__],
                 **{p.name: p.value for p in model.spectral_model.parameters}}
     return {"name": model.name, "spatial": spatial, "spectral": spectral, "apply_irf": dict(model.apply_irf)}
@@ -67,13 +68,13 @@ def dataset_to_oracle(ds):
 
 def evaluator_for(ds, conv="fft32"):
     """DatasetEvaluator with the dataset's current models / parameter values."""
-    return DatasetEvaluator(dataset_to_oracle(ds), [model_to_oracle(m) for m in (ds.models or [])], conv=conv)
+    return DatasetEvaluator(dataset_to_oracle(ds), [model_to_oracle(m, ds._geom.frame) for m in (ds.models or [])], conv=conv)
 
 
 def refresh_models(de, ds):
     """Copy the current parameter values into an existing oracle evaluator (keeps its cache state)."""
     for m in (ds.models or []):
-        new = model_to_oracle(m)
+        new = model_to_oracle(m, ds._geom.frame)
         if new.get("type") == "fov-bkg":
             de.bkg_model["spectral"].update(new["spectral"])
         else:

@@ -107,7 +107,7 @@ def model_contributes(spatial, mask_image, geom, margin=0.0):
     """modeling/models/cube.py:246-286 (mask already reduced to an image)."""
     try:
         width = 2 * _spatial.evaluation_radius(spatial) + CUTOUT_MARGIN + margin
-        _, (ys, xs) = geom.cutout_info((spatial["lon_0"], spatial["lat_0"]), width)
+        _, (ys, xs) = geom.cutout_info(_spatial.map_position(spatial), width)
         return bool(np.any(mask_image[ys, xs]))
     except (NoOverlapError, ValueError):
         return False
@@ -167,7 +167,7 @@ class Evaluator:
         s = self.model["spatial"]
         self.psf = ds.psf_kernel
         self.edisp = ds.edisp
-        position = (s["lon_0"], s["lat_0"])
+        position = _spatial.map_position(s)  # the dataset's maps are in the map frame
         if ds.edisp_map is not None:  # evaluator.py:196-204: edisp.get_edisp_kernel(position=self.position)
             self.edisp = _irf.edisp_kernel_at(ds.edisp_map, ds.irf_geom, position)
         if ds.psf_map is not None:    # evaluator.py:206-227: psf.get_psf_kernel(position, geom, containment=0.999)
@@ -180,9 +180,7 @@ class Evaluator:
         self.cutout_width = psf_width + 2 * (_spatial.evaluation_radius(s) + CUTOUT_MARGIN)
         self.contributes = model_contributes(s, ds.mask_image, ds.geom, margin=psf_width)
         if self.contributes:
-            self.geom, self.slices = ds.geom.cutout_info(
-                (s["lon_0"], s["lat_0"]), self.cutout_width, mode="trim", odd_npix=True
-            )
+            self.geom, self.slices = ds.geom.cutout_info(position, self.cutout_width, mode="trim", odd_npix=True)
             ys, xs = self.slices
             self.exposure = ds.exposure[:, ys, xs]
         self._flux_spatial = None

@@ -19,6 +19,7 @@ A spatial model is a dict ``{"type": "point"|"gauss"|"disk", "lon_0", "lat_0", .
 import numpy as np
 import scipy.integrate
 import scipy.special
+from . import frames as _frames
 from .wcs import DEG, NoOverlapError, angular_separation, position_angle
 
 MAX_OVERSAMPLING = 200  # spatial.py:54
@@ -112,6 +113,18 @@ def disk_evaluate(lon, lat, lon_0, lat_0, r_0, e=0.0, phi=0.0, edge_width=0.01):
     return norm * in_ellipse
 
 
+def map_position(model):
+    """``model.position`` in the map's frame (skycoord_to_pixel, maps/wcs/geom.py:886-930): the dict may carry the model's
+    ``frame`` and the ``map_frame`` of the geometry it is evaluated on (both None / absent: same frame)."""
+    lon, lat = _frames.transform(model["lon_0"], model["lat_0"], model.get("frame"), model.get("map_frame"))
+    return float(lon), float(lat)
+
+
+def model_coords(model, lon, lat):
+    """Map coordinates in the model's frame (``geom.get_coord(frame=self.frame)``, spatial.py:196-220)."""
+    return _frames.transform(lon, lat, model.get("map_frame"), model.get("frame"))
+
+
 def evaluate(model, lon, lat):
     t = model["type"]
     if t == "gauss":
@@ -133,7 +146,7 @@ def point_integrate_geom(model, geom):
     """spatial.py:589-631: bilinear 4-pixel weights in pixel coordinates, unit "", float64."""
     x = np.arange(geom.nx, dtype=float)[np.newaxis, :]
     y = np.arange(geom.ny, dtype=float)[:, np.newaxis]
-    x0, y0 = geom.world_to_pix(model["lon_0"], model["lat_0"])
+    x0, y0 = geom.world_to_pix(*map_position(model))
     dx = np.abs(x - x0)
     dx = np.where(dx < 1, 1 - dx, 0)
     dy = np.abs(y - y0)
@@ -156,7 +169,7 @@ def integrate_geom(model, geom, oversampling_factor=None):
     geom_cut, parent_slices = geom, None
     try:
         width = 2 * np.maximum(radius, pix_scale)
-        geom_cut, parent_slices = geom.cutout_info((model["lon_0"], model["lat_0"]), width)
+        geom_cut, parent_slices = geom.cutout_info(map_position(model), width)
     except (NoOverlapError, ValueError):
         oversampling_factor = 1
 
@@ -170,7 +183,7 @@ def integrate_geom(model, geom, oversampling_factor=None):
     if oversampling_factor > 1:
         f = int(oversampling_factor)
         up = geom_cut.upsample(f)
-        lon, lat = up.get_coord()
+        lon, lat = model_coords(model, *up.get_coord())
         values = evaluate(model, lon, lat) / f**2
         upsampled = np.zeros(up.data_shape, dtype=np.float32) + values  # float32 map += float64 array -> float64
         integrated = block_sum(upsampled, f)
@@ -184,7 +197,7 @@ def integrate_geom(model, geom, oversampling_factor=None):
         sl = geom_cut.cutout_slices(geom)
         result[sl["parent-slices"]] += data[sl["cutout-slices"]]
     else:
-        lon, lat = geom.get_coord()
+        lon, lat = model_coords(model, *geom.get_coord())
         values = evaluate(model, lon, lat)
         result = result + values  # float32 zeros + float64 -> float64
     return result * geom.solid_angle()

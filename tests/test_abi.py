@@ -25,7 +25,7 @@ def test_library_exports_every_symbol():
     lib = _lib.load()
     for name in header_functions():
         assert hasattr(lib, name), name
-    assert lib.gpy_abi_version() == 1
+    assert lib.gpy_abi_version() == 2
 
 
 def test_no_cpu_fallback():
@@ -58,7 +58,7 @@ def test_struct_layout_matches_header():
     from gammapy_b200 import _lib
 
     assert C.sizeof(_lib.GeomDesc) == 64
-    assert C.sizeof(_lib.SourceDesc) == 4 * (2 + 6 + 5 + 2)
+    assert C.sizeof(_lib.SourceDesc) == 4 * (2 + 6 + 5 + 2 + 1)
     assert C.sizeof(_lib.BackgroundDesc) == 16
     assert C.sizeof(_lib.SourceState) == 32
     assert C.sizeof(_lib.DatasetDesc) == 64 + 8 * 8 + 8 + 8 * 3 + 8 + 8 + 8 + 8  # ... weight, compact (padded), mask_row_bytes

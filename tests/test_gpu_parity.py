@@ -107,7 +107,7 @@ def test_integrate_geom(ctx, name, pars, gtype, vec):
     out = np.empty(geom.data_shape, dtype=np.float32)
     f = C.c_int32(0)
     v = np.array(vec, dtype=float)
-    _lib.check(ctx.lib.gpy_integrate_geom(ctx.handle, C.byref(_geom_desc(geom)), gtype, _ptr(v), _ptr(out), C.byref(f)))
+    _lib.check(ctx.lib.gpy_integrate_geom(ctx.handle, C.byref(_geom_desc(geom)), gtype, 0, _ptr(v), _ptr(out), C.byref(f)))
     scale = max(float(np.abs(want).max()), 1e-300)
     assert_allclose(out, want, rtol=2e-6, atol=2 * EPS32 * scale)
     if name == "gauss-tiny-f200":
@@ -386,7 +386,7 @@ def test_errors_are_loud(ctx):
     with pytest.raises(NotImplementedError):
         WcsGeom.create(skydir=(0, 10), binsz=0.1, width=2, proj="AIT")
     ds = configs.make_dataset(width=(1.0, 1.0), mask_radius=None)
-    bad = SkyModel(spatial_model=GaussianSpatialModel(frame="icrs"), spectral_model=PowerLawSpectralModel(), name="x")
+    bad = SkyModel(spatial_model=GaussianSpatialModel(frame="fk5"), spectral_model=PowerLawSpectralModel(), name="x")
     ds.models = [bad]
     with pytest.raises(NotImplementedError):
         ds.npred()
