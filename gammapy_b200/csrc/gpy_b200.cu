@@ -1151,12 +1151,13 @@ int evaluate_replay(gpy_context* c, const EvalRequest& rq, bool* done) {
     R.kernels = 0;
     if (R.k0_blocks) {
       gpy::spectral_flux_kernel<<<R.k0_blocks, R.k0_threads, (size_t)R.k0_seg_cap * sizeof(double), c->stream>>>(
-          R.k0_jobs, R.k0_seg_cap, (const double*)R.d_params.p);
+          R.k0_jobs, R.k0_seg_cap, (const double*)R.d_params.p, R.fold_params.counter);  // (also zeroes the work counter)
       R.kernels++;
+    } else if (R.fold_params.counter) {
+      cudaMemsetAsync(R.fold_params.counter, 0, sizeof(unsigned), c->stream);
     }
-    if (R.fold_params.counter) cudaMemsetAsync(R.fold_params.counter, 0, sizeof(unsigned), c->stream);
     R.fold_kernel<<<R.fold_grid, gpy::kFoldThreads, R.fold_smem, c->stream>>>(R.fold_params);
-    gpy::reduce_stat_kernel<<<dim3(1, D), 256, 0, c->stream>>>((const double*)c->partials.p, R.fold_params.ds, R.n_tiles, D, 1,
+    gpy::reduce_stat_kernel<<<dim3(1, D), gpy::kReduceThreads, 0, c->stream>>>((const double*)c->partials.p, R.fold_params.ds, R.n_tiles, D, 1,
                                                               nullptr, (double*)c->stat.p);
     R.kernels += 2;
     if (R.joint_out) {
@@ -1655,7 +1656,7 @@ int evaluate_impl(gpy_context* c, const EvalRequest& rq) {
       if (j.type != 0 && j.type != gpy::kFluxJobBackground) seg_cap = std::max(seg_cap, j.n_bins * (2 * j.n_nodes - 1));
     seg_cap = std::min(seg_cap, 5120);  // 40 KB
     gpy::spectral_flux_kernel<<<(unsigned)jobs.size(), seg_cap ? 256 : 64, (size_t)seg_cap * sizeof(double),
-                                c->stream>>>((const gpy::FluxJob*)(base + off_jb), seg_cap, nullptr);
+                                c->stream>>>((const gpy::FluxJob*)(base + off_jb), seg_cap, nullptr, nullptr);
     c->launches++;
     k0_blocks = (unsigned)jobs.size();
     k0_threads = seg_cap ? 256 : 64;
@@ -1848,7 +1849,7 @@ int evaluate_impl(gpy_context* c, const EvalRequest& rq) {
   }
   c->launches++;
   if (!rq.npred_out) {
-    gpy::reduce_stat_kernel<<<dim3(B, D), 256, 0, c->stream>>>((const double*)c->partials.p, fp.ds, n_tiles, D,
+    gpy::reduce_stat_kernel<<<dim3(B, D), gpy::kReduceThreads, 0, c->stream>>>((const double*)c->partials.p, fp.ds, n_tiles, D,
                                                               B, reduce_dup, (double*)c->stat.p);
     c->launches++;
   }
@@ -2669,7 +2670,7 @@ int gpy_spectral_integral(gpy_context_t* c, int32_t spectral_type, const double*
   if (nn) CUDA_TRY(cudaMemcpyAsync(d_nodes, nodes, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(d_job, &job, sizeof(job), cudaMemcpyHostToDevice, c->stream));
   const int seg_cap = spectral_type == GPY_SPECTRAL_PL ? 0 : std::min(n_bins * std::max(2 * n_nodes - 1, 0), 5120);
-  gpy::spectral_flux_kernel<<<1, seg_cap ? 256 : 64, (size_t)seg_cap * sizeof(double), c->stream>>>(d_job, seg_cap, nullptr);
+  gpy::spectral_flux_kernel<<<1, seg_cap ? 256 : 64, (size_t)seg_cap * sizeof(double), c->stream>>>(d_job, seg_cap, nullptr, nullptr);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(out, d_out, n_bins * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

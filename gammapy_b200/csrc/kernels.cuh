@@ -502,8 +502,12 @@ __device__ __forceinline__ double log_scale(double v) {
 // dynamic shared memory.
 // params: null, or the caller's parameter vector on the device: the job's values are then read from it (pidx), so a
 // replayed launch (CUDA graph of the steady-state step, see evaluate_replay) only needs the new vector.
-__global__ void spectral_flux_kernel(const FluxJob* __restrict__ jobs, int seg_cap, const double* __restrict__ params) {
+// reset: null, or the fold kernel's work counter, zeroed here for the launch that follows (saves the memset node of the
+// replayed step).
+__global__ void spectral_flux_kernel(const FluxJob* __restrict__ jobs, int seg_cap, const double* __restrict__ params,
+                                     unsigned* __restrict__ reset) {
   extern __shared__ double seg[];
+  if (reset && blockIdx.x == 0 && threadIdx.x == 0) *reset = 0u;
   FluxJob job = jobs[blockIdx.x];
   if (params) {
 #pragma unroll
@@ -1803,15 +1807,17 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_cash_tma_kernel(const Fo
 #endif
 }
 
-// Second stage: stat[b, d] = 2 * sum of the tile partials of dataset d, fixed summation order.
-__global__ void __launch_bounds__(256)
+// Second stage: stat[b, d] = 2 * sum of the tile partials of dataset d, fixed summation order (thread t adds tiles
+// t, t + 512, ..., then a fixed tree): 512 threads keep the dependent chain of a C3-sized dataset at 16 loads.
+constexpr int kReduceThreads = 512;
+__global__ void __launch_bounds__(kReduceThreads)
 reduce_stat_kernel(const double* __restrict__ partials, const DatasetDev* __restrict__ ds, int n_tiles,
                    int n_datasets, int B, const unsigned char* __restrict__ dup, double* __restrict__ stat) {
-  __shared__ double sm[256];
+  __shared__ double sm[kReduceThreads];
   const int b = blockIdx.x, d = blockIdx.y;
   const int begin = ds[d].tile_begin, n = ds[d].n_tiles;
   double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += 256) {
+  for (int i = threadIdx.x; i < n; i += kReduceThreads) {
     const int tile = begin + i;
     // items identical to vector 0 on this tile were not evaluated: read the partial of (tile, 0)
     const int bb = (dup && dup[(size_t)tile * B + b]) ? 0 : b;
@@ -1819,7 +1825,7 @@ reduce_stat_kernel(const double* __restrict__ partials, const DatasetDev* __rest
   }
   sm[threadIdx.x] = s;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
+  for (int o = kReduceThreads / 2; o > 0; o >>= 1) {
     if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
     __syncthreads();
   }
