@@ -113,6 +113,7 @@ SYMBOLS = {
     "gpy_peer_reduce_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "gpy_peer_reduce_init": (C.c_int, [_P, C.POINTER(_P), C.c_int32, C.c_int32, C.c_int32]),
     "gpy_stat_sum_joint_device": (C.c_int, [_P, C.POINTER(_P), C.c_int32, _P, C.c_int32, C.c_int32, _P]),
+    "gpy_stat_sum_joint": (C.c_int, [_P, C.POINTER(_P), C.c_int32, _P, C.c_int32, C.c_int32, _P]),
     "gpy_npred": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P]),
     "gpy_cash_sum": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "gpy_weighted_cash_sum": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),

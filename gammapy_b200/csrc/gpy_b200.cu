@@ -397,6 +397,7 @@ struct gpy_context {
     Source* src;
     size_t slot;  // index into src->slots
   };
+  DevBuf joint_dev;  // gpy_stat_sum_joint: the all-reduced statistics before they are copied to the host
   std::vector<PendingSpatial> pending;
   size_t conv_batch_smem_set = 0;
   bool batch_spatial = true;  // GPY_SPATIAL_BATCH=0: three launches per moved source instead (A/B, tests)
@@ -2342,6 +2343,22 @@ int gpy_stat_sum_joint_device(gpy_context_t* c, gpy_dataset_t* const* datasets, 
   EvalRequest rq{datasets, n_datasets, params, n_vec, n_par, nullptr, 1, nullptr};
   rq.joint_out = joint_device;  // the all-reduce is the last kernel of the evaluation (inside the replayed graph too)
   GPY_TRY(evaluate(c, rq));
+  return GPY_OK;
+}
+
+int gpy_stat_sum_joint(gpy_context_t* c, gpy_dataset_t* const* datasets, int32_t n_datasets, const double* params,
+                       int32_t n_vec, int32_t n_par, double* joint) {
+  if (!c || !joint) return fail(GPY_ERR_INVALID, "NULL argument to gpy_stat_sum_joint");
+  if (!c->peer_on) return fail(GPY_ERR_INVALID, "gpy_peer_reduce_init has not been called on this context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  // one device buffer for the life of the context: its address is part of the replayed graph
+  if (!c->joint_dev.p) GPY_TRY(c->joint_dev.reserve((size_t)std::max(c->peer.cap, 1) * sizeof(double)));
+  GPY_TRY(gpy_stat_sum_joint_device(c, datasets, n_datasets, params, n_vec, n_par, (double*)c->joint_dev.p));
+  GPY_TRY(ensure_stat_pinned(c, (size_t)n_vec));
+  CUDA_TRY(cudaMemcpyAsync(c->stat_pinned, c->joint_dev.p, (size_t)n_vec * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->h2d_pending = false;
+  std::memcpy(joint, c->stat_pinned, (size_t)n_vec * sizeof(double));
   return GPY_OK;
 }
 

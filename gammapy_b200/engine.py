@@ -351,6 +351,16 @@ class LikelihoodEngine:
         _lib.check(self.ctx.lib.gpy_stat_sum_joint_device(self.ctx.handle, self._handles, len(self.datasets), _ptr(v2),
                                                           v2.shape[0], self.n_par, C.c_void_p(out.data_ptr())))
 
+    def stat_sum_joint(self, values):
+        """Joint statistic over the ranks of a sharded fit as a numpy array [B] (``gpy_stat_sum_joint``: evaluation,
+        one-shot all-reduce over NVLink peer memory, copy to the host, one synchronisation -- all inside the library)."""
+        v2 = np.ascontiguousarray(values, dtype=float).reshape(-1, self.n_par)
+        self._claim()
+        out = np.empty(v2.shape[0], dtype=float)
+        _lib.check(self.ctx.lib.gpy_stat_sum_joint(self.ctx.handle, self._handles, len(self.datasets), _ptr(v2),
+                                                   v2.shape[0], self.n_par, _ptr(out)))
+        return out
+
     def npred(self, index, values=None, source_enable=None, include_background=True):
         """npred cube of dataset ``index`` as a float64 numpy array."""
         return self.npred_device(index, values, source_enable, include_background).cpu().numpy()

@@ -219,11 +219,15 @@ int gpy_stat_sum_device(gpy_context_t* ctx, gpy_dataset_t* const* datasets, int3
  *   gpy_stat_sum_joint_device calls.
  * gpy_stat_sum_joint_device: as gpy_stat_sum_device, then joint_device DEVICE [n_vec] float64 = sum over ranks of
  *   (sum over this rank's datasets, in dataset order), ranks added in rank order: bit-identical on every rank.  A rank
- *   that waits longer than 5 s for a peer writes NaN instead of hanging the device. */
+ *   that waits longer than 5 s for a peer writes NaN instead of hanging the device.
+ * gpy_stat_sum_joint: the same, with the result copied to joint HOST [n_vec] and the stream synchronised -- the
+ *   sharded counterpart of gpy_stat_sum (ShardedDatasets.stat_sum: what Fit calls on every rank). */
 int64_t gpy_peer_reduce_bytes(int32_t world, int32_t capacity);
 int gpy_peer_reduce_init(gpy_context_t* ctx, void* const* peer_buffers, int32_t rank, int32_t world, int32_t capacity);
 int gpy_stat_sum_joint_device(gpy_context_t* ctx, gpy_dataset_t* const* datasets, int32_t n_datasets,
                               const double* params, int32_t n_vec, int32_t n_par, double* joint_device);
+int gpy_stat_sum_joint(gpy_context_t* ctx, gpy_dataset_t* const* datasets, int32_t n_datasets, const double* params,
+                       int32_t n_vec, int32_t n_par, double* joint);
 
 /* MapDataset.npred (datasets/map.py:775-788) / npred_signal (:824-880) for one parameter vector.
  *   source_enable HOST [n_sources] or NULL (all): npred_signal(model_names=...)
