@@ -498,8 +498,71 @@ def _parameters_with_prior(engine):
     return cached[1]
 
 
+class _MixedEngine:
+    """Joint likelihood of Cash and WStat members (``Datasets.stat_sum``, datasets/core.py:264-277: the sum of every
+    dataset's own statistic, in dataset order): the Cash members share one ``LikelihoodEngine`` (one fold launch for all
+    of them), every ``MapDatasetOnOff`` evaluates its npred_signal and ``wstat_sum_kernel`` through its own engine; one
+    parameter vector over the union of their parameters."""
+
+    def __init__(self, datasets):
+        from .engine import LikelihoodEngine
+        from .modeling.parameter import bind_mirror
+
+        self.datasets = list(datasets)
+        self._signature = LikelihoodEngine.signature(self.datasets)
+        cash = [d for d in self.datasets if getattr(d, "stat_type", "cash") != "wstat"]
+        self._cash = LikelihoodEngine(cash) if cash else None
+        self._cash_index = {id(d): i for i, d in enumerate(cash)}
+        self._onoff = {id(d): d._fit_engine() for d in self.datasets if getattr(d, "stat_type", "cash") == "wstat"}
+        self.parameters, col = [], {}
+        for d in self.datasets:
+            for model in (d.models or []):
+                for par in model.parameters:
+                    if id(par) not in col:
+                        col[id(par)] = len(self.parameters)
+                        self.parameters.append(par)
+        self.n_par = max(len(self.parameters), 1)
+        self.ctx = (self._cash or next(iter(self._onoff.values()))).ctx
+        self._cash_cols = np.array([col[id(p)] for p in self._cash.parameters], dtype=int) if self._cash else None
+        self._onoff_cols = {k: np.array([col[id(p)] for p in e.parameters], dtype=int) for k, e in self._onoff.items()}
+        self._vec = bind_mirror(self.parameters)
+
+    def __del__(self):
+        from .modeling.parameter import release_mirror
+
+        try:
+            release_mirror(self.parameters, self._vec)
+        except Exception:
+            pass
+
+    def values(self):
+        return self._vec.copy() if self.parameters else np.zeros(self.n_par)
+
+    def stat_sum(self, values=None, per_dataset=False):
+        if values is None:
+            values = self.values()
+        values = np.ascontiguousarray(values, dtype=float)
+        single = values.ndim == 1
+        v2 = values.reshape(1, -1) if single else values
+        if v2.shape[1] != self.n_par:
+            raise ValueError(f"expected {self.n_par} parameter values per vector, got {v2.shape[1]}")
+        per = np.zeros((v2.shape[0], len(self.datasets)))
+        if self._cash is not None:
+            _, cash_per = self._cash.stat_sum(np.ascontiguousarray(v2[:, self._cash_cols]), per_dataset=True)
+        for k, d in enumerate(self.datasets):
+            if id(d) in self._onoff:
+                per[:, k] = np.atleast_1d(self._onoff[id(d)].stat_sum(np.ascontiguousarray(v2[:, self._onoff_cols[id(d)]])))
+            else:
+                per[:, k] = cash_per[:, self._cash_index[id(d)]]
+        stat = np.zeros(v2.shape[0])
+        for k in range(len(self.datasets)):  # the reference's loop: stat_sum += dataset.stat_sum_likelihood()
+            stat = stat + per[:, k]
+        if per_dataset:
+            return (float(stat[0]), per[0]) if single else (stat, per)
+        return float(stat[0]) if single else stat
+
+
 class Datasets(list):
-    # (MapDatasetOnOff members are refused in _get_engine: the joint engine evaluates Cash)
     """Container of datasets with a joint likelihood (datasets/core.py:140)."""
 
     def __init__(self, datasets=None):
@@ -593,8 +656,15 @@ class Datasets(list):
         from .engine import LikelihoodEngine
 
         if any(getattr(d, "stat_type", "cash") == "wstat" for d in self):
-            raise NotImplementedError("joint fits with MapDatasetOnOff members: the joint engine evaluates Cash; "
-                                      "fit an ON/OFF dataset on its own (Fit.run(dataset))")
+            # ON/OFF members bring their own statistic (WStat): Cash members in one engine, the others one by one
+            stale = (self._engine is None or not isinstance(self._engine, _MixedEngine)
+                     or self._engine._signature != LikelihoodEngine.signature(self))
+            if not stale:
+                stale = any(d._device is None or d._device._uploaded != d._data_fingerprint()
+                            for d in self if getattr(d, "stat_type", "cash") != "wstat")
+            if stale:
+                self._engine = _MixedEngine(self)
+            return self._engine
         stale = self._engine is None or self._engine._signature != LikelihoodEngine.signature(self)
         if not stale:
             stale = any(d._device is None or d._device._uploaded != d._data_fingerprint() for d in self)

@@ -97,3 +97,49 @@ def test_map_dataset_onoff_vs_oracle_and_fit(ctx):
     adapter.refresh_models(de, base)
     want = ow.stat_sum_dataset(n_on, n_off, np.full(geom.data_shape, alpha), de.npred_signal(), mask)
     assert abs(res.total_stat - want) < 1e-3
+
+
+def test_joint_fit_of_a_cash_and_an_on_off_dataset(ctx):
+    """``Datasets([MapDataset, MapDatasetOnOff])`` with a shared source (datasets/core.py:264-277: the sum of every
+    dataset's own statistic): the Cash member through the fold kernel's statistic, the ON/OFF member through WStat;
+    single and batched evaluations and a joint fit."""
+    from gammapy_b200 import Datasets, Fit, Map, MapDatasetOnOff, configs
+    from oracle import adapter
+
+    base = configs.make_c1(width=(2.0, 2.0), mask_radius=0.9)
+    src = [m for m in base.models if m.name == "model-simu"][0]
+    de = adapter.evaluator_for(base, conv="exact64")
+    base.counts = Map.from_geom(base._geom, data=de.fake(3), dtype=float)
+    sig = de.npred_signal()
+    rng = np.random.RandomState(8)
+    bkg = np.asarray(base.background.data, float)
+    alpha = 0.2
+    geom = base._geom
+    onoff = MapDatasetOnOff(counts=Map.from_geom(geom, data=rng.poisson(sig + bkg).astype(float), dtype=float),
+                            counts_off=Map.from_geom(geom, data=rng.poisson(bkg / alpha).astype(float), dtype=float),
+                            acceptance=Map.from_geom(geom, data=np.full(geom.data_shape, 1.0), dtype=float),
+                            acceptance_off=Map.from_geom(geom, data=np.full(geom.data_shape, 1.0 / alpha), dtype=float),
+                            exposure=base.exposure, psf=base.psf, edisp=base.edisp, mask_safe=base.mask_safe,
+                            mask_fit=base.mask_fit, models=[src], name="onoff")
+    joint = Datasets([base, onoff])
+    assert len(joint.parameters) == len(base.parameters)  # the ON/OFF member adds no parameter: it shares the source
+    want = base.stat_sum() + onoff.stat_sum()
+    assert joint.stat_sum() == pytest.approx(want, rel=0, abs=1e-6)
+    total, per = joint._get_engine().stat_sum(per_dataset=True)
+    assert per[0] == pytest.approx(base.stat_sum(), abs=1e-6) and per[1] == pytest.approx(onoff.stat_sum(), abs=1e-6)
+    vals, pars = joint.parameter_vector()
+    col = [i for i, p in enumerate(pars) if p is src.spectral_model.index][0]
+    grid = np.tile(vals, (3, 1))
+    grid[:, col] += [0.0, 0.1, -0.1]
+    scan = joint.stat_sum_batch(grid)
+    assert scan[0] == pytest.approx(want, abs=1e-6) and scan[1] != scan[0] and scan[2] != scan[0]
+    src.spectral_model.index.value += 0.1
+    assert joint.stat_sum() == pytest.approx(scan[1], abs=1e-6)
+    src.spectral_model.index.value -= 0.1
+    for p in (src.spatial_model.lon_0, src.spatial_model.lat_0, src.spatial_model.sigma):
+        p.frozen = True
+    src.spectral_model.amplitude.value *= 1.3
+    res = Fit().run(joint)
+    assert res.success, res.optimize_result.message
+    assert res.total_stat < want and abs(res.total_stat - joint.stat_sum()) < 1e-6
+    assert abs(res.total_stat - (base.stat_sum() + onoff.stat_sum())) < 1e-6
