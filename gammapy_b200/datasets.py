@@ -291,6 +291,78 @@ class MapDataset:
 
     stat_sum = stat_sum_likelihood
 
+    # -- what one looks at after a fit: all host arithmetic on the GPU's npred cubes ---------------------------------
+    @property
+    def excess(self):
+        """Observed excess: counts - background (datasets/map.py:669-672)."""
+        return Map.from_geom(self._geom, data=np.asarray(self._counts.data, float) - np.asarray(self._background.data, float),
+                             dtype=float)
+
+    def residuals(self, method="diff", **kwargs):
+        """Residual map (datasets/map.py:1210-1255, core.py:117-129): ``diff`` = data - model, ``diff/model``,
+        ``diff/sqrt(model)``; both sides multiplied by the mask, masked bins NaN.  Smoothing keywords are not supported."""
+        if kwargs:
+            raise NotImplementedError("residuals(): smoothing (Map.smooth keywords) is outside the accelerated path")
+        npred = np.asarray(self.npred().data, float)
+        counts = np.asarray(self._counts.data, float).copy()
+        mask = None if self.mask is None else np.asarray(self.mask.data, bool)
+        if mask is not None:
+            npred, counts = npred * mask, counts * mask
+        with np.errstate(invalid="ignore", divide="ignore"):
+            if method == "diff":
+                res = counts - npred
+            elif method == "diff/model":
+                res = (counts - npred) / npred
+            elif method == "diff/sqrt(model)":
+                res = (counts - npred) / np.sqrt(npred)
+            else:
+                raise AttributeError(f"Invalid method: {method!r} for computing residuals")
+        if mask is not None:
+            res[~mask] = np.nan
+        return Map.from_geom(self._geom, data=res, dtype=float)
+
+    def info_dict(self, in_safe_data_range=True):
+        """Summary statistics summed over energy (datasets/map.py:1791-1900): counts, background, excess and its
+        significance (``CashCountsStatistic`` of the summed numbers, stats/counts_statistic.py:250-288), the npred sums,
+        the exposure range and the fit statistic.  Times (livetime, ontime, rates) are not carried by this package."""
+        info = {"name": self.name}
+        mask = np.asarray(self.mask_safe.data, bool) if (self.mask_safe is not None and in_safe_data_range) else slice(None)
+        counts, background, excess, sqrt_ts = 0, np.nan, np.nan, np.nan
+        npred_background = None if self._background is None else np.asarray(self.npred_background().data, float)
+        if self._counts is not None:
+            counts = float(np.asarray(self._counts.data, float)[mask].sum())
+            if self._background is not None:
+                background = float(np.asarray(self._background.data, float)[mask].sum())
+                mu_bkg = float(npred_background[mask].sum())
+
+                def cash(n_on, mu_on):  # stats/fit_statistics.py:29-79
+                    mu_on = max(mu_on, 1e-25)
+                    return 2 * (mu_on - n_on * np.log(mu_on))
+
+                excess = counts - mu_bkg
+                ts = max(cash(counts, mu_bkg) - cash(counts, counts), 0.0)
+                sqrt_ts = float(np.sign(excess) * np.sqrt(ts))
+        info.update(counts=int(counts), excess=float(excess), sqrt_ts=sqrt_ts, background=float(background))
+        info["npred"] = float(self.npred().data[mask].sum()) if (self.models or not np.isnan(background)) else np.nan
+        info["npred_background"] = float(npred_background[mask].sum()) if npred_background is not None else np.nan
+        has_sources = self.models is not None and any(not isinstance(m, FoVBackgroundModel) for m in self.models)
+        info["npred_signal"] = float(self.npred_signal().data[mask].sum()) if has_sources else np.nan
+        exposure_min = exposure_max = np.nan
+        if self.exposure is not None:
+            data = np.asarray(self.exposure.data, float)
+            sel = data > 0
+            if self.mask_safe is not None:
+                sel = sel & np.asarray(self.mask_safe.data, bool).any(axis=0)[np.newaxis]
+            if not sel.any():
+                sel = slice(None)
+            exposure_min, exposure_max = float(data[sel].min()), float(data[sel].max())
+        info.update(exposure_min=exposure_min, exposure_max=exposure_max)
+        info["n_bins"] = int(np.asarray(self._counts.data).size) if self._counts is not None else 0
+        info["n_fit_bins"] = int(np.sum(self.mask.data)) if self.mask is not None else 0
+        info["stat_type"] = self.stat_type
+        info["stat_sum"] = float(self.stat_sum()) if (self._counts is not None and self.models is not None) else np.nan
+        return info
+
     def stat_array(self):
         """Per-bin Cash (stats/fit_statistics.py:29-79, 295-298, 323-329) from the GPU npred cube."""
         n_on = np.asarray(self._counts.data, dtype=float)

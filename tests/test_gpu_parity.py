@@ -735,3 +735,39 @@ def test_steady_state_replay_matches_the_oracle_and_the_batched_path(ctx):
     assert abs(datasets.stat_sum() - de.stat_sum()) < 1e-3
     for p, v in zip(plist, values):
         p.value = v
+
+
+def test_residuals_excess_and_info_dict(ctx):
+    """What one looks at after a fit (datasets/map.py:669-672, 1210-1255, 1791-1900): host arithmetic on the GPU's npred
+    cubes, against the same arithmetic on the oracle's cubes."""
+    from gammapy_b200 import Map, configs
+    from oracle import adapter
+
+    ds = configs.make_c2(width=(3.0, 3.0), mask_radius=1.0)
+    de = adapter.evaluator_for(ds, conv="exact64")
+    counts = de.fake(11)
+    ds.counts = Map.from_geom(ds._geom, data=counts, dtype=float)
+    npred, mask = de.npred(), np.asarray(ds.mask.data, bool)
+    for method, fn in (("diff", lambda c, m: c - m), ("diff/model", lambda c, m: (c - m) / m),
+                       ("diff/sqrt(model)", lambda c, m: (c - m) / np.sqrt(m))):
+        got = ds.residuals(method).data
+        assert np.isnan(got[~mask]).all()
+        want = fn(counts[mask], npred[mask])
+        assert_allclose(got[mask], want, rtol=2e-5, atol=2e-5 * np.abs(want).max())
+    with pytest.raises(AttributeError):
+        ds.residuals("ratio")
+    with pytest.raises(NotImplementedError):
+        ds.residuals(width="0.1 deg")
+    assert_allclose(ds.excess.data, counts - np.asarray(ds.background.data, float))
+    info = ds.info_dict()
+    safe = np.asarray(ds.mask_safe.data, bool)
+    assert info["name"] == ds.name and info["counts"] == int(counts[safe].sum())
+    assert_allclose(info["npred"], npred[safe].sum(), rtol=1e-6)
+    assert_allclose(info["npred_signal"], de.npred_signal()[safe].sum(), rtol=1e-6)
+    assert_allclose(info["npred_background"] + info["npred_signal"], info["npred"], rtol=1e-9)
+    assert_allclose(info["excess"], info["counts"] - info["npred_background"], rtol=1e-12)
+    n, mu = info["counts"], info["npred_background"]
+    assert_allclose(info["sqrt_ts"], np.sign(n - mu) * np.sqrt(2 * ((mu - n * np.log(mu)) - (n - n * np.log(n)))), rtol=1e-9)
+    assert info["n_bins"] == counts.size and info["n_fit_bins"] == int(mask.sum()) and info["stat_type"] == "cash"
+    assert_allclose(info["stat_sum"], ds.stat_sum(), rtol=0, atol=1e-9)
+    assert 0 < info["exposure_min"] <= info["exposure_max"]
