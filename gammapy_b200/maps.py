@@ -57,6 +57,13 @@ class MapAxis:
         return cls(edges, interp=interp, name=name, node_type="edges", unit=unit)
 
     @classmethod
+    def from_nodes(cls, nodes, name="", unit="", interp="lin"):
+        """maps/axes.py:663-685: bin centres given, edges half-way between them in the axis' interpolation scale."""
+        if len(nodes) < 1:
+            raise ValueError("Nodes array must have at least one element.")
+        return cls(nodes, interp=interp, name=name, node_type="center", unit=unit)
+
+    @classmethod
     def from_bounds(cls, lo_bnd, hi_bnd, nbin, interp="lin", node_type="edges", name="", unit=""):
         nnode = int(nbin) + 1 if node_type == "edges" else int(nbin)
         if interp == "lin":
@@ -145,9 +152,12 @@ class MapAxis:
         return new
 
     def upsample(self, factor):
-        """maps/axes.py upsample: factor * nbin bins between the same bounds, same interpolation."""
+        """maps/axes.py:1087-1117: factor * nbin bins between the same bounds (edges axis), (nbin - 1) * factor + 1 nodes
+        between the same end nodes (centre-node axis); same interpolation."""
         if self.node_type != "edges":
-            raise NotImplementedError("upsample needs an edges axis")
+            pix = self.coord_to_pix(self.center)
+            pix_new = np.linspace(pix.min(), pix.max(), int((self.nbin - 1) * factor) + 1)
+            return MapAxis.from_nodes(self.pix_to_coord(pix_new), name=self.name, unit=self.unit, interp=self.interp)
         edges = self.edges
         return MapAxis.from_bounds(edges[0], edges[-1], self.nbin * factor, interp=self.interp, name=self.name,
                                    unit=self.unit)

@@ -60,3 +60,28 @@ def test_two_zones_nearest_pixel_and_bilinear_profile():
     # product host mirror == oracle (independent code paths)
     want = ds.psf.get_psf_kernel(ds.exposure.geom, position=(-1.0, 0.0)).data
     np.testing.assert_allclose(k1, want, rtol=0, atol=3e-7 * want.max())
+
+
+def test_containment_radius_against_the_reference_goldens():
+    """The reference's data-free PSF-map tests (irf/psf/tests/test_map.py:429-473 ``test_psf_map_from_gauss`` /
+    ``_const_sigma``; :518-536 the RecoPSFMap variant's containment values): a Gaussian PSF map built by ``from_gauss``
+    has its 39.4 % containment radius at sigma within 1 %, and containment(0.1 deg) = 1 - exp(-0.5 (0.1 / sigma)^2) --
+    for the host mirror (``PSFMap.containment_radius``: irf/psf/core.py:39-87) and for the oracle restatement
+    (``oracle.irf.containment_radius``), which is what sizes every evaluator's kernel."""
+    from gammapy_b200 import MapAxis, PSFMap
+
+    energy_axis = MapAxis.from_nodes([1, 3, 10], name="energy_true", interp="log", unit="TeV")
+    rad_axis = MapAxis.from_nodes(np.linspace(0, 1.5, 100), name="rad", unit="deg")
+    for sigma in ([0.1, 0.2, 0.4], [0.1, 0.1, 0.1]):
+        psf = PSFMap.from_gauss(energy_axis, rad_axis, sigma)
+        assert psf.data.shape == (3, 100)
+        np.testing.assert_allclose(psf.containment_radius(0.394), sigma, rtol=0.01)
+        np.testing.assert_allclose(oirf.containment_radius(psf.data, rad_axis.edges, 0.394), sigma, rtol=0.01)
+    psf = PSFMap.from_gauss(energy_axis, rad_axis, [0.1, 0.2, 0.3])
+    np.testing.assert_allclose(psf.containment(0.1).ravel(), [0.3938, 0.1175, 0.0540], rtol=1e-2)
+    # the radius that sizes the kernels, on the fine default rad axis: 99.9 % of a Gaussian lies within 3.717 sigma
+    fine = PSFMap.from_gauss(energy_axis, sigma=[0.04, 0.07, 0.1])  # (the default rad axis ends at 0.66 deg)
+    r999 = oirf.containment_radius(fine.data, fine.rad_axis.edges, 0.999)
+    # (midpoint sums over 0.01 deg rad bins: a few per cent above the true containment, so the radius comes out low)
+    np.testing.assert_allclose(r999, np.array([0.04, 0.07, 0.1]) * np.sqrt(-2 * np.log(0.001)), rtol=0.1)
+    np.testing.assert_allclose(fine.containment_radius(0.999), r999, rtol=1e-12)
