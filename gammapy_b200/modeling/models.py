@@ -352,10 +352,22 @@ class SkyModel:
         return new
 
     def freeze(self, model_type=None):
+        """cube.py:320-330: all parameters, or those of the spatial / spectral component."""
         if model_type in (None, "spatial"):
             self.spatial_model.freeze()
         if model_type in (None, "spectral"):
             self.spectral_model.freeze()
+
+    def unfreeze(self, model_type=None):
+        """Frozen status back to the component classes' defaults (cube.py:332-342)."""
+        if model_type in (None, "spatial"):
+            self.spatial_model.unfreeze()
+        if model_type in (None, "spectral"):
+            self.spectral_model.unfreeze()
+
+    @property
+    def frozen(self):
+        return all(p.frozen for p in self.parameters)
 
     def __repr__(self):
         return f"SkyModel(name={self.name!r}, spatial_model={self.spatial_model!r}, spectral_model={self.spectral_model!r})"
@@ -391,6 +403,18 @@ class FoVBackgroundModel:
         new._name = make_name(name)
         return new
 
+    def freeze(self, model_type=None):
+        if model_type in (None, "spectral"):
+            self.spectral_model.freeze()
+
+    def unfreeze(self, model_type=None):
+        if model_type in (None, "spectral"):
+            self.spectral_model.unfreeze()
+
+    @property
+    def frozen(self):
+        return all(p.frozen for p in self.parameters)
+
     def __repr__(self):
         return f"FoVBackgroundModel(name={self.name!r}, datasets_names={self.datasets_names}, spectral_model={self.spectral_model!r})"
 
@@ -417,19 +441,143 @@ class Models(list):
     def names(self):
         return [m.name for m in self]
 
-    def select(self, datasets_names=None, name_substring=None, tag=None):
+    def selection_mask(self, name_substring=None, datasets_names=None, tag=None, model_type=None, frozen=None):
+        """Boolean mask of the models that meet all conditions (modeling/models/core.py:888-949)."""
+        tags = None if not tag else ([tag] if isinstance(tag, str) else list(tag))
+        wanted = None if not datasets_names else ([datasets_names] if isinstance(datasets_names, str) else list(datasets_names))
+        mask = np.ones(len(self), dtype=bool)
+        for i, m in enumerate(self):
+            if name_substring:
+                mask[i] &= name_substring in m.name
+            if wanted:
+                mask[i] &= m.datasets_names is None or any(n in m.datasets_names for n in wanted)
+            if tags:
+                sub = m if model_type is None else getattr(m, f"{model_type}_model", None)
+                mask[i] &= bool(sub is not None and any(t in sub.tag for t in tags))
+            if frozen is not None:
+                all_frozen = all(p.frozen for p in m.parameters)
+                mask[i] &= all_frozen if frozen else not all_frozen
+        return mask
+
+    def select(self, name_substring=None, datasets_names=None, tag=None, model_type=None, frozen=None):
+        """Models that meet all conditions (modeling/models/core.py:855-886)."""
+        mask = self.selection_mask(name_substring, datasets_names, tag, model_type, frozen)
+        return Models([m for m, keep in zip(self, mask) if keep])
+
+    # -- container operations with the reference's uniqueness rule (core.py:128-136, 776-783, 1358-1380) ----------
+    def _check_name_unique(self, model, names=None):
+        if model.name in (self.names if names is None else names):
+            raise ValueError(f"Model names must be unique. Models named '{model.name}' are duplicated.")
+
+    def append(self, model):
+        self._check_name_unique(model)
+        list.append(self, model)
+
+    def insert(self, idx, model):
+        self._check_name_unique(model)
+        list.insert(self, idx, model)
+
+    def extend(self, models):
+        for m in models:
+            self.append(m)
+
+    def __add__(self, other):
+        if isinstance(other, (SkyModel, FoVBackgroundModel)):
+            self._check_name_unique(other)
+            return Models([*self, other])
+        if isinstance(other, list):
+            return Models([*self, *other])
+        raise TypeError(f"Invalid type: {other!r}")
+
+    def __setitem__(self, key, model):
+        idx = self.index(key)
+        self._check_name_unique(model, [n for n in self.names if n != list.__getitem__(self, idx).name])
+        list.__setitem__(self, idx, model)
+
+    def __delitem__(self, key):
+        list.__delitem__(self, self.index(key))
+
+    def index(self, key, *args):
+        if isinstance(key, str):
+            return self.names.index(key)
+        if isinstance(key, (int, np.integer)):
+            return int(key)
+        return list.index(self, key, *args)
+
+    def remove(self, key):
+        del self[key]
+
+    def freeze(self, model_type=None):
+        """core.py:1077-1087."""
+        for m in self:
+            m.freeze(model_type)
+
+    def unfreeze(self, model_type=None):
+        """Frozen status back to the model classes' defaults (core.py:1089-1099)."""
+        for m in self:
+            m.unfreeze(model_type)
+
+    @property
+    def frozen(self):
+        return all(p.frozen for p in self.parameters)
+
+    def set_parameters_bounds(self, tag, model_type, parameters_names=None, min=None, max=None, value=None):
+        """Limits / start values for the named parameters of the selected model types (core.py:1046-1075)."""
+        names = None if parameters_names is None else (
+            [parameters_names] if isinstance(parameters_names, str) else list(parameters_names))
+        for m in self.select(tag=tag, model_type=model_type):
+            sub = getattr(m, f"{model_type}_model", None)
+            for p in (sub.parameters if sub is not None else []):
+                if names is not None and p.name not in names:
+                    continue
+                if min is not None:
+                    p.min = min
+                if max is not None:
+                    p.max = max
+                if value is not None:
+                    p.value = value
+
+    def reassign(self, dataset_name, new_dataset_name):
+        """Copies of the models with ``dataset_name`` replaced in their ``datasets_names`` (core.py:410-447, 1106-1119)."""
+        old = dataset_name if isinstance(dataset_name, list) else [dataset_name]
+        new = new_dataset_name if isinstance(new_dataset_name, list) else [new_dataset_name]
         out = []
         for m in self:
-            if datasets_names is not None and m.datasets_names is not None:
-                wanted = [datasets_names] if isinstance(datasets_names, str) else datasets_names
-                if not any(n in m.datasets_names for n in wanted):
-                    continue
-            if name_substring is not None and name_substring not in m.name:
-                continue
-            if tag is not None and not any(t in m.tag for t in ([tag] if isinstance(tag, str) else tag)):
-                continue
-            out.append(m)
+            c = m.copy(name=m.name)
+            if c.datasets_names:
+                for a, b in zip(old, new):
+                    c.datasets_names = [n.replace(a, b) for n in c.datasets_names]
+            out.append(c)
         return Models(out)
+
+    def to_parameters_table(self):
+        """Rows ``{model, type, name, value, unit, error, min, max, frozen}`` of every parameter (core.py:702-708,
+        parameter.py:816-831; a list of dicts instead of an astropy Table)."""
+        rows = []
+        for m in self:
+            comps = [(t, getattr(m, f"{t}_model", None)) for t in ("spectral", "spatial")]
+            for t, sub in comps:
+                for p in (sub.parameters if sub is not None else []):
+                    rows.append(dict(model=m.name, type=t, name=p.name, value=p.value, unit=p.unit, error=p.error,
+                                     min=p.min, max=p.max, frozen=p.frozen))
+        return rows
+
+    def __str__(self):
+        lines = [f"{type(self).__name__}", ""]
+        for i, m in enumerate(self):
+            lines.append(f"Component {i}: {type(m).__name__}")
+            lines.append(f"  Name                      : {m.name}")
+            lines.append(f"  Datasets names            : {m.datasets_names}")
+            lines.append(f"  Spectral model type       : {type(m.spectral_model).__name__}")
+            sp = getattr(m, "spatial_model", None)
+            lines.append(f"  Spatial  model type       : {type(sp).__name__ if sp is not None else ''}")
+            lines.append("  Parameters:")
+            for row in Models([m]).to_parameters_table():
+                frozen = " (frozen)" if row["frozen"] else ""
+                err = "" if not row["error"] else f" +/- {row['error']:.2g}"
+                lines.append(f"    {row['name']:<24}{frozen:<9}: {row['value']:.4g}{err} {row['unit']}".rstrip())
+            lines.append("")
+        return "\n".join(lines)
 
     def __getitem__(self, key):
         if isinstance(key, str):
@@ -439,6 +587,8 @@ class Models(list):
             raise KeyError(f"No model named {key!r}; available: {self.names}")
         if isinstance(key, slice):
             return Models(list.__getitem__(self, key))
+        if isinstance(key, np.ndarray) and key.dtype == bool:  # core.py:785-790: boolean mask
+            return Models([m for m, keep in zip(self, key) if keep])
         return list.__getitem__(self, key)
 
     def copy(self):

@@ -220,3 +220,48 @@ def test_on_off_dataset_fits_round_trip(tmp_path):
     for attr in ("counts", "counts_off", "acceptance", "acceptance_off", "exposure"):
         np.testing.assert_array_equal(getattr(ds, attr).data, getattr(back, attr).data)
     np.testing.assert_array_equal(back.alpha.data, np.full(geom.data_shape, 1.0 / 3.0))
+
+
+def test_models_container_operations():
+    """``Models`` as the reference's ``DatasetModels`` / ``Models`` container (modeling/models/core.py:776-790, 855-949,
+    1046-1119, 1358-1380): unique names, selection, freezing by component, bounds, reassignment."""
+    ds = configs.make_c3(width=(6.0, 3.0), n_sources=6)
+    models = Models(ds.models)
+    assert len(models) == 7 and models.names[-1] == "c3-bkg"
+    points = models.select(tag="point", model_type="spatial")
+    assert len(points) >= 1 and all(isinstance(m.spatial_model, PointSpatialModel) for m in points)
+    assert models.select(tag="PointSpatialModel", model_type="spatial").names == points.names
+    assert models.select(tag="fov-bkg").names == ["c3-bkg"] and models.select(name_substring="src-0").names == models.names[:6]
+    assert models.select(datasets_names="other").names == models.names[:6]  # the background names its dataset
+    assert models[models.selection_mask(tag="sky-model")].names == models.names[:6]
+    with pytest.raises(ValueError, match="unique"):
+        models.append(models[0])
+    with pytest.raises(ValueError, match="unique"):
+        models + models[1]
+    extra = models[0].copy(name="extra")
+    both = models + extra
+    assert both.names[-1] == "extra" and len(models) == 7
+    models.insert(0, extra)
+    assert models.names[0] == "extra" and models.index("extra") == 0
+    del models["extra"]
+    assert "extra" not in models.names and len(models) == 7
+    models.freeze("spatial")
+    assert all(p.frozen for m in models[:6] for p in m.spatial_model.parameters)
+    assert not models.frozen and not models[0].frozen
+    assert models.select(frozen=True).names == []
+    models.unfreeze("spatial")
+    assert not models[0].spatial_model.lon_0.frozen
+    models.freeze()
+    assert models.frozen and models.select(frozen=True).names == models.names
+    models.unfreeze()
+    assert not models[0].spectral_model.amplitude.frozen and models[0].spectral_model.reference.frozen  # class defaults
+    models.set_parameters_bounds(tag="pl", model_type="spectral", parameters_names="index", min=1.0, max=4.0)
+    for m in models.select(tag="pl", model_type="spectral"):
+        assert (m.spectral_model.index.min, m.spectral_model.index.max) == (1.0, 4.0)
+    moved = models.reassign("c3", "c3-stacked")
+    assert moved["c3-bkg"].datasets_names == ["c3-stacked"] and models["c3-bkg"].datasets_names == ["c3"]
+    assert moved[0] is not models[0] and moved.names == models.names
+    table = models.to_parameters_table()
+    assert {r["model"] for r in table} == set(models.names) and table[0]["type"] == "spectral"
+    text = str(models)
+    assert text.startswith("Models\n\nComponent 0: SkyModel") and "lon_0" in text and "(frozen)" in text
