@@ -116,6 +116,43 @@ class SpectralModel(ModelBase):
             out.ravel()[i] = res[0]
         return out if np.ndim(energy_min) or np.ndim(energy_max) else float(out[0])
 
+    def energy_flux(self, energy_min, energy_max, **kwargs):
+        """``SpectralModel.energy_flux`` (spectral.py:423-445): the integral of E phi(E), analytic where the class has
+        ``evaluate_energy_flux``, else the log-log trapezoid of the reference; host numpy."""
+        emin, emax = np.asarray(energy_min, dtype=float), np.asarray(energy_max, dtype=float)
+        if hasattr(self, "evaluate_energy_flux"):
+            out = self.evaluate_energy_flux(emin, emax, *[p.value for p in self.parameters])
+        else:
+            out = integrate_loglog(lambda x: x * self(x), emin, emax, **kwargs)
+        return out if np.ndim(out) else float(out)
+
+
+def _pl_integral(energy_min, energy_max, index, amplitude, reference):
+    """``PowerLawSpectralModel.evaluate_integral`` (spectral.py:1039-1067), numpy on the host."""
+    val = -1 * index + 1
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        prefactor = amplitude * reference / val
+        integral = prefactor * ((energy_max / reference) ** val - (energy_min / reference) ** val)
+        flat = np.isclose(val, 0)
+        if np.any(flat):
+            integral = np.where(flat, amplitude * reference * np.log(energy_max / energy_min), integral)
+    return integral
+
+
+def integrate_loglog(func, energy_min, energy_max, ndecade=100):
+    """``integrate_spectrum`` + ``trapz_loglog`` (spectral.py:103-164, utils/integrate.py:8-49) on the host: composite
+    trapezoid in log-log space on ``ndecade`` geomspace nodes per decade.  (The per-bin integrals of the likelihood path
+    are K0's; this serves the host-side conveniences such as ``energy_flux``.)"""
+    energy_min, energy_max = np.asarray(energy_min, dtype=float), np.asarray(energy_max, dtype=float)
+    num = np.maximum(np.max(ndecade * np.log10(energy_max / energy_min)), 2)
+    x = np.moveaxis(np.geomspace(energy_min, energy_max, num=int(num), axis=-1), -1, 0)
+    y = func(x)
+    tiny = np.finfo(float).tiny
+    with np.errstate(invalid="ignore", divide="ignore"):
+        index = -np.log(np.clip(y[:-1] / y[1:], tiny, np.inf)) / np.log(np.clip(x[:-1] / x[1:], tiny, np.inf))
+    index[np.isnan(index)] = np.inf
+    return _pl_integral(x[:-1], x[1:], index, y[:-1], x[:-1]).sum(axis=0)
+
 
 def integration_nodes(edges, ndecade=100):
     """geomspace nodes of ``integrate_spectrum`` (spectral.py:132-134): the node count sits on a float
@@ -134,6 +171,14 @@ class PowerLawSpectralModel(SpectralModel):
     reference = Parameter("reference", "1 TeV", frozen=True)
 
     @staticmethod
+    def evaluate_energy_flux(energy_min, energy_max, index, amplitude, reference):
+        """spectral.py:1070-1100."""
+        val = -1 * float(index) + 2
+        if np.isclose(val, 0):  # index 2: the logarithmic case
+            return amplitude * reference**2 * np.log(energy_max / energy_min)
+        return amplitude * reference**2 / val * ((energy_max / reference) ** val - (energy_min / reference) ** val)
+
+    @staticmethod
     def evaluate(energy, index, amplitude, reference):
         return amplitude * np.power((energy / reference), -index)
 
@@ -143,6 +188,11 @@ class PowerLawNormSpectralModel(SpectralModel):
     tilt = Parameter("tilt", 0, frozen=True)
     norm = Parameter("norm", 1, unit="", interp="log")
     reference = Parameter("reference", "1 TeV", frozen=True)
+
+    @staticmethod
+    def evaluate_energy_flux(energy_min, energy_max, tilt, norm, reference):
+        """spectral.py:1182-1200."""
+        return PowerLawSpectralModel.evaluate_energy_flux(energy_min, energy_max, tilt, norm, reference)
 
     @staticmethod
     def evaluate(energy, tilt, norm, reference):

@@ -244,3 +244,25 @@ def test_parameter_lazy_factor_and_engine_mirror():
     release_mirror([p, q], vec)
     q.value = 3.0
     assert vec[1] == 2.5 and other[0] == 3.0 and p._mirrors == ()
+
+
+def test_energy_flux_against_the_reference_goldens():
+    """``SpectralModel.energy_flux`` on the host (spectral.py:423-445; analytic for the power laws :1070-1100,
+    :1182-1200, the log-log trapezoid otherwise): ``eflux_1_10TeV`` and ``val_at_2TeV`` of the reference's
+    ``TEST_MODELS`` (modeling/models/tests/test_spectral.py:59-190)."""
+    from gammapy_b200.modeling.models import (ExpCutoffPowerLawSpectralModel, LogParabolaSpectralModel,
+                                              PowerLawNormSpectralModel, PowerLawSpectralModel)
+
+    cases = [
+        (PowerLawSpectralModel(index=2.3, amplitude=4, reference=1), 4 * 2.0 ** (-2.3), 6.650836884969039),
+        (PowerLawSpectralModel(index=2, amplitude=4, reference=1), 1.0, 9.210340371976184),
+        (PowerLawNormSpectralModel(tilt=2, norm=4, reference=1), 1.0, 9.210340371976184),
+        (ExpCutoffPowerLawSpectralModel(index=1.6, amplitude=4, reference=1, lambda_=0.1), 1.080321705479446, 9.901735870666526),
+        (LogParabolaSpectralModel(alpha=2.3, amplitude=4, reference=1, beta=0.5), 0.6387956571420305, 3.9586515834989267),
+    ]
+    for model, val_at_2, eflux in cases:
+        assert_allclose(model(2.0), val_at_2, rtol=1e-12)
+        assert_allclose(model.energy_flux(1.0, 10.0), eflux, rtol=1e-7)  # the reference's own tolerance
+    lp = cases[-1][0]
+    parts = lp.energy_flux(np.array([1.0, 3.0]), np.array([3.0, 10.0]))
+    assert parts.shape == (2,) and abs(parts.sum() - lp.energy_flux(1.0, 10.0)) < 1e-4 * parts.sum()
