@@ -333,15 +333,11 @@ class MapDataset:
             counts = float(np.asarray(self._counts.data, float)[mask].sum())
             if self._background is not None:
                 background = float(np.asarray(self._background.data, float)[mask].sum())
+                from .stats import cash_sqrt_ts
+
                 mu_bkg = float(npred_background[mask].sum())
-
-                def cash(n_on, mu_on):  # stats/fit_statistics.py:29-79
-                    mu_on = max(mu_on, 1e-25)
-                    return 2 * (mu_on - n_on * np.log(mu_on))
-
                 excess = counts - mu_bkg
-                ts = max(cash(counts, mu_bkg) - cash(counts, counts), 0.0)
-                sqrt_ts = float(np.sign(excess) * np.sqrt(ts))
+                sqrt_ts = float(cash_sqrt_ts(counts, mu_bkg))
         info.update(counts=int(counts), excess=float(excess), sqrt_ts=sqrt_ts, background=float(background))
         info["npred"] = float(self.npred().data[mask].sum()) if (self.models or not np.isnan(background)) else np.nan
         info["npred_background"] = float(npred_background[mask].sum()) if npred_background is not None else np.nan

@@ -108,6 +108,22 @@ def norm_bounds_cuda(counts, background, model):
     return out[0], out[1], out[2]
 
 
+def cash(n_on, mu_on, truncation_value=1e-25):
+    """Per-bin Cash statistic 2 (mu - n log mu) with mu truncated from below (stats/fit_statistics.py:29-79); host numpy."""
+    n_on, mu_on = np.asarray(n_on, dtype=float), np.asarray(mu_on, dtype=float)
+    mu_on = np.where(mu_on <= truncation_value, truncation_value, mu_on)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return 2 * (mu_on - n_on * np.log(mu_on))
+
+
+def cash_sqrt_ts(n_on, mu_bkg):
+    """``CashCountsStatistic(n_on, mu_bkg).sqrt_ts`` (stats/counts_statistic.py:44-58, 250-288): the significance of the
+    excess n_on - mu_bkg for a known background, sign of the excess times sqrt(stat_null - stat_max)."""
+    n_on, mu_bkg = np.asarray(n_on, dtype=float), np.asarray(mu_bkg, dtype=float)
+    ts = np.clip(cash(n_on, mu_bkg + 0) - cash(n_on, n_on), 0, None)
+    return np.sign(n_on - mu_bkg) * np.sqrt(ts)
+
+
 def get_fit_statistics_compiled(backend=None):
     backend = backend or COMPILATION_BACKEND_DEFAULT
     if backend != "cuda":

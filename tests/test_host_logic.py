@@ -266,3 +266,19 @@ def test_energy_flux_against_the_reference_goldens():
     lp = cases[-1][0]
     parts = lp.energy_flux(np.array([1.0, 3.0]), np.array([3.0, 10.0]))
     assert parts.shape == (2,) and abs(parts.sum() - lp.energy_flux(1.0, 10.0)) < 1e-4 * parts.sum()
+
+
+def test_cash_counts_statistic_goldens():
+    """``cash_sqrt_ts`` (what ``MapDataset.info_dict`` reports) against the reference's ``test_cash_basic`` values
+    (stats/tests/test_counts_statistic.py:9-29): (n_on, mu_bkg) -> excess, sqrt(TS)."""
+    from gammapy_b200.stats import cash, cash_sqrt_ts
+
+    for n_on, mu_bkg, excess, sqrt_ts in [(1, 2, -1.0, -0.78339367), (5, 1, 4.0, 2.84506224), (10, 5, 5.0, 1.96543726),
+                                          (100, 23, 77.0, 11.8294207), (1, 20, -19, -5.65760863)]:
+        assert n_on - mu_bkg == excess
+        assert_allclose(cash_sqrt_ts(n_on, mu_bkg), sqrt_ts, atol=1e-5)
+    grid = cash_sqrt_ts(5 * np.ones((3, 2, 4)), np.ones((3, 2, 4)))
+    assert grid.shape == (3, 2, 4) and np.allclose(grid, 2.84506224, atol=1e-5)
+    assert cash_sqrt_ts(0, 0) == 0.0                       # no counts, no background: mu truncated, TS = 0
+    assert_allclose(cash(0, 0.0), 2e-25)
+    assert_allclose(cash(3, 2.0), 2 * (2.0 - 3 * np.log(2.0)))
