@@ -72,3 +72,35 @@ def test_a_shifted_reference_pixel_is_not_a_shifted_reference_point():
     assert abs(shifted.center_skydir.lat - 20.0) < 1e-12 and abs(oblique.center_skydir.lat - 20.0) < 1e-12
     ratio = shifted.solid_angle()[50, 50] / oblique.solid_angle()[50, 50]
     assert abs(ratio - np.cos(20.0 * DEG)) < 1e-4
+
+
+def test_reference_spatial_model_checks_on_oblique_geometries():
+    """The reference's data-free spatial-model checks that live on geometries off the equator
+    (modeling/models/tests/test_spatial.py:40-59 ``test_sky_point_source``: a point source at (2.5, 2.5) on a map about
+    (2.4, 2.3) integrates to 1; :75-88 ``test_sky_gaussian``: an elongated Gaussian about (2, 2) is normalised to 1e-3
+    over a 20 deg map -- there on an AIT map, here on the oblique CAR map the same ``WcsGeom.create`` call builds by
+    default): coordinates and solid angles of the oblique projection, host mirror and oracle."""
+    from gammapy_b200.modeling.models import GaussianSpatialModel
+    from oracle import spatial
+
+    og = ImageGeom.create(skydir=(2.4, 2.3), npix=(10, 10), binsz=0.3)
+    w = spatial.point_integrate_geom({"type": "point", "lon_0": 2.5, "lat_0": 2.5}, og)
+    assert_sum = w.sum()
+    assert abs(assert_sum - 1.0) < 1e-12 and np.count_nonzero(w) == 4
+    px, py = og.world_to_pix(2.5, 2.5)
+    iy, ix = np.unravel_index(np.argmax(w), w.shape)
+    assert abs(ix - px) <= 0.5 and abs(iy - py) <= 0.5
+    g = WcsGeom.create(skydir=(2.4, 2.3), npix=(10, 10), binsz=0.3, frame="icrs")
+    gx, gy = g.coord_to_pix((2.5, 2.5))
+    assert abs(gx - px) < 1e-10 and abs(gy - py) < 1e-10
+
+    big = WcsGeom.create(binsz=0.05, width=(20, 20), skydir=(2, 2), frame="galactic")
+    obig = ImageGeom.create(skydir=(2.0, 2.0), binsz=0.05, npix=(400, 400))
+    model = GaussianSpatialModel(lon_0=2, lat_0=2, sigma=3, e=0.8, phi=30, frame="galactic")
+    c = big.get_coord()
+    total = np.sum(model(c["lon"], c["lat"]) * big.solid_angle())
+    assert abs(total - 1.0) < 1e-3
+    lon, lat = obig.get_coord()
+    ototal = np.sum(spatial.gauss_evaluate(lon, lat, 2.0, 2.0, 3.0, 0.8, 30.0) * obig.solid_angle())
+    assert abs(ototal - 1.0) < 1e-3 and abs(total - ototal) < 1e-9
+    assert model.evaluation_radius == 15.0
