@@ -282,3 +282,23 @@ def test_cash_counts_statistic_goldens():
     assert cash_sqrt_ts(0, 0) == 0.0                       # no counts, no background: mu truncated, TS = 0
     assert_allclose(cash(0, 0.0), 2e-25)
     assert_allclose(cash(3, 2.0), 2 * (2.0 - 3 * np.log(2.0)))
+
+
+def test_edisp_kernel_builders_against_the_reference_goldens():
+    """``EDispKernel.from_gauss`` / ``from_diagonal_response`` against the reference's data-free values
+    (irf/edisp/tests/test_kernel.py:26-70): the reco-summed response of a Gaussian kernel with sigma 0.2, bias 0.1
+    (rtol 1e-3, the reference's own tolerance -- it integrates an interpolated migra grid, here the error function is
+    integrated directly) and the 0 / 1 pattern of the diagonal response between different axes."""
+    from gammapy_b200 import EDispKernel, MapAxis
+
+    energy_axis = MapAxis.from_energy_bounds("0.1 TeV", "10 TeV", nbin=3)
+    energy_axis_true = MapAxis.from_energy_bounds("0.08 TeV", "20 TeV", nbin=5, name="energy_true")
+    edisp = EDispKernel.from_gauss(energy_axis_true, energy_axis, sigma=0.2, bias=0.1)
+    assert edisp.pdf_matrix.shape == (5, 3)
+    assert_allclose(edisp.pdf_matrix.sum(axis=1), [0.97142, 1.0, 1.0, 1.0, 0.12349], rtol=1e-3)
+    e_true = MapAxis.from_energy_edges([0.5, 1, 2, 4, 6], name="energy_true")
+    diag = EDispKernel.from_diagonal_response(e_true, MapAxis.from_energy_edges([2, 4, 6]))
+    assert diag.pdf_matrix.shape == (4, 2)
+    np.testing.assert_array_equal(diag.pdf_matrix, [[0, 0], [0, 0], [1, 0], [0, 1]])
+    square = EDispKernel.from_diagonal_response(e_true, e_true.copy(name="energy"))
+    assert square.pdf_matrix[0][0] == 1 and square.pdf_matrix[2][0] == 0 and square.pdf_matrix.sum() == 4
