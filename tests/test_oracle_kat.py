@@ -247,3 +247,31 @@ def test_golden_fixture_file():
     lp = dict(s["logpar"], type="lp")
     assert_allclose(spectral.integral(lp, [1.0], [10.0]), lp["integral_1_10TeV"], rtol=1e-5)
     assert_allclose(spatial.disk_evaluate(1.0, 46.0, 1.0, 45.0, 2.0), gold["spatial"]["disk_value"], rtol=1e-7)
+
+
+def test_psf_kernel_from_disk_models_to_image_golden():
+    """irf/psf/tests/test_kernel.py:39-67 ``test_psf_kernel_to_image``: kernels built from two disk models
+    (``PSFKernel.from_spatial_model``, irf/psf/kernel.py:99-126: odd-sized geometry, 4 x upsampled ``integrate_geom`` with
+    oversampling factor 1, block sum) and weighted over energy with a power law of index 2 (``to_image``, :165-212).
+    Pins the oracle's disk evaluation with its smoothed edge, the upsample / block-sum chain and the solid angles at
+    the reference's own 1e-5."""
+    from oracle.wcs import ImageGeom
+
+    geom = ImageGeom.create(skydir=(0.0, 0.0), binsz=0.1, npix=(50, 50)).to_odd_npix(max_radius=2.5)
+    assert (geom.nx, geom.ny) == (51, 51)
+    up = geom.upsample(4)
+    planes = []
+    for r_0 in (0.5, 0.2):
+        model = {"type": "disk", "lon_0": geom.center_skydir[0], "lat_0": geom.center_skydir[1], "r_0": r_0, "e": 0.0,
+                 "phi": 0.0, "edge_width": 0.01}
+        fine = spatial.integrate_geom(model, up, oversampling_factor=1)
+        planes.append(fine.reshape(geom.ny, 4, geom.nx, 4).sum(axis=(1, 3)))
+    planes = np.array(planes)
+    planes /= planes.sum(axis=(1, 2), keepdims=True)  # PSFKernel normalises every plane (irf/psf/kernel.py:70-80)
+    edges = np.geomspace(1.0, 10.0, 3)
+    flux = 1 / edges[:-1] - 1 / edges[1:]  # integral of E^-2 over each bin
+    for exposure, want in (([1.0, 1.0], (0.028096, 0.009615)), ([1.0, 2.0], (0.037555, 0.007752))):
+        w = flux * np.array(exposure)
+        image = (planes * (w / w.sum())[:, None, None]).sum(axis=0)
+        assert_allclose(image.sum(), 1.0, atol=1e-5)
+        assert_allclose((image[25, 25], image[22, 22], image[20, 20]), want + (0.0,), atol=1e-5)
