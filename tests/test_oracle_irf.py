@@ -85,3 +85,28 @@ def test_containment_radius_against_the_reference_goldens():
     # (midpoint sums over 0.01 deg rad bins: a few per cent above the true containment, so the radius comes out low)
     np.testing.assert_allclose(r999, np.array([0.04, 0.07, 0.1]) * np.sqrt(-2 * np.log(0.001)), rtol=0.1)
     np.testing.assert_allclose(fine.containment_radius(0.999), r999, rtol=1e-12)
+
+
+def test_get_psf_kernel_multiscale_reference_check():
+    """datasets/tests/test_map.py:2437-2459 ``test_get_psf_kernel_multiscale`` (data-free): every plane of the kernel of
+    a Gaussian PSF map with sigma 0.1 / 0.2 / 0.3 deg is cut at its own 99.9 % containment radius (the two wide ones
+    hit the end of the default rad axis), and ``max_radius`` sizes the kernel map; host mirror and oracle, which must
+    agree exactly in this position-independent case."""
+    from gammapy_b200 import MapAxis, PSFMap, WcsGeom
+    from gammapy_b200.utils import DEG, angular_separation
+
+    energy_axis = MapAxis.from_edges(np.logspace(-1.0, 1.0, 4), unit="TeV", name="energy_true", interp="log")
+    geom = WcsGeom.create(binsz=0.02, width=4.0, axes=[energy_axis])
+    psf = PSFMap.from_gauss(energy_axis, sigma=[0.1, 0.2, 0.3])
+    wide = psf.get_psf_kernel(geom=geom, max_radius=3.0)
+    assert abs(wide.data.shape[-1] * 0.02 - 2 * 3.0) <= 0.02
+    kernel = psf.get_psf_kernel(geom=geom)
+    k = kernel.data.shape[-1]
+    off = (np.arange(k) - (k - 1) / 2) * 0.02
+    sep = angular_separation(-off[None, :] * DEG, off[:, None] * DEG, 0.0, 0.0) / DEG
+    for image, width in zip(kernel.data, [0.74, 1.34, 1.34]):
+        assert np.all(image[sep > width] == 0) and np.any(image[sep <= width] > 0)
+    np.testing.assert_allclose(kernel.data.sum(axis=(1, 2)), 1.0, rtol=1e-12)
+    assert (kernel.data[0] > 0).sum() < (kernel.data[1] > 0).sum() <= (kernel.data[2] > 0).sum()
+    want = oirf.psf_kernel_at(psf.data, psf.rad_axis.edges, None, (0.0, 0.0), 0.02, (0.0, 0.0))
+    np.testing.assert_array_equal(kernel.data, want)
