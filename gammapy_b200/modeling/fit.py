@@ -11,6 +11,8 @@ import logging
 
 import numpy as np
 
+from .parameter import store_covariance
+
 log = logging.getLogger(__name__)
 
 __all__ = ["Fit", "FitResult", "OptimizeResult", "CovarianceResult"]
@@ -418,6 +420,7 @@ class Fit:
         if success:
             for p, var in zip(like.free, np.diag(cov)):
                 p.error = float(np.sqrt(var))
+            store_covariance(like.free, cov)  # what Models.covariance assembles (fit.py:172-176, 286-292)
         self._last_like = like
         return CovarianceResult(matrix=cov, success=success, message=message)
 

@@ -27,15 +27,17 @@ The layout, for a file written by either side::
         spectral: {type: PowerLawNormSpectralModel, parameters: [...]}
 
 Only the model classes of the accelerated path exist here (the registries below); a component of any other type raises
-``NotImplementedError`` naming it.  The covariance side file of the reference (``<stem>_covariance.dat``, an
-``astropy.table`` text format) is neither written nor read: a ``covariance:`` entry is ignored with a warning, the
-parameter errors in the YAML are kept.
+``NotImplementedError`` naming it.  The covariance goes to the side file of the reference, ``<stem>_covariance.dat``
+(``_write_models``, core.py:169-204; ``read_covariance`` / ``write_covariance``, :716-757): the text layout of
+``astropy.table`` ``ascii.fixed_width`` with ``|`` as the delimiter -- a header row ``Parameters | 0 | 1 | ...`` and one
+row per parameter ``model.component.name | values`` -- written and parsed here without astropy.
 """
 import logging
 import math
 import os
 import warnings
 
+import numpy as np
 import yaml
 
 from .models import (
@@ -262,51 +264,100 @@ def _set_links(models):
 
 
 # -- Models ------------------------------------------------------------------------------------------------
-def models_to_dict(models, full_output=False):
+def models_to_dict(models, full_output=False, covariance_file=None):
     update_link_label(models.parameters)
-    return {"components": [model_to_dict(m, full_output) for m in models]}
+    data = {"components": [model_to_dict(m, full_output) for m in models]}
+    if covariance_file is not None:
+        data["covariance"] = str(covariance_file)
+    return data
 
 
-def models_from_dict(data):
-    if "covariance" in data:
-        warnings.warn("the covariance side file is not read: parameter errors come from the YAML entries")
+def models_from_dict(data, path=""):
     models = Models([model_from_dict(c) for c in data["components"]])
     _set_links(models)
+    if "covariance" in data:
+        filename = os.path.join(str(path), str(data["covariance"]))
+        try:
+            read_covariance(models, filename)
+        except (OSError, ValueError) as exc:  # core.py:604-615: a warning, the errors of the YAML entries remain
+            log.warning(f"Impossible to read the covariance correctly: {exc}. Covariance will be created from errors "
+                        "and non-diagonal terms ignored.")
     return models
+
+
+def write_covariance(models, filename):
+    """``ascii.fixed_width`` with ``|`` delimiters (right-justified cells, as astropy writes them)."""
+    names = models.parameters_unique_names
+    matrix = models.covariance
+    header = ["Parameters"] + [str(i) for i in range(len(names))]
+    rows = [[name] + [repr(float(v)) for v in row] for name, row in zip(names, matrix)]
+    widths = [max(len(r[k]) for r in [header] + rows) for k in range(len(header))]
+    with open(str(filename), "w") as fh:
+        for r in [header] + rows:
+            fh.write("| " + " | ".join(cell.rjust(w) for cell, w in zip(r, widths)) + " |\n")
+
+
+def read_covariance(models, filename):
+    with open(str(filename)) as fh:
+        lines = [ln.strip() for ln in fh if ln.strip()]
+    cells = [[c.strip() for c in ln.strip("|").split("|")] for ln in lines]
+    if not cells or cells[0][0] != "Parameters":
+        raise ValueError(f"{filename}: not a covariance table (first column must be 'Parameters')")
+    matrix = np.array([[float(c) for c in row[1:]] for row in cells[1:]], dtype=float)
+    n = len(models.parameters)
+    if matrix.shape != (n, n):
+        raise ValueError(f"{filename}: covariance of shape {matrix.shape} for {n} parameters")
+    errors = [p.error for p in models.parameters]
+    models.covariance = matrix
+    for p, e in zip(models.parameters, errors):  # the YAML entries stay authoritative for the errors
+        p.error = e
 
 
 def models_to_yaml(models, full_output=False):
     return yaml.safe_dump(models_to_dict(models, full_output), **YAML_FORMAT)
 
 
-def models_from_yaml(text):
+def models_from_yaml(text, path=""):
     data = yaml.safe_load(text)
     data.pop("checksum", None)
     data.pop("metadata", None)
-    return models_from_dict(data)
+    return models_from_dict(data, path=path)
 
 
-def write_models(models, path, overwrite=False, full_output=False):
+def _has_covariance(models):
+    return any(getattr(p, "_cov_partners", None) is not None for p in models.parameters)
+
+
+def write_models(models, path, overwrite=False, full_output=False, write_covariance_file=True):
     path = str(path)
     if os.path.exists(path) and not overwrite:
         raise OSError(f"File exists already: {path}")
-    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    folder = os.path.dirname(os.path.abspath(path))
+    os.makedirs(folder, exist_ok=True)
+    covariance_file = None
+    if write_covariance_file and len(models.parameters) and _has_covariance(models):
+        covariance_file = os.path.splitext(os.path.basename(path))[0] + "_covariance.dat"
+        write_covariance(models, os.path.join(folder, covariance_file))
     with open(path, "w") as fh:
-        fh.write(models_to_yaml(models, full_output))
+        fh.write(yaml.safe_dump(models_to_dict(models, full_output, covariance_file), **YAML_FORMAT))
 
 
 def read_models(path):
     with open(str(path)) as fh:
-        return models_from_yaml(fh.read())
+        return models_from_yaml(fh.read(), path=os.path.dirname(os.path.abspath(str(path))))
 
 
 def _install():
     """The reference's method names on the model classes."""
     Models.to_dict = lambda self, full_output=False: models_to_dict(self, full_output)
-    Models.from_dict = staticmethod(lambda data, path="": models_from_dict(data))
+    Models.from_dict = staticmethod(lambda data, path="": models_from_dict(data, path=path))
     Models.to_yaml = lambda self, full_output=False: models_to_yaml(self, full_output)
-    Models.from_yaml = staticmethod(lambda text, path="": models_from_yaml(text))
-    Models.write = lambda self, path, overwrite=False, full_output=False, **kwargs: write_models(self, path, overwrite, full_output)
+    Models.from_yaml = staticmethod(lambda text, path="": models_from_yaml(text, path=path))
+    Models.write = lambda self, path, overwrite=False, full_output=False, write_covariance=True, **kwargs: write_models(
+        self, path, overwrite, full_output, write_covariance)
+    Models.write_covariance = lambda self, filename, **kwargs: write_covariance(self, filename)
+    Models.read_covariance = lambda self, path, filename="_covariance.dat", **kwargs: read_covariance(
+        self, os.path.join(str(path), filename))
     Models.read = staticmethod(read_models)
     SkyModel.to_dict = lambda self, full_output=False: model_to_dict(self, full_output)
     SkyModel.from_dict = staticmethod(model_from_dict)

@@ -491,6 +491,36 @@ class Models(list):
     def names(self):
         return [m.name for m in self]
 
+    @property
+    def parameters_unique_names(self):
+        """``model_name.component.parameter`` of every parameter, model by model (core.py:531-540)."""
+        out = []
+        for m in self:
+            for t in ("spectral", "spatial"):
+                sub = getattr(m, f"{t}_model", None)
+                out += [f"{m.name}.{t}.{p.name}" for p in (sub.parameters if sub is not None else [])]
+        return out
+
+    @property
+    def covariance(self):
+        """Covariance matrix over ``self.parameters`` (value space) as the last ``Fit.covariance`` left it on the parameter
+        objects; parameters that were frozen or not part of that fit have ``error ** 2`` on the diagonal."""
+        from .parameter import covariance_of
+
+        return covariance_of(self.parameters)
+
+    @covariance.setter
+    def covariance(self, matrix):
+        from .parameter import store_covariance
+
+        pars = list(self.parameters)
+        matrix = np.asarray(matrix, dtype=float)
+        if matrix.shape != (len(pars), len(pars)):
+            raise ValueError(f"covariance must have shape {(len(pars), len(pars))}, got {matrix.shape}")
+        store_covariance(pars, matrix)
+        for p, var in zip(pars, np.diag(matrix)):
+            p.error = float(np.sqrt(var)) if var >= 0 else float("nan")
+
     def selection_mask(self, name_substring=None, datasets_names=None, tag=None, model_type=None, frozen=None):
         """Boolean mask of the models that meet all conditions (modeling/models/core.py:888-949)."""
         tags = None if not tag else ([tag] if isinstance(tag, str) else list(tag))

@@ -36,6 +36,45 @@ def bind_mirror(parameters):
     return vec
 
 
+def store_covariance(parameters, matrix):
+    """Remember the covariance of ``parameters`` (the free parameters of a fit, value space) on the parameter objects:
+    each keeps its row and weak references to the partners, so that any ``Models`` / ``Parameters`` view over them can
+    assemble its matrix later (``covariance_of``), as the reference pushes sub-covariances down to the models
+    (modeling/models/core.py ``DatasetModels.covariance`` setter, modeling/covariance.py)."""
+    import weakref
+
+    matrix = np.asarray(matrix, dtype=float)
+    refs = tuple(weakref.ref(p) for p in parameters)
+    for i, p in enumerate(parameters):
+        p._cov_partners = refs
+        p._cov_row = matrix[i].copy()
+
+
+def covariance_of(parameters):
+    """Covariance matrix over ``parameters`` (duplicates of a linked parameter get identical rows): the stored rows where
+    both partners belong to the list, ``error ** 2`` on the diagonal otherwise, 0 for pairs never fitted together."""
+    parameters = list(parameters)
+    n = len(parameters)
+    out = np.zeros((n, n))
+    where = {}
+    for j, q in enumerate(parameters):
+        where.setdefault(id(q), []).append(j)
+    for i, p in enumerate(parameters):
+        partners, row = getattr(p, "_cov_partners", None), getattr(p, "_cov_row", None)
+        filled = False
+        if partners is not None:
+            for ref, value in zip(partners, row):
+                q = ref()
+                if q is not None and id(q) in where:
+                    for j in where[id(q)]:
+                        out[i, j] = value
+                    filled = filled or q is p
+        if not filled:
+            for j in where[id(p)]:
+                out[i, j] = p.error ** 2
+    return out
+
+
 def release_mirror(parameters, vec):
     for p in parameters:
         p._mirrors = tuple(m for m in p._mirrors if m[0] is not vec)
@@ -50,6 +89,8 @@ class Parameter:
     def __getstate__(self):  # copies and pickles are not bound to anybody's vector
         state = dict(self.__dict__)
         state.pop("_mirrors", None)
+        state.pop("_cov_partners", None)  # (weak references: a copy keeps its error, not its correlations)
+        state.pop("_cov_row", None)
         return state
 
     def __setstate__(self, state):

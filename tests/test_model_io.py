@@ -265,3 +265,55 @@ def test_models_container_operations():
     assert {r["model"] for r in table} == set(models.names) and table[0]["type"] == "spectral"
     text = str(models)
     assert text.startswith("Models\n\nComponent 0: SkyModel") and "lon_0" in text and "(frozen)" in text
+
+
+def test_fit_covariance_on_the_models_and_in_the_side_file(tmp_path):
+    """``Fit.run`` leaves the covariance where ``models.covariance`` finds it (modeling/fit.py:168-176, 286-292) and
+    ``Models.write`` puts it into ``<stem>_covariance.dat`` in the reference's ``ascii.fixed_width`` layout
+    (modeling/models/core.py:169-204, 716-757); read back, the matrix and the errors are the same.  The likelihood is a
+    quadratic form evaluated on the CPU (``ShardedDatasets(local_stat=...)``), whose covariance is known exactly."""
+    from gammapy_b200.distributed import ShardedDatasets
+    from gammapy_b200.modeling import Fit
+
+    model = SkyModel(spatial_model=PointSpatialModel(lon_0=0.1, lat_0=0.2, frame="galactic"),
+                     spectral_model=ExpCutoffPowerLawSpectralModel(index=2.0, amplitude=1e-12, reference=1, lambda_=0.1),
+                     name="src")
+    model.spatial_model.lon_0.frozen = model.spatial_model.lat_0.frozen = True
+    model.spectral_model.lambda_.frozen = True
+    pars = list(model.parameters)
+    names = [p.name for p in pars]
+    hess = np.array([[80.0, 24.0], [24.0, 60.0]])  # second derivatives of the statistic in (index, ln amplitude)
+
+    def local_stat(values):
+        d = np.stack([values[:, names.index("index")] - 2.3, np.log(values[:, names.index("amplitude")] / 2e-12)], axis=1)
+        return 0.5 * np.einsum("bi,ij,bj->b", d, hess, d)
+
+    sharded = ShardedDatasets(None, local_stat=local_stat, global_models=[model], local_parameters=pars)
+    result = Fit().run(sharded)
+    assert result.success, result.message
+    models = Models([model])
+    cov = models.covariance
+    assert cov.shape == (len(pars), len(pars)) and models.parameters_unique_names[0] == "src.spectral.index"
+    i, a = names.index("index"), names.index("amplitude")
+    amp = model.spectral_model.amplitude.value
+    want = 2.0 * np.linalg.inv(hess) * np.outer([1.0, amp], [1.0, amp])  # errordef 1 on 2 log L; d amplitude = amp d ln
+    # (the statistic is quadratic in ln(amplitude), Hesse differentiates in amplitude: agreement to the curvature of the log)
+    np.testing.assert_allclose(cov[np.ix_([i, a], [i, a])], want, rtol=1e-2)
+    np.testing.assert_allclose(np.sqrt(cov[i, i]), model.spectral_model.index.error, rtol=1e-12)
+    frozen = [k for k, p in enumerate(pars) if p.frozen]
+    assert np.all(cov[frozen][:, [i, a]] == 0) and np.all(cov[frozen, frozen] == 0)
+    path = tmp_path / "fitted.yaml"
+    models.write(path)
+    text = (tmp_path / "fitted_covariance.dat").read_text().splitlines()
+    assert text[0].replace(" ", "").startswith("|Parameters|0|1|") and text[1].replace(" ", "").startswith("|src.spectral.index|")
+    assert "covariance: fitted_covariance.dat" in path.read_text()
+    back = Models.read(path)
+    np.testing.assert_array_equal(back.covariance, cov)
+    assert back[0].spectral_model.index.error == model.spectral_model.index.error
+    # a copy keeps the errors, not the correlations; files without covariance are read as before
+    clone = models.copy()
+    assert clone.covariance[i, a] == 0 and clone.covariance[i, i] == pytest.approx(cov[i, i])
+    models.write(tmp_path / "plain.yaml", write_covariance=False)
+    assert "covariance" not in (tmp_path / "plain.yaml").read_text()
+    (tmp_path / "fitted_covariance.dat").write_text("garbage\n")
+    assert Models.read(path).covariance[i, a] == 0  # unreadable side file: a warning, diagonal from the errors
