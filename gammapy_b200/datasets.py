@@ -291,6 +291,99 @@ class MapDataset:
 
     stat_sum = stat_sum_likelihood
 
+    # -- stacking (data reduction before a fit; host arithmetic) ----------------------------------------------------
+    @classmethod
+    def from_geoms(cls, geom, geom_exposure=None, geom_psf=None, geom_edisp=None, name=None, **kwargs):
+        """Zero-filled dataset on the given geometries (datasets/map.py:883-945): counts, background, an all-False
+        ``mask_safe`` and, when its geometry is given, the exposure; IRFs are taken over by the first ``stack``."""
+        del geom_psf, geom_edisp
+        kwargs.setdefault("counts", Map.from_geom(geom, unit=""))
+        kwargs.setdefault("background", Map.from_geom(geom, unit=""))
+        kwargs.setdefault("mask_safe", Map.from_geom(geom, unit="", dtype=bool))
+        if geom_exposure is not None:
+            kwargs.setdefault("exposure", Map.from_geom(geom_exposure, unit="m2 s"))
+        return cls(name=name, **kwargs)
+
+    @property
+    def mask_safe_image(self):
+        """``mask_safe`` reduced over energy with a logical or (datasets/map.py:1050-1056), or None."""
+        if self.mask_safe is None:
+            return None
+        return np.asarray(self.mask_safe.data, bool).any(axis=0)
+
+    def _background_for_stacking(self):
+        """``npred_background()`` (datasets/map.py:790-813): the background map itself without a background model,
+        else the GPU's evaluation of it."""
+        if self.background_model is None:
+            return np.asarray(self._background.data, float)
+        return np.asarray(self.npred_background().data, float)
+
+    def _irf_weight(self):
+        """Exposure weight per true-energy bin for the IRF average: the exposure summed over the safe image pixels
+        (the reference carries an exposure map inside every IRF map, filled by the makers with the exposure at the IRF
+        pixel; for the position-independent IRFs handled here that is one number per true-energy bin)."""
+        data = np.asarray(self._exposure.data, float)
+        safe = self.mask_safe_image
+        if safe is not None:
+            data = data * safe[np.newaxis]
+        return data.sum(axis=(1, 2))
+
+    def stack(self, other, nan_to_num=True):
+        """Stack ``other`` onto this dataset in place (datasets/map.py:1104-1210): its counts, exposure and predicted
+        background enter where its ``mask_safe`` is true, the safe and fit masks are or-ed, position-independent PSF /
+        edisp are averaged with exposure weights.  The background model of ``self`` is folded into the background map
+        (as the reference does through ``npred_background()``), so assign the models of the stacked dataset afterwards."""
+        if isinstance(other, MapDatasetOnOff) or isinstance(self, MapDatasetOnOff):
+            raise NotImplementedError("stacking of MapDatasetOnOff is outside the accelerated path")
+        o_safe = None if other.mask_safe is None else np.asarray(other.mask_safe.data, bool)
+        if o_safe is not None and not o_safe.any():
+            return
+
+        def add(target, values, weights):
+            values = np.asarray(values, float)
+            if nan_to_num:
+                values = np.where(np.isfinite(values), values, 0.0)
+            return target + (values if weights is None else values * weights)
+
+        w_self = self._irf_weight() if self._exposure is not None else None
+        w_other = other._irf_weight() if other._exposure is not None else None
+        if self._counts is not None and other._counts is not None:
+            self.counts = Map.from_geom(self._geom, data=add(np.asarray(self._counts.data, float), other._counts.data, o_safe),
+                                        dtype=float)
+        if self._exposure is not None and other._exposure is not None:
+            o_img = None if o_safe is None else o_safe.any(axis=0)[np.newaxis]
+            self.exposure = Map.from_geom(self._exposure.geom, unit="m2 s",
+                                          data=add(np.asarray(self._exposure.data, float), other._exposure.data, o_img))
+        if self._background is not None and other._background is not None:
+            stacked = add(self._background_for_stacking(), other._background_for_stacking(), o_safe)
+            self._models = None if self._models is None else Models(
+                [m for m in self._models if not isinstance(m, FoVBackgroundModel)]) or None
+            self.background = Map.from_geom(self._geom, data=stacked, dtype=float)
+        for attr in ("psf", "edisp"):
+            mine, theirs = getattr(self, attr), getattr(other, attr)
+            if theirs is None:
+                continue
+            if mine is None or w_self is None or not np.any(w_self):
+                setattr(self, attr, theirs)   # the first dataset stacked onto an empty one brings its IRFs
+                continue
+            if not (mine.has_single_spatial_bin and theirs.has_single_spatial_bin):
+                raise NotImplementedError(f"stacking {attr} maps with a spatial grid is outside the accelerated path")
+            setattr(self, attr, _average_irf(attr, mine, theirs, w_self, w_other))
+        if self.mask_safe is not None and o_safe is not None:
+            self.mask_safe = Map.from_geom(self._geom, data=np.asarray(self.mask_safe.data, bool) | o_safe, dtype=bool)
+        if other.mask_fit is not None:
+            o_fit = np.asarray(other.mask_fit.data, bool)
+            mine = o_fit if self.mask_fit is None else (np.asarray(self.mask_fit.data, bool) | o_fit)
+            self.mask_fit = Map.from_geom(self._geom, data=mine.copy(), dtype=bool)
+        self.models = self._models  # (new evaluators: every cache is dropped)
+
+    def to_masked(self, name=None, nan_to_num=True):
+        """A copy with counts, background and exposure multiplied by the safe mask (datasets/map.py:1958-1986)."""
+        geoms = dict(self.geoms)
+        out = type(self).from_geoms(geoms["geom"], geom_exposure=geoms.get("geom_exposure"), name=name)
+        out.stack(self, nan_to_num=nan_to_num)
+        return out
+
     # -- what one looks at after a fit: all host arithmetic on the GPU's npred cubes ---------------------------------
     @property
     def excess(self):
@@ -566,6 +659,26 @@ def _parameters_with_prior(engine):
     return cached[1]
 
 
+def _average_irf(kind, mine, theirs, w_mine, w_theirs):
+    """Exposure-weighted average of two position-independent IRFs per true-energy bin (irf/core.py ``IRFMap.stack``)."""
+    from .irf import EDispKernel, EDispKernelMap, PSFMap
+
+    w1, w2 = np.asarray(w_mine, float), np.asarray(w_theirs, float)
+    total = w1 + w2
+    with np.errstate(invalid="ignore", divide="ignore"):
+        f1, f2 = np.nan_to_num(w1 / total), np.nan_to_num(w2 / total)
+    if kind == "psf":
+        if mine.rad_axis != theirs.rad_axis or mine.data.shape != theirs.data.shape:
+            raise ValueError("PSF maps to stack must share their axes")
+        data = mine.data * f1[:, np.newaxis] + theirs.data * f2[:, np.newaxis]
+        return PSFMap(mine.energy_axis_true, mine.rad_axis, data)
+    k1, k2 = mine.get_edisp_kernel(), theirs.get_edisp_kernel()
+    if k1.pdf_matrix.shape != k2.pdf_matrix.shape:
+        raise ValueError("edisp kernels to stack must share their axes")
+    data = k1.pdf_matrix * f1[:, np.newaxis] + k2.pdf_matrix * f2[:, np.newaxis]
+    return EDispKernelMap(EDispKernel([k1.axes["energy_true"], k1.axes["energy"]], data))
+
+
 class _MixedEngine:
     """Joint likelihood of Cash and WStat members (``Datasets.stat_sum``, datasets/core.py:264-277: the sum of every
     dataset's own statistic, in dataset order): the Cash members share one ``LikelihoodEngine`` (one fold launch for all
@@ -667,6 +780,15 @@ class Datasets(list):
     @property
     def parameters(self):
         return self.models.parameters.unique_parameters
+
+    def stack_reduce(self, name=None, nan_to_num=True):
+        """One dataset from all of them (datasets/core.py:530-569): the first one masked, the others stacked onto it."""
+        if not len(self):
+            raise ValueError("no dataset to stack")
+        stacked = self[0].to_masked(name=name, nan_to_num=nan_to_num)
+        for dataset in self[1:]:
+            stacked.stack(dataset, nan_to_num=nan_to_num)
+        return stacked
 
     def write(self, filename, filename_models=None, overwrite=False):
         """``Datasets.write`` (datasets/core.py:479-528): a YAML index ``{datasets: [{name, type, filename}]}``, one FITS

@@ -1,0 +1,83 @@
+"""``MapDataset.stack`` / ``to_masked`` / ``from_geoms`` / ``Datasets.stack_reduce`` (datasets/map.py:883-945, 1104-1210,
+1958-1986; datasets/core.py:530-569) against the numbers of the reference's data-free ``test_stack``
+(datasets/tests/test_map.py:1129-1235): host arithmetic, no GPU (datasets without a background model)."""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+from gammapy_b200 import Datasets, EDispKernelMap, Map, MapAxis, MapDataset, PSFMap, WcsGeom
+
+
+def _pair():
+    axis = MapAxis.from_energy_bounds("0.1 TeV", "10 TeV", nbin=3)
+    axis_etrue = MapAxis.from_energy_bounds("0.1 TeV", "10 TeV", nbin=5, name="energy_true")
+    geom = WcsGeom.create(skydir=(266.40498829, -28.93617776), binsz=0.05, width=(2, 2), frame="icrs", axes=[axis])
+    geom_etrue = geom.to_image().to_cube([axis_etrue])
+    edisp = EDispKernelMap.from_diagonal_response(energy_axis=axis, energy_axis_true=axis_etrue)
+    out = []
+    for k, (bkg, rows) in enumerate(((0.2, [(0, 5, 10)]), (0.1, [(0, 5, 10), (1, 10, 15)]))):
+        mask = np.ones(geom.data_shape, dtype=bool)
+        for e, lo, hi in rows:
+            mask[e][lo:hi] = False
+        out.append(MapDataset(
+            counts=Map.from_geom(geom, data=np.ones(geom.data_shape)),
+            background=Map.from_geom(geom, data=np.full(geom.data_shape, bkg)),
+            exposure=Map.from_geom(geom_etrue, data=np.full(geom_etrue.data_shape, 1e7), unit="m2 s"),
+            mask_safe=Map.from_geom(geom, data=mask.copy(), dtype=bool), mask_fit=Map.from_geom(geom, data=mask.copy(), dtype=bool),
+            edisp=edisp, name=f"dataset-{k + 1}"))
+    return out
+
+
+def test_stack_reference_numbers():
+    dataset1, dataset2 = _pair()
+    assert dataset1._geom.data_shape == (3, 40, 40)  # an oblique CAR field about the galactic centre, in ICRS
+    stacked = MapDataset.from_geoms(**dataset1.geoms)
+    stacked.stack(dataset1)
+    stacked.stack(dataset2)
+    assert_allclose(stacked.background.data.sum(), 1360, rtol=1e-5)
+    assert_allclose(stacked.counts.data.sum(), 9000, rtol=1e-5)
+    assert stacked.mask_safe.data.sum() == 4600 and stacked.mask_fit.data.sum() == 4600
+    assert_allclose(stacked.exposure.data.sum(), 1.6e11)
+    np.testing.assert_array_equal(stacked.edisp.get_edisp_kernel().pdf_matrix, dataset1.edisp.get_edisp_kernel().pdf_matrix)
+    # without safe masks everything enters, every time
+    plain = MapDataset(counts=dataset1.counts, background=dataset1.background)
+    total = MapDataset.from_geoms(**plain.geoms)
+    for _ in range(3):
+        total.stack(plain)
+    assert_allclose(total.background.data.sum(), 2880.0, rtol=1e-5)
+    assert_allclose(total.counts.data.sum(), 14400.0, rtol=1e-5)
+    # an all-false safe mask contributes nothing
+    empty = MapDataset(counts=dataset1.counts, background=dataset1.background,
+                       mask_safe=Map.from_geom(dataset1._geom, dtype=bool))
+    total.stack(empty)
+    assert_allclose(total.counts.data.sum(), 14400.0, rtol=1e-5)
+
+
+def test_to_masked_and_stack_reduce():
+    dataset1, dataset2 = _pair()
+    masked = dataset1.to_masked(name="masked")
+    safe = np.asarray(dataset1.mask_safe.data, bool)
+    assert masked.name == "masked" and masked.counts.data.sum() == safe.sum()
+    assert np.all(masked.counts.data[~safe] == 0) and np.all(masked.background.data[~safe] == 0)
+    assert_allclose(masked.background.data[safe], 0.2)
+    reduced = Datasets([dataset1, dataset2]).stack_reduce(name="stacked")
+    assert reduced.name == "stacked"
+    assert_allclose(reduced.counts.data.sum(), 9000)
+    assert_allclose(reduced.background.data.sum(), 1360)
+    assert reduced.mask_safe.data.sum() == 4600
+    assert dataset1.counts.data.sum() == 4800  # the inputs are untouched
+
+
+def test_irfs_are_averaged_with_exposure_weights():
+    dataset1, dataset2 = _pair()
+    e_true = dataset1.exposure.geom.axes["energy_true"]
+    dataset1.psf = PSFMap.from_gauss(e_true, sigma=0.1)
+    dataset2.psf = PSFMap.from_gauss(e_true, sigma=0.3)
+    dataset2.exposure = Map.from_geom(dataset2.exposure.geom, data=np.asarray(dataset2.exposure.data) * 3.0, unit="m2 s")
+    e_reco = dataset1._geom.axes["energy"]
+    dataset2.edisp = EDispKernelMap.from_gauss(energy_axis=e_reco, energy_axis_true=e_true, sigma=0.2, bias=0.0)
+    stacked = Datasets([dataset1, dataset2]).stack_reduce()
+    assert_allclose(stacked.psf.data, 0.25 * dataset1.psf.data + 0.75 * dataset2.psf.data, rtol=1e-12)
+    k1, k2 = dataset1.edisp.get_edisp_kernel().pdf_matrix, dataset2.edisp.get_edisp_kernel().pdf_matrix
+    assert_allclose(stacked.edisp.get_edisp_kernel().pdf_matrix, 0.25 * k1 + 0.75 * k2, rtol=1e-12)
+    assert_allclose(stacked.exposure.data.sum(), 1e7 * 5 * 1600 * 4)
