@@ -81,3 +81,14 @@ def test_irfs_are_averaged_with_exposure_weights():
     k1, k2 = dataset1.edisp.get_edisp_kernel().pdf_matrix, dataset2.edisp.get_edisp_kernel().pdf_matrix
     assert_allclose(stacked.edisp.get_edisp_kernel().pdf_matrix, 0.25 * k1 + 0.75 * k2, rtol=1e-12)
     assert_allclose(stacked.exposure.data.sum(), 1e7 * 5 * 1600 * 4)
+
+
+def test_to_masked_reference_number():
+    """datasets/tests/test_map.py:2413-2421 ``test_to_masked``: 200 unit counts, 30 of them outside the safe mask."""
+    axis = MapAxis.from_energy_bounds(1, 10, 2, unit="TeV")
+    geom = WcsGeom.create(npix=(10, 10), binsz=0.05, axes=[axis])
+    mask = np.ones(geom.data_shape, dtype=bool)
+    mask[0][5:8] = False
+    dataset = MapDataset(counts=Map.from_geom(geom, data=np.ones(geom.data_shape)),
+                         mask_safe=Map.from_geom(geom, data=mask, dtype=bool))
+    assert_allclose(dataset.to_masked().counts.data.sum(), 170)
