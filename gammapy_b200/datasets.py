@@ -333,8 +333,8 @@ class MapDataset:
         background enter where its ``mask_safe`` is true, the safe and fit masks are or-ed, position-independent PSF /
         edisp are averaged with exposure weights.  The background model of ``self`` is folded into the background map
         (as the reference does through ``npred_background()``), so assign the models of the stacked dataset afterwards."""
-        if isinstance(other, MapDatasetOnOff) or isinstance(self, MapDatasetOnOff):
-            raise NotImplementedError("stacking of MapDatasetOnOff is outside the accelerated path")
+        if isinstance(other, MapDatasetOnOff) != isinstance(self, MapDatasetOnOff):
+            raise TypeError("Incompatible types for stacking: a MapDataset and a MapDatasetOnOff")
         o_safe = None if other.mask_safe is None else np.asarray(other.mask_safe.data, bool)
         if o_safe is not None and not o_safe.any():
             return
@@ -566,6 +566,48 @@ class MapDatasetOnOff(MapDataset):
         self.acceptance_off = (acceptance_off if acceptance_off is not None
                                else Map.from_geom(geom, data=ones.copy(), dtype=float))
         self._onoff_dev = None
+
+    @classmethod
+    def from_geoms(cls, geom, geom_exposure=None, geom_psf=None, geom_edisp=None, name=None, **kwargs):
+        """Zero-filled ON/OFF dataset (datasets/map.py:2770-2830): also the OFF counts and both acceptances are zero."""
+        for key in ("counts_off", "acceptance", "acceptance_off"):
+            kwargs.setdefault(key, Map.from_geom(geom, unit="", dtype=float))
+        kwargs.setdefault("counts", Map.from_geom(geom, unit=""))
+        kwargs.setdefault("mask_safe", Map.from_geom(geom, unit="", dtype=bool))
+        if geom_exposure is not None:
+            kwargs.setdefault("exposure", Map.from_geom(geom_exposure, unit="m2 s"))
+        return cls(name=name, **kwargs)
+
+    def stack(self, other, nan_to_num=True):
+        """Stack another ON/OFF dataset in place (datasets/map.py:2936-3006): ON and OFF counts and the ON acceptance
+        add up under the other dataset's safe mask; the OFF acceptance is rescaled so that the stacked alpha is the
+        OFF-count weighted mean, alpha = (alpha_1 OFF_1 + alpha_2 OFF_2) / (OFF_1 + OFF_2), with the run-averaged alpha
+        where no OFF event was seen."""
+        if not isinstance(other, MapDatasetOnOff):
+            raise TypeError("Incompatible types for MapDatasetOnOff stacking")
+        for d in (self, other):
+            if d.counts_off is None or d.acceptance is None or d.acceptance_off is None:
+                raise ValueError("Cannot stack incomplete MapDatasetOnOff.")
+
+        def clean(a):
+            a = np.asarray(a, float)
+            return np.where(np.isfinite(a), a, 0.0) if nan_to_num else a
+
+        w = 1.0 if other.mask_safe is None else np.asarray(other.mask_safe.data, bool)
+        total_acceptance = clean(self.acceptance.data) + clean(other.acceptance.data) * w
+        total_off = clean(self.counts_off.data) + clean(other.counts_off.data) * w
+        total_alpha = clean(self.alpha.data * self.counts_off.data) + clean(other.alpha.data * other.counts_off.data) * w
+        with np.errstate(divide="ignore", invalid="ignore"):
+            acceptance_off = total_acceptance * total_off / total_alpha
+            average_alpha = total_alpha.sum() / total_off.sum()
+            is_zero = total_off == 0
+            acceptance_off[is_zero] = total_acceptance[is_zero] / average_alpha
+        geom = self._geom
+        self.acceptance = Map.from_geom(geom, data=total_acceptance, dtype=float)
+        self.acceptance_off = Map.from_geom(geom, data=acceptance_off, dtype=float)
+        self.counts_off = Map.from_geom(geom, data=total_off, dtype=float)
+        self._onoff_dev = None
+        MapDataset.stack(self, other, nan_to_num=nan_to_num)
 
     @property
     def alpha(self):

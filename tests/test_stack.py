@@ -92,3 +92,51 @@ def test_to_masked_reference_number():
     dataset = MapDataset(counts=Map.from_geom(geom, data=np.ones(geom.data_shape)),
                          mask_safe=Map.from_geom(geom, data=mask, dtype=bool))
     assert_allclose(dataset.to_masked().counts.data.sum(), 170)
+
+
+def _on_off(alpha, seed, mask_rows=()):
+    from gammapy_b200 import MapDatasetOnOff
+
+    axis = MapAxis.from_energy_bounds(1, 10, 2, unit="TeV")
+    geom = WcsGeom.create(npix=(10, 10), binsz=0.05, axes=[axis])
+    rng = np.random.RandomState(seed)
+    mask = np.ones(geom.data_shape, dtype=bool)
+    for e, lo, hi in mask_rows:
+        mask[e][lo:hi] = False
+    return MapDatasetOnOff(counts=Map.from_geom(geom, data=rng.poisson(3.0, geom.data_shape).astype(float)),
+                           counts_off=Map.from_geom(geom, data=rng.poisson(2.0, geom.data_shape).astype(float)),
+                           acceptance=Map.from_geom(geom, data=np.ones(geom.data_shape)),
+                           acceptance_off=Map.from_geom(geom, data=np.full(geom.data_shape, 1.0 / alpha)),
+                           mask_safe=Map.from_geom(geom, data=mask, dtype=bool), name=f"onoff-{seed}")
+
+
+def test_on_off_stacking():
+    """``MapDatasetOnOff.stack`` (datasets/map.py:2936-3006): counts and ON acceptance add up under the safe mask, the
+    stacked alpha is the OFF-count weighted mean of the alphas; ``to_masked`` as in the reference's ``test_to_masked``
+    (datasets/tests/test_map.py:2423-2435)."""
+    a, b = _on_off(0.2, 1), _on_off(0.5, 2, mask_rows=[(0, 5, 8)])
+    safe_b = np.asarray(b.mask_safe.data, bool)
+    stacked = a.to_masked(name="stacked")
+    assert type(stacked) is type(a) and stacked.counts.data.sum() == a.counts.data.sum()
+    stacked.stack(b)
+    assert_allclose(stacked.counts.data, a.counts.data + b.counts.data * safe_b)
+    assert_allclose(stacked.counts_off.data, a.counts_off.data + b.counts_off.data * safe_b)
+    assert_allclose(stacked.acceptance.data, 1.0 + safe_b)
+    off_a, off_b = a.counts_off.data, b.counts_off.data * safe_b
+    seen = (off_a + off_b) > 0
+    want = (0.2 * off_a + 0.5 * off_b)[seen] / (off_a + off_b)[seen] / (1.0 + safe_b)[seen]
+    assert_allclose((1.0 / stacked.acceptance_off.data)[seen], want, rtol=1e-12)   # 1 / a_off = alpha / a_on
+    mean_alpha = (0.2 * off_a + 0.5 * off_b).sum() / (off_a + off_b).sum()
+    assert_allclose(stacked.alpha.data[~seen], mean_alpha, rtol=1e-12)
+    assert stacked.mask_safe.data.all()
+    # stacking a dataset onto a copy of itself doubles the counts and keeps alpha
+    twice = a.to_masked()
+    twice.stack(a)
+    assert_allclose(twice.counts_off.data, 2 * a.counts_off.data)
+    assert_allclose(twice.alpha.data[a.counts_off.data > 0], 0.2, rtol=1e-12)
+    # the reference's to_masked number: 200 unit counts, 30 masked
+    ones = _on_off(0.1, 3, mask_rows=[(0, 5, 8)])
+    ones.counts = Map.from_geom(ones._geom, data=np.ones(ones._geom.data_shape))
+    assert_allclose(ones.to_masked().counts.data.sum(), 170)
+    with pytest.raises(TypeError):
+        a.stack(MapDataset(counts=a.counts))
