@@ -377,6 +377,18 @@ class MapDataset:
             self.mask_fit = Map.from_geom(self._geom, data=mine.copy(), dtype=bool)
         self.models = self._models  # (new evaluators: every cache is dropped)
 
+    def cutout(self, position, width, mode="trim", name=None):
+        """The dataset on a sub-region (datasets/map.py:2040-2094): every map cut with the integer rules of
+        ``WcsGeom.cutout`` (astropy ``Cutout2D``), the models kept.  Position-independent IRFs are shared; IRF maps on a
+        spatial grid stay whole -- they carry their own geometry, the evaluators look them up by sky position."""
+        kwargs = {"name": name, "stat_type": self.stat_type, "models": self.models, "psf": self.psf, "edisp": self.edisp}
+        for attr in ("counts", "exposure", "background", "mask_safe", "mask_fit"):
+            m = getattr(self, attr)
+            if m is not None:
+                cut = m.cutout(position, width, mode=mode)
+                kwargs[attr] = Map.from_geom(cut.geom, data=cut.data, unit=getattr(m, "unit", ""), dtype=cut.data.dtype)
+        return MapDataset(**kwargs)
+
     def to_masked(self, name=None, nan_to_num=True):
         """A copy with counts, background and exposure multiplied by the safe mask (datasets/map.py:1958-1986)."""
         geoms = dict(self.geoms)

@@ -140,3 +140,29 @@ def test_on_off_stacking():
     assert_allclose(ones.to_masked().counts.data.sum(), 170)
     with pytest.raises(TypeError):
         a.stack(MapDataset(counts=a.counts))
+
+
+def test_dataset_cutout():
+    """``MapDataset.cutout`` (datasets/map.py:2040-2094; the aligned-geometry property of the reference's
+    ``test_dataset_cutout_aligned``, datasets/tests/test_map.py:1744-1756): maps sliced with the Cutout2D rules, models
+    kept, and -- for a source whose evaluation region lies inside the cutout -- the same npred as the parent there."""
+    from gammapy_b200 import configs
+    from oracle import adapter
+
+    ds = configs.make_c1(width=(3.0, 3.0), mask_radius=1.2)   # Gaussian source near the centre + background model
+    rng = np.random.RandomState(0)
+    ds.counts = Map.from_geom(ds._geom, data=rng.poisson(1.0, ds._geom.data_shape).astype(float))
+    cut = ds.cutout(position=(0.1, -0.05), width=(2.4, 2.0), name="sub")
+    ys, xs = ds._geom.cutout_slices_for((0.1, -0.05), (2.4, 2.0))
+    assert cut.name == "sub" and cut._geom.data_shape[1:] == (ys.stop - ys.start, xs.stop - xs.start)
+    assert ds._geom.is_aligned(cut._geom) and ds.exposure.geom.is_aligned(cut.exposure.geom)
+    for attr in ("counts", "exposure", "background", "mask_safe", "mask_fit"):
+        np.testing.assert_array_equal(getattr(cut, attr).data, getattr(ds, attr).data[..., ys, xs])
+    # (the background model names the parent dataset: a cutout under another name keeps the sources only, as in the reference)
+    assert cut.mask_safe.data.dtype == bool and [m.name for m in cut.models] == [m.name for m in ds.models if m.name != "c1-bkg"]
+    assert [m.name for m in ds.cutout(position=(0.1, -0.05), width=(2.4, 2.0), name=ds.name).models] == [m.name for m in ds.models]
+    cut.models = [m.copy(name=m.name) if m.name != "c1-bkg" else type(m)(dataset_name="sub") for m in ds.models]
+    a = adapter.evaluator_for(ds, conv="exact64").npred_signal()[..., ys, xs]
+    b = adapter.evaluator_for(cut, conv="exact64").npred_signal()
+    inner = (slice(None), slice(22, -22), slice(22, -22))  # further from the cutout's edge than the PSF kernel reaches (21 px)
+    np.testing.assert_allclose(b[inner], a[inner], rtol=1e-9, atol=1e-12 * a.max())
