@@ -377,6 +377,21 @@ class MapDataset:
             self.mask_fit = Map.from_geom(self._geom, data=mine.copy(), dtype=bool)
         self.models = self._models  # (new evaluators: every cache is dropped)
 
+    def copy(self, name=None):
+        """Deep copy of the data under a new name, without models (datasets/core.py:96-114); the HBM mirror and the
+        engines are not copied -- the copy registers itself with the library when it is first evaluated."""
+        import copy as _copy
+
+        kwargs = {"name": name, "storage": self.storage, "meta": _copy.deepcopy(self.meta),
+                  "psf": _copy.deepcopy(self.psf), "edisp": _copy.deepcopy(self.edisp)}
+        if not isinstance(self, MapDatasetOnOff):
+            kwargs["stat_type"] = self.stat_type
+        for attr in ("counts", "exposure", "background", "mask_safe", "mask_fit", "counts_off", "acceptance", "acceptance_off"):
+            m = getattr(self, attr, None)
+            if m is not None:
+                kwargs[attr] = m.copy()
+        return type(self)(**kwargs)
+
     def cutout(self, position, width, mode="trim", name=None):
         """The dataset on a sub-region (datasets/map.py:2040-2094): every map cut with the integer rules of
         ``WcsGeom.cutout`` (astropy ``Cutout2D``), the models kept.  Position-independent IRFs are shared; IRF maps on a

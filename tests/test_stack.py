@@ -166,3 +166,24 @@ def test_dataset_cutout():
     b = adapter.evaluator_for(cut, conv="exact64").npred_signal()
     inner = (slice(None), slice(22, -22), slice(22, -22))  # further from the cutout's edge than the PSF kernel reaches (21 px)
     np.testing.assert_allclose(b[inner], a[inner], rtol=1e-9, atol=1e-12 * a.max())
+
+
+def test_dataset_copy():
+    """``Dataset.copy`` (datasets/core.py:96-114): the data copied, a new name, no models."""
+    dataset1, _ = _pair()
+    from gammapy_b200.modeling.models import FoVBackgroundModel
+
+    dataset1.models = [FoVBackgroundModel(dataset_name=dataset1.name)]
+    clone = dataset1.copy(name="clone")
+    assert clone.name == "clone" and clone.models is None and dataset1.models is not None
+    assert clone.counts is not dataset1.counts and clone.counts.data is not dataset1.counts.data
+    for attr in ("counts", "exposure", "background", "mask_safe", "mask_fit"):
+        np.testing.assert_array_equal(getattr(clone, attr).data, getattr(dataset1, attr).data)
+    clone.counts.data[0, 0, 0] = 99.0
+    assert dataset1.counts.data[0, 0, 0] == 1.0
+    assert dataset1.copy().name != dataset1.name
+    on_off = _on_off(0.2, 5)
+    twin = on_off.copy(name="twin")
+    assert type(twin) is type(on_off) and twin.stat_type == "wstat"
+    np.testing.assert_array_equal(twin.counts_off.data, on_off.counts_off.data)
+    np.testing.assert_array_equal(twin.alpha.data, on_off.alpha.data)
