@@ -63,3 +63,18 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.SourceState) == 32
     assert C.sizeof(_lib.DatasetDesc) == 64 + 8 * 8 + 8 + 8 * 3 + 8 + 8 + 8 + 8  # ... weight, compact (padded), mask_row_bytes
     assert C.sizeof(_lib.IrfMapsDesc) == 8 + 5 * 8 + 8 + 3 * 8  # nx, ny; binsz .. crval_lat; proj, n_rad; three pointers
+
+
+def test_every_python_module_imports_without_a_gpu():
+    """The host layer must import on a CPU-only machine (the driver's build check and the CPU test tier run there); the
+    GPU is only touched when something is evaluated."""
+    import importlib
+    import pkgutil
+
+    import gammapy_b200
+
+    names = [m.name for m in pkgutil.walk_packages(gammapy_b200.__path__, "gammapy_b200.")
+             if not m.name.rsplit(".", 1)[-1].startswith("lib")]
+    assert len(names) >= 18
+    for name in names:
+        importlib.import_module(name)
